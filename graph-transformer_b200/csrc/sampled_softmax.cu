@@ -1,0 +1,183 @@
+// K7: fused sampled-softmax loss (sampled_softmax.py:36-56): gather of the true and sampled class
+// rows, the [N, ns] logit GEMV block, exp / sum / log and the backward, without materialising the
+// [N, ns] logits in HBM.  One warp per node; the sampled rows W[ids] are staged once per CTA in
+// shared memory (chunked when ns*D does not fit) and reused by every node of the CTA.
+// Faithful to the reference: no max-subtraction, no log-Q correction, true class only in the
+// denominator if it was sampled.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kChunkFloats = 20 * 1024;  // shared-memory budget (floats) per staged chunk
+
+__device__ __forceinline__ int pitch_of(int D) { return D | 1; }
+
+__device__ __forceinline__ void stage_rows(const float* __restrict__ W, int64_t V, const int64_t* __restrict__ ids,
+                                           int s0, int sc, int D, float* ws) {
+    const int P = pitch_of(D);
+    for (int e = threadIdx.x; e < sc * D; e += blockDim.x) {
+        const int s = e / D, c = e - s * D;
+        const int64_t id = ids[s0 + s];
+        ws[s * P + c] = (id >= 0 && id < V) ? __ldg(W + id * D + c) : 0.0f;
+    }
+}
+
+__global__ void __launch_bounds__(256) ss_fwd_kernel(const float* __restrict__ x, const int64_t* __restrict__ labels,
+                                                     int64_t N, int D, const float* __restrict__ W, int64_t V,
+                                                     const int64_t* __restrict__ ids, int ns, int chunk,
+                                                     float* __restrict__ loss, float* __restrict__ denom_out,
+                                                     int64_t nodes_per_block) {
+    extern __shared__ float sm[];
+    const int P = pitch_of(D);
+    float* ws = sm;                                   // [chunk][P]
+    float* xs = sm + (size_t)chunk * P;               // [warps][D]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    float* xw = xs + (size_t)w * D;
+    const int64_t n0 = (int64_t)blockIdx.x * nodes_per_block;
+    const int64_t n1 = (n0 + nodes_per_block < N) ? n0 + nodes_per_block : N;
+    for (int s0 = 0; s0 < ns; s0 += chunk) {
+        const int sc = (ns - s0 < chunk) ? ns - s0 : chunk;
+        __syncthreads();
+        stage_rows(W, V, ids, s0, sc, D, ws);
+        __syncthreads();
+        for (int64_t i = n0 + w; i < n1; i += warps) {
+            __syncwarp();
+            for (int c = lane; c < D; c += 32) xw[c] = x[i * D + c];
+            __syncwarp();
+            float part = 0.0f;
+            for (int s = lane; s < sc; s += 32) {
+                float dot = 0.0f;
+                const float* wr = ws + s * P;
+                for (int c = 0; c < D; ++c) dot = fmaf(xw[c], wr[c], dot);
+                part += expf(dot);
+            }
+            part = warp_sum(part);
+            if (lane == 0) denom_out[i] = (s0 == 0) ? part : denom_out[i] + part;
+        }
+    }
+    __syncthreads();
+    // true logits and the loss
+    for (int64_t i = n0 + w; i < n1; i += warps) {
+        const int64_t y = labels[i];
+        float dot = 0.0f;
+        for (int c = lane; c < D; c += 32) dot = fmaf(x[i * D + c], __ldg(W + y * D + c), dot);
+        dot = warp_sum(dot);
+        if (lane == 0) loss[i] = -logf(expf(dot) / denom_out[i]);
+    }
+}
+
+__global__ void __launch_bounds__(256) ss_bwd_kernel(const float* __restrict__ dloss, const float* __restrict__ x,
+                                                     const int64_t* __restrict__ labels, int64_t N, int D,
+                                                     const float* __restrict__ W, int64_t V,
+                                                     const int64_t* __restrict__ ids, int ns, int chunk,
+                                                     const float* __restrict__ denom, float* __restrict__ dx,
+                                                     float* __restrict__ dW, int64_t nodes_per_block) {
+    extern __shared__ float sm[];
+    const int P = pitch_of(D);
+    float* ws = sm;                                   // [chunk][P]   sampled rows
+    float* dws = ws + (size_t)chunk * P;              // [chunk][P]   their gradient, accumulated per CTA
+    float* xs = dws + (size_t)chunk * P;              // [warps][D]
+    float* es = xs + (size_t)(blockDim.x >> 5) * D;   // [warps][chunk] per-sample coefficients
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    float* xw = xs + (size_t)w * D;
+    float* ew = es + (size_t)w * chunk;
+    const int64_t n0 = (int64_t)blockIdx.x * nodes_per_block;
+    const int64_t n1 = (n0 + nodes_per_block < N) ? n0 + nodes_per_block : N;
+
+    // true-class term: dx = -dloss * W[y];  dW[y] += -dloss * x
+    for (int64_t i = n0 + w; i < n1; i += warps) {
+        const int64_t y = labels[i];
+        const float g = -dloss[i];
+        for (int c = lane; c < D; c += 32) {
+            dx[i * D + c] = g * __ldg(W + y * D + c);
+            atomicAdd(dW + y * D + c, g * x[i * D + c]);
+        }
+    }
+    for (int s0 = 0; s0 < ns; s0 += chunk) {
+        const int sc = (ns - s0 < chunk) ? ns - s0 : chunk;
+        __syncthreads();
+        stage_rows(W, V, ids, s0, sc, D, ws);
+        for (int e = threadIdx.x; e < sc * P; e += blockDim.x) dws[e] = 0.0f;
+        __syncthreads();
+        for (int64_t i = n0 + w; i < n1; i += warps) {
+            __syncwarp();
+            for (int c = lane; c < D; c += 32) xw[c] = x[i * D + c];
+            __syncwarp();
+            const float coef = dloss[i] / denom[i];
+            for (int s = lane; s < sc; s += 32) {
+                float dot = 0.0f;
+                const float* wr = ws + s * P;
+                for (int c = 0; c < D; ++c) dot = fmaf(xw[c], wr[c], dot);
+                ew[s] = coef * expf(dot);
+            }
+            __syncwarp();
+            // dx[c] += sum_s e_s W_s[c];  dWs[s][c] += e_s x[c]
+            for (int c0 = 0; c0 < D; c0 += 32) {
+                const int c = c0 + lane;
+                if (c < D) {
+                    float acc = 0.0f;
+                    const float xc = xw[c];
+                    for (int s = 0; s < sc; ++s) {
+                        const float e = ew[s];
+                        acc = fmaf(e, ws[s * P + c], acc);
+                        atomicAdd(dws + s * P + c, e * xc);
+                    }
+                    dx[i * D + c] += acc;
+                }
+            }
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < sc * D; e += blockDim.x) {
+            const int s = e / D, c = e - s * D;
+            const int64_t id = ids[s0 + s];
+            if (id >= 0 && id < V) atomicAdd(dW + id * D + c, dws[s * P + c]);
+        }
+    }
+}
+
+int pick_chunk(int ns, int D, int copies) {
+    const int P = D | 1;
+    int chunk = kChunkFloats / (P * copies);
+    if (chunk > ns) chunk = ns;
+    if (chunk < 1) chunk = 1;
+    return chunk;
+}
+
+}  // namespace
+
+extern "C" int u2gnn_sampled_softmax_fwd(const float* x, const int64_t* labels, int64_t N, int D, const float* W,
+                                         int64_t V, const int64_t* ids, int ns, float* loss, float* denom,
+                                         u2gnn_stream_t stream) {
+    if (!x || !labels || !W || !ids || !loss || !denom || N < 0 || D <= 0 || V <= 0 || ns <= 0) return U2GNN_EINVAL;
+    if (D > 1024) return U2GNN_EUNSUPPORTED;
+    if (N == 0) return U2GNN_OK;
+    const int chunk = pick_chunk(ns, D, 1);
+    const int threads = 256;
+    const size_t smem = ((size_t)chunk * (D | 1) + (size_t)(threads / 32) * D) * sizeof(float);
+    const int grid = grid_for(N, 64, 2);
+    const int64_t npb = ceil_div64(N, grid);
+    cudaFuncSetAttribute(ss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ss_fwd_kernel<<<(unsigned)ceil_div64(N, npb), threads, smem, as_stream(stream)>>>(x, labels, N, D, W, V, ids, ns, chunk,
+                                                                                    loss, denom, npb);
+    U2GNN_CHECK_LAUNCH();
+}
+
+extern "C" int u2gnn_sampled_softmax_bwd(const float* dloss, const float* x, const int64_t* labels, int64_t N, int D,
+                                         const float* W, int64_t V, const int64_t* ids, int ns, const float* denom,
+                                         float* dx, float* dW, u2gnn_stream_t stream) {
+    if (!dloss || !x || !labels || !W || !ids || !denom || !dx || !dW || N < 0 || D <= 0 || V <= 0 || ns <= 0)
+        return U2GNN_EINVAL;
+    if (D > 1024) return U2GNN_EUNSUPPORTED;
+    if (N == 0) return U2GNN_OK;
+    const int threads = 256, warps = threads / 32;
+    int chunk = pick_chunk(ns, D, 2);
+    // es needs warps*chunk floats on top of the two staged copies
+    while (chunk > 1 && ((size_t)2 * chunk * (D | 1) + (size_t)warps * (D + chunk)) > (size_t)(48 * 1024)) chunk /= 2;
+    const size_t smem = ((size_t)2 * chunk * (D | 1) + (size_t)warps * (D + chunk)) * sizeof(float);
+    const int grid = grid_for(N, 64, 1);
+    const int64_t npb = ceil_div64(N, grid);
+    cudaFuncSetAttribute(ss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ss_bwd_kernel<<<(unsigned)ceil_div64(N, npb), threads, smem, as_stream(stream)>>>(dloss, x, labels, N, D, W, V, ids, ns,
+                                                                                    chunk, denom, dx, dW, npb);
+    U2GNN_CHECK_LAUNCH();
+}

@@ -1,0 +1,79 @@
+"""Loader for the C-ABI CUDA library (include/u2gnn_b200.h).
+
+The product path has no CPU fallback: if ``libu2gnn_b200.so`` is missing the import fails loudly,
+and every call raises ``RuntimeError`` with ``u2gnn_strerror`` on a non-zero status.  Signatures
+are parsed from the header so the binding cannot drift from the declared boundary.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libu2gnn_b200.so")
+HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "include", "u2gnn_b200.h"))
+
+_SCALARS = {
+    "int": ctypes.c_int, "float": ctypes.c_float, "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64,
+    "uint32_t": ctypes.c_uint32, "int32_t": ctypes.c_int32, "size_t": ctypes.c_size_t,
+    "u2gnn_stream_t": ctypes.c_void_p,
+}
+_RET = {"int": ctypes.c_int, "size_t": ctypes.c_size_t, "uint32_t": ctypes.c_uint32, "const char*": ctypes.c_char_p}
+
+
+def parse_header(path=HEADER_PATH):
+    """-> {name: (restype, [(ctype, argname), ...])} for every function the header declares."""
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    out = {}
+    for m in re.finditer(r"(const char\*|int|size_t|uint32_t)\s+(u2gnn_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        ret, name, args = m.group(1), m.group(2), " ".join(m.group(3).split())
+        params = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    params.append((ctypes.c_void_p, a.split("*")[-1].strip()))
+                else:
+                    ty, nm = a.rsplit(" ", 1)
+                    params.append((_SCALARS[ty.replace("const ", "").strip()], nm))
+        out[name] = (_RET[ret], params)
+    return out
+
+
+SIGNATURES = parse_header()
+
+
+class _Lib:
+    def __init__(self):
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "u2gnn_b200: %s is missing - build it with `python graph-transformer_b200/build.py` "
+                "(there is no CPU or PyTorch fallback for this path)" % LIB_PATH)
+        self.cdll = ctypes.CDLL(LIB_PATH)
+        for name, (ret, params) in SIGNATURES.items():
+            fn = getattr(self.cdll, name)     # AttributeError if the library lacks a declared symbol
+            fn.restype = ret
+            fn.argtypes = [t for t, _ in params]
+        self._status = {n for n, (r, _) in SIGNATURES.items() if r is ctypes.c_int}
+
+    def strerror(self, code):
+        return self.cdll.u2gnn_strerror(code).decode()
+
+    def call(self, name, *args):
+        rc = getattr(self.cdll, name)(*args)
+        if name in self._status and rc != 0 and name != "u2gnn_device_check":
+            raise RuntimeError("%s failed: %s (%d)" % (name, self.strerror(rc), rc))
+        return rc
+
+
+LIB = _Lib()
+
+
+def require_device():
+    """Raises unless the current CUDA device can run the sm_100a kernels."""
+    rc = LIB.cdll.u2gnn_device_check()
+    if rc != 0:
+        raise RuntimeError("u2gnn_b200 needs an sm_100 (B200) device: " + LIB.strerror(rc))

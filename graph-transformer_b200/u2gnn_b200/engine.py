@@ -1,0 +1,372 @@
+"""Host-side sequencing of the U2GNN train step over the C-ABI kernels.
+
+Mirrors the dataflow of the reference forward (pytorch_U2GNN_Sup.py:30-46) and of
+nn.TransformerEncoderLayer (torch/nn/modules/transformer.py:944-982); every arithmetic step is a
+call into libu2gnn_b200.so.  PyTorch is used for device memory and streams only.
+
+Two attention layouts:
+  attn_axis="nodes"      reference as written (sequence = the N nodes of the batch, column 0 only)
+  attn_axis="neighbors"  intended (sequence = [node, k sampled neighbours]); the last timestep of a
+                         U2GNN layer only produces sequence position 0 (dead-row elimination)
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import torch
+
+from ._lib import LIB, require_device
+
+PARAM_NAMES = (
+    "self_attn.in_proj_weight", "self_attn.in_proj_bias", "self_attn.out_proj.weight", "self_attn.out_proj.bias",
+    "linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias",
+    "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias",
+)
+STREAM_POOLED = 1
+STREAM_CONCAT = 9
+
+
+def stream_id(layer, timestep, site, num_timesteps):
+    """Dropout stream of encoder site (0 probs, 1 post-attention, 2 post-ReLU, 3 post-FFN)."""
+    return ((layer * num_timesteps + timestep) * 4 + site) + 16
+
+
+def dropout_threshold(p):
+    thr = int(round(float(p) * 256.0))
+    if not 0 <= thr <= 255:
+        raise ValueError("dropout probability out of range: %r" % (p,))
+    return thr
+
+
+@dataclass
+class DropoutCfg:
+    """enabled=False is model.eval().  p is quantised to thr/256 (0.5 -> 128 exactly)."""
+    enabled: bool = False
+    seed: int = 0
+    p_enc: float = 0.5
+    p_out: float = 0.5
+
+    def thr_enc(self):
+        return dropout_threshold(self.p_enc) if self.enabled else 0
+
+    def thr_out(self):
+        return dropout_threshold(self.p_out) if self.enabled else 0
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check(t, dtype, name):
+    if t.device.type != "cuda":
+        raise RuntimeError("%s must be a CUDA tensor (no CPU fallback in u2gnn_b200)" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return t
+
+
+# --------------------------------------------------------------------------------------
+# thin wrappers (tensor -> pointer)
+# --------------------------------------------------------------------------------------
+def gather_rows(table, idx, idx_stride=1, n_idx=None):
+    _check(table, torch.float32, "table"); _check(idx, torch.int64, "idx")
+    n = idx.numel() // idx_stride if n_idx is None else n_idx
+    out = torch.empty((n, table.shape[1]), dtype=torch.float32, device=table.device)
+    LIB.call("u2gnn_gather_rows", _ptr(table), table.shape[0], table.shape[1], _ptr(idx), n, idx_stride, _ptr(out), _stream())
+    return out
+
+
+def scatter_add_rows(grad, idx, n_dst, idx_stride=1, out=None):
+    d = grad.shape[-1]
+    n = grad.numel() // d
+    if out is None:
+        out = torch.zeros((n_dst, d), dtype=torch.float32, device=grad.device)
+    LIB.call("u2gnn_scatter_add_rows", _ptr(grad), n, d, _ptr(idx), idx_stride, _ptr(out), n_dst, _stream())
+    return out
+
+
+class IndexTranspose:
+    """CSR transpose of an index list, built once per batch, for the deterministic scatter-add."""
+
+    def __init__(self, idx, n_dst, idx_stride=1):
+        n = idx.numel() // idx_stride
+        dev = idx.device
+        self.n_dst = n_dst
+        self.rowptr = torch.empty(n_dst + 1, dtype=torch.int64, device=dev)
+        self.pos = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        wb = LIB.call("u2gnn_index_transpose_workspace_bytes", n, n_dst)
+        ws = torch.empty(wb, dtype=torch.uint8, device=dev)
+        LIB.call("u2gnn_index_transpose_build", _ptr(idx), n, idx_stride, n_dst, _ptr(self.rowptr), _ptr(self.pos),
+                 _ptr(ws), wb, _stream())
+
+    def scatter_add(self, grad, out=None, accumulate=False):
+        d = grad.shape[-1]
+        if out is None:
+            out = torch.empty((self.n_dst, d), dtype=torch.float32, device=grad.device)
+            accumulate = False
+        LIB.call("u2gnn_scatter_add_rows_det", _ptr(grad), d, _ptr(self.rowptr), _ptr(self.pos), _ptr(out), self.n_dst,
+                 int(accumulate), _stream())
+        return out
+
+
+def rowptr_from_graph_pool(graph_pool):
+    """CSR row pointer of the reference's COO pooling operator (train_pytorch_U2GNN_Sup.py:73-89)."""
+    if graph_pool.layout != torch.sparse_coo:
+        raise TypeError("graph_pool must be the reference's sparse COO pooling operator")
+    idx = graph_pool._indices()
+    G, N = graph_pool.shape
+    if idx.shape[1] != N:
+        raise ValueError("graph_pool must have exactly one entry per node")
+    rows = idx[0].contiguous()
+    rowptr = torch.empty(G + 1, dtype=torch.int64, device=rows.device)
+    LIB.call("u2gnn_rowptr_from_coo", _ptr(rows), N, G, _ptr(rowptr), _stream())
+    return rowptr
+
+
+def segment_sum(x, rowptr):
+    G = rowptr.numel() - 1
+    out = torch.empty((G, x.shape[1]), dtype=torch.float32, device=x.device)
+    LIB.call("u2gnn_segment_sum", _ptr(x), x.shape[0], x.shape[1], _ptr(rowptr), G, _ptr(out), _stream())
+    return out
+
+
+def segment_sum_bwd(gout, rowptr, n, out=None, accumulate=False):
+    G, d = gout.shape
+    if out is None:
+        out = torch.empty((n, d), dtype=torch.float32, device=gout.device)
+        accumulate = False
+    LIB.call("u2gnn_segment_sum_bwd", _ptr(gout), G, d, _ptr(rowptr), _ptr(out), n, int(accumulate), _stream())
+    return out
+
+
+def sgemm(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, alpha=1.0, beta=0.0, bias=None, relu=False, drop=None,
+          aux=None, ldaux=0, aux_scale=1.0, splitk=1, a_off=0, b_off=0, c_off=0):
+    """C = epi(alpha*op(A)op(B)+bias) (+beta*C).  *_off are element offsets into the tensors."""
+    epi = 0
+    seed = stream = thr = row0 = 0
+    if bias is not None:
+        epi |= 1
+    if relu:
+        epi |= 2
+    if drop is not None and drop[2] > 0:
+        epi |= 4
+        seed, stream, thr = drop[0], drop[1], drop[2]
+        row0 = drop[3] if len(drop) > 3 else 0
+    if aux is not None:
+        epi |= 8
+    if splitk > 1 or splitk == -1:
+        epi |= 16
+        splitk = max(splitk, 1)
+    LIB.call("u2gnn_sgemm", int(ta), int(tb), M, N, K, alpha, _ptr(A) + 4 * a_off, lda, _ptr(B) + 4 * b_off, ldb, beta,
+             _ptr(C) + 4 * c_off, ldc, _ptr(bias), epi, seed, stream, thr, row0, _ptr(aux), ldaux, aux_scale, splitk, _stream())
+    return C
+
+
+def _splitk_for(rows):
+    return int(max(1, min(296, rows // 2048)))
+
+
+def wgrad(dout, M_rows, n_out, inp, n_in, dW, db=None):
+    """dW[n_out, n_in] += dout[M, n_out]^T @ inp[M, n_in];  db[n_out] += colsum(dout)."""
+    if M_rows == 0:
+        return
+    sk = _splitk_for(M_rows)
+    sgemm(1, 0, n_out, n_in, M_rows, dout, n_out, inp, n_in, dW, n_in, splitk=-1 if sk == 1 else sk)
+    if db is not None:
+        LIB.call("u2gnn_colsum", _ptr(dout), M_rows, n_out, n_out, _ptr(db), 1, _stream())
+
+
+def add_dropout_ln_fwd(res, a, M, d, drop, gamma, beta):
+    dev = a.device
+    z = torch.empty((M, d), dtype=torch.float32, device=dev)
+    y = torch.empty((M, d), dtype=torch.float32, device=dev)
+    stats = torch.empty((M, 2), dtype=torch.float32, device=dev)
+    LIB.call("u2gnn_add_dropout_ln_fwd", _ptr(res), _ptr(a), M, d, drop[0], drop[1], drop[2], _ptr(gamma), _ptr(beta),
+             _ptr(z), _ptr(y), _ptr(stats), _stream())
+    return z, y, stats
+
+
+def add_dropout_ln_bwd(dy, z, stats, M, d, gamma, drop, dgamma, dbeta, want_da=True):
+    dz = torch.empty((M, d), dtype=torch.float32, device=dy.device)
+    da = torch.empty((M, d), dtype=torch.float32, device=dy.device) if (want_da and drop[2] > 0) else None
+    LIB.call("u2gnn_add_dropout_ln_bwd", _ptr(dy), _ptr(z), _ptr(stats), M, d, _ptr(gamma), drop[0], drop[1], drop[2],
+             _ptr(dz), _ptr(da), _ptr(dgamma), _ptr(dbeta), _stream())
+    return dz, (da if da is not None else dz)
+
+
+def copy_rows(src, ld_src, dst, ld_dst, rows, d, accumulate=False, src_off=0, dst_off=0):
+    LIB.call("u2gnn_copy_rows", _ptr(src) + 4 * src_off, ld_src, _ptr(dst) + 4 * dst_off, ld_dst, rows, d, int(accumulate), _stream())
+
+
+# --------------------------------------------------------------------------------------
+# one encoder layer (fp32 building-block path)
+# --------------------------------------------------------------------------------------
+@dataclass
+class LayerSaved:
+    x: torch.Tensor = None
+    xq: torch.Tensor = None
+    qkv: torch.Tensor = None
+    probs: torch.Tensor = None
+    pd: torch.Tensor = None
+    ctx: torch.Tensor = None
+    z1: torch.Tensor = None
+    st1: torch.Tensor = None
+    y1: torch.Tensor = None
+    hd: torch.Tensor = None
+    z2: torch.Tensor = None
+    st2: torch.Tensor = None
+    B: int = 0
+    S: int = 0
+    Sq: int = 0
+
+
+def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq):
+    """x[B*S, d] -> y[B*Sq, d].  p: dict name->tensor.  drop_ids: 4 stream ids.  long_seq selects the
+    attn_axis="nodes" formulation (B == 1, scores materialised as [S, S])."""
+    dev = x.device
+    M, Mq = B * S, B * Sq
+    f32 = dict(dtype=torch.float32, device=dev)
+    sv = LayerSaved(x=x, B=B, S=S, Sq=Sq)
+    qkv = torch.empty((M, 3 * d), **f32)
+    sgemm(0, 1, M, 3 * d, d, x, d, p["self_attn.in_proj_weight"], d, qkv, 3 * d, bias=p["self_attn.in_proj_bias"])
+    ctx = torch.empty((Mq, d), **f32)
+    if long_seq:
+        assert B == 1 and Sq == S
+        scores = torch.empty((S, S), **f32)
+        sgemm(0, 1, S, S, d, qkv, 3 * d, qkv, 3 * d, scores, S, alpha=math.sqrt(1.0 / d), b_off=d)
+        pd = torch.empty((S, S), **f32) if thr > 0 else scores
+        LIB.call("u2gnn_softmax_rows_fwd", _ptr(scores), S, S, _ptr(pd), seed, drop_ids[0], thr, _stream())
+        sgemm(0, 0, S, d, S, pd, S, qkv, 3 * d, ctx, d, b_off=2 * d)
+        sv.probs, sv.pd = scores, pd
+    else:
+        LIB.call("u2gnn_seqattn_fwd", _ptr(qkv), B, S, Sq, d, seed, drop_ids[0], thr, _ptr(ctx), _stream())
+    a = torch.empty((Mq, d), **f32)
+    sgemm(0, 1, Mq, d, d, ctx, d, p["self_attn.out_proj.weight"], d, a, d, bias=p["self_attn.out_proj.bias"])
+    if Sq == S:
+        xq = x
+    else:
+        xq = torch.empty((Mq, d), **f32)
+        copy_rows(x, S * d, xq, d, B, d)
+    z1, y1, st1 = add_dropout_ln_fwd(xq, a, Mq, d, (seed, drop_ids[1], thr), p["norm1.weight"], p["norm1.bias"])
+    hd = torch.empty((Mq, ff), **f32)
+    sgemm(0, 1, Mq, ff, d, y1, d, p["linear1.weight"], d, hd, ff, bias=p["linear1.bias"], relu=True,
+          drop=(seed, drop_ids[2], thr))
+    f = torch.empty((Mq, d), **f32)
+    sgemm(0, 1, Mq, d, ff, hd, ff, p["linear2.weight"], ff, f, d, bias=p["linear2.bias"])
+    z2, y2, st2 = add_dropout_ln_fwd(y1, f, Mq, d, (seed, drop_ids[3], thr), p["norm2.weight"], p["norm2.bias"])
+    sv.xq, sv.qkv, sv.ctx, sv.z1, sv.st1, sv.y1, sv.hd, sv.z2, sv.st2 = xq, qkv, ctx, z1, st1, y1, hd, z2, st2
+    return y2, sv
+
+
+def encoder_layer_bwd(dy2, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_dx=True):
+    """Backward of encoder_layer_fwd.  g: dict name->gradient tensor (accumulated into).
+    Returns dx[B*S, d] or None."""
+    dev = dy2.device
+    B, S, Sq = sv.B, sv.S, sv.Sq
+    M, Mq = B * S, B * Sq
+    f32 = dict(dtype=torch.float32, device=dev)
+    drop_scale = 256.0 / (256.0 - thr) if thr else 1.0
+    # LayerNorm2 + FFN
+    dz2, df = add_dropout_ln_bwd(dy2, sv.z2, sv.st2, Mq, d, p["norm2.weight"], (seed, drop_ids[3], thr),
+                                 g["norm2.weight"], g["norm2.bias"])
+    wgrad(df, Mq, d, sv.hd, ff, g["linear2.weight"], g["linear2.bias"])
+    dhpre = torch.empty((Mq, ff), **f32)
+    sgemm(0, 0, Mq, ff, d, df, d, p["linear2.weight"], ff, dhpre, ff, aux=sv.hd, ldaux=ff, aux_scale=drop_scale)
+    wgrad(dhpre, Mq, ff, sv.y1, d, g["linear1.weight"], g["linear1.bias"])
+    dy1 = dz2  # dy1 = dz2 + dhpre @ W1 (in place)
+    sgemm(0, 0, Mq, d, ff, dhpre, ff, p["linear1.weight"], d, dy1, d, beta=1.0)
+    del dhpre
+    # LayerNorm1 + attention
+    dz1, da = add_dropout_ln_bwd(dy1, sv.z1, sv.st1, Mq, d, p["norm1.weight"], (seed, drop_ids[1], thr),
+                                 g["norm1.weight"], g["norm1.bias"])
+    wgrad(da, Mq, d, sv.ctx, d, g["self_attn.out_proj.weight"], g["self_attn.out_proj.bias"])
+    dctx = torch.empty((Mq, d), **f32)
+    sgemm(0, 0, Mq, d, d, da, d, p["self_attn.out_proj.weight"], d, dctx, d)
+    dqkv = torch.empty((M, 3 * d), **f32)
+    if long_seq:
+        scale = math.sqrt(1.0 / d)
+        dpd = torch.empty((S, S), **f32)
+        sgemm(0, 1, S, S, d, dctx, d, sv.qkv, 3 * d, dpd, S, b_off=2 * d)                 # dP~ = dctx @ v^T
+        sgemm(1, 0, S, d, S, sv.pd, S, dctx, d, dqkv, 3 * d, c_off=2 * d)                 # dv = P~^T @ dctx
+        LIB.call("u2gnn_softmax_rows_bwd", _ptr(sv.probs), _ptr(dpd), S, S, seed, drop_ids[0], thr, _stream())
+        sgemm(0, 0, S, d, S, dpd, S, sv.qkv, 3 * d, dqkv, 3 * d, alpha=scale, b_off=d)     # dq = ds @ k * scale
+        sgemm(1, 0, S, d, S, dpd, S, sv.qkv, 3 * d, dqkv, 3 * d, alpha=scale, c_off=d)     # dk = ds^T @ q * scale
+    else:
+        LIB.call("u2gnn_seqattn_bwd", _ptr(sv.qkv), _ptr(dctx), B, S, Sq, d, seed, drop_ids[0], thr, _ptr(dqkv), _stream())
+    wgrad(dqkv, M, 3 * d, sv.x, d, g["self_attn.in_proj_weight"], g["self_attn.in_proj_bias"])
+    if not need_dx:
+        return None
+    dx = torch.empty((M, d), **f32)
+    sgemm(0, 0, M, d, 3 * d, dqkv, 3 * d, p["self_attn.in_proj_weight"], d, dx, d)
+    if Sq == S:
+        LIB.call("u2gnn_axpy", 1.0, _ptr(dz1), _ptr(dx), M * d, _stream())
+    else:
+        copy_rows(dz1, d, dx, S * d, B, d, accumulate=True)
+    return dx
+
+
+# --------------------------------------------------------------------------------------
+# one U2GNN layer = gather -> T encoder layers -> position 0
+# --------------------------------------------------------------------------------------
+@dataclass
+class StackSaved:
+    layers: list = field(default_factory=list)
+    n_src: int = 0
+    N: int = 0
+    S: int = 0
+
+
+def u2gnn_layer_fwd(src, input_x, params, l, T, attn_axis, drop: DropoutCfg):
+    """src[n_src, d], input_x[N, S] int64 -> out[N, d].  params: list (per timestep) of dicts."""
+    require_device()
+    _check(src, torch.float32, "src"); _check(input_x, torch.int64, "input_x")
+    N, S = input_x.shape
+    d = src.shape[1]
+    ff = params[0]["linear1.weight"].shape[0]
+    thr = drop.thr_enc()
+    saved = StackSaved(n_src=src.shape[0], N=N, S=S)
+    if attn_axis == "neighbors":
+        if S > 32:
+            raise ValueError("attn_axis='neighbors' supports num_neighbors <= 31")
+        x = gather_rows(src, input_x)                       # [N*S, d]
+        B, Sseq = N, S
+    elif attn_axis == "nodes":
+        x = gather_rows(src, input_x, idx_stride=S, n_idx=N)  # column 0 only
+        B, Sseq = 1, N
+    else:
+        raise ValueError("attn_axis must be 'nodes' or 'neighbors'")
+    for t in range(T):
+        last = attn_axis == "neighbors" and t == T - 1
+        Sq = 1 if last else Sseq
+        ids = [stream_id(l, t, s, T) for s in range(4)]
+        x, sv = encoder_layer_fwd(x, B, Sseq, Sq, params[t], d, ff, ids, drop.seed, thr, attn_axis == "nodes")
+        saved.layers.append(sv)
+    return x, saved  # [N, d] in both layouts
+
+
+def u2gnn_layer_bwd(dout, saved: StackSaved, input_x, params, grads, l, T, attn_axis, drop: DropoutCfg,
+                    need_dsrc=True, transpose: IndexTranspose | None = None):
+    d = dout.shape[1]
+    ff = params[0]["linear1.weight"].shape[0]
+    thr = drop.thr_enc()
+    dx = dout
+    for t in reversed(range(T)):
+        ids = [stream_id(l, t, s, T) for s in range(4)]
+        need_dx = need_dsrc or t > 0
+        dx = encoder_layer_bwd(dx, saved.layers[t], params[t], grads[t], d, ff, ids, drop.seed, thr,
+                               attn_axis == "nodes", need_dx=need_dx)
+        saved.layers[t] = None
+    if not need_dsrc:
+        return None
+    if attn_axis == "neighbors":
+        if transpose is not None:
+            return transpose.scatter_add(dx)
+        return scatter_add_rows(dx, input_x, saved.n_src)
+    return scatter_add_rows(dx, input_x, saved.n_src, idx_stride=saved.S)

@@ -1,0 +1,212 @@
+"""Fused train step: forward + loss + backward + global-norm clip + Adam without autograd.
+
+Replaces the body of `train()` in train_pytorch_U2GNN_Sup.py:149-164 / train_pytorch_U2GNN_UnSup.py:149-162
+(zero_grad, model(...), loss, backward, clip_grad_norm_(0.5), Adam.step, loss.item()) by direct calls
+into the C-ABI library over ONE flat parameter arena; data-parallel ranks all-reduce the flat
+gradient (+ the squared norm) with NCCL before the fused clip+Adam kernel.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import engine as E
+from ._lib import LIB
+from .model import TransformerU2GNN, TransformerU2GNNUnSup, _layer_param_dicts
+
+
+class FlatArena:
+    """Moves every parameter of `model` into one contiguous fp32 buffer (parameters become views, so
+    state_dict / optimizers keep working) with matching flat grad / Adam-moment buffers."""
+
+    def __init__(self, model):
+        params = [(n, p) for n, p in model.named_parameters()]
+        dev = params[0][1].device
+        offs, total = {}, 0
+        for n, p in params:
+            offs[n] = total
+            total += (p.numel() + 3) // 4 * 4                 # 16-byte aligned slots
+        self.total = total
+        self.p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.views, self.gviews = {}, {}
+        for n, p in params:
+            o = offs[n]
+            view = self.p[o:o + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            self.views[n] = p
+            self.gviews[n] = self.g[o:o + p.numel()].view_as(p)
+        self.model = model
+        self.step_count = 0
+
+    def zero_grad(self):
+        self.g.zero_()
+
+    def grads_from_autograd(self):
+        self.g.zero_()
+        for n, p in self.views.items():
+            if p.grad is not None:
+                self.gviews[n].copy_(p.grad)
+
+    def grads_to_autograd(self):
+        for n, p in self.views.items():
+            p.grad = self.gviews[n]
+
+    def clip_adam_step(self, lr, max_norm=0.5, betas=(0.9, 0.999), eps=1e-8, all_reduce=False, want_norm=True):
+        s = E._stream()
+        self.sumsq.zero_()
+        if all_reduce and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.g)                           # gradient all-reduce (sum), NCCL over NVLink
+        LIB.call("u2gnn_grad_sqnorm", self.g.data_ptr(), self.total, self.sumsq.data_ptr(), s)
+        self.step_count += 1
+        LIB.call("u2gnn_clip_adam", self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.total,
+                 self.sumsq.data_ptr(), max_norm, lr, betas[0], betas[1], eps, self.step_count, s)
+        return float(self.sumsq.sqrt().item()) if want_norm else None
+
+
+class SupTrainer:
+    """Supervised fused step.  batch = (input_x[N,S] int64, rowptr[G+1] int64, X[N,d] f32, labels[G] int64)."""
+
+    def __init__(self, model: TransformerU2GNN, lr=5e-4, smoothing=0.1, max_norm=0.5, seed=123):
+        self.model, self.lr, self.smoothing, self.max_norm = model, lr, smoothing, max_norm
+        self.arena = FlatArena(model)
+        self.seed, self.steps = seed, 0
+        self.L, self.T = model.num_U2GNN_layers, model.num_self_att_layers
+        self.params = [_layer_param_dicts(model.u2gnn_layers[l]) for l in range(self.L)]
+        name = lambda l, t, n: "u2gnn_layers.%d.layers.%d.%s" % (l, t, n)
+        self.grads = [[{n: self.arena.gviews[name(l, t, n)] for n in E.PARAM_NAMES} for t in range(self.T)]
+                      for l in range(self.L)]
+        self.loss = torch.zeros(1, dtype=torch.float32, device=self.arena.p.device)
+
+    def _drop(self, train):
+        if not train:
+            return E.DropoutCfg(enabled=False)
+        self.steps += 1
+        seed = (self.seed * 0x9E3779B97F4A7C15 + self.steps) & 0xFFFFFFFFFFFFFFFF
+        return E.DropoutCfg(enabled=True, seed=seed, p_enc=self.model.encoder_dropout, p_out=self.model.dropouts[0].p)
+
+    def forward_backward(self, input_x, rowptr, X, labels, train=True, G_total=None):
+        m, s = self.model, E._stream()
+        drop = self._drop(train)
+        axis = m.attn_axis
+        N, d = X.shape
+        G = rowptr.numel() - 1
+        C = m.num_classes
+        thr_out = drop.thr_out()
+        transpose = E.IndexTranspose(input_x, N) if (self.L > 1 and axis == "neighbors" and m.deterministic) else None
+        scores = torch.empty((G, C), dtype=torch.float32, device=X.device)
+        src, saved, outs, ges = X, [], [], []
+        for l in range(self.L):
+            pl = [{n: t.data for n, t in p.items()} for p in self.params[l]]
+            out, sv = E.u2gnn_layer_fwd(src, input_x, pl, l, self.T, axis, drop)
+            ge = E.segment_sum(out, rowptr)
+            W, b = m.predictions[l].weight.data, m.predictions[l].bias.data
+            LIB.call("u2gnn_head_fwd", ge.data_ptr(), G, d, W.data_ptr(), b.data_ptr(), C, drop.seed, E.STREAM_POOLED + l,
+                     thr_out, scores.data_ptr(), int(l > 0), s)
+            saved.append((sv, pl)); outs.append(out); ges.append(ge)
+            src = out
+        dscores = torch.empty_like(scores)
+        LIB.call("u2gnn_soft_ce_fwd_bwd", scores.data_ptr(), labels.data_ptr(), G, C, self.smoothing,
+                 G if G_total is None else G_total, self.loss.data_ptr(), dscores.data_ptr(), s)
+        self.arena.zero_grad()
+        dsrc_next = None
+        for l in reversed(range(self.L)):
+            W = m.predictions[l].weight.data
+            dge = torch.empty((G, d), dtype=torch.float32, device=X.device)
+            LIB.call("u2gnn_head_bwd", dscores.data_ptr(), ges[l].data_ptr(), G, d, W.data_ptr(), C, drop.seed,
+                     E.STREAM_POOLED + l, thr_out, self.arena.gviews["predictions.%d.weight" % l].data_ptr(),
+                     self.arena.gviews["predictions.%d.bias" % l].data_ptr(), dge.data_ptr(), s)
+            if dsrc_next is None:
+                dout = E.segment_sum_bwd(dge, rowptr, N)
+            else:
+                dout = E.segment_sum_bwd(dge, rowptr, N, out=dsrc_next, accumulate=True)
+            sv, pl = saved[l]
+            dsrc_next = E.u2gnn_layer_bwd(dout, sv, input_x, pl, self.grads[l], l, self.T, axis, drop,
+                                          need_dsrc=(l > 0), transpose=transpose)
+            saved[l] = None
+        return self.loss, scores
+
+    def step(self, input_x, rowptr, X, labels, G_total=None):
+        loss, _ = self.forward_backward(input_x, rowptr, X, labels, True, G_total)
+        self.arena.clip_adam_step(self.lr, self.max_norm, all_reduce=True, want_norm=False)
+        return loss
+
+
+class UnSupTrainer:
+    """Unsupervised fused step.  batch = (X[N,d], input_x[N,S], input_y[N]); negatives are drawn on the
+    device by the log-uniform sampler (or injected with `sample_ids`).  loss = sum of per-node losses
+    (train_pytorch_U2GNN_UnSup.py:156)."""
+
+    def __init__(self, model: TransformerU2GNNUnSup, lr=5e-3, max_norm=0.5, seed=123):
+        self.model, self.lr, self.max_norm = model, lr, max_norm
+        self.arena = FlatArena(model)
+        self.seed, self.steps = seed, 0
+        self.L, self.T = model.num_U2GNN_layers, model.num_self_att_layers
+        self.params = [_layer_param_dicts(model.u2gnn_layers[l]) for l in range(self.L)]
+        name = lambda l, t, n: "u2gnn_layers.%d.layers.%d.%s" % (l, t, n)
+        self.grads = [[{n: self.arena.gviews[name(l, t, n)] for n in E.PARAM_NAMES} for t in range(self.T)]
+                      for l in range(self.L)]
+        self.sampler = None
+
+    def step(self, X, input_x, input_y, sample_ids=None, apply=True):
+        from .model import LogUniformSampler
+        m, s = self.model, E._stream()
+        self.steps += 1
+        seed = (self.seed * 0x9E3779B97F4A7C15 + self.steps) & 0xFFFFFFFFFFFFFFFF
+        drop = E.DropoutCfg(enabled=True, seed=seed, p_enc=m.encoder_dropout, p_out=m.dropouts.p)
+        axis = m.attn_axis
+        N, d = X.shape
+        D = d * self.L
+        V = m.ss.weight.shape[0]
+        if sample_ids is None:
+            if self.sampler is None:
+                self.sampler = LogUniformSampler(V, X.device)
+            sample_ids = self.sampler.sample_device(m.sampled_num)
+        transpose = E.IndexTranspose(input_x, N) if (self.L > 1 and axis == "neighbors" and m.deterministic) else None
+        src, saved = X, []
+        cat = torch.empty((N, D), dtype=torch.float32, device=X.device) if self.L > 1 else None
+        for l in range(self.L):
+            pl = [{n: t.data for n, t in p.items()} for p in self.params[l]]
+            out, sv = E.u2gnn_layer_fwd(src, input_x, pl, l, self.T, axis, drop)
+            saved.append((sv, pl))
+            if cat is not None:
+                E.copy_rows(out, d, cat, D, N, d, dst_off=l * d)
+            else:
+                cat = out
+            src = out
+        thr = drop.thr_out()
+        vec = torch.empty_like(cat)
+        LIB.call("u2gnn_dropout_apply", cat.data_ptr(), cat.numel(), drop.seed, E.STREAM_CONCAT, thr, vec.data_ptr(), s)
+        W = m.ss.weight.data
+        node_loss = torch.empty(N, dtype=torch.float32, device=X.device)
+        denom = torch.empty(N, dtype=torch.float32, device=X.device)
+        LIB.call("u2gnn_sampled_softmax_fwd", vec.data_ptr(), input_y.data_ptr(), N, D, W.data_ptr(), V,
+                 sample_ids.data_ptr(), sample_ids.numel(), node_loss.data_ptr(), denom.data_ptr(), s)
+        self.arena.zero_grad()
+        dloss = torch.ones(N, dtype=torch.float32, device=X.device)
+        dvec = torch.empty_like(vec)
+        LIB.call("u2gnn_sampled_softmax_bwd", dloss.data_ptr(), vec.data_ptr(), input_y.data_ptr(), N, D, W.data_ptr(), V,
+                 sample_ids.data_ptr(), sample_ids.numel(), denom.data_ptr(), dvec.data_ptr(),
+                 self.arena.gviews["ss.weight"].data_ptr(), s)
+        dcat = torch.empty_like(dvec)
+        LIB.call("u2gnn_dropout_apply", dvec.data_ptr(), dvec.numel(), drop.seed, E.STREAM_CONCAT, thr, dcat.data_ptr(), s)
+        dsrc_next = None
+        for l in reversed(range(self.L)):
+            if self.L > 1:
+                dout = torch.empty((N, d), dtype=torch.float32, device=X.device)
+                E.copy_rows(dcat, D, dout, d, N, d, src_off=l * d)
+                if dsrc_next is not None:
+                    LIB.call("u2gnn_axpy", 1.0, dsrc_next.data_ptr(), dout.data_ptr(), N * d, s)
+            else:
+                dout = dcat
+            sv, pl = saved[l]
+            dsrc_next = E.u2gnn_layer_bwd(dout, sv, input_x, pl, self.grads[l], l, self.T, axis, drop,
+                                          need_dsrc=(l > 0), transpose=transpose)
+            saved[l] = None
+        if apply:
+            self.arena.clip_adam_step(self.lr, self.max_norm, all_reduce=True, want_norm=False)
+        return node_loss

@@ -1,0 +1,170 @@
+/* u2gnn_b200 — C-ABI of the B200-native U2GNN train-step hot path.
+ *
+ * Drop-in boundary.  The reference has no native boundary for the model itself
+ * (it is stock PyTorch eager); its only native code is the Cython-wrapped C++ sampler
+ * (U2GNN_pytorch/log_uniform/log_uniform.pyx:16-40 -> Log_Uniform_Sampler.cpp).  Each entry point
+ * below therefore cites the reference call it replaces.  Conventions for every function:
+ *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers unless named host_*
+ *   - the caller owns every buffer (inputs, outputs, workspaces); the library never allocates,
+ *     never synchronises and launches only on the `stream` argument (a cudaStream_t)
+ *   - returns 0 (U2GNN_OK) or a negative U2GNN_E* code; u2gnn_strerror() names it
+ *   - dropout uses an explicit counter-based stream (seed, stream id) — see csrc/rng.cuh;
+ *     p is quantised to thr/256, thr = 0 disables the site
+ *   - index tensors are int64 (the reference dtype); feature tensors are fp32 row-major
+ */
+#ifndef U2GNN_B200_H
+#define U2GNN_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* u2gnn_stream_t; /* cudaStream_t */
+
+enum {
+    U2GNN_OK = 0,
+    U2GNN_EINVAL = -1,      /* bad shape / null pointer / unsupported size */
+    U2GNN_EALIGN = -2,      /* pointer or leading dimension not aligned as required */
+    U2GNN_EUNSUPPORTED = -3,/* feature size outside the kernels' range */
+    U2GNN_ELAUNCH = -4,     /* CUDA launch error (cudaPeekAtLastError) */
+    U2GNN_EWORKSPACE = -5,  /* workspace too small */
+    U2GNN_EDEVICE = -6      /* not an sm_100 device */
+};
+
+const char* u2gnn_strerror(int code);
+int u2gnn_version(void);
+/* 0 when the current device can run the sm_100a kernels */
+int u2gnn_device_check(void);
+/* engine dropout stream: writes the keep-mask word (32 elements) for group g — host helper used
+ * by tests to pin the device stream against the oracle restatement */
+uint32_t u2gnn_rng_mask_word_host(uint64_t seed, uint32_t stream, uint64_t group, int thr);
+
+/* ---- K1: row gather.  Replaces F.embedding(input_x, X_concat) / F.embedding(input_x, output_Tr)
+ *      (pytorch_U2GNN_Sup.py:32,39).  out[i,:] = table[idx[i],:]; idx_stride lets the caller
+ *      gather only column 0 of input_x (idx element i is idx[i*idx_stride]).  Bit-exact copy. */
+int u2gnn_gather_rows(const float* table, int64_t n_table, int d, const int64_t* idx, int64_t n_idx,
+                      int64_t idx_stride, float* out, u2gnn_stream_t stream);
+/* backward of the re-gather (autograd of pytorch_U2GNN_Sup.py:39): dst[idx[i],:] += grad[i,:].
+ * dst must be initialised by the caller.  deterministic=0 uses fp32 atomics. */
+int u2gnn_scatter_add_rows(const float* grad, int64_t n_idx, int d, const int64_t* idx, int64_t idx_stride,
+                           float* dst, int64_t n_dst, u2gnn_stream_t stream);
+/* deterministic variant: CSR transpose of the index list (built once per batch) + ordered sums */
+size_t u2gnn_index_transpose_workspace_bytes(int64_t n_idx, int64_t n_dst);
+int u2gnn_index_transpose_build(const int64_t* idx, int64_t n_idx, int64_t idx_stride, int64_t n_dst,
+                                int64_t* t_rowptr /*[n_dst+1]*/, int64_t* t_pos /*[n_idx]*/,
+                                void* workspace, size_t workspace_bytes, u2gnn_stream_t stream);
+int u2gnn_scatter_add_rows_det(const float* grad, int d, const int64_t* t_rowptr, const int64_t* t_pos,
+                               float* dst, int64_t n_dst, int accumulate, u2gnn_stream_t stream);
+
+/* ---- K4: graph sum-pooling.  Replaces torch.spmm(graph_pool, output_Tr) (pytorch_U2GNN_Sup.py:41)
+ *      with the CSR form of the reference's COO operator (train_pytorch_U2GNN_Sup.py:73-89):
+ *      out[g,:] = sum_{n in [rowptr[g], rowptr[g+1])} x[n,:], summed in ascending node order. */
+int u2gnn_rowptr_from_coo(const int64_t* coo_rows, int64_t nnz, int64_t num_graphs, int64_t* rowptr,
+                          u2gnn_stream_t stream);
+int u2gnn_segment_sum(const float* x, int64_t n, int d, const int64_t* rowptr, int64_t num_graphs, float* out,
+                      u2gnn_stream_t stream);
+int u2gnn_segment_sum_bwd(const float* grad_out, int64_t num_graphs, int d, const int64_t* rowptr, float* grad_x,
+                          int64_t n, int accumulate, u2gnn_stream_t stream);
+
+/* ---- fp32 building blocks of the encoder layer (nn.TransformerEncoderLayer, post-norm, 1 head;
+ *      pytorch_U2GNN_Sup.py:20-21,35 -> torch/nn/modules/transformer.py:944-982) ---- */
+/* C[M,N] = epi(alpha * op(A) op(B) + bias) (+ beta*C).  op(A) is M x K: A[m*lda+k] (ta=0) or
+ * A[k*lda+m] (ta=1); op(B) is K x N: B[k*ldb+n] (tb=0) or B[n*ldb+k] (tb=1).
+ * epi flags: 1 = add bias[n]; 2 = ReLU; 4 = dropout with (seed, stream, thr) on linear index (rng_row0+m)*N+n;
+ *            8 = multiply by scale*(aux[m*ldaux+n] > 0) (ReLU/dropout backward through saved output);
+ *            16 = accumulate into C with atomics (split-K along K over `splitk` slices). */
+int u2gnn_sgemm(int ta, int tb, int64_t M, int N, int64_t K, float alpha, const float* A, int64_t lda,
+                const float* B, int64_t ldb, float beta, float* C, int64_t ldc, const float* bias, int epi,
+                uint64_t seed, uint32_t rng_stream, int thr, int64_t rng_row0, const float* aux, int64_t ldaux,
+                float aux_scale, int splitk, u2gnn_stream_t stream);
+/* out[n] (+)= sum_m A[m*lda+n] */
+int u2gnn_colsum(const float* A, int64_t M, int N, int64_t lda, float* out, int accumulate, u2gnn_stream_t stream);
+
+/* short-sequence self-attention (attn_axis="neighbors", S <= 32): one sequence per node.
+ * qkv[B, S, 3d] (q | k | v per row), ctx[B, Sq, d]; Sq = S, or 1 for the dead-row-eliminated last
+ * timestep (only query position 0; then q rows are read from qkv position 0).  softmax(q k^T/sqrt(d))
+ * with dropout on the probabilities (linear index (b*Sq+i)*S+j), then @ v. */
+int u2gnn_seqattn_fwd(const float* qkv, int64_t B, int S, int Sq, int d, uint64_t seed, uint32_t rng_stream, int thr,
+                      float* ctx, u2gnn_stream_t stream);
+/* dqkv[B, S, 3d] is fully written (rows without a query get dq = 0) */
+int u2gnn_seqattn_bwd(const float* qkv, const float* dctx, int64_t B, int S, int Sq, int d, uint64_t seed,
+                      uint32_t rng_stream, int thr, float* dqkv, u2gnn_stream_t stream);
+/* long-sequence pieces (attn_axis="nodes"): row softmax of scores[M, N] in place with dropout, and
+ * its backward  ds = p * (dp*mask - rowsum(dp*mask*p)) given the un-dropped probabilities p. */
+int u2gnn_softmax_rows_fwd(float* scores, int64_t M, int64_t N, float* probs_dropped, uint64_t seed,
+                           uint32_t rng_stream, int thr, u2gnn_stream_t stream);
+int u2gnn_softmax_rows_bwd(const float* probs, float* dprobs_inout, int64_t M, int64_t N, uint64_t seed,
+                           uint32_t rng_stream, int thr, u2gnn_stream_t stream);
+
+/* z = res + dropout(a);  y = LayerNorm(z) * gamma + beta  (eps 1e-5, biased variance).
+ * res may be null (plain LayerNorm of a).  Saves z (pre-norm) and stats[M,2] = (mean, rstd). */
+int u2gnn_add_dropout_ln_fwd(const float* res, const float* a, int64_t M, int d, uint64_t seed, uint32_t rng_stream,
+                             int thr, const float* gamma, const float* beta, float* z, float* y, float* stats,
+                             u2gnn_stream_t stream);
+/* dz = LN backward of dy; dgamma/dbeta accumulated (atomics); da = dz * dropout mask (may be null). */
+int u2gnn_add_dropout_ln_bwd(const float* dy, const float* z, const float* stats, int64_t M, int d,
+                             const float* gamma, uint64_t seed, uint32_t rng_stream, int thr, float* dz, float* da,
+                             float* dgamma, float* dbeta, u2gnn_stream_t stream);
+/* y = LayerNorm(z) from saved stats (re-materialises a layer input from its pre-norm value) */
+int u2gnn_ln_apply(const float* z, const float* stats, int64_t M, int d, const float* gamma, const float* beta,
+                   float* y, u2gnn_stream_t stream);
+/* elementwise helpers: y = x * keepmask * scale ; y += x */
+int u2gnn_dropout_apply(const float* x, int64_t numel, uint64_t seed, uint32_t rng_stream, int thr, float* y,
+                        u2gnn_stream_t stream);
+int u2gnn_axpy(float alpha, const float* x, float* y, int64_t numel, u2gnn_stream_t stream);
+/* strided row copy: dst[i*ld_dst + c] = src[i*ld_src + c], c < d (position-0 select, concat) */
+int u2gnn_copy_rows(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int64_t rows, int d, int accumulate,
+                    u2gnn_stream_t stream);
+
+/* ---- K5: classifier head + label-smoothed soft cross-entropy.
+ *      Replaces pytorch_U2GNN_Sup.py:42-44,48-59 and train_pytorch_U2GNN_Sup.py:140-142.
+ *      scores[G,C] += dropout(ge[G,d]) @ W[C,d]^T + b   (called once per U2GNN layer)        */
+int u2gnn_head_fwd(const float* ge, int64_t G, int d, const float* W, const float* b, int C, uint64_t seed,
+                   uint32_t rng_stream, int thr, float* scores, int accumulate, u2gnn_stream_t stream);
+/* loss = mean_g sum_c -t[g,c] log_softmax(scores)[g,c], t = label_smoothing(labels, C, smoothing);
+ * writes loss[1] and dscores[G,C] (gradient of the mean loss; G_total lets data-parallel ranks
+ * divide by the global number of graphs). */
+int u2gnn_soft_ce_fwd_bwd(const float* scores, const int64_t* labels, int64_t G, int C, float smoothing,
+                          int64_t G_total, float* loss, float* dscores, u2gnn_stream_t stream);
+/* dW[C,d] += dscores^T @ dropout(ge); db[C] += colsum(dscores); dge[G,d] = (dscores @ W) * mask */
+int u2gnn_head_bwd(const float* dscores, const float* ge, int64_t G, int d, const float* W, int C, uint64_t seed,
+                   uint32_t rng_stream, int thr, float* dW, float* db, float* dge, u2gnn_stream_t stream);
+
+/* ---- K6: log-uniform candidate sampler.  Replaces LogUniformSampler.sample
+ *      (log_uniform.pyx:29-34 -> Log_Uniform_Sampler.cpp:57-71, std::default_random_engine(1111)).
+ *      Draw i of the reference's sequential stream is recomputed independently on the device by
+ *      LCG skip-ahead; the first `size` distinct ids in stream order are kept.  state_inout[0] is
+ *      the minstd_rand0 state (1111 initially) and is advanced past the consumed draws;
+ *      out_ids[size] holds the ids in first-occurrence order, out_tries[0] the reference's
+ *      num_tries.  Single-CTA kernel; workspace from u2gnn_logu_sample_workspace_bytes. */
+size_t u2gnn_logu_sample_workspace_bytes(int64_t size);
+int u2gnn_logu_sample(int64_t range_max, int64_t size, uint32_t* state_inout, int64_t* out_ids, int32_t* out_tries,
+                      void* workspace, size_t workspace_bytes, u2gnn_stream_t stream);
+/* expected_count (Log_Uniform_Sampler.cpp:23-32): out[i] = -expm1(tries * log1p(-prob[ids[i]])) */
+int u2gnn_logu_expected_count(int64_t range_max, const int32_t* tries, const int64_t* ids, int64_t n, float* out,
+                              u2gnn_stream_t stream);
+
+/* ---- K7: fused sampled softmax.  Replaces SampledSoftmax.sampled (sampled_softmax.py:36-56):
+ *      loss[i] = -log( exp(x_i . W[y_i]) / sum_s exp(x_i . W[ids[s]]) ), no max-subtraction, no
+ *      log-Q correction.  Saves denom[N] for the backward.
+ *      Backward: dx[N,D] and a DENSE dW[V,D] accumulation (the reference's W.grad is dense). */
+int u2gnn_sampled_softmax_fwd(const float* x, const int64_t* labels, int64_t N, int D, const float* W, int64_t V,
+                              const int64_t* ids, int ns, float* loss, float* denom, u2gnn_stream_t stream);
+int u2gnn_sampled_softmax_bwd(const float* dloss, const float* x, const int64_t* labels, int64_t N, int D,
+                              const float* W, int64_t V, const int64_t* ids, int ns, const float* denom, float* dx,
+                              float* dW, u2gnn_stream_t stream);
+
+/* ---- K8: fused global-norm clip + Adam.  Replaces clip_grad_norm_(params, 0.5) + Adam.step()
+ *      (train_pytorch_U2GNN_Sup.py:145,160-161) over ONE flat parameter arena.
+ *      sqnorm: sumsq[0] += sum(g^2) (caller zeroes it; all-reduced across ranks by the host side).
+ *      adam: coef = min(1, max_norm/(sqrt(sumsq)+1e-6)); g *= coef; standard Adam, step 1-based. */
+int u2gnn_grad_sqnorm(const float* g, int64_t n, float* sumsq, u2gnn_stream_t stream);
+int u2gnn_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq, float max_norm,
+                    float lr, float beta1, float beta2, float eps, int64_t step, u2gnn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* U2GNN_B200_H */

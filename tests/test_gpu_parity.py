@@ -1,0 +1,281 @@
+"""Parity of the CUDA path (through the C-ABI library) against the oracle and the golden fixtures.
+Integer / index / copy work is compared bit-exactly; fp32 work within 1e-4 relative
+(BASELINE.json north_star).  Runs on the B200 box:  pytest -m gpu
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, split_case, rel_err
+from oracle import u2gnn_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def U():
+    import u2gnn_b200
+    u2gnn_b200.require_device()
+    return u2gnn_b200
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def random_csr(rng, G, max_nodes):
+    sizes = rng.integers(0, max_nodes + 1, size=G)
+    sizes[rng.integers(0, G)] = 1
+    return np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+
+
+# ------------------------------------------------------------------ K1 / K4 (bit-exact)
+@pytest.mark.parametrize("d", [1, 4, 7, 64, 65])
+def test_gather_scatter_bit_exact(U, d):
+    from u2gnn_b200 import engine as E
+    rng = np.random.default_rng(d)
+    table = rng.standard_normal((97, d)).astype(np.float32)
+    idx = rng.integers(0, 97, size=(53, 9)).astype(np.int64)
+    out = E.gather_rows(dev(table), dev(idx))
+    assert np.array_equal(out.cpu().numpy(), O.gather_rows(table, idx).reshape(-1, d))
+    col0 = E.gather_rows(dev(table), dev(idx), idx_stride=9, n_idx=53)
+    assert np.array_equal(col0.cpu().numpy(), table[idx[:, 0]])
+    # deterministic scatter-add: ordered sums equal a sequential fp32 accumulation in source order
+    g = rng.standard_normal((53 * 9, d)).astype(np.float32)
+    tr = E.IndexTranspose(dev(idx), 97)
+    got = tr.scatter_add(dev(g)).cpu().numpy()
+    ref = np.zeros((97, d), dtype=np.float32)
+    for i, t in enumerate(idx.reshape(-1)):
+        ref[t] = ref[t] + g[i]
+    assert np.array_equal(got, ref)
+    again = tr.scatter_add(dev(g)).cpu().numpy()
+    assert np.array_equal(got, again)
+    atom = E.scatter_add_rows(dev(g), dev(idx), 97).cpu().numpy()
+    assert rel_err(atom, ref) < 1e-5
+
+
+@pytest.mark.parametrize("d", [2, 7, 64])
+def test_segment_sum_bit_exact_and_edge_cases(U, d):
+    from u2gnn_b200 import engine as E
+    rng = np.random.default_rng(100 + d)
+    rowptr = random_csr(rng, 37, 30)
+    n = int(rowptr[-1])
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    got = E.segment_sum(dev(x), dev(rowptr)).cpu().numpy()
+    assert np.array_equal(got, O.segment_sum(x, rowptr))          # same ascending-node summation order
+    gout = rng.standard_normal((37, d)).astype(np.float32)
+    gb = E.segment_sum_bwd(dev(gout), dev(rowptr), n).cpu().numpy()
+    assert np.array_equal(gb, O.segment_sum_bwd(gout, rowptr, n))
+
+
+def test_rowptr_from_reference_coo(U):
+    from u2gnn_b200 import engine as E
+    c = load_golden("sup_neighbors_small")
+    idx = torch.from_numpy(c["pool_idx"]).cuda()
+    gp = torch.sparse_coo_tensor(idx, torch.ones(idx.shape[1], device="cuda"), (len(c["labels"]), c["X"].shape[0]))
+    assert np.array_equal(E.rowptr_from_graph_pool(gp).cpu().numpy(), c["rowptr"])
+
+
+# ------------------------------------------------------------------ dropout stream
+@pytest.mark.parametrize("p", [0.5, 0.25, 0.1, 0.9])
+def test_dropout_stream_matches_oracle_restatement(U, p):
+    from u2gnn_b200 import engine as E
+    n = 5000
+    x = torch.ones(n, device="cuda")
+    y = torch.empty_like(x)
+    thr = E.dropout_threshold(p)
+    U.LIB.call("u2gnn_dropout_apply", x.data_ptr(), n, 0xDEADBEEF12345, 77, thr, y.data_ptr(), E._stream())
+    keep, scale = O.dropout_keep_mask(0xDEADBEEF12345, 77, n, p)
+    assert np.array_equal(y.cpu().numpy(), keep.astype(np.float32) * np.float32(scale))
+    w = U.LIB.call("u2gnn_rng_mask_word_host", 0xDEADBEEF12345, 77, 3, thr)
+    assert [(w >> i) & 1 for i in range(32)] == [int(b) for b in keep[96:128]]
+
+
+# ------------------------------------------------------------------ supervised model vs golden (reference) fixtures
+SUP_CASES = ["sup_neighbors_small", "sup_neighbors_L2", "sup_neighbors_d65", "sup_neighbors_d64",
+             "sup_nodes_small", "sup_nodes_L2"]
+
+
+def build_sup(U, c, train=False):
+    params, grads, after = split_case(c)
+    k, d, ff, T, L, C = [int(v) for v in c["meta"]]
+    m = U.TransformerU2GNN(d, ff, C, T, 0.5, L, attn_axis=str(c["attn_axis"])).cuda()
+    missing = m.load_state_dict({n: torch.from_numpy(v) for n, v in params.items()}, strict=True)
+    idx = dev(c["pool_idx"])
+    gp = torch.sparse_coo_tensor(idx, torch.ones(idx.shape[1], device="cuda"), (len(c["labels"]), c["X"].shape[0]))
+    return m, gp, params, grads, after, (k, d, ff, T, L, C)
+
+
+@pytest.mark.parametrize("case", SUP_CASES)
+def test_sup_eval_scores_match_reference(U, case):
+    c = load_golden(case)
+    m, gp, *_ = build_sup(U, c)
+    m.eval()
+    with torch.no_grad():
+        s = m(dev(c["input_x"]), gp, dev(c["X"]))
+    assert rel_err(s.cpu().numpy(), c["eval_scores"]) < TOL
+
+
+@pytest.mark.parametrize("case", SUP_CASES)
+def test_sup_loss_grads_and_adam_match_reference(U, case):
+    c = load_golden(case)
+    m, gp, params, grads, after, (k, d, ff, T, L, C) = build_sup(U, c)
+    m.train()
+    m.encoder_dropout = 0.0
+    for dr in m.dropouts:
+        dr.p = 0.0
+    s = m(dev(c["input_x"]), gp, dev(c["X"]))
+    soft = U.label_smoothing(dev(c["labels"]), C)
+    assert np.allclose(soft.cpu().numpy(), c["soft"], atol=1e-7)
+    loss = torch.mean(torch.sum(-soft * torch.nn.functional.log_softmax(s, dim=1), 1))
+    assert abs(loss.item() - float(c["loss"])) < TOL * max(1.0, abs(float(c["loss"])))
+    loss.backward()
+    gmax = max(np.abs(v).max() for v in grads.values())
+    for n, p in m.named_parameters():
+        assert p.grad is not None, n
+        assert np.abs(p.grad.cpu().numpy() - grads[n]).max() < TOL * gmax, n
+    # fused clip + Adam over a flat arena vs the reference's clip_grad_norm_ + Adam.step
+    from u2gnn_b200.trainer import FlatArena
+    arena = FlatArena(m)
+    arena.grads_from_autograd()
+    norm = arena.clip_adam_step(lr=5e-4, max_norm=0.5)
+    assert abs(norm - float(c["grad_norm"])) < 1e-4 * float(c["grad_norm"])
+    for n, p in m.named_parameters():
+        assert np.abs(p.detach().cpu().numpy() - after[n]).max() < 2e-6, n
+
+
+@pytest.mark.parametrize("case", ["sup_neighbors_small", "sup_neighbors_L2", "sup_nodes_L2", "sup_neighbors_d64"])
+def test_sup_train_mode_with_dropout_matches_oracle(U, case):
+    """Dropout ON: the oracle restates the engine's counter-based stream, so masks are identical."""
+    c = load_golden(case)
+    m, gp, params, _, _, (k, d, ff, T, L, C) = build_sup(U, c)
+    m.train()
+    m.set_dropout_seed(5, 0)
+    s = m(dev(c["input_x"]), gp, dev(c["X"]))
+    soft = U.label_smoothing(dev(c["labels"]), C)
+    loss = torch.mean(torch.sum(-soft * torch.nn.functional.log_softmax(s, dim=1), 1))
+    loss.backward()
+    seed = (5 * 0x9E3779B97F4A7C15 + 1) & 0xFFFFFFFFFFFFFFFF
+    P = {n: v.astype(np.float64) for n, v in params.items()}
+    drop = O.DropoutSpec(enabled=True, seed=seed, p_enc=0.5, p_out=0.5)
+    rowptr = c["rowptr"]
+    X = c["X"].astype(np.float64)
+    so, cache = O.sup_forward(P, c["input_x"], rowptr, X, L, T, str(c["attn_axis"]), drop)
+    assert rel_err(s.detach().cpu().numpy(), so) < TOL
+    lo, dscores = O.soft_cross_entropy(so, O.label_smoothing(c["labels"], C, dtype=np.float64))
+    assert abs(loss.item() - lo) < TOL * max(1.0, abs(lo))
+    g = O.sup_backward(dscores, cache, P, c["input_x"], rowptr, X)
+    gmax = max(np.abs(v).max() for v in g.values())
+    for n, p in m.named_parameters():
+        assert np.abs(p.grad.cpu().numpy() - g[n]).max() < TOL * gmax, n
+
+
+def test_mutag_first_batch_known_answer(U):
+    c = load_golden("mutag_kat")
+    params, _, _ = split_case(c)
+    m = U.TransformerU2GNN(7, 1024, 2, 3, 0.5, 1, attn_axis="nodes").cuda()
+    m.load_state_dict({n: torch.from_numpy(v) for n, v in params.items()})
+    m.eval()
+    idx = dev(c["pool_idx"])
+    gp = torch.sparse_coo_tensor(idx, torch.ones(idx.shape[1], device="cuda"), (4, 81))
+    with torch.no_grad():
+        s = m(dev(c["input_x"]), gp, dev(c["X"]))
+    assert rel_err(s.cpu().numpy(), c["eval_scores"]) < TOL
+    assert np.allclose(s.cpu().numpy()[0], [5.5076, 26.3134], atol=2e-3)
+
+
+def test_same_seed_gives_reference_initial_weights(U):
+    c = load_golden("mutag_kat")
+    params, _, _ = split_case(c)
+    torch.manual_seed(123)                                   # train_pytorch_U2GNN_Sup.py:6
+    m = U.TransformerU2GNN(feature_dim_size=7, ff_hidden_size=1024, num_classes=2, dropout=0.5,
+                           num_self_att_layers=3, num_U2GNN_layers=1)
+    sd = m.state_dict()
+    assert set(sd) == set(params)
+    for n, v in params.items():
+        assert np.array_equal(sd[n].numpy(), v), n
+
+
+# ------------------------------------------------------------------ unsupervised: sampler + sampled softmax
+@pytest.mark.parametrize("case", ["unsup_neighbors", "unsup_nodes"])
+def test_unsup_loss_and_grads_match_reference(U, case):
+    c = load_golden(case)
+    params, grads, _ = split_case(c)
+    k, d, ff, T, L, V, ns = [int(v) for v in c["meta"]]
+    m = U.TransformerU2GNNUnSup(V, d, ff, ns, T, L, 0.5, torch.device("cuda"), attn_axis=str(c["attn_axis"])).cuda()
+    m.load_state_dict({n: torch.from_numpy(v) for n, v in params.items()}, strict=True)
+    m.train()
+    m.encoder_dropout = 0.0
+    m.dropouts.p = 0.0
+    node_loss = m(dev(c["X"]), dev(c["input_x"]), dev(c["input_y"]), sample_values=(list(c["sample_ids"]), None, None))
+    assert rel_err(node_loss.detach().cpu().numpy(), c["node_loss"]) < TOL
+    torch.sum(node_loss).backward()
+    gmax = max(np.abs(v).max() for v in grads.values())
+    for n, p in m.named_parameters():
+        assert np.abs(p.grad.cpu().numpy() - grads[n]).max() < TOL * gmax, n
+
+
+@pytest.mark.parametrize("V,ns", [(100, 50), (3371, 512), (8792, 512), (2540000, 512)])
+def test_device_sampler_matches_reference_sets_and_tries(U, V, ns):
+    g = load_golden("sampler_sets")
+    s = U.LogUniformSampler(V)
+    for call in range(2):                                    # engine state carries over between calls
+        ids = s.sample_device(ns).cpu().numpy()
+        assert int(s.tries.item()) == int(g[f"tries_{V}_{ns}_{call}"])
+        assert len(set(ids.tolist())) == ns
+        assert np.array_equal(np.sort(ids), g[f"ids_{V}_{ns}_{call}"])
+    ec = s.expected_count_device(dev(g[f"expcnt_ids_{V}_{ns}"])).cpu().numpy()
+    assert np.allclose(ec, g[f"expcnt_{V}_{ns}"], rtol=1e-6, atol=1e-9)
+    assert s.probability(7) == float(g[f"prob_{V}"][2])
+
+
+def test_device_sampler_against_c_oracle_many_calls(U):
+    from oracle.sampler import OracleSampler
+    for V, ns in [(64, 64), (1000, 3000 // 4), (50000, 2048), (777, 5)]:
+        a, b = U.LogUniformSampler(V), OracleSampler(V)
+        for _ in range(3):
+            ids = a.sample_device(ns).cpu().numpy()
+            oid, tries = b.sample_with_tries(ns)
+            assert int(a.tries.item()) == tries
+            assert np.array_equal(ids, oid)                  # same first-occurrence order as the C oracle
+    with pytest.raises(ValueError):
+        U.LogUniformSampler(10).sample_device(11)
+
+
+def test_sampled_softmax_large_sample_chunking(U):
+    rng = np.random.default_rng(3)
+    N, D, V, ns = 300, 130, 5000, 700                       # ns*D does not fit one staged chunk
+    x = (0.1 * rng.standard_normal((N, D))).astype(np.float32)
+    W = (0.1 * rng.standard_normal((V, D))).astype(np.float32)
+    y = rng.integers(0, V, size=N).astype(np.int64)
+    ids = rng.choice(V, size=ns, replace=False).astype(np.int64)
+    ss = U.SampledSoftmax(V, ns, D, torch.device("cuda")).cuda()
+    ss.weight.data.copy_(torch.from_numpy(W))
+    xt = dev(x).requires_grad_(True)
+    loss = ss.sampled(xt, dev(y), (ids, None, None))
+    lo, cache = O.sampled_softmax_fwd(x.astype(np.float64), y, W.astype(np.float64), ids)
+    assert rel_err(loss.detach().cpu().numpy(), lo) < TOL
+    w = rng.standard_normal(N).astype(np.float32)
+    (loss * dev(w)).sum().backward()
+    dx, dW = O.sampled_softmax_bwd(w.astype(np.float64), cache, x.astype(np.float64), y, W.shape, ids)
+    assert rel_err(xt.grad.cpu().numpy(), dx) < TOL
+    assert rel_err(ss.weight.grad.cpu().numpy(), dW) < TOL
+
+
+# ------------------------------------------------------------------ size-independent properties at scale
+def test_large_gather_pool_properties(U):
+    from u2gnn_b200 import engine as E
+    g = torch.Generator(device="cuda").manual_seed(1)
+    N, S, d = 1 << 20, 17, 64
+    X = torch.randn(N, d, device="cuda", generator=g)
+    idx = torch.randint(0, N, (N, S), device="cuda", generator=g)
+    out = E.gather_rows(X, idx)
+    assert torch.equal(out.view(N, S, d), X[idx])            # bit-exact copy
+    rowptr = torch.arange(0, N + 1, 64, device="cuda", dtype=torch.int64)
+    pooled = E.segment_sum(X, rowptr)
+    # linearity: pool(a*x) == a*pool(x) for a power of two (exact in fp32)
+    assert torch.equal(E.segment_sum(X * 4.0, rowptr), pooled * 4.0)
+    assert torch.allclose(pooled.sum(0), X.sum(0), rtol=1e-3, atol=1e-2)
+    gb = E.segment_sum_bwd(pooled, rowptr, N)
+    assert torch.equal(gb[::64], pooled) and torch.equal(gb[63::64], pooled)
