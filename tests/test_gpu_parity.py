@@ -141,8 +141,15 @@ def test_sup_loss_grads_and_adam_match_reference(U, case):
     arena.grads_from_autograd()
     norm = arena.clip_adam_step(lr=5e-4, max_norm=0.5)
     assert abs(norm - float(c["grad_norm"])) < 1e-4 * float(c["grad_norm"])
+    # Adam's first step is lr*g/(|g|+eps): where the true gradient is zero up to rounding (e.g. the key
+    # bias, to which softmax is invariant) the update is noise in the reference too -> compare only
+    # elements whose clipped gradient is well above eps, and bound the rest by the step size.
+    coef = min(1.0, 0.5 / (float(c["grad_norm"]) + 1e-6))
     for n, p in m.named_parameters():
-        assert np.abs(p.detach().cpu().numpy() - after[n]).max() < 2e-6, n
+        diff = np.abs(p.detach().cpu().numpy() - after[n])
+        solid = np.abs(grads[n]) * coef > 1e-5
+        assert diff[solid].max(initial=0.0) < 2e-6, n
+        assert diff.max() <= 2 * 5e-4 + 1e-7, n
 
 
 @pytest.mark.parametrize("case", ["sup_neighbors_small", "sup_neighbors_L2", "sup_nodes_L2", "sup_neighbors_d64"])
