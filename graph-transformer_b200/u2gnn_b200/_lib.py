@@ -58,12 +58,24 @@ class _Lib:
             fn.restype = ret
             fn.argtypes = [t for t, _ in params]
         self._status = {n for n, (r, _) in SIGNATURES.items() if r is ctypes.c_int}
+        self.launches = 0          # C-ABI calls that launch kernels (bench.py's gpu_launches claim)
+        self.timed = None          # {entry point: [(start_event, end_event), ...]} when profiling
 
     def strerror(self, code):
         return self.cdll.u2gnn_strerror(code).decode()
 
     def call(self, name, *args):
-        rc = getattr(self.cdll, name)(*args)
+        timed = self.timed
+        if timed is not None and name in timed:
+            import torch
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            rc = getattr(self.cdll, name)(*args)
+            b.record()
+            timed[name].append((a, b))
+        else:
+            rc = getattr(self.cdll, name)(*args)
+        self.launches += 1
         if name in self._status and rc != 0 and name != "u2gnn_device_check":
             raise RuntimeError("%s failed: %s (%d)" % (name, self.strerror(rc), rc))
         return rc

@@ -25,6 +25,7 @@ PARAM_NAMES = (
 )
 STREAM_POOLED = 1
 STREAM_CONCAT = 9
+FLOPS = {}    # entry point -> algorithmic flops issued while LIB.timed is active (bench.py roofline)
 
 
 def stream_id(layer, timestep, site, num_timesteps):
@@ -164,6 +165,8 @@ def sgemm(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, alpha=1.0, beta=0.0, bias=Non
     if splitk > 1 or splitk == -1:
         epi |= 16
         splitk = max(splitk, 1)
+    if LIB.timed is not None:
+        FLOPS["u2gnn_sgemm"] = FLOPS.get("u2gnn_sgemm", 0) + 2 * M * N * K
     LIB.call("u2gnn_sgemm", int(ta), int(tb), M, N, K, alpha, _ptr(A) + 4 * a_off, lda, _ptr(B) + 4 * b_off, ldb, beta,
              _ptr(C) + 4 * c_off, ldc, _ptr(bias), epi, seed, stream, thr, row0, _ptr(aux), ldaux, aux_scale, splitk, _stream())
     return C

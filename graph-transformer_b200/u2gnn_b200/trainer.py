@@ -71,7 +71,10 @@ class FlatArena:
 class SupTrainer:
     """Supervised fused step.  batch = (input_x[N,S] int64, rowptr[G+1] int64, X[N,d] f32, labels[G] int64)."""
 
-    def __init__(self, model: TransformerU2GNN, lr=5e-4, smoothing=0.1, max_norm=0.5, seed=123):
+    def __init__(self, model: TransformerU2GNN, lr=5e-4, smoothing=0.1, max_norm=0.5, seed=123, precision="fp32"):
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
         self.model, self.lr, self.smoothing, self.max_norm = model, lr, smoothing, max_norm
         self.arena = FlatArena(model)
         self.seed, self.steps = seed, 0
@@ -129,6 +132,22 @@ class SupTrainer:
                                           need_dsrc=(l > 0), transpose=transpose)
             saved[l] = None
         return self.loss, scores
+
+    def dominant_kernel(self):
+        return "u2gnn_sgemm" if self.precision == "fp32" else "u2gnn_ffn_tc_fwd"
+
+    def roofline(self, name, kernel_ms, launches, peaks, flops):
+        """bench.py roofline object for the dominant kernel: achieved = algorithmic flops / measured time."""
+        peak = peaks.get("bf16_tflops_sustained")
+        which = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+        if peak is None:
+            peak, which = 1590.0, "fallback (B200_PROFILING.md)"
+        achieved = flops.get(name, 0) / max(kernel_ms, 1e-9) / 1e9
+        return {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None, "launches_timed": launches,
+                "avg_launch_ms": kernel_ms / max(launches, 1), "peak_source": which,
+                "note": ("fp32 CUDA-core parity path; the tcgen05 path is --precision bf16" if self.precision == "fp32"
+                         else "fused bf16 tcgen05 FFN")}
 
     def step(self, input_x, rowptr, X, labels, G_total=None):
         loss, _ = self.forward_backward(input_x, rowptr, X, labels, True, G_total)
