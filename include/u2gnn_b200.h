@@ -164,6 +164,13 @@ int u2gnn_grad_sqnorm(const float* g, int64_t n, float* sumsq, u2gnn_stream_t st
 int u2gnn_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq, float max_norm,
                     float lr, float beta1, float beta2, float eps, int64_t step, u2gnn_stream_t stream);
 
+/* ---- tcgen05 plumbing self-test (csrc/tc_selftest.cu): one CTA runs a [128 x N x K] bf16 GEMM through
+ *      each operand path the fused kernels use (mode 0 K-major smem, 1 MN-major smem, 2 A in tensor
+ *      memory, 3 bulk-copied pre-swizzled B).  No reference counterpart: it pins hardware layout
+ *      assumptions.  A, B fp32 inputs (rounded to bf16 inside), C[128, N] fp32; scratch >= 32 KB. */
+int u2gnn_tc_selftest(int mode, const float* A, const float* B, float* C, int K, int N, void* scratch,
+                      u2gnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
