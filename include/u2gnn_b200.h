@@ -164,6 +164,21 @@ int u2gnn_grad_sqnorm(const float* g, int64_t n, float* sumsq, u2gnn_stream_t st
 int u2gnn_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq, float max_norm,
                     float lr, float beta1, float beta2, float eps, int64_t step, u2gnn_stream_t stream);
 
+/* ---- fused bf16 tensor-core FFN block (tcgen05 / TMEM), the path's dense contraction.
+ *      Replaces linear1 -> ReLU -> dropout -> linear2 -> dropout -> residual -> norm2 of
+ *      nn.TransformerEncoderLayer (torch/nn/modules/transformer.py:950-958,977-982); the [M, ff] hidden
+ *      never leaves the SM.  d <= 64, ff a multiple of 128.  Weights are packed once per optimiser step
+ *      into pre-swizzled bf16 shared-memory images (hidden_scale = 1/(1-p) of the hidden dropout is
+ *      folded into the W2 image).
+ *      z[M,d] = y1 + dropout_out( dropout_hidden(relu(y1 W1^T + b1)) W2^T + b2 );
+ *      stats[M,2] = (mean, rstd) of z;  xnext[M,d] = LayerNorm(z)*gamma + beta (may be null). */
+size_t u2gnn_ffn_tc_packed_bytes(int d, int ff);
+int u2gnn_ffn_tc_prepare(const float* W1, const float* b1, const float* W2, const float* b2, int d, int ff,
+                         float hidden_scale, void* packed, size_t packed_size, u2gnn_stream_t stream);
+int u2gnn_ffn_tc_fwd(const float* y1, int64_t M, int d, int ff, const void* packed, uint64_t seed,
+                     uint32_t stream_hidden, uint32_t stream_out, int thr, const float* gamma, const float* beta,
+                     float* z, float* stats, float* xnext, u2gnn_stream_t stream);
+
 /* ---- tcgen05 plumbing self-test (csrc/tc_selftest.cu): one CTA runs a [128 x N x K] bf16 GEMM through
  *      each operand path the fused kernels use (mode 0 K-major smem, 1 MN-major smem, 2 A in tensor
  *      memory, 3 bulk-copied pre-swizzled B).  No reference counterpart: it pins hardware layout
