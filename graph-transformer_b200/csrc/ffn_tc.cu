@@ -28,7 +28,7 @@ constexpr int STAGES = 4;
 constexpr uint32_t W1_BYTES = CH * DP * 2;       // 16 KB  [128 x 64] K-major image
 constexpr uint32_t W2_BYTES = DP * CH * 2;       // 16 KB  two [64 x 64] K-major images
 constexpr uint32_t FWD_BLOCK = W1_BYTES + W2_BYTES;
-// packed weights: per chunk [W1c | W2c | W2Tc | W1Tc] (fwd uses the first two), then b1, b2 (fp32)
+// packed weights: per chunk [W2c | W1c | W2Tc | W1Tc] (fwd: first two; dgrad: last three; wgrad: middle two), then b1, b2 (fp32)
 constexpr uint32_t CHUNK_BYTES = 4 * 16384;
 constexpr int kThreads = 384;
 
@@ -65,9 +65,9 @@ __global__ void __launch_bounds__(256) ffn_pack_kernel(const float* __restrict__
         const float w1 = (k < d) ? W1[(size_t)h * d + k] : 0.0f;
         const float w2 = (k < d) ? W2[(size_t)k * ff + h] * hidden_scale : 0.0f;
         // W1c  : B of GEMM1  [N = hidden r][K = feature k]
-        *reinterpret_cast<__nv_bfloat16*>(blk + tc::sw128_offset(r, k)) = __float2bfloat16(w1);
+        *reinterpret_cast<__nv_bfloat16*>(blk + 16384 + tc::sw128_offset(r, k)) = __float2bfloat16(w1);
         // W2c  : B of GEMM2  [N = feature k][K = hidden r]  (two K atoms of 64)
-        *reinterpret_cast<__nv_bfloat16*>(blk + 16384 + (r >> 6) * 8192 + tc::sw128_offset(k, r & 63)) = __float2bfloat16(w2);
+        *reinterpret_cast<__nv_bfloat16*>(blk + (r >> 6) * 8192 + tc::sw128_offset(k, r & 63)) = __float2bfloat16(w2);
         // W2Tc : B of dH = dF W2c   [N = hidden r][K = feature k]
         *reinterpret_cast<__nv_bfloat16*>(blk + 32768 + tc::sw128_offset(r, k)) = __float2bfloat16(w2);
         // W1Tc : B of dy1 += dPre W1c  [N = feature k][K = hidden r]
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams
             for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++q) {
                 auto g1 = [&](int i, uint32_t chunk_it) {
                     const uint32_t s = chunk_it % STAGES;
-                    const uint32_t a0 = tc::smem_u32(sX + i * 16384), b0 = tc::smem_u32(sW + s * FWD_BLOCK);
+                    const uint32_t a0 = tc::smem_u32(sX + i * 16384), b0 = tc::smem_u32(sW + s * FWD_BLOCK + W2_BYTES);
 #pragma unroll
                     for (int ks = 0; ks < DP / 16; ++ks)
                         tc::mma_ss(tmem + 128 + 128 * i, tc::make_desc_sw128(a0 + ks * 32, 16, 1024),
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams
                         ++hcount[i];
                         if (c == 0 && q > 0) tc::mbar_wait(&bars.y_free[i], (q - 1) & 1);
                         tc::tc_fence_after();
-                        const uint32_t b0 = tc::smem_u32(sW + s * FWD_BLOCK + W1_BYTES);
+                        const uint32_t b0 = tc::smem_u32(sW + s * FWD_BLOCK);
 #pragma unroll
                         for (int ks = 0; ks < CH / 16; ++ks)
                             tc::mma_ts(tmem + 64 * i, tmem + 384 + 64 * i + ks * 8,

@@ -228,9 +228,10 @@ class LayerSaved:
     B: int = 0
     S: int = 0
     Sq: int = 0
+    packed: torch.Tensor = None
 
 
-def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq):
+def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, precision="fp32"):
     """x[B*S, d] -> y[B*Sq, d].  p: dict name->tensor.  drop_ids: 4 stream ids.  long_seq selects the
     attn_axis="nodes" formulation (B == 1, scores materialised as [S, S])."""
     dev = x.device
@@ -258,14 +259,44 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq):
         xq = torch.empty((Mq, d), **f32)
         copy_rows(x, S * d, xq, d, B, d)
     z1, y1, st1 = add_dropout_ln_fwd(xq, a, Mq, d, (seed, drop_ids[1], thr), p["norm1.weight"], p["norm1.bias"])
-    hd = torch.empty((Mq, ff), **f32)
-    sgemm(0, 1, Mq, ff, d, y1, d, p["linear1.weight"], d, hd, ff, bias=p["linear1.bias"], relu=True,
-          drop=(seed, drop_ids[2], thr))
-    f = torch.empty((Mq, d), **f32)
-    sgemm(0, 1, Mq, d, ff, hd, ff, p["linear2.weight"], ff, f, d, bias=p["linear2.bias"])
-    z2, y2, st2 = add_dropout_ln_fwd(y1, f, Mq, d, (seed, drop_ids[3], thr), p["norm2.weight"], p["norm2.bias"])
+    if precision == "bf16":
+        # fused tcgen05 FFN block: the [Mq, ff] hidden never reaches HBM and is recomputed in the backward
+        packed = ffn_tc_pack(p, d, ff, thr)
+        z2 = torch.empty((Mq, d), **f32)
+        y2 = torch.empty((Mq, d), **f32)
+        st2 = torch.empty((Mq, 2), **f32)
+        if LIB.timed is not None:
+            FLOPS["u2gnn_ffn_tc_fwd"] = FLOPS.get("u2gnn_ffn_tc_fwd", 0) + 4 * Mq * d * ff
+        LIB.call("u2gnn_ffn_tc_fwd", _ptr(y1), Mq, d, ff, _ptr(packed), seed, drop_ids[2], drop_ids[3], thr,
+                 _ptr(p["norm2.weight"]), _ptr(p["norm2.bias"]), _ptr(z2), _ptr(st2), _ptr(y2), _stream())
+        hd = None
+        sv.packed = packed
+    else:
+        hd = torch.empty((Mq, ff), **f32)
+        sgemm(0, 1, Mq, ff, d, y1, d, p["linear1.weight"], d, hd, ff, bias=p["linear1.bias"], relu=True,
+              drop=(seed, drop_ids[2], thr))
+        f = torch.empty((Mq, d), **f32)
+        sgemm(0, 1, Mq, d, ff, hd, ff, p["linear2.weight"], ff, f, d, bias=p["linear2.bias"])
+        z2, y2, st2 = add_dropout_ln_fwd(y1, f, Mq, d, (seed, drop_ids[3], thr), p["norm2.weight"], p["norm2.bias"])
     sv.xq, sv.qkv, sv.ctx, sv.z1, sv.st1, sv.y1, sv.hd, sv.z2, sv.st2 = xq, qkv, ctx, z1, st1, y1, hd, z2, st2
     return y2, sv
+
+
+def ffn_tc_supported(d, ff):
+    return d <= 64 and ff % 128 == 0 and 128 <= ff <= 2048
+
+
+def ffn_tc_pack(p, d, ff, thr):
+    """bf16 pre-swizzled weight images for the tcgen05 FFN kernels (rebuilt whenever the weights change)."""
+    if not ffn_tc_supported(d, ff):
+        raise RuntimeError("precision='bf16' needs feature_dim_size <= 64 and ff_hidden_size a multiple of 128 (<= 2048); "
+                           "got d=%d ff=%d (use precision='fp32')" % (d, ff))
+    nbytes = LIB.call("u2gnn_ffn_tc_packed_bytes", d, ff)
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=p["linear1.weight"].device)
+    scale = 256.0 / (256.0 - thr) if thr else 1.0
+    LIB.call("u2gnn_ffn_tc_prepare", _ptr(p["linear1.weight"]), _ptr(p["linear1.bias"]), _ptr(p["linear2.weight"]),
+             _ptr(p["linear2.bias"]), d, ff, scale, _ptr(packed), nbytes, _stream())
+    return packed
 
 
 def encoder_layer_bwd(dy2, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_dx=True):
@@ -279,13 +310,24 @@ def encoder_layer_bwd(dy2, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
     # LayerNorm2 + FFN
     dz2, df = add_dropout_ln_bwd(dy2, sv.z2, sv.st2, Mq, d, p["norm2.weight"], (seed, drop_ids[3], thr),
                                  g["norm2.weight"], g["norm2.bias"])
-    wgrad(df, Mq, d, sv.hd, ff, g["linear2.weight"], g["linear2.bias"])
-    dhpre = torch.empty((Mq, ff), **f32)
-    sgemm(0, 0, Mq, ff, d, df, d, p["linear2.weight"], ff, dhpre, ff, aux=sv.hd, ldaux=ff, aux_scale=drop_scale)
-    wgrad(dhpre, Mq, ff, sv.y1, d, g["linear1.weight"], g["linear1.bias"])
     dy1 = dz2  # dy1 = dz2 + dhpre @ W1 (in place)
-    sgemm(0, 0, Mq, d, ff, dhpre, ff, p["linear1.weight"], d, dy1, d, beta=1.0)
-    del dhpre
+    if sv.packed is not None:
+        # fused tcgen05 backward: hidden and its gradient recomputed on chip
+        if df is dz2:                    # no output dropout: df aliases dz2, which the weight-gradient kernel still reads
+            dy1 = torch.empty_like(dz2)
+        LIB.call("u2gnn_colsum", _ptr(df), Mq, d, d, _ptr(g["linear2.bias"]), 1, _stream())
+        if LIB.timed is not None:
+            FLOPS["u2gnn_ffn_tc_bwd"] = FLOPS.get("u2gnn_ffn_tc_bwd", 0) + 8 * Mq * d * ff
+        LIB.call("u2gnn_ffn_tc_bwd", _ptr(sv.y1), _ptr(df), _ptr(dz2), Mq, d, ff, _ptr(sv.packed), drop_scale, seed,
+                 drop_ids[2], thr, _ptr(dy1), _ptr(g["linear1.weight"]), _ptr(g["linear1.bias"]),
+                 _ptr(g["linear2.weight"]), _stream())
+    else:
+        wgrad(df, Mq, d, sv.hd, ff, g["linear2.weight"], g["linear2.bias"])
+        dhpre = torch.empty((Mq, ff), **f32)
+        sgemm(0, 0, Mq, ff, d, df, d, p["linear2.weight"], ff, dhpre, ff, aux=sv.hd, ldaux=ff, aux_scale=drop_scale)
+        wgrad(dhpre, Mq, ff, sv.y1, d, g["linear1.weight"], g["linear1.bias"])
+        sgemm(0, 0, Mq, d, ff, dhpre, ff, p["linear1.weight"], d, dy1, d, beta=1.0)
+        del dhpre
     # LayerNorm1 + attention
     dz1, da = add_dropout_ln_bwd(dy1, sv.z1, sv.st1, Mq, d, p["norm1.weight"], (seed, drop_ids[1], thr),
                                  g["norm1.weight"], g["norm1.bias"])
@@ -326,7 +368,7 @@ class StackSaved:
     S: int = 0
 
 
-def u2gnn_layer_fwd(src, input_x, params, l, T, attn_axis, drop: DropoutCfg):
+def u2gnn_layer_fwd(src, input_x, params, l, T, attn_axis, drop: DropoutCfg, precision="fp32"):
     """src[n_src, d], input_x[N, S] int64 -> out[N, d].  params: list (per timestep) of dicts."""
     require_device()
     _check(src, torch.float32, "src"); _check(input_x, torch.int64, "input_x")
@@ -349,7 +391,7 @@ def u2gnn_layer_fwd(src, input_x, params, l, T, attn_axis, drop: DropoutCfg):
         last = attn_axis == "neighbors" and t == T - 1
         Sq = 1 if last else Sseq
         ids = [stream_id(l, t, s, T) for s in range(4)]
-        x, sv = encoder_layer_fwd(x, B, Sseq, Sq, params[t], d, ff, ids, drop.seed, thr, attn_axis == "nodes")
+        x, sv = encoder_layer_fwd(x, B, Sseq, Sq, params[t], d, ff, ids, drop.seed, thr, attn_axis == "nodes", precision)
         saved.layers.append(sv)
     return x, saved  # [N, d] in both layouts
 

@@ -38,16 +38,16 @@ class _StackFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, src, input_x, cfg, *flat):
-        l, T, axis, drop, transpose = cfg
+        l, T, axis, drop, transpose, precision = cfg
         params = [dict(zip(E.PARAM_NAMES, [t.detach() for t in flat[i * 12:(i + 1) * 12]])) for i in range(T)]
-        out, saved = E.u2gnn_layer_fwd(src.detach().contiguous(), input_x, params, l, T, axis, drop)
+        out, saved = E.u2gnn_layer_fwd(src.detach().contiguous(), input_x, params, l, T, axis, drop, precision)
         ctx.saved_stack, ctx.params, ctx.cfg, ctx.input_x = saved, params, cfg, input_x
         ctx.need_dsrc = src.requires_grad
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        l, T, axis, drop, transpose = ctx.cfg
+        l, T, axis, drop, transpose, precision = ctx.cfg
         grads = [{n: torch.zeros_like(t) for n, t in p.items()} for p in ctx.params]
         dsrc = E.u2gnn_layer_bwd(dout.contiguous(), ctx.saved_stack, ctx.input_x, ctx.params, grads, l, T, axis, drop,
                                  need_dsrc=ctx.need_dsrc, transpose=transpose)
@@ -116,9 +116,12 @@ class _DropoutFn(torch.autograd.Function):
 
 
 class _U2GNNBase(nn.Module):
-    def _init_engine(self, attn_axis, deterministic):
+    def _init_engine(self, attn_axis, deterministic, precision="fp32"):
         if attn_axis not in ("nodes", "neighbors"):
             raise ValueError("attn_axis must be 'nodes' or 'neighbors'")
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision            # 'bf16': FFN on tcgen05 tensor cores (2e-2 tolerance mode)
         self.attn_axis = attn_axis
         self.deterministic = deterministic
         self.encoder_dropout = 0.5            # hard-coded in the reference (pytorch_U2GNN_Sup.py:20)
@@ -137,7 +140,7 @@ class _U2GNNBase(nn.Module):
 
     def _run_stack(self, l, src, input_x, drop, transpose):
         flat = [p[n] for p in _layer_param_dicts(self.u2gnn_layers[l]) for n in E.PARAM_NAMES]
-        cfg = (l, self.num_self_att_layers, self.attn_axis, drop, transpose)
+        cfg = (l, self.num_self_att_layers, self.attn_axis, drop, transpose, self.precision)
         return _StackFn.apply(src, input_x, cfg, *flat)
 
     def _transpose_for(self, input_x, n_src):
@@ -152,7 +155,7 @@ class TransformerU2GNN(_U2GNNBase):
     ("neighbors") attention layout."""
 
     def __init__(self, feature_dim_size, ff_hidden_size, num_classes, num_self_att_layers, dropout,
-                 num_U2GNN_layers, attn_axis="nodes", deterministic=True):
+                 num_U2GNN_layers, attn_axis="nodes", deterministic=True, precision="fp32"):
         super().__init__()
         self.feature_dim_size = feature_dim_size
         self.ff_hidden_size = ff_hidden_size
@@ -168,7 +171,7 @@ class TransformerU2GNN(_U2GNNBase):
         for _ in range(num_U2GNN_layers):
             self.predictions.append(nn.Linear(feature_dim_size, num_classes))
             self.dropouts.append(nn.Dropout(dropout))
-        self._init_engine(attn_axis, deterministic)
+        self._init_engine(attn_axis, deterministic, precision)
 
     def forward(self, input_x, graph_pool, X_concat):
         require_device()
@@ -313,7 +316,7 @@ class TransformerU2GNNUnSup(_U2GNNBase):
 
     def __init__(self, vocab_size, feature_dim_size, ff_hidden_size, sampled_num, num_self_att_layers,
                  num_U2GNN_layers, dropout, device, sampler_type="default", loss_type="default", adj_mat=None,
-                 single_layer_only=True, attn_axis="nodes", deterministic=True):
+                 single_layer_only=True, attn_axis="nodes", deterministic=True, precision="fp32"):
         super().__init__()
         if sampler_type != "default" or loss_type != "default":
             raise NotImplementedError("only the default sampler / sampled-softmax loss is part of the hot path")
@@ -330,7 +333,7 @@ class TransformerU2GNNUnSup(_U2GNNBase):
             self.u2gnn_layers.append(TransformerEncoder(enc, num_self_att_layers))
         self.dropouts = nn.Dropout(dropout)
         self.ss = SampledSoftmax(vocab_size, sampled_num, feature_dim_size * num_U2GNN_layers, device)
-        self._init_engine(attn_axis, deterministic)
+        self._init_engine(attn_axis, deterministic, precision)
 
     def encode(self, X_concat, input_x, drop=None):
         drop = drop or E.DropoutCfg(enabled=False)

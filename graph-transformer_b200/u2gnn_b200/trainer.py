@@ -75,6 +75,7 @@ class SupTrainer:
         if precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")
         self.precision = precision
+        model.precision = precision
         self.model, self.lr, self.smoothing, self.max_norm = model, lr, smoothing, max_norm
         self.arena = FlatArena(model)
         self.seed, self.steps = seed, 0
@@ -105,7 +106,7 @@ class SupTrainer:
         src, saved, outs, ges = X, [], [], []
         for l in range(self.L):
             pl = [{n: t.data for n, t in p.items()} for p in self.params[l]]
-            out, sv = E.u2gnn_layer_fwd(src, input_x, pl, l, self.T, axis, drop)
+            out, sv = E.u2gnn_layer_fwd(src, input_x, pl, l, self.T, axis, drop, self.precision)
             ge = E.segment_sum(out, rowptr)
             W, b = m.predictions[l].weight.data, m.predictions[l].bias.data
             LIB.call("u2gnn_head_fwd", ge.data_ptr(), G, d, W.data_ptr(), b.data_ptr(), C, drop.seed, E.STREAM_POOLED + l,
@@ -134,7 +135,7 @@ class SupTrainer:
         return self.loss, scores
 
     def dominant_kernel(self):
-        return "u2gnn_sgemm" if self.precision == "fp32" else "u2gnn_ffn_tc_fwd"
+        return "u2gnn_sgemm" if self.precision == "fp32" else "u2gnn_ffn_tc_bwd"
 
     def roofline(self, name, kernel_ms, launches, peaks, flops):
         """bench.py roofline object for the dominant kernel: achieved = algorithmic flops / measured time."""
@@ -190,7 +191,7 @@ class UnSupTrainer:
         cat = torch.empty((N, D), dtype=torch.float32, device=X.device) if self.L > 1 else None
         for l in range(self.L):
             pl = [{n: t.data for n, t in p.items()} for p in self.params[l]]
-            out, sv = E.u2gnn_layer_fwd(src, input_x, pl, l, self.T, axis, drop)
+            out, sv = E.u2gnn_layer_fwd(src, input_x, pl, l, self.T, axis, drop, m.precision)
             saved.append((sv, pl))
             if cat is not None:
                 E.copy_rows(out, d, cat, D, N, d, dst_off=l * d)

@@ -101,3 +101,120 @@ def test_ffn_tc_forward(U, M, d, ff, p):
     assert np.abs(stats[:, 0] - mean).max() < 2e-2 * max(1.0, np.abs(mean).max())
     assert np.abs(stats[:, 1] / rstd - 1).max() < 2e-2
     assert np.abs(xn - xn_ref).max() / np.abs(xn_ref).max() < 2e-2
+
+
+# ------------------------------------------------------------------ fused FFN backward
+@pytest.mark.parametrize("M,d,ff,p", [(256, 64, 128, 0.0), (1000, 64, 2048, 0.5), (37, 64, 256, 0.0), (300, 7, 256, 0.5),
+                                      (5000, 64, 1024, 0.25), (148 * 256 * 2 + 77, 64, 256, 0.5)])
+def test_ffn_tc_backward(U, M, d, ff, p):
+    from u2gnn_b200 import engine as E
+    from oracle import u2gnn_oracle as O
+    rng = np.random.default_rng(5 + M + d + ff)
+    y1 = rng.standard_normal((M, d)).astype(np.float32)
+    df = rng.standard_normal((M, d)).astype(np.float32)
+    dz = rng.standard_normal((M, d)).astype(np.float32)
+    W1 = (rng.standard_normal((ff, d)) / np.sqrt(d)).astype(np.float32)
+    b1 = (0.1 * rng.standard_normal(ff)).astype(np.float32)
+    W2 = (rng.standard_normal((d, ff)) / np.sqrt(ff)).astype(np.float32)
+    b2 = np.zeros(d, dtype=np.float32)
+    thr = E.dropout_threshold(p)
+    scale = 256.0 / (256.0 - thr) if thr else 1.0
+    dev = lambda a: torch.from_numpy(a).cuda()
+    t = {k: dev(v) for k, v in dict(y1=y1, df=df, dz=dz, W1=W1, b1=b1, W2=W2, b2=b2).items()}
+    nbytes = U.LIB.call("u2gnn_ffn_tc_packed_bytes", d, ff)
+    packed = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    U.LIB.call("u2gnn_ffn_tc_prepare", t["W1"].data_ptr(), t["b1"].data_ptr(), t["W2"].data_ptr(), t["b2"].data_ptr(), d, ff,
+               scale, packed.data_ptr(), nbytes, E._stream())
+    dy1 = torch.zeros((M, d), device="cuda")
+    dW1 = torch.zeros((ff, d), device="cuda"); db1 = torch.zeros(ff, device="cuda"); dW2 = torch.zeros((d, ff), device="cuda")
+    SEED, S2 = 0x1234ABCD99, 18
+    U.LIB.call("u2gnn_ffn_tc_bwd", t["y1"].data_ptr(), t["df"].data_ptr(), t["dz"].data_ptr(), M, d, ff, packed.data_ptr(), scale,
+               SEED, S2, thr, dy1.data_ptr(), dW1.data_ptr(), db1.data_ptr(), dW2.data_ptr(), E._stream())
+    torch.cuda.synchronize()
+    if thr:
+        k2, _ = O.dropout_keep_mask(SEED, S2, M * ff, p)
+        m2 = k2.reshape(M, ff).astype(np.float64) * scale
+    else:
+        m2 = np.ones((M, ff))
+    y64, df64 = y1.astype(np.float64), df.astype(np.float64)
+    hpre = y64 @ W1.T.astype(np.float64) + b1
+    hd = np.maximum(hpre, 0) * m2
+    dhd = df64 @ W2.astype(np.float64)
+    dhpre = dhd * m2 * (hpre > 0)
+    ref = dict(dy1=dz + dhpre @ W1.astype(np.float64), dW1=dhpre.T @ y64, db1=dhpre.sum(0), dW2=df64.T @ hd)
+    # emulation of the tensor-core arithmetic: bf16 operands, wide accumulation, bf16 hidden / dPre.  The ReLU
+    # mask is decided by the bf16-operand pre-activation, exactly as on the device.
+    yb, dfb, W1b, W2sb = (_bf(a).astype(np.float64) for a in (y1, df, W1, W2 * scale))
+    hpre_b = yb @ W1b.T + b1
+    keep = (m2 > 0)
+    Hb = _bf(np.maximum(hpre_b, 0) * keep).astype(np.float64)
+    Pb = _bf((dfb @ W2sb) * keep * (hpre_b > 0)).astype(np.float64)
+    emu = dict(dy1=dz + Pb @ W1b, dW1=Pb.T @ yb, db1=Pb.sum(0), dW2=(dfb.T @ Hb) * scale)
+    got = dict(dy1=dy1, dW1=dW1, db1=db1, dW2=dW2)
+    for name in ref:
+        g = got[name].cpu().numpy().astype(np.float64)
+        assert np.isfinite(g).all(), name
+        e_emu = np.abs(g - emu[name]).max() / np.abs(emu[name]).max()
+        assert e_emu < 3e-3, (name, "vs bf16 emulation", e_emu)
+        # against exact fp32 semantics, norm-wise: the ReLU derivative is discontinuous, so the ~0.2% of hidden
+        # units whose pre-activation changes sign under bf16 operand rounding each move a whole term of the
+        # gradient; 5e-2 bounds that effect (the 2e-2 of BASELINE.json is stated for embeddings and loss, which
+        # tests/test_gpu_tc.py::test_bf16_train_step_vs_fp32_path checks end to end).
+        e_ref = np.linalg.norm(g - ref[name]) / np.linalg.norm(ref[name])
+        assert e_ref < 5e-2, (name, "vs oracle", e_ref)
+
+
+# ------------------------------------------------------------------ bf16-FFN mode end to end
+def _golden_model(U, case, precision):
+    from conftest import load_golden, split_case
+    c = load_golden(case)
+    params, grads, _ = split_case(c)
+    k, d, ff, T, L, C = [int(v) for v in c["meta"]]
+    m = U.TransformerU2GNN(d, ff, C, T, 0.5, L, attn_axis="neighbors", precision=precision).cuda()
+    m.load_state_dict({n: torch.from_numpy(v) for n, v in params.items()})
+    return c, m, grads, (k, d, ff, T, L, C)
+
+
+def test_bf16_eval_scores_and_loss_within_2e2_of_reference(U):
+    """north_star: embeddings and loss within 2e-2 relative in bf16-FFN mode (vs the reference fixtures)."""
+    c, m, grads, (k, d, ff, T, L, C) = _golden_model(U, "sup_neighbors_d64", "bf16")
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    m.eval()
+    with torch.no_grad():
+        s = m(dev(c["input_x"]), dev(c["rowptr"]), dev(c["X"]))
+    err = np.abs(s.cpu().numpy() - c["eval_scores"]).max() / np.abs(c["eval_scores"]).max()
+    assert err < 2e-2, err
+    m.train(); m.encoder_dropout = 0.0
+    for dr in m.dropouts:
+        dr.p = 0.0
+    s = m(dev(c["input_x"]), dev(c["rowptr"]), dev(c["X"]))
+    soft = U.label_smoothing(dev(c["labels"]), C)
+    loss = torch.mean(torch.sum(-soft * torch.nn.functional.log_softmax(s, dim=1), 1))
+    assert abs(loss.item() - float(c["loss"])) < 2e-2 * abs(float(c["loss"]))
+    loss.backward()
+    for n, p in m.named_parameters():
+        ref = grads[n]
+        if np.linalg.norm(ref) < 1e-3 * max(np.linalg.norm(v) for v in grads.values()):
+            continue                                        # numerically-zero gradients (e.g. key bias)
+        e = np.linalg.norm(p.grad.cpu().numpy() - ref) / np.linalg.norm(ref)
+        assert e < 5e-2, (n, e)
+
+
+def test_bf16_train_step_vs_fp32_path(U):
+    """Same batch, same dropout stream: the tcgen05 path tracks the fp32 CUDA path through a full fused train step
+    (forward + loss + backward + clip + Adam) on a cfg5-shaped batch."""
+    from u2gnn_b200.synthetic import make_batch
+    from u2gnn_b200.trainer import SupTrainer
+    b = make_batch(3000, 16, 64, 2, seed=5)
+    out = {}
+    for prec in ("fp32", "bf16"):
+        torch.manual_seed(7)
+        m = U.TransformerU2GNN(64, 512, 2, 2, 0.5, 1, attn_axis="neighbors").cuda()
+        tr = SupTrainer(m, lr=5e-4, precision=prec, seed=99)
+        loss, scores = tr.forward_backward(b["input_x"], b["rowptr"], b["X"], b["labels"], train=True)
+        out[prec] = (loss.item(), scores.clone(), tr.arena.g.clone())
+    l32, s32, g32 = out["fp32"]
+    l16, s16, g16 = out["bf16"]
+    assert abs(l16 - l32) < 2e-2 * abs(l32)
+    assert (s16 - s32).abs().max().item() < 2e-2 * s32.abs().max().item()
+    assert ((g16 - g32).norm() / g32.norm()).item() < 5e-2
