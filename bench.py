@@ -258,8 +258,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("U2GNN_PRECISION", "fp32"), choices=["fp32", "bf16"])
-    ap.add_argument("--nodes", type=int, default=int(os.environ.get("U2GNN_BENCH_NODES", 65536)),
+    ap.add_argument("--precision", default=os.environ.get("U2GNN_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--nodes", type=int, default=int(os.environ.get("U2GNN_BENCH_NODES", 262144)),
                     help="nodes per rank per step")
     ap.add_argument("--cpu-nodes", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -213,15 +213,21 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams
             {
                 uint8_t* xt = sX + i * 16384;
                 if (p.d == DP) {
-#pragma unroll 4
+                    float4 v[16];           // 16 independent 128-bit loads in flight per thread
+#pragma unroll
                     for (int itx = 0; itx < 16; ++itx) {
                         const int e = itx * 128 + tg;
                         const int r = e >> 4, c4 = e & 15;
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (row0 + r < p.M) v = __ldg(reinterpret_cast<const float4*>(p.y1 + (row0 + r) * DP) + c4);
+                        v[itx] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row0 + r < p.M) v[itx] = __ldg(reinterpret_cast<const float4*>(p.y1 + (row0 + r) * DP) + c4);
+                    }
+#pragma unroll
+                    for (int itx = 0; itx < 16; ++itx) {
+                        const int e = itx * 128 + tg;
+                        const int r = e >> 4, c4 = e & 15;
                         uint2 w;
-                        w.x = tc::pack_bf16(v.x, v.y);
-                        w.y = tc::pack_bf16(v.z, v.w);
+                        w.x = tc::pack_bf16(v[itx].x, v[itx].y);
+                        w.y = tc::pack_bf16(v[itx].z, v[itx].w);
                         *reinterpret_cast<uint2*>(xt + tc::sw128_offset(r, c4 * 4)) = w;
                     }
                 } else {

@@ -30,15 +30,22 @@ __device__ __forceinline__ const float* packed_b1(const uint8_t* packed, int ff)
 __device__ __forceinline__ void load_tile_bf16(uint8_t* tile, const float* __restrict__ src, int64_t row0, int64_t M, int d,
                                                int tg) {
     if (d == DP) {
-#pragma unroll 4
+        // all 16 loads of a thread are issued before the first use (latency paid once per tile)
+        float4 v[16];
+#pragma unroll
         for (int itx = 0; itx < 16; ++itx) {
             const int e = itx * 128 + tg;
             const int r = e >> 4, c4 = e & 15;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row0 + r < M) v = __ldg(reinterpret_cast<const float4*>(src + (row0 + r) * DP) + c4);
+            v[itx] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + r < M) v[itx] = __ldg(reinterpret_cast<const float4*>(src + (row0 + r) * DP) + c4);
+        }
+#pragma unroll
+        for (int itx = 0; itx < 16; ++itx) {
+            const int e = itx * 128 + tg;
+            const int r = e >> 4, c4 = e & 15;
             uint2 w;
-            w.x = tc::pack_bf16(v.x, v.y);
-            w.y = tc::pack_bf16(v.z, v.w);
+            w.x = tc::pack_bf16(v[itx].x, v[itx].y);
+            w.y = tc::pack_bf16(v[itx].z, v[itx].w);
             *reinterpret_cast<uint2*>(tile + tc::sw128_offset(r, c4 * 4)) = w;
         }
     } else {
@@ -298,21 +305,56 @@ struct WgradParams {
     float* dW2;   // [d, ff]
 };
 
+constexpr int WG_STAGES = 3;                  // ring of (X, dF) row tiles filled by the loader warps
+
 struct __align__(8) WgradBars {
-    uint64_t w_full, x_full[2], x_free[2], s_full[2], a_done[2], d_full[2], hp_full, hp_free, flush_full;
+    uint64_t w_full, ld_full[WG_STAGES], ld_free[WG_STAGES], s_full[2], a_done[2], d_full[2], hp_full, hp_free, flush_full;
 };
 
+// fp32 rows -> bf16 swizzled tile with NT loader threads (batches of 16 independent 128-bit loads)
+template <int NT>
+__device__ __forceinline__ void load_tile_bf16_nt(uint8_t* tile, const float* __restrict__ src, int64_t row0, int64_t M, int d,
+                                                  int tid) {
+    if (d == DP) {
+        for (int base = 0; base < TM * 16; base += NT * 16) {
+            float4 v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int e = base + u * NT + tid;
+                const int r = e >> 4, c4 = e & 15;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row0 + r < M) v[u] = __ldg(reinterpret_cast<const float4*>(src + (row0 + r) * DP) + c4);
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int e = base + u * NT + tid;
+                const int r = e >> 4, c4 = e & 15;
+                uint2 w;
+                w.x = tc::pack_bf16(v[u].x, v[u].y);
+                w.y = tc::pack_bf16(v[u].z, v[u].w);
+                *reinterpret_cast<uint2*>(tile + tc::sw128_offset(r, c4 * 4)) = w;
+            }
+        }
+    } else {
+        for (int e = tid; e < TM * DP; e += NT) {
+            const int r = e / DP, k = e % DP;
+            const float v = (row0 + r < M && k < d) ? src[(row0 + r) * d + k] : 0.0f;
+            *reinterpret_cast<__nv_bfloat16*>(tile + tc::sw128_offset(r, k)) = __float2bfloat16(v);
+        }
+    }
+}
+
 // TMEM: R0 [0,128) R1 [128,256) dW1c [256,320) dW2c^T [320,384) db1c [384,400)
+// Warp roles: 0 weights, 1 MMA issuer, 2-3 row-tile loaders (+ TMEM allocation), 4-7 / 8-11 epilogue of even / odd tiles.
 __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const WgradParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sX = smem;                          // 2 x 16 KB   (tile parity)
-    uint8_t* sF = smem + 2 * 16384;              // 2 x 16 KB
-    uint8_t* sH = smem + 4 * 16384;              // 32 KB: two [128 rows x 64 hidden] tiles
-    uint8_t* sP = smem + 6 * 16384;              // 32 KB
-    uint8_t* sW = smem + 8 * 16384;              // 32 KB: [W1c | W2Tc]
-    uint8_t* sOnes = smem + 10 * 16384;          // 16 KB of bf16 1.0 (layout-invariant B operand)
-    float* sB1 = reinterpret_cast<float*>(smem + 11 * 16384);   // 128 floats
+    uint8_t* sXF = smem;                                   // WG_STAGES x (X 16 KB | dF 16 KB)
+    uint8_t* sH = smem + WG_STAGES * 32768;                // 32 KB: two [128 rows x 64 hidden] tiles
+    uint8_t* sP = sH + 32768;                              // 32 KB
+    uint8_t* sW = sP + 32768;                              // 32 KB: [W1c | W2Tc]
+    uint8_t* sOnes = sW + 32768;                           // 2 KB of bf16 1.0 (layout-invariant B operand)
+    float* sB1 = reinterpret_cast<float*>(sOnes + 2048);   // 128 floats
     __shared__ WgradBars bars;
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -324,9 +366,11 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const WgradPa
 
     if (threadIdx.x == 0) {
         tc::mbar_init(&bars.w_full, 1);
+        for (int s = 0; s < WG_STAGES; ++s) {
+            tc::mbar_init(&bars.ld_full[s], 64);
+            tc::mbar_init(&bars.ld_free[s], 1);
+        }
         for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(&bars.x_full[i], 128);
-            tc::mbar_init(&bars.x_free[i], 1);
             tc::mbar_init(&bars.s_full[i], 1);
             tc::mbar_init(&bars.a_done[i], 128);
             tc::mbar_init(&bars.d_full[i], 1);
@@ -340,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const WgradPa
     {
         const float* b1g = packed_b1(p.packed, p.ff) + c * CH;
         for (int e = threadIdx.x; e < CH; e += kThreads) sB1[e] = b1g[e];
-        for (int e = threadIdx.x; e < 16384 / 4; e += kThreads) reinterpret_cast<uint32_t*>(sOnes)[e] = 0x3F803F80u;
+        for (int e = threadIdx.x; e < 2048 / 4; e += kThreads) reinterpret_cast<uint32_t*>(sOnes)[e] = 0x3F803F80u;
     }
     tc::fence_proxy_async();
     tc::tc_fence_before();
@@ -354,13 +398,25 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const WgradPa
                 tc::mbar_arrive_expect_tx(&bars.w_full, 32768);
                 tc::bulk_g2s(sW, p.packed + (size_t)c * CHUNK_BYTES + 16384, 32768, &bars.w_full);
             }
+        } else if (warp == 2 || warp == 3) {
+            // ================= row-tile loaders: global fp32 -> bf16 swizzled tiles, WG_STAGES ahead =================
+            const int tid = (warp - 2) * 32 + lane;
+            for (int64_t n = 0; n < my_tiles; ++n) {
+                const uint32_t s = (uint32_t)(n % WG_STAGES), u = (uint32_t)(n / WG_STAGES);
+                if (u > 0) tc::mbar_wait(&bars.ld_free[s], (u - 1) & 1);
+                const int64_t row0 = ((int64_t)slice + n * n_slices) * TM;
+                load_tile_bf16_nt<64>(sXF + s * 32768, p.y1, row0, p.M, p.d, tid);
+                load_tile_bf16_nt<64>(sXF + s * 32768 + 16384, p.df, row0, p.M, p.d, tid);
+                tc::fence_proxy_async();
+                tc::mbar_arrive(&bars.ld_full[s]);
+            }
         } else if (warp == 1) {
             if (lane == 0) {
                 const uint32_t idesc_n128 = tc::make_idesc(TM, CH, 0, 0);
                 const uint32_t idesc_w = tc::make_idesc(CH, DP, 1, 1);      // M = hidden, N = d, both MN-major
-                const uint32_t idesc_b = tc::make_idesc(CH, 16, 1, 0);        // B = ones, K-major [16 x 16]
+                const uint32_t idesc_b = tc::make_idesc(CH, 16, 1, 0);      // B = ones, K-major [16 x 16]
                 auto gemm_n128 = [&](int i, const uint8_t* a_tile, uint32_t b_off, uint64_t* bar) {
-                    const uint32_t a0 = tc::smem_u32(a_tile + i * 16384), b0 = tc::smem_u32(sW + b_off);
+                    const uint32_t a0 = tc::smem_u32(a_tile), b0 = tc::smem_u32(sW + b_off);
 #pragma unroll
                     for (int ks = 0; ks < DP / 16; ++ks)
                         tc::mma_ss(tmem + 128 * i, tc::make_desc_sw128(a0 + ks * 32, 16, 1024),
@@ -368,25 +424,26 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const WgradPa
                     tc::mma_commit(bar);
                 };
                 tc::mbar_wait(&bars.w_full, 0);
-                tc::mbar_wait(&bars.x_full[0], 0);
+                tc::mbar_wait(&bars.ld_full[0], 0);
                 tc::tc_fence_after();
-                gemm_n128(0, sX, 0, &bars.s_full[0]);
+                gemm_n128(0, sXF, 0, &bars.s_full[0]);
                 for (int64_t n = 0; n < my_tiles; ++n) {
                     const int i = (int)(n & 1);
                     const uint32_t ph = (uint32_t)(n >> 1) & 1;      // per-parity barriers complete every second tile
+                    const uint8_t* st = sXF + (n % WG_STAGES) * 32768;
                     tc::mbar_wait(&bars.a_done[i], ph);
                     tc::tc_fence_after();
-                    gemm_n128(i, sF, 16384, &bars.d_full[i]);
+                    gemm_n128(i, st + 16384, 16384, &bars.d_full[i]);
                     if (n + 1 < my_tiles) {
-                        const int i2 = (int)((n + 1) & 1);
-                        tc::mbar_wait(&bars.x_full[i2], (uint32_t)((n + 1) >> 1) & 1);
+                        const uint32_t s2 = (uint32_t)((n + 1) % WG_STAGES);
+                        tc::mbar_wait(&bars.ld_full[s2], (uint32_t)((n + 1) / WG_STAGES) & 1);
                         tc::tc_fence_after();
-                        gemm_n128(i2, sX, 0, &bars.s_full[i2]);
+                        gemm_n128((int)((n + 1) & 1), sXF + s2 * 32768, 0, &bars.s_full[(n + 1) & 1]);
                     }
                     tc::mbar_wait(&bars.hp_full, (uint32_t)n & 1);
                     tc::tc_fence_after();
                     const uint32_t h0 = tc::smem_u32(sH), p0 = tc::smem_u32(sP);
-                    const uint32_t x0 = tc::smem_u32(sX + i * 16384), f0 = tc::smem_u32(sF + i * 16384), o0 = tc::smem_u32(sOnes);
+                    const uint32_t x0 = tc::smem_u32(st), f0 = tc::smem_u32(st + 16384), o0 = tc::smem_u32(sOnes);
 #pragma unroll
                     for (int ks = 0; ks < TM / 16; ++ks) {
                         const uint32_t acc = (n > 0 || ks > 0);
@@ -399,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const WgradPa
                                    tc::make_desc_sw128(o0, 16, 1024), idesc_b, acc);
                     }
                     tc::mma_commit(&bars.hp_free);
-                    tc::mma_commit(&bars.x_free[i]);
+                    tc::mma_commit(&bars.ld_free[n % WG_STAGES]);
                 }
                 tc::mma_commit(&bars.flush_full);
             }
@@ -412,11 +469,6 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const WgradPa
             for (int64_t n = i; n < my_tiles; n += 2, ++k) {
                 const int64_t row0 = ((int64_t)slice + n * n_slices) * TM;
                 const int64_t row = row0 + tg;
-                if (k > 0) tc::mbar_wait(&bars.x_free[i], (k - 1) & 1);
-                load_tile_bf16(sX + i * 16384, p.y1, row0, p.M, p.d, tg);
-                load_tile_bf16(sF + i * 16384, p.df, row0, p.M, p.d, tg);
-                tc::fence_proxy_async();
-                tc::mbar_arrive(&bars.x_full[i]);
                 // ---- S -> H = relu(S + b1) * keep   (bf16, registers)
                 tc::mbar_wait(&bars.s_full[i], k & 1);
                 tc::tc_fence_after();
@@ -537,7 +589,7 @@ extern "C" int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const float* d
         p.thr = thr;
         p.hidden_scale = hidden_scale;
         p.dW1 = dW1; p.db1 = db1; p.dW2 = dW2;
-        const size_t smem = 1024 + 11 * 16384 + 512;
+        const size_t smem = 1024 + (size_t)WG_STAGES * 32768 + 3 * 32768 + 2048 + 512;
         cudaFuncSetAttribute(ffn_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int64_t n_tiles = (M + TM - 1) / TM;
         int n_slices = U2GNN_NUM_SMS / NC;

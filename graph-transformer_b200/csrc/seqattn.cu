@@ -16,23 +16,33 @@ struct AttnRng {
     float scale;
 };
 
-// loads q (pre-scaled), k, v of sequence b into this warp's shared memory
-__device__ __forceinline__ void load_qkv(const float* __restrict__ qkv, int64_t b, int S, int Sq, int d, float qscale,
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// q, k, v of sequence b -> this warp's shared memory with cp.async (LDGSTS): every element of the
+// node's contiguous [S, 3d] block is in flight at once, so the global latency is paid once per node
+__device__ __forceinline__ void load_qkv(const float* __restrict__ qkv, int64_t b, int S, int Sq, int d,
                                          float* qs, float* ks, float* vs, int lane) {
     const int P = pitch_of(d);
     const float* base = qkv + b * (int64_t)S * 3 * d;
-    for (int r = 0; r < S; ++r) {
-        const float* row = base + (int64_t)r * 3 * d;
-        for (int c = lane; c < d; c += 32) {
-            if (r < Sq) qs[r * P + c] = row[c] * qscale;
-            ks[r * P + c] = row[d + c];
-            vs[r * P + c] = row[2 * d + c];
+    const int total = S * 3 * d;
+    for (int e = lane; e < total; e += 32) {
+        const int r = e / (3 * d), rem = e - r * 3 * d;
+        const int part = rem / d, c = rem - part * d;
+        if (part == 0) {
+            if (r < Sq) cp_async4(qs + r * P + c, base + e);
+        } else {
+            cp_async4((part == 1 ? ks : vs) + r * P + c, base + e);
         }
     }
 }
 
 // probabilities of query i for key `lane`: returns p (un-dropped) and writes the dropout multiplier
-__device__ __forceinline__ float attn_probs(const float* qs, const float* ks, int i, int S, int d, int lane,
+__device__ __forceinline__ float attn_probs(const float* qs, const float* ks, int i, int S, int d, int lane, float qscale,
                                             const AttnRng& rng, uint64_t elem_base, float* mult_out) {
     const int P = pitch_of(d);
     float s = -INFINITY;
@@ -41,7 +51,7 @@ __device__ __forceinline__ float attn_probs(const float* qs, const float* ks, in
         const float* qr = qs + i * P;
         const float* kr = ks + lane * P;
         for (int c = 0; c < d; ++c) acc = fmaf(qr[c], kr[c], acc);
-        s = acc;
+        s = acc * qscale;
     }
     const float m = warp_max(s);
     const float e = (lane < S) ? expf(s - m) : 0.0f;
@@ -61,11 +71,12 @@ __global__ void __launch_bounds__(256) seqattn_fwd_kernel(const float* __restric
     const float qscale = sqrtf(1.0f / (float)d);
     for (int64_t b = (int64_t)blockIdx.x * warps + w; b < B; b += (int64_t)gridDim.x * warps) {
         __syncwarp();
-        load_qkv(qkv, b, S, Sq, d, qscale, qs, ks, vs, lane);
+        load_qkv(qkv, b, S, Sq, d, qs, ks, vs, lane);
+        cp_async_wait_all();
         __syncwarp();
         for (int i = 0; i < Sq; ++i) {
             float mult;
-            const float p = attn_probs(qs, ks, i, S, d, lane, rng, (uint64_t)(b * Sq + i) * (uint64_t)S, &mult);
+            const float p = attn_probs(qs, ks, i, S, d, lane, qscale, rng, (uint64_t)(b * Sq + i) * (uint64_t)S, &mult);
             const float pd = p * mult;
             float* out = ctx + (b * Sq + i) * (int64_t)d;
             for (int c0 = 0; c0 < d; c0 += 32) {
@@ -87,33 +98,36 @@ __global__ void __launch_bounds__(256) seqattn_bwd_kernel(const float* __restric
     extern __shared__ float sm[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int P = pitch_of(d);
-    const size_t per_warp = (size_t)(Sq + 4 * S) * P + d;
+    const size_t per_warp = (size_t)(2 * Sq + 4 * S) * P;
     float* qs = sm + (size_t)w * per_warp;
     float* ks = qs + Sq * P;
     float* vs = ks + S * P;
     float* dk = vs + S * P;
     float* dv = dk + S * P;
-    float* drow = dv + S * P;
+    float* dall = dv + S * P;      // [Sq][P] gradient rows
     const float qscale = sqrtf(1.0f / (float)d);
     for (int64_t b = (int64_t)blockIdx.x * warps + w; b < B; b += (int64_t)gridDim.x * warps) {
         __syncwarp();
-        load_qkv(qkv, b, S, Sq, d, qscale, qs, ks, vs, lane);
+        load_qkv(qkv, b, S, Sq, d, qs, ks, vs, lane);
+        {   // all Sq gradient rows of this node (contiguous [Sq, d]) in the same async batch
+            const float* gsrc = dctx + b * (int64_t)Sq * d;
+            for (int e = lane; e < Sq * d; e += 32) cp_async4(dall + (e / d) * P + (e % d), gsrc + e);
+        }
         for (int e = lane; e < S * P; e += 32) {
             dk[e] = 0.0f;
             dv[e] = 0.0f;
         }
+        cp_async_wait_all();
+        __syncwarp();
         float* gbase = dqkv + b * (int64_t)S * 3 * d;
         for (int i = 0; i < S; ++i) {
             if (i >= Sq) {  // rows without a query (dead-row-eliminated timestep): dq = 0
                 for (int c = lane; c < d; c += 32) gbase[(int64_t)i * 3 * d + c] = 0.0f;
                 continue;
             }
-            __syncwarp();
-            const float* grow = dctx + (b * Sq + i) * (int64_t)d;
-            for (int c = lane; c < d; c += 32) drow[c] = grow[c];
-            __syncwarp();
+            const float* drow = dall + i * P;
             float mult;
-            const float p = attn_probs(qs, ks, i, S, d, lane, rng, (uint64_t)(b * Sq + i) * (uint64_t)S, &mult);
+            const float p = attn_probs(qs, ks, i, S, d, lane, qscale, rng, (uint64_t)(b * Sq + i) * (uint64_t)S, &mult);
             const float pd = p * mult;
             float dpt = 0.0f;
             if (lane < S) {
@@ -126,7 +140,7 @@ __global__ void __launch_bounds__(256) seqattn_bwd_kernel(const float* __restric
             for (int c0 = 0; c0 < d; c0 += 32) {
                 const int c = c0 + lane;
                 float dq = 0.0f;
-                const float qv = (c < d) ? qs[i * P + c] : 0.0f;   // already scaled by sqrt(1/d)
+                const float qv = (c < d) ? qs[i * P + c] * qscale : 0.0f;
                 const float dr = (c < d) ? drow[c] : 0.0f;
                 for (int j = 0; j < S; ++j) {
                     const float dsj = __shfl_sync(0xffffffffu, ds, j);
@@ -200,7 +214,7 @@ AttnRng make_rng(uint64_t seed, uint32_t stream, int thr) {
 
 int pick_warps(size_t floats_per_warp) {
     int w = 8;
-    while (w > 1 && (size_t)w * floats_per_warp * sizeof(float) > 96 * 1024) w >>= 1;
+    while (w > 1 && (size_t)w * floats_per_warp * sizeof(float) > 110 * 1024) w >>= 1;   // two CTAs per SM
     return w;
 }
 
@@ -229,7 +243,7 @@ extern "C" int u2gnn_seqattn_bwd(const float* qkv, const float* dctx, int64_t B,
     if (S < 1 || S > 32 || (Sq != S && Sq != 1) || thr < 0 || thr > 255) return U2GNN_EINVAL;
     if (B == 0) return U2GNN_OK;
     const int P = d | 1;
-    const size_t per_warp = (size_t)(Sq + 4 * S) * P + d;
+    const size_t per_warp = (size_t)(2 * Sq + 4 * S) * P;
     const int warps = pick_warps(per_warp);
     const size_t smem = (size_t)warps * per_warp * sizeof(float);
     if (smem > 200 * 1024) return U2GNN_EUNSUPPORTED;
