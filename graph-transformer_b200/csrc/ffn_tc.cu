@@ -5,19 +5,26 @@
 // i.e. linear1 -> ReLU -> dropout -> linear2 -> dropout -> residual -> norm2 of
 // nn.TransformerEncoderLayer (torch/nn/modules/transformer.py:950-958,977-982).  The [rows, ff]
 // hidden activation never leaves the SM: per 128-row tile and 128-wide ff chunk
-//     S  = X W1c^T            tcgen05.mma SS  (X bf16 in smem, W1c bulk-copied pre-swizzled image)
-//     H  = act(S)             epilogue warps: tcgen05.ld -> bias/ReLU/dropout -> bf16 -> tcgen05.st
-//     Y += H W2c^T            tcgen05.mma TS  (H read from tensor memory)
+//     S  = X W1c^T            tcgen05.mma TS  (X bf16 in tensor memory, W1c bulk-copied pre-swizzled image)
+//     H  = act(S)             epilogue warps: tcgen05.ld -> bias/ReLU/dropout (packed bf16x2) -> tcgen05.st
+//     Y += H W2c^T            tcgen05.mma TS  (H read from tensor memory, aliased over the S columns it came from)
 // Persistent CTAs (one per SM) walk pairs of row tiles so that the tensor pipe works on one tile
 // while the epilogue warps convert the other.  Weights stream from L2 through a 4-stage
 // bulk-copy/mbarrier ring shared by both tiles.
 //
-// Warp roles (384 threads): warp 0 weight producer, warp 1 MMA issuer, warp 2 TMEM allocator,
-// warps 4-7 epilogue of tile 0, warps 8-11 epilogue of tile 1 (warp % 4 selects the TMEM lane quarter).
-// TMEM columns: Y0 [0,64) Y1 [64,128) S0 [128,256) S1 [256,384) H0 [384,448) H1 [448,512).
+// Measured facts behind the structure (tools/probe_mma.py, B200): an MMA issued from divergent single-thread code
+// with per-instruction descriptor arithmetic costs ~96-118 cycles regardless of N; issued from warp-uniform code
+// with immediate descriptor increments it costs 49 (N=64, TS) / 70 (N=128, TS) / 77 (N=128, SS) cycles.  Hence
+// the whole MMA warp runs uniformly (elect.sync only around the instruction) and both GEMMs take A from TMEM.
+//
+// Warp roles (640 threads): warp 0 weight producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 epilogue
+// of tile 0, warps 12-19 epilogue of tile 1 (two 64-column halves x four TMEM lane quarters per tile).
+// TMEM columns: Y0 [0,64) Y1 [64,128) S0 [128,256) S1 [256,384) X0 [384,416) X1 [416,448);
+//               H_i (packed bf16) overwrites S_i columns [0,32) and [64,96).
 #include "common.cuh"
 #include "rng.cuh"
 #include "tc_common.cuh"
+#include "ffn_epi.cuh"
 
 namespace {
 
@@ -30,7 +37,8 @@ constexpr uint32_t W2_BYTES = DP * CH * 2;       // 16 KB  two [64 x 64] K-major
 constexpr uint32_t FWD_BLOCK = W1_BYTES + W2_BYTES;
 // packed weights: per chunk [W2c | W1c | W2Tc | W1Tc] (fwd: first two; dgrad: last three; wgrad: middle two), then b1, b2 (fp32)
 constexpr uint32_t CHUNK_BYTES = 4 * 16384;
-constexpr int kThreads = 384;
+constexpr int kThreads = 640;     // 4 control warps + 16 epilogue warps
+constexpr uint32_t COL_Y = 0, COL_S = 128, COL_X = 384;
 
 struct FwdParams {
     const float* y1;
@@ -38,7 +46,7 @@ struct FwdParams {
     int d, ff;
     const uint8_t* packed;
     RngKeys keys2, keys3;
-    int thr;
+    int thr, low;
     float scale3;
     const float* gamma;
     const float* beta;
@@ -85,16 +93,44 @@ __global__ void __launch_bounds__(256) ffn_pack_kernel(const float* __restrict__
 // ---------------------------------------------------------------------------------------------
 struct __align__(8) FwdBars {
     uint64_t w_full[STAGES], w_empty[STAGES];
-    uint64_t x_full[2], x_free[2], s_full[2], h_full[2], h_free[2], y_full[2], y_free[2];
+    uint64_t x_full[2], x_free[2], s_full[2], h_full[2], y_full[2], y_free[2];
 };
+
+// 4 k-steps of S_i = X_i W1c^T (A = packed X in TMEM, 8 columns per k-step; B = W1c image), warp-uniform
+__device__ __forceinline__ void issue_gemm1(uint32_t tmem_s, uint32_t tmem_x, uint64_t b_desc, uint32_t idesc) {
+    if (tc::elect_one()) {
+        tc::mma_ts(tmem_s, tmem_x, b_desc, idesc, 0);
+        tc::mma_ts_acc(tmem_s, tmem_x + 8, b_desc + 2, idesc);
+        tc::mma_ts_acc(tmem_s, tmem_x + 16, b_desc + 4, idesc);
+        tc::mma_ts_acc(tmem_s, tmem_x + 24, b_desc + 6, idesc);
+    }
+    __syncwarp();
+}
+// 8 k-steps of Y_i (+)= H_i W2c^T (A = packed H at S_i columns [0,32) and [64,96); B = two [64 x 64] atoms of W2c)
+__device__ __forceinline__ void issue_gemm2(uint32_t tmem_y, uint32_t tmem_h, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    if (tc::elect_one()) {
+        tc::mma_ts(tmem_y, tmem_h, b_desc, idesc, acc);
+        tc::mma_ts_acc(tmem_y, tmem_h + 8, b_desc + 2, idesc);
+        tc::mma_ts_acc(tmem_y, tmem_h + 16, b_desc + 4, idesc);
+        tc::mma_ts_acc(tmem_y, tmem_h + 24, b_desc + 6, idesc);
+        tc::mma_ts_acc(tmem_y, tmem_h + 64, b_desc + 512, idesc);           // second K atom: +8192 B
+        tc::mma_ts_acc(tmem_y, tmem_h + 72, b_desc + 514, idesc);
+        tc::mma_ts_acc(tmem_y, tmem_h + 80, b_desc + 516, idesc);
+        tc::mma_ts_acc(tmem_y, tmem_h + 88, b_desc + 518, idesc);
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void commit_to(uint64_t* bar) {
+    if (tc::elect_one()) tc::mma_commit(bar);
+    __syncwarp();
+}
 
 __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sX = smem;                                    // 2 x 16 KB
-    uint8_t* sW = smem + 2 * 16384;                        // STAGES x 32 KB
-    float* sB1 = reinterpret_cast<float*>(sW + STAGES * FWD_BLOCK);   // ff floats
-    float* sB2 = sB1 + p.ff;                               // 64 floats
+    uint8_t* sW = smem;                                    // STAGES x 32 KB
+    uint32_t* sB1h = reinterpret_cast<uint32_t*>(sW + STAGES * FWD_BLOCK);   // b1 as packed bf16 pairs (ff/2 words)
+    float* sB2 = reinterpret_cast<float*>(sB1h + p.ff / 2);                  // 64 floats
     float* sG = sB2 + DP;                                  // gamma, beta (2 x 64)
     __shared__ FwdBars bars;
     __shared__ uint32_t tmem_slot;
@@ -109,21 +145,21 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams
             tc::mbar_init(&bars.w_empty[s], 1);
         }
         for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(&bars.x_full[i], 128);
+            tc::mbar_init(&bars.x_full[i], 4);      // one arrival per warp of the loading warpgroup
             tc::mbar_init(&bars.x_free[i], 1);
             tc::mbar_init(&bars.s_full[i], 1);
-            tc::mbar_init(&bars.h_full[i], 128);
-            tc::mbar_init(&bars.h_free[i], 1);
+            tc::mbar_init(&bars.h_full[i], 8);      // one arrival per epilogue warp of the tile
             tc::mbar_init(&bars.y_full[i], 1);
-            tc::mbar_init(&bars.y_free[i], 128);
+            tc::mbar_init(&bars.y_free[i], 4);
         }
         tc::fence_barrier_init();
     }
     if (warp == 2) tc::tmem_alloc<512>(&tmem_slot);
     {   // biases / LayerNorm affine into shared memory
         const float* b1g = packed_b1(p.packed, p.ff);
-        for (int e = threadIdx.x; e < p.ff + DP; e += kThreads) sB1[e] = b1g[e];
+        for (int e = threadIdx.x; e < p.ff / 2; e += kThreads) sB1h[e] = epi::cvt2(b1g[2 * e], b1g[2 * e + 1]);
         for (int e = threadIdx.x; e < DP; e += kThreads) {
+            sB2[e] = b1g[p.ff + e];
             sG[e] = (e < p.d) ? p.gamma[e] : 0.0f;
             sG[DP + e] = (e < p.d) ? p.beta[e] : 0.0f;
         }
@@ -147,179 +183,168 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc1 = tc::make_idesc(TM, CH, 0, 0);
-            const uint32_t idesc2 = tc::make_idesc(TM, DP, 0, 0);
-            uint32_t it = 0;        // global chunk counter (weights ring)
-            uint32_t q = 0;         // pair counter
-            uint32_t hcount[2] = {0, 0};
-            for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++q) {
-                auto g1 = [&](int i, uint32_t chunk_it) {
-                    const uint32_t s = chunk_it % STAGES;
-                    const uint32_t a0 = tc::smem_u32(sX + i * 16384), b0 = tc::smem_u32(sW + s * FWD_BLOCK + W2_BYTES);
+        // ================= MMA issuer: the whole warp runs this code uniformly =================
+        const uint32_t idesc1 = tc::make_idesc(TM, CH, 0, 0);
+        const uint32_t idesc2 = tc::make_idesc(TM, DP, 0, 0);
+        const uint64_t w_desc0 = tc::make_desc_sw128(tc::smem_u32(sW), 16, 1024);     // stage 0, W2c image
+        uint32_t it = 0, q = 0;
+        uint32_t hcount[2] = {0, 0};
+        for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++q) {
+            // prologue: GEMM1 of chunk 0 for both tiles
+            tc::mbar_wait(&bars.w_full[it % STAGES], (it / STAGES) & 1);
 #pragma unroll
-                    for (int ks = 0; ks < DP / 16; ++ks)
-                        tc::mma_ss(tmem + 128 + 128 * i, tc::make_desc_sw128(a0 + ks * 32, 16, 1024),
-                                   tc::make_desc_sw128(b0 + ks * 32, 16, 1024), idesc1, ks > 0);
-                    tc::mma_commit(&bars.s_full[i]);
-                };
-                // prologue: GEMM1 of chunk 0 for both tiles
-                tc::mbar_wait(&bars.w_full[it % STAGES], (it / STAGES) & 1);
+            for (int i = 0; i < 2; ++i) {
+                tc::mbar_wait(&bars.x_full[i], q & 1);
+                tc::tc_fence_after();
+                issue_gemm1(tmem + COL_S + 128 * i, tmem + COL_X + 32 * i,
+                            w_desc0 + (uint64_t)((it % STAGES) * (FWD_BLOCK >> 4) + (W2_BYTES >> 4)), idesc1);
+                commit_to(&bars.s_full[i]);
+            }
+            for (int c = 0; c < NC; ++c, ++it) {
+                const uint32_t s = it % STAGES;
+                const uint64_t w2_desc = w_desc0 + (uint64_t)(s * (FWD_BLOCK >> 4));
+                if (c + 1 < NC) tc::mbar_wait(&bars.w_full[(it + 1) % STAGES], ((it + 1) / STAGES) & 1);
+                const uint64_t w1_next = w_desc0 + (uint64_t)(((it + 1) % STAGES) * (FWD_BLOCK >> 4) + (W2_BYTES >> 4));
+#pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    tc::mbar_wait(&bars.x_full[i], q & 1);
+                    tc::mbar_wait(&bars.h_full[i], hcount[i] & 1);   // H_i(c) in TMEM (over S_i)
+                    ++hcount[i];
+                    if (c == 0 && q > 0) tc::mbar_wait(&bars.y_free[i], (q - 1) & 1);
                     tc::tc_fence_after();
-                    g1(i, it);
-                }
-                for (int c = 0; c < NC; ++c, ++it) {
-                    const uint32_t s = it % STAGES;
-                    if (c + 1 < NC) tc::mbar_wait(&bars.w_full[(it + 1) % STAGES], ((it + 1) / STAGES) & 1);
-                    for (int i = 0; i < 2; ++i) {
-                        tc::mbar_wait(&bars.h_full[i], hcount[i] & 1);   // H_i(c) in TMEM, S_i consumed
-                        ++hcount[i];
-                        if (c == 0 && q > 0) tc::mbar_wait(&bars.y_free[i], (q - 1) & 1);
-                        tc::tc_fence_after();
-                        const uint32_t b0 = tc::smem_u32(sW + s * FWD_BLOCK);
-#pragma unroll
-                        for (int ks = 0; ks < CH / 16; ++ks)
-                            tc::mma_ts(tmem + 64 * i, tmem + 384 + 64 * i + ks * 8,
-                                       tc::make_desc_sw128(b0 + (ks >> 2) * 8192 + (ks & 3) * 32, 16, 1024), idesc2,
-                                       (c > 0 || ks > 0));
-                        tc::mma_commit(&bars.h_free[i]);
-                        if (c == NC - 1) tc::mma_commit(&bars.y_full[i]);
-                        if (c + 1 < NC) {
-                            g1(i, it + 1);
-                            if (c + 2 == NC) tc::mma_commit(&bars.x_free[i]);   // last GEMM1 of this pair read X_i
-                        }
+                    issue_gemm2(tmem + COL_Y + 64 * i, tmem + COL_S + 128 * i, w2_desc, idesc2, c > 0);
+                    if (c == NC - 1) commit_to(&bars.y_full[i]);
+                    if (c + 1 < NC) {
+                        // the tensor pipe executes MMAs in issue order: this GEMM1 overwrites S_i (and the H_i aliased
+                        // over it) only after the GEMM2 above has consumed H_i
+                        issue_gemm1(tmem + COL_S + 128 * i, tmem + COL_X + 32 * i, w1_next, idesc1);
+                        commit_to(&bars.s_full[i]);
+                    } else {
+                        commit_to(&bars.x_free[i]);                  // last GEMM1 of this pair has read X_i
                     }
-                    if (NC == 1) { tc::mma_commit(&bars.x_free[0]); tc::mma_commit(&bars.x_free[1]); }
-                    tc::mma_commit(&bars.w_empty[s]);                 // chunk c weights fully consumed
                 }
+                commit_to(&bars.w_empty[s]);                         // chunk c weights fully consumed
             }
         }
     } else if (warp >= 4) {
-        // ================= epilogue groups =================
-        const int i = (warp - 4) >> 2;                  // tile within the pair
+        // ================= epilogue groups: 8 warps per tile = two 64-column halves x four TMEM lane quarters =====
+        const int i = (warp - 4) >> 3;                  // tile within the pair
+        const int wg = ((warp - 4) >> 2) & 1;           // column half of the 128-wide chunk
         const int wq = warp & 3;                        // TMEM lane quarter
-        const int tg = (warp - 4 - 4 * i) * 32 + lane;  // thread index within the group (0..127) == row in tile
+        const int tr = wq * 32 + lane;                  // row in tile
         const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-        const float scale2_unused = 1.0f;
-        (void)scale2_unused;
-        uint32_t q = 0, scount = 0, hfree_count = 0;
+        uint32_t q = 0, scount = 0;
         for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++q) {
             const int64_t row0 = pair * (2 * TM) + (int64_t)i * TM;
-            // ---- (a) X tile: fp32 rows -> bf16 K-major swizzled tile
-            if (q > 0) tc::mbar_wait(&bars.x_free[i], (q - 1) & 1);
-            {
-                uint8_t* xt = sX + i * 16384;
-                if (p.d == DP) {
-                    float4 v[16];           // 16 independent 128-bit loads in flight per thread
+            const int64_t row = row0 + tr;
+            // ---- (a) X tile: the first warpgroup converts one fp32 row per thread to packed bf16 in tensor memory
+            if (wg == 0) {
+                if (q > 0) tc::mbar_wait(&bars.x_free[i], (q - 1) & 1);
+                uint32_t xp[32];
+                if (p.d == DP && row < p.M) {
+                    const float4* src = reinterpret_cast<const float4*>(p.y1 + row * DP);
+                    float4 v[16];
 #pragma unroll
-                    for (int itx = 0; itx < 16; ++itx) {
-                        const int e = itx * 128 + tg;
-                        const int r = e >> 4, c4 = e & 15;
-                        v[itx] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (row0 + r < p.M) v[itx] = __ldg(reinterpret_cast<const float4*>(p.y1 + (row0 + r) * DP) + c4);
-                    }
+                    for (int u = 0; u < 16; ++u) v[u] = __ldg(src + u);
 #pragma unroll
-                    for (int itx = 0; itx < 16; ++itx) {
-                        const int e = itx * 128 + tg;
-                        const int r = e >> 4, c4 = e & 15;
-                        uint2 w;
-                        w.x = tc::pack_bf16(v[itx].x, v[itx].y);
-                        w.y = tc::pack_bf16(v[itx].z, v[itx].w);
-                        *reinterpret_cast<uint2*>(xt + tc::sw128_offset(r, c4 * 4)) = w;
+                    for (int u = 0; u < 16; ++u) {
+                        xp[2 * u] = epi::cvt2(v[u].x, v[u].y);
+                        xp[2 * u + 1] = epi::cvt2(v[u].z, v[u].w);
                     }
                 } else {
-                    for (int e = tg; e < TM * DP; e += 128) {
-                        const int r = e / DP, k = e % DP;
-                        const float v = (row0 + r < p.M && k < p.d) ? p.y1[(row0 + r) * p.d + k] : 0.0f;
-                        *reinterpret_cast<__nv_bfloat16*>(xt + tc::sw128_offset(r, k)) = __float2bfloat16(v);
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) {
+                        const float a = (row < p.M && 2 * u < p.d) ? p.y1[row * p.d + 2 * u] : 0.0f;
+                        const float b = (row < p.M && 2 * u + 1 < p.d) ? p.y1[row * p.d + 2 * u + 1] : 0.0f;
+                        xp[u] = epi::cvt2(a, b);
                     }
                 }
-                tc::fence_proxy_async();
-                tc::mbar_arrive(&bars.x_full[i]);
+                tc::tmem_st32(tmem + lane_base + COL_X + 32 * i, xp);
+                tc::tmem_st_wait();
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bars.x_full[i]);
             }
-            const int64_t row = row0 + tg;
-            // ---- (b) per chunk: S -> H
+            // ---- (b) per chunk: this thread turns 64 columns of its S row into packed bf16 H (written over them)
             for (int c = 0; c < NC; ++c) {
                 tc::mbar_wait(&bars.s_full[i], scount & 1);
                 ++scount;
                 tc::tc_fence_after();
-                uint32_t hp[64];
+                uint32_t hp[32];
+                const uint32_t s_addr = tmem + lane_base + COL_S + 128 * i + 64 * wg;
 #pragma unroll
-                for (int pc = 0; pc < 4; ++pc) {
+                for (int pc = 0; pc < 2; ++pc) {
                     uint32_t v[32];
-                    tc::tmem_ld32(tmem + lane_base + 128 + 128 * i + 32 * pc, v);
-                    uint32_t keep = 0xFFFFFFFFu;
-                    if (p.thr) keep = rng_keep_word(p.keys2, (uint64_t)row * (uint64_t)(p.ff >> 5) + (uint64_t)(4 * c + pc), p.thr);
-                    const float* bb = sB1 + c * CH + 32 * pc;
+                    tc::tmem_ld32(s_addr + 32 * pc, v);
+                    uint32_t km[16];
+                    if (p.thr)
+                        epi::keep_masks16(rng_keep_word_lo(p.keys2, (uint64_t)row * (uint64_t)(p.ff >> 5) + (uint64_t)(4 * c + 2 * wg + pc),
+                                                           p.thr, p.low), km);
+                    const uint4* bb = reinterpret_cast<const uint4*>(sB1h + ((c * CH + 64 * wg + 32 * pc) >> 1));
                     tc::tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        float a = fmaxf(__uint_as_float(v[j]) + bb[j], 0.0f);
-                        float b = fmaxf(__uint_as_float(v[j + 1]) + bb[j + 1], 0.0f);
-                        a = ((keep >> j) & 1u) ? a : 0.0f;
-                        b = ((keep >> (j + 1)) & 1u) ? b : 0.0f;
-                        hp[pc * 16 + (j >> 1)] = tc::pack_bf16(a, b);
-                    }
-                }
-                if (hfree_count > 0) tc::mbar_wait(&bars.h_free[i], (hfree_count - 1) & 1);   // GEMM2 of the previous chunk done with H_i
-                ++hfree_count;
-                {
-                    uint32_t lo[32], hi[32];
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const uint4 b4 = bb[q4];
+                        const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        lo[j] = hp[j];
-                        hi[j] = hp[32 + j];
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = 4 * q4 + u;
+                            uint32_t h2 = epi::relu_bias2(epi::cvt2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bw[u]);
+                            if (p.thr) h2 &= km[j];
+                            hp[pc * 16 + j] = h2;
+                        }
                     }
-                    tc::tmem_st32(tmem + lane_base + 384 + 64 * i, lo);
-                    tc::tmem_st32(tmem + lane_base + 384 + 64 * i + 32, hi);
                 }
+                tc::tmem_st32(s_addr, hp);             // H columns [64*wg, 64*wg + 32) of the S_i region: only this thread's own S data lived there
                 tc::tmem_st_wait();
                 tc::tc_fence_before();
-                tc::mbar_arrive(&bars.h_full[i]);
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bars.h_full[i]);
             }
+            if (wg != 0) continue;                      // the per-pair output epilogue is done by one warpgroup per tile
             // ---- (c) Y -> z, LayerNorm statistics, xnext
             tc::mbar_wait(&bars.y_full[i], q & 1);
             tc::tc_fence_after();
             {
                 uint32_t y0[32], y1r[32];
-                tc::tmem_ld32(tmem + lane_base + 64 * i, y0);
-                tc::tmem_ld32(tmem + lane_base + 64 * i + 32, y1r);
+                tc::tmem_ld32(tmem + lane_base + COL_Y + 64 * i, y0);
+                tc::tmem_ld32(tmem + lane_base + COL_Y + 64 * i + 32, y1r);
                 tc::tmem_ld_wait();
                 tc::tc_fence_before();
-                tc::mbar_arrive(&bars.y_free[i]);
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bars.y_free[i]);
                 if (row < p.M) {
                     float zv[DP];
-                    uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
                     const bool fast = (p.d == DP);
-                    if (p.thr && fast) {
-                        k0 = rng_keep_word(p.keys3, (uint64_t)row * 2ull, p.thr);
-                        k1 = rng_keep_word(p.keys3, (uint64_t)row * 2ull + 1ull, p.thr);
-                    }
-                    float sum = 0.0f;
-#pragma unroll
-                    for (int j = 0; j < DP; ++j) {
-                        float f = __uint_as_float(j < 32 ? y0[j] : y1r[j - 32]) + sB2[j];
-                        float mult;
-                        if (fast) mult = (((j < 32 ? k0 : k1) >> (j & 31)) & 1u) ? p.scale3 : 0.0f;
-                        else mult = (j < p.d) ? rng_dropout_mult(p.keys3, (uint64_t)row * (uint64_t)p.d + (uint64_t)j, p.thr, p.scale3) : 0.0f;
-                        if (!p.thr) mult = 1.0f;
-                        zv[j] = (j < p.d) ? f * mult : 0.0f;
-                    }
-                    if (fast) {   // residual: 128-bit loads of the fp32 input row
+                    if (fast) {
+                        uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
+                        if (p.thr) {
+                            k0 = rng_keep_word_lo(p.keys3, (uint64_t)row * 2ull, p.thr, p.low);
+                            k1 = rng_keep_word_lo(p.keys3, (uint64_t)row * 2ull + 1ull, p.thr, p.low);
+                        }
+                        const float sc = p.thr ? p.scale3 : 1.0f;
                         const float4* rr = reinterpret_cast<const float4*>(p.y1 + row * DP);
 #pragma unroll
                         for (int j = 0; j < DP; j += 4) {
                             const float4 r4 = __ldg(rr + (j >> 2));
-                            zv[j] += r4.x; zv[j + 1] += r4.y; zv[j + 2] += r4.z; zv[j + 3] += r4.w;
+                            const float res[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int jj = j + u;
+                                const float f = __uint_as_float(jj < 32 ? y0[jj] : y1r[jj - 32]) + sB2[jj];
+                                const float mult = (((jj < 32 ? k0 : k1) >> (jj & 31)) & 1u) ? sc : 0.0f;
+                                zv[jj] = res[u] + f * mult;
+                            }
                         }
                     } else {
-#pragma unroll
-                        for (int j = 0; j < DP; ++j)
-                            if (j < p.d) zv[j] += __ldg(p.y1 + row * p.d + j);
+#pragma unroll 1
+                        for (int j = 0; j < p.d; ++j) {
+                            const float f = __uint_as_float(j < 32 ? y0[j] : y1r[j - 32]) + sB2[j];
+                            const float mult = rng_dropout_mult(p.keys3, (uint64_t)row * (uint64_t)p.d + (uint64_t)j, p.thr, p.scale3);
+                            zv[j] = __ldg(p.y1 + row * p.d + j) + f * mult;
+                        }
+                        for (int j = p.d; j < DP; ++j) zv[j] = 0.0f;
                     }
+                    float sum = 0.0f;
 #pragma unroll
                     for (int j = 0; j < DP; ++j) sum += zv[j];
                     const float inv_d = 1.0f / (float)p.d;
@@ -348,12 +373,11 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams
                                                          (zv[j + 3] - mean) * rstd * sG[j + 3] + sG[DP + j + 3]);
                         }
                     } else {
-#pragma unroll
-                        for (int j = 0; j < DP; ++j)
-                            if (j < p.d) {
-                                p.z[row * p.d + j] = zv[j];
-                                if (p.xnext) p.xnext[row * p.d + j] = (zv[j] - mean) * rstd * sG[j] + sG[DP + j];
-                            }
+#pragma unroll 1
+                        for (int j = 0; j < p.d; ++j) {
+                            p.z[row * p.d + j] = zv[j];
+                            if (p.xnext) p.xnext[row * p.d + j] = (zv[j] - mean) * rstd * sG[j] + sG[DP + j];
+                        }
                     }
                 }
             }
@@ -367,6 +391,11 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams
 size_t packed_bytes(int ff) { return (size_t)(ff / CH) * CHUNK_BYTES + (size_t)(ff + DP) * sizeof(float); }
 
 }  // namespace
+
+extern "C" int u2gnn_ffn_tc_debug(int flags) {
+    (void)flags;                       // experiment switches were removed after the pipeline study (profiles/README.md)
+    return U2GNN_OK;
+}
 
 extern "C" size_t u2gnn_ffn_tc_packed_bytes(int d, int ff) {
     if (d < 1 || d > DP || ff < CH || ff % CH) return 0;
@@ -397,9 +426,10 @@ extern "C" int u2gnn_ffn_tc_fwd(const float* y1, int64_t M, int d, int ff, const
     p.keys2 = rng_keys(seed, stream_hidden);
     p.keys3 = rng_keys(seed, stream_out);
     p.thr = thr;
+    p.low = rng_thr_low(thr);
     p.scale3 = thr ? rng_keep_scale(thr) : 1.0f;
     p.gamma = gamma; p.beta = beta; p.z = z; p.stats = stats; p.xnext = xnext;
-    const size_t smem = 1024 + 2 * 16384 + (size_t)STAGES * FWD_BLOCK + (size_t)(ff + 3 * DP) * sizeof(float);
+    const size_t smem = 1024 + (size_t)STAGES * FWD_BLOCK + (size_t)(ff / 2 + 3 * DP) * sizeof(float);
     if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
     cudaFuncSetAttribute(ffn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int64_t n_pairs = (M + 2 * TM - 1) / (2 * TM);

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "rng.cuh"
 #include "tc_common.cuh"
+#include "ffn_epi.cuh"
 
 namespace {
 
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const DgradPa
     uint8_t* sX = smem;                          // 2 x 16 KB
     uint8_t* sF = smem + 2 * 16384;              // 2 x 16 KB
     uint8_t* sW = smem + 4 * 16384;              // DG_STAGES x 48 KB
-    float* sB1 = reinterpret_cast<float*>(sW + DG_STAGES * DG_BLOCK);
+    uint32_t* sB1h = reinterpret_cast<uint32_t*>(sW + DG_STAGES * DG_BLOCK);   // b1 as packed bf16 pairs
     __shared__ DgradBars bars;
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const DgradPa
     if (warp == 2) tc::tmem_alloc<512>(&tmem_slot);
     {
         const float* b1g = packed_b1(p.packed, p.ff);
-        for (int e = threadIdx.x; e < p.ff; e += kThreads) sB1[e] = b1g[e];
+        for (int e = threadIdx.x; e < p.ff / 2; e += kThreads) sB1h[e] = epi::cvt2(b1g[2 * e], b1g[2 * e + 1]);
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -205,19 +206,33 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const DgradPa
                 tc::mbar_wait(&bars.s_full[i], scount & 1);
                 ++scount;
                 tc::tc_fence_after();
-                uint32_t bits[4];
+                uint32_t msk[64];          // per pair: 0xFFFF where relu'(S + b1) = 1 and the hidden dropout kept the unit
+                {
+                    uint32_t v[2][32];
+                    const uint32_t r_addr = tmem + lane_base + 128 + 128 * i;
+                    tc::tmem_ld32(r_addr, v[0]);
 #pragma unroll
-                for (int pc = 0; pc < 4; ++pc) {
-                    uint32_t v[32];
-                    tc::tmem_ld32(tmem + lane_base + 128 + 128 * i + 32 * pc, v);
-                    uint32_t keep = 0xFFFFFFFFu;
-                    if (p.thr) keep = rng_keep_word(p.keys2, (uint64_t)row * (uint64_t)(p.ff >> 5) + (uint64_t)(4 * c + pc), p.thr);
-                    const float* bb = sB1 + c * CH + 32 * pc;
-                    tc::tmem_ld_wait();
-                    uint32_t pos = 0;
+                    for (int pc = 0; pc < 4; ++pc) {
+                        tc::tmem_ld_wait();
+                        if (pc < 3) tc::tmem_ld32(r_addr + 32 * (pc + 1), v[(pc + 1) & 1]);
+                        uint32_t km[16];
+                        if (p.thr)
+                            epi::keep_masks16(rng_keep_word(p.keys2, (uint64_t)row * (uint64_t)(p.ff >> 5) + (uint64_t)(4 * c + pc), p.thr), km);
+                        const uint4* bb = reinterpret_cast<const uint4*>(sB1h + ((c * CH + 32 * pc) >> 1));
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) pos |= (__float_as_int(__uint_as_float(v[j]) + bb[j]) > 0 ? 1u : 0u) << j;
-                    bits[pc] = pos & keep;
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            const uint4 b4 = bb[q4];
+                            const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int j = 4 * q4 + u;
+                                uint32_t m = epi::gt0_mask2(epi::relu_bias2(
+                                    epi::cvt2(__uint_as_float(v[pc & 1][2 * j]), __uint_as_float(v[pc & 1][2 * j + 1])), bw[u]));
+                                if (p.thr) m &= km[j];
+                                msk[pc * 16 + j] = m;
+                            }
+                        }
+                    }
                 }
                 tc::tc_fence_before();
                 tc::mbar_arrive(&bars.a_done[i]);
@@ -226,17 +241,17 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const DgradPa
                 ++dcount;
                 tc::tc_fence_after();
                 uint32_t hp[64];
+                {
+                    uint32_t v[2][32];
+                    const uint32_t r_addr = tmem + lane_base + 128 + 128 * i;
+                    tc::tmem_ld32(r_addr, v[0]);
 #pragma unroll
-                for (int pc = 0; pc < 4; ++pc) {
-                    uint32_t v[32];
-                    tc::tmem_ld32(tmem + lane_base + 128 + 128 * i + 32 * pc, v);
-                    tc::tmem_ld_wait();
-                    const uint32_t b = bits[pc];
+                    for (int pc = 0; pc < 4; ++pc) {
+                        tc::tmem_ld_wait();
+                        if (pc < 3) tc::tmem_ld32(r_addr + 32 * (pc + 1), v[(pc + 1) & 1]);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const float a0 = ((b >> j) & 1u) ? __uint_as_float(v[j]) : 0.0f;
-                        const float a1 = ((b >> (j + 1)) & 1u) ? __uint_as_float(v[j + 1]) : 0.0f;
-                        hp[pc * 16 + (j >> 1)] = tc::pack_bf16(a0, a1);
+                        for (int j = 0; j < 16; ++j)
+                            hp[pc * 16 + j] = epi::cvt2(__uint_as_float(v[pc & 1][2 * j]), __uint_as_float(v[pc & 1][2 * j + 1])) & msk[pc * 16 + j];
                     }
                 }
                 if (pfree_count > 0) tc::mbar_wait(&bars.p_free[i], (pfree_count - 1) & 1);
@@ -354,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const WgradPa
     uint8_t* sP = sH + 32768;                              // 32 KB
     uint8_t* sW = sP + 32768;                              // 32 KB: [W1c | W2Tc]
     uint8_t* sOnes = sW + 32768;                           // 2 KB of bf16 1.0 (layout-invariant B operand)
-    float* sB1 = reinterpret_cast<float*>(sOnes + 2048);   // 128 floats
+    uint32_t* sB1h = reinterpret_cast<uint32_t*>(sOnes + 2048);   // chunk bias as 64 packed bf16 pairs
     __shared__ WgradBars bars;
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -383,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const WgradPa
     if (warp == 2) tc::tmem_alloc<512>(&tmem_slot);
     {
         const float* b1g = packed_b1(p.packed, p.ff) + c * CH;
-        for (int e = threadIdx.x; e < CH; e += kThreads) sB1[e] = b1g[e];
+        for (int e = threadIdx.x; e < CH / 2; e += kThreads) sB1h[e] = epi::cvt2(b1g[2 * e], b1g[2 * e + 1]);
         for (int e = threadIdx.x; e < 2048 / 4; e += kThreads) reinterpret_cast<uint32_t*>(sOnes)[e] = 0x3F803F80u;
     }
     tc::fence_proxy_async();
@@ -473,21 +488,31 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const WgradPa
                 tc::mbar_wait(&bars.s_full[i], k & 1);
                 tc::tc_fence_after();
                 uint32_t hreg[64], preg[64];
+                {
+                    uint32_t v[2][32];
+                    const uint32_t r_addr = tmem + lane_base + 128 * i;
+                    tc::tmem_ld32(r_addr, v[0]);
 #pragma unroll
-                for (int pc = 0; pc < 4; ++pc) {
-                    uint32_t v[32];
-                    tc::tmem_ld32(tmem + lane_base + 128 * i + 32 * pc, v);
-                    uint32_t keep = 0xFFFFFFFFu;
-                    if (p.thr) keep = rng_keep_word(p.keys2, (uint64_t)row * (uint64_t)(p.ff >> 5) + (uint64_t)(4 * c + pc), p.thr);
-                    const float* bb = sB1 + 32 * pc;
-                    tc::tmem_ld_wait();
+                    for (int pc = 0; pc < 4; ++pc) {
+                        tc::tmem_ld_wait();
+                        if (pc < 3) tc::tmem_ld32(r_addr + 32 * (pc + 1), v[(pc + 1) & 1]);
+                        uint32_t km[16];
+                        if (p.thr)
+                            epi::keep_masks16(rng_keep_word(p.keys2, (uint64_t)row * (uint64_t)(p.ff >> 5) + (uint64_t)(4 * c + pc), p.thr), km);
+                        const uint4* bb = reinterpret_cast<const uint4*>(sB1h + 16 * pc);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        float a = fmaxf(__uint_as_float(v[j]) + bb[j], 0.0f);
-                        float b = fmaxf(__uint_as_float(v[j + 1]) + bb[j + 1], 0.0f);
-                        a = ((keep >> j) & 1u) ? a : 0.0f;
-                        b = ((keep >> (j + 1)) & 1u) ? b : 0.0f;
-                        hreg[pc * 16 + (j >> 1)] = tc::pack_bf16(a, b);
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            const uint4 b4 = bb[q4];
+                            const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int j = 4 * q4 + u;
+                                uint32_t h2 = epi::relu_bias2(
+                                    epi::cvt2(__uint_as_float(v[pc & 1][2 * j]), __uint_as_float(v[pc & 1][2 * j + 1])), bw[u]);
+                                if (p.thr) h2 &= km[j];
+                                hreg[pc * 16 + j] = h2;
+                            }
+                        }
                     }
                 }
                 tc::tc_fence_before();
@@ -495,17 +520,18 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const WgradPa
                 // ---- D -> dPre = D * [H > 0]
                 tc::mbar_wait(&bars.d_full[i], k & 1);
                 tc::tc_fence_after();
+                {
+                    uint32_t v[2][32];
+                    const uint32_t r_addr = tmem + lane_base + 128 * i;
+                    tc::tmem_ld32(r_addr, v[0]);
 #pragma unroll
-                for (int pc = 0; pc < 4; ++pc) {
-                    uint32_t v[32];
-                    tc::tmem_ld32(tmem + lane_base + 128 * i + 32 * pc, v);
-                    tc::tmem_ld_wait();
+                    for (int pc = 0; pc < 4; ++pc) {
+                        tc::tmem_ld_wait();
+                        if (pc < 3) tc::tmem_ld32(r_addr + 32 * (pc + 1), v[(pc + 1) & 1]);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const uint32_t hh = hreg[pc * 16 + (j >> 1)];
-                        const float a0 = (hh & 0x7FFFu) ? __uint_as_float(v[j]) : 0.0f;       // H >= 0: nonzero <=> positive
-                        const float a1 = (hh & 0x7FFF0000u) ? __uint_as_float(v[j + 1]) : 0.0f;
-                        preg[pc * 16 + (j >> 1)] = tc::pack_bf16(a0, a1);
+                        for (int j = 0; j < 16; ++j)
+                            preg[pc * 16 + j] = epi::cvt2(__uint_as_float(v[pc & 1][2 * j]), __uint_as_float(v[pc & 1][2 * j + 1])) &
+                                                epi::gt0_mask2(hreg[pc * 16 + j]);
                     }
                 }
                 // ---- H, dPre -> shared memory (MN-major A operands of the weight-gradient GEMMs)
@@ -574,7 +600,7 @@ extern "C" int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const float* d
         p.packed = static_cast<const uint8_t*>(packed);
         p.keys2 = rng_keys(seed, stream_hidden);
         p.thr = thr;
-        const size_t smem = 1024 + 4 * 16384 + (size_t)DG_STAGES * DG_BLOCK + (size_t)ff * sizeof(float);
+        const size_t smem = 1024 + 4 * 16384 + (size_t)DG_STAGES * DG_BLOCK + (size_t)(ff / 2) * sizeof(float);
         if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
         cudaFuncSetAttribute(ffn_tc_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int64_t n_pairs = (M + 2 * TM - 1) / (2 * TM);

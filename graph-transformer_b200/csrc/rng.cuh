@@ -61,6 +61,28 @@ __host__ __device__ __forceinline__ uint32_t rng_keep_word(RngKeys k, uint64_t g
     return gt | eq;
 }
 
+// same result as rng_keep_word with the lowest set bit of thr (`low`) precomputed by the caller; thr = 128
+// (p = 0.5, the encoder's hard-coded dropout) needs a single word
+__host__ __device__ __forceinline__ int rng_thr_low(int thr) {
+    int low = 0;
+    while (thr && ((thr >> low) & 1) == 0) ++low;
+    return low;
+}
+__device__ __forceinline__ uint32_t rng_keep_word_lo(RngKeys k, uint64_t g, int thr, int low) {
+    if (low == 7) return rng_word(k, g, 7u);
+    uint32_t gt = 0u, eq = 0xFFFFFFFFu;
+    for (int j = 7; j >= low; --j) {
+        const uint32_t w = rng_word(k, g, (uint32_t)j);
+        if ((thr >> j) & 1) {
+            eq &= w;
+        } else {
+            gt |= eq & w;
+            eq &= ~w;
+        }
+    }
+    return gt | eq;
+}
+
 __host__ __device__ __forceinline__ float rng_keep_scale(int thr) { return 256.0f / (256.0f - (float)thr); }
 
 // scalar query: multiplier (0 or scale) for element e.  thr == 0 -> 1.

@@ -220,11 +220,18 @@ int pick_warps(size_t floats_per_warp) {
 
 }  // namespace
 
+// thread-per-row kernels for the common shapes (seqattn_rows.cu)
+int seqattn_rows_try_fwd(const float* qkv, int64_t B, int S, int Sq, int d, uint64_t seed, uint32_t rng_stream, int thr,
+                         float* ctx, cudaStream_t st);
+int seqattn_rows_try_bwd(const float* qkv, const float* dctx, int64_t B, int S, int Sq, int d, uint64_t seed,
+                         uint32_t rng_stream, int thr, float* dqkv, cudaStream_t st);
+
 extern "C" int u2gnn_seqattn_fwd(const float* qkv, int64_t B, int S, int Sq, int d, uint64_t seed, uint32_t rng_stream,
                                  int thr, float* ctx, u2gnn_stream_t stream) {
     if (!qkv || !ctx || B < 0 || d <= 0) return U2GNN_EINVAL;
     if (S < 1 || S > 32 || (Sq != S && Sq != 1) || thr < 0 || thr > 255) return U2GNN_EINVAL;
     if (B == 0) return U2GNN_OK;
+    if (seqattn_rows_try_fwd(qkv, B, S, Sq, d, seed, rng_stream, thr, ctx, as_stream(stream))) { U2GNN_CHECK_LAUNCH(); }
     const int P = d | 1;
     const size_t per_warp = (size_t)(Sq + 2 * S) * P;
     const int warps = pick_warps(per_warp);
@@ -242,6 +249,7 @@ extern "C" int u2gnn_seqattn_bwd(const float* qkv, const float* dctx, int64_t B,
     if (!qkv || !dctx || !dqkv || B < 0 || d <= 0) return U2GNN_EINVAL;
     if (S < 1 || S > 32 || (Sq != S && Sq != 1) || thr < 0 || thr > 255) return U2GNN_EINVAL;
     if (B == 0) return U2GNN_OK;
+    if (seqattn_rows_try_bwd(qkv, dctx, B, S, Sq, d, seed, rng_stream, thr, dqkv, as_stream(stream))) { U2GNN_CHECK_LAUNCH(); }
     const int P = d | 1;
     const size_t per_warp = (size_t)(2 * Sq + 4 * S) * P;
     const int warps = pick_warps(per_warp);

@@ -1,0 +1,275 @@
+// Short-sequence self-attention, thread-per-row formulation (attn_axis="neighbors", every query row live).
+//
+// seqattn.cu's warp-per-node kernels are latency-bound (one accumulator chain per lane, 17 of 32 lanes busy).
+// Here a CTA stages K and V (and, in the backward, Q and the incoming gradient) of a few whole node sequences in
+// shared memory and every thread owns one query row: the q.k and p.v products are 64-wide register FMAs fed by
+// broadcast LDS.128, softmax runs inside the thread, and the key-side gradients (dk, dv) are a second phase with
+// one thread per key row reading the per-node ds / p matrices from shared memory.  Same arithmetic and dropout
+// stream as seqattn.cu (nn.MultiheadAttention, one head); fp32 throughout.
+#include "common.cuh"
+#include "rng.cuh"
+
+namespace {
+
+struct AttnRng {
+    RngKeys keys;
+    int thr;
+    float scale;
+};
+
+constexpr int PP = 33;   // pitch of the per-row score / probability scratch (S <= 32)
+
+template <int D>
+__device__ __forceinline__ float dot_row(const float (&a)[D], const float* __restrict__ b) {
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll
+    for (int c = 0; c < D; c += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(b + c);
+        acc0 = fmaf(a[c], v.x, acc0);
+        acc1 = fmaf(a[c + 1], v.y, acc1);
+        acc2 = fmaf(a[c + 2], v.z, acc2);
+        acc3 = fmaf(a[c + 3], v.w, acc3);
+    }
+    return (acc0 + acc1) + (acc2 + acc3);
+}
+
+template <int D>
+__device__ __forceinline__ void axpy_row(float (&acc)[D], float s, const float* __restrict__ b) {
+#pragma unroll
+    for (int c = 0; c < D; c += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(b + c);
+        acc[c] = fmaf(s, v.x, acc[c]);
+        acc[c + 1] = fmaf(s, v.y, acc[c + 1]);
+        acc[c + 2] = fmaf(s, v.z, acc[c + 2]);
+        acc[c + 3] = fmaf(s, v.w, acc[c + 3]);
+    }
+}
+
+// cooperative copy of `rows` rows of width D (fp32) from a strided global matrix into padded shared memory
+template <int D, int NT>
+__device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ src, int64_t src_ld, int rows, int tid) {
+    constexpr int P = D + 4;
+    for (int e = tid; e < rows * (D / 4); e += NT) {
+        const int r = e / (D / 4), c4 = e % (D / 4);
+        *reinterpret_cast<float4*>(dst + r * P + 4 * c4) = __ldg(reinterpret_cast<const float4*>(src + r * src_ld) + c4);
+    }
+}
+
+template <int D, int NT>
+__global__ void __launch_bounds__(NT) seqattn_rows_fwd_kernel(const float* __restrict__ qkv, int64_t B, int S, AttnRng rng,
+                                                              float* __restrict__ ctx, int NB) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int P = D + 4;
+    const int max_rows = NB * S;
+    float* Ks = sm;
+    float* Vs = Ks + max_rows * P;
+    float* Ps = Vs + max_rows * P;          // [max_rows][PP]
+    const int tid = threadIdx.x;
+    const float qscale = sqrtf(1.0f / (float)D);
+    const int64_t n_tiles = (B + NB - 1) / NB;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t node0 = tile * NB;
+        const int nodes = (int)((B - node0 < NB) ? B - node0 : NB);
+        const int rows = nodes * S;
+        const float* base = qkv + node0 * S * 3 * D;
+        __syncthreads();
+        stage_rows<D, NT>(Ks, base + D, 3 * D, rows, tid);
+        stage_rows<D, NT>(Vs, base + 2 * D, 3 * D, rows, tid);
+        float q[D];
+        if (tid < rows) {
+#pragma unroll
+            for (int c = 0; c < D; c += 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(base + (int64_t)tid * 3 * D + c));
+                q[c] = v.x * qscale; q[c + 1] = v.y * qscale; q[c + 2] = v.z * qscale; q[c + 3] = v.w * qscale;
+            }
+        }
+        __syncthreads();
+        if (tid < rows) {
+            const int node = tid / S, i = tid - node * S;
+            const float* kn = Ks + node * S * P;
+            const float* vn = Vs + node * S * P;
+            float* pr = Ps + tid * PP;
+            float m = -INFINITY;
+            for (int j = 0; j < S; ++j) {
+                const float s = dot_row<D>(q, kn + j * P);
+                pr[j] = s;
+                m = fmaxf(m, s);
+            }
+            float sum = 0.f;
+            for (int j = 0; j < S; ++j) {
+                const float e = expf(pr[j] - m);
+                pr[j] = e;
+                sum += e;
+            }
+            const float inv = 1.0f / sum;
+            const uint64_t ebase = (uint64_t)((node0 + node) * S + i) * (uint64_t)S;
+            float acc[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) acc[c] = 0.f;
+            for (int j = 0; j < S; ++j) {
+                const float pd = (pr[j] * inv) * rng_dropout_mult(rng.keys, ebase + (uint64_t)j, rng.thr, rng.scale);
+                axpy_row<D>(acc, pd, vn + j * P);
+            }
+            float4* out = reinterpret_cast<float4*>(ctx + ((node0 * S) + tid) * (int64_t)D);
+#pragma unroll
+            for (int c = 0; c < D; c += 4) out[c >> 2] = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+        }
+    }
+}
+
+template <int D, int NT>
+__global__ void __launch_bounds__(NT) seqattn_rows_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dctx,
+                                                              int64_t B, int S, AttnRng rng, float* __restrict__ dqkv,
+                                                              int NB) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int P = D + 4;
+    const int max_rows = NB * S;
+    float* Qs = sm;
+    float* Ks = Qs + max_rows * P;
+    float* Vs = Ks + max_rows * P;
+    float* Gs = Vs + max_rows * P;
+    float* Ps = Gs + max_rows * P;          // probabilities, then dropped probabilities  [max_rows][PP]
+    float* Ds = Ps + max_rows * PP;         // dP, then dS                                [max_rows][PP]
+    const int tid = threadIdx.x;
+    const float qscale = sqrtf(1.0f / (float)D);
+    const int64_t n_tiles = (B + NB - 1) / NB;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t node0 = tile * NB;
+        const int nodes = (int)((B - node0 < NB) ? B - node0 : NB);
+        const int rows = nodes * S;
+        const float* base = qkv + node0 * S * 3 * D;
+        __syncthreads();
+        stage_rows<D, NT>(Qs, base, 3 * D, rows, tid);
+        stage_rows<D, NT>(Ks, base + D, 3 * D, rows, tid);
+        stage_rows<D, NT>(Vs, base + 2 * D, 3 * D, rows, tid);
+        stage_rows<D, NT>(Gs, dctx + node0 * S * D, D, rows, tid);
+        __syncthreads();
+        float* gout = dqkv + (node0 * S + tid) * (int64_t)(3 * D);
+        const int node = tid / S, i = tid - node * S;
+        // ---- phase A: thread = query row.  p, dp, ds and dq
+        if (tid < rows) {
+            const float* kn = Ks + node * S * P;
+            const float* vn = Vs + node * S * P;
+            float* pr = Ps + tid * PP;
+            float* dr = Ds + tid * PP;
+            float a[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) a[c] = Qs[tid * P + c] * qscale;
+            float m = -INFINITY;
+            for (int j = 0; j < S; ++j) {
+                const float s = dot_row<D>(a, kn + j * P);
+                pr[j] = s;
+                m = fmaxf(m, s);
+            }
+            float sum = 0.f;
+            for (int j = 0; j < S; ++j) {
+                const float e = expf(pr[j] - m);
+                pr[j] = e;
+                sum += e;
+            }
+            const float inv = 1.0f / sum;
+#pragma unroll
+            for (int c = 0; c < D; ++c) a[c] = Gs[tid * P + c];          // a <- incoming gradient row
+            const uint64_t ebase = (uint64_t)((node0 + node) * S + i) * (uint64_t)S;
+            float tsum = 0.f;
+            for (int j = 0; j < S; ++j) {
+                const float mult = rng_dropout_mult(rng.keys, ebase + (uint64_t)j, rng.thr, rng.scale);
+                const float p = pr[j] * inv;
+                const float dp = dot_row<D>(a, vn + j * P) * mult;
+                dr[j] = dp;
+                tsum = fmaf(p, dp, tsum);
+                pr[j] = p;
+            }
+#pragma unroll
+            for (int c = 0; c < D; ++c) a[c] = 0.f;                       // a <- dq accumulator
+            for (int j = 0; j < S; ++j) {
+                const float p = pr[j];
+                const float ds = p * (dr[j] - tsum);
+                dr[j] = ds;
+                pr[j] = p * rng_dropout_mult(rng.keys, ebase + (uint64_t)j, rng.thr, rng.scale);
+                axpy_row<D>(a, ds, kn + j * P);
+            }
+            float4* o = reinterpret_cast<float4*>(gout);
+#pragma unroll
+            for (int c = 0; c < D; c += 4)
+                o[c >> 2] = make_float4(a[c] * qscale, a[c + 1] * qscale, a[c + 2] * qscale, a[c + 3] * qscale);
+        }
+        __syncthreads();
+        // ---- phase B: thread = key row j of its node.  dk_j = scale * sum_i ds_ij q_i ; dv_j = sum_i p~_ij g_i
+        if (tid < rows) {
+            const int j = i;
+            float dk[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) dk[c] = 0.f;
+            for (int ii = 0; ii < S; ++ii) axpy_row<D>(dk, Ds[(node * S + ii) * PP + j], Qs + (node * S + ii) * P);
+            float4* o = reinterpret_cast<float4*>(gout + D);
+#pragma unroll
+            for (int c = 0; c < D; c += 4)
+                o[c >> 2] = make_float4(dk[c] * qscale, dk[c + 1] * qscale, dk[c + 2] * qscale, dk[c + 3] * qscale);
+#pragma unroll
+            for (int c = 0; c < D; ++c) dk[c] = 0.f;                      // reuse as dv
+            for (int ii = 0; ii < S; ++ii) axpy_row<D>(dk, Ps[(node * S + ii) * PP + j], Gs + (node * S + ii) * P);
+            o = reinterpret_cast<float4*>(gout + 2 * D);
+#pragma unroll
+            for (int c = 0; c < D; c += 4) o[c >> 2] = make_float4(dk[c], dk[c + 1], dk[c + 2], dk[c + 3]);
+        }
+    }
+}
+
+template <int D>
+int launch_fwd(const float* qkv, int64_t B, int S, AttnRng rng, float* ctx, cudaStream_t st) {
+    constexpr int NT = 128;
+    const int NB = NT / S;
+    const size_t smem = ((size_t)2 * NB * S * (D + 4) + (size_t)NB * S * PP) * sizeof(float);
+    auto k = seqattn_rows_fwd_kernel<D, NT>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t tiles = (B + NB - 1) / NB;
+    const int grid = (int)(tiles < (int64_t)U2GNN_NUM_SMS * 2 ? tiles : (int64_t)U2GNN_NUM_SMS * 2);
+    k<<<grid, NT, smem, st>>>(qkv, B, S, rng, ctx, NB);
+    return 1;
+}
+
+template <int D>
+int launch_bwd(const float* qkv, const float* dctx, int64_t B, int S, AttnRng rng, float* dqkv, cudaStream_t st) {
+    constexpr int NT = 64;
+    const int NB = NT / S;
+    const size_t smem = ((size_t)4 * NB * S * (D + 4) + (size_t)2 * NB * S * PP) * sizeof(float);
+    auto k = seqattn_rows_bwd_kernel<D, NT>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t tiles = (B + NB - 1) / NB;
+    const int grid = (int)(tiles < (int64_t)U2GNN_NUM_SMS * 3 ? tiles : (int64_t)U2GNN_NUM_SMS * 3);
+    k<<<grid, NT, smem, st>>>(qkv, dctx, B, S, rng, dqkv, NB);
+    return 1;
+}
+
+AttnRng make_rng(uint64_t seed, uint32_t stream, int thr) {
+    AttnRng r;
+    r.keys = rng_keys(seed, stream);
+    r.thr = thr;
+    r.scale = thr ? rng_keep_scale(thr) : 1.0f;
+    return r;
+}
+
+bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
+
+}  // namespace
+
+// Internal dispatch used by u2gnn_seqattn_fwd / u2gnn_seqattn_bwd (seqattn.cu): returns 1 when the
+// thread-per-row kernels handled the call, 0 when the caller must use the warp-per-node kernels.
+int seqattn_rows_try_fwd(const float* qkv, int64_t B, int S, int Sq, int d, uint64_t seed, uint32_t rng_stream, int thr,
+                         float* ctx, cudaStream_t st) {
+    if (Sq != S || S < 2 || !aligned16(qkv) || !aligned16(ctx)) return 0;
+    const AttnRng rng = make_rng(seed, rng_stream, thr);
+    if (d == 64) return launch_fwd<64>(qkv, B, S, rng, ctx, st);
+    if (d == 32) return launch_fwd<32>(qkv, B, S, rng, ctx, st);
+    return 0;
+}
+
+int seqattn_rows_try_bwd(const float* qkv, const float* dctx, int64_t B, int S, int Sq, int d, uint64_t seed,
+                         uint32_t rng_stream, int thr, float* dqkv, cudaStream_t st) {
+    if (Sq != S || S < 2 || !aligned16(qkv) || !aligned16(dctx) || !aligned16(dqkv)) return 0;
+    const AttnRng rng = make_rng(seed, rng_stream, thr);
+    if (d == 64) return launch_bwd<64>(qkv, dctx, B, S, rng, dqkv, st);
+    if (d == 32) return launch_bwd<32>(qkv, dctx, B, S, rng, dqkv, st);
+    return 0;
+}

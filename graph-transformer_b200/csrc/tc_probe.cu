@@ -1,0 +1,81 @@
+// Micro-probe of tcgen05.mma issue/execute rates (one CTA): cycles per MMA for a given N, operand source
+// (SS / TS) and accumulator pattern (same accumulator vs rotating accumulators).  Used to size the fused
+// kernels' tiles; not part of the hot path.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+__global__ void __launch_bounds__(128) tc_probe_kernel(int N, int ts, int rotate, int count, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5;
+    for (int e = t; e < 65536 / 4; e += 128) reinterpret_cast<uint32_t*>(smem)[e] = 0x3C003C00u;
+    if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
+    if (t == 0) { tc::mbar_init(&bar, 1); tc::fence_barrier_init(); }
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (warp == 1 && rotate >= 2) {
+        // whole-warp uniform issue: descriptors stay in uniform registers, k-steps are immediate adds
+        const uint32_t idesc = tc::make_idesc(128, N, 0, 0);
+        const uint64_t ad = tc::make_desc_sw128(tc::smem_u32(smem), 16, 1024);
+        const uint64_t bd = tc::make_desc_sw128(tc::smem_u32(smem + 32768), 16, 1024);
+        const uint32_t at = tmem + 448;
+        const long long t0 = clock64();
+        for (int i = 0; i < count; i += 4) {
+            if (tc::elect_one()) {
+                if (ts) {
+                    tc::mma_ts_acc(tmem, at, bd, idesc);
+                    tc::mma_ts_acc(tmem, at + 8, bd + 2, idesc);
+                    tc::mma_ts_acc(tmem, at + 16, bd + 4, idesc);
+                    tc::mma_ts_acc(tmem, at + 24, bd + 6, idesc);
+                } else {
+                    tc::mma_ss_acc(tmem, ad, bd, idesc);
+                    tc::mma_ss_acc(tmem, ad + 2, bd + 2, idesc);
+                    tc::mma_ss_acc(tmem, ad + 4, bd + 4, idesc);
+                    tc::mma_ss_acc(tmem, ad + 6, bd + 6, idesc);
+                }
+            }
+            __syncwarp();
+        }
+        const long long t1 = clock64();
+        if (tc::elect_one()) tc::mma_commit(&bar);
+        __syncwarp();
+        tc::mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        if (t == 32) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    }
+    if (t == 0 && rotate < 2) {
+        const uint32_t idesc = tc::make_idesc(128, N, 0, 0);
+        const uint32_t a0 = tc::smem_u32(smem), b0 = tc::smem_u32(smem + 32768);
+        const long long t0 = clock64();
+        for (int i = 0; i < count; ++i) {
+            const uint32_t d = rotate ? (uint32_t)((i & 1) * 256) : 0u;      // accumulator columns [0,N) or [256,256+N)
+            const uint64_t bd = tc::make_desc_sw128(b0 + (i & 3) * 32, 16, 1024);
+            if (ts) tc::mma_ts(tmem + d, tmem + 448 + (i & 3) * 8, bd, idesc, 1);
+            else tc::mma_ss(tmem + d, tc::make_desc_sw128(a0 + (i & 3) * 32, 16, 1024), bd, idesc, 1);
+        }
+        const long long t1 = clock64();
+        tc::mma_commit(&bar);
+        tc::mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        out[0] = t1 - t0;
+        out[1] = t2 - t0;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
+}  // namespace
+
+extern "C" int u2gnn_tc_probe(int N, int ts, int rotate, int count, long long* out, u2gnn_stream_t stream) {
+    if (!out || N < 16 || N > 256 || N % 16 || count < 1) return U2GNN_EINVAL;
+    const int smem = 65536 + 1024;
+    cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    tc_probe_kernel<<<1, 128, smem, as_stream(stream)>>>(N, ts, rotate, count, out);
+    U2GNN_CHECK_LAUNCH();
+}

@@ -173,6 +173,8 @@ int u2gnn_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, con
  *      z[M,d] = y1 + dropout_out( dropout_hidden(relu(y1 W1^T + b1)) W2^T + b2 );
  *      stats[M,2] = (mean, rstd) of z;  xnext[M,d] = LayerNorm(z)*gamma + beta (may be null). */
 size_t u2gnn_ffn_tc_packed_bytes(int d, int ff);
+/* experiment switches for profiling the forward pipeline (0 = normal operation) */
+int u2gnn_ffn_tc_debug(int flags);
 int u2gnn_ffn_tc_prepare(const float* W1, const float* b1, const float* W2, const float* b2, int d, int ff,
                          float hidden_scale, void* packed, size_t packed_size, u2gnn_stream_t stream);
 int u2gnn_ffn_tc_fwd(const float* y1, int64_t M, int d, int ff, const void* packed, uint64_t seed,
@@ -193,6 +195,9 @@ int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const float* dz, int64_t 
  *      assumptions.  A, B fp32 inputs (rounded to bf16 inside), C[128, N] fp32; scratch >= 32 KB. */
 int u2gnn_tc_selftest(int mode, const float* A, const float* B, float* C, int K, int N, void* scratch,
                       u2gnn_stream_t stream);
+
+/* tcgen05.mma rate probe (tools/probe_mma.py): out[0] = issue cycles, out[1] = issue+execute cycles of `count` MMAs */
+int u2gnn_tc_probe(int N, int ts, int rotate, int count, long long* out, u2gnn_stream_t stream);
 
 #ifdef __cplusplus
 }

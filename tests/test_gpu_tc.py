@@ -81,7 +81,8 @@ def _ffn_case(U, M, d, ff, p, seed=11):
     y64 = y1.astype(np.float64)
     h = np.maximum(y64 @ W1.T.astype(np.float64) + b1, 0) * m2
     z_ref = y64 + (h @ W2.T.astype(np.float64) + b2) * m3
-    hb = _bf(np.maximum(_bf(y1).astype(np.float64) @ _bf(W1).T.astype(np.float64) + b1, 0) * (m2 > 0))
+    # device arithmetic: S accumulated in fp32, rounded to bf16, bias added in bf16 (one rounding), ReLU, keep mask
+    hb = np.maximum(_bf(_bf(_bf(y1).astype(np.float64) @ _bf(W1).T.astype(np.float64)) + _bf(b1)), 0) * (m2 > 0)
     z_emu = y64 + (hb.astype(np.float64) @ _bf(W2 * scale).T.astype(np.float64) + b2) * m3
     mean = z_ref.mean(1)
     rstd = 1.0 / np.sqrt(z_ref.var(1) + 1e-5)
@@ -145,7 +146,7 @@ def test_ffn_tc_backward(U, M, d, ff, p):
     # emulation of the tensor-core arithmetic: bf16 operands, wide accumulation, bf16 hidden / dPre.  The ReLU
     # mask is decided by the bf16-operand pre-activation, exactly as on the device.
     yb, dfb, W1b, W2sb = (_bf(a).astype(np.float64) for a in (y1, df, W1, W2 * scale))
-    hpre_b = yb @ W1b.T + b1
+    hpre_b = _bf(_bf(yb @ W1b.T) + _bf(b1)).astype(np.float64)      # bf16(bf16(S) + bf16(b1)), as in csrc/ffn_epi.cuh
     keep = (m2 > 0)
     Hb = _bf(np.maximum(hpre_b, 0) * keep).astype(np.float64)
     Pb = _bf((dfb @ W2sb) * keep * (hpre_b > 0)).astype(np.float64)

@@ -10,6 +10,8 @@ def main():
     d, ff = 64, 2048
     M = int(sys.argv[1]) if len(sys.argv) > 1 else 4 * 1024 * 1024
     thr = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+    dbg = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    U.LIB.call("u2gnn_ffn_tc_debug", dbg)
     g = torch.Generator(device="cuda").manual_seed(0)
     y1 = torch.randn(M, d, device="cuda", generator=g)
     W1 = torch.randn(ff, d, device="cuda", generator=g) / 8
@@ -31,7 +33,7 @@ def main():
     b.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(b) / 5
     fl = 4.0 * M * d * ff
-    print(json.dumps({"kernel": "ffn_tc_fwd", "M": M, "thr": thr, "ms": ms, "tflops": fl / ms / 1e9}))
+    print(json.dumps({"kernel": "ffn_tc_fwd", "M": M, "thr": thr, "dbg": dbg, "ms": ms, "tflops": fl / ms / 1e9}))
 
 if __name__ == "__main__":
     main()
