@@ -1,0 +1,312 @@
+// Fused bf16 FFN block, input gradient (dgrad):  dy1 = dz + dPre W1,  dPre = (dF W2) * relu'(y1 W1^T + b1) * keep.
+// Same skeleton as the forward kernel (ffn_tc.cu): persistent CTAs, pairs of 128-row tiles, 4 control warps + 16
+// epilogue warps, weights streamed through a bulk-copy ring, every MMA A operand in tensor memory and issued from
+// warp-uniform code.  Per tile i and 128-wide ff chunk c:
+//     R_i = X_i  W1c^T         (TS, N 128)   epilogue A: packed mask  m = [bf16(S)+b1 > 0] & keep   (registers)
+//     R_i = dF_i W2Tc^T        (TS, N 128)   epilogue B: dPre = bf16(D) & m  -> written over R_i (packed)
+//     dY_i += dPre_i W1Tc^T    (TS, N 64)
+// TMEM columns: dY0 [0,64) dY1 [64,128) R0 [128,256) R1 [256,384) X0/X1 [384,448) dF0/dF1 [448,512).
+#include "common.cuh"
+#include "rng.cuh"
+#include "tc_common.cuh"
+#include "ffn_epi.cuh"
+
+namespace {
+
+constexpr int DP = 64, CH = 128, TM = 128;
+constexpr uint32_t CHUNK_BYTES = 4 * 16384;   // [W2c | W1c | W2Tc | W1Tc]
+constexpr int STAGES = 4;
+constexpr uint32_t BLOCK = 3 * 16384;         // [W1c | W2Tc | W1Tc]
+constexpr int kThreads = 640;
+constexpr uint32_t COL_Y = 0, COL_R = 128, COL_X = 384, COL_F = 448;
+
+struct Params {
+    const float* y1;
+    const float* df;
+    const float* dz;
+    float* dy1;
+    int64_t M;
+    int d, ff;
+    const uint8_t* packed;
+    RngKeys keys2;
+    int thr, low;
+};
+
+struct __align__(8) Bars {
+    uint64_t w_full[STAGES], w_empty[STAGES];
+    uint64_t x_full[2], x_free[2], s_full[2], a_done[2], d_full[2], p_full[2], y_full[2], y_free[2];
+};
+
+__device__ __forceinline__ void issue_n128(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc) {
+    if (tc::elect_one()) {
+        tc::mma_ts(tmem_d, tmem_a, b_desc, idesc, 0);
+        tc::mma_ts_acc(tmem_d, tmem_a + 8, b_desc + 2, idesc);
+        tc::mma_ts_acc(tmem_d, tmem_a + 16, b_desc + 4, idesc);
+        tc::mma_ts_acc(tmem_d, tmem_a + 24, b_desc + 6, idesc);
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void issue_n64(uint32_t tmem_y, uint32_t tmem_p, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    if (tc::elect_one()) {
+        tc::mma_ts(tmem_y, tmem_p, b_desc, idesc, acc);
+        tc::mma_ts_acc(tmem_y, tmem_p + 8, b_desc + 2, idesc);
+        tc::mma_ts_acc(tmem_y, tmem_p + 16, b_desc + 4, idesc);
+        tc::mma_ts_acc(tmem_y, tmem_p + 24, b_desc + 6, idesc);
+        tc::mma_ts_acc(tmem_y, tmem_p + 64, b_desc + 512, idesc);
+        tc::mma_ts_acc(tmem_y, tmem_p + 72, b_desc + 514, idesc);
+        tc::mma_ts_acc(tmem_y, tmem_p + 80, b_desc + 516, idesc);
+        tc::mma_ts_acc(tmem_y, tmem_p + 88, b_desc + 518, idesc);
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void commit_to(uint64_t* bar) {
+    if (tc::elect_one()) tc::mma_commit(bar);
+    __syncwarp();
+}
+
+// one fp32 row (zero padded to 64) -> 32 packed bf16 words
+__device__ __forceinline__ void load_row_packed(const float* __restrict__ src, int64_t row, int64_t M, int d, uint32_t (&xp)[32]) {
+    if (d == DP && row < M) {
+        const float4* s4 = reinterpret_cast<const float4*>(src + row * DP);
+        float4 v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = __ldg(s4 + u);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            xp[2 * u] = epi::cvt2(v[u].x, v[u].y);
+            xp[2 * u + 1] = epi::cvt2(v[u].z, v[u].w);
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+            const float a = (row < M && 2 * u < d) ? src[row * d + 2 * u] : 0.0f;
+            const float b = (row < M && 2 * u + 1 < d) ? src[row * d + 2 * u + 1] : 0.0f;
+            xp[u] = epi::cvt2(a, b);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sW = smem;                                                        // STAGES x 48 KB
+    uint32_t* sB1h = reinterpret_cast<uint32_t*>(sW + STAGES * BLOCK);         // b1 as packed bf16 pairs
+    __shared__ Bars bars;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NC = p.ff / CH;
+    const int64_t n_pairs = (p.M + 2 * TM - 1) / (2 * TM);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(&bars.w_full[s], 1);
+            tc::mbar_init(&bars.w_empty[s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&bars.x_full[i], 8);      // X (warpgroup 0) and dF (warpgroup 1): one arrival per warp
+            tc::mbar_init(&bars.x_free[i], 1);
+            tc::mbar_init(&bars.s_full[i], 1);
+            tc::mbar_init(&bars.a_done[i], 8);
+            tc::mbar_init(&bars.d_full[i], 1);
+            tc::mbar_init(&bars.p_full[i], 8);
+            tc::mbar_init(&bars.y_full[i], 1);
+            tc::mbar_init(&bars.y_free[i], 4);
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tc::tmem_alloc<512>(&tmem_slot);
+    {
+        const float* b1g = reinterpret_cast<const float*>(p.packed + (size_t)NC * CHUNK_BYTES);
+        for (int e = threadIdx.x; e < p.ff / 2; e += kThreads) sB1h[e] = epi::cvt2(b1g[2 * e], b1g[2 * e + 1]);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+                for (int c = 0; c < NC; ++c, ++it) {
+                    const uint32_t s = it % STAGES, n = it / STAGES;
+                    if (n > 0) tc::mbar_wait(&bars.w_empty[s], (n - 1) & 1);
+                    tc::mbar_arrive_expect_tx(&bars.w_full[s], BLOCK);
+                    tc::bulk_g2s(sW + s * BLOCK, p.packed + (size_t)c * CHUNK_BYTES + 16384, BLOCK, &bars.w_full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (warp-uniform) =================
+        const uint32_t idesc_n128 = tc::make_idesc(TM, CH, 0, 0);
+        const uint32_t idesc_n64 = tc::make_idesc(TM, DP, 0, 0);
+        const uint64_t w_desc0 = tc::make_desc_sw128(tc::smem_u32(sW), 16, 1024);     // stage 0: [W1c | W2Tc | W1Tc]
+        uint32_t it = 0, q = 0;
+        uint32_t acount[2] = {0, 0}, pcount[2] = {0, 0};
+        for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++q) {
+            tc::mbar_wait(&bars.w_full[it % STAGES], (it / STAGES) & 1);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                tc::mbar_wait(&bars.x_full[i], q & 1);
+                tc::tc_fence_after();
+                issue_n128(tmem + COL_R + 128 * i, tmem + COL_X + 32 * i, w_desc0 + (uint64_t)((it % STAGES) * (BLOCK >> 4)), idesc_n128);
+                commit_to(&bars.s_full[i]);
+            }
+            for (int c = 0; c < NC; ++c, ++it) {
+                const uint32_t s = it % STAGES;
+                const uint64_t wd = w_desc0 + (uint64_t)(s * (BLOCK >> 4));
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    tc::mbar_wait(&bars.a_done[i], acount[i] & 1);     // epilogue has turned S_i into mask registers
+                    ++acount[i];
+                    tc::tc_fence_after();
+                    issue_n128(tmem + COL_R + 128 * i, tmem + COL_F + 32 * i, wd + 1024, idesc_n128);      // D_i = dF_i W2Tc^T
+                    commit_to(&bars.d_full[i]);
+                }
+                if (c + 1 < NC) tc::mbar_wait(&bars.w_full[(it + 1) % STAGES], ((it + 1) / STAGES) & 1);
+                const uint64_t w1_next = w_desc0 + (uint64_t)(((it + 1) % STAGES) * (BLOCK >> 4));
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    tc::mbar_wait(&bars.p_full[i], pcount[i] & 1);     // dPre_i in TMEM (over R_i)
+                    ++pcount[i];
+                    if (c == 0 && q > 0) tc::mbar_wait(&bars.y_free[i], (q - 1) & 1);
+                    tc::tc_fence_after();
+                    issue_n64(tmem + COL_Y + 64 * i, tmem + COL_R + 128 * i, wd + 2048, idesc_n64, c > 0);  // dY_i += dPre_i W1Tc^T
+                    if (c == NC - 1) {
+                        commit_to(&bars.y_full[i]);
+                        commit_to(&bars.x_free[i]);                    // X_i and dF_i no longer needed
+                    } else {
+                        issue_n128(tmem + COL_R + 128 * i, tmem + COL_X + 32 * i, w1_next, idesc_n128);     // in order after the GEMM above
+                        commit_to(&bars.s_full[i]);
+                    }
+                }
+                commit_to(&bars.w_empty[s]);
+            }
+        }
+    } else if (warp >= 4) {
+        const int i = (warp - 4) >> 3;
+        const int wg = ((warp - 4) >> 2) & 1;
+        const int wq = warp & 3;
+        const int tr = wq * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+        uint32_t q = 0, scount = 0, dcount = 0;
+        for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++q) {
+            const int64_t row = pair * (2 * TM) + (int64_t)i * TM + tr;
+            // ---- operands into tensor memory: warpgroup 0 converts X rows, warpgroup 1 converts dF rows
+            if (q > 0) tc::mbar_wait(&bars.x_free[i], (q - 1) & 1);
+            {
+                uint32_t xp[32];
+                load_row_packed(wg == 0 ? p.y1 : p.df, row, p.M, p.d, xp);
+                tc::tmem_st32(tmem + lane_base + (wg == 0 ? COL_X : COL_F) + 32 * i, xp);
+                tc::tmem_st_wait();
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bars.x_full[i]);
+            }
+            const uint32_t r_addr = tmem + lane_base + COL_R + 128 * i + 64 * wg;
+            for (int c = 0; c < NC; ++c) {
+                // ---- epilogue A: S -> packed mask
+                tc::mbar_wait(&bars.s_full[i], scount & 1);
+                ++scount;
+                tc::tc_fence_after();
+                uint32_t msk[32];
+#pragma unroll
+                for (int pc = 0; pc < 2; ++pc) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(r_addr + 32 * pc, v);
+                    uint32_t km[16];
+                    if (p.thr)
+                        epi::keep_masks16(rng_keep_word_lo(p.keys2, (uint64_t)row * (uint64_t)(p.ff >> 5) + (uint64_t)(4 * c + 2 * wg + pc),
+                                                           p.thr, p.low), km);
+                    const uint4* bb = reinterpret_cast<const uint4*>(sB1h + ((c * CH + 64 * wg + 32 * pc) >> 1));
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const uint4 b4 = bb[q4];
+                        const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = 4 * q4 + u;
+                            uint32_t m = epi::gt0_mask2(epi::relu_bias2(epi::cvt2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bw[u]));
+                            if (p.thr) m &= km[j];
+                            msk[pc * 16 + j] = m;
+                        }
+                    }
+                }
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bars.a_done[i]);
+                // ---- epilogue B: D -> dPre (packed, over this thread's own R columns)
+                tc::mbar_wait(&bars.d_full[i], dcount & 1);
+                ++dcount;
+                tc::tc_fence_after();
+                uint32_t hp[32];
+#pragma unroll
+                for (int pc = 0; pc < 2; ++pc) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(r_addr + 32 * pc, v);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        hp[pc * 16 + j] = epi::cvt2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])) & msk[pc * 16 + j];
+                }
+                tc::tmem_st32(r_addr, hp);
+                tc::tmem_st_wait();
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bars.p_full[i]);
+            }
+            if (wg != 0) continue;
+            // ---- dY + dz -> dy1
+            tc::mbar_wait(&bars.y_full[i], q & 1);
+            tc::tc_fence_after();
+            uint32_t y0[32], y1r[32];
+            tc::tmem_ld32(tmem + lane_base + COL_Y + 64 * i, y0);
+            tc::tmem_ld32(tmem + lane_base + COL_Y + 64 * i + 32, y1r);
+            tc::tmem_ld_wait();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&bars.y_free[i]);
+            if (row < p.M) {
+                if (p.d == DP) {
+                    const float4* zi = reinterpret_cast<const float4*>(p.dz + row * DP);
+                    float4* o = reinterpret_cast<float4*>(p.dy1 + row * DP);
+#pragma unroll
+                    for (int j = 0; j < DP; j += 4) {
+                        const float4 r4 = zi[j >> 2];
+                        const uint32_t* src = (j < 32) ? &y0[j] : &y1r[j - 32];
+                        o[j >> 2] = make_float4(r4.x + __uint_as_float(src[0]), r4.y + __uint_as_float(src[1]),
+                                                r4.z + __uint_as_float(src[2]), r4.w + __uint_as_float(src[3]));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < DP; ++j)
+                        if (j < p.d) p.dy1[row * p.d + j] = p.dz[row * p.d + j] + __uint_as_float(j < 32 ? y0[j] : y1r[j - 32]);
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc<512>(tmem);
+}
+
+}  // namespace
+
+// internal launch used by u2gnn_ffn_tc_bwd (ffn_tc_bwd.cu)
+int ffn_tc_dgrad_launch(const float* y1, const float* df, const float* dz, float* dy1, int64_t M, int d, int ff,
+                        const void* packed, uint64_t seed, uint32_t stream_hidden, int thr, cudaStream_t st) {
+    Params p;
+    p.y1 = y1; p.df = df; p.dz = dz; p.dy1 = dy1; p.M = M; p.d = d; p.ff = ff;
+    p.packed = static_cast<const uint8_t*>(packed);
+    p.keys2 = rng_keys(seed, stream_hidden);
+    p.thr = thr;
+    p.low = rng_thr_low(thr);
+    const size_t smem = 1024 + (size_t)STAGES * BLOCK + (size_t)(ff / 2) * sizeof(uint32_t);
+    if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
+    cudaFuncSetAttribute(ffn_tc_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t n_pairs = (M + 2 * TM - 1) / (2 * TM);
+    const int grid = (int)(n_pairs < U2GNN_NUM_SMS ? n_pairs : U2GNN_NUM_SMS);
+    ffn_tc_dgrad_kernel<<<grid, kThreads, smem, st>>>(p);
+    return U2GNN_OK;
+}

@@ -1,0 +1,333 @@
+// Fused bf16 FFN block, weight gradients (wgrad):  dW1, db1, dW2  with the hidden recomputed on chip.
+// One 128-wide ff chunk per CTA (its W1c / W2Tc images stay resident in shared memory); the CTAs of a chunk split
+// the 128-row tiles among themselves.  Per tile (parity i selects the TMEM region and the epilogue group):
+//     R_i = X  W1c^T            (SS, N 128)   epilogue A: H = relu(bf16(S)+b1) & keep              (registers)
+//     R_i = dF W2Tc^T           (SS, N 128)   epilogue B: dPre = bf16(D) & [H > 0]                 (registers)
+//     H, dPre -> shared memory as [128 rows x 128 hidden] swizzled tiles = MN-major A operands
+//     dW2c^T[hidden, d]      += H^T    dF          (SS, MN-major A and B, N 64)
+//     [dW1c | db1c][hidden,] += dPre^T [X | 1]     (SS, N 80: the second MN group of B is a tile of ones)
+// accumulated in tensor memory over all tiles of the CTA and flushed once with atomics.
+// X / dF row tiles are converted to bf16 swizzled tiles by two loader warps through a 3-stage ring; the same
+// tile is the K-major A operand of the S / D GEMMs and the MN-major B operand of the gradient GEMMs.
+// TMEM columns: R0 [0,128) R1 [128,256) dW2c^T [256,320) dW1c [320,384) db1c [384,400).
+#include "common.cuh"
+#include "rng.cuh"
+#include "tc_common.cuh"
+#include "ffn_epi.cuh"
+
+namespace {
+
+constexpr int DP = 64, CH = 128, TM = 128;
+constexpr uint32_t CHUNK_BYTES = 4 * 16384;   // [W2c | W1c | W2Tc | W1Tc]
+constexpr int kThreads = 640;
+constexpr int WG_STAGES = 3;
+constexpr uint32_t COL_R = 0, COL_DW2 = 256, COL_DW1 = 320;
+
+struct Params {
+    const float* y1;
+    const float* df;
+    int64_t M;
+    int d, ff;
+    const uint8_t* packed;
+    RngKeys keys2;
+    int thr, low;
+    float hidden_scale;
+    float* dW1;   // [ff, d]
+    float* db1;   // [ff]
+    float* dW2;   // [d, ff]
+};
+
+struct __align__(8) Bars {
+    uint64_t w_full, ld_full[WG_STAGES], ld_free[WG_STAGES], s_full[2], a_done[2], d_full[2], hp_full, hp_free, flush_full;
+};
+
+// fp32 rows -> bf16 swizzled [128 x 64] tile with NT loader threads (batches of 16 independent 128-bit loads)
+template <int NT>
+__device__ __forceinline__ void load_tile_bf16_nt(uint8_t* tile, const float* __restrict__ src, int64_t row0, int64_t M, int d,
+                                                  int tid) {
+    if (d == DP) {
+        for (int base = 0; base < TM * 16; base += NT * 16) {
+            float4 v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int e = base + u * NT + tid;
+                const int r = e >> 4, c4 = e & 15;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row0 + r < M) v[u] = __ldg(reinterpret_cast<const float4*>(src + (row0 + r) * DP) + c4);
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int e = base + u * NT + tid;
+                const int r = e >> 4, c4 = e & 15;
+                uint2 w;
+                w.x = epi::cvt2(v[u].x, v[u].y);
+                w.y = epi::cvt2(v[u].z, v[u].w);
+                *reinterpret_cast<uint2*>(tile + tc::sw128_offset(r, c4 * 4)) = w;
+            }
+        }
+    } else {
+        for (int e = tid; e < TM * DP; e += NT) {
+            const int r = e / DP, k = e % DP;
+            const float v = (row0 + r < M && k < d) ? src[(row0 + r) * d + k] : 0.0f;
+            *reinterpret_cast<__nv_bfloat16*>(tile + tc::sw128_offset(r, k)) = __float2bfloat16(v);
+        }
+    }
+}
+
+__device__ __forceinline__ void commit_to(uint64_t* bar) {
+    if (tc::elect_one()) tc::mma_commit(bar);
+    __syncwarp();
+}
+// R = A_tile(K-major, 4 k-steps) * B_image^T, N = 128
+__device__ __forceinline__ void issue_n128(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    if (tc::elect_one()) {
+        tc::mma_ss(tmem_d, a_desc, b_desc, idesc, 0);
+        tc::mma_ss_acc(tmem_d, a_desc + 2, b_desc + 2, idesc);
+        tc::mma_ss_acc(tmem_d, a_desc + 4, b_desc + 4, idesc);
+        tc::mma_ss_acc(tmem_d, a_desc + 6, b_desc + 6, idesc);
+    }
+    __syncwarp();
+}
+// acc += A^T B over the 128 rows of the tile: both operands MN-major, 8 k-steps of 16 rows (2048 B each)
+__device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    if (tc::elect_one()) {
+        tc::mma_ss(tmem_d, a_desc, b_desc, idesc, acc);
+#pragma unroll
+        for (int ks = 1; ks < 8; ++ks) tc::mma_ss_acc(tmem_d, a_desc + 128 * ks, b_desc + 128 * ks, idesc);
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sXF = smem;                                   // WG_STAGES x (X 16 KB | dF 16 KB)
+    uint8_t* sOnes = smem + WG_STAGES * 32768;             // 16 KB tile of bf16 1.0 (after the ring: LBO to it is positive)
+    uint8_t* sH = sOnes + 16384;                           // 32 KB: two [128 rows x 64 hidden] tiles
+    uint8_t* sP = sH + 32768;                              // 32 KB
+    uint8_t* sW = sP + 32768;                              // 32 KB: [W1c | W2Tc]
+    uint32_t* sB1h = reinterpret_cast<uint32_t*>(sW + 32768);   // chunk bias as 64 packed bf16 pairs
+    __shared__ Bars bars;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NC = p.ff / CH;
+    const int c = blockIdx.x % NC;
+    const int slice = blockIdx.x / NC, n_slices = gridDim.x / NC;
+    const int64_t n_tiles = (p.M + TM - 1) / TM;
+    const int64_t my_tiles = (n_tiles > slice) ? (n_tiles - slice + n_slices - 1) / n_slices : 0;
+
+    if (threadIdx.x == 0) {
+        tc::mbar_init(&bars.w_full, 1);
+        for (int s = 0; s < WG_STAGES; ++s) {
+            tc::mbar_init(&bars.ld_full[s], 2);            // one arrival per loader warp
+            tc::mbar_init(&bars.ld_free[s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&bars.s_full[i], 1);
+            tc::mbar_init(&bars.a_done[i], 8);
+            tc::mbar_init(&bars.d_full[i], 1);
+        }
+        tc::mbar_init(&bars.hp_full, 8);
+        tc::mbar_init(&bars.hp_free, 1);
+        tc::mbar_init(&bars.flush_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tc::tmem_alloc<512>(&tmem_slot);
+    {
+        const float* b1g = reinterpret_cast<const float*>(p.packed + (size_t)NC * CHUNK_BYTES) + c * CH;
+        for (int e = threadIdx.x; e < CH / 2; e += kThreads) sB1h[e] = epi::cvt2(b1g[2 * e], b1g[2 * e + 1]);
+        for (int e = threadIdx.x; e < 16384 / 4; e += kThreads) reinterpret_cast<uint32_t*>(sOnes)[e] = 0x3F803F80u;
+    }
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (my_tiles > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                tc::mbar_arrive_expect_tx(&bars.w_full, 32768);
+                tc::bulk_g2s(sW, p.packed + (size_t)c * CHUNK_BYTES + 16384, 32768, &bars.w_full);
+            }
+        } else if (warp == 2 || warp == 3) {
+            // ================= row-tile loaders =================
+            const int tid = (warp - 2) * 32 + lane;
+            for (int64_t n = 0; n < my_tiles; ++n) {
+                const uint32_t s = (uint32_t)(n % WG_STAGES), u = (uint32_t)(n / WG_STAGES);
+                if (u > 0) tc::mbar_wait(&bars.ld_free[s], (u - 1) & 1);
+                const int64_t row0 = ((int64_t)slice + n * n_slices) * TM;
+                load_tile_bf16_nt<64>(sXF + s * 32768, p.y1, row0, p.M, p.d, tid);
+                load_tile_bf16_nt<64>(sXF + s * 32768 + 16384, p.df, row0, p.M, p.d, tid);
+                tc::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bars.ld_full[s]);
+            }
+        } else if (warp == 1) {
+            // ================= MMA issuer (warp-uniform) =================
+            const uint32_t idesc_n128 = tc::make_idesc(TM, CH, 0, 0);
+            const uint32_t idesc_w2 = tc::make_idesc(CH, DP, 1, 1);        // M = hidden, N = d, both MN-major
+            const uint32_t idesc_w1 = tc::make_idesc(CH, DP + 16, 1, 1);   // N = 80: [X | ones]
+            const uint64_t xf0 = tc::make_desc_sw128(tc::smem_u32(sXF), 16, 1024);         // K-major view of stage 0 X tile
+            const uint64_t w1d = tc::make_desc_sw128(tc::smem_u32(sW), 16, 1024);
+            const uint64_t w2td = w1d + 1024;
+            const uint64_t hd = tc::make_desc_sw128(tc::smem_u32(sH), 16384, 1024);        // MN-major A: LBO = next 64-hidden tile
+            const uint64_t pd = tc::make_desc_sw128(tc::smem_u32(sP), 16384, 1024);
+            tc::mbar_wait(&bars.w_full, 0);
+            tc::mbar_wait(&bars.ld_full[0], 0);
+            tc::tc_fence_after();
+            issue_n128(tmem + COL_R, xf0, w1d, idesc_n128);
+            commit_to(&bars.s_full[0]);
+            for (int64_t n = 0; n < my_tiles; ++n) {
+                const uint32_t i = (uint32_t)(n & 1), ph = (uint32_t)(n >> 1) & 1;
+                const uint32_t s = (uint32_t)(n % WG_STAGES);
+                const uint64_t xd = xf0 + (uint64_t)(s * 2048);            // X tile of this stage (K-major view)
+                tc::mbar_wait(&bars.a_done[i], ph);
+                tc::tc_fence_after();
+                issue_n128(tmem + COL_R + 128 * i, xd + 1024, w2td, idesc_n128);            // D = dF W2Tc^T
+                commit_to(&bars.d_full[i]);
+                if (n + 1 < my_tiles) {
+                    const uint32_t s2 = (uint32_t)((n + 1) % WG_STAGES);
+                    tc::mbar_wait(&bars.ld_full[s2], (uint32_t)((n + 1) / WG_STAGES) & 1);
+                    tc::tc_fence_after();
+                    issue_n128(tmem + COL_R + 128 * (i ^ 1), xf0 + (uint64_t)(s2 * 2048), w1d, idesc_n128);
+                    commit_to(&bars.s_full[i ^ 1]);
+                }
+                tc::mbar_wait(&bars.hp_full, (uint32_t)n & 1);
+                tc::tc_fence_after();
+                // MN-major B views of the same X / dF tiles: dF has one 64-wide group; [X | ones] has two, the second
+                // one LBO bytes further (the ones tile)
+                const uint32_t x_addr = tc::smem_u32(sXF) + s * 32768;
+                const uint64_t fd_mn = tc::make_desc_sw128(x_addr + 16384, 16384, 1024);
+                const uint64_t xd_mn = tc::make_desc_sw128(x_addr, tc::smem_u32(sOnes) - x_addr, 1024);
+                issue_wgrad(tmem + COL_DW2, hd, fd_mn, idesc_w2, n > 0);
+                issue_wgrad(tmem + COL_DW1, pd, xd_mn, idesc_w1, n > 0);
+                commit_to(&bars.hp_free);
+                commit_to(&bars.ld_free[s]);
+            }
+            commit_to(&bars.flush_full);
+        } else if (warp >= 4) {
+            const int i = (warp - 4) >> 3;                  // tile parity handled by this group
+            const int wg = ((warp - 4) >> 2) & 1;           // 64-hidden half
+            const int wq = warp & 3;
+            const int tr = wq * 32 + lane;
+            const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+            const uint32_t r_addr = tmem + lane_base + COL_R + 128 * i + 64 * wg;
+            uint32_t k = 0;
+            for (int64_t n = i; n < my_tiles; n += 2, ++k) {
+                const int64_t row = ((int64_t)slice + n * n_slices) * TM + tr;
+                // ---- S -> H = relu(bf16(S) + b1) & keep
+                tc::mbar_wait(&bars.s_full[i], k & 1);
+                tc::tc_fence_after();
+                uint32_t hreg[32], preg[32];
+#pragma unroll
+                for (int pc = 0; pc < 2; ++pc) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(r_addr + 32 * pc, v);
+                    uint32_t km[16];
+                    if (p.thr)
+                        epi::keep_masks16(rng_keep_word_lo(p.keys2, (uint64_t)row * (uint64_t)(p.ff >> 5) + (uint64_t)(4 * c + 2 * wg + pc),
+                                                           p.thr, p.low), km);
+                    const uint4* bb = reinterpret_cast<const uint4*>(sB1h + 32 * wg + 16 * pc);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const uint4 b4 = bb[q4];
+                        const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = 4 * q4 + u;
+                            uint32_t h2 = epi::relu_bias2(epi::cvt2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bw[u]);
+                            if (p.thr) h2 &= km[j];
+                            hreg[pc * 16 + j] = h2;
+                        }
+                    }
+                }
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bars.a_done[i]);
+                // ---- D -> dPre = bf16(D) & [H > 0]
+                tc::mbar_wait(&bars.d_full[i], k & 1);
+                tc::tc_fence_after();
+#pragma unroll
+                for (int pc = 0; pc < 2; ++pc) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(r_addr + 32 * pc, v);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        preg[pc * 16 + j] = epi::cvt2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])) & epi::gt0_mask2(hreg[pc * 16 + j]);
+                }
+                tc::tc_fence_before();
+                // ---- H, dPre -> shared memory: this thread's row of the 64-hidden tile `wg`
+                if (n > 0) tc::mbar_wait(&bars.hp_free, (uint32_t)(n - 1) & 1);
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    const uint32_t off = (uint32_t)(wg * 16384) + tc::sw128_chunk(tr, ch);
+                    *reinterpret_cast<uint4*>(sH + off) = make_uint4(hreg[4 * ch], hreg[4 * ch + 1], hreg[4 * ch + 2], hreg[4 * ch + 3]);
+                    *reinterpret_cast<uint4*>(sP + off) = make_uint4(preg[4 * ch], preg[4 * ch + 1], preg[4 * ch + 2], preg[4 * ch + 3]);
+                }
+                tc::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bars.hp_full);
+            }
+            // ---- flush the chunk's weight gradients (first warpgroup; thread <-> hidden unit)
+            if (i == 0 && wg == 0) {
+                tc::mbar_wait(&bars.flush_full, 0);
+                tc::tc_fence_after();
+                const int h = c * CH + tr;
+                uint32_t v[32];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    tc::tmem_ld32(tmem + lane_base + COL_DW1 + 32 * half, v);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (32 * half + j < p.d) atomicAdd(p.dW1 + (size_t)h * p.d + 32 * half + j, __uint_as_float(v[j]));
+                    tc::tmem_ld32(tmem + lane_base + COL_DW2 + 32 * half, v);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (32 * half + j < p.d)
+                            atomicAdd(p.dW2 + (size_t)(32 * half + j) * p.ff + h, __uint_as_float(v[j]) * p.hidden_scale);
+                }
+                uint32_t b16[16];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                             : "=r"(b16[0]), "=r"(b16[1]), "=r"(b16[2]), "=r"(b16[3]), "=r"(b16[4]), "=r"(b16[5]), "=r"(b16[6]),
+                               "=r"(b16[7]), "=r"(b16[8]), "=r"(b16[9]), "=r"(b16[10]), "=r"(b16[11]), "=r"(b16[12]), "=r"(b16[13]),
+                               "=r"(b16[14]), "=r"(b16[15])
+                             : "r"(tmem + lane_base + COL_DW1 + 64)
+                             : "memory");
+                tc::tmem_ld_wait();
+                atomicAdd(p.db1 + h, __uint_as_float(b16[0]));
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc<512>(tmem);
+}
+
+}  // namespace
+
+// internal launch used by u2gnn_ffn_tc_bwd (ffn_tc_bwd.cu)
+int ffn_tc_wgrad_launch(const float* y1, const float* df, int64_t M, int d, int ff, const void* packed, float hidden_scale,
+                        uint64_t seed, uint32_t stream_hidden, int thr, float* dW1, float* db1, float* dW2, cudaStream_t st) {
+    Params p;
+    p.y1 = y1; p.df = df; p.M = M; p.d = d; p.ff = ff;
+    p.packed = static_cast<const uint8_t*>(packed);
+    p.keys2 = rng_keys(seed, stream_hidden);
+    p.thr = thr;
+    p.low = rng_thr_low(thr);
+    p.hidden_scale = hidden_scale;
+    p.dW1 = dW1; p.db1 = db1; p.dW2 = dW2;
+    const size_t smem = 1024 + (size_t)WG_STAGES * 32768 + 16384 + 3 * 32768 + 512;
+    cudaFuncSetAttribute(ffn_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int NC = ff / CH;
+    const int64_t n_tiles = (M + TM - 1) / TM;
+    int n_slices = U2GNN_NUM_SMS / NC;
+    if (n_slices < 1) n_slices = 1;
+    if (n_slices > n_tiles) n_slices = (int)n_tiles;
+    ffn_tc_wgrad_kernel<<<NC * n_slices, kThreads, smem, st>>>(p);
+    return U2GNN_OK;
+}
