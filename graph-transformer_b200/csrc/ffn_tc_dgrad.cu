@@ -30,6 +30,8 @@ struct Params {
     const uint8_t* packed;
     RngKeys keys2;
     int thr, low;
+    uint8_t* xb;      // [n_tiles][128 x 64] bf16 swizzled images of y1 / df, consumed by the wgrad kernel (may be null)
+    uint8_t* fb;
 };
 
 struct __align__(8) Bars {
@@ -198,6 +200,13 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const Params 
                 uint32_t xp[32];
                 load_row_packed(wg == 0 ? p.y1 : p.df, row, p.M, p.d, xp);
                 tc::tmem_st32(tmem + lane_base + (wg == 0 ? COL_X : COL_F) + 32 * i, xp);
+                uint8_t* img = (wg == 0) ? p.xb : p.fb;
+                if (img) {      // this thread's 128-byte row of the tile image, chunks at their swizzled positions
+                    img += (size_t)(pair * 2 + i) * 16384;
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch)
+                        *reinterpret_cast<uint4*>(img + tc::sw128_chunk(tr, ch)) = make_uint4(xp[4 * ch], xp[4 * ch + 1], xp[4 * ch + 2], xp[4 * ch + 3]);
+                }
                 tc::tmem_st_wait();
                 tc::tc_fence_before();
                 __syncwarp();
@@ -295,13 +304,15 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const Params 
 
 // internal launch used by u2gnn_ffn_tc_bwd (ffn_tc_bwd.cu)
 int ffn_tc_dgrad_launch(const float* y1, const float* df, const float* dz, float* dy1, int64_t M, int d, int ff,
-                        const void* packed, uint64_t seed, uint32_t stream_hidden, int thr, cudaStream_t st) {
+                        const void* packed, uint64_t seed, uint32_t stream_hidden, int thr, void* xb, void* fb, cudaStream_t st) {
     Params p;
     p.y1 = y1; p.df = df; p.dz = dz; p.dy1 = dy1; p.M = M; p.d = d; p.ff = ff;
     p.packed = static_cast<const uint8_t*>(packed);
     p.keys2 = rng_keys(seed, stream_hidden);
     p.thr = thr;
     p.low = rng_thr_low(thr);
+    p.xb = static_cast<uint8_t*>(xb);
+    p.fb = static_cast<uint8_t*>(fb);
     const size_t smem = 1024 + (size_t)STAGES * BLOCK + (size_t)(ff / 2) * sizeof(uint32_t);
     if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
     cudaFuncSetAttribute(ffn_tc_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -24,8 +24,8 @@ constexpr int WG_STAGES = 3;
 constexpr uint32_t COL_R = 0, COL_DW2 = 256, COL_DW1 = 320;
 
 struct Params {
-    const float* y1;
-    const float* df;
+    const uint8_t* xb;   // bf16 swizzled tile images written by the dgrad kernel
+    const uint8_t* fb;
     int64_t M;
     int d, ff;
     const uint8_t* packed;
@@ -40,39 +40,6 @@ struct Params {
 struct __align__(8) Bars {
     uint64_t w_full, ld_full[WG_STAGES], ld_free[WG_STAGES], s_full[2], a_done[2], d_full[2], hp_full, hp_free, flush_full;
 };
-
-// fp32 rows -> bf16 swizzled [128 x 64] tile with NT loader threads (batches of 16 independent 128-bit loads)
-template <int NT>
-__device__ __forceinline__ void load_tile_bf16_nt(uint8_t* tile, const float* __restrict__ src, int64_t row0, int64_t M, int d,
-                                                  int tid) {
-    if (d == DP) {
-        for (int base = 0; base < TM * 16; base += NT * 16) {
-            float4 v[16];
-#pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const int e = base + u * NT + tid;
-                const int r = e >> 4, c4 = e & 15;
-                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row0 + r < M) v[u] = __ldg(reinterpret_cast<const float4*>(src + (row0 + r) * DP) + c4);
-            }
-#pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const int e = base + u * NT + tid;
-                const int r = e >> 4, c4 = e & 15;
-                uint2 w;
-                w.x = epi::cvt2(v[u].x, v[u].y);
-                w.y = epi::cvt2(v[u].z, v[u].w);
-                *reinterpret_cast<uint2*>(tile + tc::sw128_offset(r, c4 * 4)) = w;
-            }
-        }
-    } else {
-        for (int e = tid; e < TM * DP; e += NT) {
-            const int r = e / DP, k = e % DP;
-            const float v = (row0 + r < M && k < d) ? src[(row0 + r) * d + k] : 0.0f;
-            *reinterpret_cast<__nv_bfloat16*>(tile + tc::sw128_offset(r, k)) = __float2bfloat16(v);
-        }
-    }
-}
 
 __device__ __forceinline__ void commit_to(uint64_t* bar) {
     if (tc::elect_one()) tc::mma_commit(bar);
@@ -119,7 +86,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params 
     if (threadIdx.x == 0) {
         tc::mbar_init(&bars.w_full, 1);
         for (int s = 0; s < WG_STAGES; ++s) {
-            tc::mbar_init(&bars.ld_full[s], 2);            // one arrival per loader warp
+            tc::mbar_init(&bars.ld_full[s], 1);            // producer arrive + 32 KB of bulk-copy bytes
             tc::mbar_init(&bars.ld_free[s], 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -150,18 +117,17 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params 
                 tc::mbar_arrive_expect_tx(&bars.w_full, 32768);
                 tc::bulk_g2s(sW, p.packed + (size_t)c * CHUNK_BYTES + 16384, 32768, &bars.w_full);
             }
-        } else if (warp == 2 || warp == 3) {
-            // ================= row-tile loaders =================
-            const int tid = (warp - 2) * 32 + lane;
-            for (int64_t n = 0; n < my_tiles; ++n) {
-                const uint32_t s = (uint32_t)(n % WG_STAGES), u = (uint32_t)(n / WG_STAGES);
-                if (u > 0) tc::mbar_wait(&bars.ld_free[s], (u - 1) & 1);
-                const int64_t row0 = ((int64_t)slice + n * n_slices) * TM;
-                load_tile_bf16_nt<64>(sXF + s * 32768, p.y1, row0, p.M, p.d, tid);
-                load_tile_bf16_nt<64>(sXF + s * 32768 + 16384, p.df, row0, p.M, p.d, tid);
-                tc::fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&bars.ld_full[s]);
+        } else if (warp == 2) {
+            // ================= row-tile producer: two 16 KB bulk copies per tile (images written by dgrad) ==========
+            if (lane == 0) {
+                for (int64_t n = 0; n < my_tiles; ++n) {
+                    const uint32_t s = (uint32_t)(n % WG_STAGES), u = (uint32_t)(n / WG_STAGES);
+                    if (u > 0) tc::mbar_wait(&bars.ld_free[s], (u - 1) & 1);
+                    const int64_t tile = (int64_t)slice + n * n_slices;
+                    tc::mbar_arrive_expect_tx(&bars.ld_full[s], 32768);
+                    tc::bulk_g2s(sXF + s * 32768, p.xb + (size_t)tile * 16384, 16384, &bars.ld_full[s]);
+                    tc::bulk_g2s(sXF + s * 32768 + 16384, p.fb + (size_t)tile * 16384, 16384, &bars.ld_full[s]);
+                }
             }
         } else if (warp == 1) {
             // ================= MMA issuer (warp-uniform) =================
@@ -311,10 +277,10 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params 
 }  // namespace
 
 // internal launch used by u2gnn_ffn_tc_bwd (ffn_tc_bwd.cu)
-int ffn_tc_wgrad_launch(const float* y1, const float* df, int64_t M, int d, int ff, const void* packed, float hidden_scale,
+int ffn_tc_wgrad_launch(const void* xb, const void* fb, int64_t M, int d, int ff, const void* packed, float hidden_scale,
                         uint64_t seed, uint32_t stream_hidden, int thr, float* dW1, float* db1, float* dW2, cudaStream_t st) {
     Params p;
-    p.y1 = y1; p.df = df; p.M = M; p.d = d; p.ff = ff;
+    p.xb = static_cast<const uint8_t*>(xb); p.fb = static_cast<const uint8_t*>(fb); p.M = M; p.d = d; p.ff = ff;
     p.packed = static_cast<const uint8_t*>(packed);
     p.keys2 = rng_keys(seed, stream_hidden);
     p.thr = thr;

@@ -318,9 +318,11 @@ def encoder_layer_bwd(dy2, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
         LIB.call("u2gnn_colsum", _ptr(df), Mq, d, d, _ptr(g["linear2.bias"]), 1, _stream())
         if LIB.timed is not None:
             FLOPS["u2gnn_ffn_tc_bwd"] = FLOPS.get("u2gnn_ffn_tc_bwd", 0) + 8 * Mq * d * ff
+        wsb = LIB.call("u2gnn_ffn_tc_bwd_workspace_bytes", Mq)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         LIB.call("u2gnn_ffn_tc_bwd", _ptr(sv.y1), _ptr(df), _ptr(dz2), Mq, d, ff, _ptr(sv.packed), drop_scale, seed,
                  drop_ids[2], thr, _ptr(dy1), _ptr(g["linear1.weight"]), _ptr(g["linear1.bias"]),
-                 _ptr(g["linear2.weight"]), _stream())
+                 _ptr(g["linear2.weight"]), _ptr(ws), wsb, _stream())
     else:
         wgrad(df, Mq, d, sv.hd, ff, g["linear2.weight"], g["linear2.bias"])
         dhpre = torch.empty((Mq, ff), **f32)

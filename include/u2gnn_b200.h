@@ -184,10 +184,12 @@ int u2gnn_ffn_tc_fwd(const float* y1, int64_t M, int d, int ff, const void* pack
 /* backward of the block above (autograd of linear1/ReLU/dropout/linear2, transformer.py:977-982) with the
  * hidden recomputed on chip: dy1[M,d] = dz + dPre W1 (dz = gradient at the residual sum, df = gradient at
  * the linear2 output after the output dropout; dy1 may alias dz); dW1[ff,d], db1[ff], dW2[d,ff] are
- * ACCUMULATED (atomics).  db2 = colsum(df) is left to u2gnn_colsum. */
+ * ACCUMULATED (atomics).  db2 = colsum(df) is left to u2gnn_colsum.  workspace (128-byte aligned) holds bf16 tile
+ * images of y1 / df handed from the input-gradient kernel to the weight-gradient kernel. */
+size_t u2gnn_ffn_tc_bwd_workspace_bytes(int64_t M);
 int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const float* dz, int64_t M, int d, int ff, const void* packed,
                      float hidden_scale, uint64_t seed, uint32_t stream_hidden, int thr, float* dy1, float* dW1,
-                     float* db1, float* dW2, u2gnn_stream_t stream);
+                     float* db1, float* dW2, void* workspace, size_t workspace_bytes, u2gnn_stream_t stream);
 
 /* ---- tcgen05 plumbing self-test (csrc/tc_selftest.cu): one CTA runs a [128 x N x K] bf16 GEMM through
  *      each operand path the fused kernels use (mode 0 K-major smem, 1 MN-major smem, 2 A in tensor

@@ -129,8 +129,9 @@ def test_ffn_tc_backward(U, M, d, ff, p):
     dy1 = torch.zeros((M, d), device="cuda")
     dW1 = torch.zeros((ff, d), device="cuda"); db1 = torch.zeros(ff, device="cuda"); dW2 = torch.zeros((d, ff), device="cuda")
     SEED, S2 = 0x1234ABCD99, 18
+    ws = torch.empty(U.LIB.call("u2gnn_ffn_tc_bwd_workspace_bytes", M), dtype=torch.uint8, device="cuda")
     U.LIB.call("u2gnn_ffn_tc_bwd", t["y1"].data_ptr(), t["df"].data_ptr(), t["dz"].data_ptr(), M, d, ff, packed.data_ptr(), scale,
-               SEED, S2, thr, dy1.data_ptr(), dW1.data_ptr(), db1.data_ptr(), dW2.data_ptr(), E._stream())
+               SEED, S2, thr, dy1.data_ptr(), dW1.data_ptr(), db1.data_ptr(), dW2.data_ptr(), ws.data_ptr(), ws.numel(), E._stream())
     torch.cuda.synchronize()
     if thr:
         k2, _ = O.dropout_keep_mask(SEED, S2, M * ff, p)

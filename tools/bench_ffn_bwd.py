@@ -1,0 +1,31 @@
+"""Microbenchmark of the fused tcgen05 FFN backward (dgrad + wgrad), CUDA events."""
+import os, sys, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "graph-transformer_b200"))
+import torch
+import u2gnn_b200 as U
+from u2gnn_b200 import engine as E
+
+d, ff = 64, 2048
+M = int(sys.argv[1]) if len(sys.argv) > 1 else 4 * 1024 * 1024
+thr = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+g = torch.Generator(device="cuda").manual_seed(0)
+y1 = torch.randn(M, d, device="cuda", generator=g); df = torch.randn(M, d, device="cuda", generator=g); dz = torch.randn(M, d, device="cuda", generator=g)
+W1 = torch.randn(ff, d, device="cuda", generator=g) / 8; W2 = torch.randn(d, ff, device="cuda", generator=g) / 45
+b1 = torch.zeros(ff, device="cuda"); b2 = torch.zeros(d, device="cuda")
+nb = U.LIB.call("u2gnn_ffn_tc_packed_bytes", d, ff)
+packed = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+U.LIB.call("u2gnn_ffn_tc_prepare", W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), d, ff, 2.0, packed.data_ptr(), nb, E._stream())
+dy = torch.empty_like(y1); dW1 = torch.zeros_like(W1); db1 = torch.zeros_like(b1); dW2 = torch.zeros_like(W2)
+ws = torch.empty(U.LIB.call("u2gnn_ffn_tc_bwd_workspace_bytes", M), dtype=torch.uint8, device="cuda")
+def run():
+    U.LIB.call("u2gnn_ffn_tc_bwd", y1.data_ptr(), df.data_ptr(), dz.data_ptr(), M, d, ff, packed.data_ptr(), 2.0, 1, 2, thr,
+               dy.data_ptr(), dW1.data_ptr(), db1.data_ptr(), dW2.data_ptr(), ws.data_ptr(), ws.numel(), E._stream())
+for _ in range(3): run()
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(5): run()
+b.record(); torch.cuda.synchronize()
+ms = a.elapsed_time(b) / 5
+print(json.dumps({"kernel": "ffn_tc_bwd(dgrad+wgrad)", "M": M, "thr": thr, "ms": ms, "algorithmic_tflops": 8.0 * M * d * ff / ms / 1e9}))
