@@ -1,0 +1,317 @@
+// bf16 tensor-core GEMMs for the attention-block projections of the bf16 mode (QKV, out-proj, their input
+// gradients and weight gradients).  The matrices are tall and skinny (M = rows of the batch, K and N in
+// {64, 128, 192}), so both kernels are HBM-bound: fp32 rows are read once with 128-bit loads, rounded to bf16
+// into swizzled shared-memory tiles, multiplied with tcgen05.mma (accumulators in tensor memory) and written /
+// accumulated in fp32.  Phase-serial CTAs (load -> MMA -> store); several CTAs per SM overlap the phases.
+//
+//   u2gnn_gemm_tc_rows   C[M, N] = A[M, K] W^T (+ bias)        W given as [N, K] (w_kn = 0) or [K, N] (w_kn = 1)
+//   u2gnn_gemm_tc_wgrad  dW[N1, N2] += A[M, N1]^T B[M, N2],  db[N1] += colsum(A)     (N2 = 64 padded)
+// Replaces the F.linear calls inside nn.MultiheadAttention (torch/nn/functional.py multi_head_attention_forward:
+// in_proj / out_proj) and their autograd in the bf16 mode; the fp32 mode keeps u2gnn_sgemm.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "ffn_epi.cuh"
+
+namespace {
+
+constexpr int TM = 128;
+constexpr int kThreads = 256;
+
+// fp32 [rows x K] block (row stride lda) -> K/64 swizzled bf16 tiles of [128 x 64]; rows >= M and cols >= K_true zero
+template <int NT>
+__device__ __forceinline__ void stage_rows_bf16(uint8_t* tiles, const float* __restrict__ src, int64_t row0, int64_t M,
+                                                int K_true, int KP, int64_t lda, int tid) {
+    const int c4n = KP / 4;                                   // float4 per padded row
+    if ((K_true & 3) == 0 && (lda & 3) == 0) {
+        for (int base = 0; base < TM * c4n; base += NT * 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = base + u * NT + tid;
+                const int r = e / c4n, c4 = e - r * c4n;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (e < TM * c4n && row0 + r < M && 4 * c4 < K_true) v[u] = __ldg(reinterpret_cast<const float4*>(src + (row0 + r) * lda) + c4);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = base + u * NT + tid;
+                if (e >= TM * c4n) continue;
+                const int r = e / c4n, c4 = e - r * c4n;
+                const int col = 4 * c4;
+                uint2 w;
+                w.x = epi::cvt2(v[u].x, v[u].y);
+                w.y = epi::cvt2(v[u].z, v[u].w);
+                *reinterpret_cast<uint2*>(tiles + (col >> 6) * 16384 + tc::sw128_offset(r, col & 63)) = w;
+            }
+        }
+    } else {
+        for (int e = tid; e < TM * KP; e += NT) {
+            const int r = e / KP, k = e - r * KP;
+            const float v = (row0 + r < M && k < K_true) ? src[(row0 + r) * lda + k] : 0.0f;
+            *reinterpret_cast<__nv_bfloat16*>(tiles + (k >> 6) * 16384 + tc::sw128_offset(r, k & 63)) = __float2bfloat16(v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// rows GEMM
+// ---------------------------------------------------------------------------------------------------------------
+struct RowsParams {
+    const float* A;
+    int64_t M, lda;
+    int K, KP;            // true / padded (multiple of 64) inner size
+    const float* W;
+    int w_kn;             // 0: W[N][K]   1: W[K][N]
+    int N, NP;            // true / padded (multiple of 16) output size
+    const float* bias;
+    float* C;
+    int64_t ldc;
+    float beta;           // C = result + beta * C  (0 or 1)
+};
+
+__global__ void __launch_bounds__(kThreads) gemm_tc_rows_kernel(const RowsParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int kt = p.KP / 64;
+    uint8_t* sA = smem;                                     // kt tiles of [128 x 64]
+    uint8_t* sB = smem + kt * 16384;                        // kt tiles of [NP x 64] (NP*128 B each)
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        tc::mbar_init(&bar, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 0) tc::tmem_alloc<256>(&tmem_slot);
+    // weights -> K-major image: element (n, k) of the [NP x KP] operand
+    for (int e = tid; e < p.NP * p.KP; e += kThreads) {
+        const int n = e / p.KP, k = e - n * p.KP;
+        float w = 0.0f;
+        if (n < p.N && k < p.K) w = p.w_kn ? p.W[(size_t)k * p.N + n] : p.W[(size_t)n * p.K + k];
+        *reinterpret_cast<__nv_bfloat16*>(sB + (k >> 6) * (p.NP * 128) + tc::sw128_offset(n, k & 63)) = __float2bfloat16(w);
+    }
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t idesc = tc::make_idesc(TM, p.NP, 0, 0);
+    const uint64_t a_desc = tc::make_desc_sw128(tc::smem_u32(sA), 16, 1024);
+    const uint64_t b_desc = tc::make_desc_sw128(tc::smem_u32(sB), 16, 1024);
+    const int64_t n_tiles = (p.M + TM - 1) / TM;
+    const int wq = warp & 3, half = warp >> 2;              // lane quarter / column half for the epilogue
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+    uint32_t phase = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * TM;
+        stage_rows_bf16<kThreads>(sA, p.A, row0, p.M, p.K, p.KP, p.lda, tid);
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        __syncthreads();
+        tc::tc_fence_after();
+        if (warp == 0) {
+            if (tc::elect_one()) {
+                for (int ks = 0; ks < p.KP / 16; ++ks) {
+                    const uint32_t ko = (uint32_t)((ks >> 2) * 1024 + (ks & 3) * 2);
+                    const uint32_t bo = (uint32_t)((ks >> 2) * (p.NP * 8) + (ks & 3) * 2);
+                    tc::mma_ss(tmem, a_desc + ko, b_desc + bo, idesc, ks > 0);
+                }
+                tc::mma_commit(&bar);
+            }
+            __syncwarp();
+        }
+        tc::mbar_wait(&bar, phase);
+        phase ^= 1;
+        tc::tc_fence_after();
+        // epilogue: thread = row (lane quarter wq), column pieces of 32 split between the two warps of a quarter
+        const int64_t row = row0 + wq * 32 + lane;
+        for (int c0 = half * 32; c0 < p.NP; c0 += 64) {
+            uint32_t v[32];
+            tc::tmem_ld32(tmem + lane_base + c0, v);
+            tc::tmem_ld_wait();
+            if (row < p.M) {
+                float* out = p.C + row * p.ldc + c0;
+                if (c0 + 32 <= p.N && (p.ldc & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        if (p.bias) { o.x += p.bias[c0 + j]; o.y += p.bias[c0 + j + 1]; o.z += p.bias[c0 + j + 2]; o.w += p.bias[c0 + j + 3]; }
+                        if (p.beta != 0.0f) {
+                            const float4 old = *reinterpret_cast<const float4*>(out + j);
+                            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                        }
+                        *reinterpret_cast<float4*>(out + j) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < p.N) {
+                            float o = __uint_as_float(v[j]) + (p.bias ? p.bias[c0 + j] : 0.0f);
+                            if (p.beta != 0.0f) o += out[j];
+                            out[j] = o;
+                        }
+                }
+            }
+        }
+        tc::tc_fence_before();
+        __syncthreads();                                     // TMEM and sA are reused by the next tile
+    }
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<256>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight-gradient GEMM:  dW[N1, N2] += A^T B,  db[N1] += colsum(A).   N1 <= 256 (64-column groups), N2 <= 64.
+// TMEM: accumulator g covers A columns [128 g, 128 g + 128): 80 columns each (64 for dW + ones column for db).
+// ---------------------------------------------------------------------------------------------------------------
+struct WgradParams {
+    const float* A;
+    const float* B;
+    int64_t M, lda, ldb;
+    int N1, N2;
+    float* dW;            // [N1, N2]
+    float* db;            // [N1] or null
+};
+
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_wgrad_kernel(const WgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int ga = (p.N1 + 63) / 64;                         // 64-column groups of A (1..4)
+    const int nacc = (ga + 1) / 2;                           // accumulators of 128 A-columns
+    // per stage: ga A tiles, 1 B tile ; then ones tile and zero tile
+    const uint32_t stage_bytes = (uint32_t)(ga + 1) * 16384;
+    uint8_t* sOnes = smem + 2 * stage_bytes;
+    uint8_t* sZero = sOnes + 16384;
+    __shared__ uint64_t bar_mma[2];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        tc::mbar_init(&bar_mma[0], 1);
+        tc::mbar_init(&bar_mma[1], 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 0) tc::tmem_alloc<256>(&tmem_slot);
+    for (int e = tid; e < 16384 / 4; e += kThreads) {
+        reinterpret_cast<uint32_t*>(sOnes)[e] = 0x3F803F80u;
+        reinterpret_cast<uint32_t*>(sZero)[e] = 0u;
+    }
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t idesc = tc::make_idesc(128, 80, 1, 1);    // M = 128 A-columns, N = [B | ones], both MN-major
+    const int64_t n_tiles = (p.M + TM - 1) / TM;
+    int64_t it = 0;
+    uint32_t ph[2] = {0, 0};
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int s = (int)(it & 1);
+        uint8_t* st = smem + s * stage_bytes;
+        if (it >= 2) {                                        // the MMAs that read this stage two tiles ago are done
+            tc::mbar_wait(&bar_mma[s], ph[s]);
+            ph[s] ^= 1;
+        }
+        const int64_t row0 = tile * TM;
+        stage_rows_bf16<kThreads>(st, p.A, row0, p.M, p.N1, ga * 64, p.lda, tid);
+        stage_rows_bf16<kThreads>(st + ga * 16384, p.B, row0, p.M, p.N2, 64, p.ldb, tid);
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        __syncthreads();
+        tc::tc_fence_after();
+        if (warp == 0) {
+            if (tc::elect_one()) {
+                const uint32_t a0 = tc::smem_u32(st), b0 = tc::smem_u32(st + ga * 16384);
+                const uint64_t bd = tc::make_desc_sw128(b0, tc::smem_u32(sOnes) - b0, 1024);       // [B | ones]
+                for (int g = 0; g < nacc; ++g) {
+                    const uint32_t t0 = a0 + (uint32_t)(2 * g) * 16384;
+                    const bool second = (2 * g + 1 < ga);
+                    const uint32_t lbo = second ? 16384u : (tc::smem_u32(sZero) - t0);
+                    const uint64_t ad = tc::make_desc_sw128(t0, lbo, 1024);
+                    for (int ks = 0; ks < 8; ++ks) tc::mma_ss(tmem + 80 * g, ad + 128 * ks, bd + 128 * ks, idesc, (it > 0 || ks > 0));
+                }
+                tc::mma_commit(&bar_mma[s]);
+            }
+            __syncwarp();
+        }
+    }
+    // drain: wait for the last one / two commits
+    if (it >= 1) {
+        const int s1 = (int)((it - 1) & 1);
+        tc::mbar_wait(&bar_mma[s1], ph[s1]);
+        if (it >= 2) {
+            const int s0 = s1 ^ 1;
+            tc::mbar_wait(&bar_mma[s0], ph[s0]);
+        }
+        tc::tc_fence_after();
+        // flush: thread = A column (row of the accumulator); 128 threads per accumulator pass
+        const int wq = warp & 3;
+        const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+        for (int g = warp >> 2; g < nacc; g += 2) {
+            const int n1 = 128 * g + wq * 32 + lane;
+            uint32_t v[32];
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                tc::tmem_ld32(tmem + lane_base + 80 * g + c0, v);
+                tc::tmem_ld_wait();
+                if (n1 < p.N1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < p.N2) atomicAdd(p.dW + (size_t)n1 * p.N2 + c0 + j, __uint_as_float(v[j]));
+                }
+            }
+            uint32_t b16[16];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                         : "=r"(b16[0]), "=r"(b16[1]), "=r"(b16[2]), "=r"(b16[3]), "=r"(b16[4]), "=r"(b16[5]), "=r"(b16[6]),
+                           "=r"(b16[7]), "=r"(b16[8]), "=r"(b16[9]), "=r"(b16[10]), "=r"(b16[11]), "=r"(b16[12]), "=r"(b16[13]),
+                           "=r"(b16[14]), "=r"(b16[15])
+                         : "r"(tmem + lane_base + 80 * g + 64)
+                         : "memory");
+            tc::tmem_ld_wait();
+            if (p.db && n1 < p.N1) atomicAdd(p.db + n1, __uint_as_float(b16[0]));
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<256>(tmem);
+}
+
+}  // namespace
+
+extern "C" int u2gnn_gemm_tc_rows(const float* A, int64_t M, int K, int64_t lda, const float* W, int w_kn, int N,
+                                  const float* bias, float beta, float* C, int64_t ldc, u2gnn_stream_t stream) {
+    if (!A || !W || !C || M < 0 || K < 1 || N < 1 || lda < K || ldc < N) return U2GNN_EINVAL;
+    if (K > 256 || N > 256) return U2GNN_EUNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(C)) % 16) return U2GNN_EALIGN;
+    if (M == 0) return U2GNN_OK;
+    RowsParams p;
+    p.A = A; p.M = M; p.lda = lda; p.K = K; p.KP = (K + 63) / 64 * 64;
+    p.W = W; p.w_kn = w_kn; p.N = N; p.NP = (N + 15) / 16 * 16;
+    p.bias = bias; p.C = C; p.ldc = ldc; p.beta = beta;
+    const int kt = p.KP / 64;
+    const size_t smem = 1024 + (size_t)kt * 16384 + (size_t)kt * p.NP * 128;
+    if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
+    cudaFuncSetAttribute(gemm_tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = (int)((220 * 1024) / smem);
+    if (per_sm > 2) per_sm = 2;                              // 256 TMEM columns per CTA
+    if (per_sm < 1) per_sm = 1;
+    const int64_t n_tiles = (M + TM - 1) / TM;
+    const int64_t cap = (int64_t)U2GNN_NUM_SMS * per_sm;
+    gemm_tc_rows_kernel<<<(int)(n_tiles < cap ? n_tiles : cap), kThreads, smem, as_stream(stream)>>>(p);
+    U2GNN_CHECK_LAUNCH();
+}
+
+extern "C" int u2gnn_gemm_tc_wgrad(const float* A, int64_t M, int N1, int64_t lda, const float* B, int N2, int64_t ldb,
+                                   float* dW, float* db, u2gnn_stream_t stream) {
+    if (!A || !B || !dW || M < 0 || N1 < 1 || N2 < 1 || lda < N1 || ldb < N2) return U2GNN_EINVAL;
+    if (N1 > 256 || N2 > 64) return U2GNN_EUNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) % 16) return U2GNN_EALIGN;
+    if (M == 0) return U2GNN_OK;
+    WgradParams p;
+    p.A = A; p.B = B; p.M = M; p.lda = lda; p.ldb = ldb; p.N1 = N1; p.N2 = N2; p.dW = dW; p.db = db;
+    const int ga = (N1 + 63) / 64;
+    const size_t smem = 1024 + (size_t)2 * (ga + 1) * 16384 + 2 * 16384;
+    if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
+    cudaFuncSetAttribute(gemm_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t n_tiles = (M + TM - 1) / TM;
+    gemm_tc_wgrad_kernel<<<(int)(n_tiles < U2GNN_NUM_SMS ? n_tiles : U2GNN_NUM_SMS), kThreads, smem, as_stream(stream)>>>(p);
+    U2GNN_CHECK_LAUNCH();
+}

@@ -186,6 +186,23 @@ def wgrad(dout, M_rows, n_out, inp, n_in, dW, db=None):
         LIB.call("u2gnn_colsum", _ptr(dout), M_rows, n_out, n_out, _ptr(db), 1, _stream())
 
 
+def linear_tc(A, M, K, W, w_kn, N, bias=None, beta=0.0, out=None):
+    """bf16 tensor-core projection: out[M,N] = A[M,K] W^T (+bias) (+beta*out)."""
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    if LIB.timed is not None:
+        FLOPS["u2gnn_gemm_tc_rows"] = FLOPS.get("u2gnn_gemm_tc_rows", 0) + 2 * M * N * K
+    LIB.call("u2gnn_gemm_tc_rows", _ptr(A), M, K, K, _ptr(W), int(w_kn), N, _ptr(bias), beta, _ptr(out), N, _stream())
+    return out
+
+
+def wgrad_tc(dout, M, n_out, inp, n_in, dW, db=None):
+    """dW[n_out, n_in] += dout^T @ inp; db[n_out] += colsum(dout)  (tensor cores, bf16 operands)."""
+    if M == 0:
+        return
+    LIB.call("u2gnn_gemm_tc_wgrad", _ptr(dout), M, n_out, n_out, _ptr(inp), n_in, n_in, _ptr(dW), _ptr(db), _stream())
+
+
 def add_dropout_ln_fwd(res, a, M, d, drop, gamma, beta):
     dev = a.device
     z = torch.empty((M, d), dtype=torch.float32, device=dev)
@@ -238,8 +255,12 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
     M, Mq = B * S, B * Sq
     f32 = dict(dtype=torch.float32, device=dev)
     sv = LayerSaved(x=x, B=B, S=S, Sq=Sq)
-    qkv = torch.empty((M, 3 * d), **f32)
-    sgemm(0, 1, M, 3 * d, d, x, d, p["self_attn.in_proj_weight"], d, qkv, 3 * d, bias=p["self_attn.in_proj_bias"])
+    tc_proj = precision == "bf16" and not long_seq and d <= 64
+    if tc_proj:
+        qkv = linear_tc(x, M, d, p["self_attn.in_proj_weight"], 0, 3 * d, bias=p["self_attn.in_proj_bias"])
+    else:
+        qkv = torch.empty((M, 3 * d), **f32)
+        sgemm(0, 1, M, 3 * d, d, x, d, p["self_attn.in_proj_weight"], d, qkv, 3 * d, bias=p["self_attn.in_proj_bias"])
     ctx = torch.empty((Mq, d), **f32)
     if long_seq:
         assert B == 1 and Sq == S
@@ -251,8 +272,11 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
         sv.probs, sv.pd = scores, pd
     else:
         LIB.call("u2gnn_seqattn_fwd", _ptr(qkv), B, S, Sq, d, seed, drop_ids[0], thr, _ptr(ctx), _stream())
-    a = torch.empty((Mq, d), **f32)
-    sgemm(0, 1, Mq, d, d, ctx, d, p["self_attn.out_proj.weight"], d, a, d, bias=p["self_attn.out_proj.bias"])
+    if tc_proj:
+        a = linear_tc(ctx, Mq, d, p["self_attn.out_proj.weight"], 0, d, bias=p["self_attn.out_proj.bias"])
+    else:
+        a = torch.empty((Mq, d), **f32)
+        sgemm(0, 1, Mq, d, d, ctx, d, p["self_attn.out_proj.weight"], d, a, d, bias=p["self_attn.out_proj.bias"])
     if Sq == S:
         xq = x
     else:
@@ -333,9 +357,14 @@ def encoder_layer_bwd(dy2, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
     # LayerNorm1 + attention
     dz1, da = add_dropout_ln_bwd(dy1, sv.z1, sv.st1, Mq, d, p["norm1.weight"], (seed, drop_ids[1], thr),
                                  g["norm1.weight"], g["norm1.bias"])
-    wgrad(da, Mq, d, sv.ctx, d, g["self_attn.out_proj.weight"], g["self_attn.out_proj.bias"])
-    dctx = torch.empty((Mq, d), **f32)
-    sgemm(0, 0, Mq, d, d, da, d, p["self_attn.out_proj.weight"], d, dctx, d)
+    tc_proj = sv.packed is not None and not long_seq and d <= 64
+    if tc_proj:
+        wgrad_tc(da, Mq, d, sv.ctx, d, g["self_attn.out_proj.weight"], g["self_attn.out_proj.bias"])
+        dctx = linear_tc(da, Mq, d, p["self_attn.out_proj.weight"], 1, d)
+    else:
+        wgrad(da, Mq, d, sv.ctx, d, g["self_attn.out_proj.weight"], g["self_attn.out_proj.bias"])
+        dctx = torch.empty((Mq, d), **f32)
+        sgemm(0, 0, Mq, d, d, da, d, p["self_attn.out_proj.weight"], d, dctx, d)
     dqkv = torch.empty((M, 3 * d), **f32)
     if long_seq:
         scale = math.sqrt(1.0 / d)
@@ -347,11 +376,17 @@ def encoder_layer_bwd(dy2, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
         sgemm(1, 0, S, d, S, dpd, S, sv.qkv, 3 * d, dqkv, 3 * d, alpha=scale, c_off=d)     # dk = ds^T @ q * scale
     else:
         LIB.call("u2gnn_seqattn_bwd", _ptr(sv.qkv), _ptr(dctx), B, S, Sq, d, seed, drop_ids[0], thr, _ptr(dqkv), _stream())
-    wgrad(dqkv, M, 3 * d, sv.x, d, g["self_attn.in_proj_weight"], g["self_attn.in_proj_bias"])
+    if tc_proj:
+        wgrad_tc(dqkv, M, 3 * d, sv.x, d, g["self_attn.in_proj_weight"], g["self_attn.in_proj_bias"])
+    else:
+        wgrad(dqkv, M, 3 * d, sv.x, d, g["self_attn.in_proj_weight"], g["self_attn.in_proj_bias"])
     if not need_dx:
         return None
-    dx = torch.empty((M, d), **f32)
-    sgemm(0, 0, M, d, 3 * d, dqkv, 3 * d, p["self_attn.in_proj_weight"], d, dx, d)
+    if tc_proj:
+        dx = linear_tc(dqkv, M, 3 * d, p["self_attn.in_proj_weight"], 1, d)
+    else:
+        dx = torch.empty((M, d), **f32)
+        sgemm(0, 0, M, d, 3 * d, dqkv, 3 * d, p["self_attn.in_proj_weight"], d, dx, d)
     if Sq == S:
         LIB.call("u2gnn_axpy", 1.0, _ptr(dz1), _ptr(dx), M * d, _stream())
     else:

@@ -191,6 +191,15 @@ int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const float* dz, int64_t 
                      float hidden_scale, uint64_t seed, uint32_t stream_hidden, int thr, float* dy1, float* dW1,
                      float* db1, float* dW2, void* workspace, size_t workspace_bytes, u2gnn_stream_t stream);
 
+/* ---- bf16 tensor-core GEMMs for the attention-block projections of the bf16 mode (csrc/gemm_tc.cu): the
+ *      F.linear calls inside nn.MultiheadAttention (in_proj / out_proj) and their autograd.
+ *      rows : C[M,N] = A[M,K] W^T (+ bias) (+ beta*C);  W is [N,K] (w_kn = 0) or [K,N] (w_kn = 1); K, N <= 256
+ *      wgrad: dW[N1,N2] += A[M,N1]^T B[M,N2];  db[N1] += colsum(A) (db may be null);  N1 <= 256, N2 <= 64 */
+int u2gnn_gemm_tc_rows(const float* A, int64_t M, int K, int64_t lda, const float* W, int w_kn, int N,
+                       const float* bias, float beta, float* C, int64_t ldc, u2gnn_stream_t stream);
+int u2gnn_gemm_tc_wgrad(const float* A, int64_t M, int N1, int64_t lda, const float* B, int N2, int64_t ldb,
+                        float* dW, float* db, u2gnn_stream_t stream);
+
 /* ---- tcgen05 plumbing self-test (csrc/tc_selftest.cu): one CTA runs a [128 x N x K] bf16 GEMM through
  *      each operand path the fused kernels use (mode 0 K-major smem, 1 MN-major smem, 2 A in tensor
  *      memory, 3 bulk-copied pre-swizzled B).  No reference counterpart: it pins hardware layout

@@ -220,3 +220,40 @@ def test_bf16_train_step_vs_fp32_path(U):
     assert abs(l16 - l32) < 2e-2 * abs(l32)
     assert (s16 - s32).abs().max().item() < 2e-2 * s32.abs().max().item()
     assert ((g16 - g32).norm() / g32.norm()).item() < 5e-2
+
+
+# ------------------------------------------------------------------ bf16 projection GEMMs
+@pytest.mark.parametrize("M,K,N,w_kn,bias,beta", [(300, 64, 192, 0, True, 0.0), (1000, 64, 64, 1, False, 0.0), (517, 192, 64, 1, False, 1.0),
+                                                  (129, 7, 21, 0, True, 0.0), (4096 * 5 + 3, 64, 192, 0, True, 0.0)])
+def test_gemm_tc_rows(U, M, K, N, w_kn, bias, beta):
+    from u2gnn_b200 import engine as E
+    g = torch.Generator(device="cuda").manual_seed(M + K + N)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn((K, N) if w_kn else (N, K), device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g) if bias else None
+    C = torch.randn(M, N, device="cuda", generator=g)
+    ref = bf16_round(A) @ (bf16_round(W) if w_kn else bf16_round(W).t())
+    if bias:
+        ref = ref + b
+    if beta:
+        ref = ref + C
+    U.LIB.call("u2gnn_gemm_tc_rows", A.data_ptr(), M, K, K, W.data_ptr(), w_kn, N, 0 if b is None else b.data_ptr(), beta,
+               C.data_ptr(), N, E._stream())
+    torch.cuda.synchronize()
+    assert ((C - ref).abs().max() / ref.abs().max()).item() < 1e-4
+
+
+@pytest.mark.parametrize("M,N1,N2", [(300, 64, 64), (1000, 192, 64), (77, 21, 7), (148 * 128 * 3 + 50, 192, 64)])
+def test_gemm_tc_wgrad(U, M, N1, N2):
+    from u2gnn_b200 import engine as E
+    g = torch.Generator(device="cuda").manual_seed(M + N1 + N2)
+    A = torch.randn(M, N1, device="cuda", generator=g)
+    B = torch.randn(M, N2, device="cuda", generator=g)
+    dW = torch.randn(N1, N2, device="cuda", generator=g)
+    db = torch.randn(N1, device="cuda", generator=g)
+    ref_w = dW.double() + bf16_round(A).double().t() @ bf16_round(B).double()
+    ref_b = db.double() + bf16_round(A).double().sum(0)
+    U.LIB.call("u2gnn_gemm_tc_wgrad", A.data_ptr(), M, N1, N1, B.data_ptr(), N2, N2, dW.data_ptr(), db.data_ptr(), E._stream())
+    torch.cuda.synchronize()
+    assert ((dW.double() - ref_w).abs().max() / ref_w.abs().max()).item() < 1e-4
+    assert ((db.double() - ref_b).abs().max() / ref_b.abs().max()).item() < 1e-4
