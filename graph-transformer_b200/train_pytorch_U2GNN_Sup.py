@@ -1,0 +1,105 @@
+#! /usr/bin/env python
+"""Supervised U2GNN training CLI on the B200 engine — same flags, seeds, log lines and output files as the
+reference script (U2GNN_pytorch/train_pytorch_U2GNN_Sup.py:24-39,191-212), plus --attn_axis / --precision /
+--dataset_root.  The train step is the fused CUDA step (u2gnn_b200.trainer.SupTrainer); batches are built on the
+host with the global numpy RNG in the reference's call order (permutation per train batch, choice per node)."""
+import os
+import sys
+import time
+from argparse import ArgumentParser, ArgumentDefaultsHelpFormatter
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import u2gnn_b200 as U                                    # noqa: E402
+from u2gnn_b200.data import build_batch, load_data, separate_data   # noqa: E402
+from u2gnn_b200.trainer import SupTrainer                 # noqa: E402
+
+
+def parse_args(argv=None):
+    p = ArgumentParser("U2GNN", formatter_class=ArgumentDefaultsHelpFormatter, conflict_handler="resolve")
+    p.add_argument("--run_folder", default="../", help="")
+    p.add_argument("--dataset", default="PTC", help="Name of the dataset.")
+    p.add_argument("--learning_rate", default=0.0005, type=float, help="Learning rate")
+    p.add_argument("--batch_size", default=4, type=int, help="Batch Size")
+    p.add_argument("--num_epochs", default=50, type=int, help="Number of training epochs")
+    p.add_argument("--model_name", default="PTC", help="")
+    p.add_argument("--sampled_num", "--num_sampled", default=512, type=int, help="")
+    p.add_argument("--dropout", default=0.5, type=float, help="")
+    p.add_argument("--num_hidden_layers", default=1, type=int, help="")
+    p.add_argument("--num_timesteps", default=1, type=int, help="Timestep T ~ Number of self-attention layers within each U2GNN layer")
+    p.add_argument("--ff_hidden_size", default=1024, type=int, help="The hidden size for the feedforward layer")
+    p.add_argument("--num_neighbors", default=4, type=int, help="")
+    p.add_argument("--fold_idx", type=int, default=1, help="The fold index. 0-9.")
+    p.add_argument("--degree_as_tag", action="store_true", help="use node degrees as tags (README/TF-era flag)")
+    p.add_argument("--attn_axis", default="nodes", choices=["nodes", "neighbors"],
+                   help="'nodes' = reference as written, 'neighbors' = intended layout (SURVEY.md F1)")
+    p.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    p.add_argument("--dataset_root", default=None)
+    return p.parse_args(argv)
+
+
+def run(args, log=print):
+    torch.manual_seed(123)
+    np.random.seed(123)
+    torch.cuda.manual_seed_all(123)
+    U.require_device()
+    dev = torch.device("cuda")
+    log(args)
+    degree_as_tag = args.degree_as_tag or args.dataset in ("COLLAB", "IMDBBINARY", "IMDBMULTI")
+    graphs, num_classes = load_data(args.dataset, degree_as_tag, args.dataset_root)
+    train_graphs, test_graphs = separate_data(graphs, args.fold_idx)
+    d = graphs[0].node_features.shape[1]
+    reddit = 4 if "REDDIT" in args.dataset else None
+    if reddit:
+        d = 4
+    model = U.TransformerU2GNN(feature_dim_size=d, ff_hidden_size=args.ff_hidden_size, num_classes=num_classes,
+                               dropout=args.dropout, num_self_att_layers=args.num_timesteps,
+                               num_U2GNN_layers=args.num_hidden_layers, attn_axis=args.attn_axis).to(dev)
+    trainer = SupTrainer(model, lr=args.learning_rate, precision=args.precision, seed=123)
+    steps_per_epoch = int((len(train_graphs) - 1) / args.batch_size) + 1
+
+    def to_dev(batch):
+        ix, rp, X, y = batch
+        return (torch.from_numpy(ix).to(dev), torch.from_numpy(rp).to(dev), torch.from_numpy(X).to(dev), torch.from_numpy(y).to(dev))
+
+    def train_epoch():
+        model.train()
+        total = 0.0
+        for _ in range(steps_per_epoch):
+            sel = np.random.permutation(len(train_graphs))[:args.batch_size]
+            ix, rp, X, y = to_dev(build_batch([train_graphs[i] for i in sel], args.num_neighbors, np.random, reddit))
+            total += float(trainer.step(ix, rp, X, y).item())
+        return total
+
+    def evaluate():
+        model.eval()
+        preds = []
+        with torch.no_grad():
+            for i in range(0, len(test_graphs), args.batch_size):
+                ix, rp, X, _ = to_dev(build_batch(test_graphs[i:i + args.batch_size], args.num_neighbors, np.random, reddit))
+                preds.append(model(ix, rp, X).argmax(1))
+        labels = torch.tensor([g.label for g in test_graphs], device=dev)
+        return float((torch.cat(preds) == labels).sum().item()) / len(test_graphs)
+
+    out_dir = os.path.abspath(os.path.join(args.run_folder, "../runs_pytorch_U2GNN_Sup", args.model_name))
+    log("Writing to {}\n".format(out_dir))
+    ckpt = os.path.join(out_dir, "checkpoints")
+    os.makedirs(ckpt, exist_ok=True)
+    accs, losses = [], []
+    with open(os.path.join(ckpt, "model_acc.txt"), "w") as w:
+        for epoch in range(1, args.num_epochs + 1):
+            t0 = time.time()
+            loss = train_epoch()
+            losses.append(loss)
+            acc = evaluate()
+            accs.append(acc)
+            log("| epoch {:3d} | time: {:5.2f}s | loss {:5.2f} | test acc {:5.2f} | ".format(epoch, time.time() - t0, loss, acc * 100))
+            # the reference's StepLR (step_size = batches/epoch, stepped at most once per epoch) never changes the lr
+            w.write("epoch " + str(epoch) + " fold " + str(args.fold_idx) + " acc " + str(acc * 100) + "%\n")
+    return accs, losses
+
+
+if __name__ == "__main__":
+    run(parse_args())
