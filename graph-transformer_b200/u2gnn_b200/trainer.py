@@ -13,6 +13,7 @@ import torch.distributed as dist
 from . import engine as E
 from ._lib import LIB
 from .model import TransformerU2GNN, TransformerU2GNNUnSup, _layer_param_dicts
+from .parallel import all_reduce_sum_
 
 
 class FlatArena:
@@ -161,8 +162,12 @@ class UnSupTrainer:
     device by the log-uniform sampler (or injected with `sample_ids`).  loss = sum of per-node losses
     (train_pytorch_U2GNN_UnSup.py:156)."""
 
-    def __init__(self, model: TransformerU2GNNUnSup, lr=5e-3, max_norm=0.5, seed=123):
+    def __init__(self, model: TransformerU2GNNUnSup, lr=5e-3, max_norm=0.5, seed=123, row_shard=None, global_vocab=None):
+        """row_shard (parallel.RowShard): data-parallel mode with the class table row-sharded in contiguous blocks
+        aligned with graph ownership — `model.ss.weight` then holds only this rank's rows [lo, hi) and `global_vocab`
+        is the size of the whole table (the sampler's range)."""
         self.model, self.lr, self.max_norm = model, lr, max_norm
+        self.row_shard, self.global_vocab = row_shard, global_vocab
         self.arena = FlatArena(model)
         self.seed, self.steps = seed, 0
         self.L, self.T = model.num_U2GNN_layers, model.num_self_att_layers
@@ -182,9 +187,10 @@ class UnSupTrainer:
         N, d = X.shape
         D = d * self.L
         V = m.ss.weight.shape[0]
+        rs = self.row_shard
         if sample_ids is None:
-            if self.sampler is None:
-                self.sampler = LogUniformSampler(V, X.device)
+            if self.sampler is None:          # every rank draws the SAME ids (replicated engine state, seed 1111)
+                self.sampler = LogUniformSampler(self.global_vocab if rs is not None else V, X.device)
             sample_ids = self.sampler.sample_device(m.sampled_num)
         transpose = E.IndexTranspose(input_x, N) if (self.L > 1 and axis == "neighbors" and m.deterministic) else None
         src, saved = X, []
@@ -202,16 +208,39 @@ class UnSupTrainer:
         vec = torch.empty_like(cat)
         LIB.call("u2gnn_dropout_apply", cat.data_ptr(), cat.numel(), drop.seed, E.STREAM_CONCAT, thr, vec.data_ptr(), s)
         W = m.ss.weight.data
+        ns = sample_ids.numel()
+        self.arena.zero_grad()
+        if rs is None:
+            W_use, V_use, labels, ids, dW_use = W, V, input_y, sample_ids, self.arena.gviews["ss.weight"]
+        else:
+            # row-sharded table: true-class rows are local (graph-aligned blocks); the ns sampled rows are assembled
+            # on every rank by one all-reduce of an [ns, D] buffer (owners fill their rows, the gather kernel skips
+            # ids outside the local block) and appended to the local block as rows V .. V+ns-1
+            local_ids = (sample_ids - rs.lo).contiguous()
+            W_use = torch.empty((V + ns, D), dtype=torch.float32, device=X.device)
+            W_use[:V].copy_(W)
+            samp = W_use[V:]
+            samp.zero_()
+            LIB.call("u2gnn_gather_rows", W.data_ptr(), V, D, local_ids.data_ptr(), ns, 1, samp.data_ptr(), s)
+            all_reduce_sum_(samp)
+            V_use = V + ns
+            labels = (input_y - rs.lo).contiguous()
+            ids = torch.arange(V, V + ns, dtype=torch.int64, device=X.device)
+            dW_use = torch.zeros((V + ns, D), dtype=torch.float32, device=X.device)
         node_loss = torch.empty(N, dtype=torch.float32, device=X.device)
         denom = torch.empty(N, dtype=torch.float32, device=X.device)
-        LIB.call("u2gnn_sampled_softmax_fwd", vec.data_ptr(), input_y.data_ptr(), N, D, W.data_ptr(), V,
-                 sample_ids.data_ptr(), sample_ids.numel(), node_loss.data_ptr(), denom.data_ptr(), s)
-        self.arena.zero_grad()
+        LIB.call("u2gnn_sampled_softmax_fwd", vec.data_ptr(), labels.data_ptr(), N, D, W_use.data_ptr(), V_use,
+                 ids.data_ptr(), ns, node_loss.data_ptr(), denom.data_ptr(), s)
         dloss = torch.ones(N, dtype=torch.float32, device=X.device)
         dvec = torch.empty_like(vec)
-        LIB.call("u2gnn_sampled_softmax_bwd", dloss.data_ptr(), vec.data_ptr(), input_y.data_ptr(), N, D, W.data_ptr(), V,
-                 sample_ids.data_ptr(), sample_ids.numel(), denom.data_ptr(), dvec.data_ptr(),
-                 self.arena.gviews["ss.weight"].data_ptr(), s)
+        LIB.call("u2gnn_sampled_softmax_bwd", dloss.data_ptr(), vec.data_ptr(), labels.data_ptr(), N, D, W_use.data_ptr(), V_use,
+                 ids.data_ptr(), ns, denom.data_ptr(), dvec.data_ptr(), dW_use.data_ptr(), s)
+        if rs is not None:
+            gW = self.arena.gviews["ss.weight"]
+            LIB.call("u2gnn_axpy", 1.0, dW_use.data_ptr(), gW.data_ptr(), V * D, s)            # local true-class rows
+            d_samp = dW_use[V:]
+            all_reduce_sum_(d_samp)                                                             # sampled-row gradients of all ranks
+            LIB.call("u2gnn_scatter_add_rows", d_samp.data_ptr(), ns, D, local_ids.data_ptr(), 1, gW.data_ptr(), V, s)
         dcat = torch.empty_like(dvec)
         LIB.call("u2gnn_dropout_apply", dvec.data_ptr(), dvec.numel(), drop.seed, E.STREAM_CONCAT, thr, dcat.data_ptr(), s)
         dsrc_next = None
@@ -228,5 +257,23 @@ class UnSupTrainer:
                                           need_dsrc=(l > 0), transpose=transpose)
             saved[l] = None
         if apply:
-            self.arena.clip_adam_step(self.lr, self.max_norm, all_reduce=True, want_norm=False)
+            if rs is None:
+                self.arena.clip_adam_step(self.lr, self.max_norm, all_reduce=True, want_norm=False)
+            else:
+                self._sharded_clip_adam()
         return node_loss
+
+    def _sharded_clip_adam(self):
+        """Encoder gradients are all-reduced, table gradients stay local; the clip norm is global:
+        |g|^2 = |g_encoder (reduced)|^2 + sum over ranks |g_table_local|^2."""
+        a, s = self.arena, E._stream()
+        n_table = self.model.ss.weight.numel()
+        n_enc = a.total - ((n_table + 3) // 4 * 4)
+        all_reduce_sum_(a.g[:n_enc])
+        a.sumsq.zero_()
+        LIB.call("u2gnn_grad_sqnorm", a.g.data_ptr() + 4 * n_enc, a.total - n_enc, a.sumsq.data_ptr(), s)
+        all_reduce_sum_(a.sumsq)
+        LIB.call("u2gnn_grad_sqnorm", a.g.data_ptr(), n_enc, a.sumsq.data_ptr(), s)
+        a.step_count += 1
+        LIB.call("u2gnn_clip_adam", a.p.data_ptr(), a.g.data_ptr(), a.m.data_ptr(), a.v.data_ptr(), a.total,
+                 a.sumsq.data_ptr(), self.max_norm, self.lr, 0.9, 0.999, 1e-8, a.step_count, s)
