@@ -149,6 +149,120 @@ __global__ void __launch_bounds__(256) copy_rows_kernel(const float* __restrict_
     }
 }
 
+
+// ---- vectorised variants (d = 4 * LPR, LPR lanes per row, 32 / LPR rows per warp): 128-bit accesses, one dropout
+//      keep word per float4 (its 4 elements share a 32-element group because d % 4 == 0)
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float4 drop4(const DropRng& rng, int low, uint64_t e, float4 v) {
+    if (rng.thr == 0) return v;
+    const uint32_t w = rng_keep_word_lo(rng.keys, e >> 5, rng.thr, low) >> (e & 31);
+    v.x = (w & 1u) ? v.x * rng.scale : 0.0f;
+    v.y = (w & 2u) ? v.y * rng.scale : 0.0f;
+    v.z = (w & 4u) ? v.z * rng.scale : 0.0f;
+    v.w = (w & 8u) ? v.w * rng.scale : 0.0f;
+    return v;
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict__ res, const float* __restrict__ a, int64_t M,
+                                                         DropRng rng, int low, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float* __restrict__ z,
+                                                         float* __restrict__ y, float* __restrict__ stats) {
+    constexpr int D = 4 * LPR, RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float4 g4 = reinterpret_cast<const float4*>(gamma)[l], b4 = reinterpret_cast<const float4*>(beta)[l];
+    const float inv_d = 1.0f / (float)D;
+    for (int64_t r0 = warp * RPW; r0 < M; r0 += nwarps * RPW) {
+        const int64_t r = r0 + sub;
+        const bool ok = r < M;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) {
+            v = drop4(rng, low, (uint64_t)(r * D + 4 * l), __ldg(reinterpret_cast<const float4*>(a + r * D) + l));
+            if (res) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(res + r * D) + l);
+                v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+            }
+            reinterpret_cast<float4*>(z + r * D)[l] = v;
+        }
+        const float mean = group_sum<LPR>((v.x + v.y) + (v.z + v.w)) * inv_d;
+        const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+        const float rstd = rsqrtf(group_sum<LPR>((dx * dx + dy * dy) + (dz * dz + dw * dw)) * inv_d + kLnEps);
+        if (ok) {
+            reinterpret_cast<float4*>(y + r * D)[l] = make_float4(dx * rstd * g4.x + b4.x, dy * rstd * g4.y + b4.y,
+                                                                  dz * rstd * g4.z + b4.z, dw * rstd * g4.w + b4.w);
+            if (l == 0 && stats) {
+                stats[2 * r] = mean;
+                stats[2 * r + 1] = rstd;
+            }
+        }
+    }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                                                         const float* __restrict__ stats, int64_t M,
+                                                         const float* __restrict__ gamma, DropRng rng, int low,
+                                                         float* __restrict__ dz, float* __restrict__ da,
+                                                         float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    constexpr int D = 4 * LPR, RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float4 g4 = reinterpret_cast<const float4*>(gamma)[l];
+    const float inv_d = 1.0f / (float)D;
+    float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r0 = warp * RPW; r0 < M; r0 += nwarps * RPW) {
+        const int64_t r = r0 + sub;
+        const bool ok = r < M;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f), x = g;
+        float mean = 0.f, rstd = 0.f;
+        if (ok) {
+            g = __ldg(reinterpret_cast<const float4*>(dy + r * D) + l);
+            x = __ldg(reinterpret_cast<const float4*>(z + r * D) + l);
+            mean = stats[2 * r];
+            rstd = stats[2 * r + 1];
+        }
+        const float4 xh = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd, (x.w - mean) * rstd);
+        const float4 dh = make_float4(g.x * g4.x, g.y * g4.y, g.z * g4.z, g.w * g4.w);
+        ag.x = fmaf(g.x, xh.x, ag.x); ag.y = fmaf(g.y, xh.y, ag.y); ag.z = fmaf(g.z, xh.z, ag.z); ag.w = fmaf(g.w, xh.w, ag.w);
+        ab.x += g.x; ab.y += g.y; ab.z += g.z; ab.w += g.w;
+        const float m1 = group_sum<LPR>((dh.x + dh.y) + (dh.z + dh.w)) * inv_d;
+        const float m2 = group_sum<LPR>((dh.x * xh.x + dh.y * xh.y) + (dh.z * xh.z + dh.w * xh.w)) * inv_d;
+        if (ok) {
+            const float4 o = make_float4(rstd * (dh.x - m1 - xh.x * m2), rstd * (dh.y - m1 - xh.y * m2),
+                                         rstd * (dh.z - m1 - xh.z * m2), rstd * (dh.w - m1 - xh.w * m2));
+            reinterpret_cast<float4*>(dz + r * D)[l] = o;
+            if (da) reinterpret_cast<float4*>(da + r * D)[l] = drop4(rng, low, (uint64_t)(r * D + 4 * l), o);
+        }
+    }
+    // reduce the row groups of the warp, then one atomic per column per warp
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+        ag.x += __shfl_xor_sync(0xffffffffu, ag.x, o); ag.y += __shfl_xor_sync(0xffffffffu, ag.y, o);
+        ag.z += __shfl_xor_sync(0xffffffffu, ag.z, o); ag.w += __shfl_xor_sync(0xffffffffu, ag.w, o);
+        ab.x += __shfl_xor_sync(0xffffffffu, ab.x, o); ab.y += __shfl_xor_sync(0xffffffffu, ab.y, o);
+        ab.z += __shfl_xor_sync(0xffffffffu, ab.z, o); ab.w += __shfl_xor_sync(0xffffffffu, ab.w, o);
+    }
+    if (sub == 0) {
+        if (dgamma) { atomicAdd(dgamma + 4 * l, ag.x); atomicAdd(dgamma + 4 * l + 1, ag.y); atomicAdd(dgamma + 4 * l + 2, ag.z); atomicAdd(dgamma + 4 * l + 3, ag.w); }
+        if (dbeta) { atomicAdd(dbeta + 4 * l, ab.x); atomicAdd(dbeta + 4 * l + 1, ab.y); atomicAdd(dbeta + 4 * l + 2, ab.z); atomicAdd(dbeta + 4 * l + 3, ab.w); }
+    }
+}
+
+bool vec_ok(int d, const void* a, const void* b, const void* c, const void* e, const void* f) {
+    if (d != 16 && d != 32 && d != 64 && d != 128) return false;
+    const uintptr_t m = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+                        reinterpret_cast<uintptr_t>(e) | reinterpret_cast<uintptr_t>(f);
+    return (m % 16) == 0;
+}
+
 DropRng make_rng(uint64_t seed, uint32_t stream, int thr) {
     DropRng r;
     r.keys = rng_keys(seed, stream);
@@ -165,6 +279,18 @@ extern "C" int u2gnn_add_dropout_ln_fwd(const float* res, const float* a, int64_
     if (!a || !gamma || !beta || !z || !y || M < 0 || d <= 0 || thr < 0 || thr > 255) return U2GNN_EINVAL;
     if (d > 32 * kMaxSlots) return U2GNN_EUNSUPPORTED;
     if (M == 0) return U2GNN_OK;
+    if (vec_ok(d, res, a, z, y, gamma) && reinterpret_cast<uintptr_t>(beta) % 16 == 0) {
+        const DropRng rng = make_rng(seed, rng_stream, thr);
+        const int low = rng_thr_low(thr);
+        const int rpb = 8 * (128 / d);                       // rows per 256-thread block
+        const int grid = grid_for(M, rpb, 8);
+        cudaStream_t st = as_stream(stream);
+        if (d == 16) ln_fwd_vec_kernel<4><<<grid, 256, 0, st>>>(res, a, M, rng, low, gamma, beta, z, y, stats);
+        else if (d == 32) ln_fwd_vec_kernel<8><<<grid, 256, 0, st>>>(res, a, M, rng, low, gamma, beta, z, y, stats);
+        else if (d == 64) ln_fwd_vec_kernel<16><<<grid, 256, 0, st>>>(res, a, M, rng, low, gamma, beta, z, y, stats);
+        else ln_fwd_vec_kernel<32><<<grid, 256, 0, st>>>(res, a, M, rng, low, gamma, beta, z, y, stats);
+        U2GNN_CHECK_LAUNCH();
+    }
     add_dropout_ln_fwd_kernel<<<grid_for(M, 8, 8), 256, 0, as_stream(stream)>>>(res, a, M, d, make_rng(seed, rng_stream, thr),
                                                                                gamma, beta, z, y, stats);
     U2GNN_CHECK_LAUNCH();
@@ -176,6 +302,17 @@ extern "C" int u2gnn_add_dropout_ln_bwd(const float* dy, const float* z, const f
     if (!dy || !z || !stats || !gamma || !dz || M < 0 || d <= 0 || thr < 0 || thr > 255) return U2GNN_EINVAL;
     if (d > 32 * kMaxSlots) return U2GNN_EUNSUPPORTED;
     if (M == 0) return U2GNN_OK;
+    if (vec_ok(d, dy, z, dz, da, gamma)) {
+        const DropRng rng = make_rng(seed, rng_stream, thr);
+        const int low = rng_thr_low(thr);
+        const int grid = grid_for(M, 64 * (128 / d), 4);
+        cudaStream_t st = as_stream(stream);
+        if (d == 16) ln_bwd_vec_kernel<4><<<grid, 256, 0, st>>>(dy, z, stats, M, gamma, rng, low, dz, da, dgamma, dbeta);
+        else if (d == 32) ln_bwd_vec_kernel<8><<<grid, 256, 0, st>>>(dy, z, stats, M, gamma, rng, low, dz, da, dgamma, dbeta);
+        else if (d == 64) ln_bwd_vec_kernel<16><<<grid, 256, 0, st>>>(dy, z, stats, M, gamma, rng, low, dz, da, dgamma, dbeta);
+        else ln_bwd_vec_kernel<32><<<grid, 256, 0, st>>>(dy, z, stats, M, gamma, rng, low, dz, da, dgamma, dbeta);
+        U2GNN_CHECK_LAUNCH();
+    }
     // fewer, fatter warps than the forward: each warp flushes d atomics at the end
     add_dropout_ln_bwd_kernel<<<grid_for(M, 64, 2), 256, 0, as_stream(stream)>>>(dy, z, stats, M, d, gamma,
                                                                                 make_rng(seed, rng_stream, thr), dz, da,

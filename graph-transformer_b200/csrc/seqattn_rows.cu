@@ -216,6 +216,131 @@ __global__ void __launch_bounds__(NT) seqattn_rows_bwd_kernel(const float* __res
     }
 }
 
+
+// ---- last timestep of a U2GNN layer (dead-row elimination): only query position 0 of every node is live.
+//      One thread per node; K / V rows are read straight from global memory (each thread streams its node's
+//      contiguous [S, 3D] block), scores live in a per-thread shared-memory scratch row.
+template <int D, int NT>
+__global__ void __launch_bounds__(NT) seqattn_last_fwd_kernel(const float* __restrict__ qkv, int64_t B, int S, AttnRng rng,
+                                                              float* __restrict__ ctx) {
+    __shared__ float Ps[NT * PP];
+    float* pr = Ps + threadIdx.x * PP;
+    const float qscale = sqrtf(1.0f / (float)D);
+    for (int64_t b = (int64_t)blockIdx.x * NT + threadIdx.x; b < B; b += (int64_t)gridDim.x * NT) {
+        const float* base = qkv + b * S * 3 * D;
+        float a[D];
+#pragma unroll
+        for (int c = 0; c < D; c += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(base + c));
+            a[c] = v.x * qscale; a[c + 1] = v.y * qscale; a[c + 2] = v.z * qscale; a[c + 3] = v.w * qscale;
+        }
+        float m = -INFINITY;
+        for (int j = 0; j < S; ++j) {
+            const float s = dot_row<D>(a, base + (int64_t)j * 3 * D + D);
+            pr[j] = s;
+            m = fmaxf(m, s);
+        }
+        float sum = 0.f;
+        for (int j = 0; j < S; ++j) {
+            const float e = expf(pr[j] - m);
+            pr[j] = e;
+            sum += e;
+        }
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int c = 0; c < D; ++c) a[c] = 0.f;
+        for (int j = 0; j < S; ++j) {
+            const float pd = (pr[j] * inv) * rng_dropout_mult(rng.keys, (uint64_t)b * (uint64_t)S + (uint64_t)j, rng.thr, rng.scale);
+            axpy_row<D>(a, pd, base + (int64_t)j * 3 * D + 2 * D);
+        }
+        float4* out = reinterpret_cast<float4*>(ctx + b * D);
+#pragma unroll
+        for (int c = 0; c < D; c += 4) out[c >> 2] = make_float4(a[c], a[c + 1], a[c + 2], a[c + 3]);
+    }
+}
+
+template <int D, int NT>
+__global__ void __launch_bounds__(NT) seqattn_last_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dctx,
+                                                              int64_t B, int S, AttnRng rng, float* __restrict__ dqkv) {
+    __shared__ float Ps[NT * PP];
+    __shared__ float Ds[NT * PP];
+    float* pr = Ps + threadIdx.x * PP;
+    float* dr = Ds + threadIdx.x * PP;
+    const float qscale = sqrtf(1.0f / (float)D);
+    for (int64_t b = (int64_t)blockIdx.x * NT + threadIdx.x; b < B; b += (int64_t)gridDim.x * NT) {
+        const float* base = qkv + b * S * 3 * D;
+        float* gout = dqkv + b * S * 3 * D;
+        float q[D], g[D];
+#pragma unroll
+        for (int c = 0; c < D; c += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(base + c));
+            q[c] = v.x * qscale; q[c + 1] = v.y * qscale; q[c + 2] = v.z * qscale; q[c + 3] = v.w * qscale;
+            const float4 w = __ldg(reinterpret_cast<const float4*>(dctx + b * D + c));
+            g[c] = w.x; g[c + 1] = w.y; g[c + 2] = w.z; g[c + 3] = w.w;
+        }
+        float m = -INFINITY;
+        for (int j = 0; j < S; ++j) {
+            const float s = dot_row<D>(q, base + (int64_t)j * 3 * D + D);
+            pr[j] = s;
+            m = fmaxf(m, s);
+        }
+        float sum = 0.f;
+        for (int j = 0; j < S; ++j) {
+            const float e = expf(pr[j] - m);
+            pr[j] = e;
+            sum += e;
+        }
+        const float inv = 1.0f / sum;
+        float tsum = 0.f;
+        for (int j = 0; j < S; ++j) {
+            const float mult = rng_dropout_mult(rng.keys, (uint64_t)b * (uint64_t)S + (uint64_t)j, rng.thr, rng.scale);
+            const float p = pr[j] * inv;
+            const float dp = dot_row<D>(g, base + (int64_t)j * 3 * D + 2 * D) * mult;
+            tsum = fmaf(p, dp, tsum);
+            pr[j] = p;
+            dr[j] = dp;
+        }
+        float dq[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) dq[c] = 0.f;
+        for (int j = 0; j < S; ++j) {
+            const float p = pr[j];
+            const float ds = p * (dr[j] - tsum);
+            const float pd = p * rng_dropout_mult(rng.keys, (uint64_t)b * (uint64_t)S + (uint64_t)j, rng.thr, rng.scale);
+            axpy_row<D>(dq, ds, base + (int64_t)j * 3 * D + D);
+            float4* ok = reinterpret_cast<float4*>(gout + (int64_t)j * 3 * D + D);
+            float4* ov = reinterpret_cast<float4*>(gout + (int64_t)j * 3 * D + 2 * D);
+            float4* oq = reinterpret_cast<float4*>(gout + (int64_t)j * 3 * D);
+#pragma unroll
+            for (int c = 0; c < D; c += 4) {
+                ok[c >> 2] = make_float4(ds * q[c], ds * q[c + 1], ds * q[c + 2], ds * q[c + 3]);       // q already carries sqrt(1/d)
+                ov[c >> 2] = make_float4(pd * g[c], pd * g[c + 1], pd * g[c + 2], pd * g[c + 3]);
+                if (j > 0) oq[c >> 2] = make_float4(0.f, 0.f, 0.f, 0.f);                                 // rows without a query
+            }
+        }
+        float4* oq0 = reinterpret_cast<float4*>(gout);
+#pragma unroll
+        for (int c = 0; c < D; c += 4) oq0[c >> 2] = make_float4(dq[c] * qscale, dq[c + 1] * qscale, dq[c + 2] * qscale, dq[c + 3] * qscale);
+    }
+}
+
+template <int D>
+int launch_last_fwd(const float* qkv, int64_t B, int S, AttnRng rng, float* ctx, cudaStream_t st) {
+    constexpr int NT = 128;
+    const int64_t blocks = (B + NT - 1) / NT;
+    const int grid = (int)(blocks < (int64_t)U2GNN_NUM_SMS * 8 ? blocks : (int64_t)U2GNN_NUM_SMS * 8);
+    seqattn_last_fwd_kernel<D, NT><<<grid, NT, 0, st>>>(qkv, B, S, rng, ctx);
+    return 1;
+}
+template <int D>
+int launch_last_bwd(const float* qkv, const float* dctx, int64_t B, int S, AttnRng rng, float* dqkv, cudaStream_t st) {
+    constexpr int NT = 64;
+    const int64_t blocks = (B + NT - 1) / NT;
+    const int grid = (int)(blocks < (int64_t)U2GNN_NUM_SMS * 8 ? blocks : (int64_t)U2GNN_NUM_SMS * 8);
+    seqattn_last_bwd_kernel<D, NT><<<grid, NT, 0, st>>>(qkv, dctx, B, S, rng, dqkv);
+    return 1;
+}
+
 template <int D>
 int launch_fwd(const float* qkv, int64_t B, int S, AttnRng rng, float* ctx, cudaStream_t st) {
     constexpr int NT = 128;
@@ -258,8 +383,13 @@ bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0;
 // thread-per-row kernels handled the call, 0 when the caller must use the warp-per-node kernels.
 int seqattn_rows_try_fwd(const float* qkv, int64_t B, int S, int Sq, int d, uint64_t seed, uint32_t rng_stream, int thr,
                          float* ctx, cudaStream_t st) {
-    if (Sq != S || S < 2 || !aligned16(qkv) || !aligned16(ctx)) return 0;
+    if (S < 2 || !aligned16(qkv) || !aligned16(ctx)) return 0;
     const AttnRng rng = make_rng(seed, rng_stream, thr);
+    if (Sq == 1) {
+        if (d == 64) return launch_last_fwd<64>(qkv, B, S, rng, ctx, st);
+        if (d == 32) return launch_last_fwd<32>(qkv, B, S, rng, ctx, st);
+        return 0;
+    }
     if (d == 64) return launch_fwd<64>(qkv, B, S, rng, ctx, st);
     if (d == 32) return launch_fwd<32>(qkv, B, S, rng, ctx, st);
     return 0;
@@ -267,8 +397,13 @@ int seqattn_rows_try_fwd(const float* qkv, int64_t B, int S, int Sq, int d, uint
 
 int seqattn_rows_try_bwd(const float* qkv, const float* dctx, int64_t B, int S, int Sq, int d, uint64_t seed,
                          uint32_t rng_stream, int thr, float* dqkv, cudaStream_t st) {
-    if (Sq != S || S < 2 || !aligned16(qkv) || !aligned16(dctx) || !aligned16(dqkv)) return 0;
+    if (S < 2 || !aligned16(qkv) || !aligned16(dctx) || !aligned16(dqkv)) return 0;
     const AttnRng rng = make_rng(seed, rng_stream, thr);
+    if (Sq == 1) {
+        if (d == 64) return launch_last_bwd<64>(qkv, dctx, B, S, rng, dqkv, st);
+        if (d == 32) return launch_last_bwd<32>(qkv, dctx, B, S, rng, dqkv, st);
+        return 0;
+    }
     if (d == 64) return launch_bwd<64>(qkv, dctx, B, S, rng, dqkv, st);
     if (d == 32) return launch_bwd<32>(qkv, dctx, B, S, rng, dqkv, st);
     return 0;
