@@ -1,0 +1,356 @@
+// Short-sequence self-attention core on the tensor cores (bf16 mode, attn_axis="neighbors", d = 64, S <= 32).
+//
+// A CTA tile holds NB = 128 / S whole node sequences (S = 17 -> 7 nodes, 119 of 128 rows).  The score matrix of the
+// tile is ONE 128 x 128 x 64 MMA (S_all = Q K^T); only its block diagonal (each node's S x S block) is meaningful
+// and is what the per-row softmax threads read back from tensor memory.  The off-diagonal work is wasted flops on
+// a pipe that is otherwise idle here; what it buys is that every product of the forward and backward is a dense
+// 128-row MMA on operands that are staged once:
+//   forward :  S = Q K^T,  P~ = dropout(softmax(S / sqrt(d))) (block diagonal),  ctx = P~ V
+//   backward:  S = Q K^T,  dP = G V^T,  per row: p, ds = p (dp - sum p dp) / sqrt(d),
+//              dV = P~^T G,  dK = dS^T Q,  dQ = dS K
+// Q, K, V, G tiles are [128 x 64] bf16 swizzled tiles that serve as K-major A / B operands and, unchanged, as
+// MN-major B operands; P~ and dS are written to shared memory as [128 x 128] tiles (zero outside the diagonal
+// blocks) and used both K-major (dQ, ctx) and MN-major (dV, dK).  Same arithmetic as seqattn.cu up to bf16
+// operand rounding; same dropout stream.  Phase-serial CTAs, two per SM.
+#include "common.cuh"
+#include "rng.cuh"
+#include "tc_common.cuh"
+#include "ffn_epi.cuh"
+
+namespace {
+
+constexpr int D = 64, TM = 128;
+constexpr int kThreads = 256;
+
+struct AttnRng {
+    RngKeys keys;
+    int thr;
+    float scale;
+};
+
+// rows [row0, row0 + 128) of a strided fp32 matrix (64 columns at column offset `coff`) -> bf16 swizzled tile
+__device__ __forceinline__ void stage_tile(uint8_t* tile, const float* __restrict__ src, int64_t ld, int coff, int64_t row0,
+                                           int valid_rows, int tid) {
+    for (int base = 0; base < TM * 16; base += kThreads * 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = base + u * kThreads + tid;
+            const int r = e >> 4, c4 = e & 15;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < valid_rows) v[u] = __ldg(reinterpret_cast<const float4*>(src + (row0 + r) * ld + coff) + c4);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = base + u * kThreads + tid;
+            const int r = e >> 4, c4 = e & 15;
+            uint2 w;
+            w.x = epi::cvt2(v[u].x, v[u].y);
+            w.y = epi::cvt2(v[u].z, v[u].w);
+            *reinterpret_cast<uint2*>(tile + tc::sw128_offset(r, c4 * 4)) = w;
+        }
+    }
+}
+
+// one row of a [128 x 128] bf16 operand (two [128 x 64] swizzled tiles `t0`, `t1`): zero it, then place `n` values at
+// columns col0 .. col0 + n - 1
+__device__ __forceinline__ void write_diag_row(uint8_t* t0, uint8_t* t1, int r, int col0, int n, const float* vals) {
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+        *reinterpret_cast<uint4*>(t0 + tc::sw128_chunk(r, ch)) = z;
+        *reinterpret_cast<uint4*>(t1 + tc::sw128_chunk(r, ch)) = z;
+    }
+    for (int j = 0; j < n; ++j) {
+        const int c = col0 + j;
+        uint8_t* t = (c < 64) ? t0 : t1;
+        *reinterpret_cast<__nv_bfloat16*>(t + tc::sw128_offset(r, c & 63)) = __float2bfloat16(vals[j]);
+    }
+}
+
+// D[128 x N] (+)= A(K-major tile(s), K = 64 * kt) * B(K-major tile)^T : used for S = Q K^T and dP = G V^T (kt = 1, N = 128)
+__device__ __forceinline__ void mma_kk(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc) {
+    const uint64_t ad = tc::make_desc_sw128(a_addr, 16, 1024), bd = tc::make_desc_sw128(b_addr, 16, 1024);
+    tc::mma_ss(tmem_d, ad, bd, idesc, 0);
+    tc::mma_ss_acc(tmem_d, ad + 2, bd + 2, idesc);
+    tc::mma_ss_acc(tmem_d, ad + 4, bd + 4, idesc);
+    tc::mma_ss_acc(tmem_d, ad + 6, bd + 6, idesc);
+}
+
+struct Params {
+    const float* qkv;
+    const float* dctx;     // backward only
+    float* out;            // forward: ctx[B*S, 64]; backward: dqkv[B*S, 192]
+    int64_t B;
+    int S;
+    AttnRng rng;
+    int low;
+};
+
+// shared memory layout (bytes): Q 0, K 16K, V 32K (P~ tile 0 reuses V in the backward), G 48K, P~1 / P~ 64K.., dS
+template <bool BWD>
+__global__ void __launch_bounds__(kThreads) attn_tc_kernel(const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + 16384;
+    uint8_t* sV = smem + 32768;
+    uint8_t* sG = smem + 49152;                                  // backward only
+    uint8_t* sP0 = BWD ? sV : smem + 49152;                      // P~ columns 0..63   (backward: over V, dead after dP)
+    uint8_t* sP1 = BWD ? smem + 65536 : smem + 65536;            // P~ columns 64..127
+    uint8_t* sS0 = smem + 81920;                                 // dS columns 0..63   (backward only)
+    uint8_t* sS1 = smem + 98304;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        tc::mbar_init(&bar, 1);
+        tc::fence_barrier_init();
+    }
+    constexpr int kTmemCols = 256;
+    if (warp == 0) tc::tmem_alloc<kTmemCols>(&tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const int S = p.S, NB = TM / S;
+    const float qscale = 0.125f;                                 // sqrt(1/64)
+    const uint32_t idesc_s = tc::make_idesc(128, 128, 0, 0);     // S, dP: K-major A and B
+    const uint32_t idesc_mn = tc::make_idesc(128, 64, 1, 1);     // dV, dK: MN-major A and B
+    const uint32_t idesc_kmn = tc::make_idesc(128, 64, 0, 1);    // ctx, dQ: K-major A, MN-major B
+    const int wq = warp & 3;
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+    const int r = wq * 32 + lane;                                // row handled in the per-row phases
+    const int64_t n_tiles = (p.B + NB - 1) / NB;
+    uint32_t phase = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t node0 = tile * NB;
+        const int nodes = (int)((p.B - node0 < NB) ? p.B - node0 : NB);
+        const int rows = nodes * S;
+        const int64_t row0 = node0 * S;
+        // ---- 1. stage operands
+        stage_tile(sQ, p.qkv, 3 * D, 0, row0, rows, tid);
+        stage_tile(sK, p.qkv, 3 * D, D, row0, rows, tid);
+        stage_tile(sV, p.qkv, 3 * D, 2 * D, row0, rows, tid);
+        if (BWD) stage_tile(sG, p.dctx, D, 0, row0, rows, tid);
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        __syncthreads();
+        tc::tc_fence_after();
+        // ---- 2. S = Q K^T (and dP = G V^T)
+        if (warp == 0) {
+            if (tc::elect_one()) {
+                mma_kk(tmem, tc::smem_u32(sQ), tc::smem_u32(sK), idesc_s);
+                if (BWD) mma_kk(tmem + 128, tc::smem_u32(sG), tc::smem_u32(sV), idesc_s);
+                tc::mma_commit(&bar);
+            }
+            __syncwarp();
+        }
+        tc::mbar_wait(&bar, phase);
+        phase ^= 1;
+        tc::tc_fence_after();
+        // ---- 3. per-row softmax (threads 0..127: row r = node * S + i reads the S columns of its own node)
+        if (warp < 4) {
+            float pd[32], ds[32];
+            const bool live = r < rows;
+            const int node = live ? r / S : 0, i = live ? r - node * S : 0;
+            const int col0 = node * S;
+            // tcgen05.ld takes ONE (warp-uniform) column address, but the 32 rows of a warp belong to up to 32/S + 2 nodes.
+            // Rows and key columns of a tile index the same positions (block diagonal), so the columns any row of this
+            // lane quarter needs lie within [32 wq - (S-1), 32 wq + 31 + (S-1)]: a uniform 96-column window covers them
+            // for every S <= 32.  Each lane then picks its node's S values at a lane-dependent offset (local memory).
+            const int c_start = (wq <= 1) ? 0 : 32;
+            float sw[96], dw[BWD ? 96 : 1];
+            {
+                uint32_t t0[32], t1[32], t2[32];
+                tc::tmem_ld32(tmem + lane_base + c_start, t0);
+                tc::tmem_ld32(tmem + lane_base + c_start + 32, t1);
+                tc::tmem_ld32(tmem + lane_base + c_start + 64, t2);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    sw[j] = __uint_as_float(t0[j]);
+                    sw[32 + j] = __uint_as_float(t1[j]);
+                    sw[64 + j] = __uint_as_float(t2[j]);
+                }
+                if (BWD) {
+                    tc::tmem_ld32(tmem + lane_base + 128 + c_start, t0);
+                    tc::tmem_ld32(tmem + lane_base + 128 + c_start + 32, t1);
+                    tc::tmem_ld32(tmem + lane_base + 128 + c_start + 64, t2);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        dw[j] = __uint_as_float(t0[j]);
+                        dw[(BWD ? 32 : 0) + j] = __uint_as_float(t1[j]);
+                        dw[(BWD ? 64 : 0) + j] = __uint_as_float(t2[j]);
+                    }
+                }
+            }
+            const int off = col0 - c_start;
+            uint32_t sv[32], dv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                sv[j] = (live && j < S) ? __float_as_uint(sw[off + j]) : 0u;
+                dv[j] = (BWD && live && j < S) ? __float_as_uint(dw[BWD ? off + j : 0]) : 0u;
+            }
+            if (live) {
+                float m = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < S) m = fmaxf(m, __uint_as_float(sv[j]) * qscale);
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    pd[j] = (j < S) ? expf(__uint_as_float(sv[j]) * qscale - m) : 0.f;
+                    sum += pd[j];
+                }
+                const float inv = 1.0f / sum;
+                const uint64_t ebase = (uint64_t)((node0 + node) * S + i) * (uint64_t)S;
+                float tsum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (j < S) {
+                        const float mult = rng_dropout_mult(p.rng.keys, ebase + (uint64_t)j, p.rng.thr, p.rng.scale);
+                        const float pj = pd[j] * inv;
+                        if (BWD) {
+                            const float dp = __uint_as_float(dv[j]) * mult;
+                            ds[j] = dp;
+                            tsum = fmaf(pj, dp, tsum);
+                            sv[j] = __float_as_uint(pj);          // keep p for the second pass
+                        }
+                        pd[j] = pj * mult;
+                    }
+                }
+                if (BWD) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < S) ds[j] = __uint_as_float(sv[j]) * (ds[j] - tsum) * qscale;
+                }
+            }
+            // the TMEM reads above must be finished before anyone overwrites S / dP (step 4 reuses the columns); the
+            // shared-memory rows are written after the block-wide barrier below for the backward (P~ reuses V)
+            tc::tc_fence_before();
+            write_diag_row(sP0, sP1, r, col0, live ? S : 0, pd);
+            if (BWD) write_diag_row(sS0, sS1, r, col0, live ? S : 0, ds);
+        }
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        __syncthreads();
+        tc::tc_fence_after();
+        // ---- 4. second round of MMAs
+        if (warp == 0) {
+            if (tc::elect_one()) {
+                if (!BWD) {
+                    // ctx = P~ V : A = P~ K-major (K = 128 keys: 8 k-steps over two tiles), B = V MN-major (16 key rows per k-step)
+                    const uint64_t bd = tc::make_desc_sw128(tc::smem_u32(sV), 16384, 1024);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint64_t ad = tc::make_desc_sw128(tc::smem_u32(ks < 4 ? sP0 : sP1) + (ks & 3) * 32, 16, 1024);
+                        tc::mma_ss(tmem, ad, bd + 128 * ks, idesc_kmn, ks > 0);
+                    }
+                } else {
+                    const uint32_t p0 = tc::smem_u32(sP0), s0 = tc::smem_u32(sS0);
+                    const uint64_t pd_mn = tc::make_desc_sw128(p0, tc::smem_u32(sP1) - p0, 1024);     // MN-major A: M = 128 keys
+                    const uint64_t ds_mn = tc::make_desc_sw128(s0, 16384, 1024);
+                    const uint64_t g_mn = tc::make_desc_sw128(tc::smem_u32(sG), 16384, 1024);
+                    const uint64_t q_mn = tc::make_desc_sw128(tc::smem_u32(sQ), 16384, 1024);
+                    const uint64_t k_mn = tc::make_desc_sw128(tc::smem_u32(sK), 16384, 1024);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        tc::mma_ss(tmem + 128, pd_mn + 128 * ks, g_mn + 128 * ks, idesc_mn, ks > 0);       // dV = P~^T G
+                        tc::mma_ss(tmem + 64, ds_mn + 128 * ks, q_mn + 128 * ks, idesc_mn, ks > 0);        // dK = dS^T Q
+                        const uint64_t ad = tc::make_desc_sw128(tc::smem_u32(ks < 4 ? sS0 : sS1) + (ks & 3) * 32, 16, 1024);
+                        tc::mma_ss(tmem, ad, k_mn + 128 * ks, idesc_kmn, ks > 0);                          // dQ = dS K
+                    }
+                }
+                tc::mma_commit(&bar);
+            }
+            __syncwarp();
+        }
+        tc::mbar_wait(&bar, phase);
+        phase ^= 1;
+        tc::tc_fence_after();
+        // ---- 5. write results (fp32): forward ctx[row, 64]; backward dqkv[row, 192] = [dQ | dK | dV]
+        if (!BWD) {
+            const int half = warp >> 2;                         // 32-column half handled by this warp set
+            uint32_t v[32];
+            tc::tmem_ld32(tmem + lane_base + 32 * half, v);
+            tc::tmem_ld_wait();
+            if (r < rows) {
+                float4* o = reinterpret_cast<float4*>(p.out + (row0 + r) * D + 32 * half);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    o[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            }
+        } else {
+            // 192 columns = 6 pieces of 32: warps 0-3 take pieces 0..2, warps 4-7 pieces 3..5
+            const int pc0 = (warp >> 2) * 3;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                uint32_t v[32];
+                tc::tmem_ld32(tmem + lane_base + 32 * (pc0 + k), v);
+                tc::tmem_ld_wait();
+                if (r < rows) {
+                    float4* o = reinterpret_cast<float4*>(p.out + (row0 + r) * (3 * D) + 32 * (pc0 + k));
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        o[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                }
+            }
+        }
+        tc::tc_fence_before();
+        __syncthreads();
+    }
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<kTmemCols>(tmem);
+}
+
+AttnRng make_rng(uint64_t seed, uint32_t stream, int thr) {
+    AttnRng r;
+    r.keys = rng_keys(seed, stream);
+    r.thr = thr;
+    r.scale = thr ? rng_keep_scale(thr) : 1.0f;
+    return r;
+}
+
+template <bool BWD>
+int launch(const Params& p, cudaStream_t st) {
+    const size_t smem = 1024 + (BWD ? 114688 : 81920);
+    auto k = attn_tc_kernel<BWD>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int NB = TM / p.S;
+    const int64_t n_tiles = (p.B + NB - 1) / NB;
+    const int64_t cap = (int64_t)U2GNN_NUM_SMS * 2 - (BWD ? U2GNN_NUM_SMS : 0);    // backward: 115 KB -> one CTA per SM
+    k<<<(int)(n_tiles < cap ? n_tiles : cap), kThreads, smem, st>>>(p);
+    return U2GNN_OK;
+}
+
+}  // namespace
+
+extern "C" int u2gnn_seqattn_tc_fwd(const float* qkv, int64_t B, int S, int d, uint64_t seed, uint32_t rng_stream, int thr,
+                                    float* ctx, u2gnn_stream_t stream) {
+    if (!qkv || !ctx || B < 0 || thr < 0 || thr > 255) return U2GNN_EINVAL;
+    if (d != D || S < 2 || S > 32) return U2GNN_EUNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(ctx)) % 16) return U2GNN_EALIGN;
+    if (B == 0) return U2GNN_OK;
+    Params p;
+    p.qkv = qkv; p.dctx = nullptr; p.out = ctx; p.B = B; p.S = S;
+    p.rng = make_rng(seed, rng_stream, thr);
+    p.low = rng_thr_low(thr);
+    launch<false>(p, as_stream(stream));
+    U2GNN_CHECK_LAUNCH();
+}
+
+extern "C" int u2gnn_seqattn_tc_bwd(const float* qkv, const float* dctx, int64_t B, int S, int d, uint64_t seed,
+                                    uint32_t rng_stream, int thr, float* dqkv, u2gnn_stream_t stream) {
+    if (!qkv || !dctx || !dqkv || B < 0 || thr < 0 || thr > 255) return U2GNN_EINVAL;
+    if (d != D || S < 2 || S > 32) return U2GNN_EUNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dctx) | reinterpret_cast<uintptr_t>(dqkv)) % 16) return U2GNN_EALIGN;
+    if (B == 0) return U2GNN_OK;
+    Params p;
+    p.qkv = qkv; p.dctx = dctx; p.out = dqkv; p.B = B; p.S = S;
+    p.rng = make_rng(seed, rng_stream, thr);
+    p.low = rng_thr_low(thr);
+    launch<true>(p, as_stream(stream));
+    U2GNN_CHECK_LAUNCH();
+}

@@ -269,18 +269,21 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams
                 tc::mbar_wait(&bars.s_full[i], scount & 1);
                 ++scount;
                 tc::tc_fence_after();
-                uint32_t hp[32];
                 const uint32_t s_addr = tmem + lane_base + COL_S + 128 * i + 64 * wg;
-#pragma unroll
-                for (int pc = 0; pc < 2; ++pc) {
-                    uint32_t v[32];
-                    tc::tmem_ld32(s_addr + 32 * pc, v);
+                uint32_t v0[32], v1[32];
+                tc::tmem_ld32(s_addr, v0);                      // both 32-column pieces in flight, one wait
+                tc::tmem_ld32(s_addr + 32, v1);
+                uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
+                if (p.thr) {
+                    const uint64_t g = (uint64_t)row * (uint64_t)(p.ff >> 5) + (uint64_t)(4 * c + 2 * wg);
+                    k0 = rng_keep_word_lo(p.keys2, g, p.thr, p.low);
+                    k1 = rng_keep_word_lo(p.keys2, g + 1, p.thr, p.low);
+                }
+                const uint4* bb = reinterpret_cast<const uint4*>(sB1h + ((c * CH + 64 * wg) >> 1));
+                tc::tmem_ld_wait();
+                {
                     uint32_t km[16];
-                    if (p.thr)
-                        epi::keep_masks16(rng_keep_word_lo(p.keys2, (uint64_t)row * (uint64_t)(p.ff >> 5) + (uint64_t)(4 * c + 2 * wg + pc),
-                                                           p.thr, p.low), km);
-                    const uint4* bb = reinterpret_cast<const uint4*>(sB1h + ((c * CH + 64 * wg + 32 * pc) >> 1));
-                    tc::tmem_ld_wait();
+                    if (p.thr) epi::keep_masks16(k0, km);
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) {
                         const uint4 b4 = bb[q4];
@@ -288,13 +291,26 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const int j = 4 * q4 + u;
-                            uint32_t h2 = epi::relu_bias2(epi::cvt2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bw[u]);
+                            uint32_t h2 = epi::relu_bias2(epi::cvt2(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1])), bw[u]);
                             if (p.thr) h2 &= km[j];
-                            hp[pc * 16 + j] = h2;
+                            v0[j] = h2;                            // in place: entries 2j, 2j+1 are already consumed
+                        }
+                    }
+                    if (p.thr) epi::keep_masks16(k1, km);
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const uint4 b4 = bb[4 + q4];
+                        const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = 4 * q4 + u;
+                            uint32_t h2 = epi::relu_bias2(epi::cvt2(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1])), bw[u]);
+                            if (p.thr) h2 &= km[j];
+                            v1[j] = h2;
                         }
                     }
                 }
-                tc::tmem_st32(s_addr, hp);             // H columns [64*wg, 64*wg + 32) of the S_i region: only this thread's own S data lived there
+                tc::tmem_st32_2x16(s_addr, v0, v1);    // H columns [64*wg, 64*wg + 32) of the S_i region: only this thread's own S data lived there
                 tc::tmem_st_wait();
                 tc::tc_fence_before();
                 __syncwarp();

@@ -21,14 +21,19 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(int N, int ts, int rotate
     const uint32_t tmem = tmem_slot;
     if (warp == 1 && rotate >= 2) {
         // whole-warp uniform issue: descriptors stay in uniform registers, k-steps are immediate adds
-        const uint32_t idesc = tc::make_idesc(128, N, 0, 0);
-        const uint64_t ad = tc::make_desc_sw128(tc::smem_u32(smem), 16, 1024);
-        const uint64_t bd = tc::make_desc_sw128(tc::smem_u32(smem + 32768), 16, 1024);
+        const uint32_t idesc = (ts == 2) ? tc::make_idesc(128, N, 1, 1) : tc::make_idesc(128, N, 0, 0);
+        const uint64_t ad = tc::make_desc_sw128(tc::smem_u32(smem), 16384, 1024);
+        const uint64_t bd = tc::make_desc_sw128(tc::smem_u32(smem + 32768), 16384, 1024);
         const uint32_t at = tmem + 448;
         const long long t0 = clock64();
         for (int i = 0; i < count; i += 4) {
             if (tc::elect_one()) {
-                if (ts) {
+                if (ts == 2) {          // both operands MN-major: k-steps advance by 16 rows = 2048 B
+                    tc::mma_ss_acc(tmem, ad, bd, idesc);
+                    tc::mma_ss_acc(tmem, ad + 128, bd + 128, idesc);
+                    tc::mma_ss_acc(tmem, ad + 256, bd + 256, idesc);
+                    tc::mma_ss_acc(tmem, ad + 384, bd + 384, idesc);
+                } else if (ts) {
                     tc::mma_ts_acc(tmem, at, bd, idesc);
                     tc::mma_ts_acc(tmem, at + 8, bd + 2, idesc);
                     tc::mma_ts_acc(tmem, at + 16, bd + 4, idesc);
@@ -70,10 +75,60 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(int N, int ts, int rotate
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc<512>(tmem);
 }
+
+// TMEM -> register bandwidth: `warps` warps (warp % 4 = lane quarter) each issue `iters` x (tcgen05.ld.32x32b.x32 + wait)
+// over rotating column offsets; out[0] = cycles of the slowest warp 0 measurement, out[1] = bytes moved by the CTA.
+__global__ void __launch_bounds__(512) tmem_bw_kernel(int warps, int iters, int batch, long long* out) {
+    __shared__ uint32_t tmem_slot;
+    __shared__ long long t_max;
+    const int t = threadIdx.x, warp = t >> 5;
+    if (t == 0) t_max = 0;
+    if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t acc = 0;
+    __syncthreads();
+    const long long t0 = clock64();
+    if (warp < warps) {
+        for (int i = 0; i < iters; ++i) {
+            uint32_t v[32], w[32];
+            const uint32_t col = (uint32_t)(((i * 2 + (warp >> 2)) * 32) & 511);
+            tc::tmem_ld32(tmem + lane_base + col, v);
+            if (batch > 1) tc::tmem_ld32(tmem + lane_base + ((col + 32) & 511), w);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc ^= v[j];
+            if (batch > 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc ^= w[j];
+            }
+        }
+    }
+    const long long t1 = clock64();
+    atomicMax((unsigned long long*)&t_max, (unsigned long long)(t1 - t0));
+    __syncthreads();
+    if (t == 0) {
+        out[0] = t_max;
+        out[1] = (long long)warps * iters * (batch > 1 ? 2 : 1) * 4096;
+        out[2] = acc;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
 }  // namespace
 
+extern "C" int u2gnn_tmem_bw_probe(int warps, int iters, int batch, long long* out, u2gnn_stream_t stream) {
+    if (!out || warps < 1 || warps > 16 || iters < 1) return U2GNN_EINVAL;
+    tmem_bw_kernel<<<1, 512, 0, as_stream(stream)>>>(warps, iters, batch, out);
+    U2GNN_CHECK_LAUNCH();
+}
+
 extern "C" int u2gnn_tc_probe(int N, int ts, int rotate, int count, long long* out, u2gnn_stream_t stream) {
-    if (!out || N < 16 || N > 256 || N % 16 || count < 1) return U2GNN_EINVAL;
+    if (!out || N < 16 || N > 256 || N % 16 || count < 1 || ts < 0 || ts > 2) return U2GNN_EINVAL;
     const int smem = 65536 + 1024;
     cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     tc_probe_kernel<<<1, 128, smem, as_stream(stream)>>>(N, ts, rotate, count, out);

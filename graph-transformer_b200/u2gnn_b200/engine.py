@@ -270,6 +270,8 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
         LIB.call("u2gnn_softmax_rows_fwd", _ptr(scores), S, S, _ptr(pd), seed, drop_ids[0], thr, _stream())
         sgemm(0, 0, S, d, S, pd, S, qkv, 3 * d, ctx, d, b_off=2 * d)
         sv.probs, sv.pd = scores, pd
+    elif tc_proj and d == 64 and Sq == S and S >= 2:
+        LIB.call("u2gnn_seqattn_tc_fwd", _ptr(qkv), B, S, d, seed, drop_ids[0], thr, _ptr(ctx), _stream())
     else:
         LIB.call("u2gnn_seqattn_fwd", _ptr(qkv), B, S, Sq, d, seed, drop_ids[0], thr, _ptr(ctx), _stream())
     if tc_proj:
@@ -374,6 +376,8 @@ def encoder_layer_bwd(dy2, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
         LIB.call("u2gnn_softmax_rows_bwd", _ptr(sv.probs), _ptr(dpd), S, S, seed, drop_ids[0], thr, _stream())
         sgemm(0, 0, S, d, S, dpd, S, sv.qkv, 3 * d, dqkv, 3 * d, alpha=scale, b_off=d)     # dq = ds @ k * scale
         sgemm(1, 0, S, d, S, dpd, S, sv.qkv, 3 * d, dqkv, 3 * d, alpha=scale, c_off=d)     # dk = ds^T @ q * scale
+    elif tc_proj and d == 64 and Sq == S and S >= 2:
+        LIB.call("u2gnn_seqattn_tc_bwd", _ptr(sv.qkv), _ptr(dctx), B, S, d, seed, drop_ids[0], thr, _ptr(dqkv), _stream())
     else:
         LIB.call("u2gnn_seqattn_bwd", _ptr(sv.qkv), _ptr(dctx), B, S, Sq, d, seed, drop_ids[0], thr, _ptr(dqkv), _stream())
     if tc_proj:

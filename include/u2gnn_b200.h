@@ -200,6 +200,13 @@ int u2gnn_gemm_tc_rows(const float* A, int64_t M, int K, int64_t lda, const floa
 int u2gnn_gemm_tc_wgrad(const float* A, int64_t M, int N1, int64_t lda, const float* B, int N2, int64_t ldb,
                         float* dW, float* db, u2gnn_stream_t stream);
 
+/* ---- short-sequence attention core on the tensor cores (bf16 mode; d = 64, 2 <= S <= 32, every query row live).
+ *      Same contract as u2gnn_seqattn_fwd / _bwd with Sq = S (qkv[B,S,192] -> ctx[B*S,64]; dctx -> dqkv[B*S,192]). */
+int u2gnn_seqattn_tc_fwd(const float* qkv, int64_t B, int S, int d, uint64_t seed, uint32_t rng_stream, int thr,
+                         float* ctx, u2gnn_stream_t stream);
+int u2gnn_seqattn_tc_bwd(const float* qkv, const float* dctx, int64_t B, int S, int d, uint64_t seed,
+                         uint32_t rng_stream, int thr, float* dqkv, u2gnn_stream_t stream);
+
 /* ---- tcgen05 plumbing self-test (csrc/tc_selftest.cu): one CTA runs a [128 x N x K] bf16 GEMM through
  *      each operand path the fused kernels use (mode 0 K-major smem, 1 MN-major smem, 2 A in tensor
  *      memory, 3 bulk-copied pre-swizzled B).  No reference counterpart: it pins hardware layout
@@ -209,6 +216,8 @@ int u2gnn_tc_selftest(int mode, const float* A, const float* B, float* C, int K,
 
 /* tcgen05.mma rate probe (tools/probe_mma.py): out[0] = issue cycles, out[1] = issue+execute cycles of `count` MMAs */
 int u2gnn_tc_probe(int N, int ts, int rotate, int count, long long* out, u2gnn_stream_t stream);
+/* TMEM -> register bandwidth probe: out[0] = cycles, out[1] = bytes */
+int u2gnn_tmem_bw_probe(int warps, int iters, int batch, long long* out, u2gnn_stream_t stream);
 
 #ifdef __cplusplus
 }

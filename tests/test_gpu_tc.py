@@ -257,3 +257,26 @@ def test_gemm_tc_wgrad(U, M, N1, N2):
     torch.cuda.synchronize()
     assert ((dW.double() - ref_w).abs().max() / ref_w.abs().max()).item() < 1e-4
     assert ((db.double() - ref_b).abs().max() / ref_b.abs().max()).item() < 1e-4
+
+
+# ------------------------------------------------------------------ tensor-core attention core vs the fp32 kernels
+@pytest.mark.parametrize("B,S,p", [(7, 17, 0.0), (50, 17, 0.5), (23, 5, 0.5), (9, 32, 0.0), (148 * 7 * 2 + 3, 17, 0.5)])
+def test_seqattn_tc_matches_fp32_kernels(U, B, S, p):
+    from u2gnn_b200 import engine as E
+    d = 64
+    g = torch.Generator(device="cuda").manual_seed(B + S)
+    qkv = torch.randn(B * S, 3 * d, device="cuda", generator=g)
+    dctx = torch.randn(B * S, d, device="cuda", generator=g)
+    thr = E.dropout_threshold(p)
+    ctx32 = torch.empty(B * S, d, device="cuda"); ctx16 = torch.empty_like(ctx32)
+    dq32 = torch.empty(B * S, 3 * d, device="cuda"); dq16 = torch.empty_like(dq32)
+    U.LIB.call("u2gnn_seqattn_fwd", qkv.data_ptr(), B, S, S, d, 77, 5, thr, ctx32.data_ptr(), E._stream())
+    U.LIB.call("u2gnn_seqattn_tc_fwd", qkv.data_ptr(), B, S, d, 77, 5, thr, ctx16.data_ptr(), E._stream())
+    U.LIB.call("u2gnn_seqattn_bwd", qkv.data_ptr(), dctx.data_ptr(), B, S, S, d, 77, 5, thr, dq32.data_ptr(), E._stream())
+    U.LIB.call("u2gnn_seqattn_tc_bwd", qkv.data_ptr(), dctx.data_ptr(), B, S, d, 77, 5, thr, dq16.data_ptr(), E._stream())
+    torch.cuda.synchronize()
+    assert torch.isfinite(ctx16).all() and torch.isfinite(dq16).all()
+    assert ((ctx16 - ctx32).norm() / ctx32.norm()).item() < 2e-2
+    for k, name in enumerate(("dq", "dk", "dv")):
+        a, b = dq16[:, k * d:(k + 1) * d], dq32[:, k * d:(k + 1) * d]
+        assert ((a - b).norm() / b.norm()).item() < 3e-2, name
