@@ -230,7 +230,12 @@ def run_ours(args):
         except Exception:
             pass
         flops_node, bytes_node = algorithmic_per_node(CFG["d"], S, CFG["T"], CFG["ff"], CFG["L"])
-        roof = trainer.roofline(dominant, kern_ms, len(timed), peaks, E.FLOPS)
+        ncu = None
+        try:
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_ffn_summary.json")))
+        except Exception:
+            pass
+        roof = trainer.roofline(dominant, kern_ms, len(timed), peaks, E.FLOPS, ncu)
         line = {"metric": METRIC, "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",

@@ -138,15 +138,24 @@ class SupTrainer:
     def dominant_kernel(self):
         return "u2gnn_sgemm" if self.precision == "fp32" else "u2gnn_ffn_tc_bwd"
 
-    def roofline(self, name, kernel_ms, launches, peaks, flops):
+    def roofline(self, name, kernel_ms, launches, peaks, flops, ncu_summary=None):
         """bench.py roofline object for the dominant kernel: achieved = algorithmic flops / measured time."""
         peak = peaks.get("bf16_tflops_sustained")
         which = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
         if peak is None:
             peak, which = 1590.0, "fallback (B200_PROFILING.md)"
         achieved = flops.get(name, 0) / max(kernel_ms, 1e-9) / 1e9
+        traffic = None
+        if name == "u2gnn_ffn_tc_bwd" and ncu_summary:
+            # DRAM bytes per row from the committed `ncu --set full` capture (dgrad + wgrad device kernels of this one
+            # entry point), scaled to the average rows per timed launch; algorithmic flops per row = 8 d ff
+            per_row = sum(ncu_summary[k]["traffic_bytes_per_launch"] / ncu_summary[k]["rows"]
+                          for k in ("ffn_tc_dgrad_kernel", "ffn_tc_wgrad_kernel") if k in ncu_summary)
+            m = self.model
+            rows = flops.get(name, 0) / (8.0 * m.feature_dim_size * m.ff_hidden_size) / max(launches, 1)
+            traffic = per_row * rows
         return {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "launches_timed": launches,
+                "frac": achieved / peak, "traffic": traffic, "launches_timed": launches,
                 "avg_launch_ms": kernel_ms / max(launches, 1), "peak_source": which,
                 "note": ("fp32 CUDA-core parity path; the tcgen05 path is --precision bf16" if self.precision == "fp32"
                          else "fused bf16 tcgen05 FFN")}
