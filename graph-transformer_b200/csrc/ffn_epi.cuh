@@ -17,6 +17,13 @@ __device__ __forceinline__ uint32_t cvt2(float lo, float hi) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
     return d;
 }
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+// (Measured, tools/trace_ffn.py: replacing cvt.rn.bf16x2 by integer rounding, IADD + IADD + PRMT, is SLOWER - all three
+// land on the same half-rate ALU pipe as F2FP, LOP3 and PRMT, which is the pipe that bounds the chunk epilogue.)
 __device__ __forceinline__ uint32_t relu_bias2(uint32_t x2, uint32_t bias2) {
     uint32_t d;
     asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(x2), "r"(0x3F803F80u), "r"(bias2));
@@ -25,11 +32,6 @@ __device__ __forceinline__ uint32_t relu_bias2(uint32_t x2, uint32_t bias2) {
 __device__ __forceinline__ uint32_t gt0_mask2(uint32_t h2) {
     uint32_t d;
     asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(h2), "r"(0u));
-    return d;
-}
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
-    uint32_t d;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
 }
 

@@ -31,13 +31,16 @@ namespace {
 constexpr int DP = 64;            // padded feature size (K of GEMM1, N of GEMM2)
 constexpr int CH = 128;           // ff chunk
 constexpr int TM = 128;           // rows per tile
-constexpr int STAGES = 4;
-constexpr uint32_t W1_BYTES = CH * DP * 2;       // 16 KB  [128 x 64] K-major image
-constexpr uint32_t W2_BYTES = DP * CH * 2;       // 16 KB  two [64 x 64] K-major images
-constexpr uint32_t FWD_BLOCK = W1_BYTES + W2_BYTES;
+constexpr int STAGES = 5;                        // weight ring: 16 KB stages, alternating W1c / W2c images
+constexpr uint32_t STAGE_BYTES = CH * DP * 2;    // 16 KB  W1c: [128 x 64] K-major image, W2c: two [64 x 64] K-major images
+constexpr uint32_t XS_ROW_BYTES = 272;           // fp32 staging row: 256 B + 16 B pad (conflict-free thread-per-row access)
+constexpr uint32_t XS_TILE_BYTES = TM * XS_ROW_BYTES;
 // packed weights: per chunk [W2c | W1c | W2Tc | W1Tc] (fwd: first two; dgrad: last three; wgrad: middle two), then b1, b2 (fp32)
 constexpr uint32_t CHUNK_BYTES = 4 * 16384;
-constexpr int kThreads = 640;     // 4 control warps + 16 epilogue warps
+constexpr int kEpiWarps = 16;
+// warp roles (704 threads): 0-15 chunk epilogue, 16-19 row I/O, 20 weight producer, 21 MMA issuer.  80 registers per
+// thread for everyone: moving registers between warpgroups with setmaxnreg was tried and made the MMA and I/O warps spill.
+constexpr int kIoWarp0 = 16, kProdWarp = 20, kMmaWarp = 21, kThreads = 704;
 constexpr uint32_t COL_Y = 0, COL_S = 128, COL_X = 384;
 
 struct FwdParams {
@@ -53,7 +56,10 @@ struct FwdParams {
     float* z;
     float* stats;
     float* xnext;
+    int dbg;             // experiment switches (u2gnn_ffn_tc_debug)
+    uint32_t* trace;     // debug: per-warp clock stamps of CTA 0 (u2gnn_ffn_tc_set_trace); null in production
 };
+constexpr int TRACE_CAP = 1024;   // stamps per warp slot (0 = MMA warp, 1..16 = chunk-epilogue warps, 17..20 = I/O warps)
 
 __device__ __forceinline__ const float* packed_b1(const uint8_t* packed, int ff) {
     return reinterpret_cast<const float*>(packed + (size_t)(ff / CH) * CHUNK_BYTES);
@@ -93,6 +99,7 @@ __global__ void __launch_bounds__(256) ffn_pack_kernel(const float* __restrict__
 // ---------------------------------------------------------------------------------------------
 struct __align__(8) FwdBars {
     uint64_t w_full[STAGES], w_empty[STAGES];
+    uint64_t xs_full[2][2];                 // fp32 staging rows of tile i landed (buffer b)
     uint64_t x_full[2], x_free[2], s_full[2], h_full[2], y_full[2], y_free[2];
 };
 
@@ -106,17 +113,19 @@ __device__ __forceinline__ void issue_gemm1(uint32_t tmem_s, uint32_t tmem_x, ui
     }
     __syncwarp();
 }
-// 8 k-steps of Y_i (+)= H_i W2c^T (A = packed H at S_i columns [0,32) and [64,96); B = two [64 x 64] atoms of W2c)
+// 8 k-steps of Y_i (+)= H_i W2c^T.  A = packed H: the epilogue warp that owns S columns [32j, 32j+32) writes its 32
+// hidden units as 16 packed columns at S column 32j, so k-step k reads columns 32*(k/2) + 8*(k%2).
+// B = two [64 x 64] K-major atoms of W2c.
 __device__ __forceinline__ void issue_gemm2(uint32_t tmem_y, uint32_t tmem_h, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
     if (tc::elect_one()) {
         tc::mma_ts(tmem_y, tmem_h, b_desc, idesc, acc);
         tc::mma_ts_acc(tmem_y, tmem_h + 8, b_desc + 2, idesc);
-        tc::mma_ts_acc(tmem_y, tmem_h + 16, b_desc + 4, idesc);
-        tc::mma_ts_acc(tmem_y, tmem_h + 24, b_desc + 6, idesc);
+        tc::mma_ts_acc(tmem_y, tmem_h + 32, b_desc + 4, idesc);
+        tc::mma_ts_acc(tmem_y, tmem_h + 40, b_desc + 6, idesc);
         tc::mma_ts_acc(tmem_y, tmem_h + 64, b_desc + 512, idesc);           // second K atom: +8192 B
         tc::mma_ts_acc(tmem_y, tmem_h + 72, b_desc + 514, idesc);
-        tc::mma_ts_acc(tmem_y, tmem_h + 80, b_desc + 516, idesc);
-        tc::mma_ts_acc(tmem_y, tmem_h + 88, b_desc + 518, idesc);
+        tc::mma_ts_acc(tmem_y, tmem_h + 96, b_desc + 516, idesc);
+        tc::mma_ts_acc(tmem_y, tmem_h + 104, b_desc + 518, idesc);
     }
     __syncwarp();
 }
@@ -125,11 +134,27 @@ __device__ __forceinline__ void commit_to(uint64_t* bar) {
     __syncwarp();
 }
 
+// Warp roles (704 threads):
+//   warps  0-15  chunk epilogue: ALL sixteen warps convert the S of ONE tile (32 columns x 32 lanes each) while the
+//                tensor pipe runs the other tile's GEMMs, then swap: per-tile latency is half of an 8-warp split
+//   warps 16-19  row I/O, off the critical path: per-row 256-byte bulk copies into a padded fp32 staging buffer
+//                (prefetched one pair ahead), fp32 -> bf16 conversion into tensor memory, and the output epilogue
+//                (Y + bias, dropout, residual from the staging row, LayerNorm) whose z / xnext rows leave through
+//                per-row bulk stores - no uncoalesced global access anywhere
+//   warp 20      weight producer (16 KB bulk copies, W1c(0) W2c(0) W1c(1) W2c(1) ...), warp 21 MMA issuer + TMEM owner
+template <bool TRACE, bool HALVES>
 __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams p) {
     extern __shared__ uint8_t smem_raw[];
+    uint32_t tr_n = 0;
+    const long long tr_t0 = TRACE ? clock64() : 0;
+    auto stamp = [&](int slot) {
+        if (TRACE && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && tr_n < (uint32_t)TRACE_CAP)
+            p.trace[slot * TRACE_CAP + tr_n++] = (uint32_t)(clock64() - tr_t0);
+    };
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sW = smem;                                    // STAGES x 32 KB
-    uint32_t* sB1h = reinterpret_cast<uint32_t*>(sW + STAGES * FWD_BLOCK);   // b1 as packed bf16 pairs (ff/2 words)
+    uint8_t* sW = smem;                                    // STAGES x 16 KB
+    uint8_t* sX = sW + STAGES * STAGE_BYTES;               // [2 buffers][2 tiles][128 rows x 272 B] fp32 staging
+    uint32_t* sB1h = reinterpret_cast<uint32_t*>(sX + 4 * XS_TILE_BYTES);    // b1 as packed bf16 pairs (ff/2 words)
     float* sB2 = reinterpret_cast<float*>(sB1h + p.ff / 2);                  // 64 floats
     float* sG = sB2 + DP;                                  // gamma, beta (2 x 64)
     __shared__ FwdBars bars;
@@ -145,16 +170,18 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams
             tc::mbar_init(&bars.w_empty[s], 1);
         }
         for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(&bars.x_full[i], 4);      // one arrival per warp of the loading warpgroup
+            tc::mbar_init(&bars.xs_full[0][i], 4);  // one arrival (+ its rows' bytes) per I/O warp
+            tc::mbar_init(&bars.xs_full[1][i], 4);
+            tc::mbar_init(&bars.x_full[i], 4);
             tc::mbar_init(&bars.x_free[i], 1);
             tc::mbar_init(&bars.s_full[i], 1);
-            tc::mbar_init(&bars.h_full[i], 8);      // one arrival per epilogue warp of the tile
+            tc::mbar_init(&bars.h_full[i], HALVES ? kEpiWarps / 2 : kEpiWarps);
             tc::mbar_init(&bars.y_full[i], 1);
             tc::mbar_init(&bars.y_free[i], 4);
         }
         tc::fence_barrier_init();
     }
-    if (warp == 2) tc::tmem_alloc<512>(&tmem_slot);
+    if (warp == kMmaWarp) tc::tmem_alloc<512>(&tmem_slot);
     {   // biases / LayerNorm affine into shared memory
         const float* b1g = packed_b1(p.packed, p.ff);
         for (int e = threadIdx.x; e < p.ff / 2; e += kThreads) sB1h[e] = epi::cvt2(b1g[2 * e], b1g[2 * e + 1]);
@@ -169,24 +196,27 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams
     tc::tc_fence_after();
     const uint32_t tmem = tmem_slot;
 
-    if (warp == 0) {
+    if (warp >= kProdWarp) {
+      if (warp == kProdWarp) {
         // ================= weight producer =================
         if (lane == 0) {
             uint32_t it = 0;
             for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-                for (int c = 0; c < NC; ++c, ++it) {
+                for (int c2 = 0; c2 < 2 * NC; ++c2, ++it) {
                     const uint32_t s = it % STAGES, n = it / STAGES;
                     if (n > 0) tc::mbar_wait(&bars.w_empty[s], (n - 1) & 1);
-                    tc::mbar_arrive_expect_tx(&bars.w_full[s], FWD_BLOCK);
-                    tc::bulk_g2s(sW + s * FWD_BLOCK, p.packed + (size_t)c * CHUNK_BYTES, FWD_BLOCK, &bars.w_full[s]);
+                    tc::mbar_arrive_expect_tx(&bars.w_full[s], STAGE_BYTES);
+                    // even: W1c(c) (second image of the chunk block), odd: W2c(c) (first image)
+                    tc::bulk_g2s(sW + s * STAGE_BYTES, p.packed + (size_t)(c2 >> 1) * CHUNK_BYTES + ((c2 & 1) ? 0 : 16384),
+                                 STAGE_BYTES, &bars.w_full[s]);
                 }
             }
         }
-    } else if (warp == 1) {
+      } else if (warp == kMmaWarp) {
         // ================= MMA issuer: the whole warp runs this code uniformly =================
         const uint32_t idesc1 = tc::make_idesc(TM, CH, 0, 0);
         const uint32_t idesc2 = tc::make_idesc(TM, DP, 0, 0);
-        const uint64_t w_desc0 = tc::make_desc_sw128(tc::smem_u32(sW), 16, 1024);     // stage 0, W2c image
+        const uint64_t w_desc0 = tc::make_desc_sw128(tc::smem_u32(sW), 16, 1024);     // stage 0
         uint32_t it = 0, q = 0;
         uint32_t hcount[2] = {0, 0};
         for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++q) {
@@ -196,18 +226,25 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams
             for (int i = 0; i < 2; ++i) {
                 tc::mbar_wait(&bars.x_full[i], q & 1);
                 tc::tc_fence_after();
-                issue_gemm1(tmem + COL_S + 128 * i, tmem + COL_X + 32 * i,
-                            w_desc0 + (uint64_t)((it % STAGES) * (FWD_BLOCK >> 4) + (W2_BYTES >> 4)), idesc1);
+                issue_gemm1(tmem + COL_S + 128 * i, tmem + COL_X + 32 * i, w_desc0 + (uint64_t)((it % STAGES) * (STAGE_BYTES >> 4)), idesc1);
                 commit_to(&bars.s_full[i]);
+                if (NC == 1) commit_to(&bars.x_free[i]);
             }
-            for (int c = 0; c < NC; ++c, ++it) {
-                const uint32_t s = it % STAGES;
-                const uint64_t w2_desc = w_desc0 + (uint64_t)(s * (FWD_BLOCK >> 4));
-                if (c + 1 < NC) tc::mbar_wait(&bars.w_full[(it + 1) % STAGES], ((it + 1) / STAGES) & 1);
-                const uint64_t w1_next = w_desc0 + (uint64_t)(((it + 1) % STAGES) * (FWD_BLOCK >> 4) + (W2_BYTES >> 4));
+            commit_to(&bars.w_empty[it % STAGES]);
+            ++it;
+            for (int c = 0; c < NC; ++c) {
+                const uint32_t s2 = it % STAGES;                    // W2c(c)
+                const uint32_t s1 = (it + 1) % STAGES;              // W1c(c + 1)
+                tc::mbar_wait(&bars.w_full[s2], (it / STAGES) & 1);
+                if (c + 1 < NC) tc::mbar_wait(&bars.w_full[s1], ((it + 1) / STAGES) & 1);
+                const uint64_t w2_desc = w_desc0 + (uint64_t)(s2 * (STAGE_BYTES >> 4));
+                const uint64_t w1_next = w_desc0 + (uint64_t)(s1 * (STAGE_BYTES >> 4));
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    tc::mbar_wait(&bars.h_full[i], hcount[i] & 1);   // H_i(c) in TMEM (over S_i)
+                    stamp(0);
+                    if (p.dbg & 2) tc::mbar_wait_relaxed(&bars.h_full[i], hcount[i] & 1);
+                    else tc::mbar_wait(&bars.h_full[i], hcount[i] & 1);   // H_i(c) in TMEM (over S_i)
+                    stamp(0);
                     ++hcount[i];
                     if (c == 0 && q > 0) tc::mbar_wait(&bars.y_free[i], (q - 1) & 1);
                     tc::tc_fence_after();
@@ -218,109 +255,209 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams
                         // over it) only after the GEMM2 above has consumed H_i
                         issue_gemm1(tmem + COL_S + 128 * i, tmem + COL_X + 32 * i, w1_next, idesc1);
                         commit_to(&bars.s_full[i]);
-                    } else {
-                        commit_to(&bars.x_free[i]);                  // last GEMM1 of this pair has read X_i
+                        if (c + 2 == NC) commit_to(&bars.x_free[i]);     // last GEMM1 of this pair reads X_i
                     }
                 }
-                commit_to(&bars.w_empty[s]);                         // chunk c weights fully consumed
+                commit_to(&bars.w_empty[s2]);
+                ++it;
+                if (c + 1 < NC) {
+                    commit_to(&bars.w_empty[s1]);
+                    ++it;
+                }
             }
         }
-    } else if (warp >= 4) {
-        // ================= epilogue groups: 8 warps per tile = two 64-column halves x four TMEM lane quarters =====
-        const int i = (warp - 4) >> 3;                  // tile within the pair
-        const int wg = ((warp - 4) >> 2) & 1;           // column half of the 128-wide chunk
+      }
+    } else if (warp < kEpiWarps) {
+        const int ew = warp;
+        // ================= chunk epilogue: 4 column quarters x 4 TMEM lane quarters, both tiles alternately =========
+        const int cq = ew >> 2;                         // 32-column quarter of the 128-wide chunk
         const int wq = warp & 3;                        // TMEM lane quarter
         const int tr = wq * 32 + lane;                  // row in tile
         const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-        uint32_t q = 0, scount = 0;
-        for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++q) {
-            const int64_t row0 = pair * (2 * TM) + (int64_t)i * TM;
-            const int64_t row = row0 + tr;
-            // ---- (a) X tile: the first warpgroup converts one fp32 row per thread to packed bf16 in tensor memory
-            if (wg == 0) {
-                if (q > 0) tc::mbar_wait(&bars.x_free[i], (q - 1) & 1);
-                uint32_t xp[32];
-                if (p.d == DP && row < p.M) {
-                    const float4* src = reinterpret_cast<const float4*>(p.y1 + row * DP);
-                    float4 v[16];
-#pragma unroll
-                    for (int u = 0; u < 16; ++u) v[u] = __ldg(src + u);
-#pragma unroll
-                    for (int u = 0; u < 16; ++u) {
-                        xp[2 * u] = epi::cvt2(v[u].x, v[u].y);
-                        xp[2 * u + 1] = epi::cvt2(v[u].z, v[u].w);
+        const uint32_t s_addr0 = tmem + lane_base + COL_S + 32 * cq;
+        const uint32_t bar_s = tc::smem_u32(&bars.s_full[0]), bar_h = tc::smem_u32(&bars.h_full[0]);
+        const uint32_t b1_addr = tc::smem_u32(sB1h) + 64u * cq;          // 16 packed-bias words per (chunk, quarter)
+        const int thr = p.thr, low = p.low;
+        const RngKeys keys2 = p.keys2;
+        const uint32_t g_per_row = (uint32_t)(p.ff >> 5);
+        const bool leader = (lane == 0);
+        uint32_t scount = 0;
+        auto keep_word = [&](int64_t pair, int c, int i) -> uint32_t {
+            const uint64_t row = (uint64_t)(pair * (2 * TM) + (int64_t)i * TM + tr);
+            return rng_keep_word_lo(keys2, row * g_per_row + (uint64_t)(4 * c + cq), thr, low);
+        };
+        if constexpr (HALVES) {
+            // 8 warps per tile, 64 columns per warp as two 32-column passes (one barrier wait / arrive per chunk): the
+            // two tiles' warps share every scheduler, so one tile's tcgen05.ld latency hides under the other's arithmetic
+            const int i = ew >> 3, wg = (ew >> 2) & 1;      // tile of the pair, 64-column half of the chunk
+            const uint32_t s_addr = tmem + lane_base + COL_S + 128 * i + 64 * wg;
+            const uint32_t b1h = tc::smem_u32(sB1h) + 128u * wg;
+            for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+                const uint64_t row = (uint64_t)(pair * (2 * TM) + (int64_t)i * TM + tr);
+                for (int c = 0; c < NC; ++c, ++scount) {
+                    uint32_t kw[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+                    if (thr) {
+                        const uint64_t g = row * g_per_row + (uint64_t)(4 * c + 2 * wg);
+                        kw[0] = rng_keep_word_lo(keys2, g, thr, low);
+                        kw[1] = rng_keep_word_lo(keys2, g + 1, thr, low);
                     }
+                    stamp(ew + 1);
+                    tc::mbar_wait_addr(bar_s + 8u * i, scount & 1);
+                    stamp(ew + 1);
+                    tc::tc_fence_after();
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t v[32];
+                        tc::tmem_ld32(s_addr + 32 * h, v);
+                        uint32_t km[16], bw[16];
+                        if (thr) epi::keep_masks16(kw[h], km);
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4)
+                            tc::lds128(b1h + (uint32_t)c * 256u + 64u * h + 16u * q4, bw[4 * q4], bw[4 * q4 + 1], bw[4 * q4 + 2], bw[4 * q4 + 3]);
+                        tc::tmem_ld_wait();
+                        if (h == 0) stamp(ew + 1);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            uint32_t h2 = epi::relu_bias2(epi::cvt2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bw[j]);
+                            if (thr) h2 &= km[j];
+                            v[j] = h2;
+                        }
+                        if (h == 1) stamp(ew + 1);
+                        tc::tmem_st16(s_addr + 32 * h, v);
+                    }
+                    tc::tmem_st_wait();
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (leader) tc::mbar_arrive_addr(bar_h + 8u * i);
+                    stamp(ew + 1);
+                }
+            }
+        } else
+        for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+            for (int c = 0; c < NC; ++c, ++scount) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    uint32_t k0 = 0xFFFFFFFFu;
+                    if (thr) k0 = keep_word(pair, c, i);
+                    stamp(ew + 1);
+                    tc::mbar_wait_addr(bar_s + 8u * i, scount & 1);
+                    stamp(ew + 1);
+                    tc::tc_fence_after();
+                    const uint32_t s_addr = s_addr0 + 128 * i;
+                    uint32_t v[32];
+                    tc::tmem_ld32(s_addr, v);
+                    // independent work under the load latency: the 16 pair masks of this step and its packed bias
+                    uint32_t km[16];
+                    if (thr) epi::keep_masks16(k0, km);
+                    uint32_t bw[16];
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4)
+                        tc::lds128(b1_addr + (uint32_t)c * 256u + 16u * q4, bw[4 * q4], bw[4 * q4 + 1], bw[4 * q4 + 2], bw[4 * q4 + 3]);
+                    tc::tmem_ld_wait();
+                    stamp(ew + 1);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        uint32_t h2 = epi::relu_bias2(epi::cvt2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bw[j]);
+                        if (thr) h2 &= km[j];
+                        v[j] = h2;                                 // in place: entries 2j, 2j+1 are already consumed
+                    }
+                    stamp(ew + 1);
+                    tc::tmem_st16(s_addr, v);          // packed H over the first 16 of this thread's own 32 S columns
+                    tc::tmem_st_wait();
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (leader) tc::mbar_arrive_addr(bar_h + 8u * i);
+                    stamp(ew + 1);
+                }
+            }
+        }
+    } else if (warp >= kIoWarp0 && warp < kIoWarp0 + 4) {
+        // ================= row I/O =================
+        const int wq = warp & 3;
+        const int tr = wq * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+        const bool fast = (p.d == DP);
+        auto stage_row = [&](int b, int i) -> uint8_t* { return sX + (size_t)((b * 2 + i) * TM + tr) * XS_ROW_BYTES; };
+        // rows of tile i of the CTA's pair number n -> staging buffer n & 1
+        auto issue_load = [&](int64_t pair, uint32_t n, int i) {
+            const int64_t row0 = pair * (2 * TM) + (int64_t)i * TM + wq * 32;
+            const int64_t row = row0 + lane;
+            uint8_t* dst = stage_row(n & 1, i);
+            uint64_t* bar = &bars.xs_full[n & 1][i];
+            tc::fence_proxy_async();                   // this thread's earlier generic accesses to the row
+            if (fast) {
+                int64_t nv = p.M - row0;
+                nv = nv < 0 ? 0 : (nv > 32 ? 32 : nv);
+                if (lane == 0) {
+                    if (nv > 0) tc::mbar_arrive_expect_tx(bar, (uint32_t)nv * 256u);
+                    else tc::mbar_arrive(bar);
+                }
+                __syncwarp();
+                if (row < p.M) {
+                    tc::bulk_g2s(dst, p.y1 + row * DP, 256, bar);
                 } else {
 #pragma unroll
-                    for (int u = 0; u < 32; ++u) {
-                        const float a = (row < p.M && 2 * u < p.d) ? p.y1[row * p.d + 2 * u] : 0.0f;
-                        const float b = (row < p.M && 2 * u + 1 < p.d) ? p.y1[row * p.d + 2 * u + 1] : 0.0f;
-                        xp[u] = epi::cvt2(a, b);
-                    }
+                    for (int u = 0; u < 16; ++u) reinterpret_cast<float4*>(dst)[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                tc::tmem_st32(tmem + lane_base + COL_X + 32 * i, xp);
-                tc::tmem_st_wait();
-                tc::tc_fence_before();
+            } else {
+                float* drow = reinterpret_cast<float*>(dst);
+                for (int j = 0; j < DP; ++j) drow[j] = (row < p.M && j < p.d) ? __ldg(p.y1 + row * p.d + j) : 0.0f;
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&bars.x_full[i]);
+                if (lane == 0) tc::mbar_arrive(bar);
             }
-            // ---- (b) per chunk: this thread turns 64 columns of its S row into packed bf16 H (written over them)
-            for (int c = 0; c < NC; ++c) {
-                tc::mbar_wait(&bars.s_full[i], scount & 1);
-                ++scount;
+        };
+        auto convert = [&](uint32_t n, int i) {
+            tc::mbar_wait(&bars.xs_full[n & 1][i], (n >> 1) & 1);
+            const float4* src = reinterpret_cast<const float4*>(stage_row(n & 1, i));
+            uint32_t xp[32];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const float4 v = src[u];
+                xp[2 * u] = epi::cvt2(v.x, v.y);
+                xp[2 * u + 1] = epi::cvt2(v.z, v.w);
+            }
+            tc::tmem_st32(tmem + lane_base + COL_X + 32 * i, xp);
+            tc::tmem_st_wait();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&bars.x_full[i]);
+        };
+        // prologue: two pairs of staging loads in flight, first pair converted
+        {
+            const int64_t p0 = blockIdx.x, p1 = p0 + gridDim.x;
+            if (p0 < n_pairs) {
+                issue_load(p0, 0, 0);
+                issue_load(p0, 0, 1);
+                if (p1 < n_pairs) {
+                    issue_load(p1, 1, 0);
+                    issue_load(p1, 1, 1);
+                }
+                convert(0, 0);
+                convert(0, 1);
+            }
+        }
+        uint32_t q = 0;
+        for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++q) {
+            const int64_t next = pair + gridDim.x, next2 = next + gridDim.x;
+            // ---- (a) next pair's X into tensor memory as soon as this pair's last GEMM1 has read the current one
+            if (next < n_pairs) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    tc::mbar_wait(&bars.x_free[i], q & 1);
+                    tc::tc_fence_after();
+                    convert(q + 1, i);
+                }
+            }
+            // ---- (b) Y -> z (in place over the residual row), LayerNorm statistics
+            float mean_[2], rstd_[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int64_t row = pair * (2 * TM) + (int64_t)i * TM + tr;
+                float* srow = reinterpret_cast<float*>(stage_row(q & 1, i));
+                stamp(17 + wq);
+                tc::mbar_wait(&bars.y_full[i], q & 1);
+                stamp(17 + wq);
                 tc::tc_fence_after();
-                const uint32_t s_addr = tmem + lane_base + COL_S + 128 * i + 64 * wg;
-                uint32_t v0[32], v1[32];
-                tc::tmem_ld32(s_addr, v0);                      // both 32-column pieces in flight, one wait
-                tc::tmem_ld32(s_addr + 32, v1);
-                uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
-                if (p.thr) {
-                    const uint64_t g = (uint64_t)row * (uint64_t)(p.ff >> 5) + (uint64_t)(4 * c + 2 * wg);
-                    k0 = rng_keep_word_lo(p.keys2, g, p.thr, p.low);
-                    k1 = rng_keep_word_lo(p.keys2, g + 1, p.thr, p.low);
-                }
-                const uint4* bb = reinterpret_cast<const uint4*>(sB1h + ((c * CH + 64 * wg) >> 1));
-                tc::tmem_ld_wait();
-                {
-                    uint32_t km[16];
-                    if (p.thr) epi::keep_masks16(k0, km);
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        const uint4 b4 = bb[q4];
-                        const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int j = 4 * q4 + u;
-                            uint32_t h2 = epi::relu_bias2(epi::cvt2(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1])), bw[u]);
-                            if (p.thr) h2 &= km[j];
-                            v0[j] = h2;                            // in place: entries 2j, 2j+1 are already consumed
-                        }
-                    }
-                    if (p.thr) epi::keep_masks16(k1, km);
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        const uint4 b4 = bb[4 + q4];
-                        const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int j = 4 * q4 + u;
-                            uint32_t h2 = epi::relu_bias2(epi::cvt2(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1])), bw[u]);
-                            if (p.thr) h2 &= km[j];
-                            v1[j] = h2;
-                        }
-                    }
-                }
-                tc::tmem_st32_2x16(s_addr, v0, v1);    // H columns [64*wg, 64*wg + 32) of the S_i region: only this thread's own S data lived there
-                tc::tmem_st_wait();
-                tc::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&bars.h_full[i]);
-            }
-            if (wg != 0) continue;                      // the per-pair output epilogue is done by one warpgroup per tile
-            // ---- (c) Y -> z, LayerNorm statistics, xnext
-            tc::mbar_wait(&bars.y_full[i], q & 1);
-            tc::tc_fence_after();
-            {
                 uint32_t y0[32], y1r[32];
                 tc::tmem_ld32(tmem + lane_base + COL_Y + 64 * i, y0);
                 tc::tmem_ld32(tmem + lane_base + COL_Y + 64 * i + 32, y1r);
@@ -328,88 +465,123 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&bars.y_free[i]);
-                if (row < p.M) {
-                    float zv[DP];
-                    const bool fast = (p.d == DP);
-                    if (fast) {
-                        uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
-                        if (p.thr) {
-                            k0 = rng_keep_word_lo(p.keys3, (uint64_t)row * 2ull, p.thr, p.low);
-                            k1 = rng_keep_word_lo(p.keys3, (uint64_t)row * 2ull + 1ull, p.thr, p.low);
+                float zv[DP];
+                if (fast) {
+                    uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
+                    if (p.thr) {
+                        k0 = rng_keep_word_lo(p.keys3, (uint64_t)row * 2ull, p.thr, p.low);
+                        k1 = rng_keep_word_lo(p.keys3, (uint64_t)row * 2ull + 1ull, p.thr, p.low);
+                    }
+                    const float sc = p.thr ? p.scale3 : 1.0f;
+                    const float4* rr = reinterpret_cast<const float4*>(srow);
+#pragma unroll
+                    for (int j = 0; j < DP; j += 4) {
+                        const float4 r4 = rr[j >> 2];
+                        const float res[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int jj = j + u;
+                            const float f = __uint_as_float(jj < 32 ? y0[jj] : y1r[jj - 32]) + sB2[jj];
+                            const float mult = (((jj < 32 ? k0 : k1) >> (jj & 31)) & 1u) ? sc : 0.0f;
+                            zv[jj] = res[u] + f * mult;
                         }
-                        const float sc = p.thr ? p.scale3 : 1.0f;
-                        const float4* rr = reinterpret_cast<const float4*>(p.y1 + row * DP);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int j = 0; j < p.d; ++j) {
+                        const float f = __uint_as_float(j < 32 ? y0[j] : y1r[j - 32]) + sB2[j];
+                        const float mult = rng_dropout_mult(p.keys3, (uint64_t)row * (uint64_t)p.d + (uint64_t)j, p.thr, p.scale3);
+                        zv[j] = srow[j] + f * mult;
+                    }
+                    for (int j = p.d; j < DP; ++j) zv[j] = 0.0f;
+                }
+                float sum = 0.0f;
+#pragma unroll
+                for (int j = 0; j < DP; ++j) sum += zv[j];
+                const float inv_d = 1.0f / (float)p.d;
+                const float mean = sum * inv_d;
+                float sq = 0.0f;
+#pragma unroll
+                for (int j = 0; j < DP; ++j) {
+                    const float tt = (j < p.d) ? zv[j] - mean : 0.0f;
+                    sq = fmaf(tt, tt, sq);
+                }
+                const float rstd = rsqrtf(sq * inv_d + 1e-5f);
+                mean_[i] = mean;
+                rstd_[i] = rstd;
+                if (p.stats && row < p.M) {
+                    p.stats[2 * row] = mean;
+                    p.stats[2 * row + 1] = rstd;
+                }
+#pragma unroll
+                for (int j = 0; j < DP; j += 4) reinterpret_cast<float4*>(srow)[j >> 2] = make_float4(zv[j], zv[j + 1], zv[j + 2], zv[j + 3]);
+                if (fast) {
+                    tc::fence_proxy_async();
+                    if (row < p.M) tc::bulk_s2g(p.z + row * DP, srow, 256);
+                    tc::bulk_commit();
+                } else if (row < p.M) {
+#pragma unroll 1
+                    for (int j = 0; j < p.d; ++j) p.z[row * p.d + j] = zv[j];
+                }
+            }
+            // ---- (c) xnext = LayerNorm(z), written over the z row once its bulk store has read it
+            if (p.xnext) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int64_t row = pair * (2 * TM) + (int64_t)i * TM + tr;
+                    float* srow = reinterpret_cast<float*>(stage_row(q & 1, i));
+                    const float mean = mean_[i], rstd = rstd_[i];
+                    if (fast) {
+                        tc::bulk_wait_read<1>();
+                        float4* r4 = reinterpret_cast<float4*>(srow);
 #pragma unroll
                         for (int j = 0; j < DP; j += 4) {
-                            const float4 r4 = __ldg(rr + (j >> 2));
-                            const float res[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int jj = j + u;
-                                const float f = __uint_as_float(jj < 32 ? y0[jj] : y1r[jj - 32]) + sB2[jj];
-                                const float mult = (((jj < 32 ? k0 : k1) >> (jj & 31)) & 1u) ? sc : 0.0f;
-                                zv[jj] = res[u] + f * mult;
-                            }
+                            const float4 zq = r4[j >> 2];
+                            r4[j >> 2] = make_float4((zq.x - mean) * rstd * sG[j] + sG[DP + j],
+                                                     (zq.y - mean) * rstd * sG[j + 1] + sG[DP + j + 1],
+                                                     (zq.z - mean) * rstd * sG[j + 2] + sG[DP + j + 2],
+                                                     (zq.w - mean) * rstd * sG[j + 3] + sG[DP + j + 3]);
                         }
-                    } else {
+                        tc::fence_proxy_async();
+                        if (row < p.M) tc::bulk_s2g(p.xnext + row * DP, srow, 256);
+                        tc::bulk_commit();
+                    } else if (row < p.M) {
 #pragma unroll 1
-                        for (int j = 0; j < p.d; ++j) {
-                            const float f = __uint_as_float(j < 32 ? y0[j] : y1r[j - 32]) + sB2[j];
-                            const float mult = rng_dropout_mult(p.keys3, (uint64_t)row * (uint64_t)p.d + (uint64_t)j, p.thr, p.scale3);
-                            zv[j] = __ldg(p.y1 + row * p.d + j) + f * mult;
-                        }
-                        for (int j = p.d; j < DP; ++j) zv[j] = 0.0f;
-                    }
-                    float sum = 0.0f;
-#pragma unroll
-                    for (int j = 0; j < DP; ++j) sum += zv[j];
-                    const float inv_d = 1.0f / (float)p.d;
-                    const float mean = sum * inv_d;
-                    float sq = 0.0f;
-#pragma unroll
-                    for (int j = 0; j < DP; ++j) {
-                        const float tt = (j < p.d) ? zv[j] - mean : 0.0f;
-                        sq = fmaf(tt, tt, sq);
-                    }
-                    const float rstd = rsqrtf(sq * inv_d + 1e-5f);
-                    if (p.stats) {
-                        p.stats[2 * row] = mean;
-                        p.stats[2 * row + 1] = rstd;
-                    }
-                    if (fast) {
-                        float4* zo = reinterpret_cast<float4*>(p.z + row * DP);
-                        float4* xo = p.xnext ? reinterpret_cast<float4*>(p.xnext + row * DP) : nullptr;
-#pragma unroll
-                        for (int j = 0; j < DP; j += 4) {
-                            zo[j >> 2] = make_float4(zv[j], zv[j + 1], zv[j + 2], zv[j + 3]);
-                            if (xo)
-                                xo[j >> 2] = make_float4((zv[j] - mean) * rstd * sG[j] + sG[DP + j],
-                                                         (zv[j + 1] - mean) * rstd * sG[j + 1] + sG[DP + j + 1],
-                                                         (zv[j + 2] - mean) * rstd * sG[j + 2] + sG[DP + j + 2],
-                                                         (zv[j + 3] - mean) * rstd * sG[j + 3] + sG[DP + j + 3]);
-                        }
-                    } else {
-#pragma unroll 1
-                        for (int j = 0; j < p.d; ++j) {
-                            p.z[row * p.d + j] = zv[j];
-                            if (p.xnext) p.xnext[row * p.d + j] = (zv[j] - mean) * rstd * sG[j] + sG[DP + j];
-                        }
+                        for (int j = 0; j < p.d; ++j) p.xnext[row * p.d + j] = (srow[j] - mean) * rstd * sG[j] + sG[DP + j];
                     }
                 }
             }
+            // ---- (d) the buffer is free once the stores have read it: prefetch the pair after next
+            if (fast) tc::bulk_wait_read<0>();
+            if (next2 < n_pairs) {
+                issue_load(next2, q + 2, 0);
+                issue_load(next2, q + 2, 1);
+            }
         }
+        if (fast) tc::bulk_wait_all<0>();
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 2) tc::tmem_dealloc<512>(tmem);
+    if (warp == kMmaWarp) tc::tmem_dealloc<512>(tmem);
 }
 
 size_t packed_bytes(int ff) { return (size_t)(ff / CH) * CHUNK_BYTES + (size_t)(ff + DP) * sizeof(float); }
 
 }  // namespace
 
+static uint32_t* g_trace = nullptr;
+// debug: device buffer of 17 x 1024 uint32 clock stamps (slot 0 = MMA warp, 1..16 = epilogue warps) written by CTA 0 of
+// the next forward launches; nullptr switches tracing off (tools/trace_ffn.py)
+extern "C" int u2gnn_ffn_tc_set_trace(void* buf) {
+    g_trace = static_cast<uint32_t*>(buf);
+    return U2GNN_OK;
+}
+
+static int g_dbg = 0;
+// experiment switches: bit 0 epilogue polls with test_wait first, bit 1 MMA warp backs off between polls,
+// bit 3 epilogue mapping: 8 warps x 64 columns per tile instead of 16 warps x 32 columns on both tiles
 extern "C" int u2gnn_ffn_tc_debug(int flags) {
-    (void)flags;                       // experiment switches were removed after the pipeline study (profiles/README.md)
+    g_dbg = flags;
     return U2GNN_OK;
 }
 
@@ -445,11 +617,22 @@ extern "C" int u2gnn_ffn_tc_fwd(const float* y1, int64_t M, int d, int ff, const
     p.low = rng_thr_low(thr);
     p.scale3 = thr ? rng_keep_scale(thr) : 1.0f;
     p.gamma = gamma; p.beta = beta; p.z = z; p.stats = stats; p.xnext = xnext;
-    const size_t smem = 1024 + (size_t)STAGES * FWD_BLOCK + (size_t)(ff / 2 + 3 * DP) * sizeof(float);
+    const size_t smem = 1024 + (size_t)STAGES * STAGE_BYTES + 4 * (size_t)XS_TILE_BYTES + (size_t)(ff / 2 + 3 * DP) * sizeof(float);
     if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
-    cudaFuncSetAttribute(ffn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    p.trace = g_trace;
     const int64_t n_pairs = (M + 2 * TM - 1) / (2 * TM);
     const int grid = (int)(n_pairs < U2GNN_NUM_SMS ? n_pairs : U2GNN_NUM_SMS);
-    ffn_tc_fwd_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(p);
+    p.dbg = g_dbg;
+    auto launch = [&](auto kern, int threads) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, threads, smem, as_stream(stream)>>>(p);
+    };
+    if (g_dbg & 8) {
+        if (g_trace) launch(ffn_tc_fwd_kernel<true, true>, kThreads);
+        else launch(ffn_tc_fwd_kernel<false, true>, kThreads);
+    } else {
+        if (g_trace) launch(ffn_tc_fwd_kernel<true, false>, kThreads);
+        else launch(ffn_tc_fwd_kernel<false, false>, kThreads);
+    }
     U2GNN_CHECK_LAUNCH();
 }

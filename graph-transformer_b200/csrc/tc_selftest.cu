@@ -5,8 +5,11 @@
 //   mode 1  C[128,N] = At[K,128]^T * Bt[K,N]   both operands MN-major in shared memory (SS)
 //   mode 2  as mode 0 with A staged in tensor memory (TS)
 //   mode 3  as mode 0 with B brought in by a 1-D bulk copy of a pre-swizzled image (UBLKCP + mbarrier tx)
+//   mode 4  as mode 0 with an fp16 accumulator (idesc c_format = 0); C receives the RAW 32-bit tensor-memory columns
+//   mode 5  as mode 2 with A staged in tensor memory as fp16 pairs (a_format = 0) against a bf16 B
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -34,9 +37,9 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(int mode, const float*
     const uint32_t tmem = tmem_slot;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
 
-    if (mode == 0 || mode == 2 || mode == 3) {
+    if (mode == 0 || mode == 2 || mode == 3 || mode == 4 || mode == 5) {
         // A: [128][K] fp32 row-major -> K/64 K-major tiles
-        if (mode != 2) {
+        if (mode != 2 && mode != 5) {
             for (int e = t; e < 128 * K; e += 128) {
                 int r = e / K, c = e % K;
                 *reinterpret_cast<__nv_bfloat16*>(sA + (c >> 6) * 16384 + tc::sw128_offset(r, c & 63)) = __float2bfloat16(A[e]);
@@ -46,7 +49,15 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(int mode, const float*
             for (int c0 = 0; c0 < K / 2; c0 += 32) {
                 uint32_t v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = tc::pack_bf16(A[t * K + 2 * (c0 + j)], A[t * K + 2 * (c0 + j) + 1]);
+                for (int j = 0; j < 32; ++j) {
+                    const float lo = A[t * K + 2 * (c0 + j)], hi = A[t * K + 2 * (c0 + j) + 1];
+                    if (mode == 5) {
+                        const __half2 h = __floats2half2_rn(lo, hi);
+                        v[j] = *reinterpret_cast<const uint32_t*>(&h);
+                    } else {
+                        v[j] = tc::pack_bf16(lo, hi);
+                    }
+                }
                 tc::tmem_st32(tmem + lane_base + 128 + c0, v);
             }
             tc::tmem_st_wait();
@@ -72,12 +83,14 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(int mode, const float*
         __syncthreads();
         tc::tc_fence_after();
         if (t == 0) {
-            const uint32_t idesc = tc::make_idesc(128, N, 0, 0);
+            uint32_t idesc = tc::make_idesc(128, N, 0, 0);
+            if (mode == 4) idesc &= ~(3u << 4);          // D format: fp16
+            if (mode == 5) idesc &= ~(7u << 7);          // A format: fp16
             for (int ks = 0; ks < K / 16; ++ks) {
                 const uint32_t koff = (uint32_t)((ks >> 2) * 16384 + (ks & 3) * 32);
                 const uint32_t boff = (uint32_t)((ks >> 2) * (N * 128) + (ks & 3) * 32);
                 const uint64_t bd = tc::make_desc_sw128(tc::smem_u32(sB) + boff, 16, 1024);
-                if (mode == 2) {
+                if (mode == 2 || mode == 5) {
                     tc::mma_ts(tmem, tmem + 128 + ks * 8, bd, idesc, ks > 0);
                 } else {
                     const uint64_t ad = tc::make_desc_sw128(tc::smem_u32(sA) + koff, 16, 1024);
@@ -129,7 +142,7 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(int mode, const float*
 extern "C" int u2gnn_tc_selftest(int mode, const float* A, const float* B, float* C, int K, int N, void* scratch,
                                  u2gnn_stream_t stream) {
     if (!A || !B || !C || !scratch) return U2GNN_EINVAL;
-    if (mode < 0 || mode > 3) return U2GNN_EINVAL;
+    if (mode < 0 || mode > 5) return U2GNN_EINVAL;
     if ((N != 64 && N != 128) || K < 16 || K > kMaxK || K % 16) return U2GNN_EINVAL;
     if (mode != 1 && K % 64) return U2GNN_EINVAL;
     const int smem = 65536 + 1024;

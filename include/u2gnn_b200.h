@@ -175,6 +175,9 @@ int u2gnn_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, con
 size_t u2gnn_ffn_tc_packed_bytes(int d, int ff);
 /* experiment switches for profiling the forward pipeline (0 = normal operation) */
 int u2gnn_ffn_tc_debug(int flags);
+/* debug: device buffer of 17 x 1024 uint32 clock stamps written by CTA 0 of the following forward launches
+   (slot 0 = MMA warp, 1..16 = epilogue warps); NULL switches tracing off (tools/trace_ffn.py) */
+int u2gnn_ffn_tc_set_trace(void* buf);
 int u2gnn_ffn_tc_prepare(const float* W1, const float* b1, const float* W2, const float* b2, int d, int ff,
                          float hidden_scale, void* packed, size_t packed_size, u2gnn_stream_t stream);
 int u2gnn_ffn_tc_fwd(const float* y1, int64_t M, int d, int ff, const void* packed, uint64_t seed,

@@ -92,7 +92,8 @@ def _ffn_case(U, M, d, ff, p, seed=11):
 
 @pytest.mark.parametrize("M,d,ff,p", [(256, 64, 256, 0.0), (1000, 64, 2048, 0.0), (37, 64, 128, 0.0), (257, 64, 1024, 0.5),
                                       (300, 7, 256, 0.5), (129, 12, 128, 0.0), (300, 64, 2048, 0.25),
-                                      (148 * 512 + 5, 64, 256, 0.5)])
+                                      (148 * 512 + 5, 64, 256, 0.5), (148 * 256 * 4 + 300, 64, 128, 0.5),
+                                      (148 * 256 * 3 + 129, 12, 128, 0.5)])
 def test_ffn_tc_forward(U, M, d, ff, p):
     z, stats, xn, z_ref, z_emu, mean, rstd, xn_ref = _ffn_case(U, M, d, ff, p)
     scale = np.abs(z_ref).max()
