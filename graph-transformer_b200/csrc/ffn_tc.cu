@@ -569,7 +569,8 @@ size_t packed_bytes(int ff) { return (size_t)(ff / CH) * CHUNK_BYTES + (size_t)(
 
 }  // namespace
 
-static uint32_t* g_trace = nullptr;
+uint32_t* g_ffn_trace = nullptr;     // shared with the dgrad / wgrad launchers
+#define g_trace g_ffn_trace
 // debug: device buffer of 17 x 1024 uint32 clock stamps (slot 0 = MMA warp, 1..16 = epilogue warps) written by CTA 0 of
 // the next forward launches; nullptr switches tracing off (tools/trace_ffn.py)
 extern "C" int u2gnn_ffn_tc_set_trace(void* buf) {

@@ -32,7 +32,9 @@ struct Params {
     int thr, low;
     uint8_t* xb;      // [n_tiles][128 x 64] bf16 swizzled images of y1 / df, consumed by the wgrad kernel (may be null)
     uint8_t* fb;
+    uint32_t* trace;   // debug clock stamps of CTA 0 (u2gnn_ffn_tc_set_trace), slots 32..
 };
+constexpr int TRACE_CAP = 1024;
 
 struct __align__(8) Bars {
     uint64_t w_full[STAGES], w_empty[STAGES];
@@ -88,8 +90,15 @@ __device__ __forceinline__ void load_row_packed(const float* __restrict__ src, i
     }
 }
 
+template <bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const Params p) {
     extern __shared__ uint8_t smem_raw[];
+    uint32_t tr_n = 0;
+    const long long tr_t0 = TRACE ? clock64() : 0;
+    auto stamp = [&](int slot) {
+        if (TRACE && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && tr_n < (uint32_t)TRACE_CAP)
+            p.trace[(32 + slot) * TRACE_CAP + tr_n++] = (uint32_t)(clock64() - tr_t0);
+    };
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sW = smem;                                                        // STAGES x 48 KB
     uint32_t* sB1h = reinterpret_cast<uint32_t*>(sW + STAGES * BLOCK);         // b1 as packed bf16 pairs
@@ -159,7 +168,9 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const Params 
                 const uint64_t wd = w_desc0 + (uint64_t)(s * (BLOCK >> 4));
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
+                    stamp(0);
                     tc::mbar_wait(&bars.a_done[i], acount[i] & 1);     // epilogue has turned S_i into mask registers
+                    stamp(0);
                     ++acount[i];
                     tc::tc_fence_after();
                     issue_n128(tmem + COL_R + 128 * i, tmem + COL_F + 32 * i, wd + 1024, idesc_n128);      // D_i = dF_i W2Tc^T
@@ -169,7 +180,9 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const Params 
                 const uint64_t w1_next = w_desc0 + (uint64_t)(((it + 1) % STAGES) * (BLOCK >> 4));
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
+                    stamp(0);
                     tc::mbar_wait(&bars.p_full[i], pcount[i] & 1);     // dPre_i in TMEM (over R_i)
+                    stamp(0);
                     ++pcount[i];
                     if (c == 0 && q > 0) tc::mbar_wait(&bars.y_free[i], (q - 1) & 1);
                     tc::tc_fence_after();
@@ -195,7 +208,9 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const Params 
         for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++q) {
             const int64_t row = pair * (2 * TM) + (int64_t)i * TM + tr;
             // ---- operands into tensor memory: warpgroup 0 converts X rows, warpgroup 1 converts dF rows
+            stamp(warp - 3);
             if (q > 0) tc::mbar_wait(&bars.x_free[i], (q - 1) & 1);
+            stamp(warp - 3);
             {
                 uint32_t xp[32];
                 load_row_packed(wg == 0 ? p.y1 : p.df, row, p.M, p.d, xp);
@@ -211,11 +226,14 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const Params 
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&bars.x_full[i]);
+                stamp(warp - 3);
             }
             const uint32_t r_addr = tmem + lane_base + COL_R + 128 * i + 64 * wg;
             for (int c = 0; c < NC; ++c) {
                 // ---- epilogue A: S -> packed mask
+                stamp(warp - 3);
                 tc::mbar_wait(&bars.s_full[i], scount & 1);
+                stamp(warp - 3);
                 ++scount;
                 tc::tc_fence_after();
                 uint32_t msk[32];
@@ -245,8 +263,10 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const Params 
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&bars.a_done[i]);
+                stamp(warp - 3);
                 // ---- epilogue B: D -> dPre (packed, over this thread's own R columns)
                 tc::mbar_wait(&bars.d_full[i], dcount & 1);
+                stamp(warp - 3);
                 ++dcount;
                 tc::tc_fence_after();
                 uint32_t hp[32];
@@ -264,7 +284,9 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const Params 
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&bars.p_full[i]);
+                stamp(warp - 3);
             }
+            stamp(warp - 3);
             if (wg != 0) continue;
             // ---- dY + dz -> dy1
             tc::mbar_wait(&bars.y_full[i], q & 1);
@@ -315,9 +337,13 @@ int ffn_tc_dgrad_launch(const float* y1, const float* df, const float* dz, float
     p.fb = static_cast<uint8_t*>(fb);
     const size_t smem = 1024 + (size_t)STAGES * BLOCK + (size_t)(ff / 2) * sizeof(uint32_t);
     if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
-    cudaFuncSetAttribute(ffn_tc_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    extern uint32_t* g_ffn_trace;
+    p.trace = g_ffn_trace;
+    cudaFuncSetAttribute(ffn_tc_dgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(ffn_tc_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int64_t n_pairs = (M + 2 * TM - 1) / (2 * TM);
     const int grid = (int)(n_pairs < U2GNN_NUM_SMS ? n_pairs : U2GNN_NUM_SMS);
-    ffn_tc_dgrad_kernel<<<grid, kThreads, smem, st>>>(p);
+    if (p.trace) ffn_tc_dgrad_kernel<true><<<grid, kThreads, smem, st>>>(p);
+    else ffn_tc_dgrad_kernel<false><<<grid, kThreads, smem, st>>>(p);
     return U2GNN_OK;
 }

@@ -35,10 +35,12 @@ struct Params {
     float* dW1;   // [ff, d]
     float* db1;   // [ff]
     float* dW2;   // [d, ff]
+    uint32_t* trace;   // debug clock stamps of CTA 0 (u2gnn_ffn_tc_set_trace)
 };
+constexpr int TRACE_CAP = 1024;
 
 struct __align__(8) Bars {
-    uint64_t w_full, ld_full[WG_STAGES], ld_free[WG_STAGES], s_full[2], a_done[2], d_full[2], hp_full, hp_free, flush_full;
+    uint64_t w_full, ld_full[WG_STAGES], ld_free[WG_STAGES], s_full[2], a_done[2], d_full[2], b_done[2], hp_full, hp_free, flush_full;
 };
 
 __device__ __forceinline__ void commit_to(uint64_t* bar) {
@@ -65,8 +67,15 @@ __device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint64_t a_desc, ui
     __syncwarp();
 }
 
+template <bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params p) {
     extern __shared__ uint8_t smem_raw[];
+    uint32_t tr_n = 0;
+    const long long tr_t0 = TRACE ? clock64() : 0;
+    auto stamp = [&](int slot) {
+        if (TRACE && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && tr_n < (uint32_t)TRACE_CAP)
+            p.trace[slot * TRACE_CAP + tr_n++] = (uint32_t)(clock64() - tr_t0);
+    };
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sXF = smem;                                   // WG_STAGES x (X 16 KB | dF 16 KB)
     uint8_t* sOnes = smem + WG_STAGES * 32768;             // 16 KB tile of bf16 1.0 (after the ring: LBO to it is positive)
@@ -91,10 +100,11 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params 
         }
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&bars.s_full[i], 1);
-            tc::mbar_init(&bars.a_done[i], 8);
+            tc::mbar_init(&bars.a_done[i], 16);
             tc::mbar_init(&bars.d_full[i], 1);
+            tc::mbar_init(&bars.b_done[i], 16);
         }
-        tc::mbar_init(&bars.hp_full, 8);
+        tc::mbar_init(&bars.hp_full, 16);
         tc::mbar_init(&bars.hp_free, 1);
         tc::mbar_init(&bars.flush_full, 1);
         tc::fence_barrier_init();
@@ -139,27 +149,20 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params 
             const uint64_t w2td = w1d + 1024;
             const uint64_t hd = tc::make_desc_sw128(tc::smem_u32(sH), 16384, 1024);        // MN-major A: LBO = next 64-hidden tile
             const uint64_t pd = tc::make_desc_sw128(tc::smem_u32(sP), 16384, 1024);
+            // Issue order (tensor pipe executes in order):  S(0) | D(0) S(1) | D(1) S(2) W(0) | D(2) S(3) W(1) | ...
+            // i.e. the S / D GEMMs run one tile ahead of the weight-gradient GEMMs, so that D(n+1) does not queue behind
+            // W(n) and the epilogue group of tile n+1 computes dPre while the other group is still storing H / dPre of
+            // tile n.  S(n+2) overwrites the region D(n) lived in: it waits for b_done(n) (D(n) is in registers).
             tc::mbar_wait(&bars.w_full, 0);
             tc::mbar_wait(&bars.ld_full[0], 0);
             tc::tc_fence_after();
             issue_n128(tmem + COL_R, xf0, w1d, idesc_n128);
             commit_to(&bars.s_full[0]);
-            for (int64_t n = 0; n < my_tiles; ++n) {
-                const uint32_t i = (uint32_t)(n & 1), ph = (uint32_t)(n >> 1) & 1;
+            auto issue_w = [&](int64_t n) {
                 const uint32_t s = (uint32_t)(n % WG_STAGES);
-                const uint64_t xd = xf0 + (uint64_t)(s * 2048);            // X tile of this stage (K-major view)
-                tc::mbar_wait(&bars.a_done[i], ph);
-                tc::tc_fence_after();
-                issue_n128(tmem + COL_R + 128 * i, xd + 1024, w2td, idesc_n128);            // D = dF W2Tc^T
-                commit_to(&bars.d_full[i]);
-                if (n + 1 < my_tiles) {
-                    const uint32_t s2 = (uint32_t)((n + 1) % WG_STAGES);
-                    tc::mbar_wait(&bars.ld_full[s2], (uint32_t)((n + 1) / WG_STAGES) & 1);
-                    tc::tc_fence_after();
-                    issue_n128(tmem + COL_R + 128 * (i ^ 1), xf0 + (uint64_t)(s2 * 2048), w1d, idesc_n128);
-                    commit_to(&bars.s_full[i ^ 1]);
-                }
+                stamp(0);
                 tc::mbar_wait(&bars.hp_full, (uint32_t)n & 1);
+                stamp(0);
                 tc::tc_fence_after();
                 // MN-major B views of the same X / dF tiles: dF has one 64-wide group; [X | ones] has two, the second
                 // one LBO bytes further (the ones tile)
@@ -170,73 +173,113 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params 
                 issue_wgrad(tmem + COL_DW1, pd, xd_mn, idesc_w1, n > 0);
                 commit_to(&bars.hp_free);
                 commit_to(&bars.ld_free[s]);
+                stamp(0);
+            };
+            for (int64_t n = 0; n < my_tiles; ++n) {
+                const uint32_t i = (uint32_t)(n & 1), ph = (uint32_t)(n >> 1) & 1;
+                const uint32_t s = (uint32_t)(n % WG_STAGES);
+                const uint64_t xd = xf0 + (uint64_t)(s * 2048);            // X tile of this stage (K-major view)
+                stamp(0);
+                tc::mbar_wait(&bars.a_done[i], ph);
+                stamp(0);
+                tc::tc_fence_after();
+                issue_n128(tmem + COL_R + 128 * i, xd + 1024, w2td, idesc_n128);            // D(n) = dF W2Tc^T
+                commit_to(&bars.d_full[i]);
+                if (n + 1 < my_tiles) {
+                    const uint32_t s2 = (uint32_t)((n + 1) % WG_STAGES);
+                    tc::mbar_wait(&bars.ld_full[s2], (uint32_t)((n + 1) / WG_STAGES) & 1);
+                    if (n >= 1) tc::mbar_wait(&bars.b_done[i ^ 1], (uint32_t)((n - 1) >> 1) & 1);   // D(n-1) has left R_{i^1}
+                    tc::tc_fence_after();
+                    issue_n128(tmem + COL_R + 128 * (i ^ 1), xf0 + (uint64_t)(s2 * 2048), w1d, idesc_n128);   // S(n+1)
+                    commit_to(&bars.s_full[i ^ 1]);
+                }
+                if (n >= 1) issue_w(n - 1);
             }
+            issue_w(my_tiles - 1);
             commit_to(&bars.flush_full);
         } else if (warp >= 4) {
-            const int i = (warp - 4) >> 3;                  // tile parity handled by this group
-            const int wg = ((warp - 4) >> 2) & 1;           // 64-hidden half
+            // ================= epilogue: 16 warps = 4 hidden quarters (32 columns) x 4 TMEM lane quarters, EVERY tile ======
+            // Software-pipelined per warp:  A(n) | B(n-1) store(n-1) | A(n+1) | B(n) store(n) | ...  so that D(n) and
+            // S(n+1) are computed by the tensor pipe while the warps finish tile n-1.
+            const int ew = warp - 4;
+            const int cq = ew >> 2;                         // hidden columns [32 cq, 32 cq + 32) of the chunk
             const int wq = warp & 3;
             const int tr = wq * 32 + lane;
             const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-            const uint32_t r_addr = tmem + lane_base + COL_R + 128 * i + 64 * wg;
-            uint32_t k = 0;
-            for (int64_t n = i; n < my_tiles; n += 2, ++k) {
+            const uint32_t r_addr0 = tmem + lane_base + COL_R + 32 * cq;
+            const uint32_t b1_addr = tc::smem_u32(sB1h) + 64u * cq;
+            const uint32_t hp_off = (uint32_t)((cq >> 1) * 16384) + (uint32_t)tr * 128u;
+            const int ch0 = (cq & 1) * 4;
+            const int thr = p.thr, low = p.low;
+            const RngKeys keys2 = p.keys2;
+            const uint32_t g_per_row = (uint32_t)(p.ff >> 5);
+            uint32_t hcur[16], hprev[16];
+            uint32_t bw[16];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) tc::lds128(b1_addr + 16u * q4, bw[4 * q4], bw[4 * q4 + 1], bw[4 * q4 + 2], bw[4 * q4 + 3]);
+            auto phase_a = [&](int64_t n) {                // S(n) -> H = relu(bf16(S) + b1) & keep      (registers hcur)
+                const uint32_t i = (uint32_t)(n & 1);
                 const int64_t row = ((int64_t)slice + n * n_slices) * TM + tr;
-                // ---- S -> H = relu(bf16(S) + b1) & keep
-                tc::mbar_wait(&bars.s_full[i], k & 1);
+                uint32_t k0 = 0xFFFFFFFFu;
+                if (thr) k0 = rng_keep_word_lo(keys2, (uint64_t)row * g_per_row + (uint64_t)(4 * c + cq), thr, low);
+                stamp(warp - 3);
+                tc::mbar_wait(&bars.s_full[i], (uint32_t)(n >> 1) & 1);
+                stamp(warp - 3);
                 tc::tc_fence_after();
-                uint32_t hreg[32], preg[32];
+                uint32_t v[32];
+                tc::tmem_ld32(r_addr0 + 128 * i, v);
+                uint32_t km[16];
+                if (thr) epi::keep_masks16(k0, km);
+                tc::tmem_ld_wait();
 #pragma unroll
-                for (int pc = 0; pc < 2; ++pc) {
-                    uint32_t v[32];
-                    tc::tmem_ld32(r_addr + 32 * pc, v);
-                    uint32_t km[16];
-                    if (p.thr)
-                        epi::keep_masks16(rng_keep_word_lo(p.keys2, (uint64_t)row * (uint64_t)(p.ff >> 5) + (uint64_t)(4 * c + 2 * wg + pc),
-                                                           p.thr, p.low), km);
-                    const uint4* bb = reinterpret_cast<const uint4*>(sB1h + 32 * wg + 16 * pc);
-                    tc::tmem_ld_wait();
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        const uint4 b4 = bb[q4];
-                        const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int j = 4 * q4 + u;
-                            uint32_t h2 = epi::relu_bias2(epi::cvt2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bw[u]);
-                            if (p.thr) h2 &= km[j];
-                            hreg[pc * 16 + j] = h2;
-                        }
-                    }
+                for (int j = 0; j < 16; ++j) {
+                    uint32_t h2 = epi::relu_bias2(epi::cvt2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bw[j]);
+                    if (thr) h2 &= km[j];
+                    hcur[j] = h2;
                 }
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&bars.a_done[i]);
-                // ---- D -> dPre = bf16(D) & [H > 0]
-                tc::mbar_wait(&bars.d_full[i], k & 1);
+                stamp(warp - 3);
+            };
+            auto phase_b = [&](int64_t n) {                // D(n) -> dPre = bf16(D) & [H > 0];  H, dPre -> shared memory
+                const uint32_t i = (uint32_t)(n & 1);
+                stamp(warp - 3);
+                tc::mbar_wait(&bars.d_full[i], (uint32_t)(n >> 1) & 1);
+                stamp(warp - 3);
                 tc::tc_fence_after();
-#pragma unroll
-                for (int pc = 0; pc < 2; ++pc) {
-                    uint32_t v[32];
-                    tc::tmem_ld32(r_addr + 32 * pc, v);
-                    tc::tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        preg[pc * 16 + j] = epi::cvt2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])) & epi::gt0_mask2(hreg[pc * 16 + j]);
-                }
+                uint32_t v[32];
+                tc::tmem_ld32(r_addr0 + 128 * i, v);
+                tc::tmem_ld_wait();
                 tc::tc_fence_before();
-                // ---- H, dPre -> shared memory: this thread's row of the 64-hidden tile `wg`
-                if (n > 0) tc::mbar_wait(&bars.hp_free, (uint32_t)(n - 1) & 1);
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bars.b_done[i]);
+                uint32_t pr[16];
 #pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                    const uint32_t off = (uint32_t)(wg * 16384) + tc::sw128_chunk(tr, ch);
-                    *reinterpret_cast<uint4*>(sH + off) = make_uint4(hreg[4 * ch], hreg[4 * ch + 1], hreg[4 * ch + 2], hreg[4 * ch + 3]);
-                    *reinterpret_cast<uint4*>(sP + off) = make_uint4(preg[4 * ch], preg[4 * ch + 1], preg[4 * ch + 2], preg[4 * ch + 3]);
+                for (int j = 0; j < 16; ++j)
+                    pr[j] = epi::cvt2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])) & epi::gt0_mask2(hprev[j]);
+                stamp(warp - 3);
+                if (n > 0) tc::mbar_wait(&bars.hp_free, (uint32_t)(n - 1) & 1);
+                stamp(warp - 3);
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    const uint32_t off = hp_off + (uint32_t)(((ch0 + ch) ^ (tr & 7)) << 4);
+                    *reinterpret_cast<uint4*>(sH + off) = make_uint4(hprev[4 * ch], hprev[4 * ch + 1], hprev[4 * ch + 2], hprev[4 * ch + 3]);
+                    *reinterpret_cast<uint4*>(sP + off) = make_uint4(pr[4 * ch], pr[4 * ch + 1], pr[4 * ch + 2], pr[4 * ch + 3]);
                 }
                 tc::fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&bars.hp_full);
+                stamp(warp - 3);
+            };
+            for (int64_t n = 0; n < my_tiles; ++n) {
+                phase_a(n);
+                if (n > 0) phase_b(n - 1);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) hprev[j] = hcur[j];
             }
+            phase_b(my_tiles - 1);
+            const int i = ew >> 3, wg = (ew >> 2) & 1;      // flush: first warpgroup
             // ---- flush the chunk's weight gradients (first warpgroup; thread <-> hidden unit)
             if (i == 0 && wg == 0) {
                 tc::mbar_wait(&bars.flush_full, 0);
@@ -288,12 +331,16 @@ int ffn_tc_wgrad_launch(const void* xb, const void* fb, int64_t M, int d, int ff
     p.hidden_scale = hidden_scale;
     p.dW1 = dW1; p.db1 = db1; p.dW2 = dW2;
     const size_t smem = 1024 + (size_t)WG_STAGES * 32768 + 16384 + 3 * 32768 + 512;
-    cudaFuncSetAttribute(ffn_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    extern uint32_t* g_ffn_trace;
+    p.trace = g_ffn_trace;
+    cudaFuncSetAttribute(ffn_tc_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(ffn_tc_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int NC = ff / CH;
     const int64_t n_tiles = (M + TM - 1) / TM;
     int n_slices = U2GNN_NUM_SMS / NC;
     if (n_slices < 1) n_slices = 1;
     if (n_slices > n_tiles) n_slices = (int)n_tiles;
-    ffn_tc_wgrad_kernel<<<NC * n_slices, kThreads, smem, st>>>(p);
+    if (p.trace) ffn_tc_wgrad_kernel<true><<<NC * n_slices, kThreads, smem, st>>>(p);
+    else ffn_tc_wgrad_kernel<false><<<NC * n_slices, kThreads, smem, st>>>(p);
     return U2GNN_OK;
 }

@@ -134,3 +134,40 @@ extern "C" int u2gnn_tc_probe(int N, int ts, int rotate, int count, long long* o
     tc_probe_kernel<<<1, 128, smem, as_stream(stream)>>>(N, ts, rotate, count, out);
     U2GNN_CHECK_LAUNCH();
 }
+
+// ---------------------------------------------------------------------------------------------
+// L2 reduction throughput probe: `groups` CTAs add into the SAME 32 KB tile at about the same time (the access pattern
+// of split-K partial sums of a [128 x 64] fp32 tile), tile after tile.  mode 0: red.global.add.v4.f32 (16 B per op),
+// mode 1: scalar atomicAdd, mode 2: plain 16-byte stores (bandwidth reference).
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(128) red_probe_kernel(float* __restrict__ buf, int64_t n_tiles, int groups, int mode) {
+    const int slice = blockIdx.x / groups, n_slices = gridDim.x / groups;
+    const float v = 1.0f;
+    for (int64_t tile = slice; tile < n_tiles; tile += n_slices) {
+        float* row = buf + tile * 8192 + (size_t)threadIdx.x * 64;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            // lanes of a warp cover consecutive 16-byte pieces: thread t handles piece (j * 128 + t) of the 2048 in the tile
+            float* dst = buf + tile * 8192 + (size_t)(j * 128 + threadIdx.x) * 4;
+            if (mode == 0) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v), "f"(v), "f"(v), "f"(v) : "memory");
+            } else if (mode == 1) {
+                atomicAdd(dst, v); atomicAdd(dst + 1, v); atomicAdd(dst + 2, v); atomicAdd(dst + 3, v);
+            } else if (mode == 2) {
+                *reinterpret_cast<float4*>(dst) = make_float4(v, v, v, v);
+            } else {
+                // thread-per-row pattern (thread t owns row t: 16 pieces 256 B apart across the warp)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + 4 * j), "f"(v), "f"(v), "f"(v), "f"(v) : "memory");
+            }
+        }
+    }
+}
+}  // namespace
+
+extern "C" int u2gnn_red_probe(float* buf, int64_t n_tiles, int groups, int mode, u2gnn_stream_t stream) {
+    if (!buf || n_tiles < 1 || groups < 1 || groups > U2GNN_NUM_SMS) return U2GNN_EINVAL;
+    const int n_slices = U2GNN_NUM_SMS / groups;
+    red_probe_kernel<<<groups * n_slices, 128, 0, as_stream(stream)>>>(buf, n_tiles, groups, mode);
+    U2GNN_CHECK_LAUNCH();
+}
