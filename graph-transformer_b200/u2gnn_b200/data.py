@@ -97,3 +97,67 @@ def global_node_ids(graphs, selected):
     """input_y of the unsupervised script (train_pytorch_U2GNN_UnSup.py:96-99): dataset-wide node ids."""
     offs = np.concatenate([[0], np.cumsum([g.n for g in graphs])]).astype(np.int64)
     return np.concatenate([np.arange(offs[i], offs[i + 1]) for i in selected]).astype(np.int64)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# device-side batch builder (SURVEY.md 8(f) row 1)
+# ------------------------------------------------------------------------------------------------------------------
+def dataset_csr(graphs):
+    """Whole dataset as ONE CSR over dataset-wide node ids -> (rowptr int64 [V+1], col int64 [E], graph_start int64 [G+1],
+    features float32 [V, d]).  Neighbour lists keep the order of `Graph.neighbors` (sorted, as the reference's
+    edge_mat-derived dict does after its own sort)."""
+    sizes = np.array([g.n for g in graphs], dtype=np.int64)
+    gstart = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    deg = np.concatenate([[len(nb) for nb in g.neighbors] for g in graphs]).astype(np.int64) if graphs else np.zeros(0, np.int64)
+    rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    parts = [np.asarray(nb, dtype=np.int64) + gstart[gi] for gi, g in enumerate(graphs) for nb in g.neighbors if len(nb)]
+    col = np.concatenate(parts).astype(np.int64) if parts else np.zeros(0, np.int64)
+    X = np.concatenate([g.node_features for g in graphs], 0).astype(np.float32)
+    return rowptr, col, gstart, X
+
+
+class DeviceBatchBuilder:
+    """Keeps the dataset (CSR adjacency + features) in HBM and builds each batch with the CUDA kernels
+    `u2gnn_build_batch` (neighbour sampling, index translation) and `u2gnn_gather_rows` (X_concat): what
+    `get_batch_data` does on the host in the reference (train_pytorch_U2GNN_Sup.py:91-119).  The only host work per
+    batch is the prefix sum over the selected graphs' sizes.  Draws come from the engine's counter-based stream
+    (seed, stream = step), not from numpy's generator: use `build_batch` above to reproduce reference index streams."""
+
+    def __init__(self, graphs, num_neighbors, device="cuda", seed=123):
+        import torch
+        from ._lib import LIB, require_device
+        require_device()
+        self._torch, self._lib = torch, LIB
+        rowptr, col, gstart, X = dataset_csr(graphs)
+        self.k, self.seed, self.step = int(num_neighbors), int(seed), 0
+        self.gstart_host = gstart
+        self.labels_host = np.array([g.label for g in graphs], dtype=np.int64)
+        dev = torch.device(device)
+        self.rowptr = torch.from_numpy(rowptr).to(dev)
+        self.col = torch.from_numpy(col if len(col) else np.zeros(1, np.int64)).to(dev)
+        self.X = torch.from_numpy(X).to(dev)
+        self.device = dev
+
+    def build(self, selected, stream_id=None):
+        """selected: iterable of graph indices -> (input_x [N, k+1] int64, pool rowptr [G+1] int64, X_concat [N, d] f32,
+        labels [G] int64, node_global [N] int64), all on the device."""
+        torch, LIB = self._torch, self._lib
+        from .engine import _ptr, _stream
+        sel = np.asarray(list(selected), dtype=np.int64)
+        sizes = self.gstart_host[sel + 1] - self.gstart_host[sel]
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        N, G = int(off[-1]), len(sel)
+        host = torch.from_numpy(np.concatenate([self.gstart_host[sel], off])).pin_memory()
+        meta = host.to(self.device, non_blocking=True)
+        gstart_d, off_d = meta[:G], meta[G:]
+        input_x = torch.empty((N, self.k + 1), dtype=torch.int64, device=self.device)
+        node_global = torch.empty((N,), dtype=torch.int64, device=self.device)
+        sid = self.step if stream_id is None else int(stream_id)
+        self.step += 1
+        LIB.call("u2gnn_build_batch", _ptr(self.rowptr), _ptr(self.col), _ptr(gstart_d), _ptr(off_d), G, N, self.k, self.seed,
+                 sid & 0xFFFFFFFF, _ptr(input_x), _ptr(node_global), _stream())
+        d = self.X.shape[1]
+        Xc = torch.empty((N, d), dtype=torch.float32, device=self.device)
+        LIB.call("u2gnn_gather_rows", _ptr(self.X), self.X.shape[0], d, _ptr(node_global), N, 1, _ptr(Xc), _stream())
+        labels = torch.from_numpy(self.labels_host[sel]).to(self.device, non_blocking=True)
+        return input_x, off_d, Xc, labels, node_global

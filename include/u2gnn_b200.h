@@ -217,6 +217,18 @@ int u2gnn_seqattn_tc_bwd(const float* qkv, const float* dctx, int64_t B, int S, 
 int u2gnn_tc_selftest(int mode, const float* A, const float* B, float* C, int K, int N, void* scratch,
                       u2gnn_stream_t stream);
 
+/* ---- device-side batch builder (replaces the host loop of get_batch_data,
+        train_pytorch_U2GNN_Sup.py:91-119 / train_pytorch_U2GNN_UnSup.py:96-128).
+        Dataset adjacency as one CSR over dataset-wide node ids (g_rowptr[V+1], g_col[E]); the batch is n_graphs selected
+        graphs: graph_start[g] = first dataset-wide node id of graph g, batch_off[n_graphs+1] = prefix sums of their node
+        counts (= the pooling rowptr), n_nodes = batch_off[n_graphs].  Writes input_x[n_nodes, k+1] (batch-local ids:
+        the node itself, then k neighbours drawn uniformly with replacement; isolated nodes repeat themselves) and, if
+        non-NULL, node_global[n_nodes] (dataset-wide ids: the X_concat gather list / input_y).  The draw is a pure
+        function of (seed, rng_stream, node, slot). ---- */
+int u2gnn_build_batch(const int64_t* g_rowptr, const int64_t* g_col, const int64_t* graph_start,
+                      const int64_t* batch_off, int64_t n_graphs, int64_t n_nodes, int k, uint64_t seed,
+                      uint32_t rng_stream, int64_t* input_x, int64_t* node_global, u2gnn_stream_t stream);
+
 /* tcgen05.mma rate probe (tools/probe_mma.py): out[0] = issue cycles, out[1] = issue+execute cycles of `count` MMAs */
 int u2gnn_tc_probe(int N, int ts, int rotate, int count, long long* out, u2gnn_stream_t stream);
 /* L2 reduction throughput probe (tools/probe_red.py): `groups` CTAs add into the same 32 KB tile, tile after tile;

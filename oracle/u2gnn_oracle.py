@@ -134,6 +134,31 @@ class DropoutSpec:
 # --------------------------------------------------------------------------------------
 # primitive ops
 # --------------------------------------------------------------------------------------
+def sample_neighbors_device_stream(g_rowptr, g_col, graph_start, batch_off, k, seed, stream):
+    """Restatement of the engine's device batch builder (csrc/batch_builder.cu), which replaces the host loop of
+    get_batch_data (train_pytorch_U2GNN_Sup.py:100-114): input_x[b] = [b, k neighbours of b drawn with replacement],
+    isolated nodes repeat themselves; draw (b, j) = (rng_word(keys, b*k + j - 1, plane 0) * deg) >> 32.
+    -> (input_x int64 [N, k+1] batch-local ids, node_global int64 [N])."""
+    g_rowptr = np.asarray(g_rowptr, dtype=np.int64); g_col = np.asarray(g_col, dtype=np.int64)
+    graph_start = np.asarray(graph_start, dtype=np.int64); batch_off = np.asarray(batch_off, dtype=np.int64)
+    N = int(batch_off[-1])
+    gi = np.searchsorted(batch_off, np.arange(N), side="right") - 1
+    shift = batch_off[gi] - graph_start[gi]
+    v = np.arange(N, dtype=np.int64) - shift
+    deg = g_rowptr[v + 1] - g_rowptr[v]
+    out = np.repeat(np.arange(N, dtype=np.int64)[:, None], k + 1, axis=1)
+    if k > 0 and N > 0:
+        k0, k1 = rng_keys(seed, stream)
+        ctr = (np.arange(N, dtype=np.uint64)[:, None] * np.uint64(k) + np.arange(k, dtype=np.uint64)[None, :])
+        r = rng_word(k0, k1, ctr.reshape(-1), 0).astype(np.uint64).reshape(N, k)
+        pick = ((r * deg[:, None].astype(np.uint64)) >> np.uint64(32)).astype(np.int64)
+        has = deg > 0
+        idx = g_rowptr[v][:, None] + pick
+        nb = g_col[np.where(has[:, None], idx, 0)] + shift[:, None]
+        out[:, 1:] = np.where(has[:, None], nb, out[:, 1:])
+    return out, v
+
+
 def gather_rows(table, idx):
     """F.embedding(idx, table) (pytorch_U2GNN_Sup.py:32,39)."""
     return table[idx]
