@@ -89,9 +89,11 @@ struct Params {
 
 // shared memory layout (bytes): Q 0, K 16K, V 32K (P~ tile 0 reuses V in the backward), G 48K, P~1 / P~ 64K.., dS
 template <bool BWD>
-__global__ void __launch_bounds__(kThreads) attn_tc_kernel(const Params p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+__global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const Params p) {
+    // no static shared memory and a 1024-byte aligned dynamic segment: the backward's seven 16 KB tiles (+ 16 bytes for
+    // the barrier and the TMEM slot behind them) then fit TWICE into an SM, so two phase-serial CTAs overlap
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((tc::smem_u32(smem) & 1023u) != 0u) __trap();
     uint8_t* sQ = smem;
     uint8_t* sK = smem + 16384;
     uint8_t* sV = smem + 32768;
@@ -100,8 +102,8 @@ __global__ void __launch_bounds__(kThreads) attn_tc_kernel(const Params p) {
     uint8_t* sP1 = BWD ? smem + 65536 : smem + 65536;            // P~ columns 64..127
     uint8_t* sS0 = smem + 81920;                                 // dS columns 0..63   (backward only)
     uint8_t* sS1 = smem + 98304;
-    __shared__ uint64_t bar;
-    __shared__ uint32_t tmem_slot;
+    uint64_t& bar = *reinterpret_cast<uint64_t*>(smem + (BWD ? 114688 : 81920));
+    uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(smem + (BWD ? 114688 : 81920) + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         tc::mbar_init(&bar, 1);
@@ -270,31 +272,32 @@ __global__ void __launch_bounds__(kThreads) attn_tc_kernel(const Params p) {
         tc::mbar_wait(&bar, phase);
         phase ^= 1;
         tc::tc_fence_after();
-        // ---- 5. write results (fp32): forward ctx[row, 64]; backward dqkv[row, 192] = [dQ | dK | dV]
-        if (!BWD) {
-            const int half = warp >> 2;                         // 32-column half handled by this warp set
-            uint32_t v[32];
-            tc::tmem_ld32(tmem + lane_base + 32 * half, v);
-            tc::tmem_ld_wait();
-            if (r < rows) {
-                float4* o = reinterpret_cast<float4*>(p.out + (row0 + r) * D + 32 * half);
+        // ---- 5. write results (fp32): forward ctx[row, 64]; backward dqkv[row, 192] = [dQ | dK | dV].
+        // Tensor memory -> registers (thread = row) -> fp32 staging in the now dead operand tiles (one 32 KB tile per 64
+        // output columns, 16-byte chunks XOR-swizzled with the row so that both the row-per-thread writes and the
+        // chunk-per-thread reads are conflict free) -> COALESCED 128-bit global stores.
+        {
+            constexpr int NP = BWD ? 3 : 1;                     // 64-column pieces
+            const int half = warp >> 2;                         // 32-column half of a piece handled by this warp
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    o[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-            }
-        } else {
-            // 192 columns = 6 pieces of 32: warps 0-3 take pieces 0..2, warps 4-7 pieces 3..5
-            const int pc0 = (warp >> 2) * 3;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
+            for (int pc = 0; pc < NP; ++pc) {
                 uint32_t v[32];
-                tc::tmem_ld32(tmem + lane_base + 32 * (pc0 + k), v);
+                tc::tmem_ld32(tmem + lane_base + 64 * pc + 32 * half, v);
                 tc::tmem_ld_wait();
-                if (r < rows) {
-                    float4* o = reinterpret_cast<float4*>(p.out + (row0 + r) * (3 * D) + 32 * (pc0 + k));
+                uint8_t* st = smem + pc * 32768 + r * 256;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        o[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4*>(st + (((8 * half + j) ^ (r & 15)) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            tc::tc_fence_before();
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < NP * 8; ++u) {
+                const int e = u * kThreads + tid;
+                const int pc = e >> 11, rr = (e >> 4) & 127, c4 = e & 15;
+                if (rr < rows) {
+                    const uint4 o = *reinterpret_cast<const uint4*>(smem + pc * 32768 + rr * 256 + ((c4 ^ (rr & 15)) << 4));
+                    *reinterpret_cast<uint4*>(p.out + (row0 + rr) * (BWD ? 3 * D : D) + 64 * pc + 4 * c4) = o;
                 }
             }
         }
@@ -315,12 +318,12 @@ AttnRng make_rng(uint64_t seed, uint32_t stream, int thr) {
 
 template <bool BWD>
 int launch(const Params& p, cudaStream_t st) {
-    const size_t smem = 1024 + (BWD ? 114688 : 81920);
+    const size_t smem = (BWD ? 114688 : 81920) + 16;          // tiles + barrier + TMEM slot
     auto k = attn_tc_kernel<BWD>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int NB = TM / p.S;
     const int64_t n_tiles = (p.B + NB - 1) / NB;
-    const int64_t cap = (int64_t)U2GNN_NUM_SMS * 2 - (BWD ? U2GNN_NUM_SMS : 0);    // backward: 115 KB -> one CTA per SM
+    const int64_t cap = (int64_t)U2GNN_NUM_SMS * 2;            // two CTAs per SM (256 TMEM columns each)
     k<<<(int)(n_tiles < cap ? n_tiles : cap), kThreads, smem, st>>>(p);
     return U2GNN_OK;
 }

@@ -578,7 +578,8 @@ extern "C" int u2gnn_ffn_tc_set_trace(void* buf) {
     return U2GNN_OK;
 }
 
-static int g_dbg = 0;
+int g_ffn_dbg = 0;                     // shared with the dgrad launcher (bit 4: dgrad pair kernel)
+#define g_dbg g_ffn_dbg
 // experiment switches: bit 0 epilogue polls with test_wait first, bit 1 MMA warp backs off between polls,
 // bit 3 epilogue mapping: 8 warps x 64 columns per tile instead of 16 warps x 32 columns on both tiles
 extern "C" int u2gnn_ffn_tc_debug(int flags) {

@@ -15,10 +15,20 @@ namespace {
 
 constexpr int DP = 64, CH = 128, TM = 128;
 constexpr uint32_t CHUNK_BYTES = 4 * 16384;   // [W2c | W1c | W2Tc | W1Tc]
-constexpr int STAGES = 4;
 constexpr uint32_t BLOCK = 3 * 16384;         // [W1c | W2Tc | W1Tc]
-constexpr int kThreads = 640;
-constexpr uint32_t COL_Y = 0, COL_R = 128, COL_X = 384, COL_F = 448;
+// NT = row tiles per CTA.  NT = 2: one CTA per SM walks pairs of tiles (640 threads, 512 TMEM columns, 4 weight stages).
+// NT = 1: TWO independent CTAs per SM, one tile each (320 threads, 256 TMEM columns, 2 weight stages), so that the row
+// I/O phase of one CTA (35 % of the NT = 2 kernel's time, tools/trace_ffn_bwd.py) overlaps the chunk loop of the other.
+// Measured: the SAME 11.46 ms per 4 M rows as NT = 2 (11.49 ms) - the chunk loop is bound by the S -> mask -> D -> dPre
+// -> dY chain latency of each tile, not by a shared resource, so only MORE tiles in flight would help and tensor memory
+// holds two.  NT = 2 stays the default (half the L2 weight traffic); NT = 1 is kept behind u2gnn_ffn_tc_debug bit 4.
+template <int NT> struct Cfg {
+    static constexpr int kCtrl = (NT == 2) ? 4 : 2;                 // warp 0 weight producer, warp 1 MMA issuer + TMEM owner
+    static constexpr int kThreads = 32 * (kCtrl + 8 * NT);
+    static constexpr int STAGES = (NT == 2) ? 4 : 2;
+    static constexpr uint32_t COL_Y = 0, COL_R = 64 * NT, COL_X = 192 * NT, COL_F = 224 * NT;
+    static constexpr int kTmemCols = 256 * NT;
+};
 
 struct Params {
     const float* y1;
@@ -37,7 +47,7 @@ struct Params {
 constexpr int TRACE_CAP = 1024;
 
 struct __align__(8) Bars {
-    uint64_t w_full[STAGES], w_empty[STAGES];
+    uint64_t w_full[4], w_empty[4];
     uint64_t x_full[2], x_free[2], s_full[2], a_done[2], d_full[2], p_full[2], y_full[2], y_free[2];
 };
 
@@ -90,8 +100,11 @@ __device__ __forceinline__ void load_row_packed(const float* __restrict__ src, i
     }
 }
 
-template <bool TRACE>
-__global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const Params p) {
+template <bool TRACE, int NT>
+__global__ void __launch_bounds__(Cfg<NT>::kThreads, 3 - NT) ffn_tc_dgrad_kernel(const Params p) {
+    using C_ = Cfg<NT>;
+    constexpr int kThreads = C_::kThreads, STAGES = C_::STAGES, kCtrl = C_::kCtrl;
+    constexpr uint32_t COL_Y = C_::COL_Y, COL_R = C_::COL_R, COL_X = C_::COL_X, COL_F = C_::COL_F;
     extern __shared__ uint8_t smem_raw[];
     uint32_t tr_n = 0;
     const long long tr_t0 = TRACE ? clock64() : 0;
@@ -106,14 +119,14 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const Params 
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NC = p.ff / CH;
-    const int64_t n_pairs = (p.M + 2 * TM - 1) / (2 * TM);
+    const int64_t n_pairs = (p.M + NT * TM - 1) / (NT * TM);      // groups of NT tiles ("pairs" for NT = 2)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             tc::mbar_init(&bars.w_full[s], 1);
             tc::mbar_init(&bars.w_empty[s], 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NT; ++i) {
             tc::mbar_init(&bars.x_full[i], 8);      // X (warpgroup 0) and dF (warpgroup 1): one arrival per warp
             tc::mbar_init(&bars.x_free[i], 1);
             tc::mbar_init(&bars.s_full[i], 1);
@@ -125,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const Params 
         }
         tc::fence_barrier_init();
     }
-    if (warp == 2) tc::tmem_alloc<512>(&tmem_slot);
+    if (warp == 1) tc::tmem_alloc<C_::kTmemCols>(&tmem_slot);
     {
         const float* b1g = reinterpret_cast<const float*>(p.packed + (size_t)NC * CHUNK_BYTES);
         for (int e = threadIdx.x; e < p.ff / 2; e += kThreads) sB1h[e] = epi::cvt2(b1g[2 * e], b1g[2 * e + 1]);
@@ -157,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const Params 
         for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++q) {
             tc::mbar_wait(&bars.w_full[it % STAGES], (it / STAGES) & 1);
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < NT; ++i) {
                 tc::mbar_wait(&bars.x_full[i], q & 1);
                 tc::tc_fence_after();
                 issue_n128(tmem + COL_R + 128 * i, tmem + COL_X + 32 * i, w_desc0 + (uint64_t)((it % STAGES) * (BLOCK >> 4)), idesc_n128);
@@ -167,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const Params 
                 const uint32_t s = it % STAGES;
                 const uint64_t wd = w_desc0 + (uint64_t)(s * (BLOCK >> 4));
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
+                for (int i = 0; i < NT; ++i) {
                     stamp(0);
                     tc::mbar_wait(&bars.a_done[i], acount[i] & 1);     // epilogue has turned S_i into mask registers
                     stamp(0);
@@ -179,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const Params 
                 if (c + 1 < NC) tc::mbar_wait(&bars.w_full[(it + 1) % STAGES], ((it + 1) / STAGES) & 1);
                 const uint64_t w1_next = w_desc0 + (uint64_t)(((it + 1) % STAGES) * (BLOCK >> 4));
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
+                for (int i = 0; i < NT; ++i) {
                     stamp(0);
                     tc::mbar_wait(&bars.p_full[i], pcount[i] & 1);     // dPre_i in TMEM (over R_i)
                     stamp(0);
@@ -198,26 +211,26 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const Params 
                 commit_to(&bars.w_empty[s]);
             }
         }
-    } else if (warp >= 4) {
-        const int i = (warp - 4) >> 3;
-        const int wg = ((warp - 4) >> 2) & 1;
+    } else if (warp >= kCtrl) {
+        const int i = (warp - kCtrl) >> 3;
+        const int wg = ((warp - kCtrl) >> 2) & 1;
         const int wq = warp & 3;
         const int tr = wq * 32 + lane;
         const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
         uint32_t q = 0, scount = 0, dcount = 0;
         for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++q) {
-            const int64_t row = pair * (2 * TM) + (int64_t)i * TM + tr;
+            const int64_t row = pair * (NT * TM) + (int64_t)i * TM + tr;
             // ---- operands into tensor memory: warpgroup 0 converts X rows, warpgroup 1 converts dF rows
-            stamp(warp - 3);
+            stamp(warp - kCtrl + 1);
             if (q > 0) tc::mbar_wait(&bars.x_free[i], (q - 1) & 1);
-            stamp(warp - 3);
+            stamp(warp - kCtrl + 1);
             {
                 uint32_t xp[32];
                 load_row_packed(wg == 0 ? p.y1 : p.df, row, p.M, p.d, xp);
                 tc::tmem_st32(tmem + lane_base + (wg == 0 ? COL_X : COL_F) + 32 * i, xp);
                 uint8_t* img = (wg == 0) ? p.xb : p.fb;
                 if (img) {      // this thread's 128-byte row of the tile image, chunks at their swizzled positions
-                    img += (size_t)(pair * 2 + i) * 16384;
+                    img += (size_t)(pair * NT + i) * 16384;
 #pragma unroll
                     for (int ch = 0; ch < 8; ++ch)
                         *reinterpret_cast<uint4*>(img + tc::sw128_chunk(tr, ch)) = make_uint4(xp[4 * ch], xp[4 * ch + 1], xp[4 * ch + 2], xp[4 * ch + 3]);
@@ -226,14 +239,14 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const Params 
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&bars.x_full[i]);
-                stamp(warp - 3);
+                stamp(warp - kCtrl + 1);
             }
             const uint32_t r_addr = tmem + lane_base + COL_R + 128 * i + 64 * wg;
             for (int c = 0; c < NC; ++c) {
                 // ---- epilogue A: S -> packed mask
-                stamp(warp - 3);
+                stamp(warp - kCtrl + 1);
                 tc::mbar_wait(&bars.s_full[i], scount & 1);
-                stamp(warp - 3);
+                stamp(warp - kCtrl + 1);
                 ++scount;
                 tc::tc_fence_after();
                 uint32_t msk[32];
@@ -263,10 +276,10 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const Params 
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&bars.a_done[i]);
-                stamp(warp - 3);
+                stamp(warp - kCtrl + 1);
                 // ---- epilogue B: D -> dPre (packed, over this thread's own R columns)
                 tc::mbar_wait(&bars.d_full[i], dcount & 1);
-                stamp(warp - 3);
+                stamp(warp - kCtrl + 1);
                 ++dcount;
                 tc::tc_fence_after();
                 uint32_t hp[32];
@@ -284,9 +297,9 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const Params 
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&bars.p_full[i]);
-                stamp(warp - 3);
+                stamp(warp - kCtrl + 1);
             }
-            stamp(warp - 3);
+            stamp(warp - kCtrl + 1);
             if (wg != 0) continue;
             // ---- dY + dz -> dy1
             tc::mbar_wait(&bars.y_full[i], q & 1);
@@ -319,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const Params 
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 2) tc::tmem_dealloc<512>(tmem);
+    if (warp == 1) tc::tmem_dealloc<C_::kTmemCols>(tmem);
 }
 
 }  // namespace
@@ -335,15 +348,23 @@ int ffn_tc_dgrad_launch(const float* y1, const float* df, const float* dz, float
     p.low = rng_thr_low(thr);
     p.xb = static_cast<uint8_t*>(xb);
     p.fb = static_cast<uint8_t*>(fb);
-    const size_t smem = 1024 + (size_t)STAGES * BLOCK + (size_t)(ff / 2) * sizeof(uint32_t);
-    if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
     extern uint32_t* g_ffn_trace;
+    extern int g_ffn_dbg;
     p.trace = g_ffn_trace;
-    cudaFuncSetAttribute(ffn_tc_dgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(ffn_tc_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int64_t n_pairs = (M + 2 * TM - 1) / (2 * TM);
-    const int grid = (int)(n_pairs < U2GNN_NUM_SMS ? n_pairs : U2GNN_NUM_SMS);
-    if (p.trace) ffn_tc_dgrad_kernel<true><<<grid, kThreads, smem, st>>>(p);
-    else ffn_tc_dgrad_kernel<false><<<grid, kThreads, smem, st>>>(p);
-    return U2GNN_OK;
+    auto launch = [&](auto kern, int nt, int threads, int stages) -> int {
+        const size_t smem = 1024 + (size_t)stages * BLOCK + (size_t)(ff / 2) * sizeof(uint32_t);
+        if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const int64_t n_groups = (M + nt * TM - 1) / (nt * TM);
+        const int64_t cap = (int64_t)U2GNN_NUM_SMS * (3 - nt);
+        kern<<<(int)(n_groups < cap ? n_groups : cap), threads, smem, st>>>(p);
+        return U2GNN_OK;
+    };
+    if (g_ffn_dbg & 16) {          // experiment switch: two independent one-tile CTAs per SM
+        if (p.trace) return launch(ffn_tc_dgrad_kernel<true, 1>, 1, Cfg<1>::kThreads, Cfg<1>::STAGES);
+        return launch(ffn_tc_dgrad_kernel<false, 1>, 1, Cfg<1>::kThreads, Cfg<1>::STAGES);
+    }
+    if (p.trace) return launch(ffn_tc_dgrad_kernel<true, 2>, 2, Cfg<2>::kThreads, Cfg<2>::STAGES);
+    return launch(ffn_tc_dgrad_kernel<false, 2>, 2, Cfg<2>::kThreads, Cfg<2>::STAGES);
 }
+

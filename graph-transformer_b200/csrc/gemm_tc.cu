@@ -69,12 +69,13 @@ struct RowsParams {
     float beta;           // C = result + beta * C  (0 or 1)
 };
 
-__global__ void __launch_bounds__(kThreads) gemm_tc_rows_kernel(const RowsParams p) {
+__global__ void __launch_bounds__(kThreads, 3) gemm_tc_rows_kernel(const RowsParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int kt = p.KP / 64;
     uint8_t* sA = smem;                                     // kt tiles of [128 x 64]
     uint8_t* sB = smem + kt * 16384;                        // kt tiles of [NP x 64] (NP*128 B each)
+    uint8_t* sOut = sB + kt * p.NP * 128;                   // fp32 staging of one 64-column output piece: [128 rows x 272 B]
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -82,7 +83,12 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_rows_kernel(const RowsParams
         tc::mbar_init(&bar, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 0) tc::tmem_alloc<256>(&tmem_slot);
+    const int tcols = (p.NP <= 64) ? 64 : (p.NP <= 128 ? 128 : 256);
+    if (warp == 0) {
+        if (tcols == 64) tc::tmem_alloc<64>(&tmem_slot);
+        else if (tcols == 128) tc::tmem_alloc<128>(&tmem_slot);
+        else tc::tmem_alloc<256>(&tmem_slot);
+    }
     // weights -> K-major image: element (n, k) of the [NP x KP] operand
     for (int e = tid; e < p.NP * p.KP; e += kThreads) {
         const int n = e / p.KP, k = e - n * p.KP;
@@ -123,41 +129,63 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_rows_kernel(const RowsParams
         tc::mbar_wait(&bar, phase);
         phase ^= 1;
         tc::tc_fence_after();
-        // epilogue: thread = row (lane quarter wq), column pieces of 32 split between the two warps of a quarter
-        const int64_t row = row0 + wq * 32 + lane;
-        for (int c0 = half * 32; c0 < p.NP; c0 += 64) {
-            uint32_t v[32];
-            tc::tmem_ld32(tmem + lane_base + c0, v);
-            tc::tmem_ld_wait();
-            if (row < p.M) {
-                float* out = p.C + row * p.ldc + c0;
-                if (c0 + 32 <= p.N && (p.ldc & 3) == 0) {
+        // epilogue, one 64-column piece at a time: tensor memory -> registers (thread = row of the lane quarter, the two
+        // warps of a quarter take 32 columns each) -> padded shared-memory staging -> COALESCED 128-bit global stores
+        // (consecutive threads = consecutive 16-byte pieces of a row).  Writing rows straight from the thread-per-row
+        // registers touched 32 cache lines per store instruction and was the largest cost of this kernel.
+        const bool vec_ok = ((p.ldc & 3) == 0) && ((p.N & 3) == 0);
+        for (int c0 = 0; c0 < p.NP; c0 += 64) {
+            if (c0 + 32 * half < p.NP) {
+                uint32_t v[32];
+                tc::tmem_ld32(tmem + lane_base + c0 + 32 * half, v);
+                tc::tmem_ld_wait();
+                float4* srow = reinterpret_cast<float4*>(sOut + (wq * 32 + lane) * 272 + 128 * half);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                        if (p.bias) { o.x += p.bias[c0 + j]; o.y += p.bias[c0 + j + 1]; o.z += p.bias[c0 + j + 2]; o.w += p.bias[c0 + j + 3]; }
-                        if (p.beta != 0.0f) {
-                            const float4 old = *reinterpret_cast<const float4*>(out + j);
-                            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                        }
-                        *reinterpret_cast<float4*>(out + j) = o;
+                for (int j = 0; j < 32; j += 4)
+                    srow[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = u * kThreads + tid;
+                const int rr = e >> 4, c4 = e & 15;
+                const int64_t row = row0 + rr;
+                const int col = c0 + 4 * c4;
+                if (row >= p.M || col >= p.N) continue;
+                float4 o = *reinterpret_cast<const float4*>(sOut + rr * 272 + 16 * c4);
+                float* out = p.C + row * p.ldc + col;
+                if (vec_ok) {
+                    if (p.bias) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                        o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
                     }
+                    if (p.beta != 0.0f) {
+                        const float4 old = *reinterpret_cast<const float4*>(out);
+                        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                    }
+                    *reinterpret_cast<float4*>(out) = o;
                 } else {
+                    const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (c0 + j < p.N) {
-                            float o = __uint_as_float(v[j]) + (p.bias ? p.bias[c0 + j] : 0.0f);
-                            if (p.beta != 0.0f) o += out[j];
-                            out[j] = o;
+                    for (int j = 0; j < 4; ++j)
+                        if (col + j < p.N) {
+                            float x = ov[j] + (p.bias ? p.bias[col + j] : 0.0f);
+                            if (p.beta != 0.0f) x += out[j];
+                            out[j] = x;
                         }
                 }
             }
+            __syncthreads();                                 // staging is reused by the next piece / tile
         }
         tc::tc_fence_before();
         __syncthreads();                                     // TMEM and sA are reused by the next tile
     }
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc<256>(tmem);
+    if (warp == 0) {
+        if (tcols == 64) tc::tmem_dealloc<64>(tmem);
+        else if (tcols == 128) tc::tmem_dealloc<128>(tmem);
+        else tc::tmem_dealloc<256>(tmem);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -287,11 +315,13 @@ extern "C" int u2gnn_gemm_tc_rows(const float* A, int64_t M, int K, int64_t lda,
     p.W = W; p.w_kn = w_kn; p.N = N; p.NP = (N + 15) / 16 * 16;
     p.bias = bias; p.C = C; p.ldc = ldc; p.beta = beta;
     const int kt = p.KP / 64;
-    const size_t smem = 1024 + (size_t)kt * 16384 + (size_t)kt * p.NP * 128;
+    const size_t smem = 1024 + (size_t)kt * 16384 + (size_t)kt * p.NP * 128 + 128 * 272;
     if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
     cudaFuncSetAttribute(gemm_tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int per_sm = (int)((220 * 1024) / smem);
-    if (per_sm > 2) per_sm = 2;                              // 256 TMEM columns per CTA
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    const int tmem_cols = (p.NP <= 64) ? 64 : (p.NP <= 128 ? 128 : 256);
+    if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;   // tensor-memory columns per CTA
+    if (per_sm > 3) per_sm = 3;                              // __launch_bounds__(256, 3)
     if (per_sm < 1) per_sm = 1;
     const int64_t n_tiles = (M + TM - 1) / TM;
     const int64_t cap = (int64_t)U2GNN_NUM_SMS * per_sm;
