@@ -53,18 +53,22 @@ __device__ __forceinline__ void stage_tile(uint8_t* tile, const float* __restric
 }
 
 // one row of a [128 x 128] bf16 operand (two [128 x 64] swizzled tiles `t0`, `t1`): zero it, then place `n` values at
-// columns col0 .. col0 + n - 1
-__device__ __forceinline__ void write_diag_row(uint8_t* t0, uint8_t* t1, int r, int col0, int n, const float* vals) {
+// columns col0 .. col0 + n - 1.  Fully unrolled with predicates so that `vals` stays in registers.
+template <int SMAX>
+__device__ __forceinline__ void write_diag_row(uint8_t* t0, uint8_t* t1, int r, int col0, int n, const float (&vals)[SMAX]) {
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
     for (int ch = 0; ch < 8; ++ch) {
         *reinterpret_cast<uint4*>(t0 + tc::sw128_chunk(r, ch)) = z;
         *reinterpret_cast<uint4*>(t1 + tc::sw128_chunk(r, ch)) = z;
     }
-    for (int j = 0; j < n; ++j) {
-        const int c = col0 + j;
-        uint8_t* t = (c < 64) ? t0 : t1;
-        *reinterpret_cast<__nv_bfloat16*>(t + tc::sw128_offset(r, c & 63)) = __float2bfloat16(vals[j]);
+#pragma unroll
+    for (int j = 0; j < SMAX; ++j) {
+        if (j < n) {
+            const int c = col0 + j;
+            uint8_t* t = (c < 64) ? t0 : t1;
+            *reinterpret_cast<__nv_bfloat16*>(t + tc::sw128_offset(r, c & 63)) = __float2bfloat16(vals[j]);
+        }
     }
 }
 
@@ -88,7 +92,7 @@ struct Params {
 };
 
 // shared memory layout (bytes): Q 0, K 16K, V 32K (P~ tile 0 reuses V in the backward), G 48K, P~1 / P~ 64K.., dS
-template <bool BWD>
+template <bool BWD, int SMAX>          // SMAX: compile-time bound of the sequence length (register arrays)
 __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const Params p) {
     // no static shared memory and a 1024-byte aligned dynamic segment: the backward's seven 16 KB tiles (+ 16 bytes for
     // the barrier and the TMEM slot behind them) then fit TWICE into an SM, so two phase-serial CTAs overlap
@@ -153,70 +157,77 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const Params p) {
         tc::tc_fence_after();
         // ---- 3. per-row softmax (threads 0..127: row r = node * S + i reads the S columns of its own node)
         if (warp < 4) {
-            float pd[32], ds[32];
+            float pd[SMAX], ds[BWD ? SMAX : 1];
             const bool live = r < rows;
             const int node = live ? r / S : 0, i = live ? r - node * S : 0;
             const int col0 = node * S;
-            // tcgen05.ld takes ONE (warp-uniform) column address, but the 32 rows of a warp belong to up to 32/S + 2 nodes.
-            // Rows and key columns of a tile index the same positions (block diagonal), so the columns any row of this
-            // lane quarter needs lie within [32 wq - (S-1), 32 wq + 31 + (S-1)]: a uniform 96-column window covers them
-            // for every S <= 32.  Each lane then picks its node's S values at a lane-dependent offset (local memory).
-            const int c_start = (wq <= 1) ? 0 : 32;
-            float sw[96], dw[BWD ? 96 : 1];
-            {
-                uint32_t t0[32], t1[32], t2[32];
-                tc::tmem_ld32(tmem + lane_base + c_start, t0);
-                tc::tmem_ld32(tmem + lane_base + c_start + 32, t1);
-                tc::tmem_ld32(tmem + lane_base + c_start + 64, t2);
-                tc::tmem_ld_wait();
+            // tcgen05.ld takes ONE (warp-uniform) column address, but the 32 rows of a warp belong to up to three nodes
+            // (S >= 11 for the tiles used here; four for shorter sequences).  The warp therefore loads the 32 columns
+            // behind EACH candidate block start (all warp-uniform) and every lane keeps the registers of its own node:
+            // selects on registers instead of a 96-column window indexed per lane in local memory.
+            const int node_lo = (wq * 32) / S;                               // node of the warp's first row
+            const int sel = node - node_lo;                                  // 0 .. 3
+            const int n_cand = ((wq * 32 + 31) / S) - node_lo + 1;           // warp-uniform
+            uint32_t sv[SMAX], dv[BWD ? SMAX : 1];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    sw[j] = __uint_as_float(t0[j]);
-                    sw[32 + j] = __uint_as_float(t1[j]);
-                    sw[64 + j] = __uint_as_float(t2[j]);
-                }
+            for (int j = 0; j < SMAX; ++j) { sv[j] = 0u; dv[BWD ? j : 0] = 0u; }
+            for (int cnd = 0; cnd < n_cand; ++cnd) {                         // warp-uniform trip count
+                uint32_t t0[32];
+                const int cb = (node_lo + cnd) * S;                          // <= 127: columns cb .. cb + 31 stay inside the allocation
+                tc::tmem_ld32(tmem + lane_base + cb, t0);
+                tc::tmem_ld_wait();
+                const bool mine = live && (sel == cnd);
+#pragma unroll
+                for (int j = 0; j < SMAX; ++j) sv[j] = (mine && j < S) ? t0[j] : sv[j];
                 if (BWD) {
-                    tc::tmem_ld32(tmem + lane_base + 128 + c_start, t0);
-                    tc::tmem_ld32(tmem + lane_base + 128 + c_start + 32, t1);
-                    tc::tmem_ld32(tmem + lane_base + 128 + c_start + 64, t2);
+                    // dP lives in columns [128, 256) = the end of the allocation: the 32-column window is clamped to it and
+                    // the registers are shifted down by the (warp-uniform) difference with a barrel shifter on registers
+                    const int cbl = cb < 96 ? cb : 96, dsh = cb - cbl;
+                    tc::tmem_ld32(tmem + lane_base + 128 + cbl, t0);
                     tc::tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        dw[j] = __uint_as_float(t0[j]);
-                        dw[(BWD ? 32 : 0) + j] = __uint_as_float(t1[j]);
-                        dw[(BWD ? 64 : 0) + j] = __uint_as_float(t2[j]);
+                    for (int bit = 16; bit >= 1; bit >>= 1) {
+                        if (dsh & bit) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) t0[j] = (j + bit < 32) ? t0[j + bit < 32 ? j + bit : 31] : 0u;
+                        }
                     }
+#pragma unroll
+                    for (int j = 0; j < SMAX; ++j) dv[BWD ? j : 0] = (mine && j < S) ? t0[j] : dv[BWD ? j : 0];
                 }
             }
-            const int off = col0 - c_start;
-            uint32_t sv[32], dv[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                sv[j] = (live && j < S) ? __float_as_uint(sw[off + j]) : 0u;
-                dv[j] = (BWD && live && j < S) ? __float_as_uint(dw[BWD ? off + j : 0]) : 0u;
+            // dropout keep bits of this row: elements ebase .. ebase + S - 1 of the [B, S, S] probability tensor lie in at
+            // most two 32-element groups of the engine's stream (one RNG word each instead of one per element)
+            const uint64_t ebase = (uint64_t)((node0 + node) * S + i) * (uint64_t)S;
+            uint32_t keep_bits = 0xFFFFFFFFu;                                // bit j = element ebase + j kept
+            if (p.rng.thr && live) {
+                const uint32_t w0 = rng_keep_word_lo(p.rng.keys, ebase >> 5, p.rng.thr, p.low);
+                const uint32_t w1 = rng_keep_word_lo(p.rng.keys, (ebase >> 5) + 1, p.rng.thr, p.low);
+                const uint32_t sh = (uint32_t)(ebase & 31);
+                keep_bits = sh ? ((w0 >> sh) | (w1 << (32 - sh))) : w0;
             }
+            const float dscale = p.rng.thr ? p.rng.scale : 1.0f;
             if (live) {
                 float m = -INFINITY;
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
+                for (int j = 0; j < SMAX; ++j)
                     if (j < S) m = fmaxf(m, __uint_as_float(sv[j]) * qscale);
                 float sum = 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    pd[j] = (j < S) ? expf(__uint_as_float(sv[j]) * qscale - m) : 0.f;
+                for (int j = 0; j < SMAX; ++j) {
+                    pd[j] = (j < S) ? __expf(__uint_as_float(sv[j]) * qscale - m) : 0.f;
                     sum += pd[j];
                 }
                 const float inv = 1.0f / sum;
-                const uint64_t ebase = (uint64_t)((node0 + node) * S + i) * (uint64_t)S;
                 float tsum = 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
+                for (int j = 0; j < SMAX; ++j) {
                     if (j < S) {
-                        const float mult = rng_dropout_mult(p.rng.keys, ebase + (uint64_t)j, p.rng.thr, p.rng.scale);
+                        const float mult = ((keep_bits >> j) & 1u) ? dscale : 0.0f;
                         const float pj = pd[j] * inv;
                         if (BWD) {
-                            const float dp = __uint_as_float(dv[j]) * mult;
-                            ds[j] = dp;
+                            const float dp = __uint_as_float(dv[BWD ? j : 0]) * mult;
+                            ds[BWD ? j : 0] = dp;
                             tsum = fmaf(pj, dp, tsum);
                             sv[j] = __float_as_uint(pj);          // keep p for the second pass
                         }
@@ -225,15 +236,15 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const Params p) {
                 }
                 if (BWD) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < S) ds[j] = __uint_as_float(sv[j]) * (ds[j] - tsum) * qscale;
+                    for (int j = 0; j < SMAX; ++j)
+                        if (j < S) ds[BWD ? j : 0] = __uint_as_float(sv[j]) * (ds[BWD ? j : 0] - tsum) * qscale;
                 }
             }
             // the TMEM reads above must be finished before anyone overwrites S / dP (step 4 reuses the columns); the
             // shared-memory rows are written after the block-wide barrier below for the backward (P~ reuses V)
             tc::tc_fence_before();
-            write_diag_row(sP0, sP1, r, col0, live ? S : 0, pd);
-            if (BWD) write_diag_row(sS0, sS1, r, col0, live ? S : 0, ds);
+            write_diag_row<SMAX>(sP0, sP1, r, col0, live ? S : 0, pd);
+            if constexpr (BWD) write_diag_row<SMAX>(sS0, sS1, r, col0, live ? S : 0, ds);
         }
         tc::fence_proxy_async();
         tc::tc_fence_before();
@@ -319,7 +330,7 @@ AttnRng make_rng(uint64_t seed, uint32_t stream, int thr) {
 template <bool BWD>
 int launch(const Params& p, cudaStream_t st) {
     const size_t smem = (BWD ? 114688 : 81920) + 16;          // tiles + barrier + TMEM slot
-    auto k = attn_tc_kernel<BWD>;
+    auto k = (p.S <= 20) ? attn_tc_kernel<BWD, 20> : attn_tc_kernel<BWD, 32>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int NB = TM / p.S;
     const int64_t n_tiles = (p.B + NB - 1) / NB;

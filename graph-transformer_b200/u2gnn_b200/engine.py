@@ -386,6 +386,9 @@ def encoder_layer_bwd(dy2, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
         wgrad(dqkv, M, 3 * d, sv.x, d, g["self_attn.in_proj_weight"], g["self_attn.in_proj_bias"])
     if not need_dx:
         return None
+    if tc_proj and Sq == S:
+        # residual gradient folded into the projection epilogue: dz1 += dqkv W_in (saves the separate axpy pass)
+        return linear_tc(dqkv, M, 3 * d, p["self_attn.in_proj_weight"], 1, d, beta=1.0, out=dz1)
     if tc_proj:
         dx = linear_tc(dqkv, M, 3 * d, p["self_attn.in_proj_weight"], 1, d)
     else:
