@@ -201,7 +201,7 @@ struct WgradParams {
     float* db;            // [N1] or null
 };
 
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_wgrad_kernel(const WgradParams p) {
+__global__ void __launch_bounds__(kThreads, 2) gemm_tc_wgrad_kernel(const WgradParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int ga = (p.N1 + 63) / 64;                         // 64-column groups of A (1..4)
@@ -342,6 +342,7 @@ extern "C" int u2gnn_gemm_tc_wgrad(const float* A, int64_t M, int N1, int64_t ld
     if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
     cudaFuncSetAttribute(gemm_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int64_t n_tiles = (M + TM - 1) / TM;
-    gemm_tc_wgrad_kernel<<<(int)(n_tiles < U2GNN_NUM_SMS ? n_tiles : U2GNN_NUM_SMS), kThreads, smem, as_stream(stream)>>>(p);
+    const int64_t cap = (int64_t)U2GNN_NUM_SMS * ((smem + 1024 <= 113 * 1024) ? 2 : 1);   // narrow A: two CTAs per SM overlap load and MMA phases
+    gemm_tc_wgrad_kernel<<<(int)(n_tiles < cap ? n_tiles : cap), kThreads, smem, as_stream(stream)>>>(p);
     U2GNN_CHECK_LAUNCH();
 }

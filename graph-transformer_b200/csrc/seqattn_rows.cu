@@ -259,68 +259,89 @@ __global__ void __launch_bounds__(NT) seqattn_last_fwd_kernel(const float* __res
     }
 }
 
+// Backward of the dead-row-eliminated last timestep (only position 0 of every node has a query).  Half a warp per node,
+// lane = four feature columns: every K / V row is ONE coalesced 256-byte read per half-warp and every dK / dV / dQ row
+// one coalesced 256-byte write (the thread-per-node version wrote each node's 13 KB from a single thread and reached
+// 14 % of the HBM roofline).  Scores and dP are reduced across the 16 lanes with shuffles and kept in registers.
 template <int D, int NT>
 __global__ void __launch_bounds__(NT) seqattn_last_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dctx,
-                                                              int64_t B, int S, AttnRng rng, float* __restrict__ dqkv) {
-    __shared__ float Ps[NT * PP];
-    __shared__ float Ds[NT * PP];
-    float* pr = Ps + threadIdx.x * PP;
-    float* dr = Ds + threadIdx.x * PP;
+                                                              int64_t B, int S, AttnRng rng, int low, float* __restrict__ dqkv) {
+    static_assert(D == 64 || D == 32, "lane = 4 feature columns");
+    constexpr int LPN = D / 4;                                        // lanes per node (16: half a warp, 8: a quarter)
+    constexpr int NPW = 32 / LPN;                                     // nodes per warp
+    const int hl = threadIdx.x % LPN;
+    const int64_t hw = ((int64_t)blockIdx.x * NT + threadIdx.x) / LPN, n_hw = ((int64_t)gridDim.x * NT) / LPN;
     const float qscale = sqrtf(1.0f / (float)D);
-    for (int64_t b = (int64_t)blockIdx.x * NT + threadIdx.x; b < B; b += (int64_t)gridDim.x * NT) {
+    auto reduce16 = [](float v) {
+#pragma unroll
+        for (int o = LPN / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    };
+    const int64_t B_pad = (B + NPW - 1) / NPW * NPW;                  // the node groups of a warp iterate together (shuffles)
+    for (int64_t b0 = hw; b0 < B_pad; b0 += n_hw) {
+        const bool live = b0 < B;
+        const int64_t b = live ? b0 : B - 1;
         const float* base = qkv + b * S * 3 * D;
         float* gout = dqkv + b * S * 3 * D;
-        float q[D], g[D];
-#pragma unroll
-        for (int c = 0; c < D; c += 4) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(base + c));
-            q[c] = v.x * qscale; q[c + 1] = v.y * qscale; q[c + 2] = v.z * qscale; q[c + 3] = v.w * qscale;
-            const float4 w = __ldg(reinterpret_cast<const float4*>(dctx + b * D + c));
-            g[c] = w.x; g[c + 1] = w.y; g[c + 2] = w.z; g[c + 3] = w.w;
-        }
+        float4 q = __ldg(reinterpret_cast<const float4*>(base) + hl);
+        q.x *= qscale; q.y *= qscale; q.z *= qscale; q.w *= qscale;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(dctx + b * D) + hl);
+        float pr[32], dr[32];
         float m = -INFINITY;
-        for (int j = 0; j < S; ++j) {
-            const float s = dot_row<D>(q, base + (int64_t)j * 3 * D + D);
-            pr[j] = s;
-            m = fmaxf(m, s);
-        }
-        float sum = 0.f;
-        for (int j = 0; j < S; ++j) {
-            const float e = expf(pr[j] - m);
-            pr[j] = e;
-            sum += e;
-        }
-        const float inv = 1.0f / sum;
-        float tsum = 0.f;
-        for (int j = 0; j < S; ++j) {
-            const float mult = rng_dropout_mult(rng.keys, (uint64_t)b * (uint64_t)S + (uint64_t)j, rng.thr, rng.scale);
-            const float p = pr[j] * inv;
-            const float dp = dot_row<D>(g, base + (int64_t)j * 3 * D + 2 * D) * mult;
-            tsum = fmaf(p, dp, tsum);
-            pr[j] = p;
-            dr[j] = dp;
-        }
-        float dq[D];
 #pragma unroll
-        for (int c = 0; c < D; ++c) dq[c] = 0.f;
-        for (int j = 0; j < S; ++j) {
-            const float p = pr[j];
-            const float ds = p * (dr[j] - tsum);
-            const float pd = p * rng_dropout_mult(rng.keys, (uint64_t)b * (uint64_t)S + (uint64_t)j, rng.thr, rng.scale);
-            axpy_row<D>(dq, ds, base + (int64_t)j * 3 * D + D);
-            float4* ok = reinterpret_cast<float4*>(gout + (int64_t)j * 3 * D + D);
-            float4* ov = reinterpret_cast<float4*>(gout + (int64_t)j * 3 * D + 2 * D);
-            float4* oq = reinterpret_cast<float4*>(gout + (int64_t)j * 3 * D);
-#pragma unroll
-            for (int c = 0; c < D; c += 4) {
-                ok[c >> 2] = make_float4(ds * q[c], ds * q[c + 1], ds * q[c + 2], ds * q[c + 3]);       // q already carries sqrt(1/d)
-                ov[c >> 2] = make_float4(pd * g[c], pd * g[c + 1], pd * g[c + 2], pd * g[c + 3]);
-                if (j > 0) oq[c >> 2] = make_float4(0.f, 0.f, 0.f, 0.f);                                 // rows without a query
+        for (int j = 0; j < 32; ++j) {
+            pr[j] = -INFINITY;
+            dr[j] = 0.f;
+            if (j < S) {
+                const float4 k = __ldg(reinterpret_cast<const float4*>(base + (int64_t)j * 3 * D + D) + hl);
+                const float4 v = __ldg(reinterpret_cast<const float4*>(base + (int64_t)j * 3 * D + 2 * D) + hl);
+                pr[j] = reduce16(q.x * k.x + q.y * k.y + q.z * k.z + q.w * k.w);
+                dr[j] = reduce16(g.x * v.x + g.y * v.y + g.z * v.z + g.w * v.w);
+                m = fmaxf(m, pr[j]);
             }
         }
-        float4* oq0 = reinterpret_cast<float4*>(gout);
+        float sum = 0.f;
 #pragma unroll
-        for (int c = 0; c < D; c += 4) oq0[c >> 2] = make_float4(dq[c] * qscale, dq[c + 1] * qscale, dq[c + 2] * qscale, dq[c + 3] * qscale);
+        for (int j = 0; j < 32; ++j) {
+            pr[j] = (j < S) ? expf(pr[j] - m) : 0.f;
+            sum += pr[j];
+        }
+        const float inv = 1.0f / sum;
+        // keep bits of elements b*S .. b*S + S - 1 of the probability tensor: at most two words of the stream
+        const uint64_t ebase = (uint64_t)b * (uint64_t)S;
+        uint32_t keep_bits = 0xFFFFFFFFu;
+        if (rng.thr) {
+            const uint32_t w0 = rng_keep_word_lo(rng.keys, ebase >> 5, rng.thr, low);
+            const uint32_t w1 = rng_keep_word_lo(rng.keys, (ebase >> 5) + 1, rng.thr, low);
+            const uint32_t sh = (uint32_t)(ebase & 31);
+            keep_bits = sh ? ((w0 >> sh) | (w1 << (32 - sh))) : w0;
+        }
+        const float dscale = rng.thr ? rng.scale : 1.0f;
+        float tsum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float mult = ((keep_bits >> j) & 1u) ? dscale : 0.0f;
+            pr[j] *= inv;
+            dr[j] *= mult;
+            tsum = fmaf(pr[j], dr[j], tsum);
+        }
+        float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (j < S) {
+                const float ds = pr[j] * (dr[j] - tsum);
+                const float pd = pr[j] * (((keep_bits >> j) & 1u) ? dscale : 0.0f);
+                const float4 k = __ldg(reinterpret_cast<const float4*>(base + (int64_t)j * 3 * D + D) + hl);
+                dq.x = fmaf(ds, k.x, dq.x); dq.y = fmaf(ds, k.y, dq.y); dq.z = fmaf(ds, k.z, dq.z); dq.w = fmaf(ds, k.w, dq.w);
+                if (live) {
+                    float4* row = reinterpret_cast<float4*>(gout + (int64_t)j * 3 * D);
+                    if (j > 0) row[hl] = make_float4(0.f, 0.f, 0.f, 0.f);                                  // rows without a query
+                    row[LPN + hl] = make_float4(ds * q.x, ds * q.y, ds * q.z, ds * q.w);                  // q already carries sqrt(1/d)
+                    row[2 * LPN + hl] = make_float4(pd * g.x, pd * g.y, pd * g.z, pd * g.w);
+                }
+            }
+        }
+        if (live) reinterpret_cast<float4*>(gout)[hl] = make_float4(dq.x * qscale, dq.y * qscale, dq.z * qscale, dq.w * qscale);
     }
 }
 
@@ -334,10 +355,10 @@ int launch_last_fwd(const float* qkv, int64_t B, int S, AttnRng rng, float* ctx,
 }
 template <int D>
 int launch_last_bwd(const float* qkv, const float* dctx, int64_t B, int S, AttnRng rng, float* dqkv, cudaStream_t st) {
-    constexpr int NT = 64;
-    const int64_t blocks = (B + NT - 1) / NT;
+    constexpr int NT = 256;
+    const int64_t blocks = (B * (D / 4) + NT - 1) / NT;
     const int grid = (int)(blocks < (int64_t)U2GNN_NUM_SMS * 8 ? blocks : (int64_t)U2GNN_NUM_SMS * 8);
-    seqattn_last_bwd_kernel<D, NT><<<grid, NT, 0, st>>>(qkv, dctx, B, S, rng, dqkv);
+    seqattn_last_bwd_kernel<D, NT><<<grid, NT, 0, st>>>(qkv, dctx, B, S, rng, rng_thr_low(rng.thr), dqkv);
     return 1;
 }
 
