@@ -21,11 +21,11 @@ constexpr uint32_t BLOCK = 3 * 16384;         // [W1c | W2Tc | W1Tc]
 // I/O phase of one CTA (35 % of the NT = 2 kernel's time, tools/trace_ffn_bwd.py) overlaps the chunk loop of the other.
 // Measured: the SAME 11.46 ms per 4 M rows as NT = 2 (11.49 ms) - the chunk loop is bound by the S -> mask -> D -> dPre
 // -> dY chain latency of each tile, not by a shared resource, so only MORE tiles in flight would help and tensor memory
-// holds two.  NT = 2 stays the default (half the L2 weight traffic); NT = 1 is kept behind u2gnn_ffn_tc_debug bit 4.
+// holds two.  Only NT = 2 is instantiated (half the L2 weight traffic; NT = 1 no longer fits two CTAs once the staging exists).
 template <int NT> struct Cfg {
     static constexpr int kCtrl = (NT == 2) ? 4 : 2;                 // warp 0 weight producer, warp 1 MMA issuer + TMEM owner
     static constexpr int kThreads = 32 * (kCtrl + 8 * NT);
-    static constexpr int STAGES = (NT == 2) ? 4 : 2;
+    static constexpr int STAGES = (NT == 2) ? 3 : 2;                // 48 KB weight stages
     static constexpr uint32_t COL_Y = 0, COL_R = 64 * NT, COL_X = 192 * NT, COL_F = 224 * NT;
     static constexpr int kTmemCols = 256 * NT;
 };
@@ -78,26 +78,8 @@ __device__ __forceinline__ void commit_to(uint64_t* bar) {
     __syncwarp();
 }
 
-// one fp32 row (zero padded to 64) -> 32 packed bf16 words
-__device__ __forceinline__ void load_row_packed(const float* __restrict__ src, int64_t row, int64_t M, int d, uint32_t (&xp)[32]) {
-    if (d == DP && row < M) {
-        const float4* s4 = reinterpret_cast<const float4*>(src + row * DP);
-        float4 v[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) v[u] = __ldg(s4 + u);
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            xp[2 * u] = epi::cvt2(v[u].x, v[u].y);
-            xp[2 * u + 1] = epi::cvt2(v[u].z, v[u].w);
-        }
-    } else {
-#pragma unroll
-        for (int u = 0; u < 32; ++u) {
-            const float a = (row < M && 2 * u < d) ? src[row * d + 2 * u] : 0.0f;
-            const float b = (row < M && 2 * u + 1 < d) ? src[row * d + 2 * u + 1] : 0.0f;
-            xp[u] = epi::cvt2(a, b);
-        }
-    }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
 template <bool TRACE, int NT>
@@ -115,6 +97,7 @@ __global__ void __launch_bounds__(Cfg<NT>::kThreads, 3 - NT) ffn_tc_dgrad_kernel
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sW = smem;                                                        // STAGES x 48 KB
     uint32_t* sB1h = reinterpret_cast<uint32_t*>(sW + STAGES * BLOCK);         // b1 as packed bf16 pairs
+    uint8_t* sIO = reinterpret_cast<uint8_t*>(sB1h + p.ff / 2);                // 16 KB per (tile, warpgroup): bf16 tile image, later dY staging
     __shared__ Bars bars;
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -134,7 +117,7 @@ __global__ void __launch_bounds__(Cfg<NT>::kThreads, 3 - NT) ffn_tc_dgrad_kernel
             tc::mbar_init(&bars.d_full[i], 1);
             tc::mbar_init(&bars.p_full[i], 8);
             tc::mbar_init(&bars.y_full[i], 1);
-            tc::mbar_init(&bars.y_free[i], 4);
+            tc::mbar_init(&bars.y_free[i], 8);      // both warpgroups of the tile drain half of dY each
         }
         tc::fence_barrier_init();
     }
@@ -220,21 +203,62 @@ __global__ void __launch_bounds__(Cfg<NT>::kThreads, 3 - NT) ffn_tc_dgrad_kernel
         uint32_t q = 0, scount = 0, dcount = 0;
         for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++q) {
             const int64_t row = pair * (NT * TM) + (int64_t)i * TM + tr;
-            // ---- operands into tensor memory: warpgroup 0 converts X rows, warpgroup 1 converts dF rows
+            // ---- operands into tensor memory: warpgroup 0 stages X, warpgroup 1 stages dF.  The 128 threads of a
+            // warpgroup read the [128 x 64] fp32 tile with COALESCED 128-bit loads, round it into the swizzled bf16 tile
+            // image in shared memory (bulk-stored from there for the wgrad kernel), and each thread then moves its own row
+            // of the image into tensor memory.  (Thread-per-row global loads touched 32 lines per instruction and made the
+            // row I/O 35 % of this kernel.)
+            const float* src = (wg == 0) ? p.y1 : p.df;
+            uint8_t* img_s = sIO + (size_t)(i * 2 + wg) * 16384;
+            const int bar_id = 1 + i * 2 + wg;
             stamp(warp - kCtrl + 1);
             if (q > 0) tc::mbar_wait(&bars.x_free[i], (q - 1) & 1);
             stamp(warp - kCtrl + 1);
             {
-                uint32_t xp[32];
-                load_row_packed(wg == 0 ? p.y1 : p.df, row, p.M, p.d, xp);
-                tc::tmem_st32(tmem + lane_base + (wg == 0 ? COL_X : COL_F) + 32 * i, xp);
-                uint8_t* img = (wg == 0) ? p.xb : p.fb;
-                if (img) {      // this thread's 128-byte row of the tile image, chunks at their swizzled positions
-                    img += (size_t)(pair * NT + i) * 16384;
+                const int64_t row0 = pair * (NT * TM) + (int64_t)i * TM;
+                if (tr == 0) tc::bulk_wait_read<0>();     // an image store of the previous pair may still read the region
+                if (p.d == DP) {
+                    // (prefetching these loads into registers before the previous pair's output phase was measured: slower,
+                    // the 64 extra live registers spill)
+                    float4 v[16];
 #pragma unroll
-                    for (int ch = 0; ch < 8; ++ch)
-                        *reinterpret_cast<uint4*>(img + tc::sw128_chunk(tr, ch)) = make_uint4(xp[4 * ch], xp[4 * ch + 1], xp[4 * ch + 2], xp[4 * ch + 3]);
+                    for (int u = 0; u < 16; ++u) {
+                        const int e = u * 128 + tr;
+                        const int64_t rg = row0 + (e >> 4);
+                        v[u] = (rg < p.M) ? __ldg(reinterpret_cast<const float4*>(src + rg * DP) + (e & 15)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    named_bar_sync(bar_id, 128);          // everybody is done reading the staging of the previous pair
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const int e = u * 128 + tr;
+                        uint2 w;
+                        w.x = epi::cvt2(v[u].x, v[u].y);
+                        w.y = epi::cvt2(v[u].z, v[u].w);
+                        *reinterpret_cast<uint2*>(img_s + tc::sw128_offset(e >> 4, (e & 15) * 4)) = w;
+                    }
+                } else {
+                    named_bar_sync(bar_id, 128);
+                    for (int e = tr; e < TM * DP; e += 128) {
+                        const int r = e >> 6, k = e & 63;
+                        const int64_t rg = row0 + r;
+                        const float x = (rg < p.M && k < p.d) ? src[rg * p.d + k] : 0.0f;
+                        *reinterpret_cast<__nv_bfloat16*>(img_s + tc::sw128_offset(r, k)) = __float2bfloat16(x);
+                    }
                 }
+                tc::fence_proxy_async();                  // generic writes -> visible to the bulk store below
+                named_bar_sync(bar_id, 128);
+                uint8_t* img = (wg == 0) ? p.xb : p.fb;
+                if (img && tr == 0) {
+                    tc::bulk_s2g(img + (size_t)(pair * NT + i) * 16384, img_s, 16384);
+                    tc::bulk_commit();
+                }
+                uint32_t xp[32];
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    const uint4 w = *reinterpret_cast<const uint4*>(img_s + tc::sw128_chunk(tr, ch));
+                    xp[4 * ch] = w.x; xp[4 * ch + 1] = w.y; xp[4 * ch + 2] = w.z; xp[4 * ch + 3] = w.w;
+                }
+                tc::tmem_st32(tmem + lane_base + (wg == 0 ? COL_X : COL_F) + 32 * i, xp);
                 tc::tmem_st_wait();
                 tc::tc_fence_before();
                 __syncwarp();
@@ -300,34 +324,43 @@ __global__ void __launch_bounds__(Cfg<NT>::kThreads, 3 - NT) ffn_tc_dgrad_kernel
                 stamp(warp - kCtrl + 1);
             }
             stamp(warp - kCtrl + 1);
-            if (wg != 0) continue;
-            // ---- dY + dz -> dy1
+            // ---- dY + dz -> dy1: each warpgroup drains 32 of the 64 columns; registers -> staging (its own 16 KB region,
+            // [128 rows x 128 B], 16-byte chunks XOR-swizzled with the row) -> coalesced dz loads and dy1 stores
             tc::mbar_wait(&bars.y_full[i], q & 1);
             tc::tc_fence_after();
-            uint32_t y0[32], y1r[32];
-            tc::tmem_ld32(tmem + lane_base + COL_Y + 64 * i, y0);
-            tc::tmem_ld32(tmem + lane_base + COL_Y + 64 * i + 32, y1r);
+            uint32_t yv[32];
+            tc::tmem_ld32(tmem + lane_base + COL_Y + 64 * i + 32 * wg, yv);
             tc::tmem_ld_wait();
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&bars.y_free[i]);
-            if (row < p.M) {
-                if (p.d == DP) {
-                    const float4* zi = reinterpret_cast<const float4*>(p.dz + row * DP);
-                    float4* o = reinterpret_cast<float4*>(p.dy1 + row * DP);
+            if (p.d == DP) {
+                if (tr == 0) tc::bulk_wait_read<0>();     // the image store of this pair has left the region
+                named_bar_sync(bar_id, 128);
 #pragma unroll
-                    for (int j = 0; j < DP; j += 4) {
-                        const float4 r4 = zi[j >> 2];
-                        const uint32_t* src = (j < 32) ? &y0[j] : &y1r[j - 32];
-                        o[j >> 2] = make_float4(r4.x + __uint_as_float(src[0]), r4.y + __uint_as_float(src[1]),
-                                                r4.z + __uint_as_float(src[2]), r4.w + __uint_as_float(src[3]));
+                for (int ch = 0; ch < 8; ++ch)
+                    *reinterpret_cast<uint4*>(img_s + tr * 128 + ((ch ^ (tr & 7)) << 4)) = make_uint4(yv[4 * ch], yv[4 * ch + 1], yv[4 * ch + 2], yv[4 * ch + 3]);
+                named_bar_sync(bar_id, 128);
+                const int64_t row0 = pair * (NT * TM) + (int64_t)i * TM;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = u * 128 + tr;
+                    const int r = e >> 3, c4 = e & 7;
+                    const int64_t rg = row0 + r;
+                    if (rg < p.M) {
+                        const float4 o = *reinterpret_cast<const float4*>(img_s + r * 128 + ((c4 ^ (r & 7)) << 4));
+                        const float4 z4 = __ldg(reinterpret_cast<const float4*>(p.dz + rg * DP + 32 * wg) + c4);
+                        reinterpret_cast<float4*>(p.dy1 + rg * DP + 32 * wg)[c4] = make_float4(o.x + z4.x, o.y + z4.y, o.z + z4.z, o.w + z4.w);
                     }
-                } else {
+                }
+            } else if (row < p.M) {
 #pragma unroll
-                    for (int j = 0; j < DP; ++j)
-                        if (j < p.d) p.dy1[row * p.d + j] = p.dz[row * p.d + j] + __uint_as_float(j < 32 ? y0[j] : y1r[j - 32]);
+                for (int j = 0; j < 32; ++j) {
+                    const int col = 32 * wg + j;
+                    if (col < p.d) p.dy1[row * p.d + col] = p.dz[row * p.d + col] + __uint_as_float(yv[j]);
                 }
             }
+            if (pair + gridDim.x >= n_pairs && tr == 0) tc::bulk_wait_all<0>();   // last pair: image stores complete before exit
         }
     }
     tc::tc_fence_before();
@@ -349,10 +382,9 @@ int ffn_tc_dgrad_launch(const float* y1, const float* df, const float* dz, float
     p.xb = static_cast<uint8_t*>(xb);
     p.fb = static_cast<uint8_t*>(fb);
     extern uint32_t* g_ffn_trace;
-    extern int g_ffn_dbg;
     p.trace = g_ffn_trace;
     auto launch = [&](auto kern, int nt, int threads, int stages) -> int {
-        const size_t smem = 1024 + (size_t)stages * BLOCK + (size_t)(ff / 2) * sizeof(uint32_t);
+        const size_t smem = 1024 + (size_t)stages * BLOCK + (size_t)(ff / 2) * sizeof(uint32_t) + (size_t)nt * 2 * 16384;
         if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int64_t n_groups = (M + nt * TM - 1) / (nt * TM);
@@ -360,10 +392,6 @@ int ffn_tc_dgrad_launch(const float* y1, const float* df, const float* dz, float
         kern<<<(int)(n_groups < cap ? n_groups : cap), threads, smem, st>>>(p);
         return U2GNN_OK;
     };
-    if (g_ffn_dbg & 16) {          // experiment switch: two independent one-tile CTAs per SM
-        if (p.trace) return launch(ffn_tc_dgrad_kernel<true, 1>, 1, Cfg<1>::kThreads, Cfg<1>::STAGES);
-        return launch(ffn_tc_dgrad_kernel<false, 1>, 1, Cfg<1>::kThreads, Cfg<1>::STAGES);
-    }
     if (p.trace) return launch(ffn_tc_dgrad_kernel<true, 2>, 2, Cfg<2>::kThreads, Cfg<2>::STAGES);
     return launch(ffn_tc_dgrad_kernel<false, 2>, 2, Cfg<2>::kThreads, Cfg<2>::STAGES);
 }
