@@ -28,9 +28,28 @@ struct AttnRng {
     float scale;
 };
 
-// rows [row0, row0 + 128) of a strided fp32 matrix (64 columns at column offset `coff`) -> bf16 swizzled tile
-__device__ __forceinline__ void stage_tile(uint8_t* tile, const float* __restrict__ src, int64_t ld, int coff, int64_t row0,
+// rows [row0, row0 + 128) of a strided matrix (64 columns at column offset `coff`; fp32, or bf16 when `bf16_src`: then the
+// producer has already rounded and the tile is a plain copy at half the bytes) -> bf16 swizzled tile
+__device__ __forceinline__ void stage_tile(uint8_t* tile, const void* __restrict__ src_, int bf16_src, int64_t ld, int coff, int64_t row0,
                                            int valid_rows, int tid) {
+    if (bf16_src) {                                             // (the kernel stages all bf16 tiles at once: stage_tiles_bf16)
+        const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(src_);
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = u * kThreads + tid;
+            const int r = e >> 3, c8 = e & 7;
+            v[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (r < valid_rows) v[u] = __ldg(reinterpret_cast<const uint4*>(src + (row0 + r) * ld + coff) + c8);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = u * kThreads + tid;
+            *reinterpret_cast<uint4*>(tile + tc::sw128_chunk(e >> 3, e & 7)) = v[u];
+        }
+        return;
+    }
+    const float* src = static_cast<const float*>(src_);
     for (int base = 0; base < TM * 16; base += kThreads * 8) {
         float4 v[8];
 #pragma unroll
@@ -82,9 +101,10 @@ __device__ __forceinline__ void mma_kk(uint32_t tmem_d, uint32_t a_addr, uint32_
 }
 
 struct Params {
-    const float* qkv;
-    const float* dctx;     // backward only
-    float* out;            // forward: ctx[B*S, 64]; backward: dqkv[B*S, 192]
+    const void* qkv;
+    const void* dctx;      // backward only
+    void* out;             // forward: ctx[B*S, 64]; backward: dqkv[B*S, 192]
+    int io_bf16;           // qkv, dctx and out are bf16 row-major instead of fp32
     int64_t B;
     int S;
     AttnRng rng;
@@ -135,10 +155,37 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const Params p) {
         const int rows = nodes * S;
         const int64_t row0 = node0 * S;
         // ---- 1. stage operands
-        stage_tile(sQ, p.qkv, 3 * D, 0, row0, rows, tid);
-        stage_tile(sK, p.qkv, 3 * D, D, row0, rows, tid);
-        stage_tile(sV, p.qkv, 3 * D, 2 * D, row0, rows, tid);
-        if (BWD) stage_tile(sG, p.dctx, D, 0, row0, rows, tid);
+        if (p.io_bf16) {
+            // bf16 sources: tiles are plain copies; every 16-byte load of all three / four tiles is in flight before the first
+            // shared-memory store (one exposed memory latency per tile-set instead of one per tile)
+            const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(p.qkv);
+            const __nv_bfloat16* gsrc = static_cast<const __nv_bfloat16*>(p.dctx);
+            uint4 v[BWD ? 4 : 3][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = u * kThreads + tid;
+                const int rr = e >> 3, c8 = e & 7;
+                const bool ok = rr < rows;
+                const uint4* rowp = reinterpret_cast<const uint4*>(q + (row0 + rr) * (3 * D));
+#pragma unroll
+                for (int t = 0; t < 3; ++t) v[t][u] = ok ? __ldg(rowp + 8 * t + c8) : make_uint4(0u, 0u, 0u, 0u);
+                if (BWD) v[BWD ? 3 : 0][u] = ok ? __ldg(reinterpret_cast<const uint4*>(gsrc + (row0 + rr) * D) + c8) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = u * kThreads + tid;
+                const uint32_t off = tc::sw128_chunk(e >> 3, e & 7);
+                *reinterpret_cast<uint4*>(sQ + off) = v[0][u];
+                *reinterpret_cast<uint4*>(sK + off) = v[1][u];
+                *reinterpret_cast<uint4*>(sV + off) = v[2][u];
+                if (BWD) *reinterpret_cast<uint4*>(sG + off) = v[BWD ? 3 : 0][u];
+            }
+        } else {
+            stage_tile(sQ, p.qkv, 0, 3 * D, 0, row0, rows, tid);
+            stage_tile(sK, p.qkv, 0, 3 * D, D, row0, rows, tid);
+            stage_tile(sV, p.qkv, 0, 3 * D, 2 * D, row0, rows, tid);
+            if (BWD) stage_tile(sG, p.dctx, 0, D, 0, row0, rows, tid);
+        }
         tc::fence_proxy_async();
         tc::tc_fence_before();
         __syncthreads();
@@ -302,13 +349,39 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const Params p) {
             }
             tc::tc_fence_before();
             __syncthreads();
+            if (p.io_bf16) {
+#pragma unroll
+                for (int u = 0; u < NP * 4; ++u) {
+                    const int e = u * kThreads + tid;
+                    const int pc = e >> 10, rr = (e >> 3) & 127, c8 = e & 7;
+                    if (rr < rows) {
+                        const uint8_t* st = smem + pc * 32768 + rr * 256;
+                        const uint4 o0 = *reinterpret_cast<const uint4*>(st + (((2 * c8) ^ (rr & 15)) << 4));
+                        const uint4 o1 = *reinterpret_cast<const uint4*>(st + (((2 * c8 + 1) ^ (rr & 15)) << 4));
+                        uint4 w;
+                        w.x = epi::cvt2(__uint_as_float(o0.x), __uint_as_float(o0.y));
+                        w.y = epi::cvt2(__uint_as_float(o0.z), __uint_as_float(o0.w));
+                        w.z = epi::cvt2(__uint_as_float(o1.x), __uint_as_float(o1.y));
+                        w.w = epi::cvt2(__uint_as_float(o1.z), __uint_as_float(o1.w));
+                        *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (row0 + rr) * (BWD ? 3 * D : D) + 64 * pc + 8 * c8) = w;
+                    }
+                }
+            } else
 #pragma unroll
             for (int u = 0; u < NP * 8; ++u) {
                 const int e = u * kThreads + tid;
                 const int pc = e >> 11, rr = (e >> 4) & 127, c4 = e & 15;
                 if (rr < rows) {
                     const uint4 o = *reinterpret_cast<const uint4*>(smem + pc * 32768 + rr * 256 + ((c4 ^ (rr & 15)) << 4));
-                    *reinterpret_cast<uint4*>(p.out + (row0 + rr) * (BWD ? 3 * D : D) + 64 * pc + 4 * c4) = o;
+                    const int64_t off = (row0 + rr) * (BWD ? 3 * D : D) + 64 * pc + 4 * c4;
+                    if (p.io_bf16) {
+                        uint2 w;
+                        w.x = epi::cvt2(__uint_as_float(o.x), __uint_as_float(o.y));
+                        w.y = epi::cvt2(__uint_as_float(o.z), __uint_as_float(o.w));
+                        *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + off) = w;
+                    } else {
+                        *reinterpret_cast<uint4*>(static_cast<float*>(p.out) + off) = o;
+                    }
                 }
             }
         }
@@ -341,30 +414,40 @@ int launch(const Params& p, cudaStream_t st) {
 
 }  // namespace
 
-extern "C" int u2gnn_seqattn_tc_fwd(const float* qkv, int64_t B, int S, int d, uint64_t seed, uint32_t rng_stream, int thr,
-                                    float* ctx, u2gnn_stream_t stream) {
+extern "C" int u2gnn_seqattn_tc_fwd_ex(const void* qkv, int64_t B, int S, int d, uint64_t seed, uint32_t rng_stream, int thr,
+                                       void* ctx, int io_bf16, u2gnn_stream_t stream) {
     if (!qkv || !ctx || B < 0 || thr < 0 || thr > 255) return U2GNN_EINVAL;
     if (d != D || S < 2 || S > 32) return U2GNN_EUNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(ctx)) % 16) return U2GNN_EALIGN;
     if (B == 0) return U2GNN_OK;
     Params p;
-    p.qkv = qkv; p.dctx = nullptr; p.out = ctx; p.B = B; p.S = S;
+    p.qkv = qkv; p.dctx = nullptr; p.out = ctx; p.io_bf16 = io_bf16; p.B = B; p.S = S;
     p.rng = make_rng(seed, rng_stream, thr);
     p.low = rng_thr_low(thr);
     launch<false>(p, as_stream(stream));
     U2GNN_CHECK_LAUNCH();
 }
 
-extern "C" int u2gnn_seqattn_tc_bwd(const float* qkv, const float* dctx, int64_t B, int S, int d, uint64_t seed,
-                                    uint32_t rng_stream, int thr, float* dqkv, u2gnn_stream_t stream) {
+extern "C" int u2gnn_seqattn_tc_fwd(const float* qkv, int64_t B, int S, int d, uint64_t seed, uint32_t rng_stream, int thr,
+                                    float* ctx, u2gnn_stream_t stream) {
+    return u2gnn_seqattn_tc_fwd_ex(qkv, B, S, d, seed, rng_stream, thr, ctx, 0, stream);
+}
+
+extern "C" int u2gnn_seqattn_tc_bwd_ex(const void* qkv, const void* dctx, int64_t B, int S, int d, uint64_t seed,
+                                       uint32_t rng_stream, int thr, void* dqkv, int io_bf16, u2gnn_stream_t stream) {
     if (!qkv || !dctx || !dqkv || B < 0 || thr < 0 || thr > 255) return U2GNN_EINVAL;
     if (d != D || S < 2 || S > 32) return U2GNN_EUNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dctx) | reinterpret_cast<uintptr_t>(dqkv)) % 16) return U2GNN_EALIGN;
     if (B == 0) return U2GNN_OK;
     Params p;
-    p.qkv = qkv; p.dctx = dctx; p.out = dqkv; p.B = B; p.S = S;
+    p.qkv = qkv; p.dctx = dctx; p.out = dqkv; p.io_bf16 = io_bf16; p.B = B; p.S = S;
     p.rng = make_rng(seed, rng_stream, thr);
     p.low = rng_thr_low(thr);
     launch<true>(p, as_stream(stream));
     U2GNN_CHECK_LAUNCH();
+}
+
+extern "C" int u2gnn_seqattn_tc_bwd(const float* qkv, const float* dctx, int64_t B, int S, int d, uint64_t seed,
+                                    uint32_t rng_stream, int thr, float* dqkv, u2gnn_stream_t stream) {
+    return u2gnn_seqattn_tc_bwd_ex(qkv, dctx, B, S, d, seed, rng_stream, thr, dqkv, 0, stream);
 }

@@ -6,6 +6,9 @@
 //     R_i = dF_i W2Tc^T        (TS, N 128)   epilogue B: dPre = bf16(D) & m  -> written over R_i (packed)
 //     dY_i += dPre_i W1Tc^T    (TS, N 64)
 // TMEM columns: dY0 [0,64) dY1 [64,128) R0 [128,256) R1 [256,384) X0/X1 [384,448) dF0/dF1 [448,512).
+// Measured dead ends (tools/trace_ffn_bwd.py, tools/bench_ffn_bwd.py): two one-tile CTAs per SM (same time), register
+// prefetch of the next pair's tiles (slower: spills), staggering the CTAs' start by 3-10 us to spread the row-I/O bursts
+// (same time).  What is left between pairs (19.5 K of 83 K cycles) is load latency + the dY drain.
 #include "common.cuh"
 #include "rng.cuh"
 #include "tc_common.cuh"

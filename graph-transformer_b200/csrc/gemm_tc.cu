@@ -17,12 +17,60 @@ namespace {
 constexpr int TM = 128;
 constexpr int kThreads = 256;
 
-// fp32 [rows x K] block (row stride lda) -> K/64 swizzled bf16 tiles of [128 x 64]; rows >= M and cols >= K_true zero
+// [rows x K] block (row stride lda in ELEMENTS; fp32, or bf16 when src_bf16) -> K/64 swizzled bf16 tiles of [128 x 64];
+// rows >= M and cols >= K_true zero.  A bf16 source is what the upstream kernel already rounded (bit-identical to
+// rounding here) at half the HBM bytes.
 template <int NT>
-__device__ __forceinline__ void stage_rows_bf16(uint8_t* tiles, const float* __restrict__ src, int64_t row0, int64_t M,
+__device__ __forceinline__ void stage_rows_bf16(uint8_t* tiles, const void* __restrict__ src_, int src_bf16, int64_t row0, int64_t M,
                                                 int K_true, int KP, int64_t lda, int tid) {
-    const int c4n = KP / 4;                                   // float4 per padded row
+    const int c4n = KP / 4;                                   // 4-element groups per padded row
     if ((K_true & 3) == 0 && (lda & 3) == 0) {
+        if (src_bf16 && (K_true & 7) == 0 && (lda & 7) == 0) {
+            // 16-byte pieces (8 bf16 = one swizzle chunk), every load of the tile in flight before the first store
+            const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(src_);
+            const int c8n = KP / 8;
+            for (int base = 0; base < TM * c8n; base += NT * 8) {
+                uint4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = base + u * NT + tid;
+                    const int r = e / c8n, c8 = e - r * c8n;
+                    v[u] = make_uint4(0u, 0u, 0u, 0u);
+                    if (e < TM * c8n && row0 + r < M && 8 * c8 < K_true) v[u] = __ldg(reinterpret_cast<const uint4*>(src + (row0 + r) * lda) + c8);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = base + u * NT + tid;
+                    if (e >= TM * c8n) continue;
+                    const int r = e / c8n, c8 = e - r * c8n;
+                    *reinterpret_cast<uint4*>(tiles + (c8 >> 3) * 16384 + tc::sw128_chunk(r, c8 & 7)) = v[u];
+                }
+            }
+            return;
+        }
+        if (src_bf16) {
+            const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(src_);
+            for (int base = 0; base < TM * c4n; base += NT * 8) {
+                uint2 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = base + u * NT + tid;
+                    const int r = e / c4n, c4 = e - r * c4n;
+                    v[u] = make_uint2(0u, 0u);
+                    if (e < TM * c4n && row0 + r < M && 4 * c4 < K_true) v[u] = __ldg(reinterpret_cast<const uint2*>(src + (row0 + r) * lda) + c4);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = base + u * NT + tid;
+                    if (e >= TM * c4n) continue;
+                    const int r = e / c4n, c4 = e - r * c4n;
+                    const int col = 4 * c4;
+                    *reinterpret_cast<uint2*>(tiles + (col >> 6) * 16384 + tc::sw128_offset(r, col & 63)) = v[u];
+                }
+            }
+            return;
+        }
+        const float* src = static_cast<const float*>(src_);
         for (int base = 0; base < TM * c4n; base += NT * 8) {
             float4 v[8];
 #pragma unroll
@@ -47,8 +95,11 @@ __device__ __forceinline__ void stage_rows_bf16(uint8_t* tiles, const float* __r
     } else {
         for (int e = tid; e < TM * KP; e += NT) {
             const int r = e / KP, k = e - r * KP;
-            const float v = (row0 + r < M && k < K_true) ? src[(row0 + r) * lda + k] : 0.0f;
-            *reinterpret_cast<__nv_bfloat16*>(tiles + (k >> 6) * 16384 + tc::sw128_offset(r, k & 63)) = __float2bfloat16(v);
+            __nv_bfloat16 v = __float2bfloat16(0.0f);
+            if (row0 + r < M && k < K_true)
+                v = src_bf16 ? static_cast<const __nv_bfloat16*>(src_)[(row0 + r) * lda + k]
+                             : __float2bfloat16(static_cast<const float*>(src_)[(row0 + r) * lda + k]);
+            *reinterpret_cast<__nv_bfloat16*>(tiles + (k >> 6) * 16384 + tc::sw128_offset(r, k & 63)) = v;
         }
     }
 }
@@ -57,16 +108,17 @@ __device__ __forceinline__ void stage_rows_bf16(uint8_t* tiles, const float* __r
 // rows GEMM
 // ---------------------------------------------------------------------------------------------------------------
 struct RowsParams {
-    const float* A;
+    const void* A;
+    int a_bf16, c_bf16;   // A / C stored as bf16 row-major instead of fp32 (lda / ldc in elements)
     int64_t M, lda;
     int K, KP;            // true / padded (multiple of 64) inner size
     const float* W;
     int w_kn;             // 0: W[N][K]   1: W[K][N]
     int N, NP;            // true / padded (multiple of 16) output size
     const float* bias;
-    float* C;
+    void* C;
     int64_t ldc;
-    float beta;           // C = result + beta * C  (0 or 1)
+    float beta;           // C = result + beta * C  (0 or 1; fp32 C only)
 };
 
 __global__ void __launch_bounds__(kThreads, 3) gemm_tc_rows_kernel(const RowsParams p) {
@@ -110,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, 3) gemm_tc_rows_kernel(const RowsPar
     uint32_t phase = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row0 = tile * TM;
-        stage_rows_bf16<kThreads>(sA, p.A, row0, p.M, p.K, p.KP, p.lda, tid);
+        stage_rows_bf16<kThreads>(sA, p.A, p.a_bf16, row0, p.M, p.K, p.KP, p.lda, tid);
         tc::fence_proxy_async();
         tc::tc_fence_before();
         __syncthreads();
@@ -145,6 +197,32 @@ __global__ void __launch_bounds__(kThreads, 3) gemm_tc_rows_kernel(const RowsPar
                     srow[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
             }
             __syncthreads();
+            if (p.c_bf16 && vec_ok && (p.ldc & 7) == 0 && (p.N & 7) == 0) {
+                // bf16 result (rounded once here: what every consumer would do on load), 8 columns = 16 bytes per thread
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = u * kThreads + tid;
+                    const int rr = e >> 3, c8 = e & 7;
+                    const int64_t row = row0 + rr;
+                    const int col = c0 + 8 * c8;
+                    if (row < p.M && col < p.N) {
+                        float4 o0 = *reinterpret_cast<const float4*>(sOut + rr * 272 + 32 * c8);
+                        float4 o1 = *reinterpret_cast<const float4*>(sOut + rr * 272 + 32 * c8 + 16);
+                        if (p.bias) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+                            o0.x += b0.x; o0.y += b0.y; o0.z += b0.z; o0.w += b0.w;
+                            o1.x += b1.x; o1.y += b1.y; o1.z += b1.z; o1.w += b1.w;
+                        }
+                        uint4 w;
+                        w.x = epi::cvt2(o0.x, o0.y); w.y = epi::cvt2(o0.z, o0.w);
+                        w.z = epi::cvt2(o1.x, o1.y); w.w = epi::cvt2(o1.z, o1.w);
+                        *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col) = w;
+                    }
+                }
+                __syncthreads();
+                continue;
+            }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int e = u * kThreads + tid;
@@ -153,7 +231,25 @@ __global__ void __launch_bounds__(kThreads, 3) gemm_tc_rows_kernel(const RowsPar
                 const int col = c0 + 4 * c4;
                 if (row >= p.M || col >= p.N) continue;
                 float4 o = *reinterpret_cast<const float4*>(sOut + rr * 272 + 16 * c4);
-                float* out = p.C + row * p.ldc + col;
+                if (p.c_bf16) {                              // rounded once here: what every consumer would do on load
+                    __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col;
+                    float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (p.bias && col + j < p.N) ov[j] += p.bias[col + j];
+                    if (vec_ok) {
+                        uint2 w;
+                        w.x = epi::cvt2(ov[0], ov[1]);
+                        w.y = epi::cvt2(ov[2], ov[3]);
+                        *reinterpret_cast<uint2*>(ob) = w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (col + j < p.N) ob[j] = __float2bfloat16(ov[j]);
+                    }
+                    continue;
+                }
+                float* out = static_cast<float*>(p.C) + row * p.ldc + col;
                 if (vec_ok) {
                     if (p.bias) {
                         const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
@@ -193,8 +289,9 @@ __global__ void __launch_bounds__(kThreads, 3) gemm_tc_rows_kernel(const RowsPar
 // TMEM: accumulator g covers A columns [128 g, 128 g + 128): 80 columns each (64 for dW + ones column for db).
 // ---------------------------------------------------------------------------------------------------------------
 struct WgradParams {
-    const float* A;
-    const float* B;
+    const void* A;
+    const void* B;
+    int a_bf16, b_bf16;   // operands stored as bf16 row-major
     int64_t M, lda, ldb;
     int N1, N2;
     float* dW;            // [N1, N2]
@@ -240,8 +337,8 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_wgrad_kernel(const WgradP
             ph[s] ^= 1;
         }
         const int64_t row0 = tile * TM;
-        stage_rows_bf16<kThreads>(st, p.A, row0, p.M, p.N1, ga * 64, p.lda, tid);
-        stage_rows_bf16<kThreads>(st + ga * 16384, p.B, row0, p.M, p.N2, 64, p.ldb, tid);
+        stage_rows_bf16<kThreads>(st, p.A, p.a_bf16, row0, p.M, p.N1, ga * 64, p.lda, tid);
+        stage_rows_bf16<kThreads>(st + ga * 16384, p.B, p.b_bf16, row0, p.M, p.N2, 64, p.ldb, tid);
         tc::fence_proxy_async();
         tc::tc_fence_before();
         __syncthreads();
@@ -304,14 +401,15 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_wgrad_kernel(const WgradP
 
 }  // namespace
 
-extern "C" int u2gnn_gemm_tc_rows(const float* A, int64_t M, int K, int64_t lda, const float* W, int w_kn, int N,
-                                  const float* bias, float beta, float* C, int64_t ldc, u2gnn_stream_t stream) {
+extern "C" int u2gnn_gemm_tc_rows_ex(const void* A, int a_bf16, int64_t M, int K, int64_t lda, const float* W, int w_kn, int N,
+                                     const float* bias, float beta, void* C, int c_bf16, int64_t ldc, u2gnn_stream_t stream) {
     if (!A || !W || !C || M < 0 || K < 1 || N < 1 || lda < K || ldc < N) return U2GNN_EINVAL;
+    if (c_bf16 && beta != 0.0f) return U2GNN_EINVAL;
     if (K > 256 || N > 256) return U2GNN_EUNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(C)) % 16) return U2GNN_EALIGN;
     if (M == 0) return U2GNN_OK;
     RowsParams p;
-    p.A = A; p.M = M; p.lda = lda; p.K = K; p.KP = (K + 63) / 64 * 64;
+    p.A = A; p.a_bf16 = a_bf16; p.c_bf16 = c_bf16; p.M = M; p.lda = lda; p.K = K; p.KP = (K + 63) / 64 * 64;
     p.W = W; p.w_kn = w_kn; p.N = N; p.NP = (N + 15) / 16 * 16;
     p.bias = bias; p.C = C; p.ldc = ldc; p.beta = beta;
     const int kt = p.KP / 64;
@@ -329,14 +427,19 @@ extern "C" int u2gnn_gemm_tc_rows(const float* A, int64_t M, int K, int64_t lda,
     U2GNN_CHECK_LAUNCH();
 }
 
-extern "C" int u2gnn_gemm_tc_wgrad(const float* A, int64_t M, int N1, int64_t lda, const float* B, int N2, int64_t ldb,
-                                   float* dW, float* db, u2gnn_stream_t stream) {
+extern "C" int u2gnn_gemm_tc_rows(const float* A, int64_t M, int K, int64_t lda, const float* W, int w_kn, int N,
+                                  const float* bias, float beta, float* C, int64_t ldc, u2gnn_stream_t stream) {
+    return u2gnn_gemm_tc_rows_ex(A, 0, M, K, lda, W, w_kn, N, bias, beta, C, 0, ldc, stream);
+}
+
+extern "C" int u2gnn_gemm_tc_wgrad_ex(const void* A, int a_bf16, int64_t M, int N1, int64_t lda, const void* B, int b_bf16, int N2,
+                                      int64_t ldb, float* dW, float* db, u2gnn_stream_t stream) {
     if (!A || !B || !dW || M < 0 || N1 < 1 || N2 < 1 || lda < N1 || ldb < N2) return U2GNN_EINVAL;
     if (N1 > 256 || N2 > 64) return U2GNN_EUNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) % 16) return U2GNN_EALIGN;
     if (M == 0) return U2GNN_OK;
     WgradParams p;
-    p.A = A; p.B = B; p.M = M; p.lda = lda; p.ldb = ldb; p.N1 = N1; p.N2 = N2; p.dW = dW; p.db = db;
+    p.A = A; p.B = B; p.a_bf16 = a_bf16; p.b_bf16 = b_bf16; p.M = M; p.lda = lda; p.ldb = ldb; p.N1 = N1; p.N2 = N2; p.dW = dW; p.db = db;
     const int ga = (N1 + 63) / 64;
     const size_t smem = 1024 + (size_t)2 * (ga + 1) * 16384 + 2 * 16384;
     if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
@@ -345,4 +448,9 @@ extern "C" int u2gnn_gemm_tc_wgrad(const float* A, int64_t M, int N1, int64_t ld
     const int64_t cap = (int64_t)U2GNN_NUM_SMS * ((smem + 1024 <= 113 * 1024) ? 2 : 1);   // narrow A: two CTAs per SM overlap load and MMA phases
     gemm_tc_wgrad_kernel<<<(int)(n_tiles < cap ? n_tiles : cap), kThreads, smem, as_stream(stream)>>>(p);
     U2GNN_CHECK_LAUNCH();
+}
+
+extern "C" int u2gnn_gemm_tc_wgrad(const float* A, int64_t M, int N1, int64_t lda, const float* B, int N2, int64_t ldb,
+                                   float* dW, float* db, u2gnn_stream_t stream) {
+    return u2gnn_gemm_tc_wgrad_ex(A, 0, M, N1, lda, B, 0, N2, ldb, dW, db, stream);
 }

@@ -186,13 +186,15 @@ def wgrad(dout, M_rows, n_out, inp, n_in, dW, db=None):
         LIB.call("u2gnn_colsum", _ptr(dout), M_rows, n_out, n_out, _ptr(db), 1, _stream())
 
 
-def linear_tc(A, M, K, W, w_kn, N, bias=None, beta=0.0, out=None):
-    """bf16 tensor-core projection: out[M,N] = A[M,K] W^T (+bias) (+beta*out)."""
+def linear_tc(A, M, K, W, w_kn, N, bias=None, beta=0.0, out=None, out_bf16=False):
+    """bf16 tensor-core projection: out[M,N] = A[M,K] W^T (+bias) (+beta*out).  A may be fp32 or bf16 (the dtype the
+    producer stored); out_bf16 stores the result rounded to bf16 (every consumer rounds it anyway)."""
     if out is None:
-        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+        out = torch.empty((M, N), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=A.device)
     if LIB.timed is not None:
         FLOPS["u2gnn_gemm_tc_rows"] = FLOPS.get("u2gnn_gemm_tc_rows", 0) + 2 * M * N * K
-    LIB.call("u2gnn_gemm_tc_rows", _ptr(A), M, K, K, _ptr(W), int(w_kn), N, _ptr(bias), beta, _ptr(out), N, _stream())
+    LIB.call("u2gnn_gemm_tc_rows_ex", _ptr(A), int(A.dtype == torch.bfloat16), M, K, K, _ptr(W), int(w_kn), N, _ptr(bias), beta,
+             _ptr(out), int(out.dtype == torch.bfloat16), N, _stream())
     return out
 
 
@@ -200,7 +202,8 @@ def wgrad_tc(dout, M, n_out, inp, n_in, dW, db=None):
     """dW[n_out, n_in] += dout^T @ inp; db[n_out] += colsum(dout)  (tensor cores, bf16 operands)."""
     if M == 0:
         return
-    LIB.call("u2gnn_gemm_tc_wgrad", _ptr(dout), M, n_out, n_out, _ptr(inp), n_in, n_in, _ptr(dW), _ptr(db), _stream())
+    LIB.call("u2gnn_gemm_tc_wgrad_ex", _ptr(dout), int(dout.dtype == torch.bfloat16), M, n_out, n_out, _ptr(inp),
+             int(inp.dtype == torch.bfloat16), n_in, n_in, _ptr(dW), _ptr(db), _stream())
 
 
 def add_dropout_ln_fwd(res, a, M, d, drop, gamma, beta):
@@ -256,12 +259,13 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
     f32 = dict(dtype=torch.float32, device=dev)
     sv = LayerSaved(x=x, B=B, S=S, Sq=Sq)
     tc_proj = precision == "bf16" and not long_seq and d <= 64
+    tc_attn = tc_proj and d == 64 and Sq == S and S >= 2        # tensor-core attention core: bf16 qkv / ctx between the kernels
     if tc_proj:
-        qkv = linear_tc(x, M, d, p["self_attn.in_proj_weight"], 0, 3 * d, bias=p["self_attn.in_proj_bias"])
+        qkv = linear_tc(x, M, d, p["self_attn.in_proj_weight"], 0, 3 * d, bias=p["self_attn.in_proj_bias"], out_bf16=tc_attn)
     else:
         qkv = torch.empty((M, 3 * d), **f32)
         sgemm(0, 1, M, 3 * d, d, x, d, p["self_attn.in_proj_weight"], d, qkv, 3 * d, bias=p["self_attn.in_proj_bias"])
-    ctx = torch.empty((Mq, d), **f32)
+    ctx = torch.empty((Mq, d), dtype=torch.bfloat16 if tc_attn else torch.float32, device=dev)
     if long_seq:
         assert B == 1 and Sq == S
         scores = torch.empty((S, S), **f32)
@@ -270,8 +274,8 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
         LIB.call("u2gnn_softmax_rows_fwd", _ptr(scores), S, S, _ptr(pd), seed, drop_ids[0], thr, _stream())
         sgemm(0, 0, S, d, S, pd, S, qkv, 3 * d, ctx, d, b_off=2 * d)
         sv.probs, sv.pd = scores, pd
-    elif tc_proj and d == 64 and Sq == S and S >= 2:
-        LIB.call("u2gnn_seqattn_tc_fwd", _ptr(qkv), B, S, d, seed, drop_ids[0], thr, _ptr(ctx), _stream())
+    elif tc_attn:
+        LIB.call("u2gnn_seqattn_tc_fwd_ex", _ptr(qkv), B, S, d, seed, drop_ids[0], thr, _ptr(ctx), 1, _stream())
     else:
         LIB.call("u2gnn_seqattn_fwd", _ptr(qkv), B, S, Sq, d, seed, drop_ids[0], thr, _ptr(ctx), _stream())
     if tc_proj:
@@ -360,14 +364,15 @@ def encoder_layer_bwd(dy2, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
     dz1, da = add_dropout_ln_bwd(dy1, sv.z1, sv.st1, Mq, d, p["norm1.weight"], (seed, drop_ids[1], thr),
                                  g["norm1.weight"], g["norm1.bias"])
     tc_proj = sv.packed is not None and not long_seq and d <= 64
+    tc_attn = tc_proj and d == 64 and Sq == S and S >= 2
     if tc_proj:
         wgrad_tc(da, Mq, d, sv.ctx, d, g["self_attn.out_proj.weight"], g["self_attn.out_proj.bias"])
-        dctx = linear_tc(da, Mq, d, p["self_attn.out_proj.weight"], 1, d)
+        dctx = linear_tc(da, Mq, d, p["self_attn.out_proj.weight"], 1, d, out_bf16=tc_attn)
     else:
         wgrad(da, Mq, d, sv.ctx, d, g["self_attn.out_proj.weight"], g["self_attn.out_proj.bias"])
         dctx = torch.empty((Mq, d), **f32)
         sgemm(0, 0, Mq, d, d, da, d, p["self_attn.out_proj.weight"], d, dctx, d)
-    dqkv = torch.empty((M, 3 * d), **f32)
+    dqkv = torch.empty((M, 3 * d), dtype=torch.bfloat16 if tc_attn else torch.float32, device=dev)
     if long_seq:
         scale = math.sqrt(1.0 / d)
         dpd = torch.empty((S, S), **f32)
@@ -376,8 +381,8 @@ def encoder_layer_bwd(dy2, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
         LIB.call("u2gnn_softmax_rows_bwd", _ptr(sv.probs), _ptr(dpd), S, S, seed, drop_ids[0], thr, _stream())
         sgemm(0, 0, S, d, S, dpd, S, sv.qkv, 3 * d, dqkv, 3 * d, alpha=scale, b_off=d)     # dq = ds @ k * scale
         sgemm(1, 0, S, d, S, dpd, S, sv.qkv, 3 * d, dqkv, 3 * d, alpha=scale, c_off=d)     # dk = ds^T @ q * scale
-    elif tc_proj and d == 64 and Sq == S and S >= 2:
-        LIB.call("u2gnn_seqattn_tc_bwd", _ptr(sv.qkv), _ptr(dctx), B, S, d, seed, drop_ids[0], thr, _ptr(dqkv), _stream())
+    elif tc_attn:
+        LIB.call("u2gnn_seqattn_tc_bwd_ex", _ptr(sv.qkv), _ptr(dctx), B, S, d, seed, drop_ids[0], thr, _ptr(dqkv), 1, _stream())
     else:
         LIB.call("u2gnn_seqattn_bwd", _ptr(sv.qkv), _ptr(dctx), B, S, Sq, d, seed, drop_ids[0], thr, _ptr(dqkv), _stream())
     if tc_proj:

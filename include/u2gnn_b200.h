@@ -217,6 +217,19 @@ int u2gnn_seqattn_tc_bwd(const float* qkv, const float* dctx, int64_t B, int S, 
 int u2gnn_tc_selftest(int mode, const float* A, const float* B, float* C, int K, int N, void* scratch,
                       u2gnn_stream_t stream);
 
+/* ---- bf16 activation I/O for the attention block of the bf16 mode.  Every consumer of qkv / ctx / dctx / dqkv rounds them
+        to bf16 before its tensor-core product, so the producers store them as bf16 row-major (rounded once, bit-identical
+        results) and the block moves half the HBM bytes.  *_bf16 flags: 0 = fp32 buffer, 1 = bf16 buffer; leading
+        dimensions are in ELEMENTS; beta must be 0 for a bf16 C. ---- */
+int u2gnn_gemm_tc_rows_ex(const void* A, int a_bf16, int64_t M, int K, int64_t lda, const float* W, int w_kn, int N,
+                          const float* bias, float beta, void* C, int c_bf16, int64_t ldc, u2gnn_stream_t stream);
+int u2gnn_gemm_tc_wgrad_ex(const void* A, int a_bf16, int64_t M, int N1, int64_t lda, const void* B, int b_bf16, int N2,
+                           int64_t ldb, float* dW, float* db, u2gnn_stream_t stream);
+int u2gnn_seqattn_tc_fwd_ex(const void* qkv, int64_t B, int S, int d, uint64_t seed, uint32_t rng_stream, int thr,
+                            void* ctx, int io_bf16, u2gnn_stream_t stream);
+int u2gnn_seqattn_tc_bwd_ex(const void* qkv, const void* dctx, int64_t B, int S, int d, uint64_t seed,
+                            uint32_t rng_stream, int thr, void* dqkv, int io_bf16, u2gnn_stream_t stream);
+
 /* ---- device-side batch builder (replaces the host loop of get_batch_data,
         train_pytorch_U2GNN_Sup.py:91-119 / train_pytorch_U2GNN_UnSup.py:96-128).
         Dataset adjacency as one CSR over dataset-wide node ids (g_rowptr[V+1], g_col[E]); the batch is n_graphs selected

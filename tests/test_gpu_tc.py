@@ -281,3 +281,59 @@ def test_seqattn_tc_matches_fp32_kernels(U, B, S, p):
     for k, name in enumerate(("dq", "dk", "dv")):
         a, b = dq16[:, k * d:(k + 1) * d], dq32[:, k * d:(k + 1) * d]
         assert ((a - b).norm() / b.norm()).item() < 3e-2, name
+
+
+# ------------------------------------------------------------------ bf16 activation I/O variants (bit-identical to fp32 I/O)
+@pytest.mark.parametrize("M,K,N", [(1000, 64, 192), (517, 192, 64), (300, 64, 64)])
+def test_gemm_tc_rows_bf16_io_matches_fp32_io(U, M, K, N):
+    """Storing the projection output as bf16 (and reading a bf16 input) must equal rounding the fp32-I/O result: every
+    consumer of these tensors rounds them to bf16 anyway."""
+    from u2gnn_b200 import engine as E
+    g = torch.Generator(device="cuda").manual_seed(M + K + N)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / 8
+    b = torch.randn(N, device="cuda", generator=g)
+    ref = E.linear_tc(A, M, K, W, 0, N, bias=b)                                # fp32 in, fp32 out
+    out_b = E.linear_tc(A, M, K, W, 0, N, bias=b, out_bf16=True)               # fp32 in, bf16 out
+    assert out_b.dtype == torch.bfloat16
+    assert torch.equal(out_b, ref.to(torch.bfloat16))
+    A_b = A.to(torch.bfloat16)
+    ref2 = E.linear_tc(A_b.float(), M, K, W, 0, N, bias=b)                     # the same rounded input through the fp32 path
+    out2 = E.linear_tc(A_b, M, K, W, 0, N, bias=b)                             # bf16 in, fp32 out
+    assert torch.equal(out2, ref2)
+
+
+@pytest.mark.parametrize("M,N1,N2", [(1000, 192, 64), (700, 64, 64)])
+def test_gemm_tc_wgrad_bf16_operands_match(U, M, N1, N2):
+    from u2gnn_b200 import engine as E
+    g = torch.Generator(device="cuda").manual_seed(M + N1)
+    A = torch.randn(M, N1, device="cuda", generator=g).to(torch.bfloat16)
+    B = torch.randn(M, N2, device="cuda", generator=g)
+    dW0 = torch.zeros(N1, N2, device="cuda"); db0 = torch.zeros(N1, device="cuda")
+    dW1 = torch.zeros(N1, N2, device="cuda"); db1 = torch.zeros(N1, device="cuda")
+    E.wgrad_tc(A.float(), M, N1, B, N2, dW0, db0)
+    E.wgrad_tc(A, M, N1, B, N2, dW1, db1)
+    torch.cuda.synchronize()
+    # same bf16 operands, fp32 accumulation; the flush uses atomics (order may differ between runs)
+    assert (dW1 - dW0).abs().max().item() <= 1e-4 * dW0.abs().max().item()
+    assert (db1 - db0).abs().max().item() <= 1e-4 * db0.abs().max().item()
+
+
+@pytest.mark.parametrize("B,S,p", [(300, 17, 0.5), (77, 9, 0.0)])
+def test_seqattn_tc_bf16_io_matches_fp32_io(U, B, S, p):
+    from u2gnn_b200 import engine as E
+    d = 64
+    thr = E.dropout_threshold(p)
+    g = torch.Generator(device="cuda").manual_seed(B + S)
+    qkv = torch.randn(B * S, 3 * d, device="cuda", generator=g).to(torch.bfloat16)
+    dctx = torch.randn(B * S, d, device="cuda", generator=g).to(torch.bfloat16)
+    ctx0 = torch.empty(B * S, d, device="cuda"); ctx1 = torch.empty(B * S, d, device="cuda", dtype=torch.bfloat16)
+    q32, g32 = qkv.float(), dctx.float()
+    U.LIB.call("u2gnn_seqattn_tc_fwd", q32.data_ptr(), B, S, d, 5, 3, thr, ctx0.data_ptr(), E._stream())
+    U.LIB.call("u2gnn_seqattn_tc_fwd_ex", qkv.data_ptr(), B, S, d, 5, 3, thr, ctx1.data_ptr(), 1, E._stream())
+    dq0 = torch.empty(B * S, 3 * d, device="cuda"); dq1 = torch.empty(B * S, 3 * d, device="cuda", dtype=torch.bfloat16)
+    U.LIB.call("u2gnn_seqattn_tc_bwd", q32.data_ptr(), g32.data_ptr(), B, S, d, 5, 3, thr, dq0.data_ptr(), E._stream())
+    U.LIB.call("u2gnn_seqattn_tc_bwd_ex", qkv.data_ptr(), dctx.data_ptr(), B, S, d, 5, 3, thr, dq1.data_ptr(), 1, E._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(ctx1, ctx0.to(torch.bfloat16))
+    assert torch.equal(dq1, dq0.to(torch.bfloat16))
