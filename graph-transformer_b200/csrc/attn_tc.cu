@@ -203,8 +203,11 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const Params p) {
         phase ^= 1;
         tc::tc_fence_after();
         // ---- 3. per-row softmax (threads 0..127: row r = node * S + i reads the S columns of its own node)
-        if (warp < 4) {
-            float pd[SMAX], ds[BWD ? SMAX : 1];
+        // Forward: warps 0-3 (thread = row).  Backward: BOTH warp sets work on every row - warps 0-3 produce the P~ row,
+        // warps 4-7 (same TMEM lane quarters) recompute the cheap softmax and produce the dS row - which halves the
+        // longest phase of the backward tile and the registers each thread holds.
+        if (warp < 4 || BWD) {
+            const bool role_ds = BWD && warp >= 4;
             const bool live = r < rows;
             const int node = live ? r / S : 0, i = live ? r - node * S : 0;
             const int col0 = node * S;
@@ -215,9 +218,9 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const Params p) {
             const int node_lo = (wq * 32) / S;                               // node of the warp's first row
             const int sel = node - node_lo;                                  // 0 .. 3
             const int n_cand = ((wq * 32 + 31) / S) - node_lo + 1;           // warp-uniform
-            uint32_t sv[SMAX], dv[BWD ? SMAX : 1];
+            float sv[SMAX], dv[BWD ? SMAX : 1];                              // scores -> p / P~ ; dP -> dS
 #pragma unroll
-            for (int j = 0; j < SMAX; ++j) { sv[j] = 0u; dv[BWD ? j : 0] = 0u; }
+            for (int j = 0; j < SMAX; ++j) { sv[j] = 0.f; dv[BWD ? j : 0] = 0.f; }
             for (int cnd = 0; cnd < n_cand; ++cnd) {                         // warp-uniform trip count
                 uint32_t t0[32];
                 const int cb = (node_lo + cnd) * S;                          // <= 127: columns cb .. cb + 31 stay inside the allocation
@@ -225,8 +228,8 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const Params p) {
                 tc::tmem_ld_wait();
                 const bool mine = live && (sel == cnd);
 #pragma unroll
-                for (int j = 0; j < SMAX; ++j) sv[j] = (mine && j < S) ? t0[j] : sv[j];
-                if (BWD) {
+                for (int j = 0; j < SMAX; ++j) sv[j] = (mine && j < S) ? __uint_as_float(t0[j]) : sv[j];
+                if (BWD && role_ds) {                                        // warp-uniform
                     // dP lives in columns [128, 256) = the end of the allocation: the 32-column window is clamped to it and
                     // the registers are shifted down by the (warp-uniform) difference with a barrel shifter on registers
                     const int cbl = cb < 96 ? cb : 96, dsh = cb - cbl;
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const Params p) {
                         }
                     }
 #pragma unroll
-                    for (int j = 0; j < SMAX; ++j) dv[BWD ? j : 0] = (mine && j < S) ? t0[j] : dv[BWD ? j : 0];
+                    for (int j = 0; j < SMAX; ++j) dv[BWD ? j : 0] = (mine && j < S) ? __uint_as_float(t0[j]) : dv[BWD ? j : 0];
                 }
             }
             // dropout keep bits of this row: elements ebase .. ebase + S - 1 of the [B, S, S] probability tensor lie in at
@@ -258,40 +261,36 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const Params p) {
                 float m = -INFINITY;
 #pragma unroll
                 for (int j = 0; j < SMAX; ++j)
-                    if (j < S) m = fmaxf(m, __uint_as_float(sv[j]) * qscale);
+                    if (j < S) m = fmaxf(m, sv[j] * qscale);
                 float sum = 0.f;
 #pragma unroll
                 for (int j = 0; j < SMAX; ++j) {
-                    pd[j] = (j < S) ? __expf(__uint_as_float(sv[j]) * qscale - m) : 0.f;
-                    sum += pd[j];
+                    sv[j] = (j < S) ? __expf(sv[j] * qscale - m) : 0.f;
+                    sum += sv[j];
                 }
                 const float inv = 1.0f / sum;
-                float tsum = 0.f;
+                if (!role_ds) {
 #pragma unroll
-                for (int j = 0; j < SMAX; ++j) {
-                    if (j < S) {
-                        const float mult = ((keep_bits >> j) & 1u) ? dscale : 0.0f;
-                        const float pj = pd[j] * inv;
-                        if (BWD) {
-                            const float dp = __uint_as_float(dv[BWD ? j : 0]) * mult;
-                            ds[BWD ? j : 0] = dp;
-                            tsum = fmaf(pj, dp, tsum);
-                            sv[j] = __float_as_uint(pj);          // keep p for the second pass
-                        }
-                        pd[j] = pj * mult;
+                    for (int j = 0; j < SMAX; ++j) sv[j] = sv[j] * inv * (((keep_bits >> j) & 1u) ? dscale : 0.0f);     // P~
+                } else {
+                    float tsum = 0.f;
+#pragma unroll
+                    for (int j = 0; j < SMAX; ++j) {
+                        sv[j] *= inv;                                                                              // p
+                        dv[BWD ? j : 0] *= (((keep_bits >> j) & 1u) ? dscale : 0.0f);                               // dp
+                        tsum = fmaf(sv[j], dv[BWD ? j : 0], tsum);
                     }
-                }
-                if (BWD) {
 #pragma unroll
-                    for (int j = 0; j < SMAX; ++j)
-                        if (j < S) ds[BWD ? j : 0] = __uint_as_float(sv[j]) * (ds[BWD ? j : 0] - tsum) * qscale;
+                    for (int j = 0; j < SMAX; ++j) dv[BWD ? j : 0] = sv[j] * (dv[BWD ? j : 0] - tsum) * qscale;      // dS
                 }
             }
             // the TMEM reads above must be finished before anyone overwrites S / dP (step 4 reuses the columns); the
             // shared-memory rows are written after the block-wide barrier below for the backward (P~ reuses V)
             tc::tc_fence_before();
-            write_diag_row<SMAX>(sP0, sP1, r, col0, live ? S : 0, pd);
-            if constexpr (BWD) write_diag_row<SMAX>(sS0, sS1, r, col0, live ? S : 0, ds);
+            if (!role_ds) write_diag_row<SMAX>(sP0, sP1, r, col0, live ? S : 0, sv);
+            if constexpr (BWD) {
+                if (role_ds) write_diag_row<SMAX>(sS0, sS1, r, col0, live ? S : 0, dv);
+            }
         }
         tc::fence_proxy_async();
         tc::tc_fence_before();
