@@ -285,6 +285,241 @@ __global__ void __launch_bounds__(kThreads, 3) gemm_tc_rows_kernel(const RowsPar
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// rows GEMM, warp-specialised persistent version (aligned shapes: fp32 A with K = 64, bf16 A with K = 64 / 192).
+// One CTA per SM, 416 threads:  warps 0-7 loaders, warps 8-11 epilogue (thread = row), warp 12 MMA issuer.
+//   loaders  : coalesced 128-bit loads of tile i+1 are IN FLIGHT (registers) while tile i is rounded / copied into the
+//              swizzled A stage -> ~64 KB of loads outstanding per SM, what HBM latency x bandwidth needs
+//   MMA warp : K/16 tcgen05.mma per tile into one of two TMEM accumulators, commit -> stage free, accumulator full
+//   epilogue : tcgen05.ld -> padded staging -> coalesced stores (bias / beta / bf16 rounding), accumulator free
+// so load(i+1), MMA(i) and epilogue(i-1) overlap; the phase-serial kernel above (kept for unaligned shapes) reached
+// 46 % of the HBM bandwidth with three CTAs per SM.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kWsLoadWarps = 8, kWsEpiWarp0 = 8, kWsMmaWarp = 12, kWsThreads = 416;
+
+struct __align__(8) WsBars {
+    uint64_t a_full[2], a_free[2], acc_full[2], acc_free[2];
+};
+
+__device__ __forceinline__ void ws_named_bar(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <bool A_BF16, int NPF>      // NPF: 16-byte pieces per loader thread per tile (fp32 K 64: 8; bf16 K 64: 4; bf16 K 192: 12)
+__global__ void __launch_bounds__(kWsThreads, 1) gemm_tc_rows_ws_kernel(const RowsParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int kt = p.KP / 64;
+    uint8_t* sA = smem;                                     // 2 stages x kt tiles of [128 x 64]
+    uint8_t* sB = sA + 2 * kt * 16384;                      // kt tiles of [NP x 64]
+    uint8_t* sOut = sB + kt * p.NP * 128;                   // fp32 staging of one 64-column piece: [128 rows x 272 B]
+    __shared__ WsBars bars;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int acc_stride = (p.NP <= 64) ? 64 : (p.NP <= 128 ? 128 : 256);
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&bars.a_full[i], kWsLoadWarps);
+            tc::mbar_init(&bars.a_free[i], 1);
+            tc::mbar_init(&bars.acc_full[i], 1);
+            tc::mbar_init(&bars.acc_free[i], 4);
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == kWsMmaWarp) {
+        if (acc_stride == 64) tc::tmem_alloc<128>(&tmem_slot);
+        else if (acc_stride == 128) tc::tmem_alloc<256>(&tmem_slot);
+        else tc::tmem_alloc<512>(&tmem_slot);
+    }
+    for (int e = tid; e < p.NP * p.KP; e += kWsThreads) {   // weights -> K-major image
+        const int n = e / p.KP, k = e - n * p.KP;
+        float w = 0.0f;
+        if (n < p.N && k < p.K) w = p.w_kn ? p.W[(size_t)k * p.N + n] : p.W[(size_t)n * p.K + k];
+        *reinterpret_cast<__nv_bfloat16*>(sB + (k >> 6) * (p.NP * 128) + tc::sw128_offset(n, k & 63)) = __float2bfloat16(w);
+    }
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const int64_t n_tiles = (p.M + TM - 1) / TM;
+    const int64_t my_tiles = (n_tiles > (int64_t)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp < kWsLoadWarps) {
+        // ================= loaders =================
+        constexpr int NT = kWsLoadWarps * 32;
+        const int ppr = A_BF16 ? p.KP / 8 : 16;              // 16-byte pieces per row
+        uint4 b0[NPF], b1[NPF];
+        auto load = [&](int64_t i, uint4 (&buf)[NPF]) {
+            const int64_t r0 = ((int64_t)blockIdx.x + i * gridDim.x) * TM;
+#pragma unroll
+            for (int u = 0; u < NPF; ++u) {
+                const int e = u * NT + tid;
+                const int r = e / ppr, c = e - r * ppr;
+                buf[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (i < my_tiles && r0 + r < p.M) {
+                    if (A_BF16) buf[u] = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.A) + (r0 + r) * p.lda) + c);
+                    else buf[u] = __ldg(reinterpret_cast<const uint4*>(static_cast<const float*>(p.A) + (r0 + r) * p.lda) + c);
+                }
+            }
+        };
+        auto store = [&](int64_t i, const uint4 (&buf)[NPF]) {
+            const int s = (int)(i & 1);
+            if (i >= 2) tc::mbar_wait(&bars.a_free[s], (uint32_t)((i >> 1) - 1) & 1);
+            uint8_t* st = sA + s * kt * 16384;
+#pragma unroll
+            for (int u = 0; u < NPF; ++u) {
+                const int e = u * NT + tid;
+                const int r = e / ppr, c = e - r * ppr;
+                if (A_BF16) {
+                    *reinterpret_cast<uint4*>(st + (c >> 3) * 16384 + tc::sw128_chunk(r, c & 7)) = buf[u];
+                } else {
+                    uint2 w;
+                    w.x = epi::cvt2(__uint_as_float(buf[u].x), __uint_as_float(buf[u].y));
+                    w.y = epi::cvt2(__uint_as_float(buf[u].z), __uint_as_float(buf[u].w));
+                    *reinterpret_cast<uint2*>(st + tc::sw128_offset(r, c * 4)) = w;
+                }
+            }
+            tc::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&bars.a_full[s]);
+        };
+        load(0, b0);
+        for (int64_t i = 0; i < my_tiles; i += 2) {
+            load(i + 1, b1);
+            store(i, b0);
+            if (i + 1 < my_tiles) {
+                load(i + 2, b0);
+                store(i + 1, b1);
+            }
+        }
+    } else if (warp == kWsMmaWarp) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = tc::make_idesc(TM, p.NP, 0, 0);
+        const uint64_t b_desc = tc::make_desc_sw128(tc::smem_u32(sB), 16, 1024);
+        for (int64_t i = 0; i < my_tiles; ++i) {
+            const int s = (int)(i & 1);
+            tc::mbar_wait(&bars.a_full[s], (uint32_t)(i >> 1) & 1);
+            if (i >= 2) tc::mbar_wait(&bars.acc_free[s], (uint32_t)((i >> 1) - 1) & 1);
+            tc::tc_fence_after();
+            if (tc::elect_one()) {
+                const uint64_t a_desc = tc::make_desc_sw128(tc::smem_u32(sA + s * kt * 16384), 16, 1024);
+                for (int ks = 0; ks < p.KP / 16; ++ks) {
+                    const uint32_t ko = (uint32_t)((ks >> 2) * 1024 + (ks & 3) * 2);
+                    const uint32_t bo = (uint32_t)((ks >> 2) * (p.NP * 8) + (ks & 3) * 2);
+                    tc::mma_ss(tmem + s * acc_stride, a_desc + ko, b_desc + bo, idesc, ks > 0);
+                }
+                tc::mma_commit(&bars.a_free[s]);
+                tc::mma_commit(&bars.acc_full[s]);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= kWsEpiWarp0 && warp < kWsEpiWarp0 + 4) {
+        // ================= epilogue (128 threads, thread = row of its TMEM lane quarter) =================
+        const int wq = warp & 3, et = (warp - kWsEpiWarp0) * 32 + lane;      // et: 0..127
+        const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+        const int rt = wq * 32 + lane;                                       // row in tile (warp 8 -> quarter 0 ...)
+        const bool vec_ok = ((p.ldc & 3) == 0) && ((p.N & 3) == 0);
+        const bool bf_vec = p.c_bf16 && vec_ok && ((p.ldc & 7) == 0) && ((p.N & 7) == 0);
+        for (int64_t i = 0; i < my_tiles; ++i) {
+            const int s = (int)(i & 1);
+            const int64_t row0 = ((int64_t)blockIdx.x + i * gridDim.x) * TM;
+            tc::mbar_wait(&bars.acc_full[s], (uint32_t)(i >> 1) & 1);
+            tc::tc_fence_after();
+            for (int c0 = 0; c0 < p.NP; c0 += 64) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (c0 + 32 * h < p.NP) {
+                        uint32_t v[32];
+                        tc::tmem_ld32(tmem + lane_base + s * acc_stride + c0 + 32 * h, v);
+                        tc::tmem_ld_wait();
+                        float4* srow = reinterpret_cast<float4*>(sOut + rt * 272 + 128 * h);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            srow[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    }
+                }
+                if (c0 + 64 >= p.NP) {                                       // last piece: the accumulator is in shared memory
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&bars.acc_free[s]);
+                }
+                ws_named_bar(1, 128);
+                if (bf_vec) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int e = u * 128 + et;
+                        const int rr = e >> 3, c8 = e & 7;
+                        const int64_t row = row0 + rr;
+                        const int col = c0 + 8 * c8;
+                        if (row < p.M && col < p.N) {
+                            float4 o0 = *reinterpret_cast<const float4*>(sOut + rr * 272 + 32 * c8);
+                            float4 o1 = *reinterpret_cast<const float4*>(sOut + rr * 272 + 32 * c8 + 16);
+                            if (p.bias) {
+                                const float4 q0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                                const float4 q1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+                                o0.x += q0.x; o0.y += q0.y; o0.z += q0.z; o0.w += q0.w;
+                                o1.x += q1.x; o1.y += q1.y; o1.z += q1.z; o1.w += q1.w;
+                            }
+                            uint4 w;
+                            w.x = epi::cvt2(o0.x, o0.y); w.y = epi::cvt2(o0.z, o0.w);
+                            w.z = epi::cvt2(o1.x, o1.y); w.w = epi::cvt2(o1.z, o1.w);
+                            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col) = w;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const int e = u * 128 + et;
+                        const int rr = e >> 4, c4 = e & 15;
+                        const int64_t row = row0 + rr;
+                        const int col = c0 + 4 * c4;
+                        if (row >= p.M || col >= p.N) continue;
+                        float4 o = *reinterpret_cast<const float4*>(sOut + rr * 272 + 16 * c4);
+                        if (p.c_bf16) {
+                            __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col;
+                            const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (col + j < p.N) ob[j] = __float2bfloat16(ov[j] + (p.bias ? p.bias[col + j] : 0.0f));
+                            continue;
+                        }
+                        float* out = static_cast<float*>(p.C) + row * p.ldc + col;
+                        if (vec_ok) {
+                            if (p.bias) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                                o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+                            }
+                            if (p.beta != 0.0f) {
+                                const float4 old = *reinterpret_cast<const float4*>(out);
+                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                            }
+                            *reinterpret_cast<float4*>(out) = o;
+                        } else {
+                            const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (col + j < p.N) {
+                                    float x = ov[j] + (p.bias ? p.bias[col + j] : 0.0f);
+                                    if (p.beta != 0.0f) x += out[j];
+                                    out[j] = x;
+                                }
+                        }
+                    }
+                }
+                ws_named_bar(1, 128);                                        // staging is reused by the next piece / tile
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == kWsMmaWarp) {
+        if (acc_stride == 64) tc::tmem_dealloc<128>(tmem);
+        else if (acc_stride == 128) tc::tmem_dealloc<256>(tmem);
+        else tc::tmem_dealloc<512>(tmem);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // weight-gradient GEMM:  dW[N1, N2] += A^T B,  db[N1] += colsum(A).   N1 <= 256 (64-column groups), N2 <= 64.
 // TMEM: accumulator g covers A columns [128 g, 128 g + 128): 80 columns each (64 for dW + ones column for db).
 // ---------------------------------------------------------------------------------------------------------------
@@ -401,6 +636,13 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_wgrad_kernel(const WgradP
 
 }  // namespace
 
+static int g_rows_ws = 1;
+// experiment switch: 0 = phase-serial projection kernel for every shape, 1 = warp-specialised kernel where it applies
+extern "C" int u2gnn_gemm_tc_debug(int ws) {
+    g_rows_ws = ws;
+    return U2GNN_OK;
+}
+
 extern "C" int u2gnn_gemm_tc_rows_ex(const void* A, int a_bf16, int64_t M, int K, int64_t lda, const float* W, int w_kn, int N,
                                      const float* bias, float beta, void* C, int c_bf16, int64_t ldc, u2gnn_stream_t stream) {
     if (!A || !W || !C || M < 0 || K < 1 || N < 1 || lda < K || ldc < N) return U2GNN_EINVAL;
@@ -413,6 +655,23 @@ extern "C" int u2gnn_gemm_tc_rows_ex(const void* A, int a_bf16, int64_t M, int K
     p.W = W; p.w_kn = w_kn; p.N = N; p.NP = (N + 15) / 16 * 16;
     p.bias = bias; p.C = C; p.ldc = ldc; p.beta = beta;
     const int kt = p.KP / 64;
+    const int64_t n_tiles_ws = (M + TM - 1) / TM;
+    {   // warp-specialised persistent kernel for the aligned shapes of the attention block
+        const bool fp32_ok = !a_bf16 && K == 64 && (lda & 3) == 0;
+        const bool bf16_ok = a_bf16 && (K == 64 || K == 192) && (lda & 7) == 0;
+        const size_t smem_ws = 1024 + (size_t)2 * kt * 16384 + (size_t)kt * p.NP * 128 + 128 * 272;
+        if ((fp32_ok || bf16_ok) && smem_ws <= 227 * 1024 && g_rows_ws) {
+            const int grid = (int)(n_tiles_ws < U2GNN_NUM_SMS ? n_tiles_ws : U2GNN_NUM_SMS);
+            auto launch = [&](auto kern) {
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws);
+                kern<<<grid, kWsThreads, smem_ws, as_stream(stream)>>>(p);
+            };
+            if (fp32_ok) launch(gemm_tc_rows_ws_kernel<false, 8>);
+            else if (p.KP == 64) launch(gemm_tc_rows_ws_kernel<true, 4>);
+            else launch(gemm_tc_rows_ws_kernel<true, 12>);
+            U2GNN_CHECK_LAUNCH();
+        }
+    }
     const size_t smem = 1024 + (size_t)kt * 16384 + (size_t)kt * p.NP * 128 + 128 * 272;
     if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
     cudaFuncSetAttribute(gemm_tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -337,3 +337,31 @@ def test_seqattn_tc_bf16_io_matches_fp32_io(U, B, S, p):
     torch.cuda.synchronize()
     assert torch.equal(ctx1, ctx0.to(torch.bfloat16))
     assert torch.equal(dq1, dq0.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("M,K,N,a_bf16,c_bf16,beta", [(1000, 64, 192, 0, 1, 0.0), (148 * 128 * 3 + 77, 64, 192, 0, 1, 0.0),
+                                                      (5000, 64, 64, 1, 0, 0.0), (4097, 192, 64, 1, 0, 1.0),
+                                                      (333, 64, 64, 0, 1, 0.0), (128, 64, 64, 0, 0, 0.0), (70000, 64, 64, 0, 0, 1.0)])
+def test_gemm_tc_rows_warp_specialised_equals_phase_serial(U, M, K, N, a_bf16, c_bf16, beta):
+    """The persistent warp-specialised projection kernel and the phase-serial one compute the same MMAs on the same
+    bf16 operands: results must be bit-identical."""
+    from u2gnn_b200 import engine as E
+    g = torch.Generator(device="cuda").manual_seed(M + K + N)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    if a_bf16:
+        A = A.to(torch.bfloat16)
+    W = torch.randn(K, N, device="cuda", generator=g) / 8            # w_kn = 1 layout
+    b = torch.randn(N, device="cuda", generator=g)
+    C0 = torch.randn(M, N, device="cuda", generator=g)
+    outs = []
+    for ws in (0, 1):
+        U.LIB.call("u2gnn_gemm_tc_debug", ws)
+        C = (C0.clone() if beta else torch.empty(M, N, device="cuda")).to(torch.bfloat16 if c_bf16 else torch.float32)
+        U.LIB.call("u2gnn_gemm_tc_rows_ex", A.data_ptr(), a_bf16, M, K, K, W.data_ptr(), 1, N, b.data_ptr(), beta,
+                   C.data_ptr(), c_bf16, N, E._stream())
+        torch.cuda.synchronize()
+        outs.append(C)
+    U.LIB.call("u2gnn_gemm_tc_debug", 1)
+    assert torch.equal(outs[0], outs[1])
+    ref = A.float().to(torch.bfloat16).float() @ W.to(torch.bfloat16).float() + b + (C0 if beta else 0)
+    assert (outs[1].float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
