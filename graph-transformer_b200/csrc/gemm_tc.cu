@@ -291,8 +291,7 @@ __global__ void __launch_bounds__(kThreads, 3) gemm_tc_rows_kernel(const RowsPar
 //              swizzled A stage -> ~64 KB of loads outstanding per SM, what HBM latency x bandwidth needs
 //   MMA warp : K/16 tcgen05.mma per tile into one of two TMEM accumulators, commit -> stage free, accumulator full
 //   epilogue : tcgen05.ld -> padded staging -> coalesced stores (bias / beta / bf16 rounding), accumulator free
-// so load(i+1), MMA(i) and epilogue(i-1) overlap; the phase-serial kernel above (kept for unaligned shapes) reached
-// 46 % of the HBM bandwidth with three CTAs per SM.
+// so load(i+1), MMA(i) and epilogue(i-1) overlap.  NOT the default: see u2gnn_gemm_tc_debug below for the measurement.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kWsLoadWarps = 8, kWsEpiWarp0 = 8, kWsMmaWarp = 12, kWsThreads = 416;
 
@@ -636,8 +635,11 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_wgrad_kernel(const WgradP
 
 }  // namespace
 
-static int g_rows_ws = 1;
-// experiment switch: 0 = phase-serial projection kernel for every shape, 1 = warp-specialised kernel where it applies
+static int g_rows_ws = 0;
+// experiment switch: 0 (default) = phase-serial projection kernel for every shape, 1 = warp-specialised kernel where it
+// applies.  Measured on B200 (65 536-node step, 40 projection launches): phase-serial 8.67 ms total, warp-specialised 9.95 ms
+// (bf16 K = 192 with beta: 637 us per launch against ~220 us) - 128 epilogue threads and 64 KB of loads in flight per SM
+// are not enough; three phase-serial CTAs of 256 threads per SM overlap better.  Kept as a verified-correct experiment.
 extern "C" int u2gnn_gemm_tc_debug(int ws) {
     g_rows_ws = ws;
     return U2GNN_OK;

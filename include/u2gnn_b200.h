@@ -221,7 +221,7 @@ int u2gnn_tc_selftest(int mode, const float* A, const float* B, float* C, int K,
         to bf16 before its tensor-core product, so the producers store them as bf16 row-major (rounded once, bit-identical
         results) and the block moves half the HBM bytes.  *_bf16 flags: 0 = fp32 buffer, 1 = bf16 buffer; leading
         dimensions are in ELEMENTS; beta must be 0 for a bf16 C. ---- */
-/* experiment switch for the projection GEMM: 1 (default) = warp-specialised persistent kernel for aligned shapes, 0 = phase-serial kernel */
+/* experiment switch for the projection GEMM: 0 (default) = phase-serial kernel, 1 = warp-specialised persistent kernel for aligned shapes (slower as measured) */
 int u2gnn_gemm_tc_debug(int ws);
 int u2gnn_gemm_tc_rows_ex(const void* A, int a_bf16, int64_t M, int K, int64_t lda, const float* W, int w_kn, int N,
                           const float* bias, float beta, void* C, int c_bf16, int64_t ldc, u2gnn_stream_t stream);

@@ -361,7 +361,7 @@ def test_gemm_tc_rows_warp_specialised_equals_phase_serial(U, M, K, N, a_bf16, c
                    C.data_ptr(), c_bf16, N, E._stream())
         torch.cuda.synchronize()
         outs.append(C)
-    U.LIB.call("u2gnn_gemm_tc_debug", 1)
+    U.LIB.call("u2gnn_gemm_tc_debug", 0)
     assert torch.equal(outs[0], outs[1])
     ref = A.float().to(torch.bfloat16).float() @ W.to(torch.bfloat16).float() + b + (C0 if beta else 0)
     assert (outs[1].float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
