@@ -9,7 +9,16 @@
 // accumulated in tensor memory over all tiles of the CTA and flushed once with atomics.
 // X / dF row tiles are converted to bf16 swizzled tiles by two loader warps through a 3-stage ring; the same
 // tile is the K-major A operand of the S / D GEMMs and the MN-major B operand of the gradient GEMMs.
-// TMEM columns: R0 [0,128) R1 [128,256) dW2c^T [256,320) dW1c [320,384) db1c [384,400).
+// TMEM columns: R0 [0,128) R1 [128,256) dW2c^T [256,320) dW1c [320,384) db1c [384,400) dY partial [400,464).
+//
+// MERGED variant (u2gnn_ffn_tc_bwd_mode(1); measured slower than dgrad + wgrad, see ffn_tc_bwd.cu): the kernel ALSO computes
+// the input gradient.  After the weight-gradient GEMMs of
+// a tile it issues  dYp = dPre W1Tc^T  (SS: the dPre tile already in shared memory is the K-major A operand, N 64) and the
+// epilogue warps add the partial of their chunk into dy1 (pre-set to dz) with red.global.add.v4.f32 - a quad of lanes
+// transposes its 4 x 4 block of 16-byte pieces with shuffles first so that one instruction covers 64 contiguous bytes of
+// a row (full 32-byte sectors; tools/probe_red.py: coalesced L2 reductions sustain 4.8 TB/s, half-sector ones 2.7).
+// This replaces the separate dgrad kernel: the hidden is recomputed once instead of twice (7 executed GEMM units per
+// tile-chunk instead of 9).
 #include "common.cuh"
 #include "rng.cuh"
 #include "tc_common.cuh"
@@ -21,7 +30,7 @@ constexpr int DP = 64, CH = 128, TM = 128;
 constexpr uint32_t CHUNK_BYTES = 4 * 16384;   // [W2c | W1c | W2Tc | W1Tc]
 constexpr int kThreads = 640;
 constexpr int WG_STAGES = 3;
-constexpr uint32_t COL_R = 0, COL_DW2 = 256, COL_DW1 = 320;
+constexpr uint32_t COL_R = 0, COL_DW2 = 256, COL_DW1 = 320, COL_DY = 400;
 
 struct Params {
     const uint8_t* xb;   // bf16 swizzled tile images written by the dgrad kernel
@@ -35,12 +44,13 @@ struct Params {
     float* dW1;   // [ff, d]
     float* db1;   // [ff]
     float* dW2;   // [d, ff]
+    float* dy1;   // MERGED: [M, d] input gradient, pre-set to dz; the chunk partials are added into it
     uint32_t* trace;   // debug clock stamps of CTA 0 (u2gnn_ffn_tc_set_trace)
 };
 constexpr int TRACE_CAP = 1024;
 
 struct __align__(8) Bars {
-    uint64_t w_full, ld_full[WG_STAGES], ld_free[WG_STAGES], s_full[2], a_done[2], d_full[2], b_done[2], hp_full, hp_free, flush_full;
+    uint64_t w_full, ld_full[WG_STAGES], ld_free[WG_STAGES], s_full[2], a_done[2], d_full[2], b_done[2], hp_full, hp_free, flush_full, dy_full, dy_free;
 };
 
 __device__ __forceinline__ void commit_to(uint64_t* bar) {
@@ -67,7 +77,7 @@ __device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint64_t a_desc, ui
     __syncwarp();
 }
 
-template <bool TRACE>
+template <bool TRACE, bool MERGED>
 __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint32_t tr_n = 0;
@@ -81,8 +91,9 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params 
     uint8_t* sOnes = smem + WG_STAGES * 32768;             // 16 KB tile of bf16 1.0 (after the ring: LBO to it is positive)
     uint8_t* sH = sOnes + 16384;                           // 32 KB: two [128 rows x 64 hidden] tiles
     uint8_t* sP = sH + 32768;                              // 32 KB
-    uint8_t* sW = sP + 32768;                              // 32 KB: [W1c | W2Tc]
-    uint32_t* sB1h = reinterpret_cast<uint32_t*>(sW + 32768);   // chunk bias as 64 packed bf16 pairs
+    uint8_t* sW = sP + 32768;                              // 32 KB: [W1c | W2Tc]  (MERGED: 48 KB, + W1Tc)
+    constexpr uint32_t W_BYTES = MERGED ? 49152 : 32768;
+    uint32_t* sB1h = reinterpret_cast<uint32_t*>(sW + W_BYTES);   // chunk bias as 64 packed bf16 pairs
     __shared__ Bars bars;
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -107,6 +118,8 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params 
         tc::mbar_init(&bars.hp_full, 16);
         tc::mbar_init(&bars.hp_free, 1);
         tc::mbar_init(&bars.flush_full, 1);
+        tc::mbar_init(&bars.dy_full, 1);
+        tc::mbar_init(&bars.dy_free, 16);
         tc::fence_barrier_init();
     }
     if (warp == 2) tc::tmem_alloc<512>(&tmem_slot);
@@ -124,8 +137,8 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params 
     if (my_tiles > 0) {
         if (warp == 0) {
             if (lane == 0) {
-                tc::mbar_arrive_expect_tx(&bars.w_full, 32768);
-                tc::bulk_g2s(sW, p.packed + (size_t)c * CHUNK_BYTES + 16384, 32768, &bars.w_full);
+                tc::mbar_arrive_expect_tx(&bars.w_full, W_BYTES);
+                tc::bulk_g2s(sW, p.packed + (size_t)c * CHUNK_BYTES + 16384, W_BYTES, &bars.w_full);
             }
         } else if (warp == 2) {
             // ================= row-tile producer: two 16 KB bulk copies per tile (images written by dgrad) ==========
@@ -144,6 +157,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params 
             const uint32_t idesc_n128 = tc::make_idesc(TM, CH, 0, 0);
             const uint32_t idesc_w2 = tc::make_idesc(CH, DP, 1, 1);        // M = hidden, N = d, both MN-major
             const uint32_t idesc_w1 = tc::make_idesc(CH, DP + 16, 1, 1);   // N = 80: [X | ones]
+            const uint32_t idesc_dy = tc::make_idesc(TM, DP, 0, 0);        // dYp: K-major A (dPre) and B (W1Tc)
             const uint64_t xf0 = tc::make_desc_sw128(tc::smem_u32(sXF), 16, 1024);         // K-major view of stage 0 X tile
             const uint64_t w1d = tc::make_desc_sw128(tc::smem_u32(sW), 16, 1024);
             const uint64_t w2td = w1d + 1024;
@@ -171,6 +185,25 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params 
                 const uint64_t xd_mn = tc::make_desc_sw128(x_addr, tc::smem_u32(sOnes) - x_addr, 1024);
                 issue_wgrad(tmem + COL_DW2, hd, fd_mn, idesc_w2, n > 0);
                 issue_wgrad(tmem + COL_DW1, pd, xd_mn, idesc_w1, n > 0);
+                if (MERGED) {
+                    // dYp(n) = dPre(n) W1Tc^T: A = the dPre tile as K-major operand (two 64-hidden tiles), B = W1Tc image (two K atoms)
+                    if (n > 0) tc::mbar_wait(&bars.dy_free, (uint32_t)(n - 1) & 1);
+                    tc::tc_fence_after();
+                    if (tc::elect_one()) {
+                        const uint64_t pk = tc::make_desc_sw128(tc::smem_u32(sP), 16, 1024);
+                        const uint64_t wt = tc::make_desc_sw128(tc::smem_u32(sW) + 32768, 16, 1024);
+                        tc::mma_ss(tmem + COL_DY, pk, wt, idesc_dy, 0);
+                        tc::mma_ss_acc(tmem + COL_DY, pk + 2, wt + 2, idesc_dy);
+                        tc::mma_ss_acc(tmem + COL_DY, pk + 4, wt + 4, idesc_dy);
+                        tc::mma_ss_acc(tmem + COL_DY, pk + 6, wt + 6, idesc_dy);
+                        tc::mma_ss_acc(tmem + COL_DY, pk + 1024, wt + 512, idesc_dy);
+                        tc::mma_ss_acc(tmem + COL_DY, pk + 1026, wt + 514, idesc_dy);
+                        tc::mma_ss_acc(tmem + COL_DY, pk + 1028, wt + 516, idesc_dy);
+                        tc::mma_ss_acc(tmem + COL_DY, pk + 1030, wt + 518, idesc_dy);
+                    }
+                    __syncwarp();
+                    commit_to(&bars.dy_full);
+                }
                 commit_to(&bars.hp_free);
                 commit_to(&bars.ld_free[s]);
                 stamp(0);
@@ -272,13 +305,72 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params 
                 if (lane == 0) tc::mbar_arrive(&bars.hp_full);
                 stamp(warp - 3);
             };
+            // MERGED: this warp's 32 rows x 16 columns of dYp(n) -> dy1.  Thread = row holds 16 consecutive floats (4 pieces of
+            // 16 bytes); the four lanes of a quad exchange pieces (4 x 4 transpose) so that lane i of the quad owns piece i of
+            // the quad's four rows: one red.global.add.v4.f32 then covers 64 contiguous bytes of one row per quad.
+            auto drain = [&](int64_t n) {
+                tc::mbar_wait(&bars.dy_full, (uint32_t)n & 1);
+                tc::tc_fence_after();
+                uint32_t y[16];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                             : "=r"(y[0]), "=r"(y[1]), "=r"(y[2]), "=r"(y[3]), "=r"(y[4]), "=r"(y[5]), "=r"(y[6]), "=r"(y[7]),
+                               "=r"(y[8]), "=r"(y[9]), "=r"(y[10]), "=r"(y[11]), "=r"(y[12]), "=r"(y[13]), "=r"(y[14]), "=r"(y[15])
+                             : "r"(tmem + lane_base + COL_DY + 16 * cq)
+                             : "memory");
+                tc::tmem_ld_wait();
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bars.dy_free);
+                // 4 x 4 transpose of 16-byte pieces inside each quad: after it, lane q of the quad holds piece q of rows 0..3
+                const int ql = lane & 3;
+#pragma unroll
+                for (int step = 1; step <= 2; step <<= 1) {
+                    // exchange with lane ^ step: the pieces whose index bit `step` differs from this lane's bit
+#pragma unroll
+                    for (int pc = 0; pc < 4; ++pc) {
+                        if ((pc & step) == 0) {
+                            const int hi = pc | step;                 // pieces (pc, hi) form a pair for this step
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const bool up = (ql & step) != 0;     // lanes with the bit set keep `hi`, send `pc`
+                                const uint32_t send = up ? y[4 * pc + k] : y[4 * hi + k];
+                                const uint32_t got = __shfl_xor_sync(0xffffffffu, send, step);
+                                if (up) y[4 * pc + k] = got; else y[4 * hi + k] = got;
+                            }
+                        }
+                    }
+                }
+                // now y[4 * j .. 4 * j + 3] = piece `ql` of the quad's row j
+                const int64_t row_q = ((int64_t)slice + n * n_slices) * TM + (tr & ~3);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int64_t rg = row_q + j;
+                    if (rg < p.M) {
+                        if (p.d == DP) {
+                            float* dst = p.dy1 + rg * DP + 16 * cq + 4 * ql;
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(y[4 * j])),
+                                         "f"(__uint_as_float(y[4 * j + 1])), "f"(__uint_as_float(y[4 * j + 2])), "f"(__uint_as_float(y[4 * j + 3]))
+                                         : "memory");
+                        } else {                                   // unpadded rows of d < 64 floats
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int col = 16 * cq + 4 * ql + k;
+                                if (col < p.d) atomicAdd(p.dy1 + rg * p.d + col, __uint_as_float(y[4 * j + k]));
+                            }
+                        }
+                    }
+                }
+            };
             for (int64_t n = 0; n < my_tiles; ++n) {
                 phase_a(n);
+                if (MERGED && n >= 2) drain(n - 2);
                 if (n > 0) phase_b(n - 1);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) hprev[j] = hcur[j];
             }
+            if (MERGED && my_tiles >= 2) drain(my_tiles - 2);
             phase_b(my_tiles - 1);
+            if (MERGED) drain(my_tiles - 1);
             const int i = ew >> 3, wg = (ew >> 2) & 1;      // flush: first warpgroup
             // ---- flush the chunk's weight gradients (first warpgroup; thread <-> hidden unit)
             if (i == 0 && wg == 0) {
@@ -321,7 +413,8 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params 
 
 // internal launch used by u2gnn_ffn_tc_bwd (ffn_tc_bwd.cu)
 int ffn_tc_wgrad_launch(const void* xb, const void* fb, int64_t M, int d, int ff, const void* packed, float hidden_scale,
-                        uint64_t seed, uint32_t stream_hidden, int thr, float* dW1, float* db1, float* dW2, cudaStream_t st) {
+                        uint64_t seed, uint32_t stream_hidden, int thr, float* dW1, float* db1, float* dW2, float* dy1_merged,
+                        cudaStream_t st) {
     Params p;
     p.xb = static_cast<const uint8_t*>(xb); p.fb = static_cast<const uint8_t*>(fb); p.M = M; p.d = d; p.ff = ff;
     p.packed = static_cast<const uint8_t*>(packed);
@@ -329,18 +422,18 @@ int ffn_tc_wgrad_launch(const void* xb, const void* fb, int64_t M, int d, int ff
     p.thr = thr;
     p.low = rng_thr_low(thr);
     p.hidden_scale = hidden_scale;
-    p.dW1 = dW1; p.db1 = db1; p.dW2 = dW2;
-    const size_t smem = 1024 + (size_t)WG_STAGES * 32768 + 16384 + 3 * 32768 + 512;
+    p.dW1 = dW1; p.db1 = db1; p.dW2 = dW2; p.dy1 = dy1_merged;
+    const size_t smem = 1024 + (size_t)WG_STAGES * 32768 + 16384 + 3 * 32768 + (dy1_merged ? 16384 : 0) + 512;
     extern uint32_t* g_ffn_trace;
     p.trace = g_ffn_trace;
-    cudaFuncSetAttribute(ffn_tc_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(ffn_tc_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = dy1_merged ? (p.trace ? ffn_tc_wgrad_kernel<true, true> : ffn_tc_wgrad_kernel<false, true>)
+                           : (p.trace ? ffn_tc_wgrad_kernel<true, false> : ffn_tc_wgrad_kernel<false, false>);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int NC = ff / CH;
     const int64_t n_tiles = (M + TM - 1) / TM;
     int n_slices = U2GNN_NUM_SMS / NC;
     if (n_slices < 1) n_slices = 1;
     if (n_slices > n_tiles) n_slices = (int)n_tiles;
-    if (p.trace) ffn_tc_wgrad_kernel<true><<<NC * n_slices, kThreads, smem, st>>>(p);
-    else ffn_tc_wgrad_kernel<false><<<NC * n_slices, kThreads, smem, st>>>(p);
+    kern<<<NC * n_slices, kThreads, smem, st>>>(p);
     return U2GNN_OK;
 }

@@ -67,26 +67,6 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
         if (++spins > (1u << 28)) __trap();
     }
 }
-// non-blocking test first (a phase that is already complete costs one round trip), then the blocking form
-__device__ __forceinline__ void mbar_wait_test_first(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (!ok) mbar_wait_addr(bar, parity);
-}
-// waiters that are off the critical path back off between polls so they do not take issue slots from the epilogue warps
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        __nanosleep(64);
-        if (++spins > (1u << 26)) __trap();
-    }
-}
 __device__ __forceinline__ void lds128(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
 }

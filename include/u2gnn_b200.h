@@ -189,6 +189,9 @@ int u2gnn_ffn_tc_fwd(const float* y1, int64_t M, int d, int ff, const void* pack
  * the linear2 output after the output dropout; dy1 may alias dz); dW1[ff,d], db1[ff], dW2[d,ff] are
  * ACCUMULATED (atomics).  db2 = colsum(df) is left to u2gnn_colsum.  workspace (128-byte aligned) holds bf16 tile
  * images of y1 / df handed from the input-gradient kernel to the weight-gradient kernel. */
+/* backward implementation: 0 (default) = dgrad + wgrad kernels, 1 = merged kernel (weight gradients + split-K input gradient
+   through L2 reductions; parity-tested, measured slower) */
+int u2gnn_ffn_tc_bwd_mode(int mode);
 size_t u2gnn_ffn_tc_bwd_workspace_bytes(int64_t M);
 int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const float* dz, int64_t M, int d, int ff, const void* packed,
                      float hidden_scale, uint64_t seed, uint32_t stream_hidden, int thr, float* dy1, float* dW1,

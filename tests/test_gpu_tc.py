@@ -108,7 +108,8 @@ def test_ffn_tc_forward(U, M, d, ff, p):
 # ------------------------------------------------------------------ fused FFN backward
 @pytest.mark.parametrize("M,d,ff,p", [(256, 64, 128, 0.0), (1000, 64, 2048, 0.5), (37, 64, 256, 0.0), (300, 7, 256, 0.5),
                                       (5000, 64, 1024, 0.25), (148 * 256 * 2 + 77, 64, 256, 0.5)])
-def test_ffn_tc_backward(U, M, d, ff, p):
+@pytest.mark.parametrize("mode", [0, 1])      # 0: dgrad + wgrad kernels (default), 1: merged kernel
+def test_ffn_tc_backward(U, M, d, ff, p, mode):
     from u2gnn_b200 import engine as E
     from oracle import u2gnn_oracle as O
     rng = np.random.default_rng(5 + M + d + ff)
@@ -131,9 +132,11 @@ def test_ffn_tc_backward(U, M, d, ff, p):
     dW1 = torch.zeros((ff, d), device="cuda"); db1 = torch.zeros(ff, device="cuda"); dW2 = torch.zeros((d, ff), device="cuda")
     SEED, S2 = 0x1234ABCD99, 18
     ws = torch.empty(U.LIB.call("u2gnn_ffn_tc_bwd_workspace_bytes", M), dtype=torch.uint8, device="cuda")
+    U.LIB.call("u2gnn_ffn_tc_bwd_mode", mode)
     U.LIB.call("u2gnn_ffn_tc_bwd", t["y1"].data_ptr(), t["df"].data_ptr(), t["dz"].data_ptr(), M, d, ff, packed.data_ptr(), scale,
                SEED, S2, thr, dy1.data_ptr(), dW1.data_ptr(), db1.data_ptr(), dW2.data_ptr(), ws.data_ptr(), ws.numel(), E._stream())
     torch.cuda.synchronize()
+    U.LIB.call("u2gnn_ffn_tc_bwd_mode", 0)
     if thr:
         k2, _ = O.dropout_keep_mask(SEED, S2, M * ff, p)
         m2 = k2.reshape(M, ff).astype(np.float64) * scale
