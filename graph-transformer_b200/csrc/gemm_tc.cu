@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "ffn_epi.cuh"
+#include "rng.cuh"
 
 namespace {
 
@@ -119,8 +120,29 @@ struct RowsParams {
     void* C;
     int64_t ldc;
     float beta;           // C = result + beta * C  (0 or 1; fp32 C only)
+    // fused residual + dropout + LayerNorm epilogue (LN kernel variant only; N == 64):
+    //   z = res + dropout(A W^T + bias);  y = LayerNorm(z) * gamma + ln_beta;  stats = (mean, rstd)
+    const float* res;
+    int64_t ldres;
+    RngKeys keys;
+    int thr, low;
+    float scale;
+    const float* gamma;
+    const float* ln_beta;
+    float* z;
+    float* y;
+    float* stats;
 };
 
+constexpr float kLnEps = 1e-5f;
+
+__device__ __forceinline__ float group16_sum(float v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <bool LN>
 __global__ void __launch_bounds__(kThreads, 3) gemm_tc_rows_kernel(const RowsParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -178,6 +200,17 @@ __global__ void __launch_bounds__(kThreads, 3) gemm_tc_rows_kernel(const RowsPar
             }
             __syncwarp();
         }
+        float4 resq[LN ? 8 : 1];
+        if constexpr (LN) {
+            // residual rows in the layout of the coalesced store phase (16 lanes x float4 per row), in flight during the MMA
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = u * kThreads + tid;
+                const int64_t row = row0 + (e >> 4);
+                resq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < p.M) resq[u] = __ldg(reinterpret_cast<const float4*>(p.res + row * p.ldres) + (e & 15));
+            }
+        }
         tc::mbar_wait(&bar, phase);
         phase ^= 1;
         tc::tc_fence_after();
@@ -197,6 +230,45 @@ __global__ void __launch_bounds__(kThreads, 3) gemm_tc_rows_kernel(const RowsPar
                     srow[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
             }
             __syncthreads();
+            if constexpr (LN) {
+                // N == 64: 16 consecutive lanes hold one row as float4 pieces - the layout of ln_fwd_vec_kernel<16>, same
+                // arithmetic in the same order (layernorm.cu), so z / y / stats are what GEMM + LayerNorm kernels produce
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma) + (tid & 15));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ln_beta) + (tid & 15));
+                const float4 bias4 = __ldg(reinterpret_cast<const float4*>(p.bias) + (tid & 15));
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = u * kThreads + tid;
+                    const int rr = e >> 4, l = e & 15;
+                    const int64_t row = row0 + rr;
+                    const bool ok = row < p.M;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok) {
+                        v = *reinterpret_cast<const float4*>(sOut + rr * 272 + 16 * l);
+                        v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+                        if (p.thr) {
+                            const uint64_t el = (uint64_t)(row * 64 + 4 * l);
+                            const uint32_t w = rng_keep_word_lo(p.keys, el >> 5, p.thr, p.low) >> (el & 31);
+                            v.x = (w & 1u) ? v.x * p.scale : 0.0f;
+                            v.y = (w & 2u) ? v.y * p.scale : 0.0f;
+                            v.z = (w & 4u) ? v.z * p.scale : 0.0f;
+                            v.w = (w & 8u) ? v.w * p.scale : 0.0f;
+                        }
+                        v.x += resq[u].x; v.y += resq[u].y; v.z += resq[u].z; v.w += resq[u].w;
+                        reinterpret_cast<float4*>(p.z + row * 64)[l] = v;
+                    }
+                    const float mean = group16_sum((v.x + v.y) + (v.z + v.w)) * (1.0f / 64.0f);
+                    const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+                    const float rstd = rsqrtf(group16_sum((dx * dx + dy * dy) + (dz * dz + dw * dw)) * (1.0f / 64.0f) + kLnEps);
+                    if (ok) {
+                        reinterpret_cast<float4*>(p.y + row * 64)[l] = make_float4(dx * rstd * g4.x + b4.x, dy * rstd * g4.y + b4.y,
+                                                                                   dz * rstd * g4.z + b4.z, dw * rstd * g4.w + b4.w);
+                        if (l == 0) *reinterpret_cast<float2*>(p.stats + 2 * row) = make_float2(mean, rstd);
+                    }
+                }
+                __syncthreads();
+                continue;
+            }
             if (p.c_bf16 && vec_ok && (p.ldc & 7) == 0 && (p.N & 7) == 0) {
                 // bf16 result (rounded once here: what every consumer would do on load), 8 columns = 16 bytes per thread
 #pragma unroll
@@ -676,7 +748,7 @@ extern "C" int u2gnn_gemm_tc_rows_ex(const void* A, int a_bf16, int64_t M, int K
     }
     const size_t smem = 1024 + (size_t)kt * 16384 + (size_t)kt * p.NP * 128 + 128 * 272;
     if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
-    cudaFuncSetAttribute(gemm_tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gemm_tc_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = (int)((220 * 1024) / (smem + 1024));
     const int tmem_cols = (p.NP <= 64) ? 64 : (p.NP <= 128 ? 128 : 256);
     if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;   // tensor-memory columns per CTA
@@ -684,7 +756,41 @@ extern "C" int u2gnn_gemm_tc_rows_ex(const void* A, int a_bf16, int64_t M, int K
     if (per_sm < 1) per_sm = 1;
     const int64_t n_tiles = (M + TM - 1) / TM;
     const int64_t cap = (int64_t)U2GNN_NUM_SMS * per_sm;
-    gemm_tc_rows_kernel<<<(int)(n_tiles < cap ? n_tiles : cap), kThreads, smem, as_stream(stream)>>>(p);
+    gemm_tc_rows_kernel<false><<<(int)(n_tiles < cap ? n_tiles : cap), kThreads, smem, as_stream(stream)>>>(p);
+    U2GNN_CHECK_LAUNCH();
+}
+
+extern "C" int u2gnn_gemm_tc_rows_ln(const void* A, int a_bf16, int64_t M, int K, int64_t lda, const float* W, int w_kn,
+                                     const float* bias, const float* res, int64_t ldres, uint64_t seed, uint32_t rng_stream,
+                                     int thr, const float* gamma, const float* beta, float* z, float* y, float* stats,
+                                     u2gnn_stream_t stream) {
+    constexpr int N = 64;
+    if (!A || !W || !bias || !res || !gamma || !beta || !z || !y || !stats || M < 0 || K < 1 || lda < K || ldres < N ||
+        thr < 0 || thr > 255)
+        return U2GNN_EINVAL;
+    if (K > 256) return U2GNN_EUNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(z) |
+         reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
+         reinterpret_cast<uintptr_t>(bias)) % 16 || reinterpret_cast<uintptr_t>(stats) % 8 || (ldres & 3))
+        return U2GNN_EALIGN;
+    if (M == 0) return U2GNN_OK;
+    RowsParams p;
+    p.A = A; p.a_bf16 = a_bf16; p.c_bf16 = 0; p.M = M; p.lda = lda; p.K = K; p.KP = (K + 63) / 64 * 64;
+    p.W = W; p.w_kn = w_kn; p.N = N; p.NP = N;
+    p.bias = bias; p.C = nullptr; p.ldc = N; p.beta = 0.0f;
+    p.res = res; p.ldres = ldres; p.keys = rng_keys(seed, rng_stream); p.thr = thr; p.low = rng_thr_low(thr);
+    p.scale = thr ? rng_keep_scale(thr) : 1.0f;
+    p.gamma = gamma; p.ln_beta = beta; p.z = z; p.y = y; p.stats = stats;
+    const int kt = p.KP / 64;
+    const size_t smem = 1024 + (size_t)kt * 16384 + (size_t)kt * p.NP * 128 + 128 * 272;
+    if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
+    cudaFuncSetAttribute(gemm_tc_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (per_sm > 3) per_sm = 3;                              // __launch_bounds__(256, 3)
+    if (per_sm < 1) per_sm = 1;
+    const int64_t n_tiles = (M + TM - 1) / TM;
+    const int64_t cap = (int64_t)U2GNN_NUM_SMS * per_sm;
+    gemm_tc_rows_kernel<true><<<(int)(n_tiles < cap ? n_tiles : cap), kThreads, smem, as_stream(stream)>>>(p);
     U2GNN_CHECK_LAUNCH();
 }
 

@@ -152,6 +152,11 @@ __global__ void __launch_bounds__(256) copy_rows_kernel(const float* __restrict_
 
 // ---- vectorised variants (d = 4 * LPR, LPR lanes per row, 32 / LPR rows per warp): 128-bit accesses, one dropout
 //      keep word per float4 (its 4 elements share a 32-element group because d % 4 == 0)
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
 template <int LPR>
 __device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
@@ -209,9 +214,12 @@ template <int LPR>
 __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                                                          const float* __restrict__ stats, int64_t M,
                                                          const float* __restrict__ gamma, DropRng rng, int low,
-                                                         float* __restrict__ dz, float* __restrict__ da,
-                                                         float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                         float* __restrict__ dz, void* __restrict__ da_, int da_bf16,
+                                                         float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                         float* __restrict__ dasum) {
     constexpr int D = 4 * LPR, RPW = 32 / LPR;
+    float* da = static_cast<float*>(da_);
+    float4 as = make_float4(0.f, 0.f, 0.f, 0.f);
     const int lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -239,7 +247,19 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict
             const float4 o = make_float4(rstd * (dh.x - m1 - xh.x * m2), rstd * (dh.y - m1 - xh.y * m2),
                                          rstd * (dh.z - m1 - xh.z * m2), rstd * (dh.w - m1 - xh.w * m2));
             reinterpret_cast<float4*>(dz + r * D)[l] = o;
-            if (da) reinterpret_cast<float4*>(da + r * D)[l] = drop4(rng, low, (uint64_t)(r * D + 4 * l), o);
+            if (da || dasum) {
+                const float4 m = drop4(rng, low, (uint64_t)(r * D + 4 * l), o);
+                if (!da) {
+                } else if (da_bf16) {      // consumers are tensor-core kernels that round on load: round once here, half the bytes
+                    uint2 w;
+                    w.x = cvt_bf16x2(m.x, m.y);
+                    w.y = cvt_bf16x2(m.z, m.w);
+                    reinterpret_cast<uint2*>(static_cast<uint16_t*>(da_) + r * D)[l] = w;
+                } else {
+                    reinterpret_cast<float4*>(da + r * D)[l] = m;
+                }
+                as.x += m.x; as.y += m.y; as.z += m.z; as.w += m.w;
+            }
         }
     }
     // reduce the row groups of the warp, then one atomic per column per warp
@@ -249,8 +269,13 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict
         ag.z += __shfl_xor_sync(0xffffffffu, ag.z, o); ag.w += __shfl_xor_sync(0xffffffffu, ag.w, o);
         ab.x += __shfl_xor_sync(0xffffffffu, ab.x, o); ab.y += __shfl_xor_sync(0xffffffffu, ab.y, o);
         ab.z += __shfl_xor_sync(0xffffffffu, ab.z, o); ab.w += __shfl_xor_sync(0xffffffffu, ab.w, o);
+        if (dasum) {
+            as.x += __shfl_xor_sync(0xffffffffu, as.x, o); as.y += __shfl_xor_sync(0xffffffffu, as.y, o);
+            as.z += __shfl_xor_sync(0xffffffffu, as.z, o); as.w += __shfl_xor_sync(0xffffffffu, as.w, o);
+        }
     }
     if (sub == 0) {
+        if (dasum) { atomicAdd(dasum + 4 * l, as.x); atomicAdd(dasum + 4 * l + 1, as.y); atomicAdd(dasum + 4 * l + 2, as.z); atomicAdd(dasum + 4 * l + 3, as.w); }
         if (dgamma) { atomicAdd(dgamma + 4 * l, ag.x); atomicAdd(dgamma + 4 * l + 1, ag.y); atomicAdd(dgamma + 4 * l + 2, ag.z); atomicAdd(dgamma + 4 * l + 3, ag.w); }
         if (dbeta) { atomicAdd(dbeta + 4 * l, ab.x); atomicAdd(dbeta + 4 * l + 1, ab.y); atomicAdd(dbeta + 4 * l + 2, ab.z); atomicAdd(dbeta + 4 * l + 3, ab.w); }
     }
@@ -296,10 +321,12 @@ extern "C" int u2gnn_add_dropout_ln_fwd(const float* res, const float* a, int64_
     U2GNN_CHECK_LAUNCH();
 }
 
-extern "C" int u2gnn_add_dropout_ln_bwd(const float* dy, const float* z, const float* stats, int64_t M, int d,
-                                        const float* gamma, uint64_t seed, uint32_t rng_stream, int thr, float* dz,
-                                        float* da, float* dgamma, float* dbeta, u2gnn_stream_t stream) {
+extern "C" int u2gnn_add_dropout_ln_bwd_ex(const float* dy, const float* z, const float* stats, int64_t M, int d,
+                                           const float* gamma, uint64_t seed, uint32_t rng_stream, int thr, float* dz,
+                                           void* da, int da_bf16, float* dgamma, float* dbeta, float* dasum,
+                                           u2gnn_stream_t stream) {
     if (!dy || !z || !stats || !gamma || !dz || M < 0 || d <= 0 || thr < 0 || thr > 255) return U2GNN_EINVAL;
+    if (da_bf16 && !da) return U2GNN_EINVAL;
     if (d > 32 * kMaxSlots) return U2GNN_EUNSUPPORTED;
     if (M == 0) return U2GNN_OK;
     if (vec_ok(d, dy, z, dz, da, gamma)) {
@@ -307,17 +334,24 @@ extern "C" int u2gnn_add_dropout_ln_bwd(const float* dy, const float* z, const f
         const int low = rng_thr_low(thr);
         const int grid = grid_for(M, 64 * (128 / d), 4);
         cudaStream_t st = as_stream(stream);
-        if (d == 16) ln_bwd_vec_kernel<4><<<grid, 256, 0, st>>>(dy, z, stats, M, gamma, rng, low, dz, da, dgamma, dbeta);
-        else if (d == 32) ln_bwd_vec_kernel<8><<<grid, 256, 0, st>>>(dy, z, stats, M, gamma, rng, low, dz, da, dgamma, dbeta);
-        else if (d == 64) ln_bwd_vec_kernel<16><<<grid, 256, 0, st>>>(dy, z, stats, M, gamma, rng, low, dz, da, dgamma, dbeta);
-        else ln_bwd_vec_kernel<32><<<grid, 256, 0, st>>>(dy, z, stats, M, gamma, rng, low, dz, da, dgamma, dbeta);
+        if (d == 16) ln_bwd_vec_kernel<4><<<grid, 256, 0, st>>>(dy, z, stats, M, gamma, rng, low, dz, da, da_bf16, dgamma, dbeta, dasum);
+        else if (d == 32) ln_bwd_vec_kernel<8><<<grid, 256, 0, st>>>(dy, z, stats, M, gamma, rng, low, dz, da, da_bf16, dgamma, dbeta, dasum);
+        else if (d == 64) ln_bwd_vec_kernel<16><<<grid, 256, 0, st>>>(dy, z, stats, M, gamma, rng, low, dz, da, da_bf16, dgamma, dbeta, dasum);
+        else ln_bwd_vec_kernel<32><<<grid, 256, 0, st>>>(dy, z, stats, M, gamma, rng, low, dz, da, da_bf16, dgamma, dbeta, dasum);
         U2GNN_CHECK_LAUNCH();
     }
+    if (da_bf16 || dasum) return U2GNN_EUNSUPPORTED;            // bf16 da / fused column sum: vectorised shapes only
     // fewer, fatter warps than the forward: each warp flushes d atomics at the end
     add_dropout_ln_bwd_kernel<<<grid_for(M, 64, 2), 256, 0, as_stream(stream)>>>(dy, z, stats, M, d, gamma,
-                                                                                make_rng(seed, rng_stream, thr), dz, da,
-                                                                                dgamma, dbeta);
+                                                                                make_rng(seed, rng_stream, thr), dz,
+                                                                                static_cast<float*>(da), dgamma, dbeta);
     U2GNN_CHECK_LAUNCH();
+}
+
+extern "C" int u2gnn_add_dropout_ln_bwd(const float* dy, const float* z, const float* stats, int64_t M, int d,
+                                        const float* gamma, uint64_t seed, uint32_t rng_stream, int thr, float* dz,
+                                        float* da, float* dgamma, float* dbeta, u2gnn_stream_t stream) {
+    return u2gnn_add_dropout_ln_bwd_ex(dy, z, stats, M, d, gamma, seed, rng_stream, thr, dz, da, 0, dgamma, dbeta, nullptr, stream);
 }
 
 extern "C" int u2gnn_ln_apply(const float* z, const float* stats, int64_t M, int d, const float* gamma,

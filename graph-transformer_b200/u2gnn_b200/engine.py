@@ -12,6 +12,7 @@ Two attention layouts:
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -25,6 +26,8 @@ PARAM_NAMES = (
 )
 STREAM_POOLED = 1
 STREAM_CONCAT = 9
+FUSE_OUT_PROJ_LN = os.environ.get("U2GNN_FUSE_EPILOGUES", "1") != "0"   # bf16 mode, d = 64: out_proj + dropout + residual + LayerNorm1 in one kernel (False: GEMM then LayerNorm kernel)
+FUSE_LN_BWD = os.environ.get("U2GNN_FUSE_EPILOGUES", "1") != "0"        # bf16 mode: bf16 da out of the LayerNorm1 backward, linear2 bias gradient inside the LayerNorm2 backward
 FLOPS = {}    # entry point -> algorithmic flops issued while LIB.timed is active (bench.py roofline)
 
 
@@ -216,12 +219,33 @@ def add_dropout_ln_fwd(res, a, M, d, drop, gamma, beta):
     return z, y, stats
 
 
-def add_dropout_ln_bwd(dy, z, stats, M, d, gamma, drop, dgamma, dbeta, want_da=True):
+def add_dropout_ln_bwd(dy, z, stats, M, d, gamma, drop, dgamma, dbeta, want_da=True, da_bf16=False, dasum=None):
+    """da_bf16: store the dropout-masked gradient as bf16 (only when its consumers are tensor-core kernels).
+    dasum[d] += colsum(masked gradient): the bias gradient of the layer in front of the dropout, folded into this pass."""
     dz = torch.empty((M, d), dtype=torch.float32, device=dy.device)
-    da = torch.empty((M, d), dtype=torch.float32, device=dy.device) if (want_da and drop[2] > 0) else None
-    LIB.call("u2gnn_add_dropout_ln_bwd", _ptr(dy), _ptr(z), _ptr(stats), M, d, _ptr(gamma), drop[0], drop[1], drop[2],
-             _ptr(dz), _ptr(da), _ptr(dgamma), _ptr(dbeta), _stream())
+    has_da = want_da and drop[2] > 0
+    da = torch.empty((M, d), dtype=torch.bfloat16 if da_bf16 else torch.float32, device=dy.device) if has_da else None
+    if (da_bf16 and has_da) or dasum is not None:
+        LIB.call("u2gnn_add_dropout_ln_bwd_ex", _ptr(dy), _ptr(z), _ptr(stats), M, d, _ptr(gamma), drop[0], drop[1], drop[2],
+                 _ptr(dz), _ptr(da), int(da_bf16 and has_da), _ptr(dgamma), _ptr(dbeta), _ptr(dasum), _stream())
+    else:
+        LIB.call("u2gnn_add_dropout_ln_bwd", _ptr(dy), _ptr(z), _ptr(stats), M, d, _ptr(gamma), drop[0], drop[1], drop[2],
+                 _ptr(dz), _ptr(da), _ptr(dgamma), _ptr(dbeta), _stream())
     return dz, (da if da is not None else dz)
+
+
+def out_proj_ln_tc(ctx, Mq, d, p, res, ldres, drop):
+    """out_proj + dropout + residual + LayerNorm1 as ONE kernel (bf16 mode, d = 64): the projection result never reaches HBM."""
+    dev = ctx.device
+    z = torch.empty((Mq, d), dtype=torch.float32, device=dev)
+    y = torch.empty((Mq, d), dtype=torch.float32, device=dev)
+    stats = torch.empty((Mq, 2), dtype=torch.float32, device=dev)
+    if LIB.timed is not None:
+        FLOPS["u2gnn_gemm_tc_rows_ln"] = FLOPS.get("u2gnn_gemm_tc_rows_ln", 0) + 2 * Mq * d * d
+    LIB.call("u2gnn_gemm_tc_rows_ln", _ptr(ctx), int(ctx.dtype == torch.bfloat16), Mq, d, d, _ptr(p["self_attn.out_proj.weight"]), 0,
+             _ptr(p["self_attn.out_proj.bias"]), _ptr(res), ldres, drop[0], drop[1], drop[2], _ptr(p["norm1.weight"]),
+             _ptr(p["norm1.bias"]), _ptr(z), _ptr(y), _ptr(stats), _stream())
+    return z, y, stats
 
 
 def copy_rows(src, ld_src, dst, ld_dst, rows, d, accumulate=False, src_off=0, dst_off=0):
@@ -278,17 +302,22 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
         LIB.call("u2gnn_seqattn_tc_fwd_ex", _ptr(qkv), B, S, d, seed, drop_ids[0], thr, _ptr(ctx), 1, _stream())
     else:
         LIB.call("u2gnn_seqattn_fwd", _ptr(qkv), B, S, Sq, d, seed, drop_ids[0], thr, _ptr(ctx), _stream())
-    if tc_proj:
-        a = linear_tc(ctx, Mq, d, p["self_attn.out_proj.weight"], 0, d, bias=p["self_attn.out_proj.bias"])
+    if tc_proj and d == 64 and FUSE_OUT_PROJ_LN:
+        # residual rows read in place (position 0 of each sequence when only that row is live)
+        xq = None
+        z1, y1, st1 = out_proj_ln_tc(ctx, Mq, d, p, x, d if Sq == S else S * d, (seed, drop_ids[1], thr))
     else:
-        a = torch.empty((Mq, d), **f32)
-        sgemm(0, 1, Mq, d, d, ctx, d, p["self_attn.out_proj.weight"], d, a, d, bias=p["self_attn.out_proj.bias"])
-    if Sq == S:
-        xq = x
-    else:
-        xq = torch.empty((Mq, d), **f32)
-        copy_rows(x, S * d, xq, d, B, d)
-    z1, y1, st1 = add_dropout_ln_fwd(xq, a, Mq, d, (seed, drop_ids[1], thr), p["norm1.weight"], p["norm1.bias"])
+        if tc_proj:
+            a = linear_tc(ctx, Mq, d, p["self_attn.out_proj.weight"], 0, d, bias=p["self_attn.out_proj.bias"])
+        else:
+            a = torch.empty((Mq, d), **f32)
+            sgemm(0, 1, Mq, d, d, ctx, d, p["self_attn.out_proj.weight"], d, a, d, bias=p["self_attn.out_proj.bias"])
+        if Sq == S:
+            xq = x
+        else:
+            xq = torch.empty((Mq, d), **f32)
+            copy_rows(x, S * d, xq, d, B, d)
+        z1, y1, st1 = add_dropout_ln_fwd(xq, a, Mq, d, (seed, drop_ids[1], thr), p["norm1.weight"], p["norm1.bias"])
     if precision == "bf16":
         # fused tcgen05 FFN block: the [Mq, ff] hidden never reaches HBM and is recomputed in the backward
         packed = ffn_tc_pack(p, d, ff, thr)
@@ -338,14 +367,16 @@ def encoder_layer_bwd(dy2, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
     f32 = dict(dtype=torch.float32, device=dev)
     drop_scale = 256.0 / (256.0 - thr) if thr else 1.0
     # LayerNorm2 + FFN
+    fold = sv.packed is not None and d in (16, 32, 64, 128) and FUSE_LN_BWD     # linear2 bias gradient inside the LayerNorm2 backward
     dz2, df = add_dropout_ln_bwd(dy2, sv.z2, sv.st2, Mq, d, p["norm2.weight"], (seed, drop_ids[3], thr),
-                                 g["norm2.weight"], g["norm2.bias"])
+                                 g["norm2.weight"], g["norm2.bias"], dasum=g["linear2.bias"] if fold else None)
     dy1 = dz2  # dy1 = dz2 + dhpre @ W1 (in place)
     if sv.packed is not None:
         # fused tcgen05 backward: hidden and its gradient recomputed on chip
         if df is dz2:                    # no output dropout: df aliases dz2, which the weight-gradient kernel still reads
             dy1 = torch.empty_like(dz2)
-        LIB.call("u2gnn_colsum", _ptr(df), Mq, d, d, _ptr(g["linear2.bias"]), 1, _stream())
+        if not fold:
+            LIB.call("u2gnn_colsum", _ptr(df), Mq, d, d, _ptr(g["linear2.bias"]), 1, _stream())
         if LIB.timed is not None:
             FLOPS["u2gnn_ffn_tc_bwd"] = FLOPS.get("u2gnn_ffn_tc_bwd", 0) + 8 * Mq * d * ff
         wsb = LIB.call("u2gnn_ffn_tc_bwd_workspace_bytes", Mq)
@@ -361,10 +392,11 @@ def encoder_layer_bwd(dy2, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
         sgemm(0, 0, Mq, d, ff, dhpre, ff, p["linear1.weight"], d, dy1, d, beta=1.0)
         del dhpre
     # LayerNorm1 + attention
-    dz1, da = add_dropout_ln_bwd(dy1, sv.z1, sv.st1, Mq, d, p["norm1.weight"], (seed, drop_ids[1], thr),
-                                 g["norm1.weight"], g["norm1.bias"])
     tc_proj = sv.packed is not None and not long_seq and d <= 64
     tc_attn = tc_proj and d == 64 and Sq == S and S >= 2
+    # da only feeds the two out_proj tensor-core GEMMs (weight gradient, input gradient): bf16, rounded once by its producer
+    dz1, da = add_dropout_ln_bwd(dy1, sv.z1, sv.st1, Mq, d, p["norm1.weight"], (seed, drop_ids[1], thr),
+                                 g["norm1.weight"], g["norm1.bias"], da_bf16=tc_proj and d == 64 and FUSE_LN_BWD)
     if tc_proj:
         wgrad_tc(da, Mq, d, sv.ctx, d, g["self_attn.out_proj.weight"], g["self_attn.out_proj.bias"])
         dctx = linear_tc(da, Mq, d, p["self_attn.out_proj.weight"], 1, d, out_bf16=tc_attn)

@@ -107,6 +107,12 @@ int u2gnn_add_dropout_ln_fwd(const float* res, const float* a, int64_t M, int d,
 int u2gnn_add_dropout_ln_bwd(const float* dy, const float* z, const float* stats, int64_t M, int d,
                              const float* gamma, uint64_t seed, uint32_t rng_stream, int thr, float* dz, float* da,
                              float* dgamma, float* dbeta, u2gnn_stream_t stream);
+/* same, with da optionally stored as bf16 (da_bf16 = 1: its consumers are tensor-core kernels that round on load, so
+ * rounding once here is bit-identical at half the bytes) and dasum[d] += colsum(dz * dropout mask) (fp32 values before
+ * rounding; may be null; works without da) - the bias gradient of the linear layer that produced a.  Both options need d in {16, 32, 64, 128}. */
+int u2gnn_add_dropout_ln_bwd_ex(const float* dy, const float* z, const float* stats, int64_t M, int d,
+                                const float* gamma, uint64_t seed, uint32_t rng_stream, int thr, float* dz, void* da,
+                                int da_bf16, float* dgamma, float* dbeta, float* dasum, u2gnn_stream_t stream);
 /* y = LayerNorm(z) from saved stats (re-materialises a layer input from its pre-norm value) */
 int u2gnn_ln_apply(const float* z, const float* stats, int64_t M, int d, const float* gamma, const float* beta,
                    float* y, u2gnn_stream_t stream);
@@ -230,6 +236,13 @@ int u2gnn_gemm_tc_rows_ex(const void* A, int a_bf16, int64_t M, int K, int64_t l
                           const float* bias, float beta, void* C, int c_bf16, int64_t ldc, u2gnn_stream_t stream);
 int u2gnn_gemm_tc_wgrad_ex(const void* A, int a_bf16, int64_t M, int N1, int64_t lda, const void* B, int b_bf16, int N2,
                            int64_t ldb, float* dW, float* db, u2gnn_stream_t stream);
+/* out_proj + dropout + residual + LayerNorm1 in one kernel (torch/nn/modules/transformer.py:946,969-972:
+ * x = norm1(x + dropout1(self_attn(x)))): z[M,64] = res + dropout(A[M,K] W^T + bias), y = LayerNorm(z) * gamma + beta,
+ * stats[M,2] = (mean, rstd).  N = d = 64 only; res row stride ldres (elements) so the last timestep can read position 0 of
+ * each sequence in place.  Same arithmetic as u2gnn_gemm_tc_rows_ex followed by u2gnn_add_dropout_ln_fwd (bit-identical). */
+int u2gnn_gemm_tc_rows_ln(const void* A, int a_bf16, int64_t M, int K, int64_t lda, const float* W, int w_kn,
+                          const float* bias, const float* res, int64_t ldres, uint64_t seed, uint32_t rng_stream, int thr,
+                          const float* gamma, const float* beta, float* z, float* y, float* stats, u2gnn_stream_t stream);
 int u2gnn_seqattn_tc_fwd_ex(const void* qkv, int64_t B, int S, int d, uint64_t seed, uint32_t rng_stream, int thr,
                             void* ctx, int io_bf16, u2gnn_stream_t stream);
 int u2gnn_seqattn_tc_bwd_ex(const void* qkv, const void* dctx, int64_t B, int S, int d, uint64_t seed,

@@ -368,3 +368,86 @@ def test_gemm_tc_rows_warp_specialised_equals_phase_serial(U, M, K, N, a_bf16, c
     assert torch.equal(outs[0], outs[1])
     ref = A.float().to(torch.bfloat16).float() @ W.to(torch.bfloat16).float() + b + (C0 if beta else 0)
     assert (outs[1].float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+
+
+# ------------------------------------------------------------------ fused attention-block epilogues
+@pytest.mark.parametrize("M,S,p,a_bf16", [(1000, 1, 0.5, 1), (4096 * 3 + 5, 1, 0.5, 1), (300, 17, 0.5, 1), (517, 1, 0.0, 0), (128, 1, 0.5, 0)])
+def test_out_proj_ln_fused_equals_gemm_then_layernorm(U, M, S, p, a_bf16):
+    """u2gnn_gemm_tc_rows_ln (out_proj + dropout + residual + LayerNorm1 in the GEMM epilogue) against the two kernels it
+    replaces: same MMAs, same fp32 arithmetic in the same order -> z, y and stats bit-identical.  S > 1 reads the residual
+    with a row stride (position 0 of each sequence, the last-timestep case)."""
+    from u2gnn_b200 import engine as E
+    d = 64
+    thr = E.dropout_threshold(p)
+    g = torch.Generator(device="cuda").manual_seed(M + S)
+    ctx = torch.randn(M, d, device="cuda", generator=g)
+    if a_bf16:
+        ctx = ctx.to(torch.bfloat16)
+    prm = {"self_attn.out_proj.weight": torch.randn(d, d, device="cuda", generator=g) / 8,
+           "self_attn.out_proj.bias": torch.randn(d, device="cuda", generator=g),
+           "norm1.weight": 1 + 0.1 * torch.randn(d, device="cuda", generator=g),
+           "norm1.bias": 0.1 * torch.randn(d, device="cuda", generator=g)}
+    x = torch.randn(M * S, d, device="cuda", generator=g)
+    drop = (0x1234ABCD5, 21, thr)
+    a = E.linear_tc(ctx, M, d, prm["self_attn.out_proj.weight"], 0, d, bias=prm["self_attn.out_proj.bias"])
+    xq = x.view(M, S, d)[:, 0, :].contiguous()
+    z0, y0, st0 = E.add_dropout_ln_fwd(xq, a, M, d, drop, prm["norm1.weight"], prm["norm1.bias"])
+    z1, y1, st1 = E.out_proj_ln_tc(ctx, M, d, prm, x, S * d, drop)
+    torch.cuda.synchronize()
+    assert torch.equal(z1, z0)
+    assert torch.equal(st1, st0)
+    assert torch.equal(y1, y0)
+
+
+@pytest.mark.parametrize("M,d,p", [(1000, 64, 0.5), (4096 * 2 + 7, 64, 0.5), (333, 32, 0.25), (200, 64, 0.0)])
+def test_ln_bwd_bf16_da_and_folded_bias_gradient(U, M, d, p):
+    """u2gnn_add_dropout_ln_bwd_ex: dz identical to the base entry point, da == bf16(da of the base entry point) bit for bit,
+    dasum == column sums of the fp32 masked gradient (what u2gnn_colsum computed in a separate pass)."""
+    from u2gnn_b200 import engine as E
+    thr = E.dropout_threshold(p)
+    g = torch.Generator(device="cuda").manual_seed(M + d)
+    dy = torch.randn(M, d, device="cuda", generator=g)
+    z = torch.randn(M, d, device="cuda", generator=g) * 2 + 0.3
+    mean = z.mean(1)
+    rstd = (z.var(1, unbiased=False) + 1e-5).rsqrt()
+    stats = torch.stack([mean, rstd], 1).contiguous()
+    gamma = 1 + 0.1 * torch.randn(d, device="cuda", generator=g)
+    drop = (77, 5, thr)
+    dg0 = torch.zeros(d, device="cuda"); db0 = torch.zeros(d, device="cuda")
+    dg1 = torch.zeros(d, device="cuda"); db1 = torch.zeros(d, device="cuda"); ds1 = torch.zeros(d, device="cuda")
+    dz0, da0 = E.add_dropout_ln_bwd(dy, z, stats, M, d, gamma, drop, dg0, db0)
+    dz1, da1 = E.add_dropout_ln_bwd(dy, z, stats, M, d, gamma, drop, dg1, db1, da_bf16=True, dasum=ds1)
+    torch.cuda.synchronize()
+    assert torch.equal(dz1, dz0)
+    if thr:
+        assert da1.dtype == torch.bfloat16 and torch.equal(da1, da0.to(torch.bfloat16))
+    else:
+        assert da1 is dz1
+    ref = da0.double().sum(0)
+    assert (ds1.double() - ref).abs().max().item() <= 1e-5 * max(1.0, da0.abs().sum(0).max().item())
+    assert (dg1 - dg0).abs().max().item() <= 1e-4 * max(1.0, dg0.abs().max().item())
+    assert (db1 - db0).abs().max().item() <= 1e-4 * max(1.0, db0.abs().max().item())
+
+
+def test_fused_attention_block_epilogues_equal_unfused_step(U):
+    """Whole train-step gradients with the fused epilogues (out_proj+LN1, bf16 da, folded linear2 bias gradient) against the
+    same step with the separate kernels: forward bit-identical, gradients equal up to the order of fp32 atomics."""
+    from u2gnn_b200 import engine as E
+    from u2gnn_b200.synthetic import make_batch
+    from u2gnn_b200.trainer import SupTrainer
+    b = make_batch(3000, 16, 64, 2, seed=9)
+    out = {}
+    try:
+        for fused in (False, True):
+            E.FUSE_OUT_PROJ_LN = E.FUSE_LN_BWD = fused
+            torch.manual_seed(3)
+            m = U.TransformerU2GNN(64, 512, 2, 3, 0.5, 1, attn_axis="neighbors").cuda()
+            tr = SupTrainer(m, lr=5e-4, precision="bf16", seed=42)
+            loss, scores = tr.forward_backward(b["input_x"], b["rowptr"], b["X"], b["labels"], train=True)
+            out[fused] = (loss.item(), scores.clone(), tr.arena.g.clone())
+    finally:
+        E.FUSE_OUT_PROJ_LN = E.FUSE_LN_BWD = True
+    assert out[True][0] == out[False][0]
+    assert torch.equal(out[True][1], out[False][1])
+    g1, g0 = out[True][2], out[False][2]
+    assert ((g1 - g0).norm() / g0.norm()).item() < 1e-5
