@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams
         if (TRACE && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && tr_n < (uint32_t)TRACE_CAP)
             p.trace[slot * TRACE_CAP + tr_n++] = (uint32_t)(clock64() - tr_t0);
     };
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset on the shared-window address: keeps LDS / STS (a uintptr_t round trip makes every access generic)
     uint8_t* sW = smem;                                    // STAGES x 16 KB
     uint8_t* sX = sW + STAGES * STAGE_BYTES;               // [2 buffers][2 tiles][128 rows x 272 B] fp32 staging
     uint32_t* sB1h = reinterpret_cast<uint32_t*>(sX + 4 * XS_TILE_BYTES);    // b1 as packed bf16 pairs (ff/2 words)

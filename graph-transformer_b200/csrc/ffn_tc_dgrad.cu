@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(Cfg<NT>::kThreads, 3 - NT) ffn_tc_dgrad_kernel
         if (TRACE && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && tr_n < (uint32_t)TRACE_CAP)
             p.trace[(32 + slot) * TRACE_CAP + tr_n++] = (uint32_t)(clock64() - tr_t0);
     };
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset on the shared-window address: keeps LDS / STS (a uintptr_t round trip makes every access generic)
     uint8_t* sW = smem;                                                        // STAGES x 48 KB
     uint32_t* sB1h = reinterpret_cast<uint32_t*>(sW + STAGES * BLOCK);         // b1 as packed bf16 pairs
     uint8_t* sIO = reinterpret_cast<uint8_t*>(sB1h + p.ff / 2);                // 16 KB per (tile, warpgroup): bf16 tile image, later dY staging

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params 
         if (TRACE && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && tr_n < (uint32_t)TRACE_CAP)
             p.trace[slot * TRACE_CAP + tr_n++] = (uint32_t)(clock64() - tr_t0);
     };
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset on the shared-window address: keeps LDS / STS (a uintptr_t round trip makes every access generic)
     uint8_t* sXF = smem;                                   // WG_STAGES x (X 16 KB | dF 16 KB)
     uint8_t* sOnes = smem + WG_STAGES * 32768;             // 16 KB tile of bf16 1.0 (after the ring: LBO to it is positive)
     uint8_t* sH = sOnes + 16384;                           // 32 KB: two [128 rows x 64 hidden] tiles

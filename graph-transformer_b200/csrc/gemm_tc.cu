@@ -21,9 +21,10 @@ constexpr int kThreads = 256;
 // [rows x K] block (row stride lda in ELEMENTS; fp32, or bf16 when src_bf16) -> K/64 swizzled bf16 tiles of [128 x 64];
 // rows >= M and cols >= K_true zero.  A bf16 source is what the upstream kernel already rounded (bit-identical to
 // rounding here) at half the HBM bytes.
-template <int NT>
+template <int NT, int KPC = 0>      // KPC: padded K known at compile time (index arithmetic without runtime divisions), 0 = runtime
 __device__ __forceinline__ void stage_rows_bf16(uint8_t* tiles, const void* __restrict__ src_, int src_bf16, int64_t row0, int64_t M,
-                                                int K_true, int KP, int64_t lda, int tid) {
+                                                int K_true, int KP_rt, int64_t lda, int tid) {
+    const int KP = KPC ? KPC : KP_rt;
     const int c4n = KP / 4;                                   // 4-element groups per padded row
     if ((K_true & 3) == 0 && (lda & 3) == 0) {
         if (src_bf16 && (K_true & 7) == 0 && (lda & 7) == 0) {
@@ -142,10 +143,10 @@ __device__ __forceinline__ float group16_sum(float v) {
     return v;
 }
 
-template <bool LN>
-__global__ void __launch_bounds__(kThreads, 3) gemm_tc_rows_kernel(const RowsParams p) {
+template <bool LN, int MINB>        // MINB: CTAs per SM the register budget is sized for (wide outputs are limited to 2 by tensor memory / smem)
+__global__ void __launch_bounds__(kThreads, MINB) gemm_tc_rows_kernel(const RowsParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset on the shared-window address: keeps LDS / STS (a uintptr_t round trip makes every access generic)
     const int kt = p.KP / 64;
     uint8_t* sA = smem;                                     // kt tiles of [128 x 64]
     uint8_t* sB = smem + kt * 16384;                        // kt tiles of [NP x 64] (NP*128 B each)
@@ -184,7 +185,9 @@ __global__ void __launch_bounds__(kThreads, 3) gemm_tc_rows_kernel(const RowsPar
     uint32_t phase = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row0 = tile * TM;
-        stage_rows_bf16<kThreads>(sA, p.A, p.a_bf16, row0, p.M, p.K, p.KP, p.lda, tid);
+        if (p.KP == 64) stage_rows_bf16<kThreads, 64>(sA, p.A, p.a_bf16, row0, p.M, p.K, 64, p.lda, tid);
+        else if (p.KP == 192) stage_rows_bf16<kThreads, 192>(sA, p.A, p.a_bf16, row0, p.M, p.K, 192, p.lda, tid);
+        else stage_rows_bf16<kThreads>(sA, p.A, p.a_bf16, row0, p.M, p.K, p.KP, p.lda, tid);
         tc::fence_proxy_async();
         tc::tc_fence_before();
         __syncthreads();
@@ -200,15 +203,22 @@ __global__ void __launch_bounds__(kThreads, 3) gemm_tc_rows_kernel(const RowsPar
             }
             __syncwarp();
         }
-        float4 resq[LN ? 8 : 1];
-        if constexpr (LN) {
-            // residual rows in the layout of the coalesced store phase (16 lanes x float4 per row), in flight during the MMA
+        // rows the coalesced phase of this thread adds in (16 lanes x float4 per row), requested while the MMA runs:
+        // the residual (LN variant) or the old C of the first 64-column piece (beta != 0)
+        const bool vec_ok = ((p.ldc & 3) == 0) && ((p.N & 3) == 0);
+        const bool pre_old = !LN && p.beta != 0.0f && !p.c_bf16 && vec_ok;
+        float4 pre[8];
+        if (LN || pre_old) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int e = u * kThreads + tid;
                 const int64_t row = row0 + (e >> 4);
-                resq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row < p.M) resq[u] = __ldg(reinterpret_cast<const float4*>(p.res + row * p.ldres) + (e & 15));
+                pre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if constexpr (LN) {
+                    if (row < p.M) pre[u] = __ldg(reinterpret_cast<const float4*>(p.res + row * p.ldres) + (e & 15));
+                } else {
+                    if (row < p.M && 4 * (e & 15) < p.N) pre[u] = *(reinterpret_cast<const float4*>(static_cast<const float*>(p.C) + row * p.ldc) + (e & 15));
+                }
             }
         }
         tc::mbar_wait(&bar, phase);
@@ -218,16 +228,24 @@ __global__ void __launch_bounds__(kThreads, 3) gemm_tc_rows_kernel(const RowsPar
         // warps of a quarter take 32 columns each) -> padded shared-memory staging -> COALESCED 128-bit global stores
         // (consecutive threads = consecutive 16-byte pieces of a row).  Writing rows straight from the thread-per-row
         // registers touched 32 cache lines per store instruction and was the largest cost of this kernel.
-        const bool vec_ok = ((p.ldc & 3) == 0) && ((p.N & 3) == 0);
+        // The copy-out loads every staged piece (and the bias, once) BEFORE the guarded arithmetic / stores: guarded
+        // loads cannot be hoisted by the compiler and made each of the 4-8 iterations wait for its own round trip.
+        const bool bf16_vec = !LN && p.c_bf16 && vec_ok && (p.ldc & 7) == 0 && (p.N & 7) == 0;
         for (int c0 = 0; c0 < p.NP; c0 += 64) {
             if (c0 + 32 * half < p.NP) {
                 uint32_t v[32];
                 tc::tmem_ld32(tmem + lane_base + c0 + 32 * half, v);
                 tc::tmem_ld_wait();
-                float4* srow = reinterpret_cast<float4*>(sOut + (wq * 32 + lane) * 272 + 128 * half);
+                uint8_t* srow = sOut + (wq * 32 + lane) * 272;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    srow[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                for (int j = 0; j < 8; ++j) {
+                    // 16-byte piece J = 8 half + j of the row.  bf16 copy-out: a thread converts pieces (2c, 2c+1), so they are
+                    // staged at positions (c, 8 + c) and each quarter-warp load covers 128 contiguous bytes (no conflicts)
+                    const int J = 8 * half + j;
+                    const int pos = bf16_vec ? ((J >> 1) + 8 * (J & 1)) : J;
+                    *reinterpret_cast<float4*>(srow + 16 * pos) = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                }
             }
             __syncthreads();
             if constexpr (LN) {
@@ -236,15 +254,20 @@ __global__ void __launch_bounds__(kThreads, 3) gemm_tc_rows_kernel(const RowsPar
                 const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma) + (tid & 15));
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ln_beta) + (tid & 15));
                 const float4 bias4 = __ldg(reinterpret_cast<const float4*>(p.bias) + (tid & 15));
+                float4 st[4];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
+                    if ((u & 3) == 0) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) st[q] = *reinterpret_cast<const float4*>(sOut + (((u + q) * kThreads + tid) >> 4) * 272 + 16 * (tid & 15));
+                    }
                     const int e = u * kThreads + tid;
                     const int rr = e >> 4, l = e & 15;
                     const int64_t row = row0 + rr;
                     const bool ok = row < p.M;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (ok) {
-                        v = *reinterpret_cast<const float4*>(sOut + rr * 272 + 16 * l);
+                        v = st[u & 3];
                         v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
                         if (p.thr) {
                             const uint64_t el = (uint64_t)(row * 64 + 4 * l);
@@ -254,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, 3) gemm_tc_rows_kernel(const RowsPar
                             v.z = (w & 4u) ? v.z * p.scale : 0.0f;
                             v.w = (w & 8u) ? v.w * p.scale : 0.0f;
                         }
-                        v.x += resq[u].x; v.y += resq[u].y; v.z += resq[u].z; v.w += resq[u].w;
+                        v.x += pre[u].x; v.y += pre[u].y; v.z += pre[u].z; v.w += pre[u].w;
                         reinterpret_cast<float4*>(p.z + row * 64)[l] = v;
                     }
                     const float mean = group16_sum((v.x + v.y) + (v.z + v.w)) * (1.0f / 64.0f);
@@ -269,32 +292,63 @@ __global__ void __launch_bounds__(kThreads, 3) gemm_tc_rows_kernel(const RowsPar
                 __syncthreads();
                 continue;
             }
-            if (p.c_bf16 && vec_ok && (p.ldc & 7) == 0 && (p.N & 7) == 0) {
+            if (bf16_vec) {
                 // bf16 result (rounded once here: what every consumer would do on load), 8 columns = 16 bytes per thread
+                const int c8 = tid & 7;
+                const int col = c0 + 8 * c8;
+                float4 bb0 = make_float4(0.f, 0.f, 0.f, 0.f), bb1 = bb0;
+                if (p.bias && col < p.N) {
+                    bb0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                    bb1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+                }
+                float4 o0[4], o1[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int e = u * kThreads + tid;
-                    const int rr = e >> 3, c8 = e & 7;
-                    const int64_t row = row0 + rr;
-                    const int col = c0 + 8 * c8;
+                    const int rr = (u * kThreads + tid) >> 3;
+                    o0[u] = *reinterpret_cast<const float4*>(sOut + rr * 272 + 16 * c8);
+                    o1[u] = *reinterpret_cast<const float4*>(sOut + rr * 272 + 128 + 16 * c8);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t row = row0 + ((u * kThreads + tid) >> 3);
                     if (row < p.M && col < p.N) {
-                        float4 o0 = *reinterpret_cast<const float4*>(sOut + rr * 272 + 32 * c8);
-                        float4 o1 = *reinterpret_cast<const float4*>(sOut + rr * 272 + 32 * c8 + 16);
-                        if (p.bias) {
-                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-                            o0.x += b0.x; o0.y += b0.y; o0.z += b0.z; o0.w += b0.w;
-                            o1.x += b1.x; o1.y += b1.y; o1.z += b1.z; o1.w += b1.w;
-                        }
                         uint4 w;
-                        w.x = epi::cvt2(o0.x, o0.y); w.y = epi::cvt2(o0.z, o0.w);
-                        w.z = epi::cvt2(o1.x, o1.y); w.w = epi::cvt2(o1.z, o1.w);
+                        w.x = epi::cvt2(o0[u].x + bb0.x, o0[u].y + bb0.y); w.y = epi::cvt2(o0[u].z + bb0.z, o0[u].w + bb0.w);
+                        w.z = epi::cvt2(o1[u].x + bb1.x, o1[u].y + bb1.y); w.w = epi::cvt2(o1[u].z + bb1.z, o1[u].w + bb1.w);
                         *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col) = w;
                     }
                 }
                 __syncthreads();
                 continue;
             }
+            if (!p.c_bf16 && vec_ok) {
+                // fp32 result, 4 columns = 16 bytes per thread, 16 lanes per row
+                const int c4 = tid & 15;
+                const int col = c0 + 4 * c4;
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias && col < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                float4 o[4];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if ((u & 3) == 0) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) o[q] = *reinterpret_cast<const float4*>(sOut + (((u + q) * kThreads + tid) >> 4) * 272 + 16 * c4);
+                    }
+                    const int64_t row = row0 + ((u * kThreads + tid) >> 4);
+                    if (row >= p.M || col >= p.N) continue;
+                    float* out = static_cast<float*>(p.C) + row * p.ldc + col;
+                    float4 r = o[u & 3];
+                    r.x += b4.x; r.y += b4.y; r.z += b4.z; r.w += b4.w;
+                    if (p.beta != 0.0f) {
+                        const float4 old = (pre_old && c0 == 0) ? pre[u] : *reinterpret_cast<const float4*>(out);
+                        r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
+                    }
+                    *reinterpret_cast<float4*>(out) = r;
+                }
+                __syncthreads();
+                continue;
+            }
+            // unaligned shapes (parity-sized feature dimensions): scalar tail handling
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int e = u * kThreads + tid;
@@ -302,46 +356,23 @@ __global__ void __launch_bounds__(kThreads, 3) gemm_tc_rows_kernel(const RowsPar
                 const int64_t row = row0 + rr;
                 const int col = c0 + 4 * c4;
                 if (row >= p.M || col >= p.N) continue;
-                float4 o = *reinterpret_cast<const float4*>(sOut + rr * 272 + 16 * c4);
+                const float4 o = *reinterpret_cast<const float4*>(sOut + rr * 272 + 16 * c4);
+                const float ov[4] = {o.x, o.y, o.z, o.w};
                 if (p.c_bf16) {                              // rounded once here: what every consumer would do on load
                     __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col;
-                    float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        if (p.bias && col + j < p.N) ov[j] += p.bias[col + j];
-                    if (vec_ok) {
-                        uint2 w;
-                        w.x = epi::cvt2(ov[0], ov[1]);
-                        w.y = epi::cvt2(ov[2], ov[3]);
-                        *reinterpret_cast<uint2*>(ob) = w;
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (col + j < p.N) ob[j] = __float2bfloat16(ov[j]);
-                    }
+                        if (col + j < p.N) ob[j] = __float2bfloat16(ov[j] + (p.bias ? p.bias[col + j] : 0.0f));
                     continue;
                 }
                 float* out = static_cast<float*>(p.C) + row * p.ldc + col;
-                if (vec_ok) {
-                    if (p.bias) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                        o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-                    }
-                    if (p.beta != 0.0f) {
-                        const float4 old = *reinterpret_cast<const float4*>(out);
-                        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                    }
-                    *reinterpret_cast<float4*>(out) = o;
-                } else {
-                    const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (col + j < p.N) {
-                            float x = ov[j] + (p.bias ? p.bias[col + j] : 0.0f);
-                            if (p.beta != 0.0f) x += out[j];
-                            out[j] = x;
-                        }
-                }
+                for (int j = 0; j < 4; ++j)
+                    if (col + j < p.N) {
+                        float x = ov[j] + (p.bias ? p.bias[col + j] : 0.0f);
+                        if (p.beta != 0.0f) x += out[j];
+                        out[j] = x;
+                    }
             }
             __syncthreads();                                 // staging is reused by the next piece / tile
         }
@@ -378,7 +409,7 @@ __device__ __forceinline__ void ws_named_bar(int id, int threads) {
 template <bool A_BF16, int NPF>      // NPF: 16-byte pieces per loader thread per tile (fp32 K 64: 8; bf16 K 64: 4; bf16 K 192: 12)
 __global__ void __launch_bounds__(kWsThreads, 1) gemm_tc_rows_ws_kernel(const RowsParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset on the shared-window address: keeps LDS / STS (a uintptr_t round trip makes every access generic)
     const int kt = p.KP / 64;
     uint8_t* sA = smem;                                     // 2 stages x kt tiles of [128 x 64]
     uint8_t* sB = sA + 2 * kt * 16384;                      // kt tiles of [NP x 64]
@@ -606,7 +637,7 @@ struct WgradParams {
 
 __global__ void __launch_bounds__(kThreads, 2) gemm_tc_wgrad_kernel(const WgradParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset on the shared-window address: keeps LDS / STS (a uintptr_t round trip makes every access generic)
     const int ga = (p.N1 + 63) / 64;                         // 64-column groups of A (1..4)
     const int nacc = (ga + 1) / 2;                           // accumulators of 128 A-columns
     // per stage: ga A tiles, 1 B tile ; then ones tile and zero tile
@@ -748,7 +779,6 @@ extern "C" int u2gnn_gemm_tc_rows_ex(const void* A, int a_bf16, int64_t M, int K
     }
     const size_t smem = 1024 + (size_t)kt * 16384 + (size_t)kt * p.NP * 128 + 128 * 272;
     if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
-    cudaFuncSetAttribute(gemm_tc_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = (int)((220 * 1024) / (smem + 1024));
     const int tmem_cols = (p.NP <= 64) ? 64 : (p.NP <= 128 ? 128 : 256);
     if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;   // tensor-memory columns per CTA
@@ -756,7 +786,14 @@ extern "C" int u2gnn_gemm_tc_rows_ex(const void* A, int a_bf16, int64_t M, int K
     if (per_sm < 1) per_sm = 1;
     const int64_t n_tiles = (M + TM - 1) / TM;
     const int64_t cap = (int64_t)U2GNN_NUM_SMS * per_sm;
-    gemm_tc_rows_kernel<false><<<(int)(n_tiles < cap ? n_tiles : cap), kThreads, smem, as_stream(stream)>>>(p);
+    const int grid = (int)(n_tiles < cap ? n_tiles : cap);
+    if (per_sm >= 3) {
+        cudaFuncSetAttribute(gemm_tc_rows_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        gemm_tc_rows_kernel<false, 3><<<grid, kThreads, smem, as_stream(stream)>>>(p);
+    } else {
+        cudaFuncSetAttribute(gemm_tc_rows_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        gemm_tc_rows_kernel<false, 2><<<grid, kThreads, smem, as_stream(stream)>>>(p);
+    }
     U2GNN_CHECK_LAUNCH();
 }
 
@@ -784,13 +821,13 @@ extern "C" int u2gnn_gemm_tc_rows_ln(const void* A, int a_bf16, int64_t M, int K
     const int kt = p.KP / 64;
     const size_t smem = 1024 + (size_t)kt * 16384 + (size_t)kt * p.NP * 128 + 128 * 272;
     if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
-    cudaFuncSetAttribute(gemm_tc_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gemm_tc_rows_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = (int)((220 * 1024) / (smem + 1024));
     if (per_sm > 3) per_sm = 3;                              // __launch_bounds__(256, 3)
     if (per_sm < 1) per_sm = 1;
     const int64_t n_tiles = (M + TM - 1) / TM;
     const int64_t cap = (int64_t)U2GNN_NUM_SMS * per_sm;
-    gemm_tc_rows_kernel<true><<<(int)(n_tiles < cap ? n_tiles : cap), kThreads, smem, as_stream(stream)>>>(p);
+    gemm_tc_rows_kernel<true, 3><<<(int)(n_tiles < cap ? n_tiles : cap), kThreads, smem, as_stream(stream)>>>(p);
     U2GNN_CHECK_LAUNCH();
 }
 

@@ -7,7 +7,7 @@
 namespace {
 __global__ void __launch_bounds__(128) tc_probe_kernel(int N, int ts, int rotate, int count, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset on the shared-window address: keeps LDS / STS (a uintptr_t round trip makes every access generic)
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     const int t = threadIdx.x, warp = t >> 5;

@@ -18,7 +18,7 @@ constexpr int kMaxK = 128;
 __global__ void __launch_bounds__(128) tc_selftest_kernel(int mode, const float* __restrict__ A, const float* __restrict__ B,
                                                           float* __restrict__ C, int K, int N, uint8_t* scratch) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset on the shared-window address: keeps LDS / STS (a uintptr_t round trip makes every access generic)
     uint8_t* sA = smem;                        // up to 2 tiles of [128 x 64] bf16 (32 KB)
     uint8_t* sB = smem + 32768;                // up to 2 tiles (32 KB)
     __shared__ uint64_t bar_mma, bar_copy;
