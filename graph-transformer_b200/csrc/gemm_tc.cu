@@ -106,6 +106,36 @@ __device__ __forceinline__ void stage_rows_bf16(uint8_t* tiles, const void* __re
     }
 }
 
+// bf16 row block -> swizzled tiles with cp.async (16-byte chunk = one swizzle chunk, no registers, asynchronous): issue only,
+// the caller commits / waits.  Rows >= M and chunks >= K_true are zero-filled (src-size 0).  Needs K_true, lda multiples of 8
+// and a 16-byte aligned base (rows_async_ok).
+__device__ __forceinline__ bool rows_async_ok(const void* src, int src_bf16, int K_true, int64_t lda) {
+    return src_bf16 && (K_true & 7) == 0 && (lda & 7) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NT>
+__device__ __forceinline__ void stage_rows_async(uint8_t* tiles, const void* __restrict__ src_, int64_t row0, int64_t M, int K_true,
+                                                 int KP, int64_t lda, int tid) {
+    const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(src_);
+    const uint32_t base = tc::smem_u32(tiles);
+    // 8 lanes = the 8 chunks (128 contiguous bytes) of one row of one 64-column tile
+    const int c = tid & 7;
+    for (int t = 0; t < KP / 64; ++t) {
+        const bool col_ok = 64 * t + 8 * c < K_true;
+        for (int r = tid >> 3; r < TM; r += NT / 8) {
+            const bool ok = col_ok && row0 + r < M;
+            const void* g = ok ? static_cast<const void*>(src + (row0 + r) * lda + 64 * t + 8 * c) : src_;
+            cp_async16(base + (uint32_t)t * 16384u + tc::sw128_chunk(r, c), g, ok ? 16u : 0u);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // rows GEMM
 // ---------------------------------------------------------------------------------------------------------------
@@ -664,18 +694,38 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_wgrad_kernel(const WgradP
     const uint32_t tmem = tmem_slot;
     const uint32_t idesc = tc::make_idesc(128, 80, 1, 1);    // M = 128 A-columns, N = [B | ones], both MN-major
     const int64_t n_tiles = (p.M + TM - 1) / TM;
+    // Two stages, loads one tile ahead of the MMAs.  bf16 operands travel with cp.async (asynchronous, no registers) straight
+    // into the swizzled tiles; an fp32 operand is converted through registers AFTER the current tile's MMAs were issued, so
+    // its load latency overlaps them and the cp.async traffic of the same tile.  (The first version loaded, converted and
+    // stored each operand synchronously: one CTA per SM for the wide in_proj gradient exposed three DRAM round trips per
+    // tile - 37 % of the HBM bandwidth.)
+    const bool a_async = rows_async_ok(p.A, p.a_bf16, p.N1, p.lda);
+    const bool b_async = rows_async_ok(p.B, p.b_bf16, p.N2, p.ldb);
+    auto issue_async = [&](int64_t tile, uint8_t* st) {
+        if (a_async) stage_rows_async<kThreads>(st, p.A, tile * TM, p.M, p.N1, ga * 64, p.lda, tid);
+        if (b_async) stage_rows_async<kThreads>(st + ga * 16384, p.B, tile * TM, p.M, p.N2, 64, p.ldb, tid);
+    };
+    auto finish_sync = [&](int64_t tile, uint8_t* st) {
+        if (!a_async) stage_rows_bf16<kThreads>(st, p.A, p.a_bf16, tile * TM, p.M, p.N1, ga * 64, p.lda, tid);
+        if (!b_async) stage_rows_bf16<kThreads>(st + ga * 16384, p.B, p.b_bf16, tile * TM, p.M, p.N2, 64, p.ldb, tid);
+    };
     int64_t it = 0;
-    uint32_t ph[2] = {0, 0};
+    if ((int64_t)blockIdx.x < n_tiles) {
+        issue_async(blockIdx.x, smem);
+        cp_async_commit();
+        finish_sync(blockIdx.x, smem);
+    }
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int s = (int)(it & 1);
         uint8_t* st = smem + s * stage_bytes;
-        if (it >= 2) {                                        // the MMAs that read this stage two tiles ago are done
-            tc::mbar_wait(&bar_mma[s], ph[s]);
-            ph[s] ^= 1;
+        uint8_t* st_next = smem + (s ^ 1) * stage_bytes;
+        const int64_t next = tile + gridDim.x;
+        if (next < n_tiles) {
+            if (it >= 1) tc::mbar_wait(&bar_mma[s ^ 1], (uint32_t)(((it - 1) >> 1) & 1));   // MMAs of tile it-1 have read that stage
+            issue_async(next, st_next);
         }
-        const int64_t row0 = tile * TM;
-        stage_rows_bf16<kThreads>(st, p.A, p.a_bf16, row0, p.M, p.N1, ga * 64, p.lda, tid);
-        stage_rows_bf16<kThreads>(st + ga * 16384, p.B, p.b_bf16, row0, p.M, p.N2, 64, p.ldb, tid);
+        cp_async_commit();
+        cp_async_wait<1>();                                   // this thread's chunks of tile `it` have landed
         tc::fence_proxy_async();
         tc::tc_fence_before();
         __syncthreads();
@@ -695,15 +745,14 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_wgrad_kernel(const WgradP
             }
             __syncwarp();
         }
+        if (next < n_tiles) finish_sync(next, st_next);
     }
-    // drain: wait for the last one / two commits
+    cp_async_wait<0>();
+    // drain: wait for the last one / two commits (commit k on a stage completes phase k & 1)
     if (it >= 1) {
         const int s1 = (int)((it - 1) & 1);
-        tc::mbar_wait(&bar_mma[s1], ph[s1]);
-        if (it >= 2) {
-            const int s0 = s1 ^ 1;
-            tc::mbar_wait(&bar_mma[s0], ph[s0]);
-        }
+        tc::mbar_wait(&bar_mma[s1], (uint32_t)(((it - 1) >> 1) & 1));
+        if (it >= 2) tc::mbar_wait(&bar_mma[s1 ^ 1], (uint32_t)(((it - 2) >> 1) & 1));
         tc::tc_fence_after();
         // flush: thread = A column (row of the accumulator); 128 threads per accumulator pass
         const int wq = warp & 3;
