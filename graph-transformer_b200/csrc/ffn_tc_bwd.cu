@@ -21,8 +21,19 @@
 #include "tc_common.cuh"
 #include "ffn_epi.cuh"
 
+struct FfnLnBwd {       // LayerNorm2 backward fused into the dgrad loader (ffn_tc_dgrad.cu)
+    const float* dy2;
+    const float* z2;
+    const float* st2;
+    const float* gamma2;
+    uint32_t stream_out;
+    float* dgamma2;
+    float* dbeta2;
+    float* db2;
+};
 int ffn_tc_dgrad_launch(const float* y1, const float* df, const float* dz, float* dy1, int64_t M, int d, int ff,
-                        const void* packed, uint64_t seed, uint32_t stream_hidden, int thr, void* xb, void* fb, cudaStream_t st);
+                        const void* packed, uint64_t seed, uint32_t stream_hidden, int thr, void* xb, void* fb, cudaStream_t st,
+                        const FfnLnBwd* ln);
 int ffn_tc_wgrad_launch(const void* xb, const void* fb, int64_t M, int d, int ff, const void* packed, float hidden_scale,
                         uint64_t seed, uint32_t stream_hidden, int thr, float* dW1, float* db1, float* dW2, float* dy1_merged,
                         cudaStream_t st);
@@ -108,7 +119,40 @@ extern "C" int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const float* d
         if (rc != U2GNN_OK) return rc;
         U2GNN_CHECK_LAUNCH();
     }
-    rc = ffn_tc_dgrad_launch(y1, df, dz, dy1, M, d, ff, packed, seed, stream_hidden, thr, xb, fb, as_stream(stream));
+    rc = ffn_tc_dgrad_launch(y1, df, dz, dy1, M, d, ff, packed, seed, stream_hidden, thr, xb, fb, as_stream(stream), nullptr);
+    if (rc != U2GNN_OK) return rc;
+    rc = ffn_tc_wgrad_launch(xb, fb, M, d, ff, packed, hidden_scale, seed, stream_hidden, thr, dW1, db1, dW2, nullptr, as_stream(stream));
+    if (rc != U2GNN_OK) return rc;
+    U2GNN_CHECK_LAUNCH();
+}
+
+// LayerNorm2 backward + output dropout + FFN backward (d == 64): dy2 is the gradient at the LayerNorm2 output, z2 / st2 the
+// saved pre-norm rows and (mean, rstd).  The dgrad kernel's dF loader computes dz = LN backward(dy2), dF = dropout(dz) on the
+// fly (the separate LayerNorm-backward pass read 520 and wrote 512 bytes per row), accumulates dgamma2 / dbeta2 and the
+// linear2 bias gradient db2 = colsum(dF), and the drain adds dPre W1 to the parked dz.
+extern "C" int u2gnn_ffn_tc_bwd_ln(const float* y1, const float* dy2, const float* z2, const float* st2, const float* gamma2,
+                                   uint32_t stream_out, int64_t M, int d, int ff, const void* packed, float hidden_scale,
+                                   uint64_t seed, uint32_t stream_hidden, int thr, float* dy1, float* dW1, float* db1, float* dW2,
+                                   float* db2, float* dgamma2, float* dbeta2, void* workspace, size_t workspace_bytes,
+                                   u2gnn_stream_t stream) {
+    if (!y1 || !dy2 || !z2 || !st2 || !gamma2 || !packed || !dy1 || !dW1 || !db1 || !dW2 || !db2 || !dgamma2 || !dbeta2 ||
+        !workspace || M < 0 || thr < 0 || thr > 255)
+        return U2GNN_EINVAL;
+    if (workspace_bytes < u2gnn_ffn_tc_bwd_workspace_bytes(M)) return U2GNN_EWORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) % 128) return U2GNN_EALIGN;
+    if (d != 64 || ff < 128 || ff % 128 || ff > 2048) return U2GNN_EUNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(y1) | reinterpret_cast<uintptr_t>(dy2) | reinterpret_cast<uintptr_t>(z2) |
+         reinterpret_cast<uintptr_t>(dy1) | reinterpret_cast<uintptr_t>(gamma2)) % 16 || reinterpret_cast<uintptr_t>(st2) % 8)
+        return U2GNN_EALIGN;
+    if (dy1 == dy2 || dy1 == z2) return U2GNN_EINVAL;          // dy1 is written while later tiles of dy2 / z2 are still unread
+    if (M == 0) return U2GNN_OK;
+    const size_t half = u2gnn_ffn_tc_bwd_workspace_bytes(M) / 2;
+    uint8_t* xb = static_cast<uint8_t*>(workspace);
+    uint8_t* fb = xb + half;
+    FfnLnBwd ln;
+    ln.dy2 = dy2; ln.z2 = z2; ln.st2 = st2; ln.gamma2 = gamma2; ln.stream_out = stream_out;
+    ln.dgamma2 = dgamma2; ln.dbeta2 = dbeta2; ln.db2 = db2;
+    int rc = ffn_tc_dgrad_launch(y1, nullptr, dy1, dy1, M, d, ff, packed, seed, stream_hidden, thr, xb, fb, as_stream(stream), &ln);
     if (rc != U2GNN_OK) return rc;
     rc = ffn_tc_wgrad_launch(xb, fb, M, d, ff, packed, hidden_scale, seed, stream_hidden, thr, dW1, db1, dW2, nullptr, as_stream(stream));
     if (rc != U2GNN_OK) return rc;

@@ -47,7 +47,24 @@ struct Params {
     uint8_t* xb;      // [n_tiles][128 x 64] bf16 swizzled images of y1 / df, consumed by the wgrad kernel (may be null)
     uint8_t* fb;
     uint32_t* trace;   // debug clock stamps of CTA 0 (u2gnn_ffn_tc_set_trace), slots 32..
+    // LayerNorm2 backward fused into the dF loader (LNF kernels, d == 64): dF = dropout3(dz), dz = LN backward of dy2 at
+    // the saved pre-norm z2 / stats; dz is parked in dy1 (p.dz == p.dy1) until the drain adds dPre W1 to it
+    const float* dy2;
+    const float* z2;
+    const float* st2;
+    const float* gamma2;
+    RngKeys keys3;
+    float scale3;
+    float* dgamma2;
+    float* dbeta2;
+    float* db2;        // linear2 bias gradient = colsum(dF)
 };
+
+__device__ __forceinline__ float group16_sum(float v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 constexpr int TRACE_CAP = 1024;
 
 struct __align__(8) Bars {
@@ -86,7 +103,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <bool TRACE, int NT>
+template <bool TRACE, int NT, bool LNF = false>
 __global__ void __launch_bounds__(Cfg<NT>::kThreads, 3 - NT) ffn_tc_dgrad_kernel(const Params p) {
     using C_ = Cfg<NT>;
     constexpr int kThreads = C_::kThreads, STAGES = C_::STAGES, kCtrl = C_::kCtrl;
@@ -104,6 +121,8 @@ __global__ void __launch_bounds__(Cfg<NT>::kThreads, 3 - NT) ffn_tc_dgrad_kernel
     uint8_t* sIO = reinterpret_cast<uint8_t*>(sB1h + p.ff / 2);                // 16 KB per (tile, warpgroup): bf16 tile image, later dY staging
     __shared__ Bars bars;
     __shared__ uint32_t tmem_slot;
+    __shared__ float s_acc[LNF ? 192 : 1];                 // dgamma2 | dbeta2 | db2 partial sums of this CTA
+    if (LNF) for (int e = threadIdx.x; e < 192; e += Cfg<NT>::kThreads) s_acc[e] = 0.0f;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NC = p.ff / CH;
     const int64_t n_pairs = (p.M + NT * TM - 1) / (NT * TM);      // groups of NT tiles ("pairs" for NT = 2)
@@ -221,7 +240,75 @@ __global__ void __launch_bounds__(Cfg<NT>::kThreads, 3 - NT) ffn_tc_dgrad_kernel
             {
                 const int64_t row0 = pair * (NT * TM) + (int64_t)i * TM;
                 if (tr == 0) tc::bulk_wait_read<0>();     // an image store of the previous pair may still read the region
-                if (p.d == DP) {
+                if (LNF && wg == 1) {
+                    // LayerNorm2 backward in the loader (same arithmetic, same order as ln_bwd_vec_kernel<16>, layernorm.cu):
+                    // 16 lanes x float4 = one row; dz -> dy1 (fp32, re-read by the drain), dF = dropout3(dz) -> bf16 image.
+                    // Batches of RB rows per thread keep the loads of a batch (g, x, stats) in flight together.
+                    const int l = tr & 15;
+                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma2) + l);
+                    float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, as = ag;
+#pragma unroll
+                    constexpr int RB = 4;                       // rows per thread per batch (8: 600 bytes of spills at 102 registers)
+#pragma unroll
+                    for (int hb = 0; hb < 16 / RB; ++hb) {
+                        float4 gv[RB], xv[RB];
+                        float2 sv[RB];
+#pragma unroll
+                        for (int u = 0; u < RB; ++u) {
+                            const int e = (hb * RB + u) * 128 + tr;
+                            const int64_t rg = row0 + (e >> 4);
+                            gv[u] = xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            sv[u] = make_float2(0.f, 0.f);
+                            if (rg < p.M) {
+                                gv[u] = __ldg(reinterpret_cast<const float4*>(p.dy2 + rg * DP) + l);
+                                xv[u] = __ldg(reinterpret_cast<const float4*>(p.z2 + rg * DP) + l);
+                                sv[u] = __ldg(reinterpret_cast<const float2*>(p.st2) + rg);
+                            }
+                        }
+                        if (hb == 0) named_bar_sync(bar_id, 128);      // everybody is done reading the staging of the previous pair
+#pragma unroll
+                        for (int u = 0; u < RB; ++u) {
+                            const int e = (hb * RB + u) * 128 + tr;
+                            const int64_t rg = row0 + (e >> 4);
+                            const float4 g = gv[u], x = xv[u];
+                            const float mean = sv[u].x, rstd = sv[u].y;
+                            const float4 xh = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd, (x.w - mean) * rstd);
+                            const float4 dh = make_float4(g.x * g4.x, g.y * g4.y, g.z * g4.z, g.w * g4.w);
+                            ag.x = fmaf(g.x, xh.x, ag.x); ag.y = fmaf(g.y, xh.y, ag.y); ag.z = fmaf(g.z, xh.z, ag.z); ag.w = fmaf(g.w, xh.w, ag.w);
+                            ab.x += g.x; ab.y += g.y; ab.z += g.z; ab.w += g.w;
+                            const float m1 = group16_sum((dh.x + dh.y) + (dh.z + dh.w)) * (1.0f / 64.0f);
+                            const float m2 = group16_sum((dh.x * xh.x + dh.y * xh.y) + (dh.z * xh.z + dh.w * xh.w)) * (1.0f / 64.0f);
+                            float4 o = make_float4(rstd * (dh.x - m1 - xh.x * m2), rstd * (dh.y - m1 - xh.y * m2),
+                                                   rstd * (dh.z - m1 - xh.z * m2), rstd * (dh.w - m1 - xh.w * m2));
+                            if (rg < p.M) reinterpret_cast<float4*>(p.dy1 + rg * DP)[l] = o;
+                            if (p.thr) {
+                                const uint64_t el = (uint64_t)(rg * DP + 4 * l);
+                                const uint32_t kw = rng_keep_word_lo(p.keys3, el >> 5, p.thr, p.low) >> (el & 31);
+                                o.x = (kw & 1u) ? o.x * p.scale3 : 0.0f;
+                                o.y = (kw & 2u) ? o.y * p.scale3 : 0.0f;
+                                o.z = (kw & 4u) ? o.z * p.scale3 : 0.0f;
+                                o.w = (kw & 8u) ? o.w * p.scale3 : 0.0f;
+                            }
+                            as.x += o.x; as.y += o.y; as.z += o.z; as.w += o.w;
+                            uint2 w;
+                            w.x = epi::cvt2(o.x, o.y);
+                            w.y = epi::cvt2(o.z, o.w);
+                            *reinterpret_cast<uint2*>(img_s + tc::sw128_offset(e >> 4, l * 4)) = w;
+                        }
+                    }
+                    // the two rows of the warp, then one shared-memory atomic per column per warp; flushed once per CTA
+                    ag.x += __shfl_xor_sync(0xffffffffu, ag.x, 16); ag.y += __shfl_xor_sync(0xffffffffu, ag.y, 16);
+                    ag.z += __shfl_xor_sync(0xffffffffu, ag.z, 16); ag.w += __shfl_xor_sync(0xffffffffu, ag.w, 16);
+                    ab.x += __shfl_xor_sync(0xffffffffu, ab.x, 16); ab.y += __shfl_xor_sync(0xffffffffu, ab.y, 16);
+                    ab.z += __shfl_xor_sync(0xffffffffu, ab.z, 16); ab.w += __shfl_xor_sync(0xffffffffu, ab.w, 16);
+                    as.x += __shfl_xor_sync(0xffffffffu, as.x, 16); as.y += __shfl_xor_sync(0xffffffffu, as.y, 16);
+                    as.z += __shfl_xor_sync(0xffffffffu, as.z, 16); as.w += __shfl_xor_sync(0xffffffffu, as.w, 16);
+                    if (lane < 16) {
+                        atomicAdd(&s_acc[4 * l], ag.x); atomicAdd(&s_acc[4 * l + 1], ag.y); atomicAdd(&s_acc[4 * l + 2], ag.z); atomicAdd(&s_acc[4 * l + 3], ag.w);
+                        atomicAdd(&s_acc[64 + 4 * l], ab.x); atomicAdd(&s_acc[64 + 4 * l + 1], ab.y); atomicAdd(&s_acc[64 + 4 * l + 2], ab.z); atomicAdd(&s_acc[64 + 4 * l + 3], ab.w);
+                        atomicAdd(&s_acc[128 + 4 * l], as.x); atomicAdd(&s_acc[128 + 4 * l + 1], as.y); atomicAdd(&s_acc[128 + 4 * l + 2], as.z); atomicAdd(&s_acc[128 + 4 * l + 3], as.w);
+                    }
+                } else if (p.d == DP) {
                     // (prefetching these loads into registers before the previous pair's output phase was measured: slower,
                     // the 64 extra live registers spill)
                     float4 v[16];
@@ -353,7 +440,9 @@ __global__ void __launch_bounds__(Cfg<NT>::kThreads, 3 - NT) ffn_tc_dgrad_kernel
                     const int64_t rg = row0 + r;
                     if (rg < p.M) {
                         const float4 o = *reinterpret_cast<const float4*>(img_s + r * 128 + ((c4 ^ (r & 7)) << 4));
-                        const float4 z4 = __ldg(reinterpret_cast<const float4*>(p.dz + rg * DP + 32 * wg) + c4);
+                        // plain load: with LNF the row was written by this CTA's loader (ordered by the mbarrier chain x_full -> y_full)
+                        const float4 z4 = LNF ? *(reinterpret_cast<const float4*>(p.dz + rg * DP + 32 * wg) + c4)
+                                              : __ldg(reinterpret_cast<const float4*>(p.dz + rg * DP + 32 * wg) + c4);
                         reinterpret_cast<float4*>(p.dy1 + rg * DP + 32 * wg)[c4] = make_float4(o.x + z4.x, o.y + z4.y, o.z + z4.z, o.w + z4.w);
                     }
                 }
@@ -370,15 +459,43 @@ __global__ void __launch_bounds__(Cfg<NT>::kThreads, 3 - NT) ffn_tc_dgrad_kernel
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 1) tc::tmem_dealloc<C_::kTmemCols>(tmem);
+    if (LNF && threadIdx.x < 192) {
+        float* dst = threadIdx.x < 64 ? p.dgamma2 : (threadIdx.x < 128 ? p.dbeta2 : p.db2);
+        atomicAdd(dst + (threadIdx.x & 63), s_acc[threadIdx.x]);
+    }
 }
 
 }  // namespace
 
 // internal launch used by u2gnn_ffn_tc_bwd (ffn_tc_bwd.cu)
+struct FfnLnBwd {       // LayerNorm2 backward inputs / outputs of the fused entry point (ffn_tc_bwd.cu)
+    const float* dy2;
+    const float* z2;
+    const float* st2;
+    const float* gamma2;
+    uint32_t stream_out;
+    float* dgamma2;
+    float* dbeta2;
+    float* db2;
+};
+
 int ffn_tc_dgrad_launch(const float* y1, const float* df, const float* dz, float* dy1, int64_t M, int d, int ff,
-                        const void* packed, uint64_t seed, uint32_t stream_hidden, int thr, void* xb, void* fb, cudaStream_t st) {
+                        const void* packed, uint64_t seed, uint32_t stream_hidden, int thr, void* xb, void* fb, cudaStream_t st,
+                        const FfnLnBwd* ln) {
     Params p;
     p.y1 = y1; p.df = df; p.dz = dz; p.dy1 = dy1; p.M = M; p.d = d; p.ff = ff;
+    p.dy2 = p.z2 = p.st2 = p.gamma2 = nullptr;
+    p.dgamma2 = p.dbeta2 = p.db2 = nullptr;
+    p.keys3 = rng_keys(seed, 0);
+    p.scale3 = thr ? rng_keep_scale(thr) : 1.0f;
+    if (ln) {
+        if (d != DP) return U2GNN_EUNSUPPORTED;
+        p.dy2 = ln->dy2; p.z2 = ln->z2; p.st2 = ln->st2; p.gamma2 = ln->gamma2;
+        p.keys3 = rng_keys(seed, ln->stream_out);
+        p.dgamma2 = ln->dgamma2; p.dbeta2 = ln->dbeta2; p.db2 = ln->db2;
+        p.df = nullptr;
+        p.dz = dy1;                                     // dz is parked in dy1 by the loader
+    }
     p.packed = static_cast<const uint8_t*>(packed);
     p.keys2 = rng_keys(seed, stream_hidden);
     p.thr = thr;
@@ -396,6 +513,7 @@ int ffn_tc_dgrad_launch(const float* y1, const float* df, const float* dz, float
         kern<<<(int)(n_groups < cap ? n_groups : cap), threads, smem, st>>>(p);
         return U2GNN_OK;
     };
+    if (ln) return launch(ffn_tc_dgrad_kernel<false, 2, true>, 2, Cfg<2>::kThreads, Cfg<2>::STAGES);
     if (p.trace) return launch(ffn_tc_dgrad_kernel<true, 2>, 2, Cfg<2>::kThreads, Cfg<2>::STAGES);
     return launch(ffn_tc_dgrad_kernel<false, 2>, 2, Cfg<2>::kThreads, Cfg<2>::STAGES);
 }
