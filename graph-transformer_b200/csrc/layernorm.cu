@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict
 }
 
 template <int LPR>
-__global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+__global__ void __launch_bounds__(256, 4) ln_bwd_vec_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                                                          const float* __restrict__ stats, int64_t M,
                                                          const float* __restrict__ gamma, DropRng rng, int low,
                                                          float* __restrict__ dz, void* __restrict__ da_, int da_bf16,
@@ -226,39 +226,53 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict
     const float4 g4 = reinterpret_cast<const float4*>(gamma)[l];
     const float inv_d = 1.0f / (float)D;
     float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t r0 = warp * RPW; r0 < M; r0 += nwarps * RPW) {
-        const int64_t r = r0 + sub;
-        const bool ok = r < M;
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f), x = g;
-        float mean = 0.f, rstd = 0.f;
-        if (ok) {
-            g = __ldg(reinterpret_cast<const float4*>(dy + r * D) + l);
-            x = __ldg(reinterpret_cast<const float4*>(z + r * D) + l);
-            mean = stats[2 * r];
-            rstd = stats[2 * r + 1];
+    // two row groups per iteration: the loads of both (dy, z, stats) are in flight together (one group per iteration kept
+    // 32 KB outstanding per SM at 32 resident warps - below what the HBM latency x bandwidth product needs)
+    constexpr int UNR = 2;
+    for (int64_t r0 = warp * (UNR * RPW); r0 < M; r0 += nwarps * (UNR * RPW)) {
+        float4 gk[UNR], xk[UNR];
+        float mk[UNR], sk[UNR];
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) {
+            const int64_t r = r0 + k * RPW + sub;
+            gk[k] = xk[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            mk[k] = sk[k] = 0.f;
+            if (r < M) {
+                gk[k] = __ldg(reinterpret_cast<const float4*>(dy + r * D) + l);
+                xk[k] = __ldg(reinterpret_cast<const float4*>(z + r * D) + l);
+                mk[k] = stats[2 * r];
+                sk[k] = stats[2 * r + 1];
+            }
         }
-        const float4 xh = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd, (x.w - mean) * rstd);
-        const float4 dh = make_float4(g.x * g4.x, g.y * g4.y, g.z * g4.z, g.w * g4.w);
-        ag.x = fmaf(g.x, xh.x, ag.x); ag.y = fmaf(g.y, xh.y, ag.y); ag.z = fmaf(g.z, xh.z, ag.z); ag.w = fmaf(g.w, xh.w, ag.w);
-        ab.x += g.x; ab.y += g.y; ab.z += g.z; ab.w += g.w;
-        const float m1 = group_sum<LPR>((dh.x + dh.y) + (dh.z + dh.w)) * inv_d;
-        const float m2 = group_sum<LPR>((dh.x * xh.x + dh.y * xh.y) + (dh.z * xh.z + dh.w * xh.w)) * inv_d;
-        if (ok) {
-            const float4 o = make_float4(rstd * (dh.x - m1 - xh.x * m2), rstd * (dh.y - m1 - xh.y * m2),
-                                         rstd * (dh.z - m1 - xh.z * m2), rstd * (dh.w - m1 - xh.w * m2));
-            reinterpret_cast<float4*>(dz + r * D)[l] = o;
-            if (da || dasum) {
-                const float4 m = drop4(rng, low, (uint64_t)(r * D + 4 * l), o);
-                if (!da) {
-                } else if (da_bf16) {      // consumers are tensor-core kernels that round on load: round once here, half the bytes
-                    uint2 w;
-                    w.x = cvt_bf16x2(m.x, m.y);
-                    w.y = cvt_bf16x2(m.z, m.w);
-                    reinterpret_cast<uint2*>(static_cast<uint16_t*>(da_) + r * D)[l] = w;
-                } else {
-                    reinterpret_cast<float4*>(da + r * D)[l] = m;
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) {
+            const int64_t r = r0 + k * RPW + sub;
+            const bool ok = r < M;
+            const float4 g = gk[k], x = xk[k];
+            const float mean = mk[k], rstd = sk[k];
+            const float4 xh = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd, (x.w - mean) * rstd);
+            const float4 dh = make_float4(g.x * g4.x, g.y * g4.y, g.z * g4.z, g.w * g4.w);
+            ag.x = fmaf(g.x, xh.x, ag.x); ag.y = fmaf(g.y, xh.y, ag.y); ag.z = fmaf(g.z, xh.z, ag.z); ag.w = fmaf(g.w, xh.w, ag.w);
+            ab.x += g.x; ab.y += g.y; ab.z += g.z; ab.w += g.w;
+            const float m1 = group_sum<LPR>((dh.x + dh.y) + (dh.z + dh.w)) * inv_d;
+            const float m2 = group_sum<LPR>((dh.x * xh.x + dh.y * xh.y) + (dh.z * xh.z + dh.w * xh.w)) * inv_d;
+            if (ok) {
+                const float4 o = make_float4(rstd * (dh.x - m1 - xh.x * m2), rstd * (dh.y - m1 - xh.y * m2),
+                                             rstd * (dh.z - m1 - xh.z * m2), rstd * (dh.w - m1 - xh.w * m2));
+                reinterpret_cast<float4*>(dz + r * D)[l] = o;
+                if (da || dasum) {
+                    const float4 m = drop4(rng, low, (uint64_t)(r * D + 4 * l), o);
+                    if (!da) {
+                    } else if (da_bf16) {      // consumers are tensor-core kernels that round on load: round once here, half the bytes
+                        uint2 w;
+                        w.x = cvt_bf16x2(m.x, m.y);
+                        w.y = cvt_bf16x2(m.z, m.w);
+                        reinterpret_cast<uint2*>(static_cast<uint16_t*>(da_) + r * D)[l] = w;
+                    } else {
+                        reinterpret_cast<float4*>(da + r * D)[l] = m;
+                    }
+                    as.x += m.x; as.y += m.y; as.z += m.z; as.w += m.w;
                 }
-                as.x += m.x; as.y += m.y; as.z += m.z; as.w += m.w;
             }
         }
     }

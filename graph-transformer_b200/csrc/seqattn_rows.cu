@@ -45,6 +45,58 @@ __device__ __forceinline__ void axpy_row(float (&acc)[D], float s, const float* 
     }
 }
 
+// ---- element-type helpers for the last-timestep kernels: qkv / dqkv either fp32 or bf16 (BF) row-major
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack_bf2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+// four consecutive elements starting at element offset `off` (multiple of 4)
+template <bool BF>
+__device__ __forceinline__ float4 ld4(const void* __restrict__ base, int64_t off) {
+    if (BF) {
+        const uint2 w = __ldg(reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(base) + off));
+        return make_float4(bf_lo(w.x), bf_hi(w.x), bf_lo(w.y), bf_hi(w.y));
+    }
+    return __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(base) + off));
+}
+template <bool BF>
+__device__ __forceinline__ void st4(void* __restrict__ base, int64_t off, float4 v) {
+    if (BF) *reinterpret_cast<uint2*>(static_cast<uint16_t*>(base) + off) = make_uint2(pack_bf2(v.x, v.y), pack_bf2(v.z, v.w));
+    else *reinterpret_cast<float4*>(static_cast<float*>(base) + off) = v;
+}
+template <int D, bool BF>
+__device__ __forceinline__ float dot_row_t(const float (&a)[D], const void* __restrict__ base, int64_t off) {
+    if (!BF) return dot_row<D>(a, static_cast<const float*>(base) + off);
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll
+    for (int c = 0; c < D; c += 8) {
+        const uint4 w = *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(base) + off + c);
+        acc0 = fmaf(a[c], bf_lo(w.x), acc0);     acc1 = fmaf(a[c + 1], bf_hi(w.x), acc1);
+        acc2 = fmaf(a[c + 2], bf_lo(w.y), acc2); acc3 = fmaf(a[c + 3], bf_hi(w.y), acc3);
+        acc0 = fmaf(a[c + 4], bf_lo(w.z), acc0); acc1 = fmaf(a[c + 5], bf_hi(w.z), acc1);
+        acc2 = fmaf(a[c + 6], bf_lo(w.w), acc2); acc3 = fmaf(a[c + 7], bf_hi(w.w), acc3);
+    }
+    return (acc0 + acc1) + (acc2 + acc3);
+}
+template <int D, bool BF>
+__device__ __forceinline__ void axpy_row_t(float (&acc)[D], float s, const void* __restrict__ base, int64_t off) {
+    if (!BF) {
+        axpy_row<D>(acc, s, static_cast<const float*>(base) + off);
+        return;
+    }
+#pragma unroll
+    for (int c = 0; c < D; c += 8) {
+        const uint4 w = *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(base) + off + c);
+        acc[c] = fmaf(s, bf_lo(w.x), acc[c]);         acc[c + 1] = fmaf(s, bf_hi(w.x), acc[c + 1]);
+        acc[c + 2] = fmaf(s, bf_lo(w.y), acc[c + 2]); acc[c + 3] = fmaf(s, bf_hi(w.y), acc[c + 3]);
+        acc[c + 4] = fmaf(s, bf_lo(w.z), acc[c + 4]); acc[c + 5] = fmaf(s, bf_hi(w.z), acc[c + 5]);
+        acc[c + 6] = fmaf(s, bf_lo(w.w), acc[c + 6]); acc[c + 7] = fmaf(s, bf_hi(w.w), acc[c + 7]);
+    }
+}
+
 // cooperative copy of `rows` rows of width D (fp32) from a strided global matrix into padded shared memory
 template <int D, int NT>
 __device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ src, int64_t src_ld, int rows, int tid) {
@@ -220,23 +272,23 @@ __global__ void __launch_bounds__(NT) seqattn_rows_bwd_kernel(const float* __res
 // ---- last timestep of a U2GNN layer (dead-row elimination): only query position 0 of every node is live.
 //      One thread per node; K / V rows are read straight from global memory (each thread streams its node's
 //      contiguous [S, 3D] block), scores live in a per-thread shared-memory scratch row.
-template <int D, int NT>
-__global__ void __launch_bounds__(NT) seqattn_last_fwd_kernel(const float* __restrict__ qkv, int64_t B, int S, AttnRng rng,
+template <int D, int NT, bool BF>      // BF: qkv stored as bf16 (rounded once by the projection that produced it)
+__global__ void __launch_bounds__(NT) seqattn_last_fwd_kernel(const void* __restrict__ qkv, int64_t B, int S, AttnRng rng,
                                                               float* __restrict__ ctx) {
     __shared__ float Ps[NT * PP];
     float* pr = Ps + threadIdx.x * PP;
     const float qscale = sqrtf(1.0f / (float)D);
     for (int64_t b = (int64_t)blockIdx.x * NT + threadIdx.x; b < B; b += (int64_t)gridDim.x * NT) {
-        const float* base = qkv + b * S * 3 * D;
+        const int64_t base = b * S * 3 * D;                    // element offset of the node's [S, 3D] block
         float a[D];
 #pragma unroll
         for (int c = 0; c < D; c += 4) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(base + c));
+            const float4 v = ld4<BF>(qkv, base + c);
             a[c] = v.x * qscale; a[c + 1] = v.y * qscale; a[c + 2] = v.z * qscale; a[c + 3] = v.w * qscale;
         }
         float m = -INFINITY;
         for (int j = 0; j < S; ++j) {
-            const float s = dot_row<D>(a, base + (int64_t)j * 3 * D + D);
+            const float s = dot_row_t<D, BF>(a, qkv, base + (int64_t)j * 3 * D + D);
             pr[j] = s;
             m = fmaxf(m, s);
         }
@@ -251,7 +303,7 @@ __global__ void __launch_bounds__(NT) seqattn_last_fwd_kernel(const float* __res
         for (int c = 0; c < D; ++c) a[c] = 0.f;
         for (int j = 0; j < S; ++j) {
             const float pd = (pr[j] * inv) * rng_dropout_mult(rng.keys, (uint64_t)b * (uint64_t)S + (uint64_t)j, rng.thr, rng.scale);
-            axpy_row<D>(a, pd, base + (int64_t)j * 3 * D + 2 * D);
+            axpy_row_t<D, BF>(a, pd, qkv, base + (int64_t)j * 3 * D + 2 * D);
         }
         float4* out = reinterpret_cast<float4*>(ctx + b * D);
 #pragma unroll
@@ -263,9 +315,9 @@ __global__ void __launch_bounds__(NT) seqattn_last_fwd_kernel(const float* __res
 // lane = four feature columns: every K / V row is ONE coalesced 256-byte read per half-warp and every dK / dV / dQ row
 // one coalesced 256-byte write (the thread-per-node version wrote each node's 13 KB from a single thread and reached
 // 14 % of the HBM roofline).  Scores and dP are reduced across the 16 lanes with shuffles and kept in registers.
-template <int D, int NT>
-__global__ void __launch_bounds__(NT) seqattn_last_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dctx,
-                                                              int64_t B, int S, AttnRng rng, int low, float* __restrict__ dqkv) {
+template <int D, int NT, bool BF>      // BF: qkv AND dqkv stored as bf16 (their other producers / consumers are tensor-core GEMMs)
+__global__ void __launch_bounds__(NT) seqattn_last_bwd_kernel(const void* __restrict__ qkv, const float* __restrict__ dctx,
+                                                              int64_t B, int S, AttnRng rng, int low, void* __restrict__ dqkv) {
     static_assert(D == 64 || D == 32, "lane = 4 feature columns");
     constexpr int LPN = D / 4;                                        // lanes per node (16: half a warp, 8: a quarter)
     constexpr int NPW = 32 / LPN;                                     // nodes per warp
@@ -281,9 +333,8 @@ __global__ void __launch_bounds__(NT) seqattn_last_bwd_kernel(const float* __res
     for (int64_t b0 = hw; b0 < B_pad; b0 += n_hw) {
         const bool live = b0 < B;
         const int64_t b = live ? b0 : B - 1;
-        const float* base = qkv + b * S * 3 * D;
-        float* gout = dqkv + b * S * 3 * D;
-        float4 q = __ldg(reinterpret_cast<const float4*>(base) + hl);
+        const int64_t base = b * S * 3 * D;                    // element offset of the node's [S, 3D] block (qkv and dqkv)
+        float4 q = ld4<BF>(qkv, base + 4 * hl);
         q.x *= qscale; q.y *= qscale; q.z *= qscale; q.w *= qscale;
         const float4 g = __ldg(reinterpret_cast<const float4*>(dctx + b * D) + hl);
         float pr[32], dr[32];
@@ -293,8 +344,8 @@ __global__ void __launch_bounds__(NT) seqattn_last_bwd_kernel(const float* __res
             pr[j] = -INFINITY;
             dr[j] = 0.f;
             if (j < S) {
-                const float4 k = __ldg(reinterpret_cast<const float4*>(base + (int64_t)j * 3 * D + D) + hl);
-                const float4 v = __ldg(reinterpret_cast<const float4*>(base + (int64_t)j * 3 * D + 2 * D) + hl);
+                const float4 k = ld4<BF>(qkv, base + (int64_t)j * 3 * D + D + 4 * hl);
+                const float4 v = ld4<BF>(qkv, base + (int64_t)j * 3 * D + 2 * D + 4 * hl);
                 pr[j] = reduce16(q.x * k.x + q.y * k.y + q.z * k.z + q.w * k.w);
                 dr[j] = reduce16(g.x * v.x + g.y * v.y + g.z * v.z + g.w * v.w);
                 m = fmaxf(m, pr[j]);
@@ -331,34 +382,34 @@ __global__ void __launch_bounds__(NT) seqattn_last_bwd_kernel(const float* __res
             if (j < S) {
                 const float ds = pr[j] * (dr[j] - tsum);
                 const float pd = pr[j] * (((keep_bits >> j) & 1u) ? dscale : 0.0f);
-                const float4 k = __ldg(reinterpret_cast<const float4*>(base + (int64_t)j * 3 * D + D) + hl);
+                const float4 k = ld4<BF>(qkv, base + (int64_t)j * 3 * D + D + 4 * hl);
                 dq.x = fmaf(ds, k.x, dq.x); dq.y = fmaf(ds, k.y, dq.y); dq.z = fmaf(ds, k.z, dq.z); dq.w = fmaf(ds, k.w, dq.w);
                 if (live) {
-                    float4* row = reinterpret_cast<float4*>(gout + (int64_t)j * 3 * D);
-                    if (j > 0) row[hl] = make_float4(0.f, 0.f, 0.f, 0.f);                                  // rows without a query
-                    row[LPN + hl] = make_float4(ds * q.x, ds * q.y, ds * q.z, ds * q.w);                  // q already carries sqrt(1/d)
-                    row[2 * LPN + hl] = make_float4(pd * g.x, pd * g.y, pd * g.z, pd * g.w);
+                    const int64_t row = base + (int64_t)j * 3 * D + 4 * hl;
+                    if (j > 0) st4<BF>(dqkv, row, make_float4(0.f, 0.f, 0.f, 0.f));                        // rows without a query
+                    st4<BF>(dqkv, row + D, make_float4(ds * q.x, ds * q.y, ds * q.z, ds * q.w));          // q already carries sqrt(1/d)
+                    st4<BF>(dqkv, row + 2 * D, make_float4(pd * g.x, pd * g.y, pd * g.z, pd * g.w));
                 }
             }
         }
-        if (live) reinterpret_cast<float4*>(gout)[hl] = make_float4(dq.x * qscale, dq.y * qscale, dq.z * qscale, dq.w * qscale);
+        if (live) st4<BF>(dqkv, base + 4 * hl, make_float4(dq.x * qscale, dq.y * qscale, dq.z * qscale, dq.w * qscale));
     }
 }
 
-template <int D>
-int launch_last_fwd(const float* qkv, int64_t B, int S, AttnRng rng, float* ctx, cudaStream_t st) {
+template <int D, bool BF = false>
+int launch_last_fwd(const void* qkv, int64_t B, int S, AttnRng rng, float* ctx, cudaStream_t st) {
     constexpr int NT = 128;
     const int64_t blocks = (B + NT - 1) / NT;
     const int grid = (int)(blocks < (int64_t)U2GNN_NUM_SMS * 8 ? blocks : (int64_t)U2GNN_NUM_SMS * 8);
-    seqattn_last_fwd_kernel<D, NT><<<grid, NT, 0, st>>>(qkv, B, S, rng, ctx);
+    seqattn_last_fwd_kernel<D, NT, BF><<<grid, NT, 0, st>>>(qkv, B, S, rng, ctx);
     return 1;
 }
-template <int D>
-int launch_last_bwd(const float* qkv, const float* dctx, int64_t B, int S, AttnRng rng, float* dqkv, cudaStream_t st) {
+template <int D, bool BF = false>
+int launch_last_bwd(const void* qkv, const float* dctx, int64_t B, int S, AttnRng rng, void* dqkv, cudaStream_t st) {
     constexpr int NT = 256;
     const int64_t blocks = (B * (D / 4) + NT - 1) / NT;
     const int grid = (int)(blocks < (int64_t)U2GNN_NUM_SMS * 8 ? blocks : (int64_t)U2GNN_NUM_SMS * 8);
-    seqattn_last_bwd_kernel<D, NT><<<grid, NT, 0, st>>>(qkv, dctx, B, S, rng, rng_thr_low(rng.thr), dqkv);
+    seqattn_last_bwd_kernel<D, NT, BF><<<grid, NT, 0, st>>>(qkv, dctx, B, S, rng, rng_thr_low(rng.thr), dqkv);
     return 1;
 }
 
@@ -428,4 +479,33 @@ int seqattn_rows_try_bwd(const float* qkv, const float* dctx, int64_t B, int S, 
     if (d == 64) return launch_bwd<64>(qkv, dctx, B, S, rng, dqkv, st);
     if (d == 32) return launch_bwd<32>(qkv, dctx, B, S, rng, dqkv, st);
     return 0;
+}
+
+// Last-timestep attention (only query position 0 of every node live) with qkv / dqkv optionally stored as bf16: in the bf16
+// mode their producer (in_proj GEMM) and consumers (in_proj weight / input gradient GEMMs) are tensor-core kernels, so the
+// [N*S, 3d] tensors cross HBM at half the bytes.  ctx / dctx ([N, d], one row per node) stay fp32.
+extern "C" int u2gnn_seqattn_last_fwd_ex(const void* qkv, int qkv_bf16, int64_t B, int S, int d, uint64_t seed, uint32_t rng_stream,
+                                         int thr, float* ctx, u2gnn_stream_t stream) {
+    if (!qkv || !ctx || B < 0 || S < 2 || S > 32 || thr < 0 || thr > 255) return U2GNN_EINVAL;
+    if (d != 64 && d != 32) return U2GNN_EUNSUPPORTED;
+    if (!aligned16(qkv) || !aligned16(ctx)) return U2GNN_EALIGN;
+    if (B == 0) return U2GNN_OK;
+    const AttnRng rng = make_rng(seed, rng_stream, thr);
+    cudaStream_t st = as_stream(stream);
+    if (d == 64) qkv_bf16 ? launch_last_fwd<64, true>(qkv, B, S, rng, ctx, st) : launch_last_fwd<64, false>(qkv, B, S, rng, ctx, st);
+    else qkv_bf16 ? launch_last_fwd<32, true>(qkv, B, S, rng, ctx, st) : launch_last_fwd<32, false>(qkv, B, S, rng, ctx, st);
+    U2GNN_CHECK_LAUNCH();
+}
+
+extern "C" int u2gnn_seqattn_last_bwd_ex(const void* qkv, const float* dctx, int io_bf16, int64_t B, int S, int d, uint64_t seed,
+                                         uint32_t rng_stream, int thr, void* dqkv, u2gnn_stream_t stream) {
+    if (!qkv || !dctx || !dqkv || B < 0 || S < 2 || S > 32 || thr < 0 || thr > 255) return U2GNN_EINVAL;
+    if (d != 64 && d != 32) return U2GNN_EUNSUPPORTED;
+    if (!aligned16(qkv) || !aligned16(dctx) || !aligned16(dqkv)) return U2GNN_EALIGN;
+    if (B == 0) return U2GNN_OK;
+    const AttnRng rng = make_rng(seed, rng_stream, thr);
+    cudaStream_t st = as_stream(stream);
+    if (d == 64) io_bf16 ? launch_last_bwd<64, true>(qkv, dctx, B, S, rng, dqkv, st) : launch_last_bwd<64, false>(qkv, dctx, B, S, rng, dqkv, st);
+    else io_bf16 ? launch_last_bwd<32, true>(qkv, dctx, B, S, rng, dqkv, st) : launch_last_bwd<32, false>(qkv, dctx, B, S, rng, dqkv, st);
+    U2GNN_CHECK_LAUNCH();
 }

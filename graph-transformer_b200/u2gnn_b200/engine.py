@@ -32,6 +32,7 @@ FUSE_LN_BWD = os.environ.get("U2GNN_FUSE_EPILOGUES", "1") != "0"        # bf16 m
 # measured on B200 (73.1 against 71.2 ms per step): the dgrad kernel's row phase is exposed (nothing overlaps it), so the extra
 # load round trips and shuffles there cost more than the separate 64 %-of-HBM LayerNorm pass they replace.  Off by default.
 FUSE_LN2_FFN_BWD = os.environ.get("U2GNN_FUSE_LN2", "0") != "0"
+LAST_STEP_BF16 = os.environ.get("U2GNN_LAST_BF16", "1") != "0"            # bf16 mode, d = 64: bf16 qkv / dqkv at the dead-row-eliminated last timestep
 FLOPS = {}    # entry point -> algorithmic flops issued while LIB.timed is active (bench.py roofline)
 
 
@@ -288,8 +289,9 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
     sv = LayerSaved(x=x, B=B, S=S, Sq=Sq)
     tc_proj = precision == "bf16" and not long_seq and d <= 64
     tc_attn = tc_proj and d == 64 and Sq == S and S >= 2        # tensor-core attention core: bf16 qkv / ctx between the kernels
+    tc_last = tc_proj and d == 64 and Sq == 1 and S >= 2 and LAST_STEP_BF16     # last timestep: bf16 qkv / dqkv around the position-0 attention
     if tc_proj:
-        qkv = linear_tc(x, M, d, p["self_attn.in_proj_weight"], 0, 3 * d, bias=p["self_attn.in_proj_bias"], out_bf16=tc_attn)
+        qkv = linear_tc(x, M, d, p["self_attn.in_proj_weight"], 0, 3 * d, bias=p["self_attn.in_proj_bias"], out_bf16=tc_attn or tc_last)
     else:
         qkv = torch.empty((M, 3 * d), **f32)
         sgemm(0, 1, M, 3 * d, d, x, d, p["self_attn.in_proj_weight"], d, qkv, 3 * d, bias=p["self_attn.in_proj_bias"])
@@ -304,6 +306,8 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
         sv.probs, sv.pd = scores, pd
     elif tc_attn:
         LIB.call("u2gnn_seqattn_tc_fwd_ex", _ptr(qkv), B, S, d, seed, drop_ids[0], thr, _ptr(ctx), 1, _stream())
+    elif tc_last:
+        LIB.call("u2gnn_seqattn_last_fwd_ex", _ptr(qkv), 1, B, S, d, seed, drop_ids[0], thr, _ptr(ctx), _stream())
     else:
         LIB.call("u2gnn_seqattn_fwd", _ptr(qkv), B, S, Sq, d, seed, drop_ids[0], thr, _ptr(ctx), _stream())
     if tc_proj and d == 64 and FUSE_OUT_PROJ_LN:
@@ -428,7 +432,8 @@ def _encoder_attn_bwd(dy1, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
         wgrad(da, Mq, d, sv.ctx, d, g["self_attn.out_proj.weight"], g["self_attn.out_proj.bias"])
         dctx = torch.empty((Mq, d), **f32)
         sgemm(0, 0, Mq, d, d, da, d, p["self_attn.out_proj.weight"], d, dctx, d)
-    dqkv = torch.empty((M, 3 * d), dtype=torch.bfloat16 if tc_attn else torch.float32, device=dev)
+    tc_last = sv.qkv.dtype == torch.bfloat16 and Sq == 1
+    dqkv = torch.empty((M, 3 * d), dtype=torch.bfloat16 if (tc_attn or tc_last) else torch.float32, device=dev)
     if long_seq:
         scale = math.sqrt(1.0 / d)
         dpd = torch.empty((S, S), **f32)
@@ -439,6 +444,8 @@ def _encoder_attn_bwd(dy1, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
         sgemm(1, 0, S, d, S, dpd, S, sv.qkv, 3 * d, dqkv, 3 * d, alpha=scale, c_off=d)     # dk = ds^T @ q * scale
     elif tc_attn:
         LIB.call("u2gnn_seqattn_tc_bwd_ex", _ptr(sv.qkv), _ptr(dctx), B, S, d, seed, drop_ids[0], thr, _ptr(dqkv), 1, _stream())
+    elif tc_last:
+        LIB.call("u2gnn_seqattn_last_bwd_ex", _ptr(sv.qkv), _ptr(dctx), 1, B, S, d, seed, drop_ids[0], thr, _ptr(dqkv), _stream())
     else:
         LIB.call("u2gnn_seqattn_bwd", _ptr(sv.qkv), _ptr(dctx), B, S, Sq, d, seed, drop_ids[0], thr, _ptr(dqkv), _stream())
     if tc_proj:

@@ -258,6 +258,14 @@ int u2gnn_seqattn_tc_fwd_ex(const void* qkv, int64_t B, int S, int d, uint64_t s
 int u2gnn_seqattn_tc_bwd_ex(const void* qkv, const void* dctx, int64_t B, int S, int d, uint64_t seed,
                             uint32_t rng_stream, int thr, void* dqkv, int io_bf16, u2gnn_stream_t stream);
 
+/* last timestep of a U2GNN layer (only query position 0 of each node live): same contract as
+ * u2gnn_seqattn_fwd / _bwd with Sq = 1, with qkv (and dqkv) optionally stored as bf16 [B*S, 3d]; ctx / dctx are fp32 [B, d].
+ * d in {32, 64}, 2 <= S <= 32. */
+int u2gnn_seqattn_last_fwd_ex(const void* qkv, int qkv_bf16, int64_t B, int S, int d, uint64_t seed, uint32_t rng_stream,
+                              int thr, float* ctx, u2gnn_stream_t stream);
+int u2gnn_seqattn_last_bwd_ex(const void* qkv, const float* dctx, int io_bf16, int64_t B, int S, int d, uint64_t seed,
+                              uint32_t rng_stream, int thr, void* dqkv, u2gnn_stream_t stream);
+
 /* ---- device-side batch builder (replaces the host loop of get_batch_data,
         train_pytorch_U2GNN_Sup.py:91-119 / train_pytorch_U2GNN_UnSup.py:96-128).
         Dataset adjacency as one CSR over dataset-wide node ids (g_rowptr[V+1], g_col[E]); the batch is n_graphs selected

@@ -495,3 +495,30 @@ def test_ffn_bwd_with_fused_layernorm2_backward(U, M, ff, p):
     close = lambda a, b: (a - b).abs().max().item() <= 2e-4 * max(1.0, b.abs().max().item())
     assert close(dW1_1, dW1_0) and close(db1_1, db1_0) and close(dW2_1, dW2_0)
     assert close(db2_1, db2_0) and close(dg1, dg0) and close(db1, db0)
+
+
+@pytest.mark.parametrize("B,S,p", [(300, 17, 0.5), (77, 9, 0.0), (4099, 17, 0.5)])
+def test_seqattn_last_bf16_io_matches_fp32_io_on_rounded_inputs(U, B, S, p):
+    """Last-timestep attention (query position 0 only) with bf16 qkv / dqkv: forward equals the fp32-I/O kernel fed the
+    same rounded qkv bit for bit; dqkv equals the rounded fp32-I/O result."""
+    from u2gnn_b200 import engine as E
+    d = 64
+    thr = E.dropout_threshold(p)
+    g = torch.Generator(device="cuda").manual_seed(B * S)
+    qkv_b = torch.randn(B * S, 3 * d, device="cuda", generator=g).to(torch.bfloat16)
+    qkv_f = qkv_b.float()
+    dctx = torch.randn(B, d, device="cuda", generator=g)
+    SEED, ST = 99, 16
+    ctx0 = torch.empty(B, d, device="cuda"); ctx1 = torch.empty(B, d, device="cuda")
+    U.LIB.call("u2gnn_seqattn_last_fwd_ex", qkv_f.data_ptr(), 0, B, S, d, SEED, ST, thr, ctx0.data_ptr(), E._stream())
+    U.LIB.call("u2gnn_seqattn_last_fwd_ex", qkv_b.data_ptr(), 1, B, S, d, SEED, ST, thr, ctx1.data_ptr(), E._stream())
+    ref = torch.empty(B, d, device="cuda")
+    U.LIB.call("u2gnn_seqattn_fwd", qkv_f.data_ptr(), B, S, 1, d, SEED, ST, thr, ref.data_ptr(), E._stream())
+    dq0 = torch.empty(B * S, 3 * d, device="cuda")
+    dq1 = torch.empty(B * S, 3 * d, device="cuda", dtype=torch.bfloat16)
+    U.LIB.call("u2gnn_seqattn_last_bwd_ex", qkv_f.data_ptr(), dctx.data_ptr(), 0, B, S, d, SEED, ST, thr, dq0.data_ptr(), E._stream())
+    U.LIB.call("u2gnn_seqattn_last_bwd_ex", qkv_b.data_ptr(), dctx.data_ptr(), 1, B, S, d, SEED, ST, thr, dq1.data_ptr(), E._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(ctx0, ref)
+    assert torch.equal(ctx1, ctx0)
+    assert torch.equal(dq1, dq0.to(torch.bfloat16))
