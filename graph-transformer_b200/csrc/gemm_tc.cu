@@ -785,6 +785,212 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_wgrad_kernel(const WgradP
     if (warp == 0) tc::tmem_dealloc<256>(tmem);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Backward of one projection in ONE pass over its output gradient A[M, N1] (bf16, N1 = 64 ga):
+//     C[M, 64]   = A W (+ beta C)          input gradient   (W = the layer's weight [N1, 64], i.e. [K][N])
+//     dW[N1, 64] += A^T B,  db[N1] += colsum(A)             weight / bias gradient (B = the layer's input rows)
+// The rows GEMM reads the staged A tiles K-major and the weight-gradient GEMM reads the SAME tiles MN-major, so A crosses
+// HBM once instead of twice (in_proj: 384 of the 1 536 bytes per row the two separate kernels moved).  NS-stage ring,
+// loads NS-1 tiles ahead: A (and a bf16 B) via cp.async, an fp32 B through registers under the MMAs; the epilogue of tile i
+// (tensor memory -> staging -> coalesced stores, old C prefetched) runs while the loads of the next tiles are in flight.
+// TMEM: weight-gradient accumulators [0, 80 nacc), rows accumulator [192, 256).
+// ---------------------------------------------------------------------------------------------------------------
+struct BwdParams {
+    const void* A;        // [M, N1] bf16
+    const void* B;        // [M, 64] fp32 or bf16
+    int b_bf16, c_bf16;
+    int64_t M, lda, ldb, ldc;
+    int N1;
+    const float* W;       // [N1, 64]
+    void* C;              // [M, 64] fp32 (beta 0 / 1) or bf16 (beta 0)
+    float beta;
+    float* dW;            // [N1, 64]
+    float* db;            // [N1] or null
+};
+
+template <int NS>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_dgrad_wgrad_kernel(const BwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int ga = p.N1 / 64;
+    const int nacc = (ga + 1) / 2;
+    const uint32_t stage_bytes = (uint32_t)(ga + 1) * 16384;
+    uint8_t* sW = smem + NS * stage_bytes;                    // ga tiles of [64 (n) x 64 (k)] K-major: element (n, k) = W[k][n]
+    uint8_t* sOut = sW + ga * 8192;                           // [128 rows x 272 B] fp32 staging
+    uint8_t* sOnes = sOut + 128 * 272;
+    uint8_t* sZero = sOnes + 16384;
+    __shared__ uint64_t bar_mma[NS];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < NS; ++i) tc::mbar_init(&bar_mma[i], 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 0) tc::tmem_alloc<256>(&tmem_slot);
+    for (int e = tid; e < 16384 / 4; e += kThreads) {
+        reinterpret_cast<uint32_t*>(sOnes)[e] = 0x3F803F80u;
+        reinterpret_cast<uint32_t*>(sZero)[e] = 0u;
+    }
+    for (int e = tid; e < p.N1 * 64; e += kThreads) {
+        const int k = e >> 6, n = e & 63;                     // consecutive threads read consecutive floats of W
+        *reinterpret_cast<__nv_bfloat16*>(sW + (k >> 6) * 8192 + tc::sw128_offset(n, k & 63)) = __float2bfloat16(p.W[e]);
+    }
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t tmem_rows = tmem + 192;
+    const uint32_t idesc_w = tc::make_idesc(128, 80, 1, 1);   // weight gradient: M = 128 A-columns, N = [B | ones], both MN-major
+    const uint32_t idesc_r = tc::make_idesc(TM, 64, 0, 0);    // rows: K-major A tiles and weights
+    const uint64_t w_desc = tc::make_desc_sw128(tc::smem_u32(sW), 16, 1024);
+    const int64_t n_tiles = (p.M + TM - 1) / TM;
+    const bool b_async = rows_async_ok(p.B, p.b_bf16, 64, p.ldb);
+    auto issue_async = [&](int64_t tile, uint8_t* st) {
+        stage_rows_async<kThreads>(st, p.A, tile * TM, p.M, p.N1, p.N1, p.lda, tid);
+        if (b_async) stage_rows_async<kThreads>(st + ga * 16384, p.B, tile * TM, p.M, 64, 64, p.ldb, tid);
+    };
+    auto finish_sync = [&](int64_t tile, uint8_t* st) {
+        if (!b_async) stage_rows_bf16<kThreads, 64>(st + ga * 16384, p.B, p.b_bf16, tile * TM, p.M, 64, 64, p.ldb, tid);
+    };
+    // prologue: tiles 0 .. NS-2 of this CTA
+#pragma unroll
+    for (int j = 0; j < NS - 1; ++j) {
+        const int64_t t = blockIdx.x + (int64_t)j * gridDim.x;
+        if (t < n_tiles) issue_async(t, smem + j * stage_bytes);
+        cp_async_commit();
+        if (t < n_tiles) finish_sync(t, smem + j * stage_bytes);
+    }
+    const int wq = warp & 3, half = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int s = (int)(it % NS), sp = (int)((it + NS - 1) % NS);
+        uint8_t* st = smem + s * stage_bytes;
+        uint8_t* st_pre = smem + sp * stage_bytes;
+        const int64_t row0 = tile * TM;
+        const int64_t nxt = tile + (int64_t)(NS - 1) * gridDim.x;
+        // stage sp was read by the MMAs of tile it-1; the epilogue of that tile has already waited for them
+        if (nxt < n_tiles) issue_async(nxt, st_pre);
+        cp_async_commit();
+        cp_async_wait<NS - 1>();                              // this thread's chunks of tile `it` have landed
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        __syncthreads();
+        tc::tc_fence_after();
+        if (warp == 0) {
+            if (tc::elect_one()) {
+                const uint32_t a0 = tc::smem_u32(st), b0 = tc::smem_u32(st + ga * 16384);
+                const uint64_t a_desc = tc::make_desc_sw128(a0, 16, 1024);
+                for (int ks = 0; ks < p.N1 / 16; ++ks)
+                    tc::mma_ss(tmem_rows, a_desc + (uint32_t)((ks >> 2) * 1024 + (ks & 3) * 2), w_desc + (uint32_t)((ks >> 2) * 512 + (ks & 3) * 2),
+                               idesc_r, ks > 0);
+                const uint64_t bd = tc::make_desc_sw128(b0, tc::smem_u32(sOnes) - b0, 1024);       // [B | ones]
+                for (int g = 0; g < nacc; ++g) {
+                    const uint32_t t0 = a0 + (uint32_t)(2 * g) * 16384;
+                    const bool second = (2 * g + 1 < ga);
+                    const uint32_t lbo = second ? 16384u : (tc::smem_u32(sZero) - t0);
+                    const uint64_t ad = tc::make_desc_sw128(t0, lbo, 1024);
+                    for (int ks = 0; ks < 8; ++ks) tc::mma_ss(tmem + 80 * g, ad + 128 * ks, bd + 128 * ks, idesc_w, (it > 0 || ks > 0));
+                }
+                tc::mma_commit(&bar_mma[s]);
+            }
+            __syncwarp();
+        }
+        // old C rows of this tile (beta), requested before the fp32 operand of the prefetched tile and the MMA wait
+        float4 pre[8];
+        const bool use_old = p.beta != 0.0f && !p.c_bf16;
+        if (use_old) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = u * kThreads + tid;
+                const int64_t row = row0 + (e >> 4);
+                pre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < p.M) pre[u] = *(reinterpret_cast<const float4*>(static_cast<const float*>(p.C) + row * p.ldc) + (e & 15));
+            }
+        }
+        if (nxt < n_tiles) finish_sync(nxt, st_pre);
+        tc::mbar_wait(&bar_mma[s], (uint32_t)((it / NS) & 1));
+        tc::tc_fence_after();
+        {
+            uint32_t v[32];
+            tc::tmem_ld32(tmem_rows + lane_base + 32 * half, v);
+            tc::tmem_ld_wait();
+            uint8_t* srow = sOut + (wq * 32 + lane) * 272;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int J = 8 * half + j;
+                const int pos = p.c_bf16 ? ((J >> 1) + 8 * (J & 1)) : J;      // bf16 copy-out: pieces (2c, 2c+1) at (c, 8 + c)
+                *reinterpret_cast<float4*>(srow + 16 * pos) = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                          __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            }
+        }
+        tc::tc_fence_before();
+        __syncthreads();
+        if (p.c_bf16) {
+            const int c8 = tid & 7;
+            float4 o0[4], o1[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int rr = (u * kThreads + tid) >> 3;
+                o0[u] = *reinterpret_cast<const float4*>(sOut + rr * 272 + 16 * c8);
+                o1[u] = *reinterpret_cast<const float4*>(sOut + rr * 272 + 128 + 16 * c8);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t row = row0 + ((u * kThreads + tid) >> 3);
+                if (row < p.M) {
+                    uint4 w;
+                    w.x = epi::cvt2(o0[u].x, o0[u].y); w.y = epi::cvt2(o0[u].z, o0[u].w);
+                    w.z = epi::cvt2(o1[u].x, o1[u].y); w.w = epi::cvt2(o1[u].z, o1[u].w);
+                    *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + 8 * c8) = w;
+                }
+            }
+        } else {
+            const int c4 = tid & 15;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int rr = (u * kThreads + tid) >> 4;
+                const int64_t row = row0 + rr;
+                float4 r = *reinterpret_cast<const float4*>(sOut + rr * 272 + 16 * c4);
+                if (row >= p.M) continue;
+                if (use_old) { r.x += pre[u].x; r.y += pre[u].y; r.z += pre[u].z; r.w += pre[u].w; }
+                *(reinterpret_cast<float4*>(static_cast<float*>(p.C) + row * p.ldc) + c4) = r;
+            }
+        }
+        __syncthreads();                                      // staging reused by the next tile
+    }
+    cp_async_wait<0>();
+    if (it >= 1) {
+        // every tile's MMAs were waited for by its epilogue: the accumulators are final
+        tc::tc_fence_after();
+        for (int g = half; g < nacc; g += 2) {
+            const int n1 = 128 * g + wq * 32 + lane;
+            uint32_t v[32];
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                tc::tmem_ld32(tmem + lane_base + 80 * g + c0, v);
+                tc::tmem_ld_wait();
+                if (n1 < p.N1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) atomicAdd(p.dW + (size_t)n1 * 64 + c0 + j, __uint_as_float(v[j]));
+                }
+            }
+            uint32_t b16[16];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                         : "=r"(b16[0]), "=r"(b16[1]), "=r"(b16[2]), "=r"(b16[3]), "=r"(b16[4]), "=r"(b16[5]), "=r"(b16[6]),
+                           "=r"(b16[7]), "=r"(b16[8]), "=r"(b16[9]), "=r"(b16[10]), "=r"(b16[11]), "=r"(b16[12]), "=r"(b16[13]),
+                           "=r"(b16[14]), "=r"(b16[15])
+                         : "r"(tmem + lane_base + 80 * g + 64)
+                         : "memory");
+            tc::tmem_ld_wait();
+            if (p.db && n1 < p.N1) atomicAdd(p.db + n1, __uint_as_float(b16[0]));
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<256>(tmem);
+}
+
 }  // namespace
 
 static int g_rows_ws = 0;
@@ -906,4 +1112,37 @@ extern "C" int u2gnn_gemm_tc_wgrad_ex(const void* A, int a_bf16, int64_t M, int 
 extern "C" int u2gnn_gemm_tc_wgrad(const float* A, int64_t M, int N1, int64_t lda, const float* B, int N2, int64_t ldb,
                                    float* dW, float* db, u2gnn_stream_t stream) {
     return u2gnn_gemm_tc_wgrad_ex(A, 0, M, N1, lda, B, 0, N2, ldb, dW, db, stream);
+}
+
+extern "C" int u2gnn_gemm_tc_dgrad_wgrad(const void* A, int64_t M, int N1, int64_t lda, const void* B, int b_bf16, int64_t ldb,
+                                         const float* W, void* C, int c_bf16, int64_t ldc, float beta, float* dW, float* db,
+                                         u2gnn_stream_t stream) {
+    if (!A || !B || !W || !C || !dW || M < 0 || N1 < 64 || lda < N1 || ldb < 64 || ldc < 64) return U2GNN_EINVAL;
+    if (c_bf16 && beta != 0.0f) return U2GNN_EINVAL;
+    if ((N1 & 63) || N1 > 256) return U2GNN_EUNSUPPORTED;
+    if ((lda & 7) || (ldc & 7) || (ldb & (b_bf16 ? 7 : 3))) return U2GNN_EALIGN;
+    if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) % 16) return U2GNN_EALIGN;
+    if (M == 0) return U2GNN_OK;
+    BwdParams p;
+    p.A = A; p.B = B; p.b_bf16 = b_bf16; p.c_bf16 = c_bf16; p.M = M; p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.N1 = N1;
+    p.W = W; p.C = C; p.beta = beta; p.dW = dW; p.db = db;
+    const int ga = N1 / 64;
+    const size_t fixed = 1024 + (size_t)ga * 8192 + 128 * 272 + 2 * 16384;
+    const size_t stage = (size_t)(ga + 1) * 16384;
+    const int64_t n_tiles = (M + TM - 1) / TM;
+    const int grid = (int)(n_tiles < U2GNN_NUM_SMS ? n_tiles : U2GNN_NUM_SMS);
+    auto launch = [&](auto kern, int ns) -> int {
+        const size_t smem = fixed + ns * stage;
+        if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, kThreads, smem, as_stream(stream)>>>(p);
+        return U2GNN_OK;
+    };
+    int rc;
+    const size_t cap = 227 * 1024 - 1024;                    // dynamic limit minus room for the static barriers
+    if (fixed + 4 * stage <= cap) rc = launch(gemm_tc_dgrad_wgrad_kernel<4>, 4);
+    else if (fixed + 3 * stage <= cap) rc = launch(gemm_tc_dgrad_wgrad_kernel<3>, 3);
+    else rc = launch(gemm_tc_dgrad_wgrad_kernel<2>, 2);
+    if (rc != U2GNN_OK) return rc;
+    U2GNN_CHECK_LAUNCH();
 }

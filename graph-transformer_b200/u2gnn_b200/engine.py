@@ -33,6 +33,7 @@ FUSE_LN_BWD = os.environ.get("U2GNN_FUSE_EPILOGUES", "1") != "0"        # bf16 m
 # load round trips and shuffles there cost more than the separate 64 %-of-HBM LayerNorm pass they replace.  Off by default.
 FUSE_LN2_FFN_BWD = os.environ.get("U2GNN_FUSE_LN2", "0") != "0"
 LAST_STEP_BF16 = os.environ.get("U2GNN_LAST_BF16", "1") != "0"            # bf16 mode, d = 64: bf16 qkv / dqkv at the dead-row-eliminated last timestep
+FUSE_PROJ_BWD = os.environ.get("U2GNN_FUSE_PROJ_BWD", "1") != "0"         # bf16 mode, d = 64: projection input + weight gradients in one pass over the output gradient
 FLOPS = {}    # entry point -> algorithmic flops issued while LIB.timed is active (bench.py roofline)
 
 
@@ -212,6 +213,18 @@ def wgrad_tc(dout, M, n_out, inp, n_in, dW, db=None):
         return
     LIB.call("u2gnn_gemm_tc_wgrad_ex", _ptr(dout), int(dout.dtype == torch.bfloat16), M, n_out, n_out, _ptr(inp),
              int(inp.dtype == torch.bfloat16), n_in, n_in, _ptr(dW), _ptr(db), _stream())
+
+
+def proj_bwd_tc(dout, M, n_out, inp, W, dW, db, out=None, out_bf16=False, beta=0.0):
+    """Backward of a projection y = inp W^T + b in one pass over dout[M, n_out] (bf16): returns dinp[M, 64] = dout W (+ beta*out)
+    and accumulates dW[n_out, 64] += dout^T inp, db += colsum(dout)."""
+    if out is None:
+        out = torch.empty((M, 64), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dout.device)
+    if LIB.timed is not None:
+        FLOPS["u2gnn_gemm_tc_dgrad_wgrad"] = FLOPS.get("u2gnn_gemm_tc_dgrad_wgrad", 0) + 4 * M * n_out * 64
+    LIB.call("u2gnn_gemm_tc_dgrad_wgrad", _ptr(dout), M, n_out, n_out, _ptr(inp), int(inp.dtype == torch.bfloat16), 64, _ptr(W),
+             _ptr(out), int(out.dtype == torch.bfloat16), 64, beta, _ptr(dW), _ptr(db), _stream())
+    return out
 
 
 def add_dropout_ln_fwd(res, a, M, d, drop, gamma, beta):
@@ -425,7 +438,12 @@ def _encoder_attn_bwd(dy1, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
     # da only feeds the two out_proj tensor-core GEMMs (weight gradient, input gradient): bf16, rounded once by its producer
     dz1, da = add_dropout_ln_bwd(dy1, sv.z1, sv.st1, Mq, d, p["norm1.weight"], (seed, drop_ids[1], thr),
                                  g["norm1.weight"], g["norm1.bias"], da_bf16=tc_proj and d == 64 and FUSE_LN_BWD)
-    if tc_proj:
+    fuse_bwd = tc_proj and d == 64 and FUSE_PROJ_BWD
+    if fuse_bwd and da.dtype == torch.bfloat16:
+        # out_proj backward: input gradient and weight gradient from one pass over da
+        dctx = proj_bwd_tc(da, Mq, d, sv.ctx, p["self_attn.out_proj.weight"], g["self_attn.out_proj.weight"],
+                           g["self_attn.out_proj.bias"], out_bf16=tc_attn)
+    elif tc_proj:
         wgrad_tc(da, Mq, d, sv.ctx, d, g["self_attn.out_proj.weight"], g["self_attn.out_proj.bias"])
         dctx = linear_tc(da, Mq, d, p["self_attn.out_proj.weight"], 1, d, out_bf16=tc_attn)
     else:
@@ -448,6 +466,15 @@ def _encoder_attn_bwd(dy1, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
         LIB.call("u2gnn_seqattn_last_bwd_ex", _ptr(sv.qkv), _ptr(dctx), 1, B, S, d, seed, drop_ids[0], thr, _ptr(dqkv), _stream())
     else:
         LIB.call("u2gnn_seqattn_bwd", _ptr(sv.qkv), _ptr(dctx), B, S, Sq, d, seed, drop_ids[0], thr, _ptr(dqkv), _stream())
+    if fuse_bwd and need_dx and dqkv.dtype == torch.bfloat16:
+        # in_proj backward in one pass over dqkv; the residual gradient dz1 is the old C of the epilogue when every row is live
+        if Sq == S:
+            return proj_bwd_tc(dqkv, M, 3 * d, sv.x, p["self_attn.in_proj_weight"], g["self_attn.in_proj_weight"],
+                               g["self_attn.in_proj_bias"], out=dz1, beta=1.0)
+        dx = proj_bwd_tc(dqkv, M, 3 * d, sv.x, p["self_attn.in_proj_weight"], g["self_attn.in_proj_weight"],
+                         g["self_attn.in_proj_bias"])
+        copy_rows(dz1, d, dx, S * d, B, d, accumulate=True)
+        return dx
     if tc_proj:
         wgrad_tc(dqkv, M, 3 * d, sv.x, d, g["self_attn.in_proj_weight"], g["self_attn.in_proj_bias"])
     else:

@@ -246,6 +246,13 @@ int u2gnn_gemm_tc_rows_ex(const void* A, int a_bf16, int64_t M, int K, int64_t l
                           const float* bias, float beta, void* C, int c_bf16, int64_t ldc, u2gnn_stream_t stream);
 int u2gnn_gemm_tc_wgrad_ex(const void* A, int a_bf16, int64_t M, int N1, int64_t lda, const void* B, int b_bf16, int N2,
                            int64_t ldb, float* dW, float* db, u2gnn_stream_t stream);
+/* backward of one attention-block projection in a single pass over its output gradient A[M,N1] (bf16; N1 = 64, 128, 192
+ * or 256): input gradient C[M,64] = A W (+ beta*C; W = the layer's weight [N1,64]; C fp32, or bf16 with beta 0) AND
+ * dW[N1,64] += A^T B, db[N1] += colsum(A) (B[M,64] = the layer's input rows, fp32 or bf16; db may be null).  Same results as
+ * u2gnn_gemm_tc_rows_ex(w_kn = 1) + u2gnn_gemm_tc_wgrad_ex on the same operands. */
+int u2gnn_gemm_tc_dgrad_wgrad(const void* A, int64_t M, int N1, int64_t lda, const void* B, int b_bf16, int64_t ldb,
+                              const float* W, void* C, int c_bf16, int64_t ldc, float beta, float* dW, float* db,
+                              u2gnn_stream_t stream);
 /* out_proj + dropout + residual + LayerNorm1 in one kernel (torch/nn/modules/transformer.py:946,969-972:
  * x = norm1(x + dropout1(self_attn(x)))): z[M,64] = res + dropout(A[M,K] W^T + bias), y = LayerNorm(z) * gamma + beta,
  * stats[M,2] = (mean, rstd).  N = d = 64 only; res row stride ldres (elements) so the last timestep can read position 0 of

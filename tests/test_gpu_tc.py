@@ -437,17 +437,17 @@ def test_fused_attention_block_epilogues_equal_unfused_step(U):
     from u2gnn_b200.trainer import SupTrainer
     b = make_batch(3000, 16, 64, 2, seed=9)
     out = {}
-    defaults = (E.FUSE_OUT_PROJ_LN, E.FUSE_LN_BWD, E.FUSE_LN2_FFN_BWD)
+    defaults = (E.FUSE_OUT_PROJ_LN, E.FUSE_LN_BWD, E.FUSE_LN2_FFN_BWD, E.FUSE_PROJ_BWD)
     try:
         for fused in (False, True):
-            E.FUSE_OUT_PROJ_LN = E.FUSE_LN_BWD = E.FUSE_LN2_FFN_BWD = fused
+            E.FUSE_OUT_PROJ_LN = E.FUSE_LN_BWD = E.FUSE_LN2_FFN_BWD = E.FUSE_PROJ_BWD = fused
             torch.manual_seed(3)
             m = U.TransformerU2GNN(64, 512, 2, 3, 0.5, 1, attn_axis="neighbors").cuda()
             tr = SupTrainer(m, lr=5e-4, precision="bf16", seed=42)
             loss, scores = tr.forward_backward(b["input_x"], b["rowptr"], b["X"], b["labels"], train=True)
             out[fused] = (loss.item(), scores.clone(), tr.arena.g.clone())
     finally:
-        E.FUSE_OUT_PROJ_LN, E.FUSE_LN_BWD, E.FUSE_LN2_FFN_BWD = defaults
+        E.FUSE_OUT_PROJ_LN, E.FUSE_LN_BWD, E.FUSE_LN2_FFN_BWD, E.FUSE_PROJ_BWD = defaults
     assert out[True][0] == out[False][0]
     assert torch.equal(out[True][1], out[False][1])
     g1, g0 = out[True][2], out[False][2]
@@ -522,3 +522,28 @@ def test_seqattn_last_bf16_io_matches_fp32_io_on_rounded_inputs(U, B, S, p):
     assert torch.equal(ctx0, ref)
     assert torch.equal(ctx1, ctx0)
     assert torch.equal(dq1, dq0.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("M,N1,b_bf16,c_bf16,beta", [(1000, 192, 0, 0, 1.0), (148 * 128 * 3 + 77, 192, 0, 0, 1.0), (5000, 64, 1, 1, 0.0),
+                                                     (333, 64, 0, 0, 0.0), (128 * 148 * 5 + 1, 64, 1, 1, 0.0), (100, 128, 0, 0, 0.0)])
+def test_gemm_tc_dgrad_wgrad_equals_separate_kernels(U, M, N1, b_bf16, c_bf16, beta):
+    """One pass over the output gradient (input gradient + weight / bias gradient) against the rows GEMM and the
+    weight-gradient GEMM on the same operands: the input gradient is bit-identical (same MMAs, same epilogue arithmetic),
+    the weight / bias gradients agree up to the order of the fp32 atomic flush."""
+    from u2gnn_b200 import engine as E
+    g = torch.Generator(device="cuda").manual_seed(M + N1)
+    A = torch.randn(M, N1, device="cuda", generator=g).to(torch.bfloat16)
+    Bm = torch.randn(M, 64, device="cuda", generator=g)
+    if b_bf16:
+        Bm = Bm.to(torch.bfloat16)
+    W = torch.randn(N1, 64, device="cuda", generator=g) / 8
+    C0 = torch.randn(M, 64, device="cuda", generator=g)
+    dW0 = torch.zeros(N1, 64, device="cuda"); db0 = torch.zeros(N1, device="cuda")
+    dW1 = torch.zeros(N1, 64, device="cuda"); db1 = torch.zeros(N1, device="cuda")
+    E.wgrad_tc(A, M, N1, Bm, 64, dW0, db0)
+    ref = E.linear_tc(A, M, N1, W, 1, 64, beta=beta, out=C0.clone() if beta else None, out_bf16=bool(c_bf16))
+    out = E.proj_bwd_tc(A, M, N1, Bm, W, dW1, db1, out=C0.clone() if beta else None, out_bf16=bool(c_bf16), beta=beta)
+    torch.cuda.synchronize()
+    assert out.dtype == ref.dtype and torch.equal(out, ref)
+    assert (dW1 - dW0).abs().max().item() <= 1e-4 * dW0.abs().max().item()
+    assert (db1 - db0).abs().max().item() <= 1e-4 * db0.abs().max().item()
