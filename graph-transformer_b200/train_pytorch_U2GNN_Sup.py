@@ -36,6 +36,9 @@ def parse_args(argv=None):
     p.add_argument("--attn_axis", default="nodes", choices=["nodes", "neighbors"],
                    help="'nodes' = reference as written, 'neighbors' = intended layout (SURVEY.md F1)")
     p.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    p.add_argument("--tie_timesteps", action="store_true",
+                   help="share ONE encoder weight set across the T timesteps (the published Universal-Transformer U2GNN); "
+                        "default = T independent sets like the reference PyTorch file")
     p.add_argument("--dataset_root", default=None)
     return p.parse_args(argv)
 
@@ -56,7 +59,8 @@ def run(args, log=print):
         d = 4
     model = U.TransformerU2GNN(feature_dim_size=d, ff_hidden_size=args.ff_hidden_size, num_classes=num_classes,
                                dropout=args.dropout, num_self_att_layers=args.num_timesteps,
-                               num_U2GNN_layers=args.num_hidden_layers, attn_axis=args.attn_axis).to(dev)
+                               num_U2GNN_layers=args.num_hidden_layers, attn_axis=args.attn_axis,
+                               tie_timesteps=args.tie_timesteps).to(dev)
     trainer = SupTrainer(model, lr=args.learning_rate, precision=args.precision, seed=123)
     steps_per_epoch = int((len(train_graphs) - 1) / args.batch_size) + 1
 

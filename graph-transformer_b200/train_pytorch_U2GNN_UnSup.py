@@ -37,6 +37,9 @@ def parse_args(argv=None):
     p.add_argument("--degree_as_tag", action="store_true", help="use node degrees as tags (README/TF-era flag)")
     p.add_argument("--attn_axis", default="nodes", choices=["nodes", "neighbors"])
     p.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    p.add_argument("--tie_timesteps", action="store_true",
+                   help="share ONE encoder weight set across the T timesteps (the published Universal-Transformer U2GNN); "
+                        "default = T independent sets like the reference PyTorch file")
     p.add_argument("--dataset_root", default=None)
     return p.parse_args(argv)
 
@@ -59,7 +62,7 @@ def run(args, log=print):
     model = U.TransformerU2GNNUnSup(feature_dim_size=d, ff_hidden_size=args.ff_hidden_size, dropout=args.dropout,
                                     num_self_att_layers=args.num_timesteps, vocab_size=vocab, sampled_num=args.sampled_num,
                                     num_U2GNN_layers=args.num_hidden_layers, device=dev, attn_axis=args.attn_axis,
-                                    precision=args.precision).to(dev)
+                                    precision=args.precision, tie_timesteps=args.tie_timesteps).to(dev)
     trainer = UnSupTrainer(model, lr=args.learning_rate, seed=123)
     steps_per_epoch = int((len(graphs) - 1) / args.batch_size) + 1
 

@@ -25,6 +25,16 @@ from . import engine as E
 from ._lib import LIB, require_device
 
 
+def _tie(encoder: TransformerEncoder, tie):
+    """tie=True: ONE weight set shared by all T timesteps - the Universal Transformer of the published U2GNN
+    (U2GNN_tf/universal_transformer_modified_utils.py:251-252, 552-586).  The reference's PyTorch
+    file clones T independent layers (torch/nn/modules/transformer.py _get_clones), which stays the default.  The same module
+    object is listed T times, so state_dict() still carries the reference names layers.{t}.* (all aliasing one tensor)."""
+    if tie:
+        encoder.layers = nn.ModuleList([encoder.layers[0]] * len(encoder.layers))
+    return encoder
+
+
 def _layer_param_dicts(encoder: TransformerEncoder):
     out = []
     for layer in encoder.layers:
@@ -155,7 +165,7 @@ class TransformerU2GNN(_U2GNNBase):
     ("neighbors") attention layout."""
 
     def __init__(self, feature_dim_size, ff_hidden_size, num_classes, num_self_att_layers, dropout,
-                 num_U2GNN_layers, attn_axis="nodes", deterministic=True, precision="fp32"):
+                 num_U2GNN_layers, attn_axis="nodes", deterministic=True, precision="fp32", tie_timesteps=False):
         super().__init__()
         self.feature_dim_size = feature_dim_size
         self.ff_hidden_size = ff_hidden_size
@@ -165,7 +175,7 @@ class TransformerU2GNN(_U2GNNBase):
         self.u2gnn_layers = nn.ModuleList()
         for _ in range(num_U2GNN_layers):
             enc = TransformerEncoderLayer(d_model=feature_dim_size, nhead=1, dim_feedforward=ff_hidden_size, dropout=0.5)
-            self.u2gnn_layers.append(TransformerEncoder(enc, num_self_att_layers))
+            self.u2gnn_layers.append(_tie(TransformerEncoder(enc, num_self_att_layers), tie_timesteps))
         self.predictions = nn.ModuleList()
         self.dropouts = nn.ModuleList()
         for _ in range(num_U2GNN_layers):
@@ -316,7 +326,7 @@ class TransformerU2GNNUnSup(_U2GNNBase):
 
     def __init__(self, vocab_size, feature_dim_size, ff_hidden_size, sampled_num, num_self_att_layers,
                  num_U2GNN_layers, dropout, device, sampler_type="default", loss_type="default", adj_mat=None,
-                 single_layer_only=True, attn_axis="nodes", deterministic=True, precision="fp32"):
+                 single_layer_only=True, attn_axis="nodes", deterministic=True, precision="fp32", tie_timesteps=False):
         super().__init__()
         if sampler_type != "default" or loss_type != "default":
             raise NotImplementedError("only the default sampler / sampled-softmax loss is part of the hot path")
@@ -330,7 +340,7 @@ class TransformerU2GNNUnSup(_U2GNNBase):
         self.u2gnn_layers = nn.ModuleList()
         for _ in range(num_U2GNN_layers):
             enc = TransformerEncoderLayer(d_model=feature_dim_size, nhead=1, dim_feedforward=ff_hidden_size, dropout=0.5)
-            self.u2gnn_layers.append(TransformerEncoder(enc, num_self_att_layers))
+            self.u2gnn_layers.append(_tie(TransformerEncoder(enc, num_self_att_layers), tie_timesteps))
         self.dropouts = nn.Dropout(dropout)
         self.ss = SampledSoftmax(vocab_size, sampled_num, feature_dim_size * num_U2GNN_layers, device)
         self._init_engine(attn_axis, deterministic, precision)

@@ -47,6 +47,12 @@ class FlatArena:
     def zero_grad(self):
         self.g.zero_()
 
+    def grad_dicts(self, params):
+        """params[l][t] = {name: Parameter}  ->  the same nesting of gradient views, looked up by parameter identity so that
+        timesteps sharing one weight set (tie_timesteps) accumulate into one gradient slot."""
+        by_id = {id(p): self.gviews[n] for n, p in self.views.items()}
+        return [[{n: by_id[id(p)] for n, p in d.items()} for d in layer] for layer in params]
+
     def grads_from_autograd(self):
         self.g.zero_()
         for n, p in self.views.items():
@@ -82,9 +88,7 @@ class SupTrainer:
         self.seed, self.steps = seed, 0
         self.L, self.T = model.num_U2GNN_layers, model.num_self_att_layers
         self.params = [_layer_param_dicts(model.u2gnn_layers[l]) for l in range(self.L)]
-        name = lambda l, t, n: "u2gnn_layers.%d.layers.%d.%s" % (l, t, n)
-        self.grads = [[{n: self.arena.gviews[name(l, t, n)] for n in E.PARAM_NAMES} for t in range(self.T)]
-                      for l in range(self.L)]
+        self.grads = self.arena.grad_dicts(self.params)
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.arena.p.device)
 
     def _drop(self, train):
@@ -184,9 +188,7 @@ class UnSupTrainer:
         self.seed, self.steps = seed, 0
         self.L, self.T = model.num_U2GNN_layers, model.num_self_att_layers
         self.params = [_layer_param_dicts(model.u2gnn_layers[l]) for l in range(self.L)]
-        name = lambda l, t, n: "u2gnn_layers.%d.layers.%d.%s" % (l, t, n)
-        self.grads = [[{n: self.arena.gviews[name(l, t, n)] for n in E.PARAM_NAMES} for t in range(self.T)]
-                      for l in range(self.L)]
+        self.grads = self.arena.grad_dicts(self.params)
         self.sampler = None
 
     def step(self, X, input_x, input_y, sample_ids=None, apply=True):

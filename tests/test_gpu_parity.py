@@ -286,3 +286,39 @@ def test_large_gather_pool_properties(U):
     assert torch.allclose(pooled.sum(0), X.sum(0), rtol=1e-3, atol=1e-2)
     gb = E.segment_sum_bwd(pooled, rowptr, N)
     assert torch.equal(gb[::64], pooled) and torch.equal(gb[63::64], pooled)
+
+
+@pytest.mark.parametrize("precision,d,ff", [("fp32", 16, 64), ("bf16", 64, 256)])
+def test_tied_timesteps_gradient_is_the_sum_over_timesteps(precision, d, ff):
+    """tie_timesteps=True (one weight set shared by the T timesteps, the published Universal-Transformer U2GNN; SURVEY.md 8(f)
+    row 4): same loss as T independent copies holding identical weights, and the shared gradient is the sum of the copies'."""
+    import u2gnn_b200 as U
+    from u2gnn_b200 import engine as E
+    from u2gnn_b200.synthetic import make_batch
+    from u2gnn_b200.trainer import SupTrainer
+    T = 3
+    b = make_batch(500, 8, d, 2, seed=4)
+    torch.manual_seed(11)
+    free = U.TransformerU2GNN(d, ff, 2, T, 0.5, 1, attn_axis="neighbors").cuda()
+    layers = free.u2gnn_layers[0].layers
+    for t in range(1, T):
+        layers[t].load_state_dict(layers[0].state_dict())
+    torch.manual_seed(11)
+    tied = U.TransformerU2GNN(d, ff, 2, T, 0.5, 1, attn_axis="neighbors", tie_timesteps=True).cuda()
+    tied.u2gnn_layers[0].layers[0].load_state_dict(layers[0].state_dict())
+    tied.predictions.load_state_dict(free.predictions.state_dict())
+    assert len(list(tied.parameters())) == 12 + 2 and len(tied.state_dict()) == len(free.state_dict())
+    tr_f = SupTrainer(free, precision=precision, seed=5)
+    tr_t = SupTrainer(tied, precision=precision, seed=5)
+    lf, sf = tr_f.forward_backward(b["input_x"], b["rowptr"], b["X"], b["labels"], train=True)
+    lt, st = tr_t.forward_backward(b["input_x"], b["rowptr"], b["X"], b["labels"], train=True)
+    assert lf.item() == lt.item() and torch.equal(sf, st)
+    for n in E.PARAM_NAMES:
+        ref = sum(tr_f.arena.gviews["u2gnn_layers.0.layers.%d.%s" % (t, n)] for t in range(T))
+        got = tr_t.arena.gviews["u2gnn_layers.0.layers.0.%s" % n]
+        assert (got - ref).abs().max().item() <= 1e-4 * max(1e-3, ref.abs().max().item()), n
+    # autograd surface: the shared parameters receive the summed gradient as well
+    tied.train()
+    s = tied(b["input_x"], b["rowptr"], b["X"])
+    s.sum().backward()
+    assert all(p.grad is not None for p in tied.parameters())
