@@ -16,6 +16,8 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
     const int lane = threadIdx.x % lanes_per_row;
     const int sub = threadIdx.x / lanes_per_row;
     const int dv = d / VEC;
+    // (four rows per thread in flight, `gridDim.x * rows_per_block` apart, was measured: 97 us against 69 us per 1.1 M rows -
+    // the row stores of a warp then spread over four distant regions; one row per iteration stays)
     for (int64_t row = (int64_t)blockIdx.x * rows_per_block + sub; row < n_idx;
          row += (int64_t)gridDim.x * rows_per_block) {
         int64_t src = __ldg(idx + row * idx_stride);
@@ -193,6 +195,29 @@ __global__ void __launch_bounds__(256) segment_bcast_kernel(const float* __restr
     }
 }
 
+// same, 128-bit pieces (d % 4 == 0): a quarter of the threads, searches and memory instructions
+__global__ void __launch_bounds__(256) segment_bcast_vec_kernel(const float* __restrict__ gout, int dv,
+                                                                const int64_t* __restrict__ rowptr, int64_t G,
+                                                                float* __restrict__ gx, int64_t n, int accumulate) {
+    const int64_t total = n * dv;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t node = e / dv;
+        const int c = (int)(e - node * dv);
+        int64_t lo = 0, hi = G;  // largest g with rowptr[g] <= node
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(rowptr + mid) <= node) lo = mid; else hi = mid;
+        }
+        float4 v = __ldg(reinterpret_cast<const float4*>(gout + lo * dv * 4) + c);
+        float4* o = reinterpret_cast<float4*>(gx) + e;
+        if (accumulate) {
+            const float4 old = *o;
+            v.x = old.x + v.x; v.y = old.y + v.y; v.z = old.z + v.z; v.w = old.w + v.w;
+        }
+        *o = v;
+    }
+}
+
 int pick_lanes(int d_units) {
     int l = 1;
     while (l < 32 && l < d_units) l <<= 1;
@@ -280,7 +305,11 @@ extern "C" int u2gnn_segment_sum_bwd(const float* grad_out, int64_t num_graphs, 
                                      float* grad_x, int64_t n, int accumulate, u2gnn_stream_t stream) {
     if (!grad_out || !rowptr || !grad_x || d <= 0 || num_graphs <= 0) return U2GNN_EINVAL;
     if (n == 0) return U2GNN_OK;
-    segment_bcast_kernel<<<grid_for(n * d, 256, 8), 256, 0, as_stream(stream)>>>(grad_out, d, rowptr, num_graphs,
-                                                                                grad_x, n, accumulate);
+    if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(grad_out) | reinterpret_cast<uintptr_t>(grad_x)) & 15) == 0)
+        segment_bcast_vec_kernel<<<grid_for(n * (d / 4), 256, 8), 256, 0, as_stream(stream)>>>(grad_out, d / 4, rowptr, num_graphs,
+                                                                                              grad_x, n, accumulate);
+    else
+        segment_bcast_kernel<<<grid_for(n * d, 256, 8), 256, 0, as_stream(stream)>>>(grad_out, d, rowptr, num_graphs,
+                                                                                    grad_x, n, accumulate);
     U2GNN_CHECK_LAUNCH();
 }
