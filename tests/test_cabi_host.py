@@ -108,6 +108,33 @@ def test_flat_arena_views_keep_state_dict(U):
     assert torch.equal(m.predictions[0].weight.data, before["predictions.0.weight"] * 2.0)
 
 
+def test_tied_timesteps_share_one_weight_set_and_one_gradient_slot(U):
+    """tie_timesteps=True: T timesteps alias ONE encoder layer; state_dict keeps the reference names,
+    the flat arena holds one copy and every timestep's gradient dict points at the same slot."""
+    from u2gnn_b200.trainer import FlatArena
+    from u2gnn_b200.model import _layer_param_dicts
+    torch.manual_seed(1)
+    free = U.TransformerU2GNN(6, 16, 2, 3, 0.5, 1)
+    tied = U.TransformerU2GNN(6, 16, 2, 3, 0.5, 1, tie_timesteps=True)
+    assert set(tied.state_dict()) == set(free.state_dict())
+    per_layer = sum(p.numel() for p in free.u2gnn_layers[0].layers[0].parameters())
+    assert sum(p.numel() for p in free.parameters()) - sum(p.numel() for p in tied.parameters()) == 2 * per_layer
+    sd = free.state_dict()
+    for t in (1, 2):                                     # a reference checkpoint with identical copies loads unchanged
+        for k in list(sd):
+            if ".layers.%d." % t in k:
+                sd[k] = sd[k.replace(".layers.%d." % t, ".layers.0.")]
+    tied.load_state_dict(sd)
+    a = FlatArena(tied)
+    g = a.grad_dicts([_layer_param_dicts(tied.u2gnn_layers[0])])
+    assert len(g[0]) == 3
+    for n in g[0][0]:
+        assert g[0][0][n].data_ptr() == g[0][1][n].data_ptr() == g[0][2][n].data_ptr()
+    u = U.TransformerU2GNNUnSup(vocab_size=50, feature_dim_size=4, ff_hidden_size=16, sampled_num=8, num_self_att_layers=2,
+                                num_U2GNN_layers=1, dropout=0.5, device=torch.device("cpu"), tie_timesteps=True)
+    assert u.u2gnn_layers[0].layers[0] is u.u2gnn_layers[0].layers[1]
+
+
 def test_label_smoothing_matches_oracle(U):
     y = torch.tensor([0, 2, 1, 1])
     assert np.allclose(U.label_smoothing(y, 3).numpy(), O.label_smoothing(y.numpy(), 3))
