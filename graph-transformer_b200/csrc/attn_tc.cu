@@ -111,9 +111,9 @@ struct Params {
     int low;
 };
 
-// shared memory layout (bytes): Q 0, K 16K, V 32K (P~ tile 0 reuses V in the backward), G 48K, P~1 / P~ 64K.., dS
+// shared memory layout (bytes): Q 0, K 16K, V 32K; forward: P~ over Q / K; backward: P~ tile 0 over V, G 48K, P~1 64K, dS 80K / 96K
 template <bool BWD, int SMAX>          // SMAX: compile-time bound of the sequence length (register arrays)
-__global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const Params p) {
+__global__ void __launch_bounds__(kThreads, BWD ? 2 : 3) attn_tc_kernel(const Params p) {
     // no static shared memory and a 1024-byte aligned dynamic segment: the backward's seven 16 KB tiles (+ 16 bytes for
     // the barrier and the TMEM slot behind them) then fit TWICE into an SM, so two phase-serial CTAs overlap
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -122,18 +122,21 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const Params p) {
     uint8_t* sK = smem + 16384;
     uint8_t* sV = smem + 32768;
     uint8_t* sG = smem + 49152;                                  // backward only
-    uint8_t* sP0 = BWD ? sV : smem + 49152;                      // P~ columns 0..63   (backward: over V, dead after dP)
-    uint8_t* sP1 = BWD ? smem + 65536 : smem + 65536;            // P~ columns 64..127
+    // forward: P~ goes over Q / K (dead once S = Q K^T has completed), so a forward CTA needs three tiles and 128 tensor-memory
+    // columns (ctx reuses the S columns) and THREE CTAs fit an SM: the tile is a serial chain (load -> S -> softmax -> ctx ->
+    // store), only more tiles in flight hide it
+    uint8_t* sP0 = BWD ? sV : sQ;                                // P~ columns 0..63   (backward: over V, dead after dP)
+    uint8_t* sP1 = BWD ? smem + 65536 : sK;                      // P~ columns 64..127
     uint8_t* sS0 = smem + 81920;                                 // dS columns 0..63   (backward only)
     uint8_t* sS1 = smem + 98304;
-    uint64_t& bar = *reinterpret_cast<uint64_t*>(smem + (BWD ? 114688 : 81920));
-    uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(smem + (BWD ? 114688 : 81920) + 8);
+    uint64_t& bar = *reinterpret_cast<uint64_t*>(smem + (BWD ? 114688 : 49152));
+    uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(smem + (BWD ? 114688 : 49152) + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         tc::mbar_init(&bar, 1);
         tc::fence_barrier_init();
     }
-    constexpr int kTmemCols = 256;
+    constexpr int kTmemCols = BWD ? 256 : 128;
     if (warp == 0) tc::tmem_alloc<kTmemCols>(&tmem_slot);
     tc::tc_fence_before();
     __syncthreads();
@@ -401,12 +404,12 @@ AttnRng make_rng(uint64_t seed, uint32_t stream, int thr) {
 
 template <bool BWD>
 int launch(const Params& p, cudaStream_t st) {
-    const size_t smem = (BWD ? 114688 : 81920) + 16;          // tiles + barrier + TMEM slot
+    const size_t smem = (BWD ? 114688 : 49152) + 16;          // tiles + barrier + TMEM slot
     auto k = (p.S <= 20) ? attn_tc_kernel<BWD, 20> : attn_tc_kernel<BWD, 32>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int NB = TM / p.S;
     const int64_t n_tiles = (p.B + NB - 1) / NB;
-    const int64_t cap = (int64_t)U2GNN_NUM_SMS * 2;            // two CTAs per SM (256 TMEM columns each)
+    const int64_t cap = (int64_t)U2GNN_NUM_SMS * (BWD ? 2 : 3);   // backward: two CTAs per SM (256 TMEM columns, seven tiles each); forward: three
     k<<<(int)(n_tiles < cap ? n_tiles : cap), kThreads, smem, st>>>(p);
     return U2GNN_OK;
 }
