@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict
 }
 
 template <int LPR>
-__global__ void __launch_bounds__(256, 4) ln_bwd_vec_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+__global__ void __launch_bounds__(256, 3) ln_bwd_vec_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                                                          const float* __restrict__ stats, int64_t M,
                                                          const float* __restrict__ gamma, DropRng rng, int low,
                                                          float* __restrict__ dz, void* __restrict__ da_, int da_bf16,
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256, 4) ln_bwd_vec_kernel(const float* __restr
     float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = make_float4(0.f, 0.f, 0.f, 0.f);
     // two row groups per iteration: the loads of both (dy, z, stats) are in flight together (one group per iteration kept
     // 32 KB outstanding per SM at 32 resident warps - below what the HBM latency x bandwidth product needs)
-    constexpr int UNR = 2;
+    constexpr int UNR = 4;
     for (int64_t r0 = warp * (UNR * RPW); r0 < M; r0 += nwarps * (UNR * RPW)) {
         float4 gk[UNR], xk[UNR];
         float mk[UNR], sk[UNR];
@@ -346,7 +346,7 @@ extern "C" int u2gnn_add_dropout_ln_bwd_ex(const float* dy, const float* z, cons
     if (vec_ok(d, dy, z, dz, da, gamma)) {
         const DropRng rng = make_rng(seed, rng_stream, thr);
         const int low = rng_thr_low(thr);
-        const int grid = grid_for(M, 64 * (128 / d), 4);
+        const int grid = grid_for(M, 64 * (128 / d), 3);
         cudaStream_t st = as_stream(stream);
         if (d == 16) ln_bwd_vec_kernel<4><<<grid, 256, 0, st>>>(dy, z, stats, M, gamma, rng, low, dz, da, da_bf16, dgamma, dbeta, dasum);
         else if (d == 32) ln_bwd_vec_kernel<8><<<grid, 256, 0, st>>>(dy, z, stats, M, gamma, rng, low, dz, da, da_bf16, dgamma, dbeta, dasum);
