@@ -109,11 +109,19 @@ struct Params {
     int S;
     AttnRng rng;
     int low;
+    // INPROJ forward: the tile's qkv rows are computed here (qkv = x W_in^T + b_in, nn.MultiheadAttention in_proj) instead of
+    // being read back: x fp32 [B*S, 64], w_in [192, 64], b_in [192]; qkv_out bf16 [B*S, 192] is still written (the backward
+    // reads it)
+    const float* x;
+    const float* w_in;
+    const float* b_in;
+    void* qkv_out;
 };
 
 // shared memory layout (bytes): Q 0, K 16K, V 32K; forward: P~ over Q / K; backward: P~ tile 0 over V, G 48K, P~1 64K, dS 80K / 96K
-template <bool BWD, int SMAX>          // SMAX: compile-time bound of the sequence length (register arrays)
+template <bool BWD, int SMAX, bool INPROJ = false>   // SMAX: compile-time bound of the sequence length (register arrays)
 __global__ void __launch_bounds__(kThreads, BWD ? 2 : 3) attn_tc_kernel(const Params p) {
+    static_assert(!(BWD && INPROJ), "the fused in_proj exists for the forward only");
     // no static shared memory and a 1024-byte aligned dynamic segment: the backward's seven 16 KB tiles (+ 16 bytes for
     // the barrier and the TMEM slot behind them) then fit TWICE into an SM, so two phase-serial CTAs overlap
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -129,8 +137,12 @@ __global__ void __launch_bounds__(kThreads, BWD ? 2 : 3) attn_tc_kernel(const Pa
     uint8_t* sP1 = BWD ? smem + 65536 : sK;                      // P~ columns 64..127
     uint8_t* sS0 = smem + 81920;                                 // dS columns 0..63   (backward only)
     uint8_t* sS1 = smem + 98304;
-    uint64_t& bar = *reinterpret_cast<uint64_t*>(smem + (BWD ? 114688 : 49152));
-    uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(smem + (BWD ? 114688 : 49152) + 8);
+    // INPROJ: the x tile is staged over V (dead until the V columns are drained), W_in as a [192 x 64] K-major image behind V
+    uint8_t* sX = sV;
+    uint8_t* sWin = smem + 49152;
+    constexpr int kBarOff = BWD ? 114688 : (INPROJ ? 73728 : 49152);
+    uint64_t& bar = *reinterpret_cast<uint64_t*>(smem + kBarOff);
+    uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(smem + kBarOff + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         tc::mbar_init(&bar, 1);
@@ -138,6 +150,11 @@ __global__ void __launch_bounds__(kThreads, BWD ? 2 : 3) attn_tc_kernel(const Pa
     }
     constexpr int kTmemCols = BWD ? 256 : 128;
     if (warp == 0) tc::tmem_alloc<kTmemCols>(&tmem_slot);
+    if constexpr (INPROJ) {
+        for (int e = tid; e < 3 * D * D; e += kThreads)        // W_in[n][k] -> K-major B image, row n = output column
+            *reinterpret_cast<__nv_bfloat16*>(sWin + tc::sw128_offset(e >> 6, e & 63)) = __float2bfloat16(p.w_in[e]);
+        tc::fence_proxy_async();
+    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -158,7 +175,80 @@ __global__ void __launch_bounds__(kThreads, BWD ? 2 : 3) attn_tc_kernel(const Pa
         const int rows = nodes * S;
         const int64_t row0 = node0 * S;
         // ---- 1. stage operands
-        if (p.io_bf16) {
+        if constexpr (INPROJ) {
+            // qkv rows of the tile from x: two MMA passes through the SAME 128 tensor-memory columns (Q | K, then V) so that the
+            // CTA stays at 128 columns and three CTAs per SM; thread = row drains them (+ bias, rounded to bf16 once - the value
+            // the separate projection kernel stores) into the swizzled operand tiles
+            const int half = warp >> 2;
+            stage_tile(sX, p.x, 0, D, 0, row0, rows, tid);
+            tc::fence_proxy_async();
+            tc::tc_fence_before();
+            __syncthreads();
+            tc::tc_fence_after();
+            if (warp == 0) {
+                if (tc::elect_one()) {
+                    mma_kk(tmem, tc::smem_u32(sX), tc::smem_u32(sWin), tc::make_idesc(128, 128, 0, 0));
+                    tc::mma_commit(&bar);
+                }
+                __syncwarp();
+            }
+            tc::mbar_wait(&bar, phase);
+            phase ^= 1;
+            tc::tc_fence_after();
+            {
+                uint8_t* tile = half ? sK : sQ;               // warps 0-3 drain Q (columns 0..63), warps 4-7 drain K
+#pragma unroll
+                for (int pc = 0; pc < 2; ++pc) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(tmem + lane_base + 64 * half + 32 * pc, v);
+                    tc::tmem_ld_wait();
+                    const float4* b4 = reinterpret_cast<const float4*>(p.b_in + 64 * half + 32 * pc);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float4 ba = __ldg(b4 + 2 * c), bb = __ldg(b4 + 2 * c + 1);
+                        uint4 w = make_uint4(0u, 0u, 0u, 0u);
+                        if (r < rows) {
+                            w.x = epi::cvt2(__uint_as_float(v[8 * c]) + ba.x, __uint_as_float(v[8 * c + 1]) + ba.y);
+                            w.y = epi::cvt2(__uint_as_float(v[8 * c + 2]) + ba.z, __uint_as_float(v[8 * c + 3]) + ba.w);
+                            w.z = epi::cvt2(__uint_as_float(v[8 * c + 4]) + bb.x, __uint_as_float(v[8 * c + 5]) + bb.y);
+                            w.w = epi::cvt2(__uint_as_float(v[8 * c + 6]) + bb.z, __uint_as_float(v[8 * c + 7]) + bb.w);
+                        }
+                        *reinterpret_cast<uint4*>(tile + tc::sw128_chunk(r, 4 * pc + c)) = w;
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            __syncthreads();
+            tc::tc_fence_after();
+            if (warp == 0) {
+                if (tc::elect_one()) {
+                    mma_kk(tmem, tc::smem_u32(sX), tc::smem_u32(sWin) + 16384, tc::make_idesc(128, 64, 0, 0));   // V = x W_v^T
+                    tc::mma_commit(&bar);
+                }
+                __syncwarp();
+            }
+            tc::mbar_wait(&bar, phase);
+            phase ^= 1;
+            tc::tc_fence_after();
+            {
+                uint32_t v[32];
+                tc::tmem_ld32(tmem + lane_base + 32 * half, v);   // warps 0-3: V columns 0..31, warps 4-7: 32..63 (x is dead now)
+                tc::tmem_ld_wait();
+                const float4* b4 = reinterpret_cast<const float4*>(p.b_in + 128 + 32 * half);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 ba = __ldg(b4 + 2 * c), bb = __ldg(b4 + 2 * c + 1);
+                    uint4 w = make_uint4(0u, 0u, 0u, 0u);
+                    if (r < rows) {
+                        w.x = epi::cvt2(__uint_as_float(v[8 * c]) + ba.x, __uint_as_float(v[8 * c + 1]) + ba.y);
+                        w.y = epi::cvt2(__uint_as_float(v[8 * c + 2]) + ba.z, __uint_as_float(v[8 * c + 3]) + ba.w);
+                        w.z = epi::cvt2(__uint_as_float(v[8 * c + 4]) + bb.x, __uint_as_float(v[8 * c + 5]) + bb.y);
+                        w.w = epi::cvt2(__uint_as_float(v[8 * c + 6]) + bb.z, __uint_as_float(v[8 * c + 7]) + bb.w);
+                    }
+                    *reinterpret_cast<uint4*>(sV + tc::sw128_chunk(r, 4 * half + c)) = w;
+                }
+            }
+        } else if (p.io_bf16) {
             // bf16 sources: tiles are plain copies; every 16-byte load of all three / four tiles is in flight before the first
             // shared-memory store (one exposed memory latency per tile-set instead of one per tile)
             const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(p.qkv);
@@ -201,6 +291,24 @@ __global__ void __launch_bounds__(kThreads, BWD ? 2 : 3) attn_tc_kernel(const Pa
                 tc::mma_commit(&bar);
             }
             __syncwarp();
+        }
+        if constexpr (INPROJ) {
+            // the three operand tiles -> qkv_out (bf16 row-major, coalesced 16-byte pieces) while the S MMA runs; the barrier
+            // keeps the P~ rows (written over Q / K below) behind every thread's reads
+            __nv_bfloat16* qo = static_cast<__nv_bfloat16*>(p.qkv_out);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = u * kThreads + tid;
+                const int rr = e >> 3, c8 = e & 7;
+                if (rr < rows) {
+                    const uint32_t off = tc::sw128_chunk(rr, c8);
+                    uint4* dst = reinterpret_cast<uint4*>(qo + (row0 + rr) * (3 * D)) + c8;
+                    dst[0] = *reinterpret_cast<const uint4*>(sQ + off);
+                    dst[8] = *reinterpret_cast<const uint4*>(sK + off);
+                    dst[16] = *reinterpret_cast<const uint4*>(sV + off);
+                }
+            }
+            __syncthreads();
         }
         tc::mbar_wait(&bar, phase);
         phase ^= 1;
@@ -402,10 +510,10 @@ AttnRng make_rng(uint64_t seed, uint32_t stream, int thr) {
     return r;
 }
 
-template <bool BWD>
+template <bool BWD, bool INPROJ = false>
 int launch(const Params& p, cudaStream_t st) {
-    const size_t smem = (BWD ? 114688 : 49152) + 16;          // tiles + barrier + TMEM slot
-    auto k = (p.S <= 20) ? attn_tc_kernel<BWD, 20> : attn_tc_kernel<BWD, 32>;
+    const size_t smem = (BWD ? 114688 : (INPROJ ? 73728 : 49152)) + 16;   // tiles (+ W_in image) + barrier + TMEM slot
+    auto k = (p.S <= 20) ? attn_tc_kernel<BWD, 20, INPROJ> : attn_tc_kernel<BWD, 32, INPROJ>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int NB = TM / p.S;
     const int64_t n_tiles = (p.B + NB - 1) / NB;
@@ -427,6 +535,26 @@ extern "C" int u2gnn_seqattn_tc_fwd_ex(const void* qkv, int64_t B, int S, int d,
     p.rng = make_rng(seed, rng_stream, thr);
     p.low = rng_thr_low(thr);
     launch<false>(p, as_stream(stream));
+    U2GNN_CHECK_LAUNCH();
+}
+
+// in_proj + attention core in one kernel (bf16 mode): qkv = x W_in^T + b_in is computed per tile on the tensor cores, written
+// once (bf16, for the backward) and consumed from shared memory; ctx as u2gnn_seqattn_tc_fwd_ex(io_bf16 = 1).
+extern "C" int u2gnn_inproj_seqattn_tc_fwd(const float* x, int64_t B, int S, int d, const float* w_in, const float* b_in,
+                                           uint64_t seed, uint32_t rng_stream, int thr, void* qkv_out, void* ctx,
+                                           u2gnn_stream_t stream) {
+    if (!x || !w_in || !b_in || !qkv_out || !ctx || B < 0 || thr < 0 || thr > 255) return U2GNN_EINVAL;
+    if (d != D || S < 2 || S > 32) return U2GNN_EUNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(qkv_out) | reinterpret_cast<uintptr_t>(ctx) |
+         reinterpret_cast<uintptr_t>(b_in)) % 16)
+        return U2GNN_EALIGN;
+    if (B == 0) return U2GNN_OK;
+    Params p;
+    p.qkv = nullptr; p.dctx = nullptr; p.out = ctx; p.io_bf16 = 1; p.B = B; p.S = S;
+    p.rng = make_rng(seed, rng_stream, thr);
+    p.low = rng_thr_low(thr);
+    p.x = x; p.w_in = w_in; p.b_in = b_in; p.qkv_out = qkv_out;
+    launch<false, true>(p, as_stream(stream));
     U2GNN_CHECK_LAUNCH();
 }
 

@@ -34,6 +34,7 @@ FUSE_LN_BWD = os.environ.get("U2GNN_FUSE_EPILOGUES", "1") != "0"        # bf16 m
 FUSE_LN2_FFN_BWD = os.environ.get("U2GNN_FUSE_LN2", "0") != "0"
 LAST_STEP_BF16 = os.environ.get("U2GNN_LAST_BF16", "1") != "0"            # bf16 mode, d = 64: bf16 qkv / dqkv at the dead-row-eliminated last timestep
 FUSE_PROJ_BWD = os.environ.get("U2GNN_FUSE_PROJ_BWD", "1") != "0"         # bf16 mode, d = 64: projection input + weight gradients in one pass over the output gradient
+FUSE_INPROJ_ATTN = os.environ.get("U2GNN_FUSE_INPROJ_ATTN", "1") != "0"   # bf16 mode, d = 64: in_proj inside the attention-forward kernel (qkv written once, never re-read in the forward)
 FLOPS = {}    # entry point -> algorithmic flops issued while LIB.timed is active (bench.py roofline)
 
 
@@ -303,7 +304,10 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
     tc_proj = precision == "bf16" and not long_seq and d <= 64
     tc_attn = tc_proj and d == 64 and Sq == S and S >= 2        # tensor-core attention core: bf16 qkv / ctx between the kernels
     tc_last = tc_proj and d == 64 and Sq == 1 and S >= 2 and LAST_STEP_BF16     # last timestep: bf16 qkv / dqkv around the position-0 attention
-    if tc_proj:
+    fused_in = tc_attn and FUSE_INPROJ_ATTN
+    if fused_in:
+        qkv = torch.empty((M, 3 * d), dtype=torch.bfloat16, device=dev)      # written once by the fused kernel, read by the backward
+    elif tc_proj:
         qkv = linear_tc(x, M, d, p["self_attn.in_proj_weight"], 0, 3 * d, bias=p["self_attn.in_proj_bias"], out_bf16=tc_attn or tc_last)
     else:
         qkv = torch.empty((M, 3 * d), **f32)
@@ -317,6 +321,11 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
         LIB.call("u2gnn_softmax_rows_fwd", _ptr(scores), S, S, _ptr(pd), seed, drop_ids[0], thr, _stream())
         sgemm(0, 0, S, d, S, pd, S, qkv, 3 * d, ctx, d, b_off=2 * d)
         sv.probs, sv.pd = scores, pd
+    elif fused_in:
+        if LIB.timed is not None:
+            FLOPS["u2gnn_inproj_seqattn_tc_fwd"] = FLOPS.get("u2gnn_inproj_seqattn_tc_fwd", 0) + 2 * M * 3 * d * d
+        LIB.call("u2gnn_inproj_seqattn_tc_fwd", _ptr(x), B, S, d, _ptr(p["self_attn.in_proj_weight"]), _ptr(p["self_attn.in_proj_bias"]),
+                 seed, drop_ids[0], thr, _ptr(qkv), _ptr(ctx), _stream())
     elif tc_attn:
         LIB.call("u2gnn_seqattn_tc_fwd_ex", _ptr(qkv), B, S, d, seed, drop_ids[0], thr, _ptr(ctx), 1, _stream())
     elif tc_last:

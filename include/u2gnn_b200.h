@@ -265,6 +265,12 @@ int u2gnn_seqattn_tc_fwd_ex(const void* qkv, int64_t B, int S, int d, uint64_t s
 int u2gnn_seqattn_tc_bwd_ex(const void* qkv, const void* dctx, int64_t B, int S, int d, uint64_t seed,
                             uint32_t rng_stream, int thr, void* dqkv, int io_bf16, u2gnn_stream_t stream);
 
+/* in_proj + attention core of one timestep in ONE kernel (bf16 mode, d = 64, every query row live): qkv = x W_in^T + b_in
+ * (nn.MultiheadAttention in_proj: w_in [192,64], b_in [192]) is computed per tile, written once as bf16 qkv_out[B*S,192] for the
+ * backward, and consumed from shared memory; ctx[B*S,64] bf16.  Same results as u2gnn_gemm_tc_rows_ex (bf16 out) followed by
+ * u2gnn_seqattn_tc_fwd_ex(io_bf16 = 1). */
+int u2gnn_inproj_seqattn_tc_fwd(const float* x, int64_t B, int S, int d, const float* w_in, const float* b_in, uint64_t seed,
+                                uint32_t rng_stream, int thr, void* qkv_out, void* ctx, u2gnn_stream_t stream);
 /* last timestep of a U2GNN layer (only query position 0 of each node live): same contract as
  * u2gnn_seqattn_fwd / _bwd with Sq = 1, with qkv (and dqkv) optionally stored as bf16 [B*S, 3d]; ctx / dctx are fp32 [B, d].
  * d in {32, 64}, 2 <= S <= 32. */

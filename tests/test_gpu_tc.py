@@ -437,17 +437,17 @@ def test_fused_attention_block_epilogues_equal_unfused_step(U):
     from u2gnn_b200.trainer import SupTrainer
     b = make_batch(3000, 16, 64, 2, seed=9)
     out = {}
-    defaults = (E.FUSE_OUT_PROJ_LN, E.FUSE_LN_BWD, E.FUSE_LN2_FFN_BWD, E.FUSE_PROJ_BWD)
+    defaults = (E.FUSE_OUT_PROJ_LN, E.FUSE_LN_BWD, E.FUSE_LN2_FFN_BWD, E.FUSE_PROJ_BWD, E.FUSE_INPROJ_ATTN)
     try:
         for fused in (False, True):
-            E.FUSE_OUT_PROJ_LN = E.FUSE_LN_BWD = E.FUSE_LN2_FFN_BWD = E.FUSE_PROJ_BWD = fused
+            E.FUSE_OUT_PROJ_LN = E.FUSE_LN_BWD = E.FUSE_LN2_FFN_BWD = E.FUSE_PROJ_BWD = E.FUSE_INPROJ_ATTN = fused
             torch.manual_seed(3)
             m = U.TransformerU2GNN(64, 512, 2, 3, 0.5, 1, attn_axis="neighbors").cuda()
             tr = SupTrainer(m, lr=5e-4, precision="bf16", seed=42)
             loss, scores = tr.forward_backward(b["input_x"], b["rowptr"], b["X"], b["labels"], train=True)
             out[fused] = (loss.item(), scores.clone(), tr.arena.g.clone())
     finally:
-        E.FUSE_OUT_PROJ_LN, E.FUSE_LN_BWD, E.FUSE_LN2_FFN_BWD, E.FUSE_PROJ_BWD = defaults
+        E.FUSE_OUT_PROJ_LN, E.FUSE_LN_BWD, E.FUSE_LN2_FFN_BWD, E.FUSE_PROJ_BWD, E.FUSE_INPROJ_ATTN = defaults
     assert out[True][0] == out[False][0]
     assert torch.equal(out[True][1], out[False][1])
     g1, g0 = out[True][2], out[False][2]
@@ -547,3 +547,27 @@ def test_gemm_tc_dgrad_wgrad_equals_separate_kernels(U, M, N1, b_bf16, c_bf16, b
     assert out.dtype == ref.dtype and torch.equal(out, ref)
     assert (dW1 - dW0).abs().max().item() <= 1e-4 * dW0.abs().max().item()
     assert (db1 - db0).abs().max().item() <= 1e-4 * db0.abs().max().item()
+
+
+@pytest.mark.parametrize("B,S,p", [(300, 17, 0.5), (77, 9, 0.0), (148 * 7 * 3 + 5, 17, 0.5), (50, 32, 0.5)])
+def test_inproj_attention_fused_equals_projection_then_attention(U, B, S, p):
+    """u2gnn_inproj_seqattn_tc_fwd (qkv computed per tile inside the attention-forward kernel) against the projection GEMM
+    followed by the attention kernel: qkv and ctx bit-identical."""
+    from u2gnn_b200 import engine as E
+    d = 64
+    thr = E.dropout_threshold(p)
+    g = torch.Generator(device="cuda").manual_seed(B * S + 1)
+    x = torch.randn(B * S, d, device="cuda", generator=g)
+    W = torch.randn(3 * d, d, device="cuda", generator=g) / 8
+    b = torch.randn(3 * d, device="cuda", generator=g)
+    SEED, ST = 4242, 16
+    qkv0 = E.linear_tc(x, B * S, d, W, 0, 3 * d, bias=b, out_bf16=True)
+    ctx0 = torch.empty(B * S, d, device="cuda", dtype=torch.bfloat16)
+    U.LIB.call("u2gnn_seqattn_tc_fwd_ex", qkv0.data_ptr(), B, S, d, SEED, ST, thr, ctx0.data_ptr(), 1, E._stream())
+    qkv1 = torch.full((B * S, 3 * d), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ctx1 = torch.full((B * S, d), float("nan"), device="cuda", dtype=torch.bfloat16)
+    U.LIB.call("u2gnn_inproj_seqattn_tc_fwd", x.data_ptr(), B, S, d, W.data_ptr(), b.data_ptr(), SEED, ST, thr, qkv1.data_ptr(),
+               ctx1.data_ptr(), E._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(qkv1, qkv0)
+    assert torch.equal(ctx1, ctx0)
