@@ -806,9 +806,22 @@ struct BwdParams {
     float beta;
     float* dW;            // [N1, 64]
     float* db;            // [N1] or null
+    // LNA kernels (N1 == 64): A is not read but computed while it is staged - the backward of the LayerNorm in front of the
+    // projection: dz = LN backward of ln_dy at the saved pre-norm rows ln_z / ln_stats (written to ln_dz, fp32), A = dropout(dz)
+    // rounded to bf16 (never stored), ln_dgamma / ln_dbeta accumulated.  Same arithmetic, same order as ln_bwd_vec_kernel<16>.
+    const float* ln_dy;
+    const float* ln_z;
+    const float* ln_stats;
+    const float* ln_gamma;
+    RngKeys ln_keys;
+    int ln_thr, ln_low;
+    float ln_scale;
+    float* ln_dz;
+    float* ln_dgamma;
+    float* ln_dbeta;
 };
 
-template <int NS>
+template <int NS, bool LNA = false>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_dgrad_wgrad_kernel(const BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -821,7 +834,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_dgrad_wgrad_kernel(const 
     uint8_t* sZero = sOnes + 16384;
     __shared__ uint64_t bar_mma[NS];
     __shared__ uint32_t tmem_slot;
+    __shared__ float s_ln[LNA ? 128 : 1];                     // dgamma | dbeta partial sums of this CTA
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (LNA && tid < 128) s_ln[tid] = 0.0f;
+    float4 ln_ag = make_float4(0.f, 0.f, 0.f, 0.f), ln_ab = ln_ag;   // this thread's four columns (4 (tid & 15) ..), all its rows
     if (tid == 0) {
         for (int i = 0; i < NS; ++i) tc::mbar_init(&bar_mma[i], 1);
         tc::fence_barrier_init();
@@ -847,11 +863,59 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_dgrad_wgrad_kernel(const 
     const int64_t n_tiles = (p.M + TM - 1) / TM;
     const bool b_async = rows_async_ok(p.B, p.b_bf16, 64, p.ldb);
     auto issue_async = [&](int64_t tile, uint8_t* st) {
-        stage_rows_async<kThreads>(st, p.A, tile * TM, p.M, p.N1, p.N1, p.lda, tid);
+        if (!LNA) stage_rows_async<kThreads>(st, p.A, tile * TM, p.M, p.N1, p.N1, p.lda, tid);
         if (b_async) stage_rows_async<kThreads>(st + ga * 16384, p.B, tile * TM, p.M, 64, 64, p.ldb, tid);
     };
     auto finish_sync = [&](int64_t tile, uint8_t* st) {
         if (!b_async) stage_rows_bf16<kThreads, 64>(st + ga * 16384, p.B, p.b_bf16, tile * TM, p.M, 64, 64, p.ldb, tid);
+        if constexpr (LNA) {
+            // LayerNorm backward of the tile's rows (16 lanes x float4 = one row, two rows per warp per step)
+            const int l = tid & 15;
+            const int64_t r0 = tile * TM;
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma) + l);
+            float4 gv[8], xv[8];
+            float2 sv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int64_t row = r0 + ((u * kThreads + tid) >> 4);
+                gv[u] = xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                sv[u] = make_float2(0.f, 0.f);
+                if (row < p.M) {
+                    gv[u] = __ldg(reinterpret_cast<const float4*>(p.ln_dy + row * 64) + l);
+                    xv[u] = __ldg(reinterpret_cast<const float4*>(p.ln_z + row * 64) + l);
+                    sv[u] = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + row);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int rr = (u * kThreads + tid) >> 4;
+                const int64_t row = r0 + rr;
+                const float4 g = gv[u], x = xv[u];
+                const float mean = sv[u].x, rstd = sv[u].y;
+                const float4 xh = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd, (x.w - mean) * rstd);
+                const float4 dh = make_float4(g.x * g4.x, g.y * g4.y, g.z * g4.z, g.w * g4.w);
+                ln_ag.x = fmaf(g.x, xh.x, ln_ag.x); ln_ag.y = fmaf(g.y, xh.y, ln_ag.y);
+                ln_ag.z = fmaf(g.z, xh.z, ln_ag.z); ln_ag.w = fmaf(g.w, xh.w, ln_ag.w);
+                ln_ab.x += g.x; ln_ab.y += g.y; ln_ab.z += g.z; ln_ab.w += g.w;
+                const float m1 = group16_sum((dh.x + dh.y) + (dh.z + dh.w)) * (1.0f / 64.0f);
+                const float m2 = group16_sum((dh.x * xh.x + dh.y * xh.y) + (dh.z * xh.z + dh.w * xh.w)) * (1.0f / 64.0f);
+                float4 o = make_float4(rstd * (dh.x - m1 - xh.x * m2), rstd * (dh.y - m1 - xh.y * m2),
+                                       rstd * (dh.z - m1 - xh.z * m2), rstd * (dh.w - m1 - xh.w * m2));
+                if (row < p.M) reinterpret_cast<float4*>(p.ln_dz + row * 64)[l] = o;
+                if (p.ln_thr) {
+                    const uint64_t el = (uint64_t)(row * 64 + 4 * l);
+                    const uint32_t kw = rng_keep_word_lo(p.ln_keys, el >> 5, p.ln_thr, p.ln_low) >> (el & 31);
+                    o.x = (kw & 1u) ? o.x * p.ln_scale : 0.0f;
+                    o.y = (kw & 2u) ? o.y * p.ln_scale : 0.0f;
+                    o.z = (kw & 4u) ? o.z * p.ln_scale : 0.0f;
+                    o.w = (kw & 8u) ? o.w * p.ln_scale : 0.0f;
+                }
+                uint2 w;
+                w.x = epi::cvt2(o.x, o.y);
+                w.y = epi::cvt2(o.z, o.w);
+                *reinterpret_cast<uint2*>(st + tc::sw128_offset(rr, 4 * l)) = w;
+            }
+        }
     };
     // prologue: tiles 0 .. NS-2 of this CTA
 #pragma unroll
@@ -986,9 +1050,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_dgrad_wgrad_kernel(const 
             if (p.db && n1 < p.N1) atomicAdd(p.db + n1, __uint_as_float(b16[0]));
         }
     }
+    if constexpr (LNA) {
+        ln_ag.x += __shfl_xor_sync(0xffffffffu, ln_ag.x, 16); ln_ag.y += __shfl_xor_sync(0xffffffffu, ln_ag.y, 16);
+        ln_ag.z += __shfl_xor_sync(0xffffffffu, ln_ag.z, 16); ln_ag.w += __shfl_xor_sync(0xffffffffu, ln_ag.w, 16);
+        ln_ab.x += __shfl_xor_sync(0xffffffffu, ln_ab.x, 16); ln_ab.y += __shfl_xor_sync(0xffffffffu, ln_ab.y, 16);
+        ln_ab.z += __shfl_xor_sync(0xffffffffu, ln_ab.z, 16); ln_ab.w += __shfl_xor_sync(0xffffffffu, ln_ab.w, 16);
+        if (lane < 16) {
+            const int l = lane;
+            atomicAdd(&s_ln[4 * l], ln_ag.x); atomicAdd(&s_ln[4 * l + 1], ln_ag.y); atomicAdd(&s_ln[4 * l + 2], ln_ag.z); atomicAdd(&s_ln[4 * l + 3], ln_ag.w);
+            atomicAdd(&s_ln[64 + 4 * l], ln_ab.x); atomicAdd(&s_ln[64 + 4 * l + 1], ln_ab.y); atomicAdd(&s_ln[64 + 4 * l + 2], ln_ab.z); atomicAdd(&s_ln[64 + 4 * l + 3], ln_ab.w);
+        }
+    }
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc<256>(tmem);
+    if (LNA && tid < 128) atomicAdd((tid < 64 ? p.ln_dgamma : p.ln_dbeta) + (tid & 63), s_ln[tid]);
 }
 
 }  // namespace
@@ -1144,5 +1220,36 @@ extern "C" int u2gnn_gemm_tc_dgrad_wgrad(const void* A, int64_t M, int N1, int64
     else if (fixed + 3 * stage <= cap) rc = launch(gemm_tc_dgrad_wgrad_kernel<3>, 3);
     else rc = launch(gemm_tc_dgrad_wgrad_kernel<2>, 2);
     if (rc != U2GNN_OK) return rc;
+    U2GNN_CHECK_LAUNCH();
+}
+
+// out_proj backward with the LayerNorm1 backward in front of it (d = 64): one kernel computes dz = LN backward of dy at the
+// saved pre-norm rows z / stats (written, fp32: the residual gradient), da = dropout(dz) on the fly as the bf16 A operand (never
+// stored), dgamma / dbeta, the input gradient C = da W and the weight / bias gradients dW += da^T B, db += colsum(da).
+// Replaces u2gnn_add_dropout_ln_bwd_ex (bf16 da) + u2gnn_gemm_tc_dgrad_wgrad on the same operands.
+extern "C" int u2gnn_ln_bwd_gemm_tc_dgrad_wgrad(const float* dy, const float* z, const float* stats, const float* gamma, uint64_t seed,
+                                                uint32_t rng_stream, int thr, int64_t M, const void* B, int b_bf16, int64_t ldb,
+                                                const float* W, void* C, int c_bf16, int64_t ldc, float* dz, float* dgamma,
+                                                float* dbeta, float* dW, float* db, u2gnn_stream_t stream) {
+    if (!dy || !z || !stats || !gamma || !B || !W || !C || !dz || !dgamma || !dbeta || !dW || M < 0 || ldb < 64 || ldc < 64 ||
+        thr < 0 || thr > 255)
+        return U2GNN_EINVAL;
+    if ((ldc & 7) || (ldb & (b_bf16 ? 7 : 3))) return U2GNN_EALIGN;
+    if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(B) |
+         reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(gamma)) % 16 || reinterpret_cast<uintptr_t>(stats) % 8)
+        return U2GNN_EALIGN;
+    if (M == 0) return U2GNN_OK;
+    BwdParams p;
+    p.A = nullptr; p.B = B; p.b_bf16 = b_bf16; p.c_bf16 = c_bf16; p.M = M; p.lda = 64; p.ldb = ldb; p.ldc = ldc; p.N1 = 64;
+    p.W = W; p.C = C; p.beta = 0.0f; p.dW = dW; p.db = db;
+    p.ln_dy = dy; p.ln_z = z; p.ln_stats = stats; p.ln_gamma = gamma;
+    p.ln_keys = rng_keys(seed, rng_stream); p.ln_thr = thr; p.ln_low = rng_thr_low(thr);
+    p.ln_scale = thr ? rng_keep_scale(thr) : 1.0f;
+    p.ln_dz = dz; p.ln_dgamma = dgamma; p.ln_dbeta = dbeta;
+    const size_t smem = 1024 + 8192 + 128 * 272 + 2 * 16384 + 4 * (size_t)2 * 16384;
+    const int64_t n_tiles = (M + TM - 1) / TM;
+    const int grid = (int)(n_tiles < U2GNN_NUM_SMS ? n_tiles : U2GNN_NUM_SMS);
+    cudaFuncSetAttribute(gemm_tc_dgrad_wgrad_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    gemm_tc_dgrad_wgrad_kernel<4, true><<<grid, kThreads, smem, as_stream(stream)>>>(p);
     U2GNN_CHECK_LAUNCH();
 }

@@ -35,6 +35,10 @@ FUSE_LN2_FFN_BWD = os.environ.get("U2GNN_FUSE_LN2", "0") != "0"
 LAST_STEP_BF16 = os.environ.get("U2GNN_LAST_BF16", "1") != "0"            # bf16 mode, d = 64: bf16 qkv / dqkv at the dead-row-eliminated last timestep
 FUSE_PROJ_BWD = os.environ.get("U2GNN_FUSE_PROJ_BWD", "1") != "0"         # bf16 mode, d = 64: projection input + weight gradients in one pass over the output gradient
 FUSE_INPROJ_ATTN = os.environ.get("U2GNN_FUSE_INPROJ_ATTN", "1") != "0"   # bf16 mode, d = 64: in_proj inside the attention-forward kernel (qkv written once, never re-read in the forward)
+# bf16 mode, d = 64: LayerNorm1 backward inside the out_proj backward kernel (da never stored).  Parity-green (dz, dctx bit-identical)
+# but SLOWER as measured (66.06 against 65.48 ms per step): one CTA of 256 threads per SM doing the LayerNorm arithmetic while
+# it stages the operand is less efficient than the 24-warp LayerNorm pass plus the cp.async-fed GEMM.  Off by default.
+FUSE_LN1_PROJ_BWD = os.environ.get("U2GNN_FUSE_LN1_PROJ_BWD", "0") != "0"
 FLOPS = {}    # entry point -> algorithmic flops issued while LIB.timed is active (bench.py roofline)
 
 
@@ -444,11 +448,23 @@ def _encoder_attn_bwd(dy1, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
     f32 = dict(dtype=torch.float32, device=dev)
     tc_proj = sv.packed is not None and not long_seq and d <= 64
     tc_attn = tc_proj and d == 64 and Sq == S and S >= 2
-    # da only feeds the two out_proj tensor-core GEMMs (weight gradient, input gradient): bf16, rounded once by its producer
-    dz1, da = add_dropout_ln_bwd(dy1, sv.z1, sv.st1, Mq, d, p["norm1.weight"], (seed, drop_ids[1], thr),
-                                 g["norm1.weight"], g["norm1.bias"], da_bf16=tc_proj and d == 64 and FUSE_LN_BWD)
     fuse_bwd = tc_proj and d == 64 and FUSE_PROJ_BWD
-    if fuse_bwd and da.dtype == torch.bfloat16:
+    if fuse_bwd and FUSE_LN1_PROJ_BWD:
+        # LayerNorm1 backward + out_proj backward in one kernel: da is formed while the operand tile is staged and never stored
+        dz1 = torch.empty((Mq, d), **f32)
+        dctx = torch.empty((Mq, d), dtype=torch.bfloat16 if tc_attn else torch.float32, device=dev)
+        LIB.call("u2gnn_ln_bwd_gemm_tc_dgrad_wgrad", _ptr(dy1), _ptr(sv.z1), _ptr(sv.st1), _ptr(p["norm1.weight"]), seed, drop_ids[1],
+                 thr, Mq, _ptr(sv.ctx), int(sv.ctx.dtype == torch.bfloat16), d, _ptr(p["self_attn.out_proj.weight"]), _ptr(dctx),
+                 int(tc_attn), d, _ptr(dz1), _ptr(g["norm1.weight"]), _ptr(g["norm1.bias"]), _ptr(g["self_attn.out_proj.weight"]),
+                 _ptr(g["self_attn.out_proj.bias"]), _stream())
+        da = None
+    else:
+        # da only feeds the two out_proj tensor-core GEMMs (weight gradient, input gradient): bf16, rounded once by its producer
+        dz1, da = add_dropout_ln_bwd(dy1, sv.z1, sv.st1, Mq, d, p["norm1.weight"], (seed, drop_ids[1], thr),
+                                     g["norm1.weight"], g["norm1.bias"], da_bf16=tc_proj and d == 64 and FUSE_LN_BWD)
+    if da is None:
+        pass
+    elif fuse_bwd and da.dtype == torch.bfloat16:
         # out_proj backward: input gradient and weight gradient from one pass over da
         dctx = proj_bwd_tc(da, Mq, d, sv.ctx, p["self_attn.out_proj.weight"], g["self_attn.out_proj.weight"],
                            g["self_attn.out_proj.bias"], out_bf16=tc_attn)

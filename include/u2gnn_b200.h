@@ -253,6 +253,15 @@ int u2gnn_gemm_tc_wgrad_ex(const void* A, int a_bf16, int64_t M, int N1, int64_t
 int u2gnn_gemm_tc_dgrad_wgrad(const void* A, int64_t M, int N1, int64_t lda, const void* B, int b_bf16, int64_t ldb,
                               const float* W, void* C, int c_bf16, int64_t ldc, float beta, float* dW, float* db,
                               u2gnn_stream_t stream);
+/* LayerNorm1 backward + out_proj backward in ONE kernel (d = 64): dz[M,64] = LN backward of dy at the saved pre-norm rows z and
+ * stats[M,2] (the residual gradient, fp32), da = dropout(dz; seed, rng_stream, thr) formed on the fly as the bf16 operand (never
+ * stored), dgamma / dbeta (+=), C[M,64] = da W (the gradient at the attention output; fp32 or bf16), dW[64,64] += da^T B,
+ * db[64] += colsum(da) with B[M,64] = the attention output rows.  Same results as u2gnn_add_dropout_ln_bwd_ex(da_bf16 = 1)
+ * followed by u2gnn_gemm_tc_dgrad_wgrad.  (torch/nn/modules/transformer.py:946,969-972 autograd) */
+int u2gnn_ln_bwd_gemm_tc_dgrad_wgrad(const float* dy, const float* z, const float* stats, const float* gamma, uint64_t seed,
+                                     uint32_t rng_stream, int thr, int64_t M, const void* B, int b_bf16, int64_t ldb,
+                                     const float* W, void* C, int c_bf16, int64_t ldc, float* dz, float* dgamma, float* dbeta,
+                                     float* dW, float* db, u2gnn_stream_t stream);
 /* out_proj + dropout + residual + LayerNorm1 in one kernel (torch/nn/modules/transformer.py:946,969-972:
  * x = norm1(x + dropout1(self_attn(x)))): z[M,64] = res + dropout(A[M,K] W^T + bias), y = LayerNorm(z) * gamma + beta,
  * stats[M,2] = (mean, rstd).  N = d = 64 only; res row stride ldres (elements) so the last timestep can read position 0 of
