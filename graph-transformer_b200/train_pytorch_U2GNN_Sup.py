@@ -36,6 +36,8 @@ def parse_args(argv=None):
     p.add_argument("--attn_axis", default="nodes", choices=["nodes", "neighbors"],
                    help="'nodes' = reference as written, 'neighbors' = intended layout (SURVEY.md F1)")
     p.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    p.add_argument("--label_smoothing_style", default="reference", choices=["reference", "tf"],
+                   help="reference: 0.9 / 0.1/(C-1) targets of the PyTorch file; tf: tf.losses.softmax_cross_entropy(label_smoothing=0.1)")
     p.add_argument("--tie_timesteps", action="store_true",
                    help="share ONE encoder weight set across the T timesteps (the published Universal-Transformer U2GNN); "
                         "default = T independent sets like the reference PyTorch file")
@@ -61,7 +63,8 @@ def run(args, log=print):
                                dropout=args.dropout, num_self_att_layers=args.num_timesteps,
                                num_U2GNN_layers=args.num_hidden_layers, attn_axis=args.attn_axis,
                                tie_timesteps=args.tie_timesteps).to(dev)
-    trainer = SupTrainer(model, lr=args.learning_rate, precision=args.precision, seed=123)
+    trainer = SupTrainer(model, lr=args.learning_rate, precision=args.precision, seed=123,
+                         smoothing_style=args.label_smoothing_style)
     steps_per_epoch = int((len(train_graphs) - 1) / args.batch_size) + 1
 
     def to_dev(batch):

@@ -75,12 +75,26 @@ class FlatArena:
         return float(self.sumsq.sqrt().item()) if want_norm else None
 
 
+def effective_smoothing(eps, classes, style="reference"):
+    """Label-smoothing strength for the loss kernel, which implements the reference's targets (pytorch_U2GNN_Sup.py:48-59):
+    1 - eps on the label, eps / (C - 1) elsewhere.  style="tf" gives the TF model's targets (tf.losses.softmax_cross_entropy
+    label_smoothing, U2GNN_tf/model_U2GNN_Sup_multi.py:73-75): 1 - eps + eps / C on the label, eps / C elsewhere - the SAME
+    family with eps' = eps (C - 1) / C, so no second kernel path is needed."""
+    if style == "reference":
+        return float(eps)
+    if style == "tf":
+        return float(eps) * (classes - 1) / classes
+    raise ValueError("smoothing_style must be 'reference' or 'tf'")
+
+
 class SupTrainer:
     """Supervised fused step.  batch = (input_x[N,S] int64, rowptr[G+1] int64, X[N,d] f32, labels[G] int64)."""
 
-    def __init__(self, model: TransformerU2GNN, lr=5e-4, smoothing=0.1, max_norm=0.5, seed=123, precision="fp32"):
+    def __init__(self, model: TransformerU2GNN, lr=5e-4, smoothing=0.1, max_norm=0.5, seed=123, precision="fp32",
+                 smoothing_style="reference"):
         if precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")
+        smoothing = effective_smoothing(smoothing, model.num_classes, smoothing_style)
         self.precision = precision
         model.precision = precision
         self.model, self.lr, self.smoothing, self.max_norm = model, lr, smoothing, max_norm

@@ -138,3 +138,19 @@ def test_tied_timesteps_share_one_weight_set_and_one_gradient_slot(U):
 def test_label_smoothing_matches_oracle(U):
     y = torch.tensor([0, 2, 1, 1])
     assert np.allclose(U.label_smoothing(y, 3).numpy(), O.label_smoothing(y.numpy(), 3))
+
+
+def test_tf_style_label_smoothing_is_the_reference_formula_with_rescaled_eps(U):
+    """tf.losses.softmax_cross_entropy(label_smoothing=eps): onehot * (1 - eps) + eps / C  ==  the reference's targets with
+    eps' = eps (C - 1) / C (trainer.effective_smoothing), so the loss kernel needs no second path."""
+    from u2gnn_b200.trainer import effective_smoothing
+    labels = torch.tensor([0, 2, 1, 2])
+    for C in (2, 3, 7):
+        lab = labels % C
+        eps = 0.1
+        tf_targets = torch.nn.functional.one_hot(lab, C).float() * (1 - eps) + eps / C
+        ours = U.label_smoothing(lab, C, smoothing=effective_smoothing(eps, C, "tf"))
+        assert torch.allclose(ours, tf_targets, atol=1e-7)
+        assert effective_smoothing(eps, C, "reference") == eps
+    with pytest.raises(ValueError):
+        effective_smoothing(0.1, 2, "other")
