@@ -457,24 +457,21 @@ def _encoder_attn_bwd(dy1, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
                  thr, Mq, _ptr(sv.ctx), int(sv.ctx.dtype == torch.bfloat16), d, _ptr(p["self_attn.out_proj.weight"]), _ptr(dctx),
                  int(tc_attn), d, _ptr(dz1), _ptr(g["norm1.weight"]), _ptr(g["norm1.bias"]), _ptr(g["self_attn.out_proj.weight"]),
                  _ptr(g["self_attn.out_proj.bias"]), _stream())
-        da = None
     else:
         # da only feeds the two out_proj tensor-core GEMMs (weight gradient, input gradient): bf16, rounded once by its producer
         dz1, da = add_dropout_ln_bwd(dy1, sv.z1, sv.st1, Mq, d, p["norm1.weight"], (seed, drop_ids[1], thr),
                                      g["norm1.weight"], g["norm1.bias"], da_bf16=tc_proj and d == 64 and FUSE_LN_BWD)
-    if da is None:
-        pass
-    elif fuse_bwd and da.dtype == torch.bfloat16:
-        # out_proj backward: input gradient and weight gradient from one pass over da
-        dctx = proj_bwd_tc(da, Mq, d, sv.ctx, p["self_attn.out_proj.weight"], g["self_attn.out_proj.weight"],
-                           g["self_attn.out_proj.bias"], out_bf16=tc_attn)
-    elif tc_proj:
-        wgrad_tc(da, Mq, d, sv.ctx, d, g["self_attn.out_proj.weight"], g["self_attn.out_proj.bias"])
-        dctx = linear_tc(da, Mq, d, p["self_attn.out_proj.weight"], 1, d, out_bf16=tc_attn)
-    else:
-        wgrad(da, Mq, d, sv.ctx, d, g["self_attn.out_proj.weight"], g["self_attn.out_proj.bias"])
-        dctx = torch.empty((Mq, d), **f32)
-        sgemm(0, 0, Mq, d, d, da, d, p["self_attn.out_proj.weight"], d, dctx, d)
+        if fuse_bwd and da.dtype == torch.bfloat16:
+            # out_proj backward: input gradient and weight gradient from one pass over da
+            dctx = proj_bwd_tc(da, Mq, d, sv.ctx, p["self_attn.out_proj.weight"], g["self_attn.out_proj.weight"],
+                               g["self_attn.out_proj.bias"], out_bf16=tc_attn)
+        elif tc_proj:
+            wgrad_tc(da, Mq, d, sv.ctx, d, g["self_attn.out_proj.weight"], g["self_attn.out_proj.bias"])
+            dctx = linear_tc(da, Mq, d, p["self_attn.out_proj.weight"], 1, d, out_bf16=tc_attn)
+        else:
+            wgrad(da, Mq, d, sv.ctx, d, g["self_attn.out_proj.weight"], g["self_attn.out_proj.bias"])
+            dctx = torch.empty((Mq, d), **f32)
+            sgemm(0, 0, Mq, d, d, da, d, p["self_attn.out_proj.weight"], d, dctx, d)
     tc_last = sv.qkv.dtype == torch.bfloat16 and Sq == 1
     dqkv = torch.empty((M, 3 * d), dtype=torch.bfloat16 if (tc_attn or tc_last) else torch.float32, device=dev)
     if long_seq:
