@@ -249,7 +249,8 @@ int u2gnn_gemm_tc_wgrad_ex(const void* A, int a_bf16, int64_t M, int N1, int64_t
 /* backward of one attention-block projection in a single pass over its output gradient A[M,N1] (bf16; N1 = 64, 128, 192
  * or 256): input gradient C[M,64] = A W (+ beta*C; W = the layer's weight [N1,64]; C fp32, or bf16 with beta 0) AND
  * dW[N1,64] += A^T B, db[N1] += colsum(A) (B[M,64] = the layer's input rows, fp32 or bf16; db may be null).  Same results as
- * u2gnn_gemm_tc_rows_ex(w_kn = 1) + u2gnn_gemm_tc_wgrad_ex on the same operands. */
+ * u2gnn_gemm_tc_rows_ex(w_kn = 1) + u2gnn_gemm_tc_wgrad_ex on the same operands.  (autograd of the in_proj / out_proj F.linear
+ * calls of nn.MultiheadAttention, which pytorch_U2GNN_Sup.py:20-21 instantiates through nn.TransformerEncoderLayer) */
 int u2gnn_gemm_tc_dgrad_wgrad(const void* A, int64_t M, int N1, int64_t lda, const void* B, int b_bf16, int64_t ldb,
                               const float* W, void* C, int c_bf16, int64_t ldc, float beta, float* dW, float* db,
                               u2gnn_stream_t stream);
