@@ -448,6 +448,40 @@ def sampled_softmax_bwd(dloss, c, x, labels, W_shape, sample_ids):
     return dx, dW
 
 
+def sampled_softmax_tf_fwd(x, labels, W, b, sample_ids, true_q, samp_q, remove_accidental_hits=True):
+    """The TF model's loss (U2GNN_tf/model_U2GNN_Unsup_multi.py:54-58: tf.nn.sampled_softmax_loss with its defaults
+    subtract_log_q=True, remove_accidental_hits=True) - NOT what the reference's PyTorch SampledSoftmax computes (above); restated
+    here as the oracle of the SURVEY.md 8(f) row-4 extra that has no CUDA path yet.
+        t_i  = x_i.W[y_i] + b[y_i] - log Q(y_i)              true_q[i]  = expected count of the label (Log_Uniform_Sampler.cpp:23-32)
+        l_is = x_i.W[s]   + b[s]   - log Q(s)                samp_q[s]  = expected count of sampled id s
+        l_is = -inf where s == y_i (accidental hit);   loss_i = logsumexp([t_i, l_i1 .. l_ins]) - t_i   (label at position 0)."""
+    ids = np.asarray(sample_ids, dtype=np.int64)
+    tw, sw = W[labels], W[ids]
+    t = (x * tw).sum(1) + b[labels] - np.log(true_q)
+    l = x @ sw.T + b[ids][None, :] - np.log(samp_q)[None, :]
+    hit = (ids[None, :] == np.asarray(labels)[:, None]) if remove_accidental_hits else np.zeros(l.shape, dtype=bool)
+    l = np.where(hit, -np.inf, l)
+    m = np.maximum(t, l.max(1))
+    et, el = np.exp(t - m), np.exp(l - m[:, None])
+    denom = et + el.sum(1)
+    loss = np.log(denom) + m - t
+    return loss, dict(tw=tw, sw=sw, p_true=et / denom, p_samp=el / denom[:, None], ids=ids)
+
+
+def sampled_softmax_tf_bwd(dloss, c, x, labels, W_shape):
+    """Gradients of sum_i dloss_i * loss_i of sampled_softmax_tf_fwd wrt x, the class table and the bias."""
+    dt = (c["p_true"] - 1.0) * dloss
+    dl = c["p_samp"] * dloss[:, None]
+    dx = dt[:, None] * c["tw"] + dl @ c["sw"]
+    dW = np.zeros(W_shape, dtype=x.dtype)
+    db = np.zeros(W_shape[0], dtype=x.dtype)
+    np.add.at(dW, labels, dt[:, None] * x)
+    np.add.at(dW, c["ids"], dl.T @ x)
+    np.add.at(db, labels, dt)
+    np.add.at(db, c["ids"], dl.sum(0))
+    return dx, dW, db
+
+
 def unsup_forward(params, X, input_x, input_y, sample_ids, L, T, attn_axis="neighbors", drop=None):
     """Assembled unsupervised model: per-layer position-0 vectors, concat over
     layers, dropout, SampledSoftmax.  Returns (per-node loss[N], cache)."""
