@@ -22,34 +22,66 @@ __device__ __forceinline__ void stage_rows(const float* __restrict__ W, int64_t 
     }
 }
 
+// TF = the TF model's variant (tf.nn.sampled_softmax_loss with its defaults, U2GNN_tf/model_U2GNN_Unsup_multi.py:54-58):
+//   t_i = x_i.W[y_i] + b[y_i] - log true_q[i],   l_is = x_i.W[s] + b[s] - log samp_q[s]  (-inf where s == y_i: accidental hit),
+//   loss_i = log(exp(t_i) + sum_s exp(l_is)) - t_i = log(1 + sum_s exp(l_is - t_i));   denom_out = 1 + sum_s exp(l_is - t_i).
+// Shifting by the true logit keeps the exponentials bounded without a second pass.
+struct TfArgs {
+    const float* bias;     // [V]
+    const float* true_q;   // [N]  expected count of each label
+    const float* samp_q;   // [ns] expected count of each sampled id
+    float* dbias;          // [V]  backward only
+};
+
+template <bool TF>
 __global__ void __launch_bounds__(256) ss_fwd_kernel(const float* __restrict__ x, const int64_t* __restrict__ labels,
                                                      int64_t N, int D, const float* __restrict__ W, int64_t V,
                                                      const int64_t* __restrict__ ids, int ns, int chunk,
                                                      float* __restrict__ loss, float* __restrict__ denom_out,
-                                                     int64_t nodes_per_block) {
+                                                     int64_t nodes_per_block, TfArgs tf) {
     extern __shared__ float sm[];
     const int P = pitch_of(D);
     float* ws = sm;                                   // [chunk][P]
     float* xs = sm + (size_t)chunk * P;               // [warps][D]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, warps = blockDim.x >> 5;
     float* xw = xs + (size_t)w * D;
+    float* offs = xs + (size_t)warps * D;             // TF: [chunk] b[id] - log samp_q
+    int* sid = reinterpret_cast<int*>(offs + chunk);  // TF: [chunk] sampled ids (V < 2^31) for the accidental-hit test
     const int64_t n0 = (int64_t)blockIdx.x * nodes_per_block;
     const int64_t n1 = (n0 + nodes_per_block < N) ? n0 + nodes_per_block : N;
     for (int s0 = 0; s0 < ns; s0 += chunk) {
         const int sc = (ns - s0 < chunk) ? ns - s0 : chunk;
         __syncthreads();
         stage_rows(W, V, ids, s0, sc, D, ws);
+        if (TF) {
+            for (int s = threadIdx.x; s < sc; s += blockDim.x) {
+                const int64_t id = ids[s0 + s];
+                const bool ok = id >= 0 && id < V;
+                offs[s] = ok ? __ldg(tf.bias + id) - logf(tf.samp_q[s0 + s]) : -INFINITY;
+                sid[s] = ok ? (int)id : -1;
+            }
+        }
         __syncthreads();
         for (int64_t i = n0 + w; i < n1; i += warps) {
             __syncwarp();
             for (int c = lane; c < D; c += 32) xw[c] = x[i * D + c];
             __syncwarp();
+            float t = 0.0f;
+            int y = -2;
+            if (TF) {
+                const int64_t yl = labels[i];
+                y = (int)yl;
+                float dot = 0.0f;
+                for (int c = lane; c < D; c += 32) dot = fmaf(xw[c], __ldg(W + yl * D + c), dot);
+                t = warp_sum(dot) + __ldg(tf.bias + yl) - logf(tf.true_q[i]);
+            }
             float part = 0.0f;
             for (int s = lane; s < sc; s += 32) {
                 float dot = 0.0f;
                 const float* wr = ws + s * P;
                 for (int c = 0; c < D; ++c) dot = fmaf(xw[c], wr[c], dot);
-                part += expf(dot);
+                if (TF) part += (sid[s] == y) ? 0.0f : expf(dot + offs[s] - t);
+                else part += expf(dot);
             }
             part = warp_sum(part);
             if (lane == 0) denom_out[i] = (s0 == 0) ? part : denom_out[i] + part;
@@ -58,6 +90,14 @@ __global__ void __launch_bounds__(256) ss_fwd_kernel(const float* __restrict__ x
     __syncthreads();
     // true logits and the loss
     for (int64_t i = n0 + w; i < n1; i += warps) {
+        if (TF) {
+            if (lane == 0) {
+                const float dn = 1.0f + denom_out[i];
+                denom_out[i] = dn;
+                loss[i] = logf(dn);
+            }
+            continue;
+        }
         const int64_t y = labels[i];
         float dot = 0.0f;
         for (int c = lane; c < D; c += 32) dot = fmaf(x[i * D + c], __ldg(W + y * D + c), dot);
@@ -66,12 +106,13 @@ __global__ void __launch_bounds__(256) ss_fwd_kernel(const float* __restrict__ x
     }
 }
 
+template <bool TF>
 __global__ void __launch_bounds__(256) ss_bwd_kernel(const float* __restrict__ dloss, const float* __restrict__ x,
                                                      const int64_t* __restrict__ labels, int64_t N, int D,
                                                      const float* __restrict__ W, int64_t V,
                                                      const int64_t* __restrict__ ids, int ns, int chunk,
                                                      const float* __restrict__ denom, float* __restrict__ dx,
-                                                     float* __restrict__ dW, int64_t nodes_per_block) {
+                                                     float* __restrict__ dW, int64_t nodes_per_block, TfArgs tf) {
     extern __shared__ float sm[];
     const int P = pitch_of(D);
     float* ws = sm;                                   // [chunk][P]   sampled rows
@@ -81,34 +122,62 @@ __global__ void __launch_bounds__(256) ss_bwd_kernel(const float* __restrict__ d
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, warps = blockDim.x >> 5;
     float* xw = xs + (size_t)w * D;
     float* ew = es + (size_t)w * chunk;
+    float* offs = es + (size_t)warps * chunk;         // TF: [chunk] b[id] - log samp_q
+    float* dbs = offs + chunk;                        // TF: [chunk] bias gradient of the staged ids, accumulated per CTA
+    int* sid = reinterpret_cast<int*>(dbs + chunk);   // TF: [chunk] sampled ids
     const int64_t n0 = (int64_t)blockIdx.x * nodes_per_block;
     const int64_t n1 = (n0 + nodes_per_block < N) ? n0 + nodes_per_block : N;
 
-    // true-class term: dx = -dloss * W[y];  dW[y] += -dloss * x
+    // true-class term: dx = g * W[y];  dW[y] += g * x   (g = -dloss; TF: g = (p_true - 1) dloss, p_true = 1 / denom, db[y] += g)
     for (int64_t i = n0 + w; i < n1; i += warps) {
         const int64_t y = labels[i];
-        const float g = -dloss[i];
+        const float g = TF ? (1.0f / denom[i] - 1.0f) * dloss[i] : -dloss[i];
         for (int c = lane; c < D; c += 32) {
             dx[i * D + c] = g * __ldg(W + y * D + c);
             atomicAdd(dW + y * D + c, g * x[i * D + c]);
         }
+        if (TF && lane == 0) atomicAdd(tf.dbias + y, g);
     }
     for (int s0 = 0; s0 < ns; s0 += chunk) {
         const int sc = (ns - s0 < chunk) ? ns - s0 : chunk;
         __syncthreads();
         stage_rows(W, V, ids, s0, sc, D, ws);
         for (int e = threadIdx.x; e < sc * P; e += blockDim.x) dws[e] = 0.0f;
+        if (TF) {
+            for (int s = threadIdx.x; s < sc; s += blockDim.x) {
+                const int64_t id = ids[s0 + s];
+                const bool ok = id >= 0 && id < V;
+                offs[s] = ok ? __ldg(tf.bias + id) - logf(tf.samp_q[s0 + s]) : -INFINITY;
+                sid[s] = ok ? (int)id : -1;
+                dbs[s] = 0.0f;
+            }
+        }
         __syncthreads();
         for (int64_t i = n0 + w; i < n1; i += warps) {
             __syncwarp();
             for (int c = lane; c < D; c += 32) xw[c] = x[i * D + c];
             __syncwarp();
+            float t = 0.0f;
+            int y = -2;
+            if (TF) {
+                const int64_t yl = labels[i];
+                y = (int)yl;
+                float dot = 0.0f;
+                for (int c = lane; c < D; c += 32) dot = fmaf(xw[c], __ldg(W + yl * D + c), dot);
+                t = warp_sum(dot) + __ldg(tf.bias + yl) - logf(tf.true_q[i]);
+            }
             const float coef = dloss[i] / denom[i];
             for (int s = lane; s < sc; s += 32) {
                 float dot = 0.0f;
                 const float* wr = ws + s * P;
                 for (int c = 0; c < D; ++c) dot = fmaf(xw[c], wr[c], dot);
-                ew[s] = coef * expf(dot);
+                if (TF) {
+                    const float e = (sid[s] == y) ? 0.0f : coef * expf(dot + offs[s] - t);
+                    ew[s] = e;
+                    atomicAdd(dbs + s, e);
+                } else {
+                    ew[s] = coef * expf(dot);
+                }
             }
             __syncwarp();
             // dx[c] += sum_s e_s W_s[c];  dWs[s][c] += e_s x[c]
@@ -132,6 +201,10 @@ __global__ void __launch_bounds__(256) ss_bwd_kernel(const float* __restrict__ d
             const int64_t id = ids[s0 + s];
             if (id >= 0 && id < V) atomicAdd(dW + id * D + c, dws[s * P + c]);
         }
+        if (TF) {
+            for (int s = threadIdx.x; s < sc; s += blockDim.x)
+                if (sid[s] >= 0) atomicAdd(tf.dbias + sid[s], dbs[s]);
+        }
     }
 }
 
@@ -145,21 +218,58 @@ int pick_chunk(int ns, int D, int copies) {
 
 }  // namespace
 
-extern "C" int u2gnn_sampled_softmax_fwd(const float* x, const int64_t* labels, int64_t N, int D, const float* W,
-                                         int64_t V, const int64_t* ids, int ns, float* loss, float* denom,
-                                         u2gnn_stream_t stream) {
-    if (!x || !labels || !W || !ids || !loss || !denom || N < 0 || D <= 0 || V <= 0 || ns <= 0) return U2GNN_EINVAL;
+namespace {
+
+int launch_ss_fwd(bool is_tf, const float* x, const int64_t* labels, int64_t N, int D, const float* W, int64_t V, const int64_t* ids,
+                  int ns, float* loss, float* denom, TfArgs tf, cudaStream_t st) {
     if (D > 1024) return U2GNN_EUNSUPPORTED;
     if (N == 0) return U2GNN_OK;
     const int chunk = pick_chunk(ns, D, 1);
     const int threads = 256;
-    const size_t smem = ((size_t)chunk * (D | 1) + (size_t)(threads / 32) * D) * sizeof(float);
+    const size_t smem = ((size_t)chunk * (D | 1) + (size_t)(threads / 32) * D + (size_t)2 * chunk) * sizeof(float);
     const int grid = grid_for(N, 64, 2);
     const int64_t npb = ceil_div64(N, grid);
-    cudaFuncSetAttribute(ss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    ss_fwd_kernel<<<(unsigned)ceil_div64(N, npb), threads, smem, as_stream(stream)>>>(x, labels, N, D, W, V, ids, ns, chunk,
-                                                                                    loss, denom, npb);
+    const unsigned blocks = (unsigned)ceil_div64(N, npb);
+    if (is_tf) {
+        cudaFuncSetAttribute(ss_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ss_fwd_kernel<true><<<blocks, threads, smem, st>>>(x, labels, N, D, W, V, ids, ns, chunk, loss, denom, npb, tf);
+    } else {
+        cudaFuncSetAttribute(ss_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ss_fwd_kernel<false><<<blocks, threads, smem, st>>>(x, labels, N, D, W, V, ids, ns, chunk, loss, denom, npb, tf);
+    }
     U2GNN_CHECK_LAUNCH();
+}
+
+int launch_ss_bwd(bool is_tf, const float* dloss, const float* x, const int64_t* labels, int64_t N, int D, const float* W, int64_t V,
+                  const int64_t* ids, int ns, const float* denom, float* dx, float* dW, TfArgs tf, cudaStream_t st) {
+    if (D > 1024) return U2GNN_EUNSUPPORTED;
+    if (N == 0) return U2GNN_OK;
+    const int threads = 256, warps = threads / 32;
+    int chunk = pick_chunk(ns, D, 2);
+    // es needs warps*chunk floats on top of the two staged copies (+ 3 chunk for the TF offsets / bias gradients / ids)
+    auto floats = [&](int ch) { return (size_t)2 * ch * (D | 1) + (size_t)warps * (D + ch) + (size_t)3 * ch; };
+    while (chunk > 1 && floats(chunk) > (size_t)(48 * 1024)) chunk /= 2;
+    const size_t smem = floats(chunk) * sizeof(float);
+    const int grid = grid_for(N, 64, 1);
+    const int64_t npb = ceil_div64(N, grid);
+    const unsigned blocks = (unsigned)ceil_div64(N, npb);
+    if (is_tf) {
+        cudaFuncSetAttribute(ss_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ss_bwd_kernel<true><<<blocks, threads, smem, st>>>(dloss, x, labels, N, D, W, V, ids, ns, chunk, denom, dx, dW, npb, tf);
+    } else {
+        cudaFuncSetAttribute(ss_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ss_bwd_kernel<false><<<blocks, threads, smem, st>>>(dloss, x, labels, N, D, W, V, ids, ns, chunk, denom, dx, dW, npb, tf);
+    }
+    U2GNN_CHECK_LAUNCH();
+}
+
+}  // namespace
+
+extern "C" int u2gnn_sampled_softmax_fwd(const float* x, const int64_t* labels, int64_t N, int D, const float* W,
+                                         int64_t V, const int64_t* ids, int ns, float* loss, float* denom,
+                                         u2gnn_stream_t stream) {
+    if (!x || !labels || !W || !ids || !loss || !denom || N < 0 || D <= 0 || V <= 0 || ns <= 0) return U2GNN_EINVAL;
+    return launch_ss_fwd(false, x, labels, N, D, W, V, ids, ns, loss, denom, TfArgs{nullptr, nullptr, nullptr, nullptr}, as_stream(stream));
 }
 
 extern "C" int u2gnn_sampled_softmax_bwd(const float* dloss, const float* x, const int64_t* labels, int64_t N, int D,
@@ -167,17 +277,28 @@ extern "C" int u2gnn_sampled_softmax_bwd(const float* dloss, const float* x, con
                                          float* dx, float* dW, u2gnn_stream_t stream) {
     if (!dloss || !x || !labels || !W || !ids || !denom || !dx || !dW || N < 0 || D <= 0 || V <= 0 || ns <= 0)
         return U2GNN_EINVAL;
-    if (D > 1024) return U2GNN_EUNSUPPORTED;
-    if (N == 0) return U2GNN_OK;
-    const int threads = 256, warps = threads / 32;
-    int chunk = pick_chunk(ns, D, 2);
-    // es needs warps*chunk floats on top of the two staged copies
-    while (chunk > 1 && ((size_t)2 * chunk * (D | 1) + (size_t)warps * (D + chunk)) > (size_t)(48 * 1024)) chunk /= 2;
-    const size_t smem = ((size_t)2 * chunk * (D | 1) + (size_t)warps * (D + chunk)) * sizeof(float);
-    const int grid = grid_for(N, 64, 1);
-    const int64_t npb = ceil_div64(N, grid);
-    cudaFuncSetAttribute(ss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    ss_bwd_kernel<<<(unsigned)ceil_div64(N, npb), threads, smem, as_stream(stream)>>>(dloss, x, labels, N, D, W, V, ids, ns,
-                                                                                    chunk, denom, dx, dW, npb);
-    U2GNN_CHECK_LAUNCH();
+    return launch_ss_bwd(false, dloss, x, labels, N, D, W, V, ids, ns, denom, dx, dW, TfArgs{nullptr, nullptr, nullptr, nullptr},
+                         as_stream(stream));
+}
+
+// TF-model variant (see TfArgs): bias[V], true_q[N] / samp_q[ns] = expected counts from u2gnn_logu_expected_count.
+extern "C" int u2gnn_sampled_softmax_tf_fwd(const float* x, const int64_t* labels, int64_t N, int D, const float* W, const float* bias,
+                                            int64_t V, const int64_t* ids, int ns, const float* true_q, const float* samp_q,
+                                            float* loss, float* denom, u2gnn_stream_t stream) {
+    if (!x || !labels || !W || !bias || !ids || !true_q || !samp_q || !loss || !denom || N < 0 || D <= 0 || V <= 0 || ns <= 0)
+        return U2GNN_EINVAL;
+    if (V > 2147483647LL) return U2GNN_EUNSUPPORTED;
+    return launch_ss_fwd(true, x, labels, N, D, W, V, ids, ns, loss, denom, TfArgs{bias, true_q, samp_q, nullptr}, as_stream(stream));
+}
+
+extern "C" int u2gnn_sampled_softmax_tf_bwd(const float* dloss, const float* x, const int64_t* labels, int64_t N, int D,
+                                            const float* W, const float* bias, int64_t V, const int64_t* ids, int ns,
+                                            const float* true_q, const float* samp_q, const float* denom, float* dx, float* dW,
+                                            float* dbias, u2gnn_stream_t stream) {
+    if (!dloss || !x || !labels || !W || !bias || !ids || !true_q || !samp_q || !denom || !dx || !dW || !dbias || N < 0 || D <= 0 ||
+        V <= 0 || ns <= 0)
+        return U2GNN_EINVAL;
+    if (V > 2147483647LL) return U2GNN_EUNSUPPORTED;
+    return launch_ss_bwd(true, dloss, x, labels, N, D, W, V, ids, ns, denom, dx, dW, TfArgs{bias, true_q, samp_q, dbias},
+                         as_stream(stream));
 }

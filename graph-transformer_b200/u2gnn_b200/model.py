@@ -290,6 +290,41 @@ class _SampledSoftmaxFn(torch.autograd.Function):
         return dx, dW, None, None
 
 
+class _SampledSoftmaxTFFn(torch.autograd.Function):
+    """tf.nn.sampled_softmax_loss semantics (bias, log-Q correction, accidental hits removed, label inside the softmax)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, labels, ids, true_q, samp_q):
+        x, Wd, bd = x.detach().contiguous(), W.detach(), b.detach()
+        N, D = x.shape
+        loss = torch.empty(N, dtype=torch.float32, device=x.device)
+        denom = torch.empty(N, dtype=torch.float32, device=x.device)
+        LIB.call("u2gnn_sampled_softmax_tf_fwd", x.data_ptr(), labels.data_ptr(), N, D, Wd.data_ptr(), bd.data_ptr(), W.shape[0],
+                 ids.data_ptr(), ids.numel(), true_q.data_ptr(), samp_q.data_ptr(), loss.data_ptr(), denom.data_ptr(), E._stream())
+        ctx.args = (x, Wd, bd, labels, ids, true_q, samp_q, denom)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        x, W, b, labels, ids, true_q, samp_q, denom = ctx.args
+        N, D = x.shape
+        dloss = dloss.contiguous()
+        dx = torch.empty_like(x)
+        dW = torch.zeros_like(W)
+        db = torch.zeros_like(b)
+        LIB.call("u2gnn_sampled_softmax_tf_bwd", dloss.data_ptr(), x.data_ptr(), labels.data_ptr(), N, D, W.data_ptr(), b.data_ptr(),
+                 W.shape[0], ids.data_ptr(), ids.numel(), true_q.data_ptr(), samp_q.data_ptr(), denom.data_ptr(), dx.data_ptr(),
+                 dW.data_ptr(), db.data_ptr(), E._stream())
+        return dx, dW, db, None, None, None, None
+
+
+def sampled_softmax_tf(inputs, weight, bias, labels, ids, true_q, samp_q):
+    """Per-node loss of the TF model (U2GNN_tf/model_U2GNN_Unsup_multi.py:54-58) on the device; `true_q` / `samp_q` are the
+    expected counts from LogUniformSampler.expected_count_device."""
+    f32 = lambda t: t.to(torch.float32).contiguous()
+    return _SampledSoftmaxTFFn.apply(inputs, weight, bias, labels.contiguous(), ids.contiguous(), f32(true_q), f32(samp_q))
+
+
 class SampledSoftmax(nn.Module):
     """sampled_softmax.py:11-56.  forward() draws the negatives on the device (no D2H sync);
     sampled() takes injected `sample_values = (ids, true_freq, sample_freq)` like the reference."""

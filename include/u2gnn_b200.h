@@ -161,6 +161,18 @@ int u2gnn_sampled_softmax_fwd(const float* x, const int64_t* labels, int64_t N, 
 int u2gnn_sampled_softmax_bwd(const float* dloss, const float* x, const int64_t* labels, int64_t N, int D,
                               const float* W, int64_t V, const int64_t* ids, int ns, const float* denom, float* dx,
                               float* dW, u2gnn_stream_t stream);
+/* TF-model variant of the loss (U2GNN_tf/model_U2GNN_Unsup_multi.py:54-58, tf.nn.sampled_softmax_loss with
+ * its defaults): t_i = x_i.W[y_i] + bias[y_i] - log true_q[i], l_is = x_i.W[s] + bias[s] - log samp_q[s] (accidental hits
+ * s == y_i removed), loss_i = log(exp t_i + sum_s exp l_is) - t_i.  true_q / samp_q are the expected counts of the labels and of
+ * the sampled ids (u2gnn_logu_expected_count, Log_Uniform_Sampler.cpp:23-32).  denom[N] is saved for the backward, which also
+ * accumulates the bias gradient dbias[V] (+=, like dW). */
+int u2gnn_sampled_softmax_tf_fwd(const float* x, const int64_t* labels, int64_t N, int D, const float* W, const float* bias,
+                                 int64_t V, const int64_t* ids, int ns, const float* true_q, const float* samp_q, float* loss,
+                                 float* denom, u2gnn_stream_t stream);
+int u2gnn_sampled_softmax_tf_bwd(const float* dloss, const float* x, const int64_t* labels, int64_t N, int D, const float* W,
+                                 const float* bias, int64_t V, const int64_t* ids, int ns, const float* true_q,
+                                 const float* samp_q, const float* denom, float* dx, float* dW, float* dbias,
+                                 u2gnn_stream_t stream);
 
 /* ---- K8: fused global-norm clip + Adam.  Replaces clip_grad_norm_(params, 0.5) + Adam.step()
  *      (train_pytorch_U2GNN_Sup.py:145,160-161) over ONE flat parameter arena.

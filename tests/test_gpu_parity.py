@@ -270,6 +270,36 @@ def test_sampled_softmax_large_sample_chunking(U):
     assert rel_err(ss.weight.grad.cpu().numpy(), dW) < TOL
 
 
+@pytest.mark.parametrize("N,D,V,ns", [(300, 4, 8792, 512), (77, 130, 5000, 700), (1000, 8, 100, 50)])
+def test_sampled_softmax_tf_variant_against_oracle(U, N, D, V, ns):
+    """TF-model loss (bias, log-Q correction from the device sampler's expected counts, accidental hits removed, label inside the
+    softmax) against the oracle pinned on torch autograd (tests/test_oracle_golden.py): loss, dx, dW, db."""
+    from u2gnn_b200.model import sampled_softmax_tf
+    rng = np.random.default_rng(N + D)
+    x = (0.3 * rng.standard_normal((N, D))).astype(np.float32)
+    W = (0.3 * rng.standard_normal((V, D))).astype(np.float32)
+    b = (0.1 * rng.standard_normal(V)).astype(np.float32)
+    y = rng.integers(0, V, size=N).astype(np.int64)
+    smp = U.LogUniformSampler(V, torch.device("cuda"))
+    ids = smp.sample_device(ns)
+    y[:5] = ids[:5].cpu().numpy()                                  # accidental hits
+    yt = dev(y)
+    true_q = smp.expected_count_device(yt)
+    samp_q = smp.expected_count_device(ids)
+    xt, Wt, bt = dev(x).requires_grad_(True), dev(W).requires_grad_(True), dev(b).requires_grad_(True)
+    loss = sampled_softmax_tf(xt, Wt, bt, yt, ids, true_q, samp_q)
+    ids_h = ids.cpu().numpy()
+    lo, cache = O.sampled_softmax_tf_fwd(x.astype(np.float64), y, W.astype(np.float64), b.astype(np.float64), ids_h,
+                                         true_q.cpu().numpy().astype(np.float64), samp_q.cpu().numpy().astype(np.float64))
+    assert rel_err(loss.detach().cpu().numpy(), lo) < TOL
+    w = rng.standard_normal(N).astype(np.float32)
+    (loss * dev(w)).sum().backward()
+    dx, dW, db = O.sampled_softmax_tf_bwd(w.astype(np.float64), cache, x.astype(np.float64), y, W.shape)
+    assert rel_err(xt.grad.cpu().numpy(), dx) < TOL
+    assert rel_err(Wt.grad.cpu().numpy(), dW) < TOL
+    assert rel_err(bt.grad.cpu().numpy(), db) < TOL
+
+
 # ------------------------------------------------------------------ size-independent properties at scale
 def test_large_gather_pool_properties(U):
     from u2gnn_b200 import engine as E
