@@ -35,7 +35,7 @@ int ffn_tc_dgrad_launch(const float* y1, const float* df, const float* dz, float
                         const void* packed, uint64_t seed, uint32_t stream_hidden, int thr, void* xb, void* fb, cudaStream_t st,
                         const FfnLnBwd* ln);
 int ffn_tc_wgrad_launch(const void* xb, const void* fb, int64_t M, int d, int ff, const void* packed, float hidden_scale,
-                        uint64_t seed, uint32_t stream_hidden, int thr, float* dW1, float* db1, float* dW2, float* dy1_merged,
+                        uint64_t seed, uint32_t stream_hidden, int thr, float* dW1, float* db1, float* dW2, void* mask,
                         cudaStream_t st);
 
 namespace {
@@ -110,15 +110,6 @@ extern "C" int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const float* d
     uint8_t* xb = static_cast<uint8_t*>(workspace);
     uint8_t* fb = xb + half;
     int rc;
-    if (g_bwd_mode == 1) {
-        if (dy1 != dz && cudaMemcpyAsync(dy1, dz, (size_t)M * d * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(stream)) != cudaSuccess)
-            return U2GNN_ELAUNCH;
-        const int64_t n_tiles = (M + 127) / 128;
-        rows_to_images_kernel<<<(int)(n_tiles < 4 * U2GNN_NUM_SMS ? n_tiles : 4 * U2GNN_NUM_SMS), 256, 0, as_stream(stream)>>>(y1, df, M, d, xb, fb);
-        rc = ffn_tc_wgrad_launch(xb, fb, M, d, ff, packed, hidden_scale, seed, stream_hidden, thr, dW1, db1, dW2, dy1, as_stream(stream));
-        if (rc != U2GNN_OK) return rc;
-        U2GNN_CHECK_LAUNCH();
-    }
     rc = ffn_tc_dgrad_launch(y1, df, dz, dy1, M, d, ff, packed, seed, stream_hidden, thr, xb, fb, as_stream(stream), nullptr);
     if (rc != U2GNN_OK) return rc;
     rc = ffn_tc_wgrad_launch(xb, fb, M, d, ff, packed, hidden_scale, seed, stream_hidden, thr, dW1, db1, dW2, nullptr, as_stream(stream));

@@ -163,11 +163,57 @@ __global__ void __launch_bounds__(128) red_probe_kernel(float* __restrict__ buf,
         }
     }
 }
+
+// bulk reductions (cp.reduce.async.bulk ... add.f32, issued by the copy engine instead of the LSU): the same split-K pattern.
+// mode 4: 128 threads, one 256-byte row each per tile (rows staged at a 272-byte stride); mode 5: one 32 KB operation per tile;
+// mode 6: ONE warp, 64-row halves through a single staging buffer with a read-wait between halves (the merged FFN backward's
+// drain protocol: the wait is the time the staging buffer is blocked).
+__device__ __forceinline__ void bulk_red_add_f32(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(tc::smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__global__ void __launch_bounds__(128) red_bulk_probe_kernel(float* __restrict__ buf, int64_t n_tiles, int groups, int mode) {
+    extern __shared__ __align__(128) uint8_t stage[];
+    for (int e = threadIdx.x; e < 128 * 272 / 4; e += 128) reinterpret_cast<float*>(stage)[e] = 1.0f;
+    tc::fence_proxy_async();
+    __syncthreads();
+    const int slice = blockIdx.x / groups, n_slices = gridDim.x / groups;
+    const int t = threadIdx.x;
+    for (int64_t tile = slice; tile < n_tiles; tile += n_slices) {
+        float* dst = buf + tile * 8192;
+        if (mode == 4) {
+            bulk_red_add_f32(dst + t * 64, stage + t * 272, 256);
+            tc::bulk_commit();
+            tc::bulk_wait_read<8>();
+        } else if (mode == 5) {
+            if (t == 0) {
+                bulk_red_add_f32(dst, stage, 32768);
+                tc::bulk_commit();
+                tc::bulk_wait_read<8>();
+            }
+        } else if (t < 32) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                bulk_red_add_f32(dst + (h * 64 + t) * 64, stage + t * 272, 256);
+                bulk_red_add_f32(dst + (h * 64 + 32 + t) * 64, stage + (32 + t) * 272, 256);
+                tc::bulk_commit();
+                tc::bulk_wait_read<0>();
+                __syncwarp();
+            }
+        }
+    }
+    tc::bulk_wait_all<0>();
+}
 }  // namespace
 
 extern "C" int u2gnn_red_probe(float* buf, int64_t n_tiles, int groups, int mode, u2gnn_stream_t stream) {
     if (!buf || n_tiles < 1 || groups < 1 || groups > U2GNN_NUM_SMS) return U2GNN_EINVAL;
     const int n_slices = U2GNN_NUM_SMS / groups;
+    if (mode >= 4) {
+        red_bulk_probe_kernel<<<groups * n_slices, 128, 128 * 272, as_stream(stream)>>>(buf, n_tiles, groups, mode);
+        U2GNN_CHECK_LAUNCH();
+    }
     red_probe_kernel<<<groups * n_slices, 128, 0, as_stream(stream)>>>(buf, n_tiles, groups, mode);
     U2GNN_CHECK_LAUNCH();
 }
