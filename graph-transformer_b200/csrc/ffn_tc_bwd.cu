@@ -1,18 +1,17 @@
 // Fused bf16 FFN block on tcgen05 + TMEM, backward entry point.  The [rows, ff] hidden activation and its
-// gradient are recomputed on chip (never stored in HBM).  Two implementations (u2gnn_ffn_tc_bwd_mode):
-//
-//   mode 0 (default)  two kernels with opposite loop orders (the hidden is recomputed in both):
-//                       dgrad  (ffn_tc_dgrad.cu: rows outer, ff chunks inner)          dy1 = dz + dPre W1
-//                       wgrad  (ffn_tc_wgrad.cu: one ff chunk per CTA, row tiles inner)  dW1, db1, dW2
-//   mode 1            MERGED: one kernel per (ff chunk, row slice) computes dW1, db1, dW2 AND the chunk's partial of
-//                     dy1 = dz + dPre W1, which it adds into dy1 with vector reductions (ffn_tc_wgrad.cu, MERGED).  The
-//                     bf16 tile images of y1 / dF it streams are produced by rows_to_images_kernel below.
-//                     Parity-tested (tests/test_gpu_tc.py::test_ffn_tc_backward[mode 1]) but SLOWER on B200: 11.31 ms per
-//                     4.19 M rows against 10.81 ms for mode 0.  The 16 chunk partials are 18 GB of L2 reductions per
-//                     launch (3.8 ms at the measured 4.84 TB/s) and they do not overlap the epilogue warps that issue
-//                     them: the kernel takes wgrad (6.3 ms) + reductions instead of hiding them.  Removing the second
-//                     recomputation needs fewer partials per row (a cluster of CTAs reducing dY through distributed
-//                     shared memory), not a faster reduction.
+// gradient are recomputed on chip (never stored in HBM).  Three launches:
+//   images  rows_to_images_kernel: fp32 rows of y1 / dF -> bf16 swizzled [128 x 64] tile images (the operand format both
+//           tensor-core kernels bulk-copy)
+//   wgrad   (ffn_tc_wgrad.cu: one ff chunk per CTA, row tiles inner, computed transposed)  dW1, db1, dW2  + 1 mask bit per
+//           hidden activation (ReLU live AND dropout keep)
+//   dgrad   (ffn_tc_dgrad.cu: rows outer, ff chunks inner)  dy1 = dz + dPre W1, dPre = (dF W2) & mask - no second
+//           recomputation of the hidden: 4 + 2 = 6 executed GEMM units per (tile, chunk) for 4 algorithmic
+//           (round 1: 4 + 3, with the hidden and its gradient staged through shared memory in wgrad).
+// Measured dead end (round 1, kept as a note): ONE merged kernel adding its 16 chunk partials of dy1 into L2 with
+// red.global.add.v4.f32 was slower (11.3 against 10.8 ms per 4.19 M rows): the reductions are LSU-issue bound (0.85-1.3
+// cycles per lane and instruction).  Bulk reductions (cp.reduce.async.bulk, tools/probe_red.py: 5.25 TB/s, issued by the copy
+// engine) would fix the issue cost but need a 34 KB staging buffer per tile in flight, which the merged kernel's shared
+// memory does not have.
 //
 // with X = y1 (block input), dF = gradient at the linear2 output (after the output dropout),
 // dz = gradient at the residual sum.  These are the autograd of linear1/ReLU/dropout/linear2 in
@@ -21,19 +20,8 @@
 #include "tc_common.cuh"
 #include "ffn_epi.cuh"
 
-struct FfnLnBwd {       // LayerNorm2 backward fused into the dgrad loader (ffn_tc_dgrad.cu)
-    const float* dy2;
-    const float* z2;
-    const float* st2;
-    const float* gamma2;
-    uint32_t stream_out;
-    float* dgamma2;
-    float* dbeta2;
-    float* db2;
-};
-int ffn_tc_dgrad_launch(const float* y1, const float* df, const float* dz, float* dy1, int64_t M, int d, int ff,
-                        const void* packed, uint64_t seed, uint32_t stream_hidden, int thr, void* xb, void* fb, cudaStream_t st,
-                        const FfnLnBwd* ln);
+int ffn_tc_dgrad_launch(const float* dz, float* dy1, int64_t M, int d, int ff, const void* packed, const void* fb, const void* mask,
+                        cudaStream_t st);
 int ffn_tc_wgrad_launch(const void* xb, const void* fb, int64_t M, int d, int ff, const void* packed, float hidden_scale,
                         uint64_t seed, uint32_t stream_hidden, int thr, float* dW1, float* db1, float* dW2, void* mask,
                         cudaStream_t st);
@@ -79,18 +67,16 @@ __global__ void __launch_bounds__(256) rows_to_images_kernel(const float* __rest
     }
 }
 
-int g_bwd_mode = 0;
-
 }  // namespace
 
-extern "C" int u2gnn_ffn_tc_bwd_mode(int mode) {
-    g_bwd_mode = mode;
-    return U2GNN_OK;
-}
+namespace {
+// workspace layout: [y1 images | dF images | mask words], all sized for whole PAIRS of 128-row tiles (the dgrad kernel walks pairs)
+inline size_t tiles_padded(int64_t M) { return (size_t)(2 * ((M + 255) / 256)); }
+}  // namespace
 
 extern "C" size_t u2gnn_ffn_tc_bwd_workspace_bytes(int64_t M) {
     if (M < 0) return 0;
-    return (size_t)(2 * ((M + 255) / 256)) * 2 * 16384;      // two images (y1, df) of 16 KB per 128-row tile, pairs of tiles
+    return tiles_padded(M) * (2 * 16384 + 16 * 2048);      // two 16 KB images + 2 KB of mask words per ff chunk (ff <= 2048) per tile
 }
 
 extern "C" int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const float* dz, int64_t M, int d, int ff,
@@ -105,47 +91,15 @@ extern "C" int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const float* d
                      reinterpret_cast<uintptr_t>(dy1)) % 16))
         return U2GNN_EALIGN;
     if (M == 0) return U2GNN_OK;
-    // workspace: bf16 swizzled tile images of y1 and df (written by dgrad, bulk-copied by wgrad)
-    const size_t half = u2gnn_ffn_tc_bwd_workspace_bytes(M) / 2;
+    const size_t tp = tiles_padded(M);
     uint8_t* xb = static_cast<uint8_t*>(workspace);
-    uint8_t* fb = xb + half;
-    int rc;
-    rc = ffn_tc_dgrad_launch(y1, df, dz, dy1, M, d, ff, packed, seed, stream_hidden, thr, xb, fb, as_stream(stream), nullptr);
+    uint8_t* fb = xb + tp * 16384;
+    uint8_t* mask = fb + tp * 16384;
+    const int64_t n_tiles = (M + 127) / 128;
+    rows_to_images_kernel<<<(int)(n_tiles < 4 * U2GNN_NUM_SMS ? n_tiles : 4 * U2GNN_NUM_SMS), 256, 0, as_stream(stream)>>>(y1, df, M, d, xb, fb);
+    int rc = ffn_tc_wgrad_launch(xb, fb, M, d, ff, packed, hidden_scale, seed, stream_hidden, thr, dW1, db1, dW2, mask, as_stream(stream));
     if (rc != U2GNN_OK) return rc;
-    rc = ffn_tc_wgrad_launch(xb, fb, M, d, ff, packed, hidden_scale, seed, stream_hidden, thr, dW1, db1, dW2, nullptr, as_stream(stream));
-    if (rc != U2GNN_OK) return rc;
-    U2GNN_CHECK_LAUNCH();
-}
-
-// LayerNorm2 backward + output dropout + FFN backward (d == 64): dy2 is the gradient at the LayerNorm2 output, z2 / st2 the
-// saved pre-norm rows and (mean, rstd).  The dgrad kernel's dF loader computes dz = LN backward(dy2), dF = dropout(dz) on the
-// fly (the separate LayerNorm-backward pass read 520 and wrote 512 bytes per row), accumulates dgamma2 / dbeta2 and the
-// linear2 bias gradient db2 = colsum(dF), and the drain adds dPre W1 to the parked dz.
-extern "C" int u2gnn_ffn_tc_bwd_ln(const float* y1, const float* dy2, const float* z2, const float* st2, const float* gamma2,
-                                   uint32_t stream_out, int64_t M, int d, int ff, const void* packed, float hidden_scale,
-                                   uint64_t seed, uint32_t stream_hidden, int thr, float* dy1, float* dW1, float* db1, float* dW2,
-                                   float* db2, float* dgamma2, float* dbeta2, void* workspace, size_t workspace_bytes,
-                                   u2gnn_stream_t stream) {
-    if (!y1 || !dy2 || !z2 || !st2 || !gamma2 || !packed || !dy1 || !dW1 || !db1 || !dW2 || !db2 || !dgamma2 || !dbeta2 ||
-        !workspace || M < 0 || thr < 0 || thr > 255)
-        return U2GNN_EINVAL;
-    if (workspace_bytes < u2gnn_ffn_tc_bwd_workspace_bytes(M)) return U2GNN_EWORKSPACE;
-    if (reinterpret_cast<uintptr_t>(workspace) % 128) return U2GNN_EALIGN;
-    if (d != 64 || ff < 128 || ff % 128 || ff > 2048) return U2GNN_EUNSUPPORTED;
-    if ((reinterpret_cast<uintptr_t>(y1) | reinterpret_cast<uintptr_t>(dy2) | reinterpret_cast<uintptr_t>(z2) |
-         reinterpret_cast<uintptr_t>(dy1) | reinterpret_cast<uintptr_t>(gamma2)) % 16 || reinterpret_cast<uintptr_t>(st2) % 8)
-        return U2GNN_EALIGN;
-    if (dy1 == dy2 || dy1 == z2) return U2GNN_EINVAL;          // dy1 is written while later tiles of dy2 / z2 are still unread
-    if (M == 0) return U2GNN_OK;
-    const size_t half = u2gnn_ffn_tc_bwd_workspace_bytes(M) / 2;
-    uint8_t* xb = static_cast<uint8_t*>(workspace);
-    uint8_t* fb = xb + half;
-    FfnLnBwd ln;
-    ln.dy2 = dy2; ln.z2 = z2; ln.st2 = st2; ln.gamma2 = gamma2; ln.stream_out = stream_out;
-    ln.dgamma2 = dgamma2; ln.dbeta2 = dbeta2; ln.db2 = db2;
-    int rc = ffn_tc_dgrad_launch(y1, nullptr, dy1, dy1, M, d, ff, packed, seed, stream_hidden, thr, xb, fb, as_stream(stream), &ln);
-    if (rc != U2GNN_OK) return rc;
-    rc = ffn_tc_wgrad_launch(xb, fb, M, d, ff, packed, hidden_scale, seed, stream_hidden, thr, dW1, db1, dW2, nullptr, as_stream(stream));
+    rc = ffn_tc_dgrad_launch(dz, dy1, M, d, ff, packed, fb, mask, as_stream(stream));
     if (rc != U2GNN_OK) return rc;
     U2GNN_CHECK_LAUNCH();
 }

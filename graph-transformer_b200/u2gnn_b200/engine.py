@@ -28,10 +28,6 @@ STREAM_POOLED = 1
 STREAM_CONCAT = 9
 FUSE_OUT_PROJ_LN = os.environ.get("U2GNN_FUSE_EPILOGUES", "1") != "0"   # bf16 mode, d = 64: out_proj + dropout + residual + LayerNorm1 in one kernel (False: GEMM then LayerNorm kernel)
 FUSE_LN_BWD = os.environ.get("U2GNN_FUSE_EPILOGUES", "1") != "0"        # bf16 mode: bf16 da out of the LayerNorm1 backward, linear2 bias gradient inside the LayerNorm2 backward
-# bf16 mode, d = 64: LayerNorm2 backward inside the FFN dgrad kernel's loader.  Parity-green (bit-identical dy1) but SLOWER as
-# measured on B200 (73.1 against 71.2 ms per step): the dgrad kernel's row phase is exposed (nothing overlaps it), so the extra
-# load round trips and shuffles there cost more than the separate 64 %-of-HBM LayerNorm pass they replace.  Off by default.
-FUSE_LN2_FFN_BWD = os.environ.get("U2GNN_FUSE_LN2", "0") != "0"
 LAST_STEP_BF16 = os.environ.get("U2GNN_LAST_BF16", "1") != "0"            # bf16 mode, d = 64: bf16 qkv / dqkv at the dead-row-eliminated last timestep
 FUSE_PROJ_BWD = os.environ.get("U2GNN_FUSE_PROJ_BWD", "1") != "0"         # bf16 mode, d = 64: projection input + weight gradients in one pass over the output gradient
 FUSE_INPROJ_ATTN = os.environ.get("U2GNN_FUSE_INPROJ_ATTN", "1") != "0"   # bf16 mode, d = 64: in_proj inside the attention-forward kernel (qkv written once, never re-read in the forward)
@@ -401,18 +397,6 @@ def encoder_layer_bwd(dy2, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
     f32 = dict(dtype=torch.float32, device=dev)
     drop_scale = 256.0 / (256.0 - thr) if thr else 1.0
     # LayerNorm2 + FFN
-    if sv.packed is not None and d == 64 and FUSE_LN2_FFN_BWD:
-        # LayerNorm2 backward evaluated by the FFN dgrad kernel's loader: no separate pass, dz2 / dF never round-trip HBM
-        dy1 = torch.empty((Mq, d), **f32)
-        if LIB.timed is not None:
-            FLOPS["u2gnn_ffn_tc_bwd_ln"] = FLOPS.get("u2gnn_ffn_tc_bwd_ln", 0) + 8 * Mq * d * ff
-        wsb = LIB.call("u2gnn_ffn_tc_bwd_workspace_bytes", Mq)
-        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-        LIB.call("u2gnn_ffn_tc_bwd_ln", _ptr(sv.y1), _ptr(dy2), _ptr(sv.z2), _ptr(sv.st2), _ptr(p["norm2.weight"]), drop_ids[3],
-                 Mq, d, ff, _ptr(sv.packed), drop_scale, seed, drop_ids[2], thr, _ptr(dy1), _ptr(g["linear1.weight"]),
-                 _ptr(g["linear1.bias"]), _ptr(g["linear2.weight"]), _ptr(g["linear2.bias"]), _ptr(g["norm2.weight"]),
-                 _ptr(g["norm2.bias"]), _ptr(ws), wsb, _stream())
-        return _encoder_attn_bwd(dy1, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_dx)
     fold = sv.packed is not None and d in (16, 32, 64, 128) and FUSE_LN_BWD     # linear2 bias gradient inside the LayerNorm2 backward
     dz2, df = add_dropout_ln_bwd(dy2, sv.z2, sv.st2, Mq, d, p["norm2.weight"], (seed, drop_ids[3], thr),
                                  g["norm2.weight"], g["norm2.bias"], dasum=g["linear2.bias"] if fold else None)

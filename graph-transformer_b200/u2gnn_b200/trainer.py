@@ -156,8 +156,7 @@ class SupTrainer:
     def dominant_kernel(self):
         if self.precision == "fp32":
             return "u2gnn_sgemm"
-        fused = E.FUSE_LN2_FFN_BWD and self.model.feature_dim_size == 64      # LayerNorm2 backward inside the dgrad loader
-        return "u2gnn_ffn_tc_bwd_ln" if fused else "u2gnn_ffn_tc_bwd"
+        return "u2gnn_ffn_tc_bwd"
 
     def roofline(self, name, kernel_ms, launches, peaks, flops, ncu_summary=None):
         """bench.py roofline object for the dominant kernel: achieved = algorithmic flops / measured time."""
@@ -167,7 +166,7 @@ class SupTrainer:
             peak, which = 1590.0, "fallback (B200_PROFILING.md)"
         achieved = flops.get(name, 0) / max(kernel_ms, 1e-9) / 1e9
         traffic = None
-        if name in ("u2gnn_ffn_tc_bwd", "u2gnn_ffn_tc_bwd_ln") and ncu_summary:
+        if name == "u2gnn_ffn_tc_bwd" and ncu_summary:
             # DRAM bytes per row from the committed `ncu --set full` capture (dgrad + wgrad device kernels of this one
             # entry point), scaled to the average rows per timed launch; algorithmic flops per row = 8 d ff
             per_row = sum(ncu_summary[k]["traffic_bytes_per_launch"] / ncu_summary[k]["rows"]

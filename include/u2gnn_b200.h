@@ -205,25 +205,13 @@ int u2gnn_ffn_tc_fwd(const float* y1, int64_t M, int d, int ff, const void* pack
 /* backward of the block above (autograd of linear1/ReLU/dropout/linear2, transformer.py:977-982) with the
  * hidden recomputed on chip: dy1[M,d] = dz + dPre W1 (dz = gradient at the residual sum, df = gradient at
  * the linear2 output after the output dropout; dy1 may alias dz); dW1[ff,d], db1[ff], dW2[d,ff] are
- * ACCUMULATED (atomics).  db2 = colsum(df) is left to u2gnn_colsum.  workspace (128-byte aligned) holds bf16 tile
- * images of y1 / df handed from the input-gradient kernel to the weight-gradient kernel. */
-/* backward implementation: 0 (default) = dgrad + wgrad kernels, 1 = merged kernel (weight gradients + split-K input gradient
-   through L2 reductions; parity-tested, measured slower) */
-int u2gnn_ffn_tc_bwd_mode(int mode);
+ * ACCUMULATED (atomics).  db2 = colsum(df) is left to u2gnn_colsum.  workspace (128-byte aligned) holds the bf16 tile
+ * images of y1 / df both tensor-core kernels read and the 1-bit ReLU-and-keep mask words the weight-gradient kernel hands
+ * to the input-gradient kernel (so the hidden is recomputed once, not twice). */
 size_t u2gnn_ffn_tc_bwd_workspace_bytes(int64_t M);
 int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const float* dz, int64_t M, int d, int ff, const void* packed,
                      float hidden_scale, uint64_t seed, uint32_t stream_hidden, int thr, float* dy1, float* dW1,
                      float* db1, float* dW2, void* workspace, size_t workspace_bytes, u2gnn_stream_t stream);
-
-/* LayerNorm2 backward + output dropout + FFN backward in the same two kernels (d == 64): replaces
- * u2gnn_add_dropout_ln_bwd(dy2, z2, st2 -> dz, dF) + u2gnn_colsum(dF) + u2gnn_ffn_tc_bwd(y1, dF, dz).  The dgrad kernel's dF
- * loader evaluates dz = LN backward of dy2 (saved pre-norm rows z2, stats st2[M,2] = (mean, rstd), weight gamma2) and
- * dF = dropout(dz; seed, stream_out, thr) on the fly, accumulates dgamma2 / dbeta2 / db2 = colsum(dF) (atomics, +=) and
- * writes dy1 = dz + dPre W1.  dy1 must not alias dy2 or z2.  (transformer.py:977-982 autograd of norm2(x + dropout2(ff(x)))) */
-int u2gnn_ffn_tc_bwd_ln(const float* y1, const float* dy2, const float* z2, const float* st2, const float* gamma2,
-                        uint32_t stream_out, int64_t M, int d, int ff, const void* packed, float hidden_scale, uint64_t seed,
-                        uint32_t stream_hidden, int thr, float* dy1, float* dW1, float* db1, float* dW2, float* db2,
-                        float* dgamma2, float* dbeta2, void* workspace, size_t workspace_bytes, u2gnn_stream_t stream);
 
 /* ---- bf16 tensor-core GEMMs for the attention-block projections of the bf16 mode (csrc/gemm_tc.cu): the
  *      F.linear calls inside nn.MultiheadAttention (in_proj / out_proj) and their autograd.

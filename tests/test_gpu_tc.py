@@ -108,8 +108,7 @@ def test_ffn_tc_forward(U, M, d, ff, p):
 # ------------------------------------------------------------------ fused FFN backward
 @pytest.mark.parametrize("M,d,ff,p", [(256, 64, 128, 0.0), (1000, 64, 2048, 0.5), (37, 64, 256, 0.0), (300, 7, 256, 0.5),
                                       (5000, 64, 1024, 0.25), (148 * 256 * 2 + 77, 64, 256, 0.5)])
-@pytest.mark.parametrize("mode", [0, 1])      # 0: dgrad + wgrad kernels (default), 1: merged kernel
-def test_ffn_tc_backward(U, M, d, ff, p, mode):
+def test_ffn_tc_backward(U, M, d, ff, p):
     from u2gnn_b200 import engine as E
     from oracle import u2gnn_oracle as O
     rng = np.random.default_rng(5 + M + d + ff)
@@ -132,11 +131,9 @@ def test_ffn_tc_backward(U, M, d, ff, p, mode):
     dW1 = torch.zeros((ff, d), device="cuda"); db1 = torch.zeros(ff, device="cuda"); dW2 = torch.zeros((d, ff), device="cuda")
     SEED, S2 = 0x1234ABCD99, 18
     ws = torch.empty(U.LIB.call("u2gnn_ffn_tc_bwd_workspace_bytes", M), dtype=torch.uint8, device="cuda")
-    U.LIB.call("u2gnn_ffn_tc_bwd_mode", mode)
     U.LIB.call("u2gnn_ffn_tc_bwd", t["y1"].data_ptr(), t["df"].data_ptr(), t["dz"].data_ptr(), M, d, ff, packed.data_ptr(), scale,
                SEED, S2, thr, dy1.data_ptr(), dW1.data_ptr(), db1.data_ptr(), dW2.data_ptr(), ws.data_ptr(), ws.numel(), E._stream())
     torch.cuda.synchronize()
-    U.LIB.call("u2gnn_ffn_tc_bwd_mode", 0)
     if thr:
         k2, _ = O.dropout_keep_mask(SEED, S2, M * ff, p)
         m2 = k2.reshape(M, ff).astype(np.float64) * scale
@@ -437,64 +434,21 @@ def test_fused_attention_block_epilogues_equal_unfused_step(U):
     from u2gnn_b200.trainer import SupTrainer
     b = make_batch(3000, 16, 64, 2, seed=9)
     out = {}
-    defaults = (E.FUSE_OUT_PROJ_LN, E.FUSE_LN_BWD, E.FUSE_LN2_FFN_BWD, E.FUSE_PROJ_BWD, E.FUSE_INPROJ_ATTN, E.FUSE_LN1_PROJ_BWD)
+    defaults = (E.FUSE_OUT_PROJ_LN, E.FUSE_LN_BWD, E.FUSE_PROJ_BWD, E.FUSE_INPROJ_ATTN, E.FUSE_LN1_PROJ_BWD)
     try:
         for fused in (False, True):
-            E.FUSE_OUT_PROJ_LN = E.FUSE_LN_BWD = E.FUSE_LN2_FFN_BWD = E.FUSE_PROJ_BWD = E.FUSE_INPROJ_ATTN = E.FUSE_LN1_PROJ_BWD = fused
+            E.FUSE_OUT_PROJ_LN = E.FUSE_LN_BWD = E.FUSE_PROJ_BWD = E.FUSE_INPROJ_ATTN = E.FUSE_LN1_PROJ_BWD = fused
             torch.manual_seed(3)
             m = U.TransformerU2GNN(64, 512, 2, 3, 0.5, 1, attn_axis="neighbors").cuda()
             tr = SupTrainer(m, lr=5e-4, precision="bf16", seed=42)
             loss, scores = tr.forward_backward(b["input_x"], b["rowptr"], b["X"], b["labels"], train=True)
             out[fused] = (loss.item(), scores.clone(), tr.arena.g.clone())
     finally:
-        E.FUSE_OUT_PROJ_LN, E.FUSE_LN_BWD, E.FUSE_LN2_FFN_BWD, E.FUSE_PROJ_BWD, E.FUSE_INPROJ_ATTN, E.FUSE_LN1_PROJ_BWD = defaults
+        E.FUSE_OUT_PROJ_LN, E.FUSE_LN_BWD, E.FUSE_PROJ_BWD, E.FUSE_INPROJ_ATTN, E.FUSE_LN1_PROJ_BWD = defaults
     assert out[True][0] == out[False][0]
     assert torch.equal(out[True][1], out[False][1])
     g1, g0 = out[True][2], out[False][2]
     assert ((g1 - g0).norm() / g0.norm()).item() < 1e-5
-
-
-@pytest.mark.parametrize("M,ff,p", [(1000, 512, 0.5), (256 * 148 + 300, 256, 0.5), (130, 2048, 0.0)])
-def test_ffn_bwd_with_fused_layernorm2_backward(U, M, ff, p):
-    """u2gnn_ffn_tc_bwd_ln (LayerNorm2 backward evaluated by the dgrad kernel's loader) against the three calls it replaces
-    (u2gnn_add_dropout_ln_bwd + u2gnn_colsum + u2gnn_ffn_tc_bwd): the loader uses the same arithmetic in the same order, so
-    dy1 is bit-identical; weight / bias / LayerNorm gradients agree up to the order of fp32 atomics."""
-    from u2gnn_b200 import engine as E
-    d = 64
-    thr = E.dropout_threshold(p)
-    scale = 256.0 / (256.0 - thr) if thr else 1.0
-    g = torch.Generator(device="cuda").manual_seed(M + ff)
-    rnd = lambda *s: torch.randn(*s, device="cuda", generator=g)
-    prm = {"linear1.weight": rnd(ff, d) / 8, "linear1.bias": 0.1 * rnd(ff), "linear2.weight": rnd(d, ff) / (ff ** 0.5),
-           "linear2.bias": 0.1 * rnd(d)}
-    packed = E.ffn_tc_pack(prm, d, ff, thr)
-    y1, dy2 = rnd(M, d), rnd(M, d)
-    z2 = rnd(M, d) * 1.5 + 0.2
-    st2 = torch.stack([z2.mean(1), (z2.var(1, unbiased=False) + 1e-5).rsqrt()], 1).contiguous()
-    gamma = 1 + 0.1 * rnd(d)
-    SEED, S_H, S_O = 0x5EED1234, 30, 31
-    wsb = U.LIB.call("u2gnn_ffn_tc_bwd_workspace_bytes", M)
-    z = lambda *s: torch.zeros(*s, device="cuda")
-    # reference: separate kernels
-    dg0, db0, dW1_0, db1_0, dW2_0, db2_0 = z(d), z(d), z(ff, d), z(ff), z(d, ff), z(d)
-    dz2, df = E.add_dropout_ln_bwd(dy2, z2, st2, M, d, gamma, (SEED, S_O, thr), dg0, db0)
-    U.LIB.call("u2gnn_colsum", df.data_ptr(), M, d, d, db2_0.data_ptr(), 1, E._stream())
-    dy1_0 = torch.empty(M, d, device="cuda")
-    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
-    U.LIB.call("u2gnn_ffn_tc_bwd", y1.data_ptr(), df.data_ptr(), dz2.data_ptr(), M, d, ff, packed.data_ptr(), scale, SEED, S_H, thr,
-               dy1_0.data_ptr(), dW1_0.data_ptr(), db1_0.data_ptr(), dW2_0.data_ptr(), ws.data_ptr(), wsb, E._stream())
-    # fused
-    dg1, db1, dW1_1, db1_1, dW2_1, db2_1 = z(d), z(d), z(ff, d), z(ff), z(d, ff), z(d)
-    dy1_1 = torch.full((M, d), float("nan"), device="cuda")
-    ws1 = torch.empty(wsb, dtype=torch.uint8, device="cuda")
-    U.LIB.call("u2gnn_ffn_tc_bwd_ln", y1.data_ptr(), dy2.data_ptr(), z2.data_ptr(), st2.data_ptr(), gamma.data_ptr(), S_O, M, d, ff,
-               packed.data_ptr(), scale, SEED, S_H, thr, dy1_1.data_ptr(), dW1_1.data_ptr(), db1_1.data_ptr(), dW2_1.data_ptr(),
-               db2_1.data_ptr(), dg1.data_ptr(), db1.data_ptr(), ws1.data_ptr(), wsb, E._stream())
-    torch.cuda.synchronize()
-    assert torch.equal(dy1_1, dy1_0)
-    close = lambda a, b: (a - b).abs().max().item() <= 2e-4 * max(1.0, b.abs().max().item())
-    assert close(dW1_1, dW1_0) and close(db1_1, db1_0) and close(dW2_1, dW2_0)
-    assert close(db2_1, db2_0) and close(dg1, dg0) and close(db1, db0)
 
 
 @pytest.mark.parametrize("B,S,p", [(300, 17, 0.5), (77, 9, 0.0), (4099, 17, 0.5)])
