@@ -14,6 +14,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import u2gnn_b200 as U                                    # noqa: E402
 from u2gnn_b200.data import build_batch, load_data, separate_data   # noqa: E402
+from u2gnn_b200.evaluate import ConditionalStepLR, sup_accuracy   # noqa: E402
 from u2gnn_b200.trainer import SupTrainer                 # noqa: E402
 
 
@@ -81,20 +82,14 @@ def run(args, log=print):
         return total
 
     def evaluate():
-        model.eval()
-        preds = []
-        with torch.no_grad():
-            for i in range(0, len(test_graphs), args.batch_size):
-                ix, rp, X, _ = to_dev(build_batch(test_graphs[i:i + args.batch_size], args.num_neighbors, np.random, reddit))
-                preds.append(model(ix, rp, X).argmax(1))
-        labels = torch.tensor([g.label for g in test_graphs], device=dev)
-        return float((torch.cat(preds) == labels).sum().item()) / len(test_graphs)
+        return sup_accuracy(model, test_graphs, args.batch_size, args.num_neighbors, np.random, reddit, dev)
 
     out_dir = os.path.abspath(os.path.join(args.run_folder, "../runs_pytorch_U2GNN_Sup", args.model_name))
     log("Writing to {}\n".format(out_dir))
     ckpt = os.path.join(out_dir, "checkpoints")
     os.makedirs(ckpt, exist_ok=True)
     accs, losses = [], []
+    sched = ConditionalStepLR(args.learning_rate, steps_per_epoch)
     with open(os.path.join(ckpt, "model_acc.txt"), "w") as w:
         for epoch in range(1, args.num_epochs + 1):
             t0 = time.time()
@@ -103,7 +98,7 @@ def run(args, log=print):
             acc = evaluate()
             accs.append(acc)
             log("| epoch {:3d} | time: {:5.2f}s | loss {:5.2f} | test acc {:5.2f} | ".format(epoch, time.time() - t0, loss, acc * 100))
-            # the reference's StepLR (step_size = batches/epoch, stepped at most once per epoch) never changes the lr
+            trainer.lr = sched.epoch_end(loss)       # the reference's conditional StepLR (train_pytorch_U2GNN_Sup.py:147,209-210)
             w.write("epoch " + str(epoch) + " fold " + str(args.fold_idx) + " acc " + str(acc * 100) + "%\n")
     return accs, losses
 

@@ -16,6 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import u2gnn_b200 as U                                    # noqa: E402
 from u2gnn_b200 import engine as E                        # noqa: E402
 from u2gnn_b200.data import build_batch, global_node_ids, load_data   # noqa: E402
+from u2gnn_b200.evaluate import ConditionalStepLR, unsup_accuracy   # noqa: E402
 from u2gnn_b200.trainer import UnSupTrainer               # noqa: E402
 
 
@@ -78,27 +79,21 @@ def run(args, log=print):
         return total
 
     def evaluate():
-        emb = E.segment_sum(model.ss.weight.data.contiguous(), pool_rowptr).cpu().numpy()   # spmm(graph_pool, ss.weight)
-        accs = []
-        for fold in range(10):
-            skf = StratifiedKFold(n_splits=10, shuffle=True, random_state=0)
-            tr, te = list(skf.split(np.zeros(len(labels)), labels))[fold]
-            cls = LogisticRegression(solver="liblinear", tol=0.001)
-            cls.fit(emb[tr], labels[tr])
-            accs.append(cls.score(emb[te], labels[te]))
-        return float(np.mean(accs) * 100), float(np.std(accs) * 100)
+        return unsup_accuracy(model.ss.weight.data, pool_rowptr, labels)
 
     out_dir = os.path.abspath(os.path.join(args.run_folder, "../runs_pytorch_U2GNN_UnSup", args.model_name))
     log("Writing to {}\n".format(out_dir))
     ckpt = os.path.join(out_dir, "checkpoints")
     os.makedirs(ckpt, exist_ok=True)
     hist = []
+    sched = ConditionalStepLR(args.learning_rate, steps_per_epoch)
     with open(os.path.join(ckpt, "model_acc.txt"), "w") as w:
         for epoch in range(1, args.num_epochs + 1):
             t0 = time.time()
             loss = train_epoch()
             mean, std = evaluate()
             hist.append((mean, std, loss))
+            trainer.lr = sched.epoch_end(loss)       # the reference's conditional StepLR (train_pytorch_U2GNN_UnSup.py:147,210-211)
             log("| epoch {:3d} | time: {:5.2f}s | loss {:5.2f} | mean {:5.2f} | std {:5.2f} | ".format(epoch, time.time() - t0, loss, mean, std))
             w.write("epoch " + str(epoch) + " mean: " + str(mean) + " std: " + str(std) + "\n")
     return hist

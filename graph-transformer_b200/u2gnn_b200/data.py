@@ -5,6 +5,16 @@ and `get_batch_data` (train_pytorch_U2GNN_Sup.py:91-119): the text format is par
 neighbour lists (numpy), features are the one-hot node tag (or degree, `degree_as_tag`), folds come from the
 same `StratifiedKFold(10, shuffle=True, random_state=0)`.  This is plumbing around the hot path (SURVEY.md
 §8(f) rows 1 and 3), kept on the host; batches are handed to the CUDA engine as index / feature tensors.
+
+Index parity with the reference (checked bit for bit against reference-generated fixtures in tests/test_data_parity.py):
+the reference samples a node's neighbours from `dict_Adj_block`, which lists them in `edge_mat` order
+(train_pytorch_U2GNN_Sup.py:100-110).  `edge_mat` is `g.g.edges()` followed by the same pairs reversed (util.py:127-134), and
+networkx yields edges node by node in node-INSERTION order, neighbour by neighbour in adjacency-insertion order, skipping
+pairs whose other end was already visited.  Node insertion order is the order of first appearance in the file (a node is
+created by `add_edge` before its own line is read when an earlier line names it).  `_edge_order` below restates exactly
+that; `degree_as_tag` tags follow the same insertion order positionally (util.py:139-141 - a quirk of the reference: row i
+gets the degree of the i-th INSERTED node), and the tag -> feature column map is the iteration order of the same Python
+set the reference builds (util.py:144-149).
 """
 from __future__ import annotations
 
@@ -14,12 +24,14 @@ from dataclasses import dataclass
 import numpy as np
 
 _ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "datasets"))
+CACHE_MAGIC = b"U2GNNCSR"
+CACHE_VERSION = 1
 
 
 @dataclass
 class Graph:
     label: int
-    neighbors: list            # list of int arrays (undirected, deduplicated, no self loops removed)
+    neighbors: list            # per node: int64 array of neighbour ids in the reference's edge_mat order (a self loop appears twice)
     node_tags: list
     node_features: np.ndarray = None
 
@@ -28,32 +40,134 @@ class Graph:
         return len(self.neighbors)
 
 
-def load_data(dataset, degree_as_tag=False, root=None):
-    """-> (graphs, num_classes).  `dataset` is a name under `root` (default: <repo>/datasets) or a file path."""
-    path = dataset if os.path.isfile(dataset) else os.path.join(root or _ROOT, dataset, dataset + ".txt")
-    graphs, label_map, tag_map = [], {}, {}
+def _edge_order(n, lines):
+    """lines[j] = neighbour ids on node j's line.  -> (neighbour lists in edge_mat order, node insertion order, degrees
+    in insertion order) with networkx.Graph semantics (util.py:78-100,112-134)."""
+    adj = {}                                   # node -> {neighbour: None}, both dicts in insertion order
+
+    def add_node(u):
+        if u not in adj:
+            adj[u] = {}
+
+    for j in range(n):
+        add_node(j)
+        for k in lines[j]:
+            add_node(k)
+            adj[j][k] = None
+            adj[k][j] = None
+    if len(adj) != n:
+        raise ValueError("edge list names a node outside [0, n)")
+    seen = set()
+    src, dst = [], []
+    for u, nbrs in adj.items():                # Graph.edges(): each pair once, from the end inserted first
+        for v in nbrs:
+            if v not in seen:
+                src.append(u)
+                dst.append(v)
+        seen.add(u)
+    out = [[] for _ in range(n)]
+    for u, v in zip(src, dst):                 # edge_mat = [edges | reversed edges]; dict_Adj_block[row].append(col) in that order
+        out[u].append(v)
+    for u, v in zip(src, dst):
+        out[v].append(u)
+    order = list(adj.keys())
+    degree = [len(adj[u]) + (1 if u in adj[u] else 0) for u in order]      # networkx counts a self loop twice
+    return [np.array(o, dtype=np.int64) for o in out], order, degree
+
+
+def _parse_text(path):
+    """-> list of (label_raw, neighbour lists, tags_raw, insertion-order degrees)."""
+    raw = []
     with open(path) as f:
         n_g = int(f.readline().strip())
         for _ in range(n_g):
             n, l = (int(w) for w in f.readline().split())
-            label_map.setdefault(l, len(label_map))
-            nbr_sets = [set() for _ in range(n)]
-            tags = []
-            for j in range(n):
+            lines, tags = [], []
+            for _j in range(n):
                 row = f.readline().split()
                 deg = int(row[1])
-                tag = int(row[0])
-                tag_map.setdefault(tag, len(tag_map))
-                tags.append(tag_map[tag])
-                for k in row[2:2 + deg]:
-                    k = int(k)
-                    nbr_sets[j].add(k)
-                    nbr_sets[k].add(j)
-            graphs.append(Graph(label_map[l], [np.array(sorted(s), dtype=np.int64) for s in nbr_sets], tags))
-    if degree_as_tag:
-        for g in graphs:
-            g.node_tags = [len(nb) for nb in g.neighbors]
-    tagset = sorted({t for g in graphs for t in g.node_tags})
+                tags.append(int(row[0]))
+                lines.append([int(k) for k in row[2:2 + deg]])
+            nbrs, _, degree = _edge_order(n, lines)
+            raw.append((l, nbrs, tags, degree))
+    return raw
+
+
+def cache_path(text_path):
+    return text_path + ".csr"
+
+
+def write_cache(path, raw):
+    """Binary CSR cache of a parsed dataset: one file, little-endian int64 sections
+    [magic 8 B | version | G | V | E] [graph_ptr G+1] [labels G] [tags V] [ins_degree V] [row_ptr V+1] [col E]
+    (col = graph-local neighbour ids in the reference's edge_mat order)."""
+    G = len(raw)
+    sizes = np.array([len(r[1]) for r in raw], dtype=np.int64)
+    gptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    labels = np.array([r[0] for r in raw], dtype=np.int64)
+    tags = np.concatenate([np.asarray(r[2], dtype=np.int64) for r in raw]) if G else np.zeros(0, np.int64)
+    insdeg = np.concatenate([np.asarray(r[3], dtype=np.int64) for r in raw]) if G else np.zeros(0, np.int64)
+    deg = np.concatenate([[len(nb) for nb in r[1]] for r in raw]).astype(np.int64) if G else np.zeros(0, np.int64)
+    rptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    parts = [nb for r in raw for nb in r[1] if len(nb)]
+    col = np.concatenate(parts).astype(np.int64) if parts else np.zeros(0, np.int64)
+    tmp = path + ".tmp.%d" % os.getpid()
+    with open(tmp, "wb") as f:
+        f.write(CACHE_MAGIC)
+        np.array([CACHE_VERSION, G, int(gptr[-1]), len(col)], dtype="<i8").tofile(f)
+        for a in (gptr, labels, tags, insdeg, rptr, col):
+            a.astype("<i8").tofile(f)
+    os.replace(tmp, path)
+
+
+def read_cache(path):
+    with open(path, "rb") as f:
+        if f.read(8) != CACHE_MAGIC:
+            raise ValueError("%s is not a U2GNN CSR cache" % path)
+        ver, G, V, E = (int(v) for v in np.fromfile(f, dtype="<i8", count=4))
+        if ver != CACHE_VERSION:
+            raise ValueError("%s: cache version %d, expected %d" % (path, ver, CACHE_VERSION))
+        gptr = np.fromfile(f, dtype="<i8", count=G + 1)
+        labels = np.fromfile(f, dtype="<i8", count=G)
+        tags = np.fromfile(f, dtype="<i8", count=V)
+        insdeg = np.fromfile(f, dtype="<i8", count=V)
+        rptr = np.fromfile(f, dtype="<i8", count=V + 1)
+        col = np.fromfile(f, dtype="<i8", count=E)
+    if len(col) != E or len(rptr) != V + 1:
+        raise ValueError("%s: truncated cache" % path)
+    raw = []
+    for g in range(G):
+        a, b = int(gptr[g]), int(gptr[g + 1])
+        nbrs = [col[rptr[v]:rptr[v + 1]].copy() for v in range(a, b)]
+        raw.append((int(labels[g]), nbrs, tags[a:b].tolist(), insdeg[a:b].tolist()))
+    return raw
+
+
+def load_data(dataset, degree_as_tag=False, root=None, cache=None):
+    """-> (graphs, num_classes).  `dataset` is a name under `root` (default: <repo>/datasets) or a file path.
+    cache: None = use `<file>.csr` when it exists and is newer than the text file; True = also (re)write it; False = ignore it."""
+    path = dataset if os.path.isfile(dataset) else os.path.join(root or _ROOT, dataset, dataset + ".txt")
+    cpath = cache_path(path)
+    raw = None
+    if cache is not False and os.path.exists(cpath) and os.path.getmtime(cpath) >= os.path.getmtime(path):
+        raw = read_cache(cpath)
+    if raw is None:
+        raw = _parse_text(path)
+        if cache:
+            write_cache(cpath, raw)
+    label_map, tag_map = {}, {}
+    graphs = []
+    for l, nbrs, tags, degree in raw:
+        label_map.setdefault(l, len(label_map))
+        mapped = []
+        for t in tags:
+            tag_map.setdefault(t, len(tag_map))
+            mapped.append(tag_map[t])
+        graphs.append(Graph(label_map[l], nbrs, degree if degree_as_tag else mapped))
+    tagset = set([])
+    for g in graphs:                            # same set operations as util.py:144-149 -> same iteration order -> same columns
+        tagset = tagset.union(set(g.node_tags))
+    tagset = list(tagset)
     index = {t: i for i, t in enumerate(tagset)}
     for g in graphs:
         feat = np.zeros((g.n, len(tagset)), dtype=np.float32)
@@ -104,8 +218,7 @@ def global_node_ids(graphs, selected):
 # ------------------------------------------------------------------------------------------------------------------
 def dataset_csr(graphs):
     """Whole dataset as ONE CSR over dataset-wide node ids -> (rowptr int64 [V+1], col int64 [E], graph_start int64 [G+1],
-    features float32 [V, d]).  Neighbour lists keep the order of `Graph.neighbors` (sorted, as the reference's
-    edge_mat-derived dict does after its own sort)."""
+    features float32 [V, d]).  Neighbour lists keep the order of `Graph.neighbors` (the reference's edge_mat order)."""
     sizes = np.array([g.n for g in graphs], dtype=np.int64)
     gstart = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     deg = np.concatenate([[len(nb) for nb in g.neighbors] for g in graphs]).astype(np.int64) if graphs else np.zeros(0, np.int64)

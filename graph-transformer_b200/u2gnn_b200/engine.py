@@ -24,8 +24,8 @@ PARAM_NAMES = (
     "linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias",
     "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias",
 )
-STREAM_POOLED = 1
-STREAM_CONCAT = 9
+STREAM_POOLED = 0x40000000
+STREAM_CONCAT = 0x50000000
 FUSE_OUT_PROJ_LN = os.environ.get("U2GNN_FUSE_EPILOGUES", "1") != "0"   # bf16 mode, d = 64: out_proj + dropout + residual + LayerNorm1 in one kernel (False: GEMM then LayerNorm kernel)
 FUSE_LN_BWD = os.environ.get("U2GNN_FUSE_EPILOGUES", "1") != "0"        # bf16 mode: bf16 da out of the LayerNorm1 backward, linear2 bias gradient inside the LayerNorm2 backward
 LAST_STEP_BF16 = os.environ.get("U2GNN_LAST_BF16", "1") != "0"            # bf16 mode, d = 64: bf16 qkv / dqkv at the dead-row-eliminated last timestep
@@ -39,8 +39,13 @@ FLOPS = {}    # entry point -> algorithmic flops issued while LIB.timed is activ
 
 
 def stream_id(layer, timestep, site, num_timesteps):
-    """Dropout stream of encoder site (0 probs, 1 post-attention, 2 post-ReLU, 3 post-FFN)."""
-    return ((layer * num_timesteps + timestep) * 4 + site) + 16
+    """Dropout stream of encoder site (0 probs, 1 post-attention, 2 post-ReLU, 3 post-FFN).  Encoder streams live in
+    [16, 0x40000000); the pooled-embedding (STREAM_POOLED + layer) and concatenated-vector (STREAM_CONCAT) streams sit
+    above that range, so no (layer, timestep) count can make two sites share a stream."""
+    sid = ((layer * num_timesteps + timestep) * 4 + site) + 16
+    if sid >= STREAM_POOLED:
+        raise ValueError("too many encoder layers x timesteps for the dropout stream layout")
+    return sid
 
 
 def dropout_threshold(p):

@@ -114,8 +114,8 @@ def stream_id(layer: int, timestep: int, site: int, num_timesteps: int) -> int:
     return ((layer * num_timesteps + timestep) * 4 + site) + 16
 
 
-STREAM_POOLED = 1  # + layer  (dropout on pooled graph embeddings, p = args.dropout)
-STREAM_CONCAT = 9  # dropout on concatenated node vectors (unsupervised)
+STREAM_POOLED = 0x40000000  # + layer  (dropout on pooled graph embeddings, p = args.dropout)
+STREAM_CONCAT = 0x50000000  # dropout on concatenated node vectors (unsupervised)
 
 
 class DropoutSpec:

@@ -16,6 +16,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests are skipped (not failed) on a box without an sm_100 device; the driver's GPU tier runs them on a B200."""
+    try:
+        import u2gnn_b200
+        have = u2gnn_b200.LIB.cdll.u2gnn_device_check() == 0
+    except Exception:
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason="no sm_100 (B200) device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
     return {k: z[k] for k in z.files}

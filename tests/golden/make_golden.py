@@ -206,6 +206,111 @@ def make_mutag_kat():
     print("mutag_kat N", input_x.shape[0], "sum", int(input_x.sum()), out["sha1"], scores.numpy().tolist())
 
 
+def make_data_fixtures():
+    """Dataset front-end + host batch builder KATs straight from the reference (util.load_data, get_batch_data): a PTC
+    degree-as-tag batch and whole-dataset digests of the edge_mat-order neighbour lists / features / folds."""
+    argv = sys.argv
+    sys.argv = ["train_pytorch_U2GNN_Sup.py", "--dataset", "MUTAG", "--fold_idx", "1", "--num_neighbors", "4",
+                "--num_timesteps", "1", "--ff_hidden_size", "64", "--batch_size", "4", "--num_epochs", "0",
+                "--run_folder", "/tmp/u2gnn_golden/x/", "--model_name", "MUTAG_kat2"]
+    cwd = os.getcwd()
+    os.chdir(REF)
+    try:
+        g = runpy.run_path(os.path.join(REF, "train_pytorch_U2GNN_Sup.py"), run_name="__main__")
+    finally:
+        os.chdir(cwd)
+        sys.argv = argv
+    out = {}
+    for name, deg in (("MUTAG", False), ("PTC", True), ("PTC", False)):
+        graphs, C = g["load_data"](name, deg)
+        key = "%s_%d" % (name, int(deg))
+        nbr = []
+        for gr in graphs:
+            d = {}
+            for r, c in zip(gr.edge_mat[0], gr.edge_mat[1]):        # the order dict_Adj_block sees (train_pytorch_U2GNN_Sup.py:100-105)
+                d.setdefault(int(r), []).append(int(c))
+            for v in range(len(gr.g)):
+                nbr.append(np.array(d.get(v, []), dtype=np.int64))
+        deg_arr = np.array([len(a) for a in nbr], dtype=np.int64)
+        col = np.concatenate(nbr) if len(nbr) else np.zeros(0, np.int64)
+        feat = np.concatenate([gr.node_features for gr in graphs], 0)
+        out[key + "_deg_sha1"] = np.array(hashlib.sha1(deg_arr.tobytes()).hexdigest())
+        out[key + "_col_sha1"] = np.array(hashlib.sha1(col.tobytes()).hexdigest())
+        out[key + "_feat_sha1"] = np.array(hashlib.sha1(np.ascontiguousarray(feat, dtype=np.float32).tobytes()).hexdigest())
+        out[key + "_labels"] = np.array([gr.label for gr in graphs], dtype=np.int64)
+        out[key + "_shape"] = np.array([len(graphs), feat.shape[0], feat.shape[1], len(col), C], dtype=np.int64)
+        tr, te = g["separate_data"](graphs, 3)
+        ids = {id(gr): i for i, gr in enumerate(graphs)}
+        out[key + "_fold3_test"] = np.array([ids[id(gr)] for gr in te], dtype=np.int64)
+        if name == "PTC" and deg:
+            sel = [5, 100, 7, 343]
+            np.random.seed(321)
+            ix, gp, X, y = g["get_batch_data"]([graphs[i] for i in sel])     # num_neighbors = 4 from the argv above
+            out["ptc_batch_sel"] = np.array(sel, dtype=np.int64)
+            out["ptc_batch_input_x"] = ix.numpy()
+            out["ptc_batch_X"] = X.numpy()
+            out["ptc_batch_labels"] = y.numpy()
+            out["ptc_batch_pool_idx"] = gp._indices().numpy()
+    np.savez_compressed(os.path.join(HERE, "data_kat.npz"), **out)
+    print("data_kat", {k: (v.tolist() if v.ndim and v.size < 8 else str(v)[:18]) for k, v in out.items() if "shape" in k or "sha1" in k})
+
+
+def make_eval_fixtures():
+    """Evaluation path KATs: the reference's supervised evaluate() on the MUTAG fold-1 test graphs at
+    init (train_pytorch_U2GNN_Sup.py:166-187) and the unsupervised protocol (spmm over ALL graphs of the class table ->
+    10-fold LogisticRegression, train_pytorch_U2GNN_UnSup.py:164-188) on PTC degree-as-tag with a fixed table."""
+    from scipy.sparse import coo_matrix  # noqa: F401  (sklearn dependency check)
+    from sklearn.linear_model import LogisticRegression
+    from sklearn.model_selection import StratifiedKFold
+    argv = sys.argv
+    sys.argv = ["train_pytorch_U2GNN_Sup.py", "--dataset", "MUTAG", "--fold_idx", "1", "--num_neighbors", "8",
+                "--num_timesteps", "3", "--ff_hidden_size", "1024", "--batch_size", "4", "--num_epochs", "0",
+                "--run_folder", "/tmp/u2gnn_golden/x/", "--model_name", "MUTAG_eval"]
+    cwd = os.getcwd()
+    os.chdir(REF)
+    try:
+        g = runpy.run_path(os.path.join(REF, "train_pytorch_U2GNN_Sup.py"), run_name="__main__")
+    finally:
+        os.chdir(cwd)
+        sys.argv = argv
+    model, test_graphs = g["model"], g["test_graphs"]
+    with torch.no_grad():                       # move the classifier away from its init so the argmax is not degenerate
+        for n_, p_ in model.named_parameters():
+            if n_.startswith("predictions"):
+                p_.add_(0.05 * torch.randn_like(p_))
+    np.random.seed(5)
+    acc = g["evaluate"]()
+    model.eval()
+    np.random.seed(5)
+    outs = []
+    with torch.no_grad():
+        for i in range(0, len(test_graphs), 4):
+            ix, gp, X, _ = g["get_batch_data"](test_graphs[i:i + 4])
+            outs.append(model(ix, gp, X))
+    out = dict(sup_logits=torch.cat(outs, 0).numpy(), sup_acc=np.float64(acc),
+               sup_labels=np.array([gr.label for gr in test_graphs], dtype=np.int64))
+    out.update({"param." + k_: v for k_, v in sd_np(model).items()})
+    # unsupervised: the reference's lines on a fixed, exactly representable class table
+    graphs, _ = g["load_data"]("PTC", True)
+    V = sum(len(gr.g) for gr in graphs)
+    rng = np.random.default_rng(77)
+    Wq = rng.integers(-64, 65, size=(V, 4)).astype(np.int8)
+    W = torch.from_numpy(Wq.astype(np.float32) / 64.0)
+    graph_pool = g["get_graphpool"](graphs)
+    labels = np.array([gr.label for gr in graphs])
+    emb = torch.spmm(graph_pool, W).data.cpu().numpy()
+    accs = []
+    for fold in range(10):
+        skf = StratifiedKFold(n_splits=10, shuffle=True, random_state=0)
+        tr, te = list(skf.split(np.zeros(len(labels)), labels))[fold]
+        cls = LogisticRegression(solver="liblinear", tol=0.001)
+        cls.fit(emb[tr], labels[tr])
+        accs.append(cls.score(emb[te], labels[te]))
+    out.update(unsup_Wq=Wq, unsup_emb=emb, unsup_mean=np.float64(np.mean(accs) * 100), unsup_std=np.float64(np.std(accs) * 100))
+    np.savez_compressed(os.path.join(HERE, "eval_kat.npz"), **out)
+    print("eval_kat sup acc", acc, "unsup", np.mean(accs) * 100, np.std(accs) * 100)
+
+
 def make_sampler_sets():
     out = {}
     for V, ns in [(100, 50), (3371, 512), (8792, 512), (2540000, 512)]:
@@ -222,7 +327,15 @@ def make_sampler_sets():
 
 
 if __name__ == "__main__":
+    if "--data-only" in sys.argv:
+        make_data_fixtures()
+        sys.exit(0)
+    if "--eval-only" in sys.argv:
+        make_eval_fixtures()
+        sys.exit(0)
     make_mutag_kat()
+    make_data_fixtures()
+    make_eval_fixtures()
     make_sampler_sets()
     #                 name                    seed sizes                 k  d   ff   T  L  C  axis
     make_sup_case("sup_neighbors_small", 11, [5, 1, 9, 3, 2],            4, 7,  32,  2, 1, 2, "neighbors")
