@@ -11,7 +11,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ table, int64_t n_table, int d,
                                                           const int64_t* __restrict__ idx, int64_t n_idx,
                                                           int64_t idx_stride, float* __restrict__ out,
-                                                          int lanes_per_row) {
+                                                          int lanes_per_row, int* __restrict__ err) {
     const int rows_per_block = blockDim.x / lanes_per_row;
     const int lane = threadIdx.x % lanes_per_row;
     const int sub = threadIdx.x / lanes_per_row;
@@ -21,7 +21,17 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
     for (int64_t row = (int64_t)blockIdx.x * rows_per_block + sub; row < n_idx;
          row += (int64_t)gridDim.x * rows_per_block) {
         int64_t src = __ldg(idx + row * idx_stride);
-        if (src < 0 || src >= n_table) continue;  // out-of-range ids are skipped
+        if (src < 0 || src >= n_table) {          // F.embedding raises here: zero row + error word (never uninitialised output)
+            if (VEC == 4) {
+                float4* o = reinterpret_cast<float4*>(out + row * d);
+                for (int c = lane; c < dv; c += lanes_per_row) o[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                float* o = out + row * d;
+                for (int c = lane; c < d; c += lanes_per_row) o[c] = 0.0f;
+            }
+            if (err && lane == 0) atomicOr(err, 2);
+            continue;
+        }
         if (VEC == 4) {
             const float4* s = reinterpret_cast<const float4*>(table + src * d);
             float4* o = reinterpret_cast<float4*>(out + row * d);
@@ -227,16 +237,16 @@ int pick_lanes(int d_units) {
 }  // namespace
 
 extern "C" int u2gnn_gather_rows(const float* table, int64_t n_table, int d, const int64_t* idx, int64_t n_idx,
-                                 int64_t idx_stride, float* out, u2gnn_stream_t stream) {
+                                 int64_t idx_stride, float* out, int* err, u2gnn_stream_t stream) {
     if (!table || !idx || !out || d <= 0 || n_idx < 0 || idx_stride < 1) return U2GNN_EINVAL;
     if (n_idx == 0) return U2GNN_OK;
     const bool vec = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
     const int lanes = pick_lanes(vec ? d / 4 : d);
     const int grid = grid_for(n_idx, 256 / lanes, 8);
     if (vec)
-        gather_rows_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(table, n_table, d, idx, n_idx, idx_stride, out, lanes);
+        gather_rows_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(table, n_table, d, idx, n_idx, idx_stride, out, lanes, err);
     else
-        gather_rows_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(table, n_table, d, idx, n_idx, idx_stride, out, lanes);
+        gather_rows_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(table, n_table, d, idx, n_idx, idx_stride, out, lanes, err);
     U2GNN_CHECK_LAUNCH();
 }
 

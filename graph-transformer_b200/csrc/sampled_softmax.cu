@@ -12,13 +12,19 @@ constexpr int kChunkFloats = 20 * 1024;  // shared-memory budget (floats) per st
 
 __device__ __forceinline__ int pitch_of(int D) { return D | 1; }
 
+// samp != nullptr: the sampled rows were gathered by the caller (row-sharded table: every rank holds all ns rows in one
+// [ns, D] buffer) and ids are not dereferenced into W
 __device__ __forceinline__ void stage_rows(const float* __restrict__ W, int64_t V, const int64_t* __restrict__ ids,
-                                           int s0, int sc, int D, float* ws) {
+                                           const float* __restrict__ samp, int s0, int sc, int D, float* ws) {
     const int P = pitch_of(D);
     for (int e = threadIdx.x; e < sc * D; e += blockDim.x) {
         const int s = e / D, c = e - s * D;
-        const int64_t id = ids[s0 + s];
-        ws[s * P + c] = (id >= 0 && id < V) ? __ldg(W + id * D + c) : 0.0f;
+        if (samp) {
+            ws[s * P + c] = __ldg(samp + (size_t)(s0 + s) * D + c);
+        } else {
+            const int64_t id = ids[s0 + s];
+            ws[s * P + c] = (id >= 0 && id < V) ? __ldg(W + id * D + c) : 0.0f;
+        }
     }
 }
 
@@ -32,13 +38,19 @@ struct TfArgs {
     const float* samp_q;   // [ns] expected count of each sampled id
     float* dbias;          // [V]  backward only
 };
+// rows gathered by the caller + where their gradient goes + the device error word (bit 0: a label outside [0, V))
+struct SsExtra {
+    const float* samp;     // [ns, D] or null
+    float* dsamp;          // [ns, D] or null (backward)
+    int* err;              // or null
+};
 
 template <bool TF>
 __global__ void __launch_bounds__(256) ss_fwd_kernel(const float* __restrict__ x, const int64_t* __restrict__ labels,
                                                      int64_t N, int D, const float* __restrict__ W, int64_t V,
                                                      const int64_t* __restrict__ ids, int ns, int chunk,
                                                      float* __restrict__ loss, float* __restrict__ denom_out,
-                                                     int64_t nodes_per_block, TfArgs tf) {
+                                                     int64_t nodes_per_block, TfArgs tf, SsExtra ex) {
     extern __shared__ float sm[];
     const int P = pitch_of(D);
     float* ws = sm;                                   // [chunk][P]
@@ -52,7 +64,7 @@ __global__ void __launch_bounds__(256) ss_fwd_kernel(const float* __restrict__ x
     for (int s0 = 0; s0 < ns; s0 += chunk) {
         const int sc = (ns - s0 < chunk) ? ns - s0 : chunk;
         __syncthreads();
-        stage_rows(W, V, ids, s0, sc, D, ws);
+        stage_rows(W, V, ids, ex.samp, s0, sc, D, ws);
         if (TF) {
             for (int s = threadIdx.x; s < sc; s += blockDim.x) {
                 const int64_t id = ids[s0 + s];
@@ -70,6 +82,7 @@ __global__ void __launch_bounds__(256) ss_fwd_kernel(const float* __restrict__ x
             int y = -2;
             if (TF) {
                 const int64_t yl = labels[i];
+                if (yl < 0 || yl >= V) continue;              // reported below (loss 0, error word)
                 y = (int)yl;
                 float dot = 0.0f;
                 for (int c = lane; c < D; c += 32) dot = fmaf(xw[c], __ldg(W + yl * D + c), dot);
@@ -90,6 +103,16 @@ __global__ void __launch_bounds__(256) ss_fwd_kernel(const float* __restrict__ x
     __syncthreads();
     // true logits and the loss
     for (int64_t i = n0 + w; i < n1; i += warps) {
+        const int64_t y = labels[i];
+        if (y < 0 || y >= V) {
+            // the reference's index_select raises here; the kernel reports through the error word and yields loss 0
+            if (lane == 0) {
+                loss[i] = 0.0f;
+                denom_out[i] = 1.0f;
+                if (ex.err) atomicOr(ex.err, 1);
+            }
+            continue;
+        }
         if (TF) {
             if (lane == 0) {
                 const float dn = 1.0f + denom_out[i];
@@ -98,7 +121,6 @@ __global__ void __launch_bounds__(256) ss_fwd_kernel(const float* __restrict__ x
             }
             continue;
         }
-        const int64_t y = labels[i];
         float dot = 0.0f;
         for (int c = lane; c < D; c += 32) dot = fmaf(x[i * D + c], __ldg(W + y * D + c), dot);
         dot = warp_sum(dot);
@@ -112,7 +134,7 @@ __global__ void __launch_bounds__(256) ss_bwd_kernel(const float* __restrict__ d
                                                      const float* __restrict__ W, int64_t V,
                                                      const int64_t* __restrict__ ids, int ns, int chunk,
                                                      const float* __restrict__ denom, float* __restrict__ dx,
-                                                     float* __restrict__ dW, int64_t nodes_per_block, TfArgs tf) {
+                                                     float* __restrict__ dW, int64_t nodes_per_block, TfArgs tf, SsExtra ex) {
     extern __shared__ float sm[];
     const int P = pitch_of(D);
     float* ws = sm;                                   // [chunk][P]   sampled rows
@@ -131,6 +153,11 @@ __global__ void __launch_bounds__(256) ss_bwd_kernel(const float* __restrict__ d
     // true-class term: dx = g * W[y];  dW[y] += g * x   (g = -dloss; TF: g = (p_true - 1) dloss, p_true = 1 / denom, db[y] += g)
     for (int64_t i = n0 + w; i < n1; i += warps) {
         const int64_t y = labels[i];
+        if (y < 0 || y >= V) {                                // invalid label: no gradient, error word set
+            for (int c = lane; c < D; c += 32) dx[i * D + c] = 0.0f;
+            if (lane == 0 && ex.err) atomicOr(ex.err, 1);
+            continue;
+        }
         const float g = TF ? (1.0f / denom[i] - 1.0f) * dloss[i] : -dloss[i];
         for (int c = lane; c < D; c += 32) {
             dx[i * D + c] = g * __ldg(W + y * D + c);
@@ -141,7 +168,7 @@ __global__ void __launch_bounds__(256) ss_bwd_kernel(const float* __restrict__ d
     for (int s0 = 0; s0 < ns; s0 += chunk) {
         const int sc = (ns - s0 < chunk) ? ns - s0 : chunk;
         __syncthreads();
-        stage_rows(W, V, ids, s0, sc, D, ws);
+        stage_rows(W, V, ids, ex.samp, s0, sc, D, ws);
         for (int e = threadIdx.x; e < sc * P; e += blockDim.x) dws[e] = 0.0f;
         if (TF) {
             for (int s = threadIdx.x; s < sc; s += blockDim.x) {
@@ -154,13 +181,14 @@ __global__ void __launch_bounds__(256) ss_bwd_kernel(const float* __restrict__ d
         }
         __syncthreads();
         for (int64_t i = n0 + w; i < n1; i += warps) {
+            const int64_t yl = labels[i];
+            if (yl < 0 || yl >= V) continue;                  // invalid label (reported above): contributes nothing
             __syncwarp();
             for (int c = lane; c < D; c += 32) xw[c] = x[i * D + c];
             __syncwarp();
             float t = 0.0f;
             int y = -2;
             if (TF) {
-                const int64_t yl = labels[i];
                 y = (int)yl;
                 float dot = 0.0f;
                 for (int c = lane; c < D; c += 32) dot = fmaf(xw[c], __ldg(W + yl * D + c), dot);
@@ -198,8 +226,12 @@ __global__ void __launch_bounds__(256) ss_bwd_kernel(const float* __restrict__ d
         __syncthreads();
         for (int e = threadIdx.x; e < sc * D; e += blockDim.x) {
             const int s = e / D, c = e - s * D;
-            const int64_t id = ids[s0 + s];
-            if (id >= 0 && id < V) atomicAdd(dW + id * D + c, dws[s * P + c]);
+            if (ex.dsamp) {
+                atomicAdd(ex.dsamp + (size_t)(s0 + s) * D + c, dws[s * P + c]);
+            } else {
+                const int64_t id = ids[s0 + s];
+                if (id >= 0 && id < V) atomicAdd(dW + id * D + c, dws[s * P + c]);
+            }
         }
         if (TF) {
             for (int s = threadIdx.x; s < sc; s += blockDim.x)
@@ -221,7 +253,7 @@ int pick_chunk(int ns, int D, int copies) {
 namespace {
 
 int launch_ss_fwd(bool is_tf, const float* x, const int64_t* labels, int64_t N, int D, const float* W, int64_t V, const int64_t* ids,
-                  int ns, float* loss, float* denom, TfArgs tf, cudaStream_t st) {
+                  int ns, float* loss, float* denom, TfArgs tf, SsExtra ex, cudaStream_t st) {
     if (D > 1024) return U2GNN_EUNSUPPORTED;
     if (N == 0) return U2GNN_OK;
     const int chunk = pick_chunk(ns, D, 1);
@@ -232,16 +264,16 @@ int launch_ss_fwd(bool is_tf, const float* x, const int64_t* labels, int64_t N, 
     const unsigned blocks = (unsigned)ceil_div64(N, npb);
     if (is_tf) {
         cudaFuncSetAttribute(ss_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ss_fwd_kernel<true><<<blocks, threads, smem, st>>>(x, labels, N, D, W, V, ids, ns, chunk, loss, denom, npb, tf);
+        ss_fwd_kernel<true><<<blocks, threads, smem, st>>>(x, labels, N, D, W, V, ids, ns, chunk, loss, denom, npb, tf, ex);
     } else {
         cudaFuncSetAttribute(ss_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ss_fwd_kernel<false><<<blocks, threads, smem, st>>>(x, labels, N, D, W, V, ids, ns, chunk, loss, denom, npb, tf);
+        ss_fwd_kernel<false><<<blocks, threads, smem, st>>>(x, labels, N, D, W, V, ids, ns, chunk, loss, denom, npb, tf, ex);
     }
     U2GNN_CHECK_LAUNCH();
 }
 
 int launch_ss_bwd(bool is_tf, const float* dloss, const float* x, const int64_t* labels, int64_t N, int D, const float* W, int64_t V,
-                  const int64_t* ids, int ns, const float* denom, float* dx, float* dW, TfArgs tf, cudaStream_t st) {
+                  const int64_t* ids, int ns, const float* denom, float* dx, float* dW, TfArgs tf, SsExtra ex, cudaStream_t st) {
     if (D > 1024) return U2GNN_EUNSUPPORTED;
     if (N == 0) return U2GNN_OK;
     const int threads = 256, warps = threads / 32;
@@ -255,10 +287,10 @@ int launch_ss_bwd(bool is_tf, const float* dloss, const float* x, const int64_t*
     const unsigned blocks = (unsigned)ceil_div64(N, npb);
     if (is_tf) {
         cudaFuncSetAttribute(ss_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ss_bwd_kernel<true><<<blocks, threads, smem, st>>>(dloss, x, labels, N, D, W, V, ids, ns, chunk, denom, dx, dW, npb, tf);
+        ss_bwd_kernel<true><<<blocks, threads, smem, st>>>(dloss, x, labels, N, D, W, V, ids, ns, chunk, denom, dx, dW, npb, tf, ex);
     } else {
         cudaFuncSetAttribute(ss_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ss_bwd_kernel<false><<<blocks, threads, smem, st>>>(dloss, x, labels, N, D, W, V, ids, ns, chunk, denom, dx, dW, npb, tf);
+        ss_bwd_kernel<false><<<blocks, threads, smem, st>>>(dloss, x, labels, N, D, W, V, ids, ns, chunk, denom, dx, dW, npb, tf, ex);
     }
     U2GNN_CHECK_LAUNCH();
 }
@@ -266,39 +298,42 @@ int launch_ss_bwd(bool is_tf, const float* dloss, const float* x, const int64_t*
 }  // namespace
 
 extern "C" int u2gnn_sampled_softmax_fwd(const float* x, const int64_t* labels, int64_t N, int D, const float* W,
-                                         int64_t V, const int64_t* ids, int ns, float* loss, float* denom,
-                                         u2gnn_stream_t stream) {
+                                         int64_t V, const int64_t* ids, int ns, const float* samp_rows, float* loss, float* denom,
+                                         int* err, u2gnn_stream_t stream) {
     if (!x || !labels || !W || !ids || !loss || !denom || N < 0 || D <= 0 || V <= 0 || ns <= 0) return U2GNN_EINVAL;
-    return launch_ss_fwd(false, x, labels, N, D, W, V, ids, ns, loss, denom, TfArgs{nullptr, nullptr, nullptr, nullptr}, as_stream(stream));
+    return launch_ss_fwd(false, x, labels, N, D, W, V, ids, ns, loss, denom, TfArgs{nullptr, nullptr, nullptr, nullptr},
+                         SsExtra{samp_rows, nullptr, err}, as_stream(stream));
 }
 
 extern "C" int u2gnn_sampled_softmax_bwd(const float* dloss, const float* x, const int64_t* labels, int64_t N, int D,
-                                         const float* W, int64_t V, const int64_t* ids, int ns, const float* denom,
-                                         float* dx, float* dW, u2gnn_stream_t stream) {
+                                         const float* W, int64_t V, const int64_t* ids, int ns, const float* samp_rows,
+                                         const float* denom, float* dx, float* dW, float* dsamp, int* err, u2gnn_stream_t stream) {
     if (!dloss || !x || !labels || !W || !ids || !denom || !dx || !dW || N < 0 || D <= 0 || V <= 0 || ns <= 0)
         return U2GNN_EINVAL;
+    if ((samp_rows == nullptr) != (dsamp == nullptr)) return U2GNN_EINVAL;     // pre-gathered rows take their gradient back the same way
     return launch_ss_bwd(false, dloss, x, labels, N, D, W, V, ids, ns, denom, dx, dW, TfArgs{nullptr, nullptr, nullptr, nullptr},
-                         as_stream(stream));
+                         SsExtra{samp_rows, dsamp, err}, as_stream(stream));
 }
 
-// TF-model variant (see TfArgs): bias[V], true_q[N] / samp_q[ns] = expected counts from u2gnn_logu_expected_count.
+// the TF model's loss (bias, log-Q correction, accidental hits removed, label inside the softmax)
 extern "C" int u2gnn_sampled_softmax_tf_fwd(const float* x, const int64_t* labels, int64_t N, int D, const float* W, const float* bias,
                                             int64_t V, const int64_t* ids, int ns, const float* true_q, const float* samp_q,
-                                            float* loss, float* denom, u2gnn_stream_t stream) {
+                                            float* loss, float* denom, int* err, u2gnn_stream_t stream) {
     if (!x || !labels || !W || !bias || !ids || !true_q || !samp_q || !loss || !denom || N < 0 || D <= 0 || V <= 0 || ns <= 0)
         return U2GNN_EINVAL;
     if (V > 2147483647LL) return U2GNN_EUNSUPPORTED;
-    return launch_ss_fwd(true, x, labels, N, D, W, V, ids, ns, loss, denom, TfArgs{bias, true_q, samp_q, nullptr}, as_stream(stream));
+    return launch_ss_fwd(true, x, labels, N, D, W, V, ids, ns, loss, denom, TfArgs{bias, true_q, samp_q, nullptr},
+                         SsExtra{nullptr, nullptr, err}, as_stream(stream));
 }
 
 extern "C" int u2gnn_sampled_softmax_tf_bwd(const float* dloss, const float* x, const int64_t* labels, int64_t N, int D,
                                             const float* W, const float* bias, int64_t V, const int64_t* ids, int ns,
                                             const float* true_q, const float* samp_q, const float* denom, float* dx, float* dW,
-                                            float* dbias, u2gnn_stream_t stream) {
+                                            float* dbias, int* err, u2gnn_stream_t stream) {
     if (!dloss || !x || !labels || !W || !bias || !ids || !true_q || !samp_q || !denom || !dx || !dW || !dbias || N < 0 || D <= 0 ||
         V <= 0 || ns <= 0)
         return U2GNN_EINVAL;
     if (V > 2147483647LL) return U2GNN_EUNSUPPORTED;
     return launch_ss_bwd(true, dloss, x, labels, N, D, W, V, ids, ns, denom, dx, dW, TfArgs{bias, true_q, samp_q, dbias},
-                         as_stream(stream));
+                         SsExtra{nullptr, nullptr, err}, as_stream(stream));
 }

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(kThreads) logu_sample_kernel(double log_n, int
                                                                int64_t* __restrict__ out_ids,
                                                                int32_t* __restrict__ out_tries,
                                                                uint32_t* __restrict__ keys, uint32_t* __restrict__ minidx,
-                                                               uint32_t cap_mask) {
+                                                               uint32_t cap_mask, const uint32_t* __restrict__ exclude) {
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t s_got, s_stop;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -73,10 +73,15 @@ __global__ void __launch_bounds__(kThreads) logu_sample_kernel(double log_n, int
         g[2] = mulmod(g[1], kMul);
         g[3] = mulmod(g[2], kMul);
         uint32_t v[2], slot[2];
+        bool skip[2];
         v[0] = (uint32_t)draw_value(g[0], g[1], log_n);
         v[1] = (uint32_t)draw_value(g[2], g[3], log_n);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
+            // sample_unique (Log_Uniform_Sampler.cpp:73-88): a draw that hits a label consumes the stream and is dropped
+            skip[k] = exclude && ((exclude[v[k] >> 5] >> (v[k] & 31u)) & 1u);
+            slot[k] = 0u;
+            if (skip[k]) continue;
             uint32_t s = hash_slot(v[k], cap_mask);
             while (true) {
                 uint32_t prev = atomicCAS(keys + s, 0xFFFFFFFFu, v[k]);
@@ -88,8 +93,8 @@ __global__ void __launch_bounds__(kThreads) logu_sample_kernel(double log_n, int
         }
         __syncthreads();
         // ---- first occurrence flags and ordered prefix sum
-        const uint32_t f0 = (minidx[slot[0]] == t0) ? 1u : 0u;
-        const uint32_t f1 = (minidx[slot[1]] == t0 + 1u) ? 1u : 0u;
+        const uint32_t f0 = (!skip[0] && minidx[slot[0]] == t0) ? 1u : 0u;
+        const uint32_t f1 = (!skip[1] && minidx[slot[1]] == t0 + 1u) ? 1u : 0u;
         uint32_t incl = f0 + f1;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -141,6 +146,14 @@ __global__ void expected_count_kernel(double log_np1, const int32_t* __restrict_
     }
 }
 
+// bit v of the map = id v is excluded (one of the labels)
+__global__ void exclude_bitmap_kernel(const int64_t* __restrict__ labels, int64_t n, int64_t range_max, uint32_t* __restrict__ map) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = labels[i];
+        if (v >= 0 && v < range_max) atomicOr(map + (v >> 5), 1u << (v & 31));
+    }
+}
+
 uint32_t table_capacity(int64_t size) {
     uint64_t need = 4ull * (uint64_t)(size + kBatch);
     uint64_t cap = 1024;
@@ -168,7 +181,32 @@ extern "C" int u2gnn_logu_sample(int64_t range_max, int64_t size, uint32_t* stat
     // log(N) is evaluated on the host with the same libm call as the reference (:60)
     const double log_n = log((double)range_max);
     logu_sample_kernel<<<1, kThreads, 0, as_stream(stream)>>>(log_n, size, state_inout, out_ids, out_tries, keys, minidx,
-                                                              cap - 1u);
+                                                              cap - 1u, nullptr);
+    U2GNN_CHECK_LAUNCH();
+}
+
+extern "C" size_t u2gnn_logu_sample_unique_workspace_bytes(int64_t range_max, int64_t size) {
+    if (size < 0 || range_max < 1) return 0;
+    return u2gnn_logu_sample_workspace_bytes(size) + (size_t)((range_max + 31) / 32) * sizeof(uint32_t) + sizeof(int32_t);
+}
+
+extern "C" int u2gnn_logu_sample_unique(int64_t range_max, int64_t size, const int64_t* labels, int64_t n_labels,
+                                        uint32_t* state_inout, int64_t* out_ids, void* workspace, size_t workspace_bytes,
+                                        u2gnn_stream_t stream) {
+    if (!state_inout || !out_ids || !workspace || (!labels && n_labels > 0) || n_labels < 0) return U2GNN_EINVAL;
+    if (range_max < 1 || range_max >= (1ll << 31) || size < 1) return U2GNN_EINVAL;
+    if (size + n_labels > range_max) return U2GNN_EINVAL;  // fewer than `size` ids might remain: the reference would loop forever
+    if (size > (1ll << 26)) return U2GNN_EUNSUPPORTED;
+    if (workspace_bytes < u2gnn_logu_sample_unique_workspace_bytes(range_max, size)) return U2GNN_EWORKSPACE;
+    const uint32_t cap = table_capacity(size);
+    uint32_t* keys = static_cast<uint32_t*>(workspace);
+    uint32_t* minidx = keys + cap;
+    uint32_t* map = minidx + cap;
+    int32_t* tries = reinterpret_cast<int32_t*>(map + (range_max + 31) / 32);
+    cudaStream_t st = as_stream(stream);
+    if (cudaMemsetAsync(map, 0, (size_t)((range_max + 31) / 32) * sizeof(uint32_t), st) != cudaSuccess) return U2GNN_ELAUNCH;
+    if (n_labels > 0) exclude_bitmap_kernel<<<grid_for(n_labels, 256, 4), 256, 0, st>>>(labels, n_labels, range_max, map);
+    logu_sample_kernel<<<1, kThreads, 0, st>>>(log((double)range_max), size, state_inout, out_ids, tries, keys, minidx, cap - 1u, map);
     U2GNN_CHECK_LAUNCH();
 }
 

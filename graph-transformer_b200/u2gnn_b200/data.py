@@ -271,6 +271,6 @@ class DeviceBatchBuilder:
                  sid & 0xFFFFFFFF, _ptr(input_x), _ptr(node_global), _stream())
         d = self.X.shape[1]
         Xc = torch.empty((N, d), dtype=torch.float32, device=self.device)
-        LIB.call("u2gnn_gather_rows", _ptr(self.X), self.X.shape[0], d, _ptr(node_global), N, 1, _ptr(Xc), _stream())
+        LIB.call("u2gnn_gather_rows", _ptr(self.X), self.X.shape[0], d, _ptr(node_global), N, 1, _ptr(Xc), 0, _stream())
         labels = torch.from_numpy(self.labels_host[sel]).to(self.device, non_blocking=True)
         return input_x, off_d, Xc, labels, node_global

@@ -91,11 +91,38 @@ def _check(t, dtype, name):
 # --------------------------------------------------------------------------------------
 # thin wrappers (tensor -> pointer)
 # --------------------------------------------------------------------------------------
+_ERR = {}          # device index -> int32 error word the kernels OR into (bit 0: label out of range, bit 1: gather index out of range)
+ERR_MESSAGES = {1: "sampled softmax: a label lies outside [0, vocab) (the reference's index_select raises, sampled_softmax.py:45)",
+                2: "row gather: an index lies outside the table (the reference's F.embedding raises, pytorch_U2GNN_Sup.py:32)"}
+DEBUG_CHECKS = os.environ.get("U2GNN_DEBUG_CHECKS", "0") != "0"     # check the error word (one device sync) after every model forward
+
+
+def err_word(device=None):
+    """The device error word of `device` (allocated on first use).  Kernels set bits instead of reading out of bounds."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    w = _ERR.get(key)
+    if w is None:
+        w = _ERR[key] = torch.zeros(1, dtype=torch.int32, device=dev)
+    return w
+
+
+def check_device_errors(device=None):
+    """Raises IndexError if any kernel since the last check met an out-of-range index (synchronises; call it where the host
+    already waits for the device, e.g. next to loss.item())."""
+    w = err_word(device)
+    bits = int(w.item())
+    if bits:
+        w.zero_()
+        raise IndexError("; ".join(m for b, m in ERR_MESSAGES.items() if bits & b))
+
+
 def gather_rows(table, idx, idx_stride=1, n_idx=None):
     _check(table, torch.float32, "table"); _check(idx, torch.int64, "idx")
     n = idx.numel() // idx_stride if n_idx is None else n_idx
     out = torch.empty((n, table.shape[1]), dtype=torch.float32, device=table.device)
-    LIB.call("u2gnn_gather_rows", _ptr(table), table.shape[0], table.shape[1], _ptr(idx), n, idx_stride, _ptr(out), _stream())
+    LIB.call("u2gnn_gather_rows", _ptr(table), table.shape[0], table.shape[1], _ptr(idx), n, idx_stride, _ptr(out),
+             _ptr(err_word(table.device)), _stream())
     return out
 
 

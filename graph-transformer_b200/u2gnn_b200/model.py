@@ -258,6 +258,19 @@ class LogUniformSampler:
         sample_freq = self.expected_count_device(ids)
         return ids.tolist(), true_freq.tolist(), sample_freq.tolist()
 
+    def sample_unique(self, size, labels):
+        """log_uniform.pyx:25-27 -> Log_Uniform_Sampler.cpp:73-88: `size` distinct ids none of which is a label."""
+        size = int(size)
+        lab = torch.as_tensor(np.asarray(list(labels)), dtype=torch.int64, device=self.device).contiguous()
+        if size + lab.numel() > self.N:
+            raise ValueError("size + len(labels) > N: the reference sampler may never terminate")
+        wb = LIB.call("u2gnn_logu_sample_unique_workspace_bytes", self.N, size)
+        ws = torch.empty(wb, dtype=torch.uint8, device=self.device)
+        ids = torch.empty(size, dtype=torch.int64, device=self.device)
+        LIB.call("u2gnn_logu_sample_unique", self.N, size, lab.data_ptr(), lab.numel(), self.state.data_ptr(), ids.data_ptr(),
+                 ws.data_ptr(), wb, E._stream())
+        return ids.tolist()
+
     def probability(self, idx):
         return float(np.float32((math.log(idx + 2) - math.log(idx + 1)) / math.log(self.N + 1)))
 
@@ -274,7 +287,9 @@ class _SampledSoftmaxFn(torch.autograd.Function):
         loss = torch.empty(N, dtype=torch.float32, device=x.device)
         denom = torch.empty(N, dtype=torch.float32, device=x.device)
         LIB.call("u2gnn_sampled_softmax_fwd", x.data_ptr(), labels.data_ptr(), N, D, Wd.data_ptr(), W.shape[0],
-                 ids.data_ptr(), ids.numel(), loss.data_ptr(), denom.data_ptr(), E._stream())
+                 ids.data_ptr(), ids.numel(), 0, loss.data_ptr(), denom.data_ptr(), E.err_word(x.device).data_ptr(), E._stream())
+        if E.DEBUG_CHECKS:
+            E.check_device_errors(x.device)
         ctx.args = (x, Wd, labels, ids, denom)
         return loss
 
@@ -286,7 +301,8 @@ class _SampledSoftmaxFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         dW = torch.zeros_like(W)                      # dense, like the reference's W.grad
         LIB.call("u2gnn_sampled_softmax_bwd", dloss.data_ptr(), x.data_ptr(), labels.data_ptr(), N, D, W.data_ptr(),
-                 W.shape[0], ids.data_ptr(), ids.numel(), denom.data_ptr(), dx.data_ptr(), dW.data_ptr(), E._stream())
+                 W.shape[0], ids.data_ptr(), ids.numel(), 0, denom.data_ptr(), dx.data_ptr(), dW.data_ptr(), 0,
+                 E.err_word(x.device).data_ptr(), E._stream())
         return dx, dW, None, None
 
 
@@ -300,7 +316,8 @@ class _SampledSoftmaxTFFn(torch.autograd.Function):
         loss = torch.empty(N, dtype=torch.float32, device=x.device)
         denom = torch.empty(N, dtype=torch.float32, device=x.device)
         LIB.call("u2gnn_sampled_softmax_tf_fwd", x.data_ptr(), labels.data_ptr(), N, D, Wd.data_ptr(), bd.data_ptr(), W.shape[0],
-                 ids.data_ptr(), ids.numel(), true_q.data_ptr(), samp_q.data_ptr(), loss.data_ptr(), denom.data_ptr(), E._stream())
+                 ids.data_ptr(), ids.numel(), true_q.data_ptr(), samp_q.data_ptr(), loss.data_ptr(), denom.data_ptr(),
+                 E.err_word(x.device).data_ptr(), E._stream())
         ctx.args = (x, Wd, bd, labels, ids, true_q, samp_q, denom)
         return loss
 
@@ -314,7 +331,7 @@ class _SampledSoftmaxTFFn(torch.autograd.Function):
         db = torch.zeros_like(b)
         LIB.call("u2gnn_sampled_softmax_tf_bwd", dloss.data_ptr(), x.data_ptr(), labels.data_ptr(), N, D, W.data_ptr(), b.data_ptr(),
                  W.shape[0], ids.data_ptr(), ids.numel(), true_q.data_ptr(), samp_q.data_ptr(), denom.data_ptr(), dx.data_ptr(),
-                 dW.data_ptr(), db.data_ptr(), E._stream())
+                 dW.data_ptr(), db.data_ptr(), E.err_word(x.device).data_ptr(), E._stream())
         return dx, dW, db, None, None, None, None
 
 

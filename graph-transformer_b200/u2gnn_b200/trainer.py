@@ -237,37 +237,34 @@ class UnSupTrainer:
         W = m.ss.weight.data
         ns = sample_ids.numel()
         self.arena.zero_grad()
+        gW = self.arena.gviews["ss.weight"]
+        err = E.err_word(X.device).data_ptr()
         if rs is None:
-            W_use, V_use, labels, ids, dW_use = W, V, input_y, sample_ids, self.arena.gviews["ss.weight"]
+            labels, samp, dsamp, samp_ptr, dsamp_ptr = input_y, None, None, 0, 0
         else:
-            # row-sharded table: true-class rows are local (graph-aligned blocks); the ns sampled rows are assembled
-            # on every rank by one all-reduce of an [ns, D] buffer (owners fill their rows, the gather kernel skips
-            # ids outside the local block) and appended to the local block as rows V .. V+ns-1
+            # row-sharded table: true-class rows are local (graph-aligned blocks, labels re-based to the block; a label outside
+            # it sets the device error word instead of reading out of bounds).  The ns sampled rows are assembled on every rank
+            # by ONE all-reduce of an [ns, D] buffer (owners fill their rows, the gather zero-fills ids outside the local
+            # block) and handed to the loss kernels as a second table; their gradient comes back the same way.  Nothing of
+            # size V is copied or zeroed per step besides the gradient arena itself.
             local_ids = (sample_ids - rs.lo).contiguous()
-            W_use = torch.empty((V + ns, D), dtype=torch.float32, device=X.device)
-            W_use[:V].copy_(W)
-            samp = W_use[V:]
-            samp.zero_()
-            LIB.call("u2gnn_gather_rows", W.data_ptr(), V, D, local_ids.data_ptr(), ns, 1, samp.data_ptr(), s)
+            samp = torch.empty((ns, D), dtype=torch.float32, device=X.device)
+            LIB.call("u2gnn_gather_rows", W.data_ptr(), V, D, local_ids.data_ptr(), ns, 1, samp.data_ptr(), 0, s)
             all_reduce_sum_(samp)
-            V_use = V + ns
             labels = (input_y - rs.lo).contiguous()
-            ids = torch.arange(V, V + ns, dtype=torch.int64, device=X.device)
-            dW_use = torch.zeros((V + ns, D), dtype=torch.float32, device=X.device)
+            dsamp = torch.zeros((ns, D), dtype=torch.float32, device=X.device)
+            samp_ptr, dsamp_ptr = samp.data_ptr(), dsamp.data_ptr()
         node_loss = torch.empty(N, dtype=torch.float32, device=X.device)
         denom = torch.empty(N, dtype=torch.float32, device=X.device)
-        LIB.call("u2gnn_sampled_softmax_fwd", vec.data_ptr(), labels.data_ptr(), N, D, W_use.data_ptr(), V_use,
-                 ids.data_ptr(), ns, node_loss.data_ptr(), denom.data_ptr(), s)
+        LIB.call("u2gnn_sampled_softmax_fwd", vec.data_ptr(), labels.data_ptr(), N, D, W.data_ptr(), V,
+                 sample_ids.data_ptr(), ns, samp_ptr, node_loss.data_ptr(), denom.data_ptr(), err, s)
         dloss = torch.ones(N, dtype=torch.float32, device=X.device)
         dvec = torch.empty_like(vec)
-        LIB.call("u2gnn_sampled_softmax_bwd", dloss.data_ptr(), vec.data_ptr(), labels.data_ptr(), N, D, W_use.data_ptr(), V_use,
-                 ids.data_ptr(), ns, denom.data_ptr(), dvec.data_ptr(), dW_use.data_ptr(), s)
+        LIB.call("u2gnn_sampled_softmax_bwd", dloss.data_ptr(), vec.data_ptr(), labels.data_ptr(), N, D, W.data_ptr(), V,
+                 sample_ids.data_ptr(), ns, samp_ptr, denom.data_ptr(), dvec.data_ptr(), gW.data_ptr(), dsamp_ptr, err, s)
         if rs is not None:
-            gW = self.arena.gviews["ss.weight"]
-            LIB.call("u2gnn_axpy", 1.0, dW_use.data_ptr(), gW.data_ptr(), V * D, s)            # local true-class rows
-            d_samp = dW_use[V:]
-            all_reduce_sum_(d_samp)                                                             # sampled-row gradients of all ranks
-            LIB.call("u2gnn_scatter_add_rows", d_samp.data_ptr(), ns, D, local_ids.data_ptr(), 1, gW.data_ptr(), V, s)
+            all_reduce_sum_(dsamp)                                                              # sampled-row gradients of all ranks
+            LIB.call("u2gnn_scatter_add_rows", dsamp.data_ptr(), ns, D, local_ids.data_ptr(), 1, gW.data_ptr(), V, s)
         dcat = torch.empty_like(dvec)
         LIB.call("u2gnn_dropout_apply", dvec.data_ptr(), dvec.numel(), drop.seed, E.STREAM_CONCAT, thr, dcat.data_ptr(), s)
         dsrc_next = None

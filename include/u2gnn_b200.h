@@ -43,9 +43,11 @@ uint32_t u2gnn_rng_mask_word_host(uint64_t seed, uint32_t stream, uint64_t group
 
 /* ---- K1: row gather.  Replaces F.embedding(input_x, X_concat) / F.embedding(input_x, output_Tr)
  *      (pytorch_U2GNN_Sup.py:32,39).  out[i,:] = table[idx[i],:]; idx_stride lets the caller
- *      gather only column 0 of input_x (idx element i is idx[i*idx_stride]).  Bit-exact copy. */
+ *      gather only column 0 of input_x (idx element i is idx[i*idx_stride]).  Bit-exact copy.
+ *      An index outside [0, n_table) - where F.embedding raises - yields a ZERO row and sets bit 1 of the device
+ *      error word err (may be NULL: the row-sharded sampled-row gather uses the zero rows on purpose). */
 int u2gnn_gather_rows(const float* table, int64_t n_table, int d, const int64_t* idx, int64_t n_idx,
-                      int64_t idx_stride, float* out, u2gnn_stream_t stream);
+                      int64_t idx_stride, float* out, int* err, u2gnn_stream_t stream);
 /* backward of the re-gather (autograd of pytorch_U2GNN_Sup.py:39): dst[idx[i],:] += grad[i,:].
  * dst must be initialised by the caller.  deterministic=0 uses fp32 atomics. */
 int u2gnn_scatter_add_rows(const float* grad, int64_t n_idx, int d, const int64_t* idx, int64_t idx_stride,
@@ -148,6 +150,12 @@ int u2gnn_head_bwd(const float* dscores, const float* ge, int64_t G, int d, cons
 size_t u2gnn_logu_sample_workspace_bytes(int64_t size);
 int u2gnn_logu_sample(int64_t range_max, int64_t size, uint32_t* state_inout, int64_t* out_ids, int32_t* out_tries,
                       void* workspace, size_t workspace_bytes, u2gnn_stream_t stream);
+/* sample_unique (Log_Uniform_Sampler.cpp:73-88; binding log_uniform.pyx:25-27): `size` distinct ids NOT in labels[n_labels];
+ * draws that hit a label consume the engine stream and are dropped.  Same id set and advanced state as the reference.
+ * Requires size + n_labels <= range_max (otherwise the reference may never terminate). */
+size_t u2gnn_logu_sample_unique_workspace_bytes(int64_t range_max, int64_t size);
+int u2gnn_logu_sample_unique(int64_t range_max, int64_t size, const int64_t* labels, int64_t n_labels, uint32_t* state_inout,
+                             int64_t* out_ids, void* workspace, size_t workspace_bytes, u2gnn_stream_t stream);
 /* expected_count (Log_Uniform_Sampler.cpp:23-32): out[i] = -expm1(tries * log1p(-prob[ids[i]])) */
 int u2gnn_logu_expected_count(int64_t range_max, const int32_t* tries, const int64_t* ids, int64_t n, float* out,
                               u2gnn_stream_t stream);
@@ -155,12 +163,18 @@ int u2gnn_logu_expected_count(int64_t range_max, const int32_t* tries, const int
 /* ---- K7: fused sampled softmax.  Replaces SampledSoftmax.sampled (sampled_softmax.py:36-56):
  *      loss[i] = -log( exp(x_i . W[y_i]) / sum_s exp(x_i . W[ids[s]]) ), no max-subtraction, no
  *      log-Q correction.  Saves denom[N] for the backward.
- *      Backward: dx[N,D] and a DENSE dW[V,D] accumulation (the reference's W.grad is dense). */
+ *      Backward: dx[N,D] and a DENSE dW[V,D] accumulation (the reference's W.grad is dense).
+ *      samp_rows (may be NULL): the ns sampled rows already gathered into one [ns, D] buffer (row-sharded table: the
+ *      owners' rows all-reduced, parallel.py) - ids are then not dereferenced into W, and the backward adds the sampled
+ *      rows' gradient into dsamp[ns, D] instead of dW[ids] (samp_rows and dsamp go together).
+ *      err (may be NULL): device error word; bit 0 is set when a label lies outside [0, V) - the reference's
+ *      index_select raises there (sampled_softmax.py:45); the kernels give such a row loss 0 and no gradient. */
 int u2gnn_sampled_softmax_fwd(const float* x, const int64_t* labels, int64_t N, int D, const float* W, int64_t V,
-                              const int64_t* ids, int ns, float* loss, float* denom, u2gnn_stream_t stream);
+                              const int64_t* ids, int ns, const float* samp_rows, float* loss, float* denom, int* err,
+                              u2gnn_stream_t stream);
 int u2gnn_sampled_softmax_bwd(const float* dloss, const float* x, const int64_t* labels, int64_t N, int D,
-                              const float* W, int64_t V, const int64_t* ids, int ns, const float* denom, float* dx,
-                              float* dW, u2gnn_stream_t stream);
+                              const float* W, int64_t V, const int64_t* ids, int ns, const float* samp_rows,
+                              const float* denom, float* dx, float* dW, float* dsamp, int* err, u2gnn_stream_t stream);
 /* TF-model variant of the loss (U2GNN_tf/model_U2GNN_Unsup_multi.py:54-58, tf.nn.sampled_softmax_loss with
  * its defaults): t_i = x_i.W[y_i] + bias[y_i] - log true_q[i], l_is = x_i.W[s] + bias[s] - log samp_q[s] (accidental hits
  * s == y_i removed), loss_i = log(exp t_i + sum_s exp l_is) - t_i.  true_q / samp_q are the expected counts of the labels and of
@@ -168,11 +182,11 @@ int u2gnn_sampled_softmax_bwd(const float* dloss, const float* x, const int64_t*
  * accumulates the bias gradient dbias[V] (+=, like dW). */
 int u2gnn_sampled_softmax_tf_fwd(const float* x, const int64_t* labels, int64_t N, int D, const float* W, const float* bias,
                                  int64_t V, const int64_t* ids, int ns, const float* true_q, const float* samp_q, float* loss,
-                                 float* denom, u2gnn_stream_t stream);
+                                 float* denom, int* err, u2gnn_stream_t stream);
 int u2gnn_sampled_softmax_tf_bwd(const float* dloss, const float* x, const int64_t* labels, int64_t N, int D, const float* W,
                                  const float* bias, int64_t V, const int64_t* ids, int ns, const float* true_q,
                                  const float* samp_q, const float* denom, float* dx, float* dW, float* dbias,
-                                 u2gnn_stream_t stream);
+                                 int* err, u2gnn_stream_t stream);
 
 /* ---- K8: fused global-norm clip + Adam.  Replaces clip_grad_norm_(params, 0.5) + Adam.step()
  *      (train_pytorch_U2GNN_Sup.py:145,160-161) over ONE flat parameter arena.

@@ -333,6 +333,11 @@ if __name__ == "__main__":
     if "--eval-only" in sys.argv:
         make_eval_fixtures()
         sys.exit(0)
+    if "--cfg-shapes-only" in sys.argv:
+        make_sup_case("sup_cfg1_shape",      31, [17, 23, 13, 28],           8, 7,  1024, 3, 1, 2, "nodes")
+        make_unsup_case("unsup_cfg2_shape",  32, [26, 19, 31, 14],           4, 4,  1024, 2, 1, 8792, 512, "nodes")
+        make_unsup_case("unsup_cfg2_shape_nb", 33, [26, 19, 31, 14],         4, 4,  1024, 2, 1, 8792, 512, "neighbors")
+        sys.exit(0)
     make_mutag_kat()
     make_data_fixtures()
     make_eval_fixtures()
@@ -346,3 +351,8 @@ if __name__ == "__main__":
     make_sup_case("sup_nodes_L2",        15, [17, 23, 9, 28],            8, 7,  64,  3, 2, 2, "nodes")
     make_unsup_case("unsup_neighbors",   21, [7, 3, 12, 5],              4, 4,  32,  2, 2, 300, 40, "neighbors")
     make_unsup_case("unsup_nodes",       22, [7, 3, 12, 5],              4, 4,  32,  2, 1, 300, 40, "nodes")
+    # the exact shapes of BASELINE.json configs[0] / configs[1] (MUTAG: d 7, k 8, T 3, ff 1024; PTC degree-as-tag: d 4, k 4, T 2,
+    # ff 1024, V 8 792, ns 512), attention as the reference runs it (nodes) and the intended layout
+    make_sup_case("sup_cfg1_shape",      31, [17, 23, 13, 28],           8, 7,  1024, 3, 1, 2, "nodes")
+    make_unsup_case("unsup_cfg2_shape",  32, [26, 19, 31, 14],           4, 4,  1024, 2, 1, 8792, 512, "nodes")
+    make_unsup_case("unsup_cfg2_shape_nb", 33, [26, 19, 31, 14],         4, 4,  1024, 2, 1, 8792, 512, "neighbors")

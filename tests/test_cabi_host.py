@@ -47,7 +47,7 @@ def test_status_codes_without_gpu(U):
             U.require_device()
     # argument validation happens before any launch: null pointers / bad sizes -> EINVAL, raised as RuntimeError
     with pytest.raises(RuntimeError, match="invalid argument"):
-        lib.call("u2gnn_gather_rows", 0, 10, 4, 0, 5, 1, 0, 0)
+        lib.call("u2gnn_gather_rows", 0, 10, 4, 0, 5, 1, 0, 0, 0)
     with pytest.raises(RuntimeError, match="invalid argument"):
         lib.call("u2gnn_seqattn_fwd", 1, 4, 40, 40, 8, 0, 0, 0, 1, 0)      # S > 32
     with pytest.raises(RuntimeError, match="invalid argument"):

@@ -94,7 +94,7 @@ def test_dropout_stream_matches_oracle_restatement(U, p):
 
 # ------------------------------------------------------------------ supervised model vs golden (reference) fixtures
 SUP_CASES = ["sup_neighbors_small", "sup_neighbors_L2", "sup_neighbors_d65", "sup_neighbors_d64",
-             "sup_nodes_small", "sup_nodes_L2"]
+             "sup_nodes_small", "sup_nodes_L2", "sup_cfg1_shape"]
 
 
 def build_sup(U, c, train=False):
@@ -205,7 +205,7 @@ def test_same_seed_gives_reference_initial_weights(U):
 
 
 # ------------------------------------------------------------------ unsupervised: sampler + sampled softmax
-@pytest.mark.parametrize("case", ["unsup_neighbors", "unsup_nodes"])
+@pytest.mark.parametrize("case", ["unsup_neighbors", "unsup_nodes", "unsup_cfg2_shape", "unsup_cfg2_shape_nb"])
 def test_unsup_loss_and_grads_match_reference(U, case):
     c = load_golden(case)
     params, grads, _ = split_case(c)
@@ -352,3 +352,110 @@ def test_tied_timesteps_gradient_is_the_sum_over_timesteps(precision, d, ff):
     s = tied(b["input_x"], b["rowptr"], b["X"])
     s.sum().backward()
     assert all(p.grad is not None for p in tied.parameters())
+
+
+# ------------------------------------------------------------------ round 2: library hygiene paths
+def test_sample_unique_matches_reference(U):
+    """LogUniformSampler.sample_unique (log_uniform.pyx:25-27 -> Log_Uniform_Sampler.cpp:73-88): same id set as the compiled
+    reference / the C oracle, labels excluded, engine state carried into the next plain sample() call."""
+    from oracle.sampler import OracleSampler, RefSampler
+    checker = RefSampler if RefSampler.available() else OracleSampler
+    rng = np.random.default_rng(3)
+    for V, ns, nl in [(100, 20, 30), (8792, 512, 75), (2540000, 512, 4000), (64, 10, 54)]:
+        labels = rng.choice(min(V, 5000), size=nl, replace=False).astype(np.int64)      # low ids: the ones log-uniform draws hit
+        a, b = U.LogUniformSampler(V), checker(V)
+        for _ in range(2):
+            ids = a.sample_unique(ns, labels.tolist())
+            ref = b.sample_unique(ns, labels.tolist())
+            assert len(ids) == ns and len(set(ids)) == ns
+            assert not (set(ids) & set(labels.tolist()))
+            assert sorted(ids) == sorted(int(v) for v in ref)
+        after = a.sample_device(ns).cpu().numpy()                                       # the stream position agrees afterwards
+        oid, tries = b.sample_with_tries(ns)
+        assert int(a.tries.item()) == tries and np.array_equal(np.sort(after), np.sort(oid))
+    with pytest.raises(ValueError):
+        U.LogUniformSampler(10).sample_unique(6, [0, 1, 2, 3, 4])
+
+
+def test_gather_out_of_range_index_zero_row_and_error_word(U):
+    """F.embedding raises on an out-of-range id (pytorch_U2GNN_Sup.py:32); the kernel writes a zero row (never uninitialised
+    memory) and sets the device error word, which check_device_errors turns into an IndexError."""
+    from u2gnn_b200 import engine as E
+    table = torch.arange(40, dtype=torch.float32, device="cuda").reshape(10, 4) + 1
+    idx = torch.tensor([0, 9, 10, -1, 3], dtype=torch.int64, device="cuda")
+    E.err_word().zero_()
+    out = E.gather_rows(table, idx)
+    assert torch.equal(out[[0, 1, 4]], table[[0, 9, 3]])
+    assert torch.equal(out[[2, 3]], torch.zeros(2, 4, device="cuda"))
+    with pytest.raises(IndexError):
+        E.check_device_errors()
+    E.check_device_errors()                                  # cleared by the raise
+    out = E.gather_rows(table, idx[:2])
+    E.check_device_errors()
+
+
+def test_sampled_softmax_label_out_of_range_is_reported_not_read(U):
+    """sampled_softmax.py:45 index_select raises on a bad label; the kernels skip the row (loss 0, zero gradient), touch no
+    memory outside W / dW and set the error word.  Valid rows are unaffected."""
+    from u2gnn_b200 import engine as E
+    from oracle import u2gnn_oracle as O
+    rng = np.random.default_rng(8)
+    N, D, V, ns = 37, 4, 50, 16
+    x = rng.standard_normal((N, D)).astype(np.float32)
+    W = (0.3 * rng.standard_normal((V, D))).astype(np.float32)
+    y = rng.integers(0, V, size=N).astype(np.int64)
+    ids = rng.choice(V, size=ns, replace=False).astype(np.int64)
+    bad = y.copy()
+    bad[5], bad[20] = V, -3
+    guard = 64                                               # canary rows around dW
+    dWbuf = torch.zeros((V + 2 * guard, D), device="cuda")
+    dW = dWbuf[guard:guard + V]
+    xt, Wt, it = dev(x), dev(W), dev(ids)
+    loss = torch.empty(N, device="cuda"); denom = torch.empty(N, device="cuda"); dx = torch.full((N, D), 7.0, device="cuda")
+    E.err_word().zero_()
+    err = E.err_word().data_ptr()
+    yt = dev(bad)
+    U.LIB.call("u2gnn_sampled_softmax_fwd", xt.data_ptr(), yt.data_ptr(), N, D, Wt.data_ptr(), V, it.data_ptr(), ns, 0,
+               loss.data_ptr(), denom.data_ptr(), err, E._stream())
+    dl = torch.ones(N, device="cuda")
+    U.LIB.call("u2gnn_sampled_softmax_bwd", dl.data_ptr(), xt.data_ptr(), yt.data_ptr(), N, D, Wt.data_ptr(), V, it.data_ptr(), ns, 0,
+               denom.data_ptr(), dx.data_ptr(), dW.data_ptr(), 0, err, E._stream())
+    with pytest.raises(IndexError):
+        E.check_device_errors()
+    ok = np.ones(N, dtype=bool); ok[[5, 20]] = False
+    lo, cache = O.sampled_softmax_fwd(x[ok].astype(np.float64), y[ok], W.astype(np.float64), ids)
+    dxo, dWo = O.sampled_softmax_bwd(np.ones(ok.sum()), cache, x[ok].astype(np.float64), y[ok], W.shape, ids)
+    assert rel_err(loss.cpu().numpy()[ok], lo) < TOL and np.all(loss.cpu().numpy()[~ok] == 0)
+    assert rel_err(dx.cpu().numpy()[ok], dxo) < TOL and np.all(dx.cpu().numpy()[~ok] == 0)
+    assert rel_err(dW.cpu().numpy(), dWo) < TOL
+    assert float(dWbuf[:guard].abs().sum()) == 0 and float(dWbuf[guard + V:].abs().sum()) == 0
+
+
+def test_sampled_softmax_with_pregathered_rows_equals_plain_path(U):
+    """Row-sharded mode: the ns sampled rows handed in as a second [ns, D] table (and their gradient returned in dsamp) give
+    the same loss / dx / true-row gradient as indexing W directly; dsamp equals the sampled rows' share of dW."""
+    from u2gnn_b200 import engine as E
+    rng = np.random.default_rng(9)
+    N, D, V, ns = 300, 8, 200, 64
+    x = dev(rng.standard_normal((N, D)).astype(np.float32))
+    W = dev((0.3 * rng.standard_normal((V, D))).astype(np.float32))
+    y = dev(rng.integers(0, V, size=N).astype(np.int64))
+    ids = dev(rng.choice(V, size=ns, replace=False).astype(np.int64))
+    samp = W[ids].contiguous()
+    err = E.err_word().data_ptr()
+    out = {}
+    for mode in ("plain", "rows"):
+        loss = torch.empty(N, device="cuda"); denom = torch.empty(N, device="cuda"); dx = torch.empty((N, D), device="cuda")
+        dW = torch.zeros((V, D), device="cuda"); dsamp = torch.zeros((ns, D), device="cuda")
+        sp, dp = (samp.data_ptr(), dsamp.data_ptr()) if mode == "rows" else (0, 0)
+        U.LIB.call("u2gnn_sampled_softmax_fwd", x.data_ptr(), y.data_ptr(), N, D, W.data_ptr(), V, ids.data_ptr(), ns, sp,
+                   loss.data_ptr(), denom.data_ptr(), err, E._stream())
+        dl = torch.ones(N, device="cuda")
+        U.LIB.call("u2gnn_sampled_softmax_bwd", dl.data_ptr(), x.data_ptr(), y.data_ptr(), N, D, W.data_ptr(), V, ids.data_ptr(), ns, sp,
+                   denom.data_ptr(), dx.data_ptr(), dW.data_ptr(), dp, err, E._stream())
+        out[mode] = (loss, dx, dW, dsamp)
+    E.check_device_errors()
+    assert torch.equal(out["plain"][0], out["rows"][0]) and torch.equal(out["plain"][1], out["rows"][1])
+    full = out["rows"][2].clone()
+    full.index_add_(0, ids, out["rows"][3])
+    assert (full - out["plain"][2]).abs().max().item() <= 1e-5 * out["plain"][2].abs().max().item()
