@@ -1,16 +1,22 @@
 #!/usr/bin/env python
-"""bench.py — nodes/sec of the U2GNN train step (forward + loss + backward + clip + Adam).
+"""bench.py - nodes/sec of the U2GNN train step (forward + loss + backward + clip + Adam).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W     # the reference's CPU path (torch.nn port)
+    python bench.py --gpus N --steps K --warmup W [--workload cfg5]     # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W               # the reference's CPU path (torch.nn port)
 
-Workload (config.workload): BASELINE.json configs[4] shape — supervised U2GNN on a synthetic graph
-batch, d 64, num_neighbors 16 (S 17), T 4, L 1, ff 2048, attn_axis="neighbors", `--nodes` nodes per
-rank per step (weak scaling: every rank owns its own graphs; the only collective is the gradient
-all-reduce).  Prints ONE JSON line (contract in the task statement); the oracle / torch port is used
-only for the cpu_baseline leg and the reference arm.
+Workloads (config.workload) are the five BASELINE.json configs as synthetic batches of the named shapes:
+  cfg1  supervised, MUTAG shape      d 7,  k 8,  T 3, ff 1024, 4 graphs (~72 nodes) per step, attention as the reference runs it
+  cfg2  unsupervised, PTC-degree shape d 4, k 4,  T 2, ff 1024, ns 512, V 8 792, 4 graphs (~100 nodes) per step
+  cfg3  supervised, IMDBBINARY shape d 65, k 16, T 4, ff 1024, 4 096 graphs (~82 K nodes) per rank per step
+  cfg4  unsupervised, REDDITMULTI5K shape: 4 999 graphs / ~2.54 M nodes, d 4, k 4, T 2, ff 1024, ns 512, class table row-sharded
+        over the ranks, 512 graphs (~260 K nodes) per rank per step
+  cfg5  supervised, 64 M-node-graph shape: d 64, k 16, T 4, ff 2048, 262 144 nodes per rank per step   (DEFAULT, the metric's config)
+Supervised multi-GPU runs shard ONE global batch with parallel.shard_graph_batch (weak scaling: the global batch grows with N;
+the only collective is the gradient all-reduce).  Prints ONE JSON line (contract in the task statement); the oracle / torch
+port is used only for the cpu_baseline leg and the reference arm, which never imports the CUDA package.
 """
 import argparse
+import importlib.util
 import json
 import os
 import subprocess
@@ -19,18 +25,47 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "graph-transformer_b200")):
-    if p not in sys.path:
-        sys.path.insert(0, p)
+PKG = os.path.join(ROOT, "graph-transformer_b200")
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
 METRIC = "nodes/sec U2GNN train step"
-CFG = dict(d=64, k=16, T=4, L=1, ff=2048, C=2)
+WORKLOADS = {
+    "cfg1": dict(kind="sup", d=7, k=8, T=3, L=1, ff=1024, C=2, axis="nodes", nodes=72, avg_graph=18, precision="fp32",
+                 desc="cfg1-shape (MUTAG) synthetic batch: supervised U2GNN, d 7, num_neighbors 8, T 3, L 1, ff 1024, 4 graphs per step, "
+                      "attn_axis=nodes (reference as written) (BASELINE.json configs[0])"),
+    "cfg2": dict(kind="unsup", d=4, k=4, T=2, L=1, ff=1024, ns=512, V=8792, axis="nodes", nodes=100, avg_graph=25, precision="fp32",
+                 desc="cfg2-shape (PTC degree-as-tag) synthetic batch: unsupervised U2GNN, d 4, num_neighbors 4, T 2, L 1, ff 1024, "
+                      "sampled softmax ns 512 over V 8792, 4 graphs per step, attn_axis=nodes (BASELINE.json configs[1])"),
+    "cfg3": dict(kind="sup", d=65, k=16, T=4, L=1, ff=1024, C=2, axis="neighbors", nodes=4096 * 20, avg_graph=20, precision="bf16",
+                 desc="cfg3-shape (IMDBBINARY) synthetic batch: supervised U2GNN, d 65, num_neighbors 16, T 4, L 1, ff 1024, 4096 graphs "
+                      "per rank per step, attn_axis=neighbors (BASELINE.json configs[2])"),
+    "cfg4": dict(kind="unsup", d=4, k=4, T=2, L=1, ff=1024, ns=512, V=2540000, graphs=4999, graphs_per_step=512, axis="neighbors",
+                 precision="bf16",
+                 desc="cfg4-shape (REDDITMULTI5K) synthetic dataset: 4999 graphs / ~2.54 M nodes, unsupervised U2GNN, d 4, num_neighbors 4, "
+                      "T 2, L 1, ff 1024, sampled softmax ns 512, class table row-sharded over the ranks, 512 graphs per rank per step, "
+                      "attn_axis=neighbors (BASELINE.json configs[3])"),
+    "cfg5": dict(kind="sup", d=64, k=16, T=4, L=1, ff=2048, C=2, axis="neighbors", nodes=262144, avg_graph=61, precision="bf16",
+                 desc="cfg5-shape synthetic graph batch: supervised U2GNN, d 64, num_neighbors 16, T 4, L 1, ff 2048, "
+                      "attn_axis=neighbors (BASELINE.json configs[4])"),
+}
+# entry points timed per launch for the HBM-side roofline list (north_star: gather / attention / pooling kernels)
+HBM_KERNELS = ("u2gnn_gather_rows", "u2gnn_inproj_seqattn_tc_fwd", "u2gnn_seqattn_tc_bwd_ex", "u2gnn_segment_sum",
+               "u2gnn_add_dropout_ln_bwd_ex", "u2gnn_gemm_tc_rows_ln", "u2gnn_gemm_tc_dgrad_wgrad")
+
+
+def _load_synthetic():
+    """u2gnn_b200/synthetic.py loaded by PATH: the reference arm must not import the package (its __init__ dlopens the CUDA library)."""
+    spec = importlib.util.spec_from_file_location("u2gnn_synthetic", os.path.join(PKG, "u2gnn_b200", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def algorithmic_per_node(d, S, T, ff, L=1):
-    """SURVEY.md §8(d): fwd flops F = T(8Sd^2 + 4S^2 d + 4Sd ff); fwd+bwd = 3F.  HBM bytes fwd
+    """SURVEY.md 8(d): fwd flops F = T(8Sd^2 + 4S^2 d + 4Sd ff); fwd+bwd = 3F.  HBM bytes fwd
     B = 8S + 4Sd + 4d + 4d; fwd+bwd = 2B."""
     F = T * (8 * S * d * d + 4 * S * S * d + 4 * S * d * ff) * L
     B = (8 * S + 4 * S * d + 4 * d + 4 * d) * L
@@ -83,58 +118,104 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # reference CPU path (oracle/torch_port.py: the reference's own torch.nn modules)
 # ----------------------------------------------------------------------------------------------
-def cpu_train_rate(nodes, steps, warmup, threads):
-    """nodes/s of the reference CPU train step (train mode, real p=0.5 dropouts, clip 0.5, Adam) on a
-    bounded sample of the workload: `nodes` nodes of the same synthetic graph batch."""
+def _host_graphs(b, k):
+    """Graph objects (neighbour lists) of a synthetic batch for the host batch builder: every node's candidates are the other
+    nodes of its graph, which is what make_batch samples from."""
+    import numpy as np
+    rp = b["rowptr"].cpu().numpy()
+    X = b["X"].cpu().numpy()
+    labels = b["labels"].cpu().numpy() if "labels" in b else np.zeros(len(rp) - 1, dtype=np.int64)
+    graphs = []
+    for g in range(len(rp) - 1):
+        n = int(rp[g + 1] - rp[g])
+        nb = [np.delete(np.arange(n, dtype=np.int64), i) for i in range(n)]
+        graphs.append(dict(n=n, neighbors=nb, node_features=X[rp[g]:rp[g + 1]], label=int(labels[g])))
+    return graphs
+
+
+def _host_build_batch(graphs, k):
+    """The reference's host batch builder restated (train_pytorch_U2GNN_Sup.py:91-119: per node np.random.choice with
+    replacement, isolated nodes repeat themselves) - timed for the `with_host_batch_builder` CPU number."""
+    import numpy as np
+    rows, start = [], 0
+    for g in graphs:
+        for i, nb in enumerate(g["neighbors"]):
+            node = start + i
+            rows.append([node] + list(start + np.random.choice(nb, k, replace=True)) if len(nb) else [node] * (k + 1))
+        start += g["n"]
+    return np.array(rows, dtype=np.int64), np.concatenate([g["node_features"] for g in graphs], 0)
+
+
+def cpu_train_rate(w, nodes, steps, warmup, threads, with_builder=False):
+    """nodes/s of the reference CPU train step (train mode, real p=0.5 dropouts, clip 0.5, Adam) on a bounded sample of the
+    workload: `nodes` nodes of the same synthetic batch generator."""
     from oracle import torch_port as TP
-    from u2gnn_b200.synthetic import make_batch
+    syn = _load_synthetic()
     torch.set_num_threads(threads)
     torch.manual_seed(123)
-    b = make_batch(nodes, CFG["k"], CFG["d"], CFG["C"], seed=2024, device="cpu")
-    model = TP.SupPort(CFG["d"], CFG["ff"], CFG["C"], CFG["T"], 0.5, CFG["L"], attn_axis="neighbors")
+    vocab = w.get("V")
+    b = syn.make_batch(nodes, w["k"], w["d"], w.get("C", 2), avg_graph=w.get("avg_graph", 61), seed=2024, device="cpu",
+                       vocab=max(vocab, nodes) if vocab else None)
+    N, G = b["X"].shape[0], b["G"]
+    if w["kind"] == "sup":
+        model = TP.SupPort(w["d"], w["ff"], w["C"], w["T"], 0.5, w["L"], attn_axis=w["axis"])
+        idx = torch.stack([torch.repeat_interleave(torch.arange(G), b["rowptr"][1:] - b["rowptr"][:-1]), torch.arange(N)])
+        gp = torch.sparse_coo_tensor(idx, torch.ones(N), (G, N))
+        soft = TP.smooth_labels(b["labels"], w["C"])
+        loss_of = lambda ix, X: TP.soft_ce(model(ix, gp, X), soft)
+    else:
+        from oracle.sampler import OracleSampler
+        model = TP.UnSupPort(max(vocab, nodes), w["d"], w["ff"], w["T"], w["L"], 0.5, attn_axis=w["axis"])
+        sampler = OracleSampler(max(vocab, nodes))
+        loss_of = lambda ix, X: torch.sum(model(X, ix, b["input_y"], sampler.sample_with_tries(w["ns"])[0]))
     model.train()
     opt = torch.optim.Adam(model.parameters(), lr=5e-4)
-    N, G = b["X"].shape[0], b["G"]
-    idx = torch.stack([torch.repeat_interleave(torch.arange(G), b["rowptr"][1:] - b["rowptr"][:-1]), torch.arange(N)])
-    gp = torch.sparse_coo_tensor(idx, torch.ones(N), (G, N))
-    soft = TP.smooth_labels(b["labels"], CFG["C"])
+    graphs = _host_graphs(b, w["k"]) if with_builder else None
 
-    def loss_fn():
-        return TP.soft_ce(model(b["input_x"], gp, b["X"]), soft)
+    def one():
+        if with_builder:
+            ix, X = _host_build_batch(graphs, w["k"])
+            ix, X = torch.from_numpy(ix), torch.from_numpy(X)
+        else:
+            ix, X = b["input_x"], b["X"]
+        TP.train_step(model, opt, lambda: loss_of(ix, X))
 
     for _ in range(warmup):
-        TP.train_step(model, opt, loss_fn)
+        one()
     t0 = time.perf_counter()
     for _ in range(steps):
-        TP.train_step(model, opt, loss_fn)
+        one()
     dt = time.perf_counter() - t0
     return N * steps / dt, dt / steps
 
 
-def run_reference(args):
+def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    # bounded sample: calibrate on 128 nodes, then size the step so the whole run takes ~2 minutes
-    rate, _ = cpu_train_rate(128, 1, 1, threads)
+    # bounded sample: calibrate on a small batch, then size the step so the whole run takes ~2 minutes
+    probe = min(128, w.get("nodes", 128))
+    rate, _ = cpu_train_rate(w, probe, 1, 1, threads)
     budget = 120.0
-    nodes = int(max(64, min(8192, rate * budget / max(1, args.steps + args.warmup))))
-    rate, sec = cpu_train_rate(nodes, args.steps, args.warmup, threads)
+    cap = w.get("nodes", 8192) if w["axis"] == "nodes" else 8192
+    nodes = int(max(min(64, cap), min(cap, rate * budget / max(1, args.steps + args.warmup))))
+    rate, sec = cpu_train_rate(w, nodes, args.steps, args.warmup, threads)
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "nodes/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(nodes),
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, w, nodes),
             "cpu_baseline": {"value": rate, "unit": "nodes/s", "cores": threads, "kind": "port",
-                             "sample": "%d nodes/step of the cfg5-shape batch, torch.nn port of the reference model "
-                                       "(oracle/torch_port.py), train mode with p=0.5 dropouts" % nodes},
+                             "sample": "%d nodes/step of the %s-shape batch (node subsample of the GPU arm's step, SURVEY.md 8(d)), torch.nn "
+                                       "port of the reference model (oracle/torch_port.py), fp32, train mode with p=0.5 dropouts"
+                                       % (nodes, args.workload)},
             "e2e": {"value": rate, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def workload_config(nodes, extra=None):
-    c = {"workload": "cfg5-shape synthetic graph batch: supervised U2GNN, d 64, num_neighbors 16, T 4, L 1, ff 2048, "
-                     "attn_axis=neighbors (BASELINE.json configs[4])",
-         "nodes_per_rank_per_step": nodes, "l2_policy": "inputs larger than L2 (X + input_x + activations >> 126 MB)"}
+def workload_config(args, w, nodes, extra=None):
+    c = {"workload": w["desc"], "workload_id": args.workload, "nodes_per_rank_per_step": nodes,
+         "l2_policy": ("inputs larger than L2 (X + input_x + activations >> 126 MB)" if nodes >= 65536 else
+                       "L2 flushed between timed steps (256 MB write): the batch itself fits in L2")}
     if extra:
         c.update(extra)
     return c
@@ -143,7 +224,36 @@ def workload_config(nodes, extra=None):
 # ----------------------------------------------------------------------------------------------
 # this repo's arm
 # ----------------------------------------------------------------------------------------------
-def run_ours(args):
+def _tree_dataset(w, seed, device):
+    """cfg4: REDDITMULTI5K-shaped dataset resident on the device: `graphs` graphs, log-normal sizes summing to V, tree-like
+    (every node but the first of its graph links to a random earlier node of the graph: ~1 undirected edge per node), features
+    one-hot(degree mod 4) * 0.01-scaled like the reference's REDDIT rule.  -> (rowptr, col, gstart, X)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    G, V = w["graphs"], w["V"]
+    raw = torch.exp(torch.randn(G, generator=g, device=device) * 0.75)
+    sizes = torch.clamp((raw / raw.sum() * V).long(), min=2)
+    sizes[-1] += V - int(sizes.sum().item())
+    gstart = torch.zeros(G + 1, dtype=torch.int64, device=device)
+    gstart[1:] = torch.cumsum(sizes, 0)
+    gid = torch.repeat_interleave(torch.arange(G, device=device), sizes)
+    local = torch.arange(V, device=device) - gstart[gid]
+    parent = gstart[gid] + (torch.rand(V, generator=g, device=device) * local.clamp(min=1)).long().clamp(max=(local - 1).clamp(min=0))
+    child = torch.arange(V, device=device)
+    keep = local > 0
+    src = torch.cat([child[keep], parent[keep]])
+    dst = torch.cat([parent[keep], child[keep]])
+    order = torch.argsort(src * V + dst)
+    src, dst = src[order], dst[order]
+    deg = torch.bincount(src, minlength=V)
+    rowptr = torch.zeros(V + 1, dtype=torch.int64, device=device)
+    rowptr[1:] = torch.cumsum(deg, 0)
+    X = torch.zeros((V, w["d"]), dtype=torch.float32, device=device)
+    X[torch.arange(V, device=device), deg % w["d"]] = 1.0
+    X = X * 0.99 + 0.01
+    return rowptr, dst.contiguous(), gstart, X
+
+
+def run_ours(args, w):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -151,97 +261,173 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sys.path.insert(0, PKG)
     import u2gnn_b200 as U
     from u2gnn_b200 import engine as E
+    from u2gnn_b200 import parallel as P
     from u2gnn_b200.synthetic import make_batch
-    from u2gnn_b200.trainer import SupTrainer
+    from u2gnn_b200.trainer import SupTrainer, UnSupTrainer
     U.require_device()
-    S = CFG["k"] + 1
-    nodes = args.nodes
+    S = w["k"] + 1
+    precision = args.precision or w["precision"]
+    note = None
+    if precision == "bf16" and not E.ffn_tc_supported(w["d"], w["ff"]):
+        precision, note = "fp32", "the tcgen05 FFN path supports d <= 64: this workload ran on the fp32 path"
     torch.manual_seed(123)
-    model = U.TransformerU2GNN(CFG["d"], CFG["ff"], CFG["C"], CFG["T"], 0.5, CFG["L"], attn_axis="neighbors").cuda()
-    trainer = SupTrainer(model, lr=5e-4, precision=args.precision)
-    b = make_batch(nodes, CFG["k"], CFG["d"], CFG["C"], seed=2024 + rank, device="cuda")
-    G_total = b["G"] * world
-    dominant = trainer.dominant_kernel()
+    dev = torch.device("cuda", local)
+    batches = []                                   # resident batches, cycled over the timed steps
+    if w["kind"] == "sup":
+        nodes = args.nodes or w["nodes"]
+        model = U.TransformerU2GNN(w["d"], w["ff"], w["C"], w["T"], 0.5, w["L"], attn_axis=w["axis"]).cuda()
+        trainer = SupTrainer(model, lr=5e-4, precision=precision)
+        # ONE global batch (the same on every rank: seeded device generator), sharded by balanced graph ranges
+        gb = make_batch(nodes * world, w["k"], w["d"], w["C"], avg_graph=w["avg_graph"], seed=2024, device="cuda")
+        sh = P.shard_graph_batch(gb["input_x"], gb["rowptr"], gb["X"], gb["labels"], rank, world)
+        G_total = gb["G"]
+        del gb
+        torch.cuda.empty_cache()
+        batches.append(dict(input_x=sh["input_x"], rowptr=sh["rowptr"], X=sh["X"], labels=sh["labels"]))
+        my_nodes = sh["X"].shape[0]
 
-    def step():
-        return trainer.step(b["input_x"], b["rowptr"], b["X"], b["labels"], G_total=G_total)
+        def step_on(b):
+            return trainer.step(b["input_x"], b["rowptr"], b["X"], b["labels"], G_total=G_total)
+    else:
+        if "graphs" in w:                          # cfg4: dataset resident in HBM, device batch builder, row-sharded table
+            rowptr, col, gstart, X = _tree_dataset(w, 2024, dev)
+            V = w["V"]
+            ranges = P.balanced_graph_ranges(gstart, world)
+            g0, g1 = ranges[rank]
+            bounds = [int(gstart[r[0]]) for r in ranges] + [V]
+            shard = P.RowShard(V, world, rank, bounds) if world > 1 else None
+            from u2gnn_b200.data import DeviceBatchBuilder
+            ds = DeviceBatchBuilder.from_device_tensors(rowptr, col, gstart, X, w["k"], seed=7)
+            gen = torch.Generator().manual_seed(100 + rank)
+            gps = min(args.graphs_per_step or w["graphs_per_step"], g1 - g0)
+            for i in range(4):
+                sel = (g0 + torch.randperm(g1 - g0, generator=gen)[:gps]).sort().values.numpy()
+                ix, rp, Xc, _, node_global = ds.build(sel, stream_id=i)
+                batches.append(dict(input_x=ix, X=Xc, input_y=node_global))
+            local_rows = bounds[rank + 1] - bounds[rank] if shard is not None else V
+            model = U.TransformerU2GNNUnSup(local_rows, w["d"], w["ff"], w["ns"], w["T"], w["L"], 0.5, dev, attn_axis=w["axis"],
+                                            precision=precision).cuda()
+            trainer = UnSupTrainer(model, lr=5e-3, row_shard=shard, global_vocab=V)
+            my_nodes = sum(b["X"].shape[0] for b in batches) / len(batches)
+        else:                                      # cfg2: one tiny batch, whole table on every rank
+            nodes = args.nodes or w["nodes"]
+            b = make_batch(nodes, w["k"], w["d"], 2, avg_graph=w["avg_graph"], seed=2024 + rank, device="cuda", vocab=w["V"])
+            batches.append(dict(input_x=b["input_x"], X=b["X"], input_y=b["input_y"]))
+            model = U.TransformerU2GNNUnSup(w["V"], w["d"], w["ff"], w["ns"], w["T"], w["L"], 0.5, dev, attn_axis=w["axis"],
+                                            precision=precision).cuda()
+            trainer = UnSupTrainer(model, lr=5e-3)
+            my_nodes = nodes
+
+        def step_on(b):
+            return trainer.step(b["X"], b["input_x"], b["input_y"])
+    dominant = trainer.dominant_kernel()
+    small = my_nodes < 65536
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if small else None
 
     def sync():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
+    for i in range(args.warmup):
+        step_on(batches[i % len(batches)])
     sync()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     U.LIB.launches = 0
-    U.LIB.timed = {dominant: []}
-    E.FLOPS.clear()
+    names = (dominant,) + tuple(n for n in HBM_KERNELS if n != dominant)
+    U.LIB.timed = {n: [] for n in names}
+    E.FLOPS.clear(); E.BYTES.clear()
+    nodes_done = 0
+    ms = 0.0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
-    e0.record()
-    for _ in range(args.steps):
-        loss = step()
-    e1.record()
-    sync()
-    ms = e0.elapsed_time(e1)
+    if not small:
+        e0.record()
+        for i in range(args.steps):
+            b = batches[i % len(batches)]
+            loss = step_on(b)
+            nodes_done += b["X"].shape[0]
+        e1.record()
+        sync()
+        ms = e0.elapsed_time(e1)
+    else:
+        # tiny batches fit in L2: flush it between the timed steps and time each step on its own
+        for i in range(args.steps):
+            b = batches[i % len(batches)]
+            flush.fill_(i & 0xFF)
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            loss = step_on(b)
+            b_.record()
+            torch.cuda.synchronize()
+            ms += a_.elapsed_time(b_)
+            nodes_done += b["X"].shape[0]
     launches = U.LIB.launches
-    timed = U.LIB.timed[dominant]
+    timed = U.LIB.timed
     U.LIB.timed = None
-    kern_ms = sum(a.elapsed_time(b_) for a, b_ in timed)
+    kern = {n: (sum(a.elapsed_time(b_) for a, b_ in v), len(v)) for n, v in timed.items()}
+    flops, nbytes = dict(E.FLOPS), dict(E.BYTES)
     clk = clocks.stop() if rank == 0 else None
-    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    t = torch.tensor([ms, float(nodes_done)], device="cuda", dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = nodes * world * args.steps / (ms / 1e3)
+        tn = t[1:].clone()
+        dist.all_reduce(t[:1], op=dist.ReduceOp.MAX)
+        dist.all_reduce(tn, op=dist.ReduceOp.SUM)
+        t[1] = tn[0]
+    ms, total_nodes = float(t[0].item()), float(t[1].item())
+    value = total_nodes / (ms / 1e3)
 
     # ---- end-to-end through the public API with HOST buffers (H2D of the batch + D2H of the loss per step)
-    host = {k: v.cpu().pin_memory() for k, v in b.items() if torch.is_tensor(v)}
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    hosts = [{k: v.cpu().pin_memory() for k, v in b.items() if torch.is_tensor(v)} for b in batches]
+    h2d = sum(v.numel() * v.element_size() for v in hosts[0].values())
 
     # The input feed is pipelined the way a training loop's loader is: the host->device copy of step i+1's batch is issued on
     # a copy stream while step i computes; every timed step still copies its own inputs from pinned host memory (K copies
     # in the region) and ends with the device->host read of its loss.
     copy_stream = torch.cuda.Stream()
 
-    def issue_copy():
+    def issue_copy(i):
         with torch.cuda.stream(copy_stream):
-            dev = {k: v.cuda(non_blocking=True) for k, v in host.items()}
+            devb = {k: v.cuda(non_blocking=True) for k, v in hosts[i % len(hosts)].items()}
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return dev, ev
+        return devb, ev
 
     def run_host_steps(n):
-        nxt = issue_copy()
-        last = 0.0
+        nxt = issue_copy(0)
+        last, done = 0.0, 0
         for i in range(n):
-            dev, ev = nxt
+            devb, ev = nxt
             cur = torch.cuda.current_stream()
             cur.wait_event(ev)
-            for v in dev.values():
+            for v in devb.values():
                 v.record_stream(cur)
-            l = trainer.step(dev["input_x"], dev["rowptr"], dev["X"], dev["labels"], G_total=G_total)
+            l = step_on(devb)
+            done += devb["X"].shape[0]
             if i + 1 < n:
-                nxt = issue_copy()
-            last = float(l.item())      # device->host read of the step's loss
-        return last
+                nxt = issue_copy(i + 1)
+            last = float(l.sum().item())      # device->host read of the step's loss
+        return last, done
 
     run_host_steps(min(2, args.warmup))
     sync()
     e0.record()
-    run_host_steps(args.steps)
+    _, done = run_host_steps(args.steps)
     e1.record()
     sync()
-    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    t = torch.tensor([e0.elapsed_time(e1), float(done)], device="cuda", dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e = nodes * world * args.steps / (float(t.item()) / 1e3)
+        tn = t[1:].clone()
+        dist.all_reduce(t[:1], op=dist.ReduceOp.MAX)
+        dist.all_reduce(tn, op=dist.ReduceOp.SUM)
+        t[1] = tn[0]
+    e2e = float(t[1].item()) / (float(t[0].item()) / 1e3)
+    E.check_device_errors()
 
     if rank == 0:
         peaks = {}
@@ -249,29 +435,45 @@ def run_ours(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        flops_node, bytes_node = algorithmic_per_node(CFG["d"], S, CFG["T"], CFG["ff"], CFG["L"])
+        flops_node, bytes_node = algorithmic_per_node(w["d"], S, w["T"], w["ff"], w["L"])
         ncu = None
         try:
-            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_ffn_summary.json")))
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_ffn_summary.json")))
         except Exception:
             pass
-        roof = trainer.roofline(dominant, kern_ms, len(timed), peaks, E.FLOPS, ncu)
+        roof = trainer.roofline(dominant, kern[dominant][0], kern[dominant][1], peaks, flops, ncu)
+        hbm_peak = peaks.get("hbm_gbs", 6550.0)
+        hbm = []
+        for n in HBM_KERNELS:
+            tms, cnt = kern.get(n, (0.0, 0))
+            if cnt and nbytes.get(n):
+                gbs = nbytes[n] / (tms * 1e-3) / 1e9
+                hbm.append({"kernel": n, "achieved_gbs": gbs, "frac": gbs / hbm_peak, "launches": cnt, "ms_per_step": tms / args.steps,
+                            "algorithmic_bytes_per_launch": nbytes[n] / cnt})
         line = {"metric": METRIC, "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-                "config": workload_config(nodes, {"precision": args.precision, "parallelism": "dp%d" % world,
-                                                   "algorithmic_mflop_per_node": flops_node / 1e6,
-                                                   "algorithmic_bytes_per_node": bytes_node,
-                                                   "loss": float(loss.item())}),
-                "roofline": roof, "clocks": clk,
+                "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+                "config": workload_config(args, w, int(round(total_nodes / args.steps / world)),
+                                          {"precision": precision, "parallelism": "dp%d" % world,
+                                           "algorithmic_mflop_per_node": flops_node / 1e6, "algorithmic_bytes_per_node": bytes_node,
+                                           "loss": float(loss.sum().item())}),
+                "roofline": roof, "roofline_hbm": hbm, "hbm_peak_gbs": hbm_peak, "clocks": clk,
                 "e2e": {"value": e2e, "unit": "nodes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches}
+        if note:
+            line["config"]["note"] = note
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            rate, sec = cpu_train_rate(args.cpu_nodes, 2, 1, threads)
+            cn = min(args.cpu_nodes, w.get("nodes", args.cpu_nodes)) if w["axis"] == "nodes" else args.cpu_nodes
+            rate, sec = cpu_train_rate(w, cn, 2, 1, threads)
+            rate_b, _ = cpu_train_rate(w, cn, 2, 1, threads, with_builder=True)
+            rate_1, _ = cpu_train_rate(w, cn, 1, 1, 1)
             line["cpu_baseline"] = {"value": rate, "unit": "nodes/s", "cores": threads, "kind": "port",
-                                    "sample": "%d nodes/step x 2 steps (+1 warm-up) of the same cfg5-shape batch through the "
-                                              "torch.nn port of the reference model, train mode" % args.cpu_nodes}
+                                    "with_host_batch_builder": rate_b, "one_thread": rate_1,
+                                    "sample": "%d nodes/step x 2 steps (+1 warm-up) of the same %s-shape batch through the torch.nn "
+                                              "port of the reference model, fp32, train mode; with_host_batch_builder adds the "
+                                              "reference's per-node np.random.choice loop per step; one_thread = 1 step on 1 thread"
+                                              % (cn, args.workload)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -280,20 +482,24 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("U2GNN_PRECISION", "bf16"), choices=["fp32", "bf16"])
-    ap.add_argument("--nodes", type=int, default=int(os.environ.get("U2GNN_BENCH_NODES", 262144)),
-                    help="nodes per rank per step")
+    ap.add_argument("--workload", default=os.environ.get("U2GNN_WORKLOAD", "cfg5"), choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default=os.environ.get("U2GNN_PRECISION"), choices=["fp32", "bf16"])
+    ap.add_argument("--nodes", type=int, default=int(os.environ.get("U2GNN_BENCH_NODES", 0)),
+                    help="nodes per rank per step (default: the workload's)")
+    ap.add_argument("--graphs-per-step", type=int, default=0, help="cfg4: graphs per rank per step")
     ap.add_argument("--cpu-nodes", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "ours":
+        args.warmup = max(args.warmup, 3)
+    w = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, w)
     else:
-        run_ours(args)
+        run_ours(args, w)
 
 
 if __name__ == "__main__":

@@ -251,6 +251,22 @@ class DeviceBatchBuilder:
         self.X = torch.from_numpy(X).to(dev)
         self.device = dev
 
+    @classmethod
+    def from_device_tensors(cls, rowptr, col, gstart, X, num_neighbors, seed=123, labels=None):
+        """Builder over a dataset that is ALREADY resident on the device (synthetic datasets generated in HBM, bench.py cfg4):
+        rowptr[V+1], col[E] (dataset-wide CSR), gstart[G+1] (first node of every graph), X[V, d]."""
+        import torch
+        from ._lib import LIB, require_device
+        require_device()
+        self = cls.__new__(cls)
+        self._torch, self._lib = torch, LIB
+        self.k, self.seed, self.step = int(num_neighbors), int(seed), 0
+        self.gstart_host = gstart.detach().cpu().numpy().astype(np.int64)
+        G = len(self.gstart_host) - 1
+        self.labels_host = np.zeros(G, dtype=np.int64) if labels is None else np.asarray(labels, dtype=np.int64)
+        self.rowptr, self.col, self.X, self.device = rowptr.contiguous(), col.contiguous(), X.contiguous(), X.device
+        return self
+
     def build(self, selected, stream_id=None):
         """selected: iterable of graph indices -> (input_x [N, k+1] int64, pool rowptr [G+1] int64, X_concat [N, d] f32,
         labels [G] int64, node_global [N] int64), all on the device."""

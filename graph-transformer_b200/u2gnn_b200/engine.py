@@ -36,6 +36,12 @@ FUSE_INPROJ_ATTN = os.environ.get("U2GNN_FUSE_INPROJ_ATTN", "1") != "0"   # bf16
 # it stages the operand is less efficient than the 24-warp LayerNorm pass plus the cp.async-fed GEMM.  Off by default.
 FUSE_LN1_PROJ_BWD = os.environ.get("U2GNN_FUSE_LN1_PROJ_BWD", "0") != "0"
 FLOPS = {}    # entry point -> algorithmic flops issued while LIB.timed is active (bench.py roofline)
+BYTES = {}    # entry point -> algorithmic HBM bytes (the tensors the call must read + write once) while LIB.timed is active
+
+
+def _acct_bytes(name, nbytes):
+    if LIB.timed is not None:
+        BYTES[name] = BYTES.get(name, 0) + int(nbytes)
 
 
 def stream_id(layer, timestep, site, num_timesteps):
@@ -121,6 +127,8 @@ def gather_rows(table, idx, idx_stride=1, n_idx=None):
     _check(table, torch.float32, "table"); _check(idx, torch.int64, "idx")
     n = idx.numel() // idx_stride if n_idx is None else n_idx
     out = torch.empty((n, table.shape[1]), dtype=torch.float32, device=table.device)
+    # HBM-minimal traffic: every index and output row once, the table once (a row gathered k+1 times is re-read from L2)
+    _acct_bytes("u2gnn_gather_rows", n * (8 + 4 * table.shape[1]) + min(n, table.shape[0]) * 4 * table.shape[1])
     LIB.call("u2gnn_gather_rows", _ptr(table), table.shape[0], table.shape[1], _ptr(idx), n, idx_stride, _ptr(out),
              _ptr(err_word(table.device)), _stream())
     return out
@@ -176,6 +184,7 @@ def rowptr_from_graph_pool(graph_pool):
 def segment_sum(x, rowptr):
     G = rowptr.numel() - 1
     out = torch.empty((G, x.shape[1]), dtype=torch.float32, device=x.device)
+    _acct_bytes("u2gnn_segment_sum", 4 * x.shape[1] * (x.shape[0] + G) + 8 * (G + 1))
     LIB.call("u2gnn_segment_sum", _ptr(x), x.shape[0], x.shape[1], _ptr(rowptr), G, _ptr(out), _stream())
     return out
 
@@ -253,6 +262,8 @@ def proj_bwd_tc(dout, M, n_out, inp, W, dW, db, out=None, out_bf16=False, beta=0
     and accumulates dW[n_out, 64] += dout^T inp, db += colsum(dout)."""
     if out is None:
         out = torch.empty((M, 64), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dout.device)
+    _acct_bytes("u2gnn_gemm_tc_dgrad_wgrad", M * (2 * n_out + (2 if inp.dtype == torch.bfloat16 else 4) * 64 +
+                                                  (2 if (out_bf16 or (out is not None and out.dtype == torch.bfloat16)) else 4) * 64 * (2 if beta else 1)))
     if LIB.timed is not None:
         FLOPS["u2gnn_gemm_tc_dgrad_wgrad"] = FLOPS.get("u2gnn_gemm_tc_dgrad_wgrad", 0) + 4 * M * n_out * 64
     LIB.call("u2gnn_gemm_tc_dgrad_wgrad", _ptr(dout), M, n_out, n_out, _ptr(inp), int(inp.dtype == torch.bfloat16), 64, _ptr(W),
@@ -276,6 +287,7 @@ def add_dropout_ln_bwd(dy, z, stats, M, d, gamma, drop, dgamma, dbeta, want_da=T
     dz = torch.empty((M, d), dtype=torch.float32, device=dy.device)
     has_da = want_da and drop[2] > 0
     da = torch.empty((M, d), dtype=torch.bfloat16 if da_bf16 else torch.float32, device=dy.device) if has_da else None
+    _acct_bytes("u2gnn_add_dropout_ln_bwd_ex", M * (4 * d * 3 + 8 + ((2 if da_bf16 else 4) * d if has_da else 0)))   # dy, z, stats -> dz (+ da)
     if (da_bf16 and has_da) or dasum is not None:
         LIB.call("u2gnn_add_dropout_ln_bwd_ex", _ptr(dy), _ptr(z), _ptr(stats), M, d, _ptr(gamma), drop[0], drop[1], drop[2],
                  _ptr(dz), _ptr(da), int(da_bf16 and has_da), _ptr(dgamma), _ptr(dbeta), _ptr(dasum), _stream())
@@ -291,6 +303,7 @@ def out_proj_ln_tc(ctx, Mq, d, p, res, ldres, drop):
     z = torch.empty((Mq, d), dtype=torch.float32, device=dev)
     y = torch.empty((Mq, d), dtype=torch.float32, device=dev)
     stats = torch.empty((Mq, 2), dtype=torch.float32, device=dev)
+    _acct_bytes("u2gnn_gemm_tc_rows_ln", Mq * ((2 if ctx.dtype == torch.bfloat16 else 4) * d + 4 * d * 3 + 8))       # ctx, residual -> z, y, stats
     if LIB.timed is not None:
         FLOPS["u2gnn_gemm_tc_rows_ln"] = FLOPS.get("u2gnn_gemm_tc_rows_ln", 0) + 2 * Mq * d * d
     LIB.call("u2gnn_gemm_tc_rows_ln", _ptr(ctx), int(ctx.dtype == torch.bfloat16), Mq, d, d, _ptr(p["self_attn.out_proj.weight"]), 0,
@@ -354,6 +367,7 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
         sgemm(0, 0, S, d, S, pd, S, qkv, 3 * d, ctx, d, b_off=2 * d)
         sv.probs, sv.pd = scores, pd
     elif fused_in:
+        _acct_bytes("u2gnn_inproj_seqattn_tc_fwd", M * (4 * d + 2 * 3 * d + 2 * d))     # x (fp32) -> qkv, ctx (bf16)
         if LIB.timed is not None:
             FLOPS["u2gnn_inproj_seqattn_tc_fwd"] = FLOPS.get("u2gnn_inproj_seqattn_tc_fwd", 0) + 2 * M * 3 * d * d
         LIB.call("u2gnn_inproj_seqattn_tc_fwd", _ptr(x), B, S, d, _ptr(p["self_attn.in_proj_weight"]), _ptr(p["self_attn.in_proj_bias"]),
@@ -499,6 +513,7 @@ def _encoder_attn_bwd(dy1, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
         sgemm(0, 0, S, d, S, dpd, S, sv.qkv, 3 * d, dqkv, 3 * d, alpha=scale, b_off=d)     # dq = ds @ k * scale
         sgemm(1, 0, S, d, S, dpd, S, sv.qkv, 3 * d, dqkv, 3 * d, alpha=scale, c_off=d)     # dk = ds^T @ q * scale
     elif tc_attn:
+        _acct_bytes("u2gnn_seqattn_tc_bwd_ex", M * (2 * 3 * d * 2 + 2 * d))                # qkv, dctx -> dqkv (bf16)
         LIB.call("u2gnn_seqattn_tc_bwd_ex", _ptr(sv.qkv), _ptr(dctx), B, S, d, seed, drop_ids[0], thr, _ptr(dqkv), 1, _stream())
     elif tc_last:
         LIB.call("u2gnn_seqattn_last_bwd_ex", _ptr(sv.qkv), _ptr(dctx), 1, B, S, d, seed, drop_ids[0], thr, _ptr(dqkv), _stream())

@@ -87,6 +87,33 @@ def effective_smoothing(eps, classes, style="reference"):
     raise ValueError("smoothing_style must be 'reference' or 'tf'")
 
 
+def dominant_kernel(precision):
+    """Entry point whose launches bench.py times for the roofline object: the FFN backward (the path's largest dense
+    contraction, tcgen05) in bf16 mode, the CUDA-core SGEMM in fp32 mode."""
+    return "u2gnn_sgemm" if precision == "fp32" else "u2gnn_ffn_tc_bwd"
+
+
+def roofline(model, precision, name, kernel_ms, launches, peaks, flops, ncu_summary=None):
+    """bench.py roofline object for the dominant kernel: achieved = algorithmic flops / measured time."""
+    peak = peaks.get("bf16_tflops_sustained")
+    which = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    if peak is None:
+        peak, which = 1590.0, "fallback (B200_PROFILING.md)"
+    achieved = flops.get(name, 0) / max(kernel_ms, 1e-9) / 1e9
+    traffic = None
+    if name == "u2gnn_ffn_tc_bwd" and ncu_summary:
+        # DRAM bytes per row from the committed `ncu` capture (image + wgrad + dgrad device kernels of this one entry
+        # point), scaled to the average rows per timed launch; algorithmic flops per row = 8 d ff
+        per_row = sum(v["traffic_bytes_per_launch"] / v["rows"] for v in ncu_summary.values() if isinstance(v, dict) and "rows" in v)
+        rows = flops.get(name, 0) / (8.0 * model.feature_dim_size * model.ff_hidden_size) / max(launches, 1)
+        traffic = per_row * rows
+    return {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": achieved / peak, "traffic": traffic, "launches_timed": launches,
+            "avg_launch_ms": kernel_ms / max(launches, 1), "peak_source": which,
+            "note": ("fp32 CUDA-core parity path; the tcgen05 path is --precision bf16" if precision == "fp32"
+                     else "fused bf16 tcgen05 FFN backward (image pass + weight-gradient kernel + input-gradient kernel)")}
+
+
 class SupTrainer:
     """Supervised fused step.  batch = (input_x[N,S] int64, rowptr[G+1] int64, X[N,d] f32, labels[G] int64)."""
 
@@ -154,31 +181,10 @@ class SupTrainer:
         return self.loss, scores
 
     def dominant_kernel(self):
-        if self.precision == "fp32":
-            return "u2gnn_sgemm"
-        return "u2gnn_ffn_tc_bwd"
+        return dominant_kernel(self.precision)
 
     def roofline(self, name, kernel_ms, launches, peaks, flops, ncu_summary=None):
-        """bench.py roofline object for the dominant kernel: achieved = algorithmic flops / measured time."""
-        peak = peaks.get("bf16_tflops_sustained")
-        which = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
-        if peak is None:
-            peak, which = 1590.0, "fallback (B200_PROFILING.md)"
-        achieved = flops.get(name, 0) / max(kernel_ms, 1e-9) / 1e9
-        traffic = None
-        if name == "u2gnn_ffn_tc_bwd" and ncu_summary:
-            # DRAM bytes per row from the committed `ncu --set full` capture (dgrad + wgrad device kernels of this one
-            # entry point), scaled to the average rows per timed launch; algorithmic flops per row = 8 d ff
-            per_row = sum(ncu_summary[k]["traffic_bytes_per_launch"] / ncu_summary[k]["rows"]
-                          for k in ("ffn_tc_dgrad_kernel", "ffn_tc_wgrad_kernel") if k in ncu_summary)
-            m = self.model
-            rows = flops.get(name, 0) / (8.0 * m.feature_dim_size * m.ff_hidden_size) / max(launches, 1)
-            traffic = per_row * rows
-        return {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": traffic, "launches_timed": launches,
-                "avg_launch_ms": kernel_ms / max(launches, 1), "peak_source": which,
-                "note": ("fp32 CUDA-core parity path; the tcgen05 path is --precision bf16" if self.precision == "fp32"
-                         else "fused bf16 tcgen05 FFN")}
+        return roofline(self.model, self.precision, name, kernel_ms, launches, peaks, flops, ncu_summary)
 
     def step(self, input_x, rowptr, X, labels, G_total=None):
         loss, _ = self.forward_backward(input_x, rowptr, X, labels, True, G_total)
@@ -286,6 +292,12 @@ class UnSupTrainer:
             else:
                 self._sharded_clip_adam()
         return node_loss
+
+    def dominant_kernel(self):
+        return dominant_kernel(self.model.precision)
+
+    def roofline(self, name, kernel_ms, launches, peaks, flops, ncu_summary=None):
+        return roofline(self.model, self.model.precision, name, kernel_ms, launches, peaks, flops, ncu_summary)
 
     def _sharded_clip_adam(self):
         """Encoder gradients are all-reduced, table gradients stay local; the clip norm is global:

@@ -5,8 +5,8 @@ The reference's arithmetic for this path lives in PyTorch itself (third-party, n
 ``F.embedding``, ``torch.spmm`` (pytorch_U2GNN_Sup.py:18-28,30-46).  This port calls exactly
 those modules so that (a) the numpy oracle can be checked against autograd anywhere torch is
 installed, and (b) ``bench.py`` has the reference's CPU path to time on the GPU box, where
-/root/reference does not exist.  It is checked against the real reference classes by
-``tests/golden/make_golden.py`` (same seed -> identical parameters and scores).
+/root/reference does not exist.  It is checked against the reference-generated fixtures (same
+parameters -> same scores, loss and gradients) by ``tests/test_bench_contract.py``.
 
 Only tests/, bench.py's cpu_baseline / --impl reference legs and __graft_entry__.smoke() may
 import this file.
