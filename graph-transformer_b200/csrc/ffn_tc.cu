@@ -568,23 +568,16 @@ size_t packed_bytes(int ff) { return (size_t)(ff / CH) * CHUNK_BYTES + (size_t)(
 
 }  // namespace
 
-uint32_t* g_ffn_trace = nullptr;     // shared with the dgrad / wgrad launchers
-#define g_trace g_ffn_trace
-// debug: device buffer of 17 x 1024 uint32 clock stamps (slot 0 = MMA warp, 1..16 = epilogue warps) written by CTA 0 of
-// the next forward launches; nullptr switches tracing off (tools/trace_ffn.py)
+#ifdef U2GNN_PROBE_BUILD
+// probe library only (libu2gnn_b200_probe.so, include/u2gnn_b200_probe.h): device buffer of clock stamps written by CTA 0 of the
+// next FFN launches (slot 0 = MMA warp, 1..16 = epilogue warps; the backward kernels use slots 0.. and 32..); nullptr = off.
+// The product library has no such state: its kernels are the TRACE = false instantiations.
+uint32_t* g_ffn_trace = nullptr;
 extern "C" int u2gnn_ffn_tc_set_trace(void* buf) {
-    g_trace = static_cast<uint32_t*>(buf);
+    g_ffn_trace = static_cast<uint32_t*>(buf);
     return U2GNN_OK;
 }
-
-static int g_dbg = 0;
-// experiment switch: bit 3 = epilogue mapping with 8 warps x 64 columns per tile instead of 16 warps x 32 columns on both
-// tiles (measured equal within 2 %; polling variants - test_wait first, back-off in the MMA warp - made no difference
-// and were removed)
-extern "C" int u2gnn_ffn_tc_debug(int flags) {
-    g_dbg = flags;
-    return U2GNN_OK;
-}
+#endif
 
 extern "C" size_t u2gnn_ffn_tc_packed_bytes(int d, int ff) {
     if (d < 1 || d > DP || ff < CH || ff % CH) return 0;
@@ -620,19 +613,20 @@ extern "C" int u2gnn_ffn_tc_fwd(const float* y1, int64_t M, int d, int ff, const
     p.gamma = gamma; p.beta = beta; p.z = z; p.stats = stats; p.xnext = xnext;
     const size_t smem = 1024 + (size_t)STAGES * STAGE_BYTES + 4 * (size_t)XS_TILE_BYTES + (size_t)(ff / 2 + 3 * DP) * sizeof(float);
     if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
-    p.trace = g_trace;
+    p.trace = nullptr;
     const int64_t n_pairs = (M + 2 * TM - 1) / (2 * TM);
     const int grid = (int)(n_pairs < U2GNN_NUM_SMS ? n_pairs : U2GNN_NUM_SMS);
     auto launch = [&](auto kern, int threads) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kern<<<grid, threads, smem, as_stream(stream)>>>(p);
     };
-    if (g_dbg & 8) {
-        if (g_trace) launch(ffn_tc_fwd_kernel<true, true>, kThreads);
-        else launch(ffn_tc_fwd_kernel<false, true>, kThreads);
-    } else {
-        if (g_trace) launch(ffn_tc_fwd_kernel<true, false>, kThreads);
-        else launch(ffn_tc_fwd_kernel<false, false>, kThreads);
+#ifdef U2GNN_PROBE_BUILD
+    p.trace = g_ffn_trace;
+    if (p.trace) {
+        launch(ffn_tc_fwd_kernel<true, false>, kThreads);
+        U2GNN_CHECK_LAUNCH();
     }
+#endif
+    launch(ffn_tc_fwd_kernel<false, false>, kThreads);
     U2GNN_CHECK_LAUNCH();
 }

@@ -418,240 +418,6 @@ __global__ void __launch_bounds__(kThreads, MINB) gemm_tc_rows_kernel(const Rows
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// rows GEMM, warp-specialised persistent version (aligned shapes: fp32 A with K = 64, bf16 A with K = 64 / 192).
-// One CTA per SM, 416 threads:  warps 0-7 loaders, warps 8-11 epilogue (thread = row), warp 12 MMA issuer.
-//   loaders  : coalesced 128-bit loads of tile i+1 are IN FLIGHT (registers) while tile i is rounded / copied into the
-//              swizzled A stage -> ~64 KB of loads outstanding per SM, what HBM latency x bandwidth needs
-//   MMA warp : K/16 tcgen05.mma per tile into one of two TMEM accumulators, commit -> stage free, accumulator full
-//   epilogue : tcgen05.ld -> padded staging -> coalesced stores (bias / beta / bf16 rounding), accumulator free
-// so load(i+1), MMA(i) and epilogue(i-1) overlap.  NOT the default: see u2gnn_gemm_tc_debug below for the measurement.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int kWsLoadWarps = 8, kWsEpiWarp0 = 8, kWsMmaWarp = 12, kWsThreads = 416;
-
-struct __align__(8) WsBars {
-    uint64_t a_full[2], a_free[2], acc_full[2], acc_free[2];
-};
-
-__device__ __forceinline__ void ws_named_bar(int id, int threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-
-template <bool A_BF16, int NPF>      // NPF: 16-byte pieces per loader thread per tile (fp32 K 64: 8; bf16 K 64: 4; bf16 K 192: 12)
-__global__ void __launch_bounds__(kWsThreads, 1) gemm_tc_rows_ws_kernel(const RowsParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset on the shared-window address: keeps LDS / STS (a uintptr_t round trip makes every access generic)
-    const int kt = p.KP / 64;
-    uint8_t* sA = smem;                                     // 2 stages x kt tiles of [128 x 64]
-    uint8_t* sB = sA + 2 * kt * 16384;                      // kt tiles of [NP x 64]
-    uint8_t* sOut = sB + kt * p.NP * 128;                   // fp32 staging of one 64-column piece: [128 rows x 272 B]
-    __shared__ WsBars bars;
-    __shared__ uint32_t tmem_slot;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int acc_stride = (p.NP <= 64) ? 64 : (p.NP <= 128 ? 128 : 256);
-    if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(&bars.a_full[i], kWsLoadWarps);
-            tc::mbar_init(&bars.a_free[i], 1);
-            tc::mbar_init(&bars.acc_full[i], 1);
-            tc::mbar_init(&bars.acc_free[i], 4);
-        }
-        tc::fence_barrier_init();
-    }
-    if (warp == kWsMmaWarp) {
-        if (acc_stride == 64) tc::tmem_alloc<128>(&tmem_slot);
-        else if (acc_stride == 128) tc::tmem_alloc<256>(&tmem_slot);
-        else tc::tmem_alloc<512>(&tmem_slot);
-    }
-    for (int e = tid; e < p.NP * p.KP; e += kWsThreads) {   // weights -> K-major image
-        const int n = e / p.KP, k = e - n * p.KP;
-        float w = 0.0f;
-        if (n < p.N && k < p.K) w = p.w_kn ? p.W[(size_t)k * p.N + n] : p.W[(size_t)n * p.K + k];
-        *reinterpret_cast<__nv_bfloat16*>(sB + (k >> 6) * (p.NP * 128) + tc::sw128_offset(n, k & 63)) = __float2bfloat16(w);
-    }
-    tc::fence_proxy_async();
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    const uint32_t tmem = tmem_slot;
-    const int64_t n_tiles = (p.M + TM - 1) / TM;
-    const int64_t my_tiles = (n_tiles > (int64_t)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-
-    if (warp < kWsLoadWarps) {
-        // ================= loaders =================
-        constexpr int NT = kWsLoadWarps * 32;
-        const int ppr = A_BF16 ? p.KP / 8 : 16;              // 16-byte pieces per row
-        uint4 b0[NPF], b1[NPF];
-        auto load = [&](int64_t i, uint4 (&buf)[NPF]) {
-            const int64_t r0 = ((int64_t)blockIdx.x + i * gridDim.x) * TM;
-#pragma unroll
-            for (int u = 0; u < NPF; ++u) {
-                const int e = u * NT + tid;
-                const int r = e / ppr, c = e - r * ppr;
-                buf[u] = make_uint4(0u, 0u, 0u, 0u);
-                if (i < my_tiles && r0 + r < p.M) {
-                    if (A_BF16) buf[u] = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.A) + (r0 + r) * p.lda) + c);
-                    else buf[u] = __ldg(reinterpret_cast<const uint4*>(static_cast<const float*>(p.A) + (r0 + r) * p.lda) + c);
-                }
-            }
-        };
-        auto store = [&](int64_t i, const uint4 (&buf)[NPF]) {
-            const int s = (int)(i & 1);
-            if (i >= 2) tc::mbar_wait(&bars.a_free[s], (uint32_t)((i >> 1) - 1) & 1);
-            uint8_t* st = sA + s * kt * 16384;
-#pragma unroll
-            for (int u = 0; u < NPF; ++u) {
-                const int e = u * NT + tid;
-                const int r = e / ppr, c = e - r * ppr;
-                if (A_BF16) {
-                    *reinterpret_cast<uint4*>(st + (c >> 3) * 16384 + tc::sw128_chunk(r, c & 7)) = buf[u];
-                } else {
-                    uint2 w;
-                    w.x = epi::cvt2(__uint_as_float(buf[u].x), __uint_as_float(buf[u].y));
-                    w.y = epi::cvt2(__uint_as_float(buf[u].z), __uint_as_float(buf[u].w));
-                    *reinterpret_cast<uint2*>(st + tc::sw128_offset(r, c * 4)) = w;
-                }
-            }
-            tc::fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&bars.a_full[s]);
-        };
-        load(0, b0);
-        for (int64_t i = 0; i < my_tiles; i += 2) {
-            load(i + 1, b1);
-            store(i, b0);
-            if (i + 1 < my_tiles) {
-                load(i + 2, b0);
-                store(i + 1, b1);
-            }
-        }
-    } else if (warp == kWsMmaWarp) {
-        // ================= MMA issuer =================
-        const uint32_t idesc = tc::make_idesc(TM, p.NP, 0, 0);
-        const uint64_t b_desc = tc::make_desc_sw128(tc::smem_u32(sB), 16, 1024);
-        for (int64_t i = 0; i < my_tiles; ++i) {
-            const int s = (int)(i & 1);
-            tc::mbar_wait(&bars.a_full[s], (uint32_t)(i >> 1) & 1);
-            if (i >= 2) tc::mbar_wait(&bars.acc_free[s], (uint32_t)((i >> 1) - 1) & 1);
-            tc::tc_fence_after();
-            if (tc::elect_one()) {
-                const uint64_t a_desc = tc::make_desc_sw128(tc::smem_u32(sA + s * kt * 16384), 16, 1024);
-                for (int ks = 0; ks < p.KP / 16; ++ks) {
-                    const uint32_t ko = (uint32_t)((ks >> 2) * 1024 + (ks & 3) * 2);
-                    const uint32_t bo = (uint32_t)((ks >> 2) * (p.NP * 8) + (ks & 3) * 2);
-                    tc::mma_ss(tmem + s * acc_stride, a_desc + ko, b_desc + bo, idesc, ks > 0);
-                }
-                tc::mma_commit(&bars.a_free[s]);
-                tc::mma_commit(&bars.acc_full[s]);
-            }
-            __syncwarp();
-        }
-    } else if (warp >= kWsEpiWarp0 && warp < kWsEpiWarp0 + 4) {
-        // ================= epilogue (128 threads, thread = row of its TMEM lane quarter) =================
-        const int wq = warp & 3, et = (warp - kWsEpiWarp0) * 32 + lane;      // et: 0..127
-        const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-        const int rt = wq * 32 + lane;                                       // row in tile (warp 8 -> quarter 0 ...)
-        const bool vec_ok = ((p.ldc & 3) == 0) && ((p.N & 3) == 0);
-        const bool bf_vec = p.c_bf16 && vec_ok && ((p.ldc & 7) == 0) && ((p.N & 7) == 0);
-        for (int64_t i = 0; i < my_tiles; ++i) {
-            const int s = (int)(i & 1);
-            const int64_t row0 = ((int64_t)blockIdx.x + i * gridDim.x) * TM;
-            tc::mbar_wait(&bars.acc_full[s], (uint32_t)(i >> 1) & 1);
-            tc::tc_fence_after();
-            for (int c0 = 0; c0 < p.NP; c0 += 64) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (c0 + 32 * h < p.NP) {
-                        uint32_t v[32];
-                        tc::tmem_ld32(tmem + lane_base + s * acc_stride + c0 + 32 * h, v);
-                        tc::tmem_ld_wait();
-                        float4* srow = reinterpret_cast<float4*>(sOut + rt * 272 + 128 * h);
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            srow[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                    }
-                }
-                if (c0 + 64 >= p.NP) {                                       // last piece: the accumulator is in shared memory
-                    tc::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(&bars.acc_free[s]);
-                }
-                ws_named_bar(1, 128);
-                if (bf_vec) {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int e = u * 128 + et;
-                        const int rr = e >> 3, c8 = e & 7;
-                        const int64_t row = row0 + rr;
-                        const int col = c0 + 8 * c8;
-                        if (row < p.M && col < p.N) {
-                            float4 o0 = *reinterpret_cast<const float4*>(sOut + rr * 272 + 32 * c8);
-                            float4 o1 = *reinterpret_cast<const float4*>(sOut + rr * 272 + 32 * c8 + 16);
-                            if (p.bias) {
-                                const float4 q0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                                const float4 q1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-                                o0.x += q0.x; o0.y += q0.y; o0.z += q0.z; o0.w += q0.w;
-                                o1.x += q1.x; o1.y += q1.y; o1.z += q1.z; o1.w += q1.w;
-                            }
-                            uint4 w;
-                            w.x = epi::cvt2(o0.x, o0.y); w.y = epi::cvt2(o0.z, o0.w);
-                            w.z = epi::cvt2(o1.x, o1.y); w.w = epi::cvt2(o1.z, o1.w);
-                            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col) = w;
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int u = 0; u < 16; ++u) {
-                        const int e = u * 128 + et;
-                        const int rr = e >> 4, c4 = e & 15;
-                        const int64_t row = row0 + rr;
-                        const int col = c0 + 4 * c4;
-                        if (row >= p.M || col >= p.N) continue;
-                        float4 o = *reinterpret_cast<const float4*>(sOut + rr * 272 + 16 * c4);
-                        if (p.c_bf16) {
-                            __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col;
-                            const float ov[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (col + j < p.N) ob[j] = __float2bfloat16(ov[j] + (p.bias ? p.bias[col + j] : 0.0f));
-                            continue;
-                        }
-                        float* out = static_cast<float*>(p.C) + row * p.ldc + col;
-                        if (vec_ok) {
-                            if (p.bias) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                                o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-                            }
-                            if (p.beta != 0.0f) {
-                                const float4 old = *reinterpret_cast<const float4*>(out);
-                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                            }
-                            *reinterpret_cast<float4*>(out) = o;
-                        } else {
-                            const float ov[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (col + j < p.N) {
-                                    float x = ov[j] + (p.bias ? p.bias[col + j] : 0.0f);
-                                    if (p.beta != 0.0f) x += out[j];
-                                    out[j] = x;
-                                }
-                        }
-                    }
-                }
-                ws_named_bar(1, 128);                                        // staging is reused by the next piece / tile
-            }
-        }
-    }
-    tc::tc_fence_before();
-    __syncthreads();
-    if (warp == kWsMmaWarp) {
-        if (acc_stride == 64) tc::tmem_dealloc<128>(tmem);
-        else if (acc_stride == 128) tc::tmem_dealloc<256>(tmem);
-        else tc::tmem_dealloc<512>(tmem);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // weight-gradient GEMM:  dW[N1, N2] += A^T B,  db[N1] += colsum(A).   N1 <= 256 (64-column groups), N2 <= 64.
 // TMEM: accumulator g covers A columns [128 g, 128 g + 128): 80 columns each (64 for dW + ones column for db).
 // ---------------------------------------------------------------------------------------------------------------
@@ -806,22 +572,9 @@ struct BwdParams {
     float beta;
     float* dW;            // [N1, 64]
     float* db;            // [N1] or null
-    // LNA kernels (N1 == 64): A is not read but computed while it is staged - the backward of the LayerNorm in front of the
-    // projection: dz = LN backward of ln_dy at the saved pre-norm rows ln_z / ln_stats (written to ln_dz, fp32), A = dropout(dz)
-    // rounded to bf16 (never stored), ln_dgamma / ln_dbeta accumulated.  Same arithmetic, same order as ln_bwd_vec_kernel<16>.
-    const float* ln_dy;
-    const float* ln_z;
-    const float* ln_stats;
-    const float* ln_gamma;
-    RngKeys ln_keys;
-    int ln_thr, ln_low;
-    float ln_scale;
-    float* ln_dz;
-    float* ln_dgamma;
-    float* ln_dbeta;
 };
 
-template <int NS, bool LNA = false>
+template <int NS>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_dgrad_wgrad_kernel(const BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -834,10 +587,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_dgrad_wgrad_kernel(const 
     uint8_t* sZero = sOnes + 16384;
     __shared__ uint64_t bar_mma[NS];
     __shared__ uint32_t tmem_slot;
-    __shared__ float s_ln[LNA ? 128 : 1];                     // dgamma | dbeta partial sums of this CTA
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (LNA && tid < 128) s_ln[tid] = 0.0f;
-    float4 ln_ag = make_float4(0.f, 0.f, 0.f, 0.f), ln_ab = ln_ag;   // this thread's four columns (4 (tid & 15) ..), all its rows
     if (tid == 0) {
         for (int i = 0; i < NS; ++i) tc::mbar_init(&bar_mma[i], 1);
         tc::fence_barrier_init();
@@ -863,59 +613,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_dgrad_wgrad_kernel(const 
     const int64_t n_tiles = (p.M + TM - 1) / TM;
     const bool b_async = rows_async_ok(p.B, p.b_bf16, 64, p.ldb);
     auto issue_async = [&](int64_t tile, uint8_t* st) {
-        if (!LNA) stage_rows_async<kThreads>(st, p.A, tile * TM, p.M, p.N1, p.N1, p.lda, tid);
+        stage_rows_async<kThreads>(st, p.A, tile * TM, p.M, p.N1, p.N1, p.lda, tid);
         if (b_async) stage_rows_async<kThreads>(st + ga * 16384, p.B, tile * TM, p.M, 64, 64, p.ldb, tid);
     };
     auto finish_sync = [&](int64_t tile, uint8_t* st) {
         if (!b_async) stage_rows_bf16<kThreads, 64>(st + ga * 16384, p.B, p.b_bf16, tile * TM, p.M, 64, 64, p.ldb, tid);
-        if constexpr (LNA) {
-            // LayerNorm backward of the tile's rows (16 lanes x float4 = one row, two rows per warp per step)
-            const int l = tid & 15;
-            const int64_t r0 = tile * TM;
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma) + l);
-            float4 gv[8], xv[8];
-            float2 sv[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int64_t row = r0 + ((u * kThreads + tid) >> 4);
-                gv[u] = xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                sv[u] = make_float2(0.f, 0.f);
-                if (row < p.M) {
-                    gv[u] = __ldg(reinterpret_cast<const float4*>(p.ln_dy + row * 64) + l);
-                    xv[u] = __ldg(reinterpret_cast<const float4*>(p.ln_z + row * 64) + l);
-                    sv[u] = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + row);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int rr = (u * kThreads + tid) >> 4;
-                const int64_t row = r0 + rr;
-                const float4 g = gv[u], x = xv[u];
-                const float mean = sv[u].x, rstd = sv[u].y;
-                const float4 xh = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd, (x.w - mean) * rstd);
-                const float4 dh = make_float4(g.x * g4.x, g.y * g4.y, g.z * g4.z, g.w * g4.w);
-                ln_ag.x = fmaf(g.x, xh.x, ln_ag.x); ln_ag.y = fmaf(g.y, xh.y, ln_ag.y);
-                ln_ag.z = fmaf(g.z, xh.z, ln_ag.z); ln_ag.w = fmaf(g.w, xh.w, ln_ag.w);
-                ln_ab.x += g.x; ln_ab.y += g.y; ln_ab.z += g.z; ln_ab.w += g.w;
-                const float m1 = group16_sum((dh.x + dh.y) + (dh.z + dh.w)) * (1.0f / 64.0f);
-                const float m2 = group16_sum((dh.x * xh.x + dh.y * xh.y) + (dh.z * xh.z + dh.w * xh.w)) * (1.0f / 64.0f);
-                float4 o = make_float4(rstd * (dh.x - m1 - xh.x * m2), rstd * (dh.y - m1 - xh.y * m2),
-                                       rstd * (dh.z - m1 - xh.z * m2), rstd * (dh.w - m1 - xh.w * m2));
-                if (row < p.M) reinterpret_cast<float4*>(p.ln_dz + row * 64)[l] = o;
-                if (p.ln_thr) {
-                    const uint64_t el = (uint64_t)(row * 64 + 4 * l);
-                    const uint32_t kw = rng_keep_word_lo(p.ln_keys, el >> 5, p.ln_thr, p.ln_low) >> (el & 31);
-                    o.x = (kw & 1u) ? o.x * p.ln_scale : 0.0f;
-                    o.y = (kw & 2u) ? o.y * p.ln_scale : 0.0f;
-                    o.z = (kw & 4u) ? o.z * p.ln_scale : 0.0f;
-                    o.w = (kw & 8u) ? o.w * p.ln_scale : 0.0f;
-                }
-                uint2 w;
-                w.x = epi::cvt2(o.x, o.y);
-                w.y = epi::cvt2(o.z, o.w);
-                *reinterpret_cast<uint2*>(st + tc::sw128_offset(rr, 4 * l)) = w;
-            }
-        }
     };
     // prologue: tiles 0 .. NS-2 of this CTA
 #pragma unroll
@@ -1050,35 +752,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_dgrad_wgrad_kernel(const 
             if (p.db && n1 < p.N1) atomicAdd(p.db + n1, __uint_as_float(b16[0]));
         }
     }
-    if constexpr (LNA) {
-        ln_ag.x += __shfl_xor_sync(0xffffffffu, ln_ag.x, 16); ln_ag.y += __shfl_xor_sync(0xffffffffu, ln_ag.y, 16);
-        ln_ag.z += __shfl_xor_sync(0xffffffffu, ln_ag.z, 16); ln_ag.w += __shfl_xor_sync(0xffffffffu, ln_ag.w, 16);
-        ln_ab.x += __shfl_xor_sync(0xffffffffu, ln_ab.x, 16); ln_ab.y += __shfl_xor_sync(0xffffffffu, ln_ab.y, 16);
-        ln_ab.z += __shfl_xor_sync(0xffffffffu, ln_ab.z, 16); ln_ab.w += __shfl_xor_sync(0xffffffffu, ln_ab.w, 16);
-        if (lane < 16) {
-            const int l = lane;
-            atomicAdd(&s_ln[4 * l], ln_ag.x); atomicAdd(&s_ln[4 * l + 1], ln_ag.y); atomicAdd(&s_ln[4 * l + 2], ln_ag.z); atomicAdd(&s_ln[4 * l + 3], ln_ag.w);
-            atomicAdd(&s_ln[64 + 4 * l], ln_ab.x); atomicAdd(&s_ln[64 + 4 * l + 1], ln_ab.y); atomicAdd(&s_ln[64 + 4 * l + 2], ln_ab.z); atomicAdd(&s_ln[64 + 4 * l + 3], ln_ab.w);
-        }
-    }
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc<256>(tmem);
-    if (LNA && tid < 128) atomicAdd((tid < 64 ? p.ln_dgamma : p.ln_dbeta) + (tid & 63), s_ln[tid]);
 }
 
 }  // namespace
 
-static int g_rows_ws = 0;
-// experiment switch: 0 (default) = phase-serial projection kernel for every shape, 1 = warp-specialised kernel where it
-// applies.  Measured on B200 (65 536-node step, 40 projection launches): phase-serial 8.67 ms total, warp-specialised 9.95 ms
-// (bf16 K = 192 with beta: 637 us per launch against ~220 us) - 128 epilogue threads and 64 KB of loads in flight per SM
-// are not enough; three phase-serial CTAs of 256 threads per SM overlap better.  Kept as a verified-correct experiment.
-extern "C" int u2gnn_gemm_tc_debug(int ws) {
-    g_rows_ws = ws;
-    return U2GNN_OK;
-}
-
+// (Round 1 also had a warp-specialised persistent version of the rows kernel - 8 loader warps, 4 epilogue warps, 1 MMA warp per SM.
+// Measured on B200 over 40 projection launches of a 65 536-node step: 9.95 ms against 8.67 ms for this phase-serial kernel
+// (bf16 K = 192 with beta: 637 us per launch against ~220 us): 128 epilogue threads and 64 KB of loads in flight per SM are not
+// enough; three phase-serial CTAs of 256 threads per SM overlap better.  Removed in round 2.)
 extern "C" int u2gnn_gemm_tc_rows_ex(const void* A, int a_bf16, int64_t M, int K, int64_t lda, const float* W, int w_kn, int N,
                                      const float* bias, float beta, void* C, int c_bf16, int64_t ldc, u2gnn_stream_t stream) {
     if (!A || !W || !C || M < 0 || K < 1 || N < 1 || lda < K || ldc < N) return U2GNN_EINVAL;
@@ -1091,23 +775,6 @@ extern "C" int u2gnn_gemm_tc_rows_ex(const void* A, int a_bf16, int64_t M, int K
     p.W = W; p.w_kn = w_kn; p.N = N; p.NP = (N + 15) / 16 * 16;
     p.bias = bias; p.C = C; p.ldc = ldc; p.beta = beta;
     const int kt = p.KP / 64;
-    const int64_t n_tiles_ws = (M + TM - 1) / TM;
-    {   // warp-specialised persistent kernel for the aligned shapes of the attention block
-        const bool fp32_ok = !a_bf16 && K == 64 && (lda & 3) == 0;
-        const bool bf16_ok = a_bf16 && (K == 64 || K == 192) && (lda & 7) == 0;
-        const size_t smem_ws = 1024 + (size_t)2 * kt * 16384 + (size_t)kt * p.NP * 128 + 128 * 272;
-        if ((fp32_ok || bf16_ok) && smem_ws <= 227 * 1024 && g_rows_ws) {
-            const int grid = (int)(n_tiles_ws < U2GNN_NUM_SMS ? n_tiles_ws : U2GNN_NUM_SMS);
-            auto launch = [&](auto kern) {
-                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws);
-                kern<<<grid, kWsThreads, smem_ws, as_stream(stream)>>>(p);
-            };
-            if (fp32_ok) launch(gemm_tc_rows_ws_kernel<false, 8>);
-            else if (p.KP == 64) launch(gemm_tc_rows_ws_kernel<true, 4>);
-            else launch(gemm_tc_rows_ws_kernel<true, 12>);
-            U2GNN_CHECK_LAUNCH();
-        }
-    }
     const size_t smem = 1024 + (size_t)kt * 16384 + (size_t)kt * p.NP * 128 + 128 * 272;
     if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
     int per_sm = (int)((220 * 1024) / (smem + 1024));
@@ -1223,33 +890,7 @@ extern "C" int u2gnn_gemm_tc_dgrad_wgrad(const void* A, int64_t M, int N1, int64
     U2GNN_CHECK_LAUNCH();
 }
 
-// out_proj backward with the LayerNorm1 backward in front of it (d = 64): one kernel computes dz = LN backward of dy at the
-// saved pre-norm rows z / stats (written, fp32: the residual gradient), da = dropout(dz) on the fly as the bf16 A operand (never
-// stored), dgamma / dbeta, the input gradient C = da W and the weight / bias gradients dW += da^T B, db += colsum(da).
-// Replaces u2gnn_add_dropout_ln_bwd_ex (bf16 da) + u2gnn_gemm_tc_dgrad_wgrad on the same operands.
-extern "C" int u2gnn_ln_bwd_gemm_tc_dgrad_wgrad(const float* dy, const float* z, const float* stats, const float* gamma, uint64_t seed,
-                                                uint32_t rng_stream, int thr, int64_t M, const void* B, int b_bf16, int64_t ldb,
-                                                const float* W, void* C, int c_bf16, int64_t ldc, float* dz, float* dgamma,
-                                                float* dbeta, float* dW, float* db, u2gnn_stream_t stream) {
-    if (!dy || !z || !stats || !gamma || !B || !W || !C || !dz || !dgamma || !dbeta || !dW || M < 0 || ldb < 64 || ldc < 64 ||
-        thr < 0 || thr > 255)
-        return U2GNN_EINVAL;
-    if ((ldc & 7) || (ldb & (b_bf16 ? 7 : 3))) return U2GNN_EALIGN;
-    if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(B) |
-         reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(gamma)) % 16 || reinterpret_cast<uintptr_t>(stats) % 8)
-        return U2GNN_EALIGN;
-    if (M == 0) return U2GNN_OK;
-    BwdParams p;
-    p.A = nullptr; p.B = B; p.b_bf16 = b_bf16; p.c_bf16 = c_bf16; p.M = M; p.lda = 64; p.ldb = ldb; p.ldc = ldc; p.N1 = 64;
-    p.W = W; p.C = C; p.beta = 0.0f; p.dW = dW; p.db = db;
-    p.ln_dy = dy; p.ln_z = z; p.ln_stats = stats; p.ln_gamma = gamma;
-    p.ln_keys = rng_keys(seed, rng_stream); p.ln_thr = thr; p.ln_low = rng_thr_low(thr);
-    p.ln_scale = thr ? rng_keep_scale(thr) : 1.0f;
-    p.ln_dz = dz; p.ln_dgamma = dgamma; p.ln_dbeta = dbeta;
-    const size_t smem = 1024 + 8192 + 128 * 272 + 2 * 16384 + 4 * (size_t)2 * 16384;
-    const int64_t n_tiles = (M + TM - 1) / TM;
-    const int grid = (int)(n_tiles < U2GNN_NUM_SMS ? n_tiles : U2GNN_NUM_SMS);
-    cudaFuncSetAttribute(gemm_tc_dgrad_wgrad_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    gemm_tc_dgrad_wgrad_kernel<4, true><<<grid, kThreads, smem, as_stream(stream)>>>(p);
-    U2GNN_CHECK_LAUNCH();
-}
+// (Round 1 also had a variant of this kernel with the LayerNorm1 backward evaluated while the operand tile is staged, so that the
+// dropout-masked gradient was never stored.  Parity-green but slower as measured on B200 - 66.06 against 65.48 ms per step: one
+// CTA of 256 threads per SM doing the LayerNorm arithmetic in its load phase is less efficient than the 24-warp LayerNorm pass
+// followed by this cp.async-fed kernel.  Removed in round 2.)

@@ -1,8 +1,8 @@
 // Micro-probe of tcgen05.mma issue/execute rates (one CTA): cycles per MMA for a given N, operand source
 // (SS / TS) and accumulator pattern (same accumulator vs rotating accumulators).  Used to size the fused
 // kernels' tiles; not part of the hot path.
-#include "common.cuh"
-#include "tc_common.cuh"
+#include "../common.cuh"
+#include "../tc_common.cuh"
 
 namespace {
 __global__ void __launch_bounds__(128) tc_probe_kernel(int N, int ts, int rotate, int count, long long* out) {

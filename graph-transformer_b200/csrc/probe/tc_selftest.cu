@@ -7,8 +7,8 @@
 //   mode 3  as mode 0 with B brought in by a 1-D bulk copy of a pre-swizzled image (UBLKCP + mbarrier tx)
 //   mode 4  as mode 0 with an fp16 accumulator (idesc c_format = 0); C receives the RAW 32-bit tensor-memory columns
 //   mode 5  as mode 2 with A staged in tensor memory as fp16 pairs (a_format = 0) against a bf16 B
-#include "common.cuh"
-#include "tc_common.cuh"
+#include "../common.cuh"
+#include "../tc_common.cuh"
 #include <cuda_fp16.h>
 
 namespace {

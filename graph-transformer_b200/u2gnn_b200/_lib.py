@@ -12,7 +12,9 @@ import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libu2gnn_b200.so")
+PROBE_LIB_PATH = os.path.join(_HERE, "libu2gnn_b200_probe.so")
 HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "include", "u2gnn_b200.h"))
+PROBE_HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "include", "u2gnn_b200_probe.h"))
 
 _SCALARS = {
     "int": ctypes.c_int, "float": ctypes.c_float, "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64,
@@ -47,17 +49,18 @@ SIGNATURES = parse_header()
 
 
 class _Lib:
-    def __init__(self):
-        if not os.path.exists(LIB_PATH):
+    def __init__(self, path=LIB_PATH, signatures=None):
+        signatures = SIGNATURES if signatures is None else signatures
+        if not os.path.exists(path):
             raise ImportError(
                 "u2gnn_b200: %s is missing - build it with `python graph-transformer_b200/build.py` "
-                "(there is no CPU or PyTorch fallback for this path)" % LIB_PATH)
-        self.cdll = ctypes.CDLL(LIB_PATH)
-        for name, (ret, params) in SIGNATURES.items():
+                "(there is no CPU or PyTorch fallback for this path)" % path)
+        self.cdll = ctypes.CDLL(path)
+        for name, (ret, params) in signatures.items():
             fn = getattr(self.cdll, name)     # AttributeError if the library lacks a declared symbol
             fn.restype = ret
             fn.argtypes = [t for t, _ in params]
-        self._status = {n for n, (r, _) in SIGNATURES.items() if r is ctypes.c_int}
+        self._status = {n for n, (r, _) in signatures.items() if r is ctypes.c_int}
         self.launches = 0          # C-ABI calls that launch kernels (bench.py's gpu_launches claim)
         self.timed = None          # {entry point: [(start_event, end_event), ...]} when profiling
 
@@ -82,6 +85,18 @@ class _Lib:
 
 
 LIB = _Lib()
+_PROBE = None
+
+
+def probe_lib():
+    """The PROBE library (layout self-tests, micro-benchmarks, kernel tracing; include/u2gnn_b200_probe.h): a superset build
+    of the product sources loaded side by side with it.  Only tools/ and the hardware-layout tests use it."""
+    global _PROBE
+    if _PROBE is None:
+        sig = dict(SIGNATURES)
+        sig.update(parse_header(PROBE_HEADER_PATH))
+        _PROBE = _Lib(PROBE_LIB_PATH, sig)
+    return _PROBE
 
 
 def require_device():

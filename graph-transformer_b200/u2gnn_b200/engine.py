@@ -31,10 +31,6 @@ FUSE_LN_BWD = os.environ.get("U2GNN_FUSE_EPILOGUES", "1") != "0"        # bf16 m
 LAST_STEP_BF16 = os.environ.get("U2GNN_LAST_BF16", "1") != "0"            # bf16 mode, d = 64: bf16 qkv / dqkv at the dead-row-eliminated last timestep
 FUSE_PROJ_BWD = os.environ.get("U2GNN_FUSE_PROJ_BWD", "1") != "0"         # bf16 mode, d = 64: projection input + weight gradients in one pass over the output gradient
 FUSE_INPROJ_ATTN = os.environ.get("U2GNN_FUSE_INPROJ_ATTN", "1") != "0"   # bf16 mode, d = 64: in_proj inside the attention-forward kernel (qkv written once, never re-read in the forward)
-# bf16 mode, d = 64: LayerNorm1 backward inside the out_proj backward kernel (da never stored).  Parity-green (dz, dctx bit-identical)
-# but SLOWER as measured (66.06 against 65.48 ms per step): one CTA of 256 threads per SM doing the LayerNorm arithmetic while
-# it stages the operand is less efficient than the 24-warp LayerNorm pass plus the cp.async-fed GEMM.  Off by default.
-FUSE_LN1_PROJ_BWD = os.environ.get("U2GNN_FUSE_LN1_PROJ_BWD", "0") != "0"
 FLOPS = {}    # entry point -> algorithmic flops issued while LIB.timed is active (bench.py roofline)
 BYTES = {}    # entry point -> algorithmic HBM bytes (the tensors the call must read + write once) while LIB.timed is active
 
@@ -479,29 +475,20 @@ def _encoder_attn_bwd(dy1, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
     tc_proj = sv.packed is not None and not long_seq and d <= 64
     tc_attn = tc_proj and d == 64 and Sq == S and S >= 2
     fuse_bwd = tc_proj and d == 64 and FUSE_PROJ_BWD
-    if fuse_bwd and FUSE_LN1_PROJ_BWD:
-        # LayerNorm1 backward + out_proj backward in one kernel: da is formed while the operand tile is staged and never stored
-        dz1 = torch.empty((Mq, d), **f32)
-        dctx = torch.empty((Mq, d), dtype=torch.bfloat16 if tc_attn else torch.float32, device=dev)
-        LIB.call("u2gnn_ln_bwd_gemm_tc_dgrad_wgrad", _ptr(dy1), _ptr(sv.z1), _ptr(sv.st1), _ptr(p["norm1.weight"]), seed, drop_ids[1],
-                 thr, Mq, _ptr(sv.ctx), int(sv.ctx.dtype == torch.bfloat16), d, _ptr(p["self_attn.out_proj.weight"]), _ptr(dctx),
-                 int(tc_attn), d, _ptr(dz1), _ptr(g["norm1.weight"]), _ptr(g["norm1.bias"]), _ptr(g["self_attn.out_proj.weight"]),
-                 _ptr(g["self_attn.out_proj.bias"]), _stream())
+    # da only feeds the two out_proj tensor-core GEMMs (weight gradient, input gradient): bf16, rounded once by its producer
+    dz1, da = add_dropout_ln_bwd(dy1, sv.z1, sv.st1, Mq, d, p["norm1.weight"], (seed, drop_ids[1], thr),
+                                 g["norm1.weight"], g["norm1.bias"], da_bf16=tc_proj and d == 64 and FUSE_LN_BWD)
+    if fuse_bwd and da.dtype == torch.bfloat16:
+        # out_proj backward: input gradient and weight gradient from one pass over da
+        dctx = proj_bwd_tc(da, Mq, d, sv.ctx, p["self_attn.out_proj.weight"], g["self_attn.out_proj.weight"],
+                           g["self_attn.out_proj.bias"], out_bf16=tc_attn)
+    elif tc_proj:
+        wgrad_tc(da, Mq, d, sv.ctx, d, g["self_attn.out_proj.weight"], g["self_attn.out_proj.bias"])
+        dctx = linear_tc(da, Mq, d, p["self_attn.out_proj.weight"], 1, d, out_bf16=tc_attn)
     else:
-        # da only feeds the two out_proj tensor-core GEMMs (weight gradient, input gradient): bf16, rounded once by its producer
-        dz1, da = add_dropout_ln_bwd(dy1, sv.z1, sv.st1, Mq, d, p["norm1.weight"], (seed, drop_ids[1], thr),
-                                     g["norm1.weight"], g["norm1.bias"], da_bf16=tc_proj and d == 64 and FUSE_LN_BWD)
-        if fuse_bwd and da.dtype == torch.bfloat16:
-            # out_proj backward: input gradient and weight gradient from one pass over da
-            dctx = proj_bwd_tc(da, Mq, d, sv.ctx, p["self_attn.out_proj.weight"], g["self_attn.out_proj.weight"],
-                               g["self_attn.out_proj.bias"], out_bf16=tc_attn)
-        elif tc_proj:
-            wgrad_tc(da, Mq, d, sv.ctx, d, g["self_attn.out_proj.weight"], g["self_attn.out_proj.bias"])
-            dctx = linear_tc(da, Mq, d, p["self_attn.out_proj.weight"], 1, d, out_bf16=tc_attn)
-        else:
-            wgrad(da, Mq, d, sv.ctx, d, g["self_attn.out_proj.weight"], g["self_attn.out_proj.bias"])
-            dctx = torch.empty((Mq, d), **f32)
-            sgemm(0, 0, Mq, d, d, da, d, p["self_attn.out_proj.weight"], d, dctx, d)
+        wgrad(da, Mq, d, sv.ctx, d, g["self_attn.out_proj.weight"], g["self_attn.out_proj.bias"])
+        dctx = torch.empty((Mq, d), **f32)
+        sgemm(0, 0, Mq, d, d, da, d, p["self_attn.out_proj.weight"], d, dctx, d)
     tc_last = sv.qkv.dtype == torch.bfloat16 and Sq == 1
     dqkv = torch.empty((M, 3 * d), dtype=torch.bfloat16 if (tc_attn or tc_last) else torch.float32, device=dev)
     if long_seq:

@@ -205,11 +205,6 @@ int u2gnn_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, con
  *      z[M,d] = y1 + dropout_out( dropout_hidden(relu(y1 W1^T + b1)) W2^T + b2 );
  *      stats[M,2] = (mean, rstd) of z;  xnext[M,d] = LayerNorm(z)*gamma + beta (may be null). */
 size_t u2gnn_ffn_tc_packed_bytes(int d, int ff);
-/* experiment switches for profiling the forward pipeline (0 = normal operation) */
-int u2gnn_ffn_tc_debug(int flags);
-/* debug: device buffer of 17 x 1024 uint32 clock stamps written by CTA 0 of the following forward launches
-   (slot 0 = MMA warp, 1..16 = epilogue warps); NULL switches tracing off (tools/trace_ffn.py) */
-int u2gnn_ffn_tc_set_trace(void* buf);
 int u2gnn_ffn_tc_prepare(const float* W1, const float* b1, const float* W2, const float* b2, int d, int ff,
                          float hidden_scale, void* packed, size_t packed_size, u2gnn_stream_t stream);
 int u2gnn_ffn_tc_fwd(const float* y1, int64_t M, int d, int ff, const void* packed, uint64_t seed,
@@ -243,19 +238,10 @@ int u2gnn_seqattn_tc_fwd(const float* qkv, int64_t B, int S, int d, uint64_t see
 int u2gnn_seqattn_tc_bwd(const float* qkv, const float* dctx, int64_t B, int S, int d, uint64_t seed,
                          uint32_t rng_stream, int thr, float* dqkv, u2gnn_stream_t stream);
 
-/* ---- tcgen05 plumbing self-test (csrc/tc_selftest.cu): one CTA runs a [128 x N x K] bf16 GEMM through
- *      each operand path the fused kernels use (mode 0 K-major smem, 1 MN-major smem, 2 A in tensor
- *      memory, 3 bulk-copied pre-swizzled B).  No reference counterpart: it pins hardware layout
- *      assumptions.  A, B fp32 inputs (rounded to bf16 inside), C[128, N] fp32; scratch >= 32 KB. */
-int u2gnn_tc_selftest(int mode, const float* A, const float* B, float* C, int K, int N, void* scratch,
-                      u2gnn_stream_t stream);
-
 /* ---- bf16 activation I/O for the attention block of the bf16 mode.  Every consumer of qkv / ctx / dctx / dqkv rounds them
         to bf16 before its tensor-core product, so the producers store them as bf16 row-major (rounded once, bit-identical
         results) and the block moves half the HBM bytes.  *_bf16 flags: 0 = fp32 buffer, 1 = bf16 buffer; leading
         dimensions are in ELEMENTS; beta must be 0 for a bf16 C. ---- */
-/* experiment switch for the projection GEMM: 0 (default) = phase-serial kernel, 1 = warp-specialised persistent kernel for aligned shapes (slower as measured) */
-int u2gnn_gemm_tc_debug(int ws);
 int u2gnn_gemm_tc_rows_ex(const void* A, int a_bf16, int64_t M, int K, int64_t lda, const float* W, int w_kn, int N,
                           const float* bias, float beta, void* C, int c_bf16, int64_t ldc, u2gnn_stream_t stream);
 int u2gnn_gemm_tc_wgrad_ex(const void* A, int a_bf16, int64_t M, int N1, int64_t lda, const void* B, int b_bf16, int N2,
@@ -268,15 +254,6 @@ int u2gnn_gemm_tc_wgrad_ex(const void* A, int a_bf16, int64_t M, int N1, int64_t
 int u2gnn_gemm_tc_dgrad_wgrad(const void* A, int64_t M, int N1, int64_t lda, const void* B, int b_bf16, int64_t ldb,
                               const float* W, void* C, int c_bf16, int64_t ldc, float beta, float* dW, float* db,
                               u2gnn_stream_t stream);
-/* LayerNorm1 backward + out_proj backward in ONE kernel (d = 64): dz[M,64] = LN backward of dy at the saved pre-norm rows z and
- * stats[M,2] (the residual gradient, fp32), da = dropout(dz; seed, rng_stream, thr) formed on the fly as the bf16 operand (never
- * stored), dgamma / dbeta (+=), C[M,64] = da W (the gradient at the attention output; fp32 or bf16), dW[64,64] += da^T B,
- * db[64] += colsum(da) with B[M,64] = the attention output rows.  Same results as u2gnn_add_dropout_ln_bwd_ex(da_bf16 = 1)
- * followed by u2gnn_gemm_tc_dgrad_wgrad.  (torch/nn/modules/transformer.py:946,969-972 autograd) */
-int u2gnn_ln_bwd_gemm_tc_dgrad_wgrad(const float* dy, const float* z, const float* stats, const float* gamma, uint64_t seed,
-                                     uint32_t rng_stream, int thr, int64_t M, const void* B, int b_bf16, int64_t ldb,
-                                     const float* W, void* C, int c_bf16, int64_t ldc, float* dz, float* dgamma, float* dbeta,
-                                     float* dW, float* db, u2gnn_stream_t stream);
 /* out_proj + dropout + residual + LayerNorm1 in one kernel (torch/nn/modules/transformer.py:946,969-972:
  * x = norm1(x + dropout1(self_attn(x)))): z[M,64] = res + dropout(A[M,K] W^T + bias), y = LayerNorm(z) * gamma + beta,
  * stats[M,2] = (mean, rstd).  N = d = 64 only; res row stride ldres (elements) so the last timestep can read position 0 of
@@ -314,14 +291,6 @@ int u2gnn_seqattn_last_bwd_ex(const void* qkv, const float* dctx, int io_bf16, i
 int u2gnn_build_batch(const int64_t* g_rowptr, const int64_t* g_col, const int64_t* graph_start,
                       const int64_t* batch_off, int64_t n_graphs, int64_t n_nodes, int k, uint64_t seed,
                       uint32_t rng_stream, int64_t* input_x, int64_t* node_global, u2gnn_stream_t stream);
-
-/* tcgen05.mma rate probe (tools/probe_mma.py): out[0] = issue cycles, out[1] = issue+execute cycles of `count` MMAs */
-int u2gnn_tc_probe(int N, int ts, int rotate, int count, long long* out, u2gnn_stream_t stream);
-/* L2 reduction throughput probe (tools/probe_red.py): `groups` CTAs add into the same 32 KB tile, tile after tile;
-   mode 0 red.v4.f32, 1 scalar atomicAdd, 2 plain stores, 3 red.v4.f32 thread-per-row */
-int u2gnn_red_probe(float* buf, int64_t n_tiles, int groups, int mode, u2gnn_stream_t stream);
-/* TMEM -> register bandwidth probe: out[0] = cycles, out[1] = bytes */
-int u2gnn_tmem_bw_probe(int warps, int iters, int batch, long long* out, u2gnn_stream_t stream);
 
 #ifdef __cplusplus
 }

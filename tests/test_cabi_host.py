@@ -29,6 +29,21 @@ def test_library_exports_every_declared_symbol(U):
     assert {e for e in exported if e.startswith("u2gnn_")} == declared     # nothing undeclared leaks out
 
 
+def test_product_library_has_no_probe_entry_points_or_global_state(U):
+    """probes / self-tests / tracing live in libu2gnn_b200_probe.so; the product library exports only what
+    include/u2gnn_b200.h declares and defines no writable global data of its own (B / D symbols)."""
+    from u2gnn_b200 import _lib
+    syms = subprocess.run(["nm", "-D", "--defined-only", U.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    names = [l.split()[-1] for l in syms.splitlines()]
+    assert not [n for n in names if any(w in n for w in ("probe", "selftest", "trace", "debug", "_mode"))]
+    assert not [l for l in syms.splitlines() if l.split()[-2] in ("B", "D") and l.split()[-1].startswith(("g_", "u2gnn"))]
+    probe_decl = set(_lib.parse_header(_lib.PROBE_HEADER_PATH))
+    assert probe_decl and not (probe_decl & set(U.SIGNATURES))
+    psyms = subprocess.run(["nm", "-D", "--defined-only", _lib.PROBE_LIB_PATH], capture_output=True, text=True, check=True).stdout
+    pexp = {l.split()[-1] for l in psyms.splitlines() if " T " in l}
+    assert probe_decl <= pexp and set(U.SIGNATURES) <= pexp       # the probe library is a superset build
+
+
 def test_header_has_no_torch_types_and_cites_reference():
     text = open(os.path.join(ROOT, "include", "u2gnn_b200.h")).read()
     assert "at::" not in text and "torch::" not in text and "#include <torch" not in text and "Tensor " not in text

@@ -9,7 +9,6 @@ from u2gnn_b200 import engine as E
 d, ff = 64, 2048
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 4 * 1024 * 1024
 thr = int(sys.argv[2]) if len(sys.argv) > 2 else 128
-U.LIB.call("u2gnn_ffn_tc_debug", int(sys.argv[3]) if len(sys.argv) > 3 else 0)
 g = torch.Generator(device="cuda").manual_seed(0)
 y1 = torch.randn(M, d, device="cuda", generator=g); df = torch.randn(M, d, device="cuda", generator=g); dz = torch.randn(M, d, device="cuda", generator=g)
 W1 = torch.randn(ff, d, device="cuda", generator=g) / 8; W2 = torch.randn(d, ff, device="cuda", generator=g) / 45

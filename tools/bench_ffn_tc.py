@@ -11,7 +11,6 @@ def main():
     M = int(sys.argv[1]) if len(sys.argv) > 1 else 4 * 1024 * 1024
     thr = int(sys.argv[2]) if len(sys.argv) > 2 else 128
     dbg = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-    U.LIB.call("u2gnn_ffn_tc_debug", dbg)
     g = torch.Generator(device="cuda").manual_seed(0)
     y1 = torch.randn(M, d, device="cuda", generator=g)
     W1 = torch.randn(ff, d, device="cuda", generator=g) / 8

@@ -6,6 +6,8 @@ sys.path.insert(0, os.path.join(ROOT, "graph-transformer_b200"))
 import numpy as np, torch
 import u2gnn_b200 as U
 from u2gnn_b200 import engine as E
+from u2gnn_b200._lib import probe_lib
+PROBE = probe_lib()     # libu2gnn_b200_probe.so: the product library exports no probe / trace entry points
 torch.manual_seed(0)
 K, N = 64, 128
 A = torch.randn(128, K, device="cuda"); B = torch.randn(N, K, device="cuda")
@@ -13,7 +15,7 @@ bf = lambda x: x.to(torch.bfloat16).float()
 ref = bf(A) @ bf(B).t()
 scratch = torch.zeros(65536, dtype=torch.uint8, device="cuda")
 C = torch.zeros(128, N, device="cuda")
-U.LIB.call("u2gnn_tc_selftest", 4, A.data_ptr(), B.data_ptr(), C.data_ptr(), K, N, scratch.data_ptr(), E._stream())
+PROBE.call("u2gnn_tc_selftest", 4, A.data_ptr(), B.data_ptr(), C.data_ptr(), K, N, scratch.data_ptr(), E._stream())
 torch.cuda.synchronize()
 raw = C.cpu().numpy().view(np.uint32)
 lo = (raw & 0xFFFF).astype(np.uint16).view(np.float16).astype(np.float32)
@@ -27,7 +29,7 @@ pk = np.stack([lo[:, : N // 2], hi[:, : N // 2]], axis=2).reshape(128, N)
 print("hyp packed (col j = elems 2j,2j+1): max err", np.abs(pk - r).max())
 print("cols N/2.. raw nonzero:", int((raw[:, N // 2:] != 0).sum()))
 C2 = torch.zeros(128, N, device="cuda")
-U.LIB.call("u2gnn_tc_selftest", 5, A.data_ptr(), B.data_ptr(), C2.data_ptr(), K, N, scratch.data_ptr(), E._stream())
+PROBE.call("u2gnn_tc_selftest", 5, A.data_ptr(), B.data_ptr(), C2.data_ptr(), K, N, scratch.data_ptr(), E._stream())
 torch.cuda.synchronize()
 ref5 = A.half().float() @ bf(B).t()
 print("fp16 A (TMEM) x bf16 B: rel err", ((C2 - ref5).abs().max() / ref5.abs().max()).item())

@@ -5,11 +5,13 @@ sys.path.insert(0, os.path.join(ROOT, "graph-transformer_b200"))
 import torch
 import u2gnn_b200 as U
 from u2gnn_b200 import engine as E
+from u2gnn_b200._lib import probe_lib
+PROBE = probe_lib()     # libu2gnn_b200_probe.so: the product library exports no probe / trace entry points
 n_tiles = 34816                      # 4.456 M rows
 buf = torch.zeros(n_tiles * 8192, device="cuda")
 for groups in (16, 8, 1):
     for mode in (0, 3, 1, 2, 4, 5, 6):
-        def run(): U.LIB.call("u2gnn_red_probe", buf.data_ptr(), n_tiles, groups, mode, E._stream())
+        def run(): PROBE.call("u2gnn_red_probe", buf.data_ptr(), n_tiles, groups, mode, E._stream())
         run(); torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); run(); b.record(); torch.cuda.synchronize()

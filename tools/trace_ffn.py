@@ -7,33 +7,34 @@ import numpy as np
 import torch
 import u2gnn_b200 as U
 from u2gnn_b200 import engine as E
+from u2gnn_b200._lib import probe_lib
+PROBE = probe_lib()     # libu2gnn_b200_probe.so: the product library exports no probe / trace entry points
 
 def main():
     d, ff = 64, 2048
     pairs = 6
     M = 148 * 256 * pairs
     thr = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-    U.LIB.call("u2gnn_ffn_tc_debug", int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     g = torch.Generator(device="cuda").manual_seed(0)
     y1 = torch.randn(M, d, device="cuda", generator=g)
     W1 = torch.randn(ff, d, device="cuda", generator=g) / 8
     W2 = torch.randn(d, ff, device="cuda", generator=g) / 45
     b1 = torch.zeros(ff, device="cuda"); b2 = torch.zeros(d, device="cuda")
     gamma = torch.ones(d, device="cuda"); beta = torch.zeros(d, device="cuda")
-    nb = U.LIB.call("u2gnn_ffn_tc_packed_bytes", d, ff)
+    nb = PROBE.call("u2gnn_ffn_tc_packed_bytes", d, ff)
     packed = torch.zeros(nb, dtype=torch.uint8, device="cuda")
-    U.LIB.call("u2gnn_ffn_tc_prepare", W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), d, ff, 2.0, packed.data_ptr(), nb, E._stream())
+    PROBE.call("u2gnn_ffn_tc_prepare", W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), d, ff, 2.0, packed.data_ptr(), nb, E._stream())
     z = torch.empty_like(y1); xn = torch.empty_like(y1); st = torch.empty(M, 2, device="cuda")
     CAP = 1024
     SLOTS = 21
     tr = torch.zeros(SLOTS * CAP, dtype=torch.int32, device="cuda")
     def run():
-        U.LIB.call("u2gnn_ffn_tc_fwd", y1.data_ptr(), M, d, ff, packed.data_ptr(), 1, 2, 3, thr, gamma.data_ptr(), beta.data_ptr(),
+        PROBE.call("u2gnn_ffn_tc_fwd", y1.data_ptr(), M, d, ff, packed.data_ptr(), 1, 2, 3, thr, gamma.data_ptr(), beta.data_ptr(),
                    z.data_ptr(), st.data_ptr(), xn.data_ptr(), E._stream())
     run(); torch.cuda.synchronize()
-    U.LIB.call("u2gnn_ffn_tc_set_trace", tr.data_ptr())
+    PROBE.call("u2gnn_ffn_tc_set_trace", tr.data_ptr())
     run(); torch.cuda.synchronize()
-    U.LIB.call("u2gnn_ffn_tc_set_trace", 0)
+    PROBE.call("u2gnn_ffn_tc_set_trace", 0)
     t = tr.cpu().numpy().astype(np.int64).reshape(SLOTS, CAP)
     NC = ff // 128
     # MMA warp: per (c, i): [before h wait, after h wait]

@@ -6,6 +6,8 @@ import numpy as np
 import torch
 import u2gnn_b200 as U
 from u2gnn_b200 import engine as E
+from u2gnn_b200._lib import probe_lib
+PROBE = probe_lib()     # libu2gnn_b200_probe.so: the product library exports no probe / trace entry points
 
 d, ff = 64, 2048
 pairs = 6
@@ -15,20 +17,20 @@ g = torch.Generator(device="cuda").manual_seed(0)
 y1 = torch.randn(M, d, device="cuda", generator=g); df = torch.randn(M, d, device="cuda", generator=g); dz = torch.randn(M, d, device="cuda", generator=g)
 W1 = torch.randn(ff, d, device="cuda", generator=g) / 8; W2 = torch.randn(d, ff, device="cuda", generator=g) / 45
 b1 = torch.zeros(ff, device="cuda"); b2 = torch.zeros(d, device="cuda")
-nb = U.LIB.call("u2gnn_ffn_tc_packed_bytes", d, ff)
+nb = PROBE.call("u2gnn_ffn_tc_packed_bytes", d, ff)
 packed = torch.zeros(nb, dtype=torch.uint8, device="cuda")
-U.LIB.call("u2gnn_ffn_tc_prepare", W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), d, ff, 2.0, packed.data_ptr(), nb, E._stream())
+PROBE.call("u2gnn_ffn_tc_prepare", W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), d, ff, 2.0, packed.data_ptr(), nb, E._stream())
 dy = torch.empty_like(y1); dW1 = torch.zeros_like(W1); db1 = torch.zeros_like(b1); dW2 = torch.zeros_like(W2)
-ws = torch.empty(U.LIB.call("u2gnn_ffn_tc_bwd_workspace_bytes", M), dtype=torch.uint8, device="cuda")
+ws = torch.empty(PROBE.call("u2gnn_ffn_tc_bwd_workspace_bytes", M), dtype=torch.uint8, device="cuda")
 def run():
-    U.LIB.call("u2gnn_ffn_tc_bwd", y1.data_ptr(), df.data_ptr(), dz.data_ptr(), M, d, ff, packed.data_ptr(), 2.0, 1, 2, thr,
+    PROBE.call("u2gnn_ffn_tc_bwd", y1.data_ptr(), df.data_ptr(), dz.data_ptr(), M, d, ff, packed.data_ptr(), 2.0, 1, 2, thr,
                dy.data_ptr(), dW1.data_ptr(), db1.data_ptr(), dW2.data_ptr(), ws.data_ptr(), ws.numel(), E._stream())
 CAP, SLOTS = 1024, 64
 tr = torch.zeros(SLOTS * CAP, dtype=torch.int32, device="cuda")
 run(); torch.cuda.synchronize()
-U.LIB.call("u2gnn_ffn_tc_set_trace", tr.data_ptr())
+PROBE.call("u2gnn_ffn_tc_set_trace", tr.data_ptr())
 run(); torch.cuda.synchronize()
-U.LIB.call("u2gnn_ffn_tc_set_trace", 0)
+PROBE.call("u2gnn_ffn_tc_set_trace", 0)
 t = tr.cpu().numpy().astype(np.int64).reshape(SLOTS, CAP)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 np.save(os.path.join(ROOT, "gpurun_out", "ffn_bwd_trace.npy"), t)
