@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(256) rows_to_images_kernel(const float* __rest
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
             const float* src = which ? b : a;
+            if (!src) continue;
             uint8_t* img = (which ? ib : ia) + (size_t)tile * 16384;
             if (d == 64) {
                 float4 v[8];
@@ -79,11 +80,15 @@ extern "C" size_t u2gnn_ffn_tc_bwd_workspace_bytes(int64_t M) {
     return tiles_padded(M) * (2 * 16384 + 16 * 2048);      // two 16 KB images + 2 KB of mask words per ff chunk (ff <= 2048) per tile
 }
 
-extern "C" int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const float* dz, int64_t M, int d, int ff,
-                                const void* packed, float hidden_scale, uint64_t seed, uint32_t stream_hidden, int thr,
+extern "C" size_t u2gnn_ffn_tc_image_bytes(int64_t M) { return M < 0 ? 0 : tiles_padded(M) * 16384; }
+
+extern "C" int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const void* y1_img, const void* df_img, const float* dz, int64_t M,
+                                int d, int ff, const void* packed, float hidden_scale, uint64_t seed, uint32_t stream_hidden, int thr,
                                 float* dy1, float* dW1, float* db1, float* dW2, void* workspace, size_t workspace_bytes,
                                 u2gnn_stream_t stream) {
-    if (!y1 || !df || !dz || !packed || !dy1 || !dW1 || !db1 || !dW2 || !workspace || M < 0 || thr < 0 || thr > 255) return U2GNN_EINVAL;
+    if ((!y1 && !y1_img) || (!df && !df_img) || !dz || !packed || !dy1 || !dW1 || !db1 || !dW2 || !workspace || M < 0 || thr < 0 || thr > 255)
+        return U2GNN_EINVAL;
+    if ((y1_img && reinterpret_cast<uintptr_t>(y1_img) % 128) || (df_img && reinterpret_cast<uintptr_t>(df_img) % 128)) return U2GNN_EALIGN;
     if (workspace_bytes < u2gnn_ffn_tc_bwd_workspace_bytes(M)) return U2GNN_EWORKSPACE;
     if (reinterpret_cast<uintptr_t>(workspace) % 128) return U2GNN_EALIGN;
     if (d < 1 || d > 64 || ff < 128 || ff % 128 || ff > 2048) return U2GNN_EUNSUPPORTED;
@@ -96,7 +101,13 @@ extern "C" int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const float* d
     uint8_t* fb = xb + tp * 16384;
     uint8_t* mask = fb + tp * 16384;
     const int64_t n_tiles = (M + 127) / 128;
-    rows_to_images_kernel<<<(int)(n_tiles < 4 * U2GNN_NUM_SMS ? n_tiles : 4 * U2GNN_NUM_SMS), 256, 0, as_stream(stream)>>>(y1, df, M, d, xb, fb);
+    // operands the producers did not already leave as tile images (u2gnn_gemm_tc_rows_ln: y1, u2gnn_add_dropout_ln_bwd_ex: dF)
+    // are converted here; a null source pointer skips that tensor
+    if (!y1_img || !df_img)
+        rows_to_images_kernel<<<(int)(n_tiles < 4 * U2GNN_NUM_SMS ? n_tiles : 4 * U2GNN_NUM_SMS), 256, 0, as_stream(stream)>>>(
+            y1_img ? nullptr : y1, df_img ? nullptr : df, M, d, xb, fb);
+    if (y1_img) xb = const_cast<uint8_t*>(static_cast<const uint8_t*>(y1_img));
+    if (df_img) fb = const_cast<uint8_t*>(static_cast<const uint8_t*>(df_img));
     int rc = ffn_tc_wgrad_launch(xb, fb, M, d, ff, packed, hidden_scale, seed, stream_hidden, thr, dW1, db1, dW2, mask, as_stream(stream));
     if (rc != U2GNN_OK) return rc;
     rc = ffn_tc_dgrad_launch(dz, dy1, M, d, ff, packed, fb, mask, as_stream(stream));

@@ -163,6 +163,7 @@ struct RowsParams {
     float* z;
     float* y;
     float* stats;
+    uint8_t* y_img;       // optional: y also as bf16 swizzled [128 x 64] tile images (the FFN backward's operand format)
 };
 
 constexpr float kLnEps = 1e-5f;
@@ -314,8 +315,15 @@ __global__ void __launch_bounds__(kThreads, MINB) gemm_tc_rows_kernel(const Rows
                     const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
                     const float rstd = rsqrtf(group16_sum((dx * dx + dy * dy) + (dz * dz + dw * dw)) * (1.0f / 64.0f) + kLnEps);
                     if (ok) {
-                        reinterpret_cast<float4*>(p.y + row * 64)[l] = make_float4(dx * rstd * g4.x + b4.x, dy * rstd * g4.y + b4.y,
-                                                                                   dz * rstd * g4.z + b4.z, dw * rstd * g4.w + b4.w);
+                        const float4 yv = make_float4(dx * rstd * g4.x + b4.x, dy * rstd * g4.y + b4.y, dz * rstd * g4.z + b4.z, dw * rstd * g4.w + b4.w);
+                        reinterpret_cast<float4*>(p.y + row * 64)[l] = yv;
+                        if (p.y_img) {      // the tile image the FFN backward bulk-copies: 128-byte rows, 16-byte chunks XOR (row & 7)
+                            uint2 w;
+                            w.x = tc::pack_bf16(yv.x, yv.y);
+                            w.y = tc::pack_bf16(yv.z, yv.w);
+                            *reinterpret_cast<uint2*>(p.y_img + (size_t)(row >> 7) * 16384 + (size_t)(row & 127) * 128 +
+                                                      ((((l >> 1) ^ (int)(row & 7)) << 4) | ((l & 1) << 3))) = w;
+                        }
                         if (l == 0) *reinterpret_cast<float2*>(p.stats + 2 * row) = make_float2(mean, rstd);
                     }
                 }
@@ -798,7 +806,7 @@ extern "C" int u2gnn_gemm_tc_rows_ex(const void* A, int a_bf16, int64_t M, int K
 extern "C" int u2gnn_gemm_tc_rows_ln(const void* A, int a_bf16, int64_t M, int K, int64_t lda, const float* W, int w_kn,
                                      const float* bias, const float* res, int64_t ldres, uint64_t seed, uint32_t rng_stream,
                                      int thr, const float* gamma, const float* beta, float* z, float* y, float* stats,
-                                     u2gnn_stream_t stream) {
+                                     void* y_img, u2gnn_stream_t stream) {
     constexpr int N = 64;
     if (!A || !W || !bias || !res || !gamma || !beta || !z || !y || !stats || M < 0 || K < 1 || lda < K || ldres < N ||
         thr < 0 || thr > 255)
@@ -816,6 +824,7 @@ extern "C" int u2gnn_gemm_tc_rows_ln(const void* A, int a_bf16, int64_t M, int K
     p.res = res; p.ldres = ldres; p.keys = rng_keys(seed, rng_stream); p.thr = thr; p.low = rng_thr_low(thr);
     p.scale = thr ? rng_keep_scale(thr) : 1.0f;
     p.gamma = gamma; p.ln_beta = beta; p.z = z; p.y = y; p.stats = stats;
+    p.y_img = static_cast<uint8_t*>(y_img);
     const int kt = p.KP / 64;
     const size_t smem = 1024 + (size_t)kt * 16384 + (size_t)kt * p.NP * 128 + 128 * 272;
     if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;

@@ -267,7 +267,11 @@ __global__ void __launch_bounds__(256, 3) ln_bwd_vec_kernel(const float* __restr
                         uint2 w;
                         w.x = cvt_bf16x2(m.x, m.y);
                         w.y = cvt_bf16x2(m.z, m.w);
-                        reinterpret_cast<uint2*>(static_cast<uint16_t*>(da_) + r * D)[l] = w;
+                        if (da_bf16 == 2)      // D == 64: swizzled [128 x 64] tile images (16-byte chunks XOR (row & 7)), the FFN backward's operand format
+                            *reinterpret_cast<uint2*>(static_cast<uint8_t*>(da_) + (size_t)(r >> 7) * 16384 + (size_t)(r & 127) * 128 +
+                                                      ((((l >> 1) ^ (int)(r & 7)) << 4) | ((l & 1) << 3))) = w;
+                        else
+                            reinterpret_cast<uint2*>(static_cast<uint16_t*>(da_) + r * D)[l] = w;
                     } else {
                         reinterpret_cast<float4*>(da + r * D)[l] = m;
                     }
@@ -341,6 +345,7 @@ extern "C" int u2gnn_add_dropout_ln_bwd_ex(const float* dy, const float* z, cons
                                            u2gnn_stream_t stream) {
     if (!dy || !z || !stats || !gamma || !dz || M < 0 || d <= 0 || thr < 0 || thr > 255) return U2GNN_EINVAL;
     if (da_bf16 && !da) return U2GNN_EINVAL;
+    if (da_bf16 < 0 || da_bf16 > 2 || (da_bf16 == 2 && d != 64)) return U2GNN_EUNSUPPORTED;
     if (d > 32 * kMaxSlots) return U2GNN_EUNSUPPORTED;
     if (M == 0) return U2GNN_OK;
     if (vec_ok(d, dy, z, dz, da, gamma)) {

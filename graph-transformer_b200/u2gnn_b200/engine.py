@@ -31,6 +31,7 @@ FUSE_LN_BWD = os.environ.get("U2GNN_FUSE_EPILOGUES", "1") != "0"        # bf16 m
 LAST_STEP_BF16 = os.environ.get("U2GNN_LAST_BF16", "1") != "0"            # bf16 mode, d = 64: bf16 qkv / dqkv at the dead-row-eliminated last timestep
 FUSE_PROJ_BWD = os.environ.get("U2GNN_FUSE_PROJ_BWD", "1") != "0"         # bf16 mode, d = 64: projection input + weight gradients in one pass over the output gradient
 FUSE_INPROJ_ATTN = os.environ.get("U2GNN_FUSE_INPROJ_ATTN", "1") != "0"   # bf16 mode, d = 64: in_proj inside the attention-forward kernel (qkv written once, never re-read in the forward)
+FFN_BWD_IMAGES = os.environ.get("U2GNN_FFN_BWD_IMAGES", "1") != "0"      # bf16 mode, d = 64: y1 / dF leave their producers as bf16 tile images (no conversion pass in the FFN backward)
 FLOPS = {}    # entry point -> algorithmic flops issued while LIB.timed is active (bench.py roofline)
 BYTES = {}    # entry point -> algorithmic HBM bytes (the tensors the call must read + write once) while LIB.timed is active
 
@@ -277,10 +278,28 @@ def add_dropout_ln_fwd(res, a, M, d, drop, gamma, beta):
     return z, y, stats
 
 
-def add_dropout_ln_bwd(dy, z, stats, M, d, gamma, drop, dgamma, dbeta, want_da=True, da_bf16=False, dasum=None):
+def tile_images(M, device):
+    """Buffer for bf16 swizzled [128 x 64] tile images of an [M, 64] operand (the FFN backward's operand format), padded to whole
+    pairs of tiles; the rows past M (never written by the producers) are zeroed."""
+    nbytes = LIB.call("u2gnn_ffn_tc_image_bytes", M)
+    img = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    tail = (M // 128) * 16384
+    if tail < nbytes:
+        img[tail:].zero_()
+    return img
+
+
+def add_dropout_ln_bwd(dy, z, stats, M, d, gamma, drop, dgamma, dbeta, want_da=True, da_bf16=False, dasum=None, da_img=False):
     """da_bf16: store the dropout-masked gradient as bf16 (only when its consumers are tensor-core kernels).
-    dasum[d] += colsum(masked gradient): the bias gradient of the layer in front of the dropout, folded into this pass."""
+    dasum[d] += colsum(masked gradient): the bias gradient of the layer in front of the dropout, folded into this pass.
+    da_img (d == 64): the masked gradient is written as bf16 tile images for the FFN backward (returned as a uint8 buffer)."""
     dz = torch.empty((M, d), dtype=torch.float32, device=dy.device)
+    if da_img:
+        img = tile_images(M, dy.device)
+        _acct_bytes("u2gnn_add_dropout_ln_bwd_ex", M * (4 * d * 3 + 8 + 2 * d))
+        LIB.call("u2gnn_add_dropout_ln_bwd_ex", _ptr(dy), _ptr(z), _ptr(stats), M, d, _ptr(gamma), drop[0], drop[1], drop[2],
+                 _ptr(dz), _ptr(img), 2, _ptr(dgamma), _ptr(dbeta), _ptr(dasum), _stream())
+        return dz, img
     has_da = want_da and drop[2] > 0
     da = torch.empty((M, d), dtype=torch.bfloat16 if da_bf16 else torch.float32, device=dy.device) if has_da else None
     _acct_bytes("u2gnn_add_dropout_ln_bwd_ex", M * (4 * d * 3 + 8 + ((2 if da_bf16 else 4) * d if has_da else 0)))   # dy, z, stats -> dz (+ da)
@@ -293,19 +312,21 @@ def add_dropout_ln_bwd(dy, z, stats, M, d, gamma, drop, dgamma, dbeta, want_da=T
     return dz, (da if da is not None else dz)
 
 
-def out_proj_ln_tc(ctx, Mq, d, p, res, ldres, drop):
-    """out_proj + dropout + residual + LayerNorm1 as ONE kernel (bf16 mode, d = 64): the projection result never reaches HBM."""
+def out_proj_ln_tc(ctx, Mq, d, p, res, ldres, drop, want_img=False):
+    """out_proj + dropout + residual + LayerNorm1 as ONE kernel (bf16 mode, d = 64): the projection result never reaches HBM.
+    want_img: y1 is also written as bf16 tile images, which the FFN backward bulk-copies (no conversion pass there)."""
     dev = ctx.device
     z = torch.empty((Mq, d), dtype=torch.float32, device=dev)
     y = torch.empty((Mq, d), dtype=torch.float32, device=dev)
     stats = torch.empty((Mq, 2), dtype=torch.float32, device=dev)
-    _acct_bytes("u2gnn_gemm_tc_rows_ln", Mq * ((2 if ctx.dtype == torch.bfloat16 else 4) * d + 4 * d * 3 + 8))       # ctx, residual -> z, y, stats
+    img = tile_images(Mq, dev) if want_img else None
+    _acct_bytes("u2gnn_gemm_tc_rows_ln", Mq * ((2 if ctx.dtype == torch.bfloat16 else 4) * d + 4 * d * 3 + 8 + (2 * d if want_img else 0)))   # ctx, residual -> z, y, stats (+ y image)
     if LIB.timed is not None:
         FLOPS["u2gnn_gemm_tc_rows_ln"] = FLOPS.get("u2gnn_gemm_tc_rows_ln", 0) + 2 * Mq * d * d
     LIB.call("u2gnn_gemm_tc_rows_ln", _ptr(ctx), int(ctx.dtype == torch.bfloat16), Mq, d, d, _ptr(p["self_attn.out_proj.weight"]), 0,
              _ptr(p["self_attn.out_proj.bias"]), _ptr(res), ldres, drop[0], drop[1], drop[2], _ptr(p["norm1.weight"]),
-             _ptr(p["norm1.bias"]), _ptr(z), _ptr(y), _ptr(stats), _stream())
-    return z, y, stats
+             _ptr(p["norm1.bias"]), _ptr(z), _ptr(y), _ptr(stats), _ptr(img), _stream())
+    return z, y, stats, img
 
 
 def copy_rows(src, ld_src, dst, ld_dst, rows, d, accumulate=False, src_off=0, dst_off=0):
@@ -333,6 +354,7 @@ class LayerSaved:
     S: int = 0
     Sq: int = 0
     packed: torch.Tensor = None
+    y1_img: torch.Tensor = None
 
 
 def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, precision="fp32"):
@@ -377,7 +399,7 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
     if tc_proj and d == 64 and FUSE_OUT_PROJ_LN:
         # residual rows read in place (position 0 of each sequence when only that row is live)
         xq = None
-        z1, y1, st1 = out_proj_ln_tc(ctx, Mq, d, p, x, d if Sq == S else S * d, (seed, drop_ids[1], thr))
+        z1, y1, st1, sv.y1_img = out_proj_ln_tc(ctx, Mq, d, p, x, d if Sq == S else S * d, (seed, drop_ids[1], thr), want_img=FFN_BWD_IMAGES)
     else:
         if tc_proj:
             a = linear_tc(ctx, Mq, d, p["self_attn.out_proj.weight"], 0, d, bias=p["self_attn.out_proj.bias"])
@@ -440,8 +462,15 @@ def encoder_layer_bwd(dy2, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
     drop_scale = 256.0 / (256.0 - thr) if thr else 1.0
     # LayerNorm2 + FFN
     fold = sv.packed is not None and d in (16, 32, 64, 128) and FUSE_LN_BWD     # linear2 bias gradient inside the LayerNorm2 backward
-    dz2, df = add_dropout_ln_bwd(dy2, sv.z2, sv.st2, Mq, d, p["norm2.weight"], (seed, drop_ids[3], thr),
-                                 g["norm2.weight"], g["norm2.bias"], dasum=g["linear2.bias"] if fold else None)
+    df_img = None
+    if fold and d == 64 and sv.y1_img is not None:
+        # dF leaves the LayerNorm2 backward as bf16 tile images: the FFN backward bulk-copies them, the fp32 dF never exists
+        dz2, df_img = add_dropout_ln_bwd(dy2, sv.z2, sv.st2, Mq, d, p["norm2.weight"], (seed, drop_ids[3], thr),
+                                         g["norm2.weight"], g["norm2.bias"], dasum=g["linear2.bias"], da_img=True)
+        df = None
+    else:
+        dz2, df = add_dropout_ln_bwd(dy2, sv.z2, sv.st2, Mq, d, p["norm2.weight"], (seed, drop_ids[3], thr),
+                                     g["norm2.weight"], g["norm2.bias"], dasum=g["linear2.bias"] if fold else None)
     dy1 = dz2  # dy1 = dz2 + dhpre @ W1 (in place)
     if sv.packed is not None:
         # fused tcgen05 backward: hidden and its gradient recomputed on chip
@@ -453,9 +482,9 @@ def encoder_layer_bwd(dy2, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
             FLOPS["u2gnn_ffn_tc_bwd"] = FLOPS.get("u2gnn_ffn_tc_bwd", 0) + 8 * Mq * d * ff
         wsb = LIB.call("u2gnn_ffn_tc_bwd_workspace_bytes", Mq)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-        LIB.call("u2gnn_ffn_tc_bwd", _ptr(sv.y1), _ptr(df), _ptr(dz2), Mq, d, ff, _ptr(sv.packed), drop_scale, seed,
-                 drop_ids[2], thr, _ptr(dy1), _ptr(g["linear1.weight"]), _ptr(g["linear1.bias"]),
-                 _ptr(g["linear2.weight"]), _ptr(ws), wsb, _stream())
+        LIB.call("u2gnn_ffn_tc_bwd", _ptr(sv.y1), _ptr(df), _ptr(sv.y1_img if df_img is not None else None), _ptr(df_img), _ptr(dz2),
+                 Mq, d, ff, _ptr(sv.packed), drop_scale, seed, drop_ids[2], thr, _ptr(dy1), _ptr(g["linear1.weight"]),
+                 _ptr(g["linear1.bias"]), _ptr(g["linear2.weight"]), _ptr(ws), wsb, _stream())
     else:
         wgrad(df, Mq, d, sv.hd, ff, g["linear2.weight"], g["linear2.bias"])
         dhpre = torch.empty((Mq, ff), **f32)

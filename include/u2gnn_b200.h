@@ -111,7 +111,9 @@ int u2gnn_add_dropout_ln_bwd(const float* dy, const float* z, const float* stats
                              float* dgamma, float* dbeta, u2gnn_stream_t stream);
 /* same, with da optionally stored as bf16 (da_bf16 = 1: its consumers are tensor-core kernels that round on load, so
  * rounding once here is bit-identical at half the bytes) and dasum[d] += colsum(dz * dropout mask) (fp32 values before
- * rounding; may be null; works without da) - the bias gradient of the linear layer that produced a.  Both options need d in {16, 32, 64, 128}. */
+ * rounding; may be null; works without da) - the bias gradient of the linear layer that produced a.  Both options need d in {16, 32, 64, 128}.
+ * da_bf16 = 2 (d = 64): da is written as bf16 swizzled [128 x 64] tile images (row r -> image r / 128, 128-byte rows, 16-byte chunk
+ * index XOR (r & 7)), the operand format u2gnn_ffn_tc_bwd bulk-copies (df_img): the fp32 gradient never reaches HBM. */
 int u2gnn_add_dropout_ln_bwd_ex(const float* dy, const float* z, const float* stats, int64_t M, int d,
                                 const float* gamma, uint64_t seed, uint32_t rng_stream, int thr, float* dz, void* da,
                                 int da_bf16, float* dgamma, float* dbeta, float* dasum, u2gnn_stream_t stream);
@@ -216,11 +218,15 @@ int u2gnn_ffn_tc_fwd(const float* y1, int64_t M, int d, int ff, const void* pack
  * the linear2 output after the output dropout; dy1 may alias dz); dW1[ff,d], db1[ff], dW2[d,ff] are
  * ACCUMULATED (atomics).  db2 = colsum(df) is left to u2gnn_colsum.  workspace (128-byte aligned) holds the bf16 tile
  * images of y1 / df both tensor-core kernels read and the 1-bit ReLU-and-keep mask words the weight-gradient kernel hands
- * to the input-gradient kernel (so the hidden is recomputed once, not twice). */
+ * to the input-gradient kernel (so the hidden is recomputed once, not twice).
+ * y1_img / df_img (may be NULL): the same two operands ALREADY stored as bf16 swizzled [128 x 64] tile images of
+ * u2gnn_ffn_tc_image_bytes(M) bytes (128-byte aligned; rows >= M of the last tile zero) - what u2gnn_gemm_tc_rows_ln (y_img)
+ * and u2gnn_add_dropout_ln_bwd_ex (da_bf16 = 2) write; the fp32 pointer of an operand given as an image may be NULL. */
 size_t u2gnn_ffn_tc_bwd_workspace_bytes(int64_t M);
-int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const float* dz, int64_t M, int d, int ff, const void* packed,
-                     float hidden_scale, uint64_t seed, uint32_t stream_hidden, int thr, float* dy1, float* dW1,
-                     float* db1, float* dW2, void* workspace, size_t workspace_bytes, u2gnn_stream_t stream);
+size_t u2gnn_ffn_tc_image_bytes(int64_t M);
+int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const void* y1_img, const void* df_img, const float* dz, int64_t M, int d,
+                     int ff, const void* packed, float hidden_scale, uint64_t seed, uint32_t stream_hidden, int thr, float* dy1,
+                     float* dW1, float* db1, float* dW2, void* workspace, size_t workspace_bytes, u2gnn_stream_t stream);
 
 /* ---- bf16 tensor-core GEMMs for the attention-block projections of the bf16 mode (csrc/gemm_tc.cu): the
  *      F.linear calls inside nn.MultiheadAttention (in_proj / out_proj) and their autograd.
@@ -257,10 +263,12 @@ int u2gnn_gemm_tc_dgrad_wgrad(const void* A, int64_t M, int N1, int64_t lda, con
 /* out_proj + dropout + residual + LayerNorm1 in one kernel (torch/nn/modules/transformer.py:946,969-972:
  * x = norm1(x + dropout1(self_attn(x)))): z[M,64] = res + dropout(A[M,K] W^T + bias), y = LayerNorm(z) * gamma + beta,
  * stats[M,2] = (mean, rstd).  N = d = 64 only; res row stride ldres (elements) so the last timestep can read position 0 of
- * each sequence in place.  Same arithmetic as u2gnn_gemm_tc_rows_ex followed by u2gnn_add_dropout_ln_fwd (bit-identical). */
+ * each sequence in place.  Same arithmetic as u2gnn_gemm_tc_rows_ex followed by u2gnn_add_dropout_ln_fwd (bit-identical).
+ * y_img (may be NULL): y additionally as bf16 swizzled tile images (u2gnn_ffn_tc_image_bytes(M) bytes) for u2gnn_ffn_tc_bwd. */
 int u2gnn_gemm_tc_rows_ln(const void* A, int a_bf16, int64_t M, int K, int64_t lda, const float* W, int w_kn,
                           const float* bias, const float* res, int64_t ldres, uint64_t seed, uint32_t rng_stream, int thr,
-                          const float* gamma, const float* beta, float* z, float* y, float* stats, u2gnn_stream_t stream);
+                          const float* gamma, const float* beta, float* z, float* y, float* stats, void* y_img,
+                          u2gnn_stream_t stream);
 int u2gnn_seqattn_tc_fwd_ex(const void* qkv, int64_t B, int S, int d, uint64_t seed, uint32_t rng_stream, int thr,
                             void* ctx, int io_bf16, u2gnn_stream_t stream);
 int u2gnn_seqattn_tc_bwd_ex(const void* qkv, const void* dctx, int64_t B, int S, int d, uint64_t seed,

@@ -132,7 +132,7 @@ def test_ffn_tc_backward(U, M, d, ff, p):
     dW1 = torch.zeros((ff, d), device="cuda"); db1 = torch.zeros(ff, device="cuda"); dW2 = torch.zeros((d, ff), device="cuda")
     SEED, S2 = 0x1234ABCD99, 18
     ws = torch.empty(U.LIB.call("u2gnn_ffn_tc_bwd_workspace_bytes", M), dtype=torch.uint8, device="cuda")
-    U.LIB.call("u2gnn_ffn_tc_bwd", t["y1"].data_ptr(), t["df"].data_ptr(), t["dz"].data_ptr(), M, d, ff, packed.data_ptr(), scale,
+    U.LIB.call("u2gnn_ffn_tc_bwd", t["y1"].data_ptr(), t["df"].data_ptr(), 0, 0, t["dz"].data_ptr(), M, d, ff, packed.data_ptr(), scale,
                SEED, S2, thr, dy1.data_ptr(), dW1.data_ptr(), db1.data_ptr(), dW2.data_ptr(), ws.data_ptr(), ws.numel(), E._stream())
     torch.cuda.synchronize()
     if thr:
@@ -340,32 +340,6 @@ def test_seqattn_tc_bf16_io_matches_fp32_io(U, B, S, p):
     assert torch.equal(dq1, dq0.to(torch.bfloat16))
 
 
-@pytest.mark.parametrize("M,K,N,a_bf16,c_bf16,beta", [(1000, 64, 192, 0, 1, 0.0), (148 * 128 * 3 + 77, 64, 192, 0, 1, 0.0),
-                                                      (5000, 64, 64, 1, 0, 0.0), (4097, 192, 64, 1, 0, 1.0),
-                                                      (333, 64, 64, 0, 1, 0.0), (128, 64, 64, 0, 0, 0.0), (70000, 64, 64, 0, 0, 1.0)])
-def test_gemm_tc_rows_warp_specialised_equals_phase_serial(U, M, K, N, a_bf16, c_bf16, beta):
-    """The persistent warp-specialised projection kernel and the phase-serial one compute the same MMAs on the same
-    bf16 operands: results must be bit-identical."""
-    from u2gnn_b200 import engine as E
-    g = torch.Generator(device="cuda").manual_seed(M + K + N)
-    A = torch.randn(M, K, device="cuda", generator=g)
-    if a_bf16:
-        A = A.to(torch.bfloat16)
-    W = torch.randn(K, N, device="cuda", generator=g) / 8            # w_kn = 1 layout
-    b = torch.randn(N, device="cuda", generator=g)
-    C0 = torch.randn(M, N, device="cuda", generator=g)
-    outs = []
-    for ws in (0, 1):
-        U.LIB.call("u2gnn_gemm_tc_debug", ws)
-        C = (C0.clone() if beta else torch.empty(M, N, device="cuda")).to(torch.bfloat16 if c_bf16 else torch.float32)
-        U.LIB.call("u2gnn_gemm_tc_rows_ex", A.data_ptr(), a_bf16, M, K, K, W.data_ptr(), 1, N, b.data_ptr(), beta,
-                   C.data_ptr(), c_bf16, N, E._stream())
-        torch.cuda.synchronize()
-        outs.append(C)
-    U.LIB.call("u2gnn_gemm_tc_debug", 0)
-    assert torch.equal(outs[0], outs[1])
-    ref = A.float().to(torch.bfloat16).float() @ W.to(torch.bfloat16).float() + b + (C0 if beta else 0)
-    assert (outs[1].float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
 
 
 # ------------------------------------------------------------------ fused attention-block epilogues
@@ -390,7 +364,7 @@ def test_out_proj_ln_fused_equals_gemm_then_layernorm(U, M, S, p, a_bf16):
     a = E.linear_tc(ctx, M, d, prm["self_attn.out_proj.weight"], 0, d, bias=prm["self_attn.out_proj.bias"])
     xq = x.view(M, S, d)[:, 0, :].contiguous()
     z0, y0, st0 = E.add_dropout_ln_fwd(xq, a, M, d, drop, prm["norm1.weight"], prm["norm1.bias"])
-    z1, y1, st1 = E.out_proj_ln_tc(ctx, M, d, prm, x, S * d, drop)
+    z1, y1, st1, _ = E.out_proj_ln_tc(ctx, M, d, prm, x, S * d, drop)
     torch.cuda.synchronize()
     assert torch.equal(z1, z0)
     assert torch.equal(st1, st0)
@@ -528,3 +502,65 @@ def test_inproj_attention_fused_equals_projection_then_attention(U, B, S, p):
     assert torch.equal(ctx1, ctx0)
 
 
+
+
+# ------------------------------------------------------------------ round 2: operand tile images written by the producers
+def _image_of(rows_bf16):
+    """Expected bf16 swizzled [128 x 64] tile images of an [M, 64] bf16 tensor (rows past M zero), as bytes."""
+    M = rows_bf16.shape[0]
+    nt = 2 * ((M + 255) // 256)
+    pad = torch.zeros((nt * 128, 64), dtype=torch.bfloat16, device=rows_bf16.device)
+    pad[:M] = rows_bf16
+    chunks = pad.view(nt * 128, 8, 8)                                   # [row, 16-byte chunk, 8 bf16]
+    r = torch.arange(nt * 128, device=pad.device)
+    perm = (torch.arange(8, device=pad.device)[None, :] ^ (r[:, None] & 7))   # stored position p holds chunk p ^ (row & 7)
+    return torch.gather(chunks, 1, perm[:, :, None].expand(-1, -1, 8)).contiguous().view(torch.uint8).reshape(-1)
+
+
+@pytest.mark.parametrize("M,p", [(1000, 0.5), (128 * 7, 0.0), (148 * 128 * 3 + 77, 0.5), (5, 0.5)])
+def test_producers_write_ffn_backward_tile_images(U, M, p):
+    """u2gnn_add_dropout_ln_bwd_ex(da_bf16 = 2) and u2gnn_gemm_tc_rows_ln(y_img) write exactly the images the conversion pass of
+    u2gnn_ffn_tc_bwd would build from their row-major outputs; the FFN backward fed with them gives bit-identical dy1."""
+    from u2gnn_b200 import engine as E
+    d, ff = 64, 256
+    thr = E.dropout_threshold(p)
+    g = torch.Generator(device="cuda").manual_seed(M)
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    dy, z = rnd(M, d), rnd(M, d) * 1.3 + 0.1
+    st = torch.stack([z.mean(1), (z.var(1, unbiased=False) + 1e-5).rsqrt()], 1).contiguous()
+    gamma = 1 + 0.1 * rnd(d)
+    drop = (0xBEEF, 21, thr)
+    zg = lambda: torch.zeros(d, device="cuda")
+    dz0, da0 = E.add_dropout_ln_bwd(dy, z, st, M, d, gamma, drop, zg(), zg(), da_bf16=True, dasum=zg())
+    dz1, img = E.add_dropout_ln_bwd(dy, z, st, M, d, gamma, drop, zg(), zg(), dasum=zg(), da_img=True)
+    torch.cuda.synchronize()
+    assert torch.equal(dz0, dz1)
+    ref_rows = da0 if da0.dtype == torch.bfloat16 else dz0.to(torch.bfloat16)      # p = 0: no separate da
+    n_real = ((M + 127) // 128) * 16384
+    assert torch.equal(img[:n_real], _image_of(ref_rows)[:n_real])
+    # out_proj + LN1 with the y image
+    ctx = rnd(M, d).to(torch.bfloat16)
+    prm = {"self_attn.out_proj.weight": rnd(d, d) / 8, "self_attn.out_proj.bias": 0.1 * rnd(d), "norm1.weight": gamma, "norm1.bias": 0.1 * rnd(d)}
+    res = rnd(M, d)
+    z1, y1, s1, yimg = E.out_proj_ln_tc(ctx, M, d, prm, res, d, (0xBEEF, 22, thr), want_img=True)
+    torch.cuda.synchronize()
+    assert torch.equal(yimg[:n_real], _image_of(y1.to(torch.bfloat16))[:n_real])
+    # FFN backward: images from the producers vs the conversion pass
+    prm2 = {"linear1.weight": rnd(ff, d) / 8, "linear1.bias": 0.1 * rnd(ff), "linear2.weight": rnd(d, ff) / 16, "linear2.bias": 0.1 * rnd(d)}
+    packed = E.ffn_tc_pack(prm2, d, ff, thr)
+    scale = 256.0 / (256.0 - thr) if thr else 1.0
+    wsb = U.LIB.call("u2gnn_ffn_tc_bwd_workspace_bytes", M)
+    df_rows = ref_rows.float().contiguous()
+    outs = []
+    for use_img in (False, True):
+        dy1 = torch.empty(M, d, device="cuda")
+        dW1, db1, dW2 = torch.zeros(ff, d, device="cuda"), torch.zeros(ff, device="cuda"), torch.zeros(d, ff, device="cuda")
+        ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+        U.LIB.call("u2gnn_ffn_tc_bwd", y1.data_ptr(), df_rows.data_ptr(), yimg.data_ptr() if use_img else 0, img.data_ptr() if use_img else 0,
+                   dz1.data_ptr(), M, d, ff, packed.data_ptr(), scale, 0xBEEF, 23, thr, dy1.data_ptr(), dW1.data_ptr(), db1.data_ptr(),
+                   dW2.data_ptr(), ws.data_ptr(), wsb, E._stream())
+        outs.append((dy1, dW1, db1, dW2))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1:], outs[1][1:]):
+        assert (a - b).abs().max().item() <= 2e-4 * max(1.0, a.abs().max().item())
