@@ -240,6 +240,101 @@ __global__ void __launch_bounds__(256) ss_bwd_kernel(const float* __restrict__ d
     }
 }
 
+// Backward for small D (the unsupervised configs: D = d * L = 4 .. 16), reference loss only.  The generic kernel above gives
+// one LANE per column, so at D = 4 only 4 of 32 lanes work and every (node, sample, column) costs a shared-memory atomic
+// (8.0 ms per 258 K-node step of bench.py cfg4, 45 % of the step).  Here a lane owns SPL samples of the staged chunk: it
+// forms e_s = coef * exp(x . w_s) for them, keeps the sampled rows' gradient in REGISTERS across all nodes of its warp
+// (acc[SPL][D]) and contributes to dx through one warp reduction per node; the gradient leaves with one global atomic per
+// (warp, sample, column).
+template <int D, int SPL>
+__global__ void __launch_bounds__(256) ss_bwd_small_kernel(const float* __restrict__ dloss, const float* __restrict__ x,
+                                                           const int64_t* __restrict__ labels, int64_t N, const float* __restrict__ W,
+                                                           int64_t V, const int64_t* __restrict__ ids, int ns,
+                                                           const float* __restrict__ denom, float* __restrict__ dx,
+                                                           float* __restrict__ dW, int64_t nodes_per_block, SsExtra ex) {
+    constexpr int P = D | 1, CHUNK = 32 * SPL;
+    __shared__ float ws[CHUNK * P];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int64_t n0 = (int64_t)blockIdx.x * nodes_per_block;
+    const int64_t n1 = (n0 + nodes_per_block < N) ? n0 + nodes_per_block : N;
+    for (int s0 = 0; s0 < ns; s0 += CHUNK) {
+        const int sc = (ns - s0 < CHUNK) ? ns - s0 : CHUNK;
+        __syncthreads();
+        stage_rows(W, V, ids, ex.samp, s0, sc, D, ws);
+        __syncthreads();
+        float acc[SPL][D];
+#pragma unroll
+        for (int j = 0; j < SPL; ++j)
+#pragma unroll
+            for (int c = 0; c < D; ++c) acc[j][c] = 0.0f;
+        for (int64_t i = n0 + w; i < n1; i += warps) {
+            const int64_t y = labels[i];
+            const bool bad = y < 0 || y >= V;                 // reported through the error word, contributes nothing
+            float xr[D], dxp[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                xr[c] = x[i * D + c];
+                dxp[c] = 0.0f;
+            }
+            const float coef = bad ? 0.0f : dloss[i] / denom[i];
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) {
+                const int sl = lane + 32 * j;
+                if (sl < sc) {
+                    const float* wr = ws + sl * P;
+                    float dot = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < D; ++c) dot = fmaf(xr[c], wr[c], dot);
+                    const float e = coef * expf(dot);
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        dxp[c] = fmaf(e, wr[c], dxp[c]);
+                        acc[j][c] = fmaf(e, xr[c], acc[j][c]);
+                    }
+                }
+            }
+            float dxl = 0.0f, xl = 0.0f;                     // this lane's column (static indexing keeps the arrays in registers)
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                const float t = warp_sum(dxp[c]);
+                if (lane == c) {
+                    dxl = t;
+                    xl = xr[c];
+                }
+            }
+            if (s0 == 0) {
+                // true-class term (first chunk only): dx = g W[y], dW[y] += g x, g = -dloss
+                if (bad) {
+                    if (lane == 0 && ex.err) atomicOr(ex.err, 1);
+                    if (lane < D) dx[i * D + lane] = 0.0f;
+                } else if (lane < D) {
+                    const float g = -dloss[i];
+                    dx[i * D + lane] = g * __ldg(W + y * D + lane) + dxl;
+                    atomicAdd(dW + y * D + lane, g * xl);
+                }
+            } else if (!bad && lane < D) {
+                dx[i * D + lane] += dxl;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            const int sl = lane + 32 * j;
+            if (sl < sc) {
+                if (ex.dsamp) {
+#pragma unroll
+                    for (int c = 0; c < D; ++c) atomicAdd(ex.dsamp + (size_t)(s0 + sl) * D + c, acc[j][c]);
+                } else {
+                    const int64_t id = ids[s0 + sl];
+                    if (id >= 0 && id < V) {
+#pragma unroll
+                        for (int c = 0; c < D; ++c) atomicAdd(dW + id * D + c, acc[j][c]);
+                    }
+                }
+            }
+        }
+    }
+}
+
 int pick_chunk(int ns, int D, int copies) {
     const int P = D | 1;
     int chunk = kChunkFloats / (P * copies);
@@ -276,6 +371,15 @@ int launch_ss_bwd(bool is_tf, const float* dloss, const float* x, const int64_t*
                   const int64_t* ids, int ns, const float* denom, float* dx, float* dW, TfArgs tf, SsExtra ex, cudaStream_t st) {
     if (D > 1024) return U2GNN_EUNSUPPORTED;
     if (N == 0) return U2GNN_OK;
+    if (!is_tf && (D == 4 || D == 8 || D == 16)) {
+        const int grid = grid_for(N, 64, 2);
+        const int64_t npb = ceil_div64(N, grid);
+        const unsigned blocks = (unsigned)ceil_div64(N, npb);
+        if (D == 4) ss_bwd_small_kernel<4, 16><<<blocks, 256, 0, st>>>(dloss, x, labels, N, W, V, ids, ns, denom, dx, dW, npb, ex);
+        else if (D == 8) ss_bwd_small_kernel<8, 8><<<blocks, 256, 0, st>>>(dloss, x, labels, N, W, V, ids, ns, denom, dx, dW, npb, ex);
+        else ss_bwd_small_kernel<16, 4><<<blocks, 256, 0, st>>>(dloss, x, labels, N, W, V, ids, ns, denom, dx, dW, npb, ex);
+        U2GNN_CHECK_LAUNCH();
+    }
     const int threads = 256, warps = threads / 32;
     int chunk = pick_chunk(ns, D, 2);
     // es needs warps*chunk floats on top of the two staged copies (+ 3 chunk for the TF offsets / bias gradients / ids)
