@@ -50,6 +50,13 @@ WORKLOADS = {
     "cfg5": dict(kind="sup", d=64, k=16, T=4, L=1, ff=2048, C=2, axis="neighbors", nodes=262144, avg_graph=61, precision="bf16",
                  desc="cfg5-shape synthetic graph batch: supervised U2GNN, d 64, num_neighbors 16, T 4, L 1, ff 2048, "
                       "attn_axis=neighbors (BASELINE.json configs[4])"),
+    # one PASS over a rank's share of the 64 M-node / 1 B-edge graph (8 M nodes, ~125 M directed edges per rank: the full graph at 8
+    # GPUs), dataset CSR + features resident in HBM, every micro-batch built on the device INSIDE the timed region
+    "cfg5-full": dict(kind="epoch", d=64, k=16, T=4, L=1, ff=2048, C=2, axis="neighbors", nodes=262144, avg_graph=61, precision="bf16",
+                      nodes_per_rank=8 * 1024 * 1024, mean_degree=15.6,
+                      desc="cfg5 full pass: 8 Mi nodes / ~125 M directed edges per rank (64 Mi nodes / 1 B edges at 8 GPUs), power-law degrees, "
+                           "graphs of ~61 nodes, supervised U2GNN d 64, num_neighbors 16, T 4, L 1, ff 2048; micro-batches of <= 262144 nodes "
+                           "built on the device (CSR neighbour sampling + feature gather) inside the timed region (BASELINE.json configs[4])"),
 }
 # entry points timed per launch for the HBM-side roofline list (north_star: gather / attention / pooling kernels)
 HBM_KERNELS = ("u2gnn_gather_rows", "u2gnn_inproj_seqattn_tc_fwd", "u2gnn_seqattn_tc_bwd_ex", "u2gnn_segment_sum",
@@ -251,6 +258,126 @@ def _tree_dataset(w, seed, device):
     X[torch.arange(V, device=device), deg % w["d"]] = 1.0
     X = X * 0.99 + 0.01
     return rowptr, dst.contiguous(), gstart, X
+
+
+def _powerlaw_dataset(w, n_nodes, seed, device):
+    """Graph-sharded share of the cfg5 graph, generated in HBM: graphs of ~avg_graph nodes, per-node degree ~ Pareto (alpha 2.1)
+    clipped to [1, graph size - 1] and scaled to the target mean, neighbours uniform inside the node's graph (no cross-rank
+    edges).  -> (rowptr int64 [V+1], col int64 [E], gstart int64 [G+1], X f32 [V, d], labels int64 [G])."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    avg = w["avg_graph"]
+    G = n_nodes // avg
+    sizes = torch.randint(avg // 2, avg + avg // 2 + 1, (G,), generator=g, device=device, dtype=torch.int64)
+    sizes[-1] += n_nodes - int(sizes.sum().item())
+    gstart = torch.zeros(G + 1, dtype=torch.int64, device=device)
+    gstart[1:] = torch.cumsum(sizes, 0)
+    gid = torch.repeat_interleave(torch.arange(G, device=device), sizes)
+    size = sizes[gid]
+    u = torch.rand(n_nodes, generator=g, device=device).clamp_(min=1e-7)
+    pareto = u.pow_(-1.0 / 1.1)                                   # density ~ x^-2.1 on [1, inf)
+    lo, hi = 0.5, 32.0
+    for _ in range(24):                                           # scale so the clipped mean hits the target
+        mid = 0.5 * (lo + hi)
+        mean = torch.minimum((pareto * mid).floor().clamp_(min=1), (size - 1).float()).mean().item()
+        lo, hi = (mid, hi) if mean < w["mean_degree"] else (lo, mid)
+    deg = torch.minimum((pareto * hi).floor().clamp_(min=1), (size - 1).float()).long()
+    del pareto, u
+    rowptr = torch.zeros(n_nodes + 1, dtype=torch.int64, device=device)
+    rowptr[1:] = torch.cumsum(deg, 0)
+    E_ = int(rowptr[-1].item())
+    src = torch.repeat_interleave(torch.arange(n_nodes, device=device), deg)
+    col = gstart[gid[src]] + (torch.rand(E_, generator=g, device=device) * sizes[gid[src]].float()).long().clamp_(max=10 ** 9)
+    col = torch.minimum(col, gstart[gid[src] + 1] - 1)
+    del src
+    X = torch.randn((n_nodes, w["d"]), generator=g, device=device)
+    labels = torch.randint(0, w["C"], (G,), generator=g, device=device, dtype=torch.int64)
+    return rowptr, col.contiguous(), gstart, X, labels, float(deg.float().mean().item())
+
+
+def run_full_epoch(args, w):
+    """cfg5-full: ONE pass over this rank's share of the big graph.  The dataset (CSR adjacency + features) lives in HBM; every
+    micro-batch is built by the device batch builder (u2gnn_build_batch + u2gnn_gather_rows) and trained inside the timed region,
+    so input generation, neighbour sampling and load balance are part of the number.  Every rank runs the same number of
+    micro-batches (balanced by node count) because each step ends in the gradient all-reduce."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sys.path.insert(0, PKG)
+    import u2gnn_b200 as U
+    from u2gnn_b200 import engine as E
+    from u2gnn_b200 import parallel as P
+    from u2gnn_b200.data import DeviceBatchBuilder
+    from u2gnn_b200.trainer import SupTrainer
+    U.require_device()
+    dev = torch.device("cuda", local)
+    V = args.full_nodes or w["nodes_per_rank"]
+    rowptr, col, gstart, X, labels, mean_deg = _powerlaw_dataset(w, V, 2024 + rank, dev)
+    edges = int(col.numel())
+    ds = DeviceBatchBuilder.from_device_tensors(rowptr, col, gstart, X, w["k"], seed=7, labels=labels.cpu().numpy())
+    torch.manual_seed(123)
+    model = U.TransformerU2GNN(w["d"], w["ff"], w["C"], w["T"], 0.5, w["L"], attn_axis=w["axis"]).cuda()
+    trainer = SupTrainer(model, lr=5e-4, precision=args.precision or w["precision"])
+    nb = (V + w["nodes"] - 1) // w["nodes"]
+    ranges = P.balanced_graph_ranges(gstart, nb)                  # nb micro-batches of whole graphs, balanced by node count
+    G_total = sum(r[1] - r[0] for r in ranges) * world            # per-step loss normalisation is per micro-batch below
+    import numpy as np
+
+    def epoch(limit=None):
+        done = 0
+        loss = None
+        for i, (g0, g1) in enumerate(ranges[:limit]):
+            ix, rp, Xc, y, _ = ds.build(np.arange(g0, g1), stream_id=i)
+            loss = trainer.step(ix, rp, Xc, y, G_total=(g1 - g0) * world)
+            done += int(Xc.shape[0])
+        return done, loss
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    epoch(limit=3)                                                # warm-up: 3 micro-batches
+    sync()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    U.LIB.launches = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    done, loss = epoch()
+    e1.record()
+    sync()
+    E.check_device_errors()
+    launches = U.LIB.launches
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    n = torch.tensor([float(done)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    ms, total = float(t.item()), float(n.item())
+    if rank == 0:
+        flops_node, bytes_node = algorithmic_per_node(w["d"], w["k"] + 1, w["T"], w["ff"], w["L"])
+        line = {"metric": METRIC, "value": total / (ms / 1e3), "unit": "nodes/s", "n_gpus": world, "steps": nb, "warmup": 3,
+                "ms_per_step": ms / nb, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": workload_config(args, w, int(total / nb / world),
+                                          {"precision": args.precision or w["precision"], "parallelism": "dp%d" % world,
+                                           "nodes_per_rank": V, "directed_edges_per_rank": edges, "mean_degree": mean_deg,
+                                           "micro_batches_per_rank": nb, "epoch_s": ms / 1e3, "loss": float(loss.item()),
+                                           "dataset_bytes_in_hbm_per_rank": int(rowptr.numel() * 8 + col.numel() * 8 + X.numel() * 4),
+                                           "algorithmic_mflop_per_node": flops_node / 1e6, "algorithmic_bytes_per_node": bytes_node,
+                                           "timed_region": "whole pass: device batch build (neighbour sampling, feature gather) + train step per micro-batch"}),
+                "clocks": clk, "gpu_launches": launches,
+                "e2e": {"value": total / (ms / 1e3), "unit": "nodes/s", "h2d_bytes_per_step": int(16 * (len(ranges[0]) + 2) * 0 + 2 * 8 * (ranges[0][1] - ranges[0][0] + 1)),
+                        "d2h_bytes_per_step": 0, "note": "the dataset is resident in HBM; per micro-batch only the graph offsets travel host->device"}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_ours(args, w):
@@ -490,6 +617,7 @@ def main():
     ap.add_argument("--nodes", type=int, default=int(os.environ.get("U2GNN_BENCH_NODES", 0)),
                     help="nodes per rank per step (default: the workload's)")
     ap.add_argument("--graphs-per-step", type=int, default=0, help="cfg4: graphs per rank per step")
+    ap.add_argument("--full-nodes", type=int, default=0, help="cfg5-full: nodes per rank (default 8 Mi)")
     ap.add_argument("--cpu-nodes", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -498,6 +626,8 @@ def main():
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, w)
+    elif w["kind"] == "epoch":
+        run_full_epoch(args, w)
     else:
         run_ours(args, w)
 
