@@ -13,7 +13,9 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import u2gnn_b200 as U                                    # noqa: E402
-from u2gnn_b200.data import build_batch, load_data, separate_data   # noqa: E402
+from u2gnn_b200 import engine as E                        # noqa: E402
+from u2gnn_b200.data import DeviceBatchBuilder, build_batch, load_data, separate_data   # noqa: E402
+from u2gnn_b200.parallel import balanced_graph_ranges, shard_graph_batch   # noqa: E402
 from u2gnn_b200.evaluate import ConditionalStepLR, sup_accuracy   # noqa: E402
 from u2gnn_b200.trainer import SupTrainer                 # noqa: E402
 
@@ -43,6 +45,12 @@ def parse_args(argv=None):
                    help="share ONE encoder weight set across the T timesteps (the published Universal-Transformer U2GNN); "
                         "default = T independent sets like the reference PyTorch file")
     p.add_argument("--dataset_root", default=None)
+    p.add_argument("--batch_builder", default="host", choices=["host", "device"],
+                   help="host: the reference's numpy loop (reproduces its index stream bit for bit); device: dataset resident in HBM, "
+                        "neighbours sampled by the CUDA batch builder (counter-based stream, no host loop)")
+    p.add_argument("--world_size", default=1, type=int,
+                   help="data-parallel ranks (launch with torchrun; every rank draws the same graph batch and trains on its balanced share, "
+                        "gradients are all-reduced over NCCL)")
     return p.parse_args(argv)
 
 
@@ -51,7 +59,22 @@ def run(args, log=print):
     np.random.seed(123)
     torch.cuda.manual_seed_all(123)
     U.require_device()
-    dev = torch.device("cuda")
+    world, rank = max(1, args.world_size), 0
+    if world > 1:
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if dist.get_world_size() != world:
+            raise ValueError("--world_size %d but torchrun started %d ranks" % (world, dist.get_world_size()))
+        rank = dist.get_rank()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if world > 1 and args.attn_axis == "nodes":
+        raise ValueError("attn_axis='nodes' couples every node of a batch (SURVEY.md F1): a batch cannot be sharded across ranks; "
+                         "use --attn_axis neighbors with --world_size > 1")
+    if rank != 0:
+        log = lambda *a, **k: None
     log(args)
     degree_as_tag = args.degree_as_tag or args.dataset in ("COLLAB", "IMDBBINARY", "IMDBMULTI")
     graphs, num_classes = load_data(args.dataset, degree_as_tag, args.dataset_root)
@@ -72,13 +95,32 @@ def run(args, log=print):
         ix, rp, X, y = batch
         return (torch.from_numpy(ix).to(dev), torch.from_numpy(rp).to(dev), torch.from_numpy(X).to(dev), torch.from_numpy(y).to(dev))
 
+    builder = DeviceBatchBuilder(train_graphs, args.num_neighbors, device=dev, seed=123) if args.batch_builder == "device" else None
+    if builder is not None and reddit:
+        builder.X = (builder.X.repeat(1, reddit) * 0.01).contiguous()       # the reference's REDDIT feature rule (train_pytorch_U2GNN_Sup.py:93-95)
+
+    def train_batch(sel):
+        """One global batch `sel` (the same on every rank: the numpy stream is seeded identically) -> this rank's share."""
+        G = len(sel)
+        if builder is not None:
+            sizes = np.array([train_graphs[i].n for i in sel])
+            g0, g1 = balanced_graph_ranges(torch.from_numpy(np.concatenate([[0], np.cumsum(sizes)])), world)[rank]
+            ix, rp, X, y, _ = builder.build(np.asarray(sel)[g0:g1])
+            return ix, rp, X, y, G
+        ix, rp, X, y = to_dev(build_batch([train_graphs[i] for i in sel], args.num_neighbors, np.random, reddit))
+        if world > 1:
+            sh = shard_graph_batch(ix, rp, X, y, rank, world)
+            ix, rp, X, y = sh["input_x"], sh["rowptr"], sh["X"], sh["labels"]
+        return ix, rp, X, y, G
+
     def train_epoch():
         model.train()
         total = 0.0
         for _ in range(steps_per_epoch):
             sel = np.random.permutation(len(train_graphs))[:args.batch_size]
-            ix, rp, X, y = to_dev(build_batch([train_graphs[i] for i in sel], args.num_neighbors, np.random, reddit))
-            total += float(trainer.step(ix, rp, X, y).item())
+            ix, rp, X, y, G = train_batch(sel)
+            total += float(trainer.step(ix, rp, X, y, G_total=G).item())      # loss.item(): the reference's per-step device sync
+            E.check_device_errors(dev)
         return total
 
     def evaluate():
@@ -90,10 +132,14 @@ def run(args, log=print):
     os.makedirs(ckpt, exist_ok=True)
     accs, losses = [], []
     sched = ConditionalStepLR(args.learning_rate, steps_per_epoch)
-    with open(os.path.join(ckpt, "model_acc.txt"), "w") as w:
+    with open(os.path.join(ckpt, "model_acc.txt") if rank == 0 else os.devnull, "w") as w:
         for epoch in range(1, args.num_epochs + 1):
             t0 = time.time()
             loss = train_epoch()
+            if world > 1:                            # every rank holds its share of the (globally normalised) loss
+                t = torch.tensor([loss], device=dev, dtype=torch.float64)
+                torch.distributed.all_reduce(t)
+                loss = float(t.item())
             losses.append(loss)
             acc = evaluate()
             accs.append(acc)
