@@ -50,4 +50,21 @@ __device__ __forceinline__ void keep_masks16(uint32_t keep, uint32_t (&m)[16]) {
     }
 }
 
+// "split-pair" word (bit j = element 2j, bit 16 + j = element 2j + 1: what one LOP3 per register pair builds from the
+// set.gt masks of packed values) -> 16 pair masks (0xFFFF per set element).  The mask words the FFN kernels exchange use
+// this bit order over the 32 hidden units of a group.
+__device__ __forceinline__ void split_masks16(uint32_t w, uint32_t (&m)[16]) {
+    uint32_t sh[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) sh[s] = w << s;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const uint32_t lo = 8u | (uint32_t)(j >> 3), hi = 8u | (uint32_t)(2 + (j >> 3));
+        m[j] = prmt(sh[7 - (j & 7)], 0u, (hi << 12) | (hi << 8) | (lo << 4) | lo);
+    }
+}
+// position of element e in a split-pair word, and its inverse
+__device__ __forceinline__ int split_pos(int e) { return (e & 1) * 16 + (e >> 1); }
+__device__ __forceinline__ int split_elem(int b) { return (b < 16) ? 2 * b : 2 * (b - 16) + 1; }
+
 }  // namespace epi

@@ -56,6 +56,7 @@ struct FwdParams {
     float* z;
     float* stats;
     float* xnext;
+    uint32_t* mask;      // EMIT: [n_pairs * 2][ff / 128][4][128] mask words (see ffn_tc_wgrad.cu)
     uint32_t* trace;     // debug: per-warp clock stamps of CTA 0 (u2gnn_ffn_tc_set_trace); null in production
 };
 constexpr int TRACE_CAP = 1024;   // stamps per warp slot (0 = MMA warp, 1..16 = chunk-epilogue warps, 17..20 = I/O warps)
@@ -142,7 +143,7 @@ __device__ __forceinline__ void commit_to(uint64_t* bar) {
 //                (Y + bias, dropout, residual from the staging row, LayerNorm) whose z / xnext rows leave through
 //                per-row bulk stores - no uncoalesced global access anywhere
 //   warp 20      weight producer (16 KB bulk copies, W1c(0) W2c(0) W1c(1) W2c(1) ...), warp 21 MMA issuer + TMEM owner
-template <bool TRACE, bool HALVES>
+template <bool TRACE, bool EMIT>      // EMIT: write the 1-bit ReLU-and-keep mask of every hidden activation for the backward kernels
 __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint32_t tr_n = 0;
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams
             tc::mbar_init(&bars.x_full[i], 4);
             tc::mbar_init(&bars.x_free[i], 1);
             tc::mbar_init(&bars.s_full[i], 1);
-            tc::mbar_init(&bars.h_full[i], HALVES ? kEpiWarps / 2 : kEpiWarps);
+            tc::mbar_init(&bars.h_full[i], kEpiWarps);
             tc::mbar_init(&bars.y_full[i], 1);
             tc::mbar_init(&bars.y_free[i], 4);
         }
@@ -285,53 +286,6 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams
             const uint64_t row = (uint64_t)(pair * (2 * TM) + (int64_t)i * TM + tr);
             return rng_keep_word_lo(keys2, row * g_per_row + (uint64_t)(4 * c + cq), thr, low);
         };
-        if constexpr (HALVES) {
-            // 8 warps per tile, 64 columns per warp as two 32-column passes (one barrier wait / arrive per chunk): the
-            // two tiles' warps share every scheduler, so one tile's tcgen05.ld latency hides under the other's arithmetic
-            const int i = ew >> 3, wg = (ew >> 2) & 1;      // tile of the pair, 64-column half of the chunk
-            const uint32_t s_addr = tmem + lane_base + COL_S + 128 * i + 64 * wg;
-            const uint32_t b1h = tc::smem_u32(sB1h) + 128u * wg;
-            for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-                const uint64_t row = (uint64_t)(pair * (2 * TM) + (int64_t)i * TM + tr);
-                for (int c = 0; c < NC; ++c, ++scount) {
-                    uint32_t kw[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
-                    if (thr) {
-                        const uint64_t g = row * g_per_row + (uint64_t)(4 * c + 2 * wg);
-                        kw[0] = rng_keep_word_lo(keys2, g, thr, low);
-                        kw[1] = rng_keep_word_lo(keys2, g + 1, thr, low);
-                    }
-                    stamp(ew + 1);
-                    tc::mbar_wait_addr(bar_s + 8u * i, scount & 1);
-                    stamp(ew + 1);
-                    tc::tc_fence_after();
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint32_t v[32];
-                        tc::tmem_ld32(s_addr + 32 * h, v);
-                        uint32_t km[16], bw[16];
-                        if (thr) epi::keep_masks16(kw[h], km);
-#pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4)
-                            tc::lds128(b1h + (uint32_t)c * 256u + 64u * h + 16u * q4, bw[4 * q4], bw[4 * q4 + 1], bw[4 * q4 + 2], bw[4 * q4 + 3]);
-                        tc::tmem_ld_wait();
-                        if (h == 0) stamp(ew + 1);
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            uint32_t h2 = epi::relu_bias2(epi::cvt2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bw[j]);
-                            if (thr) h2 &= km[j];
-                            v[j] = h2;
-                        }
-                        if (h == 1) stamp(ew + 1);
-                        tc::tmem_st16(s_addr + 32 * h, v);
-                    }
-                    tc::tmem_st_wait();
-                    tc::tc_fence_before();
-                    __syncwarp();
-                    if (leader) tc::mbar_arrive_addr(bar_h + 8u * i);
-                    stamp(ew + 1);
-                }
-            }
-        } else
         for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
             for (int c = 0; c < NC; ++c, ++scount) {
 #pragma unroll
@@ -354,14 +308,17 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams
                         tc::lds128(b1_addr + (uint32_t)c * 256u + 16u * q4, bw[4 * q4], bw[4 * q4 + 1], bw[4 * q4 + 2], bw[4 * q4 + 3]);
                     tc::tmem_ld_wait();
                     stamp(ew + 1);
+                    uint32_t nz = 0;                   // "split-pair" mask word: bit j = hidden 2j of the group is live and kept, bit 16 + j = hidden 2j + 1
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         uint32_t h2 = epi::relu_bias2(epi::cvt2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bw[j]);
                         if (thr) h2 &= km[j];
                         v[j] = h2;                                 // in place: entries 2j, 2j+1 are already consumed
+                        if (EMIT) nz |= epi::gt0_mask2(h2) & (0x00010001u << j);
                     }
                     stamp(ew + 1);
                     tc::tmem_st16(s_addr, v);          // packed H over the first 16 of this thread's own 32 S columns
+                    if (EMIT) p.mask[(((size_t)(pair * 2 + i) * NC + c) * 4 + cq) * TM + tr] = nz;      // 128 bytes per warp, coalesced
                     tc::tmem_st_wait();
                     tc::tc_fence_before();
                     __syncwarp();
@@ -596,7 +553,7 @@ extern "C" int u2gnn_ffn_tc_prepare(const float* W1, const float* b1, const floa
 
 extern "C" int u2gnn_ffn_tc_fwd(const float* y1, int64_t M, int d, int ff, const void* packed, uint64_t seed,
                                 uint32_t stream_hidden, uint32_t stream_out, int thr, const float* gamma,
-                                const float* beta, float* z, float* stats, float* xnext, u2gnn_stream_t stream) {
+                                const float* beta, float* z, float* stats, float* xnext, void* mask_out, u2gnn_stream_t stream) {
     if (!y1 || !packed || !gamma || !beta || !z || M < 0 || thr < 0 || thr > 255) return U2GNN_EINVAL;
     if (d < 1 || d > DP || ff < CH || ff % CH || ff > 8192) return U2GNN_EUNSUPPORTED;
     if (d == DP && ((reinterpret_cast<uintptr_t>(y1) | reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(xnext)) % 16))
@@ -611,6 +568,7 @@ extern "C" int u2gnn_ffn_tc_fwd(const float* y1, int64_t M, int d, int ff, const
     p.low = rng_thr_low(thr);
     p.scale3 = thr ? rng_keep_scale(thr) : 1.0f;
     p.gamma = gamma; p.beta = beta; p.z = z; p.stats = stats; p.xnext = xnext;
+    p.mask = static_cast<uint32_t*>(mask_out);
     const size_t smem = 1024 + (size_t)STAGES * STAGE_BYTES + 4 * (size_t)XS_TILE_BYTES + (size_t)(ff / 2 + 3 * DP) * sizeof(float);
     if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
     p.trace = nullptr;
@@ -623,10 +581,12 @@ extern "C" int u2gnn_ffn_tc_fwd(const float* y1, int64_t M, int d, int ff, const
 #ifdef U2GNN_PROBE_BUILD
     p.trace = g_ffn_trace;
     if (p.trace) {
-        launch(ffn_tc_fwd_kernel<true, false>, kThreads);
+        if (p.mask) launch(ffn_tc_fwd_kernel<true, true>, kThreads);
+        else launch(ffn_tc_fwd_kernel<true, false>, kThreads);
         U2GNN_CHECK_LAUNCH();
     }
 #endif
-    launch(ffn_tc_fwd_kernel<false, false>, kThreads);
+    if (p.mask) launch(ffn_tc_fwd_kernel<false, true>, kThreads);
+    else launch(ffn_tc_fwd_kernel<false, false>, kThreads);
     U2GNN_CHECK_LAUNCH();
 }

@@ -24,7 +24,7 @@ int ffn_tc_dgrad_launch(const float* dz, float* dy1, int64_t M, int d, int ff, c
                         cudaStream_t st);
 int ffn_tc_wgrad_launch(const void* xb, const void* fb, int64_t M, int d, int ff, const void* packed, float hidden_scale,
                         uint64_t seed, uint32_t stream_hidden, int thr, float* dW1, float* db1, float* dW2, void* mask,
-                        cudaStream_t st);
+                        bool mask_from_forward, cudaStream_t st);
 
 namespace {
 
@@ -81,9 +81,11 @@ extern "C" size_t u2gnn_ffn_tc_bwd_workspace_bytes(int64_t M) {
 }
 
 extern "C" size_t u2gnn_ffn_tc_image_bytes(int64_t M) { return M < 0 ? 0 : tiles_padded(M) * 16384; }
+extern "C" size_t u2gnn_ffn_tc_mask_bytes(int64_t M, int ff) { return (M < 0 || ff < 128) ? 0 : tiles_padded(M) * (size_t)(ff / 128) * 2048; }
 
-extern "C" int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const void* y1_img, const void* df_img, const float* dz, int64_t M,
-                                int d, int ff, const void* packed, float hidden_scale, uint64_t seed, uint32_t stream_hidden, int thr,
+extern "C" int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const void* y1_img, const void* df_img, const void* fwd_mask,
+                                const float* dz, int64_t M, int d, int ff, const void* packed, float hidden_scale, uint64_t seed,
+                                uint32_t stream_hidden, int thr,
                                 float* dy1, float* dW1, float* db1, float* dW2, void* workspace, size_t workspace_bytes,
                                 u2gnn_stream_t stream) {
     if ((!y1 && !y1_img) || (!df && !df_img) || !dz || !packed || !dy1 || !dW1 || !db1 || !dW2 || !workspace || M < 0 || thr < 0 || thr > 255)
@@ -108,7 +110,9 @@ extern "C" int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const void* y1
             y1_img ? nullptr : y1, df_img ? nullptr : df, M, d, xb, fb);
     if (y1_img) xb = const_cast<uint8_t*>(static_cast<const uint8_t*>(y1_img));
     if (df_img) fb = const_cast<uint8_t*>(static_cast<const uint8_t*>(df_img));
-    int rc = ffn_tc_wgrad_launch(xb, fb, M, d, ff, packed, hidden_scale, seed, stream_hidden, thr, dW1, db1, dW2, mask, as_stream(stream));
+    if (fwd_mask) mask = const_cast<uint8_t*>(static_cast<const uint8_t*>(fwd_mask));      // written by u2gnn_ffn_tc_fwd(mask_out): nothing to recompute
+    int rc = ffn_tc_wgrad_launch(xb, fb, M, d, ff, packed, hidden_scale, seed, stream_hidden, thr, dW1, db1, dW2, mask, fwd_mask != nullptr,
+                                 as_stream(stream));
     if (rc != U2GNN_OK) return rc;
     rc = ffn_tc_dgrad_launch(dz, dy1, M, d, ff, packed, fb, mask, as_stream(stream));
     if (rc != U2GNN_OK) return rc;

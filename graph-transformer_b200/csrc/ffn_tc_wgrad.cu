@@ -40,7 +40,8 @@ struct Params {
     float* dW1;   // [ff, d]
     float* db1;   // [ff]
     float* dW2;   // [d, ff]
-    uint32_t* mask;    // [n_tiles][ff / 128][4][128] words: bit u of word (tile, chunk, q, row) = hidden unit 128 chunk + 32 q + u of that row is live (may be null)
+    uint32_t* mask;    // [n_tiles][ff / 128][4][128] words: word (tile, chunk, q, row) holds the live-and-kept bits of hidden units
+                       // 128 chunk + 32 q + [0, 32) of that row in split-pair order (ffn_epi.cuh).  FWD_MASK: read; else written (may be null)
     uint32_t* trace;   // debug clock stamps of CTA 0 (probe build only)
 };
 constexpr int TRACE_CAP = 1024;
@@ -89,19 +90,9 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
     }
     return x;
 }
-// "split-pair" word (bit j = element 2j, bit 16 + j = element 2j + 1) -> 16 pair masks (0xFFFF per set element)
-__device__ __forceinline__ void split_masks16(uint32_t w, uint32_t (&m)[16]) {
-    uint32_t sh[8];
-#pragma unroll
-    for (int s = 0; s < 8; ++s) sh[s] = w << s;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const uint32_t lo = 8u | (uint32_t)(j >> 3), hi = 8u | (uint32_t)(2 + (j >> 3));
-        m[j] = epi::prmt(sh[7 - (j & 7)], 0u, (hi << 12) | (hi << 8) | (lo << 4) | lo);
-    }
-}
-
-template <bool TRACE>
+// FWD_MASK: the forward kernel already left the mask words (ffn_tc.cu, EMIT); this kernel then neither evaluates the dropout
+// stream nor extracts / writes the mask - it loads the 32 words of its (32 rows x 32 hidden units) block and transposes them.
+template <bool TRACE, bool FWD_MASK>
 __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint32_t tr_n = 0;
@@ -241,12 +232,24 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params 
                 bb = epi::cvt2(b, b);
             }
             uint32_t nz_cur = 0, nz_prev = 0;               // split-pair words: bit j = row 2j of the group is live, bit 16 + j = row 2j + 1
+            uint32_t mw_next = 0;                           // FWD_MASK: mask word of this lane's row in the NEXT tile
+            if (FWD_MASK) mw_next = __ldg(p.mask + (((size_t)slice * NC + c) * 4 + wq) * TM + 32 * cg + lane);
             auto phase_a = [&](int64_t n) {                // S^T(n) -> H^T = relu(bf16(S^T) + b1) & keep, packed over R_i
                 const uint32_t i = (uint32_t)(n & 1);
                 const int64_t tile = (int64_t)slice + n * n_slices;
                 const int64_t row0 = tile * TM + 32 * cg;
-                uint32_t kw = 0xFFFFFFFFu;                  // bit r = this hidden unit is kept in row row0 + r
-                if (thr) kw = transpose32(rng_keep_word_lo(keys2, (uint64_t)(row0 + lane) * g_per_row + (uint64_t)(4 * c + wq), thr, low), lane);
+                uint32_t kw = 0xFFFFFFFFu;                  // bit r = this hidden unit is kept (FWD_MASK: kept AND live) in row row0 + r
+                if (FWD_MASK) {
+                    // lane j holds the word of row row0 + j (loaded one tile AHEAD: a load issued here would expose its full
+                    // latency); after the transpose lane k holds the row bits of the hidden unit at split-pair position k, so
+                    // hidden unit `lane` fetches them from lane split_pos(lane)
+                    const uint32_t w = mw_next;
+                    if (n + 1 < my_tiles)
+                        mw_next = __ldg(p.mask + (((size_t)(tile + n_slices) * NC + c) * 4 + wq) * TM + 32 * cg + lane);
+                    kw = __shfl_sync(0xffffffffu, transpose32(w, lane), epi::split_pos(lane));
+                } else if (thr) {
+                    kw = transpose32(rng_keep_word_lo(keys2, (uint64_t)(row0 + lane) * g_per_row + (uint64_t)(4 * c + wq), thr, low), lane);
+                }
                 stamp(warp - 3);
                 tc::mbar_wait(&bars.s_full[i], (uint32_t)(n >> 1) & 1);
                 stamp(warp - 3);
@@ -254,27 +257,27 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params 
                 uint32_t v[32];
                 tc::tmem_ld32(r_addr0 + 128 * i, v);
                 uint32_t km[16];
-                if (thr) epi::keep_masks16(kw, km);
+                if (FWD_MASK || thr) epi::keep_masks16(kw, km);
                 tc::tmem_ld_wait();
                 uint32_t nz = 0;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     uint32_t h2 = epi::relu_bias2(epi::cvt2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bb);
-                    if (thr) h2 &= km[j];
+                    if (FWD_MASK || thr) h2 &= km[j];
                     v[j] = h2;
-                    nz |= epi::gt0_mask2(h2) & (0x00010001u << j);
+                    if (!FWD_MASK) nz |= epi::gt0_mask2(h2) & (0x00010001u << j);
                 }
                 tc::tmem_st16(r_addr0 + 128 * i, v);       // packed H^T over the first 16 of this warp's own 32 columns
                 tc::tmem_st_wait();
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&bars.a_done[i]);
-                nz_cur = nz;
-                if (p.mask) {
-                    // lane k now holds the word of row pi(k) (k < 16: row 2k, else row 2(k - 16) + 1), bit u = hidden unit 32 wq + u
-                    const uint32_t w = transpose32(nz, lane);
-                    const int r = (lane < 16) ? 2 * lane : 2 * (lane - 16) + 1;
-                    p.mask[(((size_t)tile * NC + c) * 4 + wq) * TM + 32 * cg + r] = w;
+                nz_cur = FWD_MASK ? kw : nz;                // FWD_MASK: natural row order (bit r = row r); else split-pair over the rows
+                if (!FWD_MASK && p.mask) {
+                    // hidden units are moved to their split-pair lane first, so that after the transpose lane k holds the word of
+                    // row split_elem(k) with the hidden bits in split-pair order - the format the forward kernel writes
+                    const uint32_t w = transpose32(__shfl_sync(0xffffffffu, nz, epi::split_elem(lane)), lane);
+                    p.mask[(((size_t)tile * NC + c) * 4 + wq) * TM + 32 * cg + epi::split_elem(lane)] = w;
                 }
                 stamp(warp - 3);
             };
@@ -287,7 +290,8 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params 
                 uint32_t v[32];
                 tc::tmem_ld32(r_addr0 + 128 * i, v);
                 uint32_t pm[16];
-                split_masks16(nz_prev, pm);
+                if (FWD_MASK) epi::keep_masks16(nz_prev, pm);
+                else epi::split_masks16(nz_prev, pm);
                 tc::tmem_ld_wait();
                 tc::tc_fence_before();
                 __syncwarp();
@@ -359,7 +363,7 @@ size_t ffn_tc_mask_bytes(int64_t M, int ff) { return (size_t)((M + TM - 1) / TM)
 // internal launch used by u2gnn_ffn_tc_bwd (ffn_tc_bwd.cu)
 int ffn_tc_wgrad_launch(const void* xb, const void* fb, int64_t M, int d, int ff, const void* packed, float hidden_scale,
                         uint64_t seed, uint32_t stream_hidden, int thr, float* dW1, float* db1, float* dW2, void* mask,
-                        cudaStream_t st) {
+                        bool mask_from_forward, cudaStream_t st) {
     Params p;
     p.xb = static_cast<const uint8_t*>(xb); p.fb = static_cast<const uint8_t*>(fb); p.M = M; p.d = d; p.ff = ff;
     p.packed = static_cast<const uint8_t*>(packed);
@@ -371,10 +375,11 @@ int ffn_tc_wgrad_launch(const void* xb, const void* fb, int64_t M, int d, int ff
     p.mask = static_cast<uint32_t*>(mask);
     p.trace = nullptr;
     const size_t smem = 1024 + (size_t)WG_STAGES * 32768 + 16384 + 32768;
-    auto kern = ffn_tc_wgrad_kernel<false>;
+    if (mask_from_forward && !mask) return U2GNN_EINVAL;
+    auto kern = mask_from_forward ? ffn_tc_wgrad_kernel<false, true> : ffn_tc_wgrad_kernel<false, false>;
 #ifdef U2GNN_PROBE_BUILD
     p.trace = g_ffn_trace;
-    if (p.trace) kern = ffn_tc_wgrad_kernel<true>;
+    if (p.trace) kern = mask_from_forward ? ffn_tc_wgrad_kernel<true, true> : ffn_tc_wgrad_kernel<true, false>;
 #endif
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int NC = ff / CH;

@@ -31,6 +31,7 @@ FUSE_LN_BWD = os.environ.get("U2GNN_FUSE_EPILOGUES", "1") != "0"        # bf16 m
 LAST_STEP_BF16 = os.environ.get("U2GNN_LAST_BF16", "1") != "0"            # bf16 mode, d = 64: bf16 qkv / dqkv at the dead-row-eliminated last timestep
 FUSE_PROJ_BWD = os.environ.get("U2GNN_FUSE_PROJ_BWD", "1") != "0"         # bf16 mode, d = 64: projection input + weight gradients in one pass over the output gradient
 FUSE_INPROJ_ATTN = os.environ.get("U2GNN_FUSE_INPROJ_ATTN", "1") != "0"   # bf16 mode, d = 64: in_proj inside the attention-forward kernel (qkv written once, never re-read in the forward)
+FFN_FWD_MASK = os.environ.get("U2GNN_FFN_FWD_MASK", "1") != "0"          # bf16 mode: the FFN forward leaves the 1-bit live-and-kept mask of the hidden for the backward
 FFN_BWD_IMAGES = os.environ.get("U2GNN_FFN_BWD_IMAGES", "1") != "0"      # bf16 mode, d = 64: y1 / dF leave their producers as bf16 tile images (no conversion pass in the FFN backward)
 FLOPS = {}    # entry point -> algorithmic flops issued while LIB.timed is active (bench.py roofline)
 BYTES = {}    # entry point -> algorithmic HBM bytes (the tensors the call must read + write once) while LIB.timed is active
@@ -355,9 +356,10 @@ class LayerSaved:
     Sq: int = 0
     packed: torch.Tensor = None
     y1_img: torch.Tensor = None
+    ffn_mask: torch.Tensor = None
 
 
-def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, precision="fp32"):
+def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, precision="fp32", for_backward=True):
     """x[B*S, d] -> y[B*Sq, d].  p: dict name->tensor.  drop_ids: 4 stream ids.  long_seq selects the
     attn_axis="nodes" formulation (B == 1, scores materialised as [S, S])."""
     dev = x.device
@@ -420,8 +422,12 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
         st2 = torch.empty((Mq, 2), **f32)
         if LIB.timed is not None:
             FLOPS["u2gnn_ffn_tc_fwd"] = FLOPS.get("u2gnn_ffn_tc_fwd", 0) + 4 * Mq * d * ff
+        if for_backward and FFN_FWD_MASK:
+            # one bit per hidden activation (ReLU live AND kept), 256 B per row at ff 2048: the backward kernels load it instead
+            # of re-evaluating the dropout stream and the sign of the recomputed hidden
+            sv.ffn_mask = torch.empty(LIB.call("u2gnn_ffn_tc_mask_bytes", Mq, ff), dtype=torch.uint8, device=dev)
         LIB.call("u2gnn_ffn_tc_fwd", _ptr(y1), Mq, d, ff, _ptr(packed), seed, drop_ids[2], drop_ids[3], thr,
-                 _ptr(p["norm2.weight"]), _ptr(p["norm2.bias"]), _ptr(z2), _ptr(st2), _ptr(y2), _stream())
+                 _ptr(p["norm2.weight"]), _ptr(p["norm2.bias"]), _ptr(z2), _ptr(st2), _ptr(y2), _ptr(sv.ffn_mask), _stream())
         hd = None
         sv.packed = packed
     else:
@@ -482,7 +488,7 @@ def encoder_layer_bwd(dy2, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
             FLOPS["u2gnn_ffn_tc_bwd"] = FLOPS.get("u2gnn_ffn_tc_bwd", 0) + 8 * Mq * d * ff
         wsb = LIB.call("u2gnn_ffn_tc_bwd_workspace_bytes", Mq)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-        LIB.call("u2gnn_ffn_tc_bwd", _ptr(sv.y1), _ptr(df), _ptr(sv.y1_img if df_img is not None else None), _ptr(df_img), _ptr(dz2),
+        LIB.call("u2gnn_ffn_tc_bwd", _ptr(sv.y1), _ptr(df), _ptr(sv.y1_img if df_img is not None else None), _ptr(df_img), _ptr(sv.ffn_mask), _ptr(dz2),
                  Mq, d, ff, _ptr(sv.packed), drop_scale, seed, drop_ids[2], thr, _ptr(dy1), _ptr(g["linear1.weight"]),
                  _ptr(g["linear1.bias"]), _ptr(g["linear2.weight"]), _ptr(ws), wsb, _stream())
     else:
@@ -576,7 +582,7 @@ class StackSaved:
     S: int = 0
 
 
-def u2gnn_layer_fwd(src, input_x, params, l, T, attn_axis, drop: DropoutCfg, precision="fp32"):
+def u2gnn_layer_fwd(src, input_x, params, l, T, attn_axis, drop: DropoutCfg, precision="fp32", for_backward=True):
     """src[n_src, d], input_x[N, S] int64 -> out[N, d].  params: list (per timestep) of dicts."""
     require_device()
     _check(src, torch.float32, "src"); _check(input_x, torch.int64, "input_x")
@@ -599,7 +605,7 @@ def u2gnn_layer_fwd(src, input_x, params, l, T, attn_axis, drop: DropoutCfg, pre
         last = attn_axis == "neighbors" and t == T - 1
         Sq = 1 if last else Sseq
         ids = [stream_id(l, t, s, T) for s in range(4)]
-        x, sv = encoder_layer_fwd(x, B, Sseq, Sq, params[t], d, ff, ids, drop.seed, thr, attn_axis == "nodes", precision)
+        x, sv = encoder_layer_fwd(x, B, Sseq, Sq, params[t], d, ff, ids, drop.seed, thr, attn_axis == "nodes", precision, for_backward)
         saved.layers.append(sv)
     return x, saved  # [N, d] in both layouts
 

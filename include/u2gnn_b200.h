@@ -205,13 +205,17 @@ int u2gnn_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, con
  *      into pre-swizzled bf16 shared-memory images (hidden_scale = 1/(1-p) of the hidden dropout is
  *      folded into the W2 image).
  *      z[M,d] = y1 + dropout_out( dropout_hidden(relu(y1 W1^T + b1)) W2^T + b2 );
- *      stats[M,2] = (mean, rstd) of z;  xnext[M,d] = LayerNorm(z)*gamma + beta (may be null). */
+ *      stats[M,2] = (mean, rstd) of z;  xnext[M,d] = LayerNorm(z)*gamma + beta (may be null).
+ *      mask_out (may be NULL): u2gnn_ffn_tc_mask_bytes(M, ff) bytes receiving one bit per hidden activation (ReLU live AND
+ *      dropout keep), which u2gnn_ffn_tc_bwd(fwd_mask) consumes instead of recomputing the sign of the hidden and the dropout
+ *      stream. */
 size_t u2gnn_ffn_tc_packed_bytes(int d, int ff);
 int u2gnn_ffn_tc_prepare(const float* W1, const float* b1, const float* W2, const float* b2, int d, int ff,
                          float hidden_scale, void* packed, size_t packed_size, u2gnn_stream_t stream);
+size_t u2gnn_ffn_tc_mask_bytes(int64_t M, int ff);
 int u2gnn_ffn_tc_fwd(const float* y1, int64_t M, int d, int ff, const void* packed, uint64_t seed,
                      uint32_t stream_hidden, uint32_t stream_out, int thr, const float* gamma, const float* beta,
-                     float* z, float* stats, float* xnext, u2gnn_stream_t stream);
+                     float* z, float* stats, float* xnext, void* mask_out, u2gnn_stream_t stream);
 
 /* backward of the block above (autograd of linear1/ReLU/dropout/linear2, transformer.py:977-982) with the
  * hidden recomputed on chip: dy1[M,d] = dz + dPre W1 (dz = gradient at the residual sum, df = gradient at
@@ -221,12 +225,14 @@ int u2gnn_ffn_tc_fwd(const float* y1, int64_t M, int d, int ff, const void* pack
  * to the input-gradient kernel (so the hidden is recomputed once, not twice).
  * y1_img / df_img (may be NULL): the same two operands ALREADY stored as bf16 swizzled [128 x 64] tile images of
  * u2gnn_ffn_tc_image_bytes(M) bytes (128-byte aligned; rows >= M of the last tile zero) - what u2gnn_gemm_tc_rows_ln (y_img)
- * and u2gnn_add_dropout_ln_bwd_ex (da_bf16 = 2) write; the fp32 pointer of an operand given as an image may be NULL. */
+ * and u2gnn_add_dropout_ln_bwd_ex (da_bf16 = 2) write; the fp32 pointer of an operand given as an image may be NULL.
+ * fwd_mask (may be NULL): the mask words u2gnn_ffn_tc_fwd(mask_out) wrote for the same rows, weights and dropout stream: the
+ * weight-gradient kernel then loads them instead of evaluating the dropout stream and extracting the sign of the hidden. */
 size_t u2gnn_ffn_tc_bwd_workspace_bytes(int64_t M);
 size_t u2gnn_ffn_tc_image_bytes(int64_t M);
-int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const void* y1_img, const void* df_img, const float* dz, int64_t M, int d,
-                     int ff, const void* packed, float hidden_scale, uint64_t seed, uint32_t stream_hidden, int thr, float* dy1,
-                     float* dW1, float* db1, float* dW2, void* workspace, size_t workspace_bytes, u2gnn_stream_t stream);
+int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const void* y1_img, const void* df_img, const void* fwd_mask, const float* dz,
+                     int64_t M, int d, int ff, const void* packed, float hidden_scale, uint64_t seed, uint32_t stream_hidden, int thr,
+                     float* dy1, float* dW1, float* db1, float* dW2, void* workspace, size_t workspace_bytes, u2gnn_stream_t stream);
 
 /* ---- bf16 tensor-core GEMMs for the attention-block projections of the bf16 mode (csrc/gemm_tc.cu): the
  *      F.linear calls inside nn.MultiheadAttention (in_proj / out_proj) and their autograd.

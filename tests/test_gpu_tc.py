@@ -69,7 +69,7 @@ def _ffn_case(U, M, d, ff, p, seed=11):
     xn = torch.zeros((M, d), device="cuda")
     SEED, S2, S3 = 0xABCDEF0123, 18, 19
     U.LIB.call("u2gnn_ffn_tc_fwd", t["y1"].data_ptr(), M, d, ff, packed.data_ptr(), SEED, S2, S3, thr, t["gamma"].data_ptr(),
-               t["beta"].data_ptr(), z.data_ptr(), stats.data_ptr(), xn.data_ptr(), E._stream())
+               t["beta"].data_ptr(), z.data_ptr(), stats.data_ptr(), xn.data_ptr(), 0, E._stream())
     torch.cuda.synchronize()
     # oracle (exact fp32 semantics) and a bf16-operand emulation of what the tensor cores compute
     if thr:
@@ -132,7 +132,7 @@ def test_ffn_tc_backward(U, M, d, ff, p):
     dW1 = torch.zeros((ff, d), device="cuda"); db1 = torch.zeros(ff, device="cuda"); dW2 = torch.zeros((d, ff), device="cuda")
     SEED, S2 = 0x1234ABCD99, 18
     ws = torch.empty(U.LIB.call("u2gnn_ffn_tc_bwd_workspace_bytes", M), dtype=torch.uint8, device="cuda")
-    U.LIB.call("u2gnn_ffn_tc_bwd", t["y1"].data_ptr(), t["df"].data_ptr(), 0, 0, t["dz"].data_ptr(), M, d, ff, packed.data_ptr(), scale,
+    U.LIB.call("u2gnn_ffn_tc_bwd", t["y1"].data_ptr(), t["df"].data_ptr(), 0, 0, 0, t["dz"].data_ptr(), M, d, ff, packed.data_ptr(), scale,
                SEED, S2, thr, dy1.data_ptr(), dW1.data_ptr(), db1.data_ptr(), dW2.data_ptr(), ws.data_ptr(), ws.numel(), E._stream())
     torch.cuda.synchronize()
     if thr:
@@ -557,10 +557,56 @@ def test_producers_write_ffn_backward_tile_images(U, M, p):
         dW1, db1, dW2 = torch.zeros(ff, d, device="cuda"), torch.zeros(ff, device="cuda"), torch.zeros(d, ff, device="cuda")
         ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
         U.LIB.call("u2gnn_ffn_tc_bwd", y1.data_ptr(), df_rows.data_ptr(), yimg.data_ptr() if use_img else 0, img.data_ptr() if use_img else 0,
-                   dz1.data_ptr(), M, d, ff, packed.data_ptr(), scale, 0xBEEF, 23, thr, dy1.data_ptr(), dW1.data_ptr(), db1.data_ptr(),
+                   0, dz1.data_ptr(), M, d, ff, packed.data_ptr(), scale, 0xBEEF, 23, thr, dy1.data_ptr(), dW1.data_ptr(), db1.data_ptr(),
                    dW2.data_ptr(), ws.data_ptr(), wsb, E._stream())
         outs.append((dy1, dW1, db1, dW2))
     torch.cuda.synchronize()
     assert torch.equal(outs[0][0], outs[1][0])
     for a, b in zip(outs[0][1:], outs[1][1:]):
+        assert (a - b).abs().max().item() <= 2e-4 * max(1.0, a.abs().max().item())
+
+
+@pytest.mark.parametrize("M,ff,p", [(1000, 256, 0.5), (148 * 256 + 77, 512, 0.5), (300, 2048, 0.0), (129, 128, 0.25)])
+def test_ffn_backward_with_forward_mask_equals_recomputed_mask(U, M, ff, p):
+    """u2gnn_ffn_tc_fwd(mask_out) leaves one bit per hidden activation (ReLU live AND kept); u2gnn_ffn_tc_bwd(fwd_mask) must give the
+    SAME results as the self-contained backward that recomputes the dropout stream and the sign of the hidden: dy1 bit-identical
+    (same mask bits, same MMAs), weight gradients equal up to the order of the fp32 atomics."""
+    from u2gnn_b200 import engine as E
+    d = 64
+    thr = E.dropout_threshold(p)
+    scale = 256.0 / (256.0 - thr) if thr else 1.0
+    g = torch.Generator(device="cuda").manual_seed(M + ff)
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    prm = {"linear1.weight": rnd(ff, d) / 8, "linear1.bias": 0.1 * rnd(ff), "linear2.weight": rnd(d, ff) / (ff ** 0.5), "linear2.bias": 0.1 * rnd(d)}
+    packed = E.ffn_tc_pack(prm, d, ff, thr)
+    y1, df, dz = rnd(M, d), rnd(M, d), rnd(M, d)
+    gamma, beta = 1 + 0.1 * rnd(d), 0.1 * rnd(d)
+    SEED, S_H, S_O = 0x77AA, 40, 41
+    mask = torch.zeros(U.LIB.call("u2gnn_ffn_tc_mask_bytes", M, ff), dtype=torch.uint8, device="cuda")
+    z = torch.empty(M, d, device="cuda"); st = torch.empty(M, 2, device="cuda"); xn = torch.empty(M, d, device="cuda")
+    z0 = torch.empty(M, d, device="cuda"); st0 = torch.empty(M, 2, device="cuda"); xn0 = torch.empty(M, d, device="cuda")
+    U.LIB.call("u2gnn_ffn_tc_fwd", y1.data_ptr(), M, d, ff, packed.data_ptr(), SEED, S_H, S_O, thr, gamma.data_ptr(), beta.data_ptr(),
+               z.data_ptr(), st.data_ptr(), xn.data_ptr(), mask.data_ptr(), E._stream())
+    U.LIB.call("u2gnn_ffn_tc_fwd", y1.data_ptr(), M, d, ff, packed.data_ptr(), SEED, S_H, S_O, thr, gamma.data_ptr(), beta.data_ptr(),
+               z0.data_ptr(), st0.data_ptr(), xn0.data_ptr(), 0, E._stream())
+    wsb = U.LIB.call("u2gnn_ffn_tc_bwd_workspace_bytes", M)
+    outs = []
+    for use_mask in (False, True):
+        dy1 = torch.empty(M, d, device="cuda")
+        dW1, db1, dW2 = torch.zeros(ff, d, device="cuda"), torch.zeros(ff, device="cuda"), torch.zeros(d, ff, device="cuda")
+        ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+        U.LIB.call("u2gnn_ffn_tc_bwd", y1.data_ptr(), df.data_ptr(), 0, 0, mask.data_ptr() if use_mask else 0, dz.data_ptr(), M, d, ff,
+                   packed.data_ptr(), scale, SEED, S_H, thr, dy1.data_ptr(), dW1.data_ptr(), db1.data_ptr(), dW2.data_ptr(), ws.data_ptr(),
+                   wsb, E._stream())
+        outs.append((dy1, dW1, db1, dW2, ws))
+    torch.cuda.synchronize()
+    assert torch.equal(z, z0) and torch.equal(xn, xn0)                   # emitting the mask does not change the forward
+    # the self-contained backward writes its own mask words into the workspace: same bits for every real row
+    tp = 2 * ((M + 255) // 256)
+    own = outs[0][4][tp * 32768:tp * 32768 + mask.numel()].view(torch.int32).view(tp, ff // 128, 4, 128)
+    fwd = mask.view(torch.int32).view(tp, ff // 128, 4, 128)
+    rows = torch.arange(tp * 128, device="cuda").view(tp, 1, 1, 128).expand_as(fwd) < M
+    assert torch.equal(own[rows], fwd[rows])
+    assert torch.equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1:4], outs[1][1:4]):
         assert (a - b).abs().max().item() <= 2e-4 * max(1.0, a.abs().max().item())

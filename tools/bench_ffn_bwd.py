@@ -19,7 +19,7 @@ U.LIB.call("u2gnn_ffn_tc_prepare", W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), 
 dy = torch.empty_like(y1); dW1 = torch.zeros_like(W1); db1 = torch.zeros_like(b1); dW2 = torch.zeros_like(W2)
 ws = torch.empty(U.LIB.call("u2gnn_ffn_tc_bwd_workspace_bytes", M), dtype=torch.uint8, device="cuda")
 def run():
-    U.LIB.call("u2gnn_ffn_tc_bwd", y1.data_ptr(), df.data_ptr(), 0, 0, dz.data_ptr(), M, d, ff, packed.data_ptr(), 2.0, 1, 2, thr,
+    U.LIB.call("u2gnn_ffn_tc_bwd", y1.data_ptr(), df.data_ptr(), 0, 0, 0, dz.data_ptr(), M, d, ff, packed.data_ptr(), 2.0, 1, 2, thr,
                dy.data_ptr(), dW1.data_ptr(), db1.data_ptr(), dW2.data_ptr(), ws.data_ptr(), ws.numel(), E._stream())
 for _ in range(3): run()
 torch.cuda.synchronize()

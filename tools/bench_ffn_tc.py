@@ -23,7 +23,7 @@ def main():
     z = torch.empty_like(y1); xn = torch.empty_like(y1); st = torch.empty(M, 2, device="cuda")
     def run():
         U.LIB.call("u2gnn_ffn_tc_fwd", y1.data_ptr(), M, d, ff, packed.data_ptr(), 1, 2, 3, thr, gamma.data_ptr(), beta.data_ptr(),
-                   z.data_ptr(), st.data_ptr(), xn.data_ptr(), E._stream())
+                   z.data_ptr(), st.data_ptr(), xn.data_ptr(), 0, E._stream())
     for _ in range(3): run()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -30,7 +30,7 @@ def main():
     tr = torch.zeros(SLOTS * CAP, dtype=torch.int32, device="cuda")
     def run():
         PROBE.call("u2gnn_ffn_tc_fwd", y1.data_ptr(), M, d, ff, packed.data_ptr(), 1, 2, 3, thr, gamma.data_ptr(), beta.data_ptr(),
-                   z.data_ptr(), st.data_ptr(), xn.data_ptr(), E._stream())
+                   z.data_ptr(), st.data_ptr(), xn.data_ptr(), 0, E._stream())
     run(); torch.cuda.synchronize()
     PROBE.call("u2gnn_ffn_tc_set_trace", tr.data_ptr())
     run(); torch.cuda.synchronize()
