@@ -60,7 +60,7 @@ WORKLOADS = {
 }
 # entry points timed per launch for the HBM-side roofline list (north_star: gather / attention / pooling kernels)
 HBM_KERNELS = ("u2gnn_gather_rows", "u2gnn_inproj_seqattn_tc_fwd", "u2gnn_seqattn_tc_bwd_ex", "u2gnn_segment_sum",
-               "u2gnn_add_dropout_ln_bwd_ex", "u2gnn_gemm_tc_rows_ln", "u2gnn_gemm_tc_dgrad_wgrad")
+               "u2gnn_add_dropout_ln_bwd_ex", "u2gnn_gemm_tc_rows_ln", "u2gnn_gemm_tc_dgrad_wgrad", "u2gnn_clip_adam")
 
 
 def _load_synthetic():

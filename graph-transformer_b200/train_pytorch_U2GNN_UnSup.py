@@ -15,7 +15,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import u2gnn_b200 as U                                    # noqa: E402
 from u2gnn_b200 import engine as E                        # noqa: E402
-from u2gnn_b200.data import build_batch, global_node_ids, load_data   # noqa: E402
+from u2gnn_b200.data import DeviceBatchBuilder, build_batch, global_node_ids, load_data   # noqa: E402
 from u2gnn_b200.evaluate import ConditionalStepLR, unsup_accuracy   # noqa: E402
 from u2gnn_b200.trainer import UnSupTrainer               # noqa: E402
 
@@ -42,12 +42,13 @@ def parse_args(argv=None):
                    help="share ONE encoder weight set across the T timesteps (the published Universal-Transformer U2GNN); "
                         "default = T independent sets like the reference PyTorch file")
     p.add_argument("--dataset_root", default=None)
+    p.add_argument("--batch_builder", default="host", choices=["host", "device"],
+                   help="host: the reference's numpy loop (reproduces its index stream bit for bit); device: dataset resident in HBM, "
+                        "neighbours sampled by the CUDA batch builder")
     return p.parse_args(argv)
 
 
 def run(args, log=print):
-    from sklearn.linear_model import LogisticRegression
-    from sklearn.model_selection import StratifiedKFold
     torch.manual_seed(123)
     np.random.seed(123)
     torch.cuda.manual_seed_all(123)
@@ -67,15 +68,22 @@ def run(args, log=print):
     trainer = UnSupTrainer(model, lr=args.learning_rate, seed=123)
     steps_per_epoch = int((len(graphs) - 1) / args.batch_size) + 1
 
+    builder = DeviceBatchBuilder(graphs, args.num_neighbors, device=dev, seed=123) if args.batch_builder == "device" else None
+
     def train_epoch():
         model.train()
         total = 0.0
         for _ in range(steps_per_epoch):
             sel = np.random.permutation(len(graphs))[:args.batch_size]
-            ix, _, X, _ = build_batch([graphs[i] for i in sel], args.num_neighbors, np.random)
-            iy = global_node_ids(graphs, sel)
-            loss = trainer.step(torch.from_numpy(X).to(dev), torch.from_numpy(ix).to(dev), torch.from_numpy(iy).to(dev))
-            total += float(loss.sum().item())
+            if builder is not None:                   # input_y = the dataset-wide node ids the builder returns (train_pytorch_U2GNN_UnSup.py:96-99)
+                ix, _, X, _, iy = builder.build(sel)
+                loss = trainer.step(X, ix, iy)
+            else:
+                ix, _, X, _ = build_batch([graphs[i] for i in sel], args.num_neighbors, np.random)
+                iy = global_node_ids(graphs, sel)
+                loss = trainer.step(torch.from_numpy(X).to(dev), torch.from_numpy(ix).to(dev), torch.from_numpy(iy).to(dev))
+            total += float(loss.sum().item())         # the reference's per-step device sync (loss.item())
+            E.check_device_errors(dev)
         return total
 
     def evaluate():

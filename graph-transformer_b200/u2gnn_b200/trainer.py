@@ -70,6 +70,7 @@ class FlatArena:
             dist.all_reduce(self.g)                           # gradient all-reduce (sum), NCCL over NVLink
         LIB.call("u2gnn_grad_sqnorm", self.g.data_ptr(), self.total, self.sumsq.data_ptr(), s)
         self.step_count += 1
+        E._acct_bytes("u2gnn_clip_adam", 28 * self.total)     # read p, g, m, v; write p, m, v (dense over every parameter, the class table included)
         LIB.call("u2gnn_clip_adam", self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.total,
                  self.sumsq.data_ptr(), max_norm, lr, betas[0], betas[1], eps, self.step_count, s)
         return float(self.sumsq.sqrt().item()) if want_norm else None
@@ -311,5 +312,6 @@ class UnSupTrainer:
         all_reduce_sum_(a.sumsq)
         LIB.call("u2gnn_grad_sqnorm", a.g.data_ptr(), n_enc, a.sumsq.data_ptr(), s)
         a.step_count += 1
+        E._acct_bytes("u2gnn_clip_adam", 28 * a.total)
         LIB.call("u2gnn_clip_adam", a.p.data_ptr(), a.g.data_ptr(), a.m.data_ptr(), a.v.data_ptr(), a.total,
                  a.sumsq.data_ptr(), self.max_norm, self.lr, 0.9, 0.999, 1e-8, a.step_count, s)

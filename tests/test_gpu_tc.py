@@ -610,3 +610,47 @@ def test_ffn_backward_with_forward_mask_equals_recomputed_mask(U, M, ff, p):
     assert torch.equal(outs[0][0], outs[1][0])
     for a, b in zip(outs[0][1:4], outs[1][1:4]):
         assert (a - b).abs().max().item() <= 2e-4 * max(1.0, a.abs().max().item())
+
+
+@pytest.mark.parametrize("M,ff,p", [(37, 128, 0.5), (300, 256, 0.5), (129, 2048, 0.0)])
+def test_ffn_kernels_write_nothing_outside_their_outputs(U, M, ff, p):
+    """Bounds check of our own (compute-sanitizer is closed on this GPU pool, profiles/r02_sanitizer_unavailable.txt): every output
+    of the fused FFN forward / backward sits between guard bands filled with a sentinel; the bulk stores, tensor-memory drains
+    and atomics of the tcgen05 kernels must leave the bands untouched on shapes with partial tiles."""
+    from u2gnn_b200 import engine as E
+    d = 64
+    thr = E.dropout_threshold(p)
+    scale = 256.0 / (256.0 - thr) if thr else 1.0
+    g = torch.Generator(device="cuda").manual_seed(M * 3 + ff)
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    prm = {"linear1.weight": rnd(ff, d) / 8, "linear1.bias": 0.1 * rnd(ff), "linear2.weight": rnd(d, ff) / (ff ** 0.5), "linear2.bias": 0.1 * rnd(d)}
+    packed = E.ffn_tc_pack(prm, d, ff, thr)
+    G = 4096                                                # guard elements on each side
+    SENT = 12345.0
+
+    class Guarded:
+        def __init__(self, numel, dtype=torch.float32):
+            self.buf = torch.full((numel + 2 * G,), SENT if dtype == torch.float32 else 0x5A, dtype=dtype, device="cuda")
+            self.view = self.buf[G:G + numel]
+            self.ref = self.buf.clone()
+
+        def intact(self):
+            return torch.equal(self.buf[:G], self.ref[:G]) and torch.equal(self.buf[-G:], self.ref[-G:])
+
+    y1, df, dz, gamma, beta = rnd(M, d), rnd(M, d), rnd(M, d), 1 + 0.1 * rnd(d), 0.1 * rnd(d)
+    out = {n: Guarded(k) for n, k in dict(z=M * d, st=M * 2, xn=M * d, dy1=M * d, dW1=ff * d, db1=ff, dW2=d * ff).items()}
+    out["mask"] = Guarded(U.LIB.call("u2gnn_ffn_tc_mask_bytes", M, ff), torch.uint8)
+    out["ws"] = Guarded(U.LIB.call("u2gnn_ffn_tc_bwd_workspace_bytes", M), torch.uint8)
+    for n in ("dW1", "db1", "dW2"):
+        out[n].view.zero_()
+    ptr = lambda n: out[n].view.data_ptr()
+    assert ptr("ws") % 128 == 0 and ptr("mask") % 128 == 0
+    U.LIB.call("u2gnn_ffn_tc_fwd", y1.data_ptr(), M, d, ff, packed.data_ptr(), 7, 50, 51, thr, gamma.data_ptr(), beta.data_ptr(),
+               ptr("z"), ptr("st"), ptr("xn"), ptr("mask"), E._stream())
+    U.LIB.call("u2gnn_ffn_tc_bwd", y1.data_ptr(), df.data_ptr(), 0, 0, ptr("mask"), dz.data_ptr(), M, d, ff, packed.data_ptr(), scale, 7, 50, thr,
+               ptr("dy1"), ptr("dW1"), ptr("db1"), ptr("dW2"), ptr("ws"), out["ws"].view.numel(), E._stream())
+    torch.cuda.synchronize()
+    for n, o in out.items():
+        assert o.intact(), n
+    for n in ("z", "xn", "dy1", "dW1", "dW2"):
+        assert bool(torch.isfinite(out[n].view).all()) and not bool((out[n].view == SENT).any()), n
