@@ -187,6 +187,34 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const float* __restric
     }
 }
 
+// d % 4 == 0: 128-bit loads, d / 4 lanes per graph, EIGHT rows in flight per lane (the scalar kernel kept 4 x 4 bytes per lane in
+// flight: 2.3 TB/s on 262 144 x 64 rows, latency-bound).  Every column is still summed in ascending node order, so the result
+// is bit-identical to the scalar kernel and to the reference's CPU COO spmm.
+__global__ void __launch_bounds__(256) segment_sum_vec_kernel(const float* __restrict__ x, int dv, const int64_t* __restrict__ rowptr,
+                                                              int64_t G, float* __restrict__ out) {
+    const int per_block = blockDim.x / dv;
+    const int lane = threadIdx.x % dv, sub = threadIdx.x / dv;
+    if (sub >= per_block) return;
+    const float4* xv = reinterpret_cast<const float4*>(x);
+    for (int64_t g = (int64_t)blockIdx.x * per_block + sub; g < G; g += (int64_t)gridDim.x * per_block) {
+        const int64_t b = rowptr[g], e = rowptr[g + 1];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int64_t n = b;
+        for (; n + 8 <= e; n += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(xv + (n + u) * dv + lane);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+        }
+        for (; n < e; ++n) {
+            const float4 v = __ldg(xv + n * dv + lane);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        reinterpret_cast<float4*>(out)[g * dv + lane] = acc;
+    }
+}
+
 __global__ void __launch_bounds__(256) segment_bcast_kernel(const float* __restrict__ gout, int d,
                                                             const int64_t* __restrict__ rowptr, int64_t G,
                                                             float* __restrict__ gx, int64_t n, int accumulate) {
@@ -305,6 +333,11 @@ extern "C" int u2gnn_segment_sum(const float* x, int64_t n, int d, const int64_t
     (void)n;
     if (!x || !rowptr || !out || d <= 0 || num_graphs < 0) return U2GNN_EINVAL;
     if (num_graphs == 0) return U2GNN_OK;
+    if ((d & 3) == 0 && d <= 1024 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+        const int dv = d / 4;
+        segment_sum_vec_kernel<<<grid_for(num_graphs, 256 / dv, 8), 256, 0, as_stream(stream)>>>(x, dv, rowptr, num_graphs, out);
+        U2GNN_CHECK_LAUNCH();
+    }
     const int lanes = pick_lanes(d);
     segment_sum_kernel<<<grid_for(num_graphs, 256 / lanes, 8), 256, 0, as_stream(stream)>>>(x, d, rowptr, num_graphs,
                                                                                            out, lanes);

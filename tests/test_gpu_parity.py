@@ -55,7 +55,7 @@ def test_gather_scatter_bit_exact(U, d):
     assert rel_err(atom, ref) < 1e-5
 
 
-@pytest.mark.parametrize("d", [2, 7, 64])
+@pytest.mark.parametrize("d", [2, 4, 7, 64, 128, 260])
 def test_segment_sum_bit_exact_and_edge_cases(U, d):
     from u2gnn_b200 import engine as E
     rng = np.random.default_rng(100 + d)
