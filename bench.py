@@ -398,8 +398,11 @@ def run_ours(args, w):
     S = w["k"] + 1
     precision = args.precision or w["precision"]
     note = None
-    if precision == "bf16" and not E.ffn_tc_supported(w["d"], w["ff"]):
-        precision, note = "fp32", "the tcgen05 FFN path supports d <= 64: this workload ran on the fp32 path"
+    if precision == "bf16" and not (E.ffn_tc_supported(w["d"], w["ff"]) or E.ffn_wide_supported(w["d"], w["ff"])):
+        precision, note = "fp32", "no tcgen05 FFN path for this feature size: this workload ran on the fp32 path"
+    elif precision == "bf16" and E.ffn_wide_supported(w["d"], w["ff"]):
+        note = ("bf16 FFN as named by the config: 64 < d <= 128 runs the FFN as tcgen05 GEMMs with the hidden materialised in bf16 "
+                "(engine.ffn_wide_*); the attention block of this feature size stays on the fp32 kernels")
     torch.manual_seed(123)
     dev = torch.device("cuda", local)
     batches = []                                   # resident batches, cycled over the timed steps

@@ -357,6 +357,7 @@ class LayerSaved:
     packed: torch.Tensor = None
     y1_img: torch.Tensor = None
     ffn_mask: torch.Tensor = None
+    wide: bool = False
 
 
 def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, precision="fp32", for_backward=True):
@@ -414,7 +415,13 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
             xq = torch.empty((Mq, d), **f32)
             copy_rows(x, S * d, xq, d, B, d)
         z1, y1, st1 = add_dropout_ln_fwd(xq, a, Mq, d, (seed, drop_ids[1], thr), p["norm1.weight"], p["norm1.bias"])
-    if precision == "bf16":
+    if precision == "bf16" and ffn_wide_supported(d, ff):
+        # 64 < d <= 128 (configs[2]): bf16 FFN on the general tcgen05 GEMMs, hidden materialised in bf16; the attention block of
+        # this feature size runs on the fp32 kernels ("bf16 FFN" exactly as the config names it)
+        f, hd = ffn_wide_fwd(y1, Mq, d, ff, p, seed, drop_ids[2], thr)
+        z2, y2, st2 = add_dropout_ln_fwd(y1, f, Mq, d, (seed, drop_ids[3], thr), p["norm2.weight"], p["norm2.bias"])
+        sv.wide = True
+    elif precision == "bf16":
         # fused tcgen05 FFN block: the [Mq, ff] hidden never reaches HBM and is recomputed in the backward
         packed = ffn_tc_pack(p, d, ff, thr)
         z2 = torch.empty((Mq, d), **f32)
@@ -441,6 +448,74 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
     return y2, sv
 
 
+def ffn_wide_supported(d, ff):
+    """bf16 FFN for 64 < d <= 128: tcgen05 GEMMs of the general rows / weight-gradient kernels, hidden materialised in bf16."""
+    return 64 < d <= 128 and ff % 64 == 0 and ff >= 64
+
+
+def ffn_wide_fwd(y1, Mq, d, ff, p, seed, stream_hidden, thr):
+    """f = linear2(dropout(relu(linear1(y1)))) for 64 < d <= 128 (transformer.py:977-982).  Returns (f [Mq, d] fp32, h [Mq, ff] bf16 =
+    the hidden after ReLU, dropout and its 1/(1-p) scale, saved for the backward)."""
+    dev = y1.device
+    s = _stream()
+    h = torch.empty((Mq, ff), dtype=torch.bfloat16, device=dev)
+    W1, b1, W2, b2 = p["linear1.weight"], p["linear1.bias"], p["linear2.weight"], p["linear2.bias"]
+    for j in range(0, ff, 256):                      # N slices of linear1 (the rows kernel holds N <= 256 accumulator columns)
+        n = min(256, ff - j)
+        LIB.call("u2gnn_gemm_tc_rows_ex", _ptr(y1), 0, Mq, d, d, _ptr(W1) + 4 * j * d, 0, n, _ptr(b1) + 4 * j, 0.0,
+                 _ptr(h) + 2 * j, 1, ff, s)
+    scale = 256.0 / (256.0 - thr) if thr else 1.0
+    LIB.call("u2gnn_relu_dropout_bf16", _ptr(h), Mq, ff, seed, stream_hidden, thr, scale, s)
+    f = torch.empty((Mq, d), dtype=torch.float32, device=dev)
+    W2T = W2.t().contiguous()                        # [ff, d]: a K slice of linear2 is then a contiguous [K, N] block (weights only: 4 * d * ff bytes)
+    for j in range(0, ff, 256):                      # K slices of linear2, accumulated into f
+        k = min(256, ff - j)
+        LIB.call("u2gnn_gemm_tc_rows_ex", _ptr(h) + 2 * j, 1, Mq, k, ff, _ptr(W2T) + 4 * j * d, 1, d, _ptr(b2) if j == 0 else 0,
+                 0.0 if j == 0 else 1.0, _ptr(f), 0, d, s)
+    if LIB.timed is not None:                        # both GEMMs go through the rows entry point: 2 x (2 M d ff)
+        FLOPS["u2gnn_gemm_tc_rows_ex"] = FLOPS.get("u2gnn_gemm_tc_rows_ex", 0) + 4 * Mq * d * ff
+    return f, h
+
+
+def ffn_wide_bwd(df, dz, y1, h, Mq, d, ff, p, g, thr):
+    """Backward of ffn_wide_fwd: dy1 = dz + dPre W1 (accumulated INTO dz and returned), dW1 / db1 / dW2 accumulated into g
+    (db2 = colsum(df) is the caller's).  df [Mq, d] fp32 = gradient at the linear2 output, h = the saved bf16 hidden."""
+    dev = df.device
+    s = _stream()
+    W1, W2 = p["linear1.weight"], p["linear2.weight"]
+    scale = 256.0 / (256.0 - thr) if thr else 1.0
+    W2T = W2.t().contiguous()                        # [ff, d] = [N, K] for dH = df W2
+    dh = torch.empty((Mq, ff), dtype=torch.bfloat16, device=dev)
+    for j in range(0, ff, 256):
+        n = min(256, ff - j)
+        LIB.call("u2gnn_gemm_tc_rows_ex", _ptr(df), 0, Mq, d, d, _ptr(W2T) + 4 * j * d, 0, n, 0, 0.0, _ptr(dh) + 2 * j, 1, ff, s)
+    # dW2[d, ff] += df^T h: the weight-gradient kernel takes at most 64 columns of its second operand, so 64-wide slices of h;
+    # each slice's [d, 64] result is added into its columns of dW2
+    n_sl = ff // 64
+    tmp = torch.zeros((n_sl, d * 64), dtype=torch.float32, device=dev)
+    for i in range(n_sl):
+        LIB.call("u2gnn_gemm_tc_wgrad_ex", _ptr(df), 0, Mq, d, d, _ptr(h) + 2 * 64 * i, 1, 64, ff, _ptr(tmp) + 4 * i * d * 64, 0, s)
+        LIB.call("u2gnn_copy_rows", _ptr(tmp) + 4 * i * d * 64, 64, _ptr(g["linear2.weight"]) + 4 * 64 * i, ff, d, 64, 1, s)
+    LIB.call("u2gnn_relu_dropout_bwd_bf16", _ptr(dh), _ptr(h), Mq, ff, scale, s)            # dh is now dPre
+    # dW1[ff, d] += dPre^T y1, db1 += colsum(dPre): 256-row slices of dW1 x (64 | d - 64)-column blocks of y1
+    blocks = [(0, 64), (64, d - 64)]
+    n_a = (ff + 255) // 256
+    tmp1 = torch.zeros((n_a, 2, 256 * 64), dtype=torch.float32, device=dev)
+    for i in range(n_a):
+        n1 = min(256, ff - 256 * i)
+        for bi, (c0, nc) in enumerate(blocks):
+            t = _ptr(tmp1) + 4 * (i * 2 + bi) * 256 * 64
+            LIB.call("u2gnn_gemm_tc_wgrad_ex", _ptr(dh) + 2 * 256 * i, 1, Mq, n1, ff, _ptr(y1) + 4 * c0, 0, nc, d, t,
+                     (_ptr(g["linear1.bias"]) + 4 * 256 * i) if bi == 0 else 0, s)
+            LIB.call("u2gnn_copy_rows", t, nc, _ptr(g["linear1.weight"]) + 4 * (256 * i * d + c0), d, n1, nc, 1, s)
+    for j in range(0, ff, 256):                      # dy1 = dz + dPre W1 (K slices; W1 rows j.. are a contiguous [K, N] block)
+        k = min(256, ff - j)
+        LIB.call("u2gnn_gemm_tc_rows_ex", _ptr(dh) + 2 * j, 1, Mq, k, ff, _ptr(W1) + 4 * j * d, 1, d, 0, 1.0, _ptr(dz), 0, d, s)
+    if LIB.timed is not None:                        # dH and dy1 go through the rows entry point (the two weight gradients through wgrad_ex)
+        FLOPS["u2gnn_gemm_tc_rows_ex"] = FLOPS.get("u2gnn_gemm_tc_rows_ex", 0) + 4 * Mq * d * ff
+    return dz
+
+
 def ffn_tc_supported(d, ff):
     return d <= 64 and ff % 128 == 0 and 128 <= ff <= 2048
 
@@ -448,7 +523,7 @@ def ffn_tc_supported(d, ff):
 def ffn_tc_pack(p, d, ff, thr):
     """bf16 pre-swizzled weight images for the tcgen05 FFN kernels (rebuilt whenever the weights change)."""
     if not ffn_tc_supported(d, ff):
-        raise RuntimeError("precision='bf16' needs feature_dim_size <= 64 and ff_hidden_size a multiple of 128 (<= 2048); "
+        raise RuntimeError("precision='bf16' needs feature_dim_size <= 64 and ff_hidden_size a multiple of 128 (<= 2048), or 64 < feature_dim_size <= 128 with ff_hidden_size a multiple of 64; "
                            "got d=%d ff=%d (use precision='fp32')" % (d, ff))
     nbytes = LIB.call("u2gnn_ffn_tc_packed_bytes", d, ff)
     packed = torch.empty(nbytes, dtype=torch.uint8, device=p["linear1.weight"].device)
@@ -478,7 +553,12 @@ def encoder_layer_bwd(dy2, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
         dz2, df = add_dropout_ln_bwd(dy2, sv.z2, sv.st2, Mq, d, p["norm2.weight"], (seed, drop_ids[3], thr),
                                      g["norm2.weight"], g["norm2.bias"], dasum=g["linear2.bias"] if fold else None)
     dy1 = dz2  # dy1 = dz2 + dhpre @ W1 (in place)
-    if sv.packed is not None:
+    if sv.wide:
+        if df is dz2:                    # no output dropout: df aliases dz2, which ffn_wide_bwd accumulates into
+            df = dz2.clone()
+        LIB.call("u2gnn_colsum", _ptr(df), Mq, d, d, _ptr(g["linear2.bias"]), 1, _stream())
+        ffn_wide_bwd(df, dz2, sv.y1, sv.hd, Mq, d, ff, p, g, thr)
+    elif sv.packed is not None:
         # fused tcgen05 backward: hidden and its gradient recomputed on chip
         if df is dz2:                    # no output dropout: df aliases dz2, which the weight-gradient kernel still reads
             dy1 = torch.empty_like(dz2)

@@ -88,10 +88,13 @@ def effective_smoothing(eps, classes, style="reference"):
     raise ValueError("smoothing_style must be 'reference' or 'tf'")
 
 
-def dominant_kernel(precision):
+def dominant_kernel(precision, d=64):
     """Entry point whose launches bench.py times for the roofline object: the FFN backward (the path's largest dense
-    contraction, tcgen05) in bf16 mode, the CUDA-core SGEMM in fp32 mode."""
-    return "u2gnn_sgemm" if precision == "fp32" else "u2gnn_ffn_tc_bwd"
+    contraction, tcgen05) in bf16 mode, the CUDA-core SGEMM in fp32 mode; for 64 < d <= 128 in bf16 mode the FFN runs as
+    general tcgen05 rows GEMMs (engine.ffn_wide_*), which are then what is timed."""
+    if precision == "fp32":
+        return "u2gnn_sgemm"
+    return "u2gnn_gemm_tc_rows_ex" if d > 64 else "u2gnn_ffn_tc_bwd"
 
 
 def roofline(model, precision, name, kernel_ms, launches, peaks, flops, ncu_summary=None):
@@ -112,7 +115,9 @@ def roofline(model, precision, name, kernel_ms, launches, peaks, flops, ncu_summ
             "frac": achieved / peak, "traffic": traffic, "launches_timed": launches,
             "avg_launch_ms": kernel_ms / max(launches, 1), "peak_source": which,
             "note": ("fp32 CUDA-core parity path; the tcgen05 path is --precision bf16" if precision == "fp32"
-                     else "fused bf16 tcgen05 FFN backward (image pass + weight-gradient kernel + input-gradient kernel)")}
+                     else "bf16 FFN for 64 < d <= 128: four of its six GEMMs (linear1, linear2, dH, dy1) through the general tcgen05 rows kernel, hidden materialised in bf16"
+                     if name == "u2gnn_gemm_tc_rows_ex"
+                     else "fused bf16 tcgen05 FFN backward (weight-gradient kernel + input-gradient kernel)")}
 
 
 class SupTrainer:
@@ -182,7 +187,7 @@ class SupTrainer:
         return self.loss, scores
 
     def dominant_kernel(self):
-        return dominant_kernel(self.precision)
+        return dominant_kernel(self.precision, self.model.feature_dim_size)
 
     def roofline(self, name, kernel_ms, launches, peaks, flops, ncu_summary=None):
         return roofline(self.model, self.precision, name, kernel_ms, launches, peaks, flops, ncu_summary)
@@ -295,7 +300,7 @@ class UnSupTrainer:
         return node_loss
 
     def dominant_kernel(self):
-        return dominant_kernel(self.model.precision)
+        return dominant_kernel(self.model.precision, self.model.feature_dim_size)
 
     def roofline(self, name, kernel_ms, launches, peaks, flops, ncu_summary=None):
         return roofline(self.model, self.model.precision, name, kernel_ms, launches, peaks, flops, ncu_summary)

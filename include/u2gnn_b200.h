@@ -234,6 +234,13 @@ int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const void* y1_img, const
                      int64_t M, int d, int ff, const void* packed, float hidden_scale, uint64_t seed, uint32_t stream_hidden, int thr,
                      float* dy1, float* dW1, float* db1, float* dW2, void* workspace, size_t workspace_bytes, u2gnn_stream_t stream);
 
+/* ---- bf16 FFN for 64 < d <= 128 (csrc/ffn_wide.cu; BASELINE.json configs[2], d = 65): the FFN runs as the general tcgen05 GEMMs
+ *      below with the [M, ff] hidden materialised in bf16; these are the elementwise steps between them (ReLU + dropout of
+ *      transformer.py:977-982 and their autograd).  fwd: h <- relu(h) * keep * scale in place (keep = engine dropout stream over
+ *      element row * ff + col; ff a multiple of 32);  bwd: dh <- (h > 0) ? dh * scale : 0 with h the saved forward result. */
+int u2gnn_relu_dropout_bf16(void* h, int64_t M, int ff, uint64_t seed, uint32_t rng_stream, int thr, float scale, u2gnn_stream_t stream);
+int u2gnn_relu_dropout_bwd_bf16(void* dh, const void* h, int64_t M, int ff, float scale, u2gnn_stream_t stream);
+
 /* ---- bf16 tensor-core GEMMs for the attention-block projections of the bf16 mode (csrc/gemm_tc.cu): the
  *      F.linear calls inside nn.MultiheadAttention (in_proj / out_proj) and their autograd.
  *      rows : C[M,N] = A[M,K] W^T (+ bias) (+ beta*C);  W is [N,K] (w_kn = 0) or [K,N] (w_kn = 1); K, N <= 256

@@ -150,3 +150,71 @@ def test_bf16_training_tracks_fp32_over_120_steps(U):
     assert f[-1] < 0.7 * f[0] and h[-1] < 0.7 * h[0], (f, h)             # both learn
     assert abs(h.mean() - f.mean()) <= 5e-2 * f.mean(), (f, h)
     assert (np.abs(h - f) / f).max() <= 0.25, (f, h)
+
+
+def test_d65_bf16_ffn_matches_reference_fixture(U):
+    """configs[2] (IMDBBINARY shape, d = 65) in its named precision: for 64 < d <= 128 `precision="bf16"` runs the FFN as tcgen05 GEMMs
+    with the hidden materialised in bf16 (engine.ffn_wide_fwd / _bwd), the attention block in fp32.  Against the reference-generated
+    fixture `sup_neighbors_d65`: eval scores and p = 0 loss within 2e-2, every gradient norm-wise within 5e-2."""
+    from conftest import load_golden, split_case
+    c = load_golden("sup_neighbors_d65")
+    params, grads, _ = split_case(c)
+    k, d, ff, T, L, C = [int(v) for v in c["meta"]]
+    assert d == 65
+    m = U.TransformerU2GNN(d, ff, C, T, 0.5, L, attn_axis="neighbors", precision="bf16").cuda()
+    m.load_state_dict({n: torch.from_numpy(v) for n, v in params.items()})
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    m.eval()
+    with torch.no_grad():
+        s = m(dev(c["input_x"]), dev(c["rowptr"]), dev(c["X"]))
+    assert np.abs(s.cpu().numpy() - c["eval_scores"]).max() <= 2e-2 * np.abs(c["eval_scores"]).max()
+    m.train(); m.encoder_dropout = 0.0
+    for dr in m.dropouts:
+        dr.p = 0.0
+    s = m(dev(c["input_x"]), dev(c["rowptr"]), dev(c["X"]))
+    soft = U.label_smoothing(dev(c["labels"]), C)
+    loss = torch.mean(torch.sum(-soft * torch.nn.functional.log_softmax(s, dim=1), 1))
+    assert abs(loss.item() - float(c["loss"])) <= 2e-2 * abs(float(c["loss"]))
+    loss.backward()
+    gmax = max(np.linalg.norm(v) for v in grads.values())
+    for n, p in m.named_parameters():
+        if np.linalg.norm(grads[n]) < 1e-3 * gmax:
+            continue
+        assert _nrm(_np(p.grad), grads[n].astype(np.float64)) < 5e-2, n
+
+
+@pytest.mark.parametrize("d,ff,p", [(65, 1024, 0.5), (100, 320, 0.5), (128, 256, 0.0)])
+def test_wide_ffn_forward_backward_vs_fp64_oracle(U, d, ff, p):
+    """engine.ffn_wide_fwd / _bwd (64 < d <= 128) with dropout ON against the fp64 arithmetic of transformer.py:977-982 and its
+    autograd, using the engine's dropout stream (oracle.dropout_keep_mask)."""
+    from u2gnn_b200 import engine as E
+    M = 700
+    thr = E.dropout_threshold(p)
+    scale = 256.0 / (256.0 - thr) if thr else 1.0
+    rng = np.random.default_rng(d + ff)
+    y1 = rng.standard_normal((M, d)).astype(np.float32)
+    prm = {"linear1.weight": (rng.standard_normal((ff, d)) / np.sqrt(d)).astype(np.float32), "linear1.bias": (0.1 * rng.standard_normal(ff)).astype(np.float32),
+           "linear2.weight": (rng.standard_normal((d, ff)) / np.sqrt(ff)).astype(np.float32), "linear2.bias": (0.1 * rng.standard_normal(d)).astype(np.float32)}
+    df = rng.standard_normal((M, d)).astype(np.float32)
+    dz = rng.standard_normal((M, d)).astype(np.float32)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    pt = {n: dev(v) for n, v in prm.items()}
+    gt = {n: torch.zeros_like(v) for n, v in pt.items()}
+    SEED, ST = 0xC0FFEE, 77
+    f, h = E.ffn_wide_fwd(dev(y1), M, d, ff, pt, SEED, ST, thr)
+    dzt = dev(dz)
+    dy1 = E.ffn_wide_bwd(dev(df), dzt, dev(y1), h, M, d, ff, pt, gt, thr)
+    torch.cuda.synchronize()
+    keep = np.ones((M, ff))
+    if thr:
+        keep = O.dropout_keep_mask(SEED, ST, M * ff, p)[0].reshape(M, ff).astype(np.float64)
+    P = {n: v.astype(np.float64) for n, v in prm.items()}
+    pre = y1.astype(np.float64) @ P["linear1.weight"].T + P["linear1.bias"]
+    hid = np.maximum(pre, 0) * keep * scale
+    f_o = hid @ P["linear2.weight"].T + P["linear2.bias"]
+    dh = (df.astype(np.float64) @ P["linear2.weight"]) * keep * scale * (pre > 0)
+    ref = {"f": f_o, "dy1": dz + dh @ P["linear1.weight"], "linear1.weight": dh.T @ y1, "linear1.bias": dh.sum(0), "linear2.weight": df.T.astype(np.float64) @ hid}
+    got = {"f": _np(f), "dy1": _np(dy1), "linear1.weight": _np(gt["linear1.weight"]), "linear1.bias": _np(gt["linear1.bias"]), "linear2.weight": _np(gt["linear2.weight"])}
+    assert np.abs(got["f"] - ref["f"]).max() <= 2e-2 * np.abs(ref["f"]).max()
+    for n in ref:
+        assert _nrm(got[n], ref[n]) < 5e-2, n
