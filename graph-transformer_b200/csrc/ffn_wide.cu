@@ -47,7 +47,28 @@ __global__ void __launch_bounds__(256) relu_dropout_bwd_bf16_kernel(__nv_bfloat1
     }
 }
 
+// fp32 rows [M, d] -> bf16 rows [M, dp] zero-padded (dp a multiple of 8, >= d): the aligned operand copy the general GEMM kernels
+// stream with 16-byte accesses (rows of 65 floats are not 16-byte aligned: their scalar staging path ran 10x below HBM speed)
+__global__ void __launch_bounds__(256) pad_rows_bf16_kernel(const float* __restrict__ src, int64_t M, int d, __nv_bfloat16* __restrict__ dst, int dp) {
+    const int64_t total = M * (int64_t)(dp / 2);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = t / (dp / 2);
+        const int c = (int)(t - row * (dp / 2)) * 2;
+        const float a = (c < d) ? __ldg(src + row * d + c) : 0.0f;
+        const float b = (c + 1 < d) ? __ldg(src + row * d + c + 1) : 0.0f;
+        reinterpret_cast<__nv_bfloat162*>(dst)[t] = __floats2bfloat162_rn(a, b);
+    }
+}
+
 }  // namespace
+
+extern "C" int u2gnn_pad_rows_bf16(const float* src, int64_t M, int d, void* dst, int dp, u2gnn_stream_t stream) {
+    if (!src || !dst || M < 0 || d < 1 || dp < d || (dp & 7)) return U2GNN_EINVAL;
+    if (reinterpret_cast<uintptr_t>(dst) % 16) return U2GNN_EALIGN;
+    if (M == 0) return U2GNN_OK;
+    pad_rows_bf16_kernel<<<grid_for(M * (int64_t)(dp / 2), 256, 8), 256, 0, as_stream(stream)>>>(src, M, d, static_cast<__nv_bfloat16*>(dst), dp);
+    U2GNN_CHECK_LAUNCH();
+}
 
 extern "C" int u2gnn_relu_dropout_bf16(void* h, int64_t M, int ff, uint64_t seed, uint32_t rng_stream, int thr, float scale,
                                        u2gnn_stream_t stream) {

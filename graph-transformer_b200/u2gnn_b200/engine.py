@@ -453,51 +453,77 @@ def ffn_wide_supported(d, ff):
     return 64 < d <= 128 and ff % 64 == 0 and ff >= 64
 
 
+WIDE_DP = 128      # padded feature size of the wide path's operand copies (two 64-column K atoms, 256-byte bf16 rows)
+
+
+def _pad_bf16(x, M, d):
+    out = torch.empty((M, WIDE_DP), dtype=torch.bfloat16, device=x.device)
+    LIB.call("u2gnn_pad_rows_bf16", _ptr(x), M, d, _ptr(out), WIDE_DP, _stream())
+    return out
+
+
+def _pad_cols(W, d):
+    """[n, d] fp32 weight -> [n, WIDE_DP] zero-padded (weights only: plumbing, 4 * n * 128 bytes)."""
+    out = torch.zeros((W.shape[0], WIDE_DP), dtype=torch.float32, device=W.device)
+    out[:, :d].copy_(W)
+    return out
+
+
 def ffn_wide_fwd(y1, Mq, d, ff, p, seed, stream_hidden, thr):
-    """f = linear2(dropout(relu(linear1(y1)))) for 64 < d <= 128 (transformer.py:977-982).  Returns (f [Mq, d] fp32, h [Mq, ff] bf16 =
-    the hidden after ReLU, dropout and its 1/(1-p) scale, saved for the backward)."""
+    """f = linear2(dropout(relu(linear1(y1)))) for 64 < d <= 128 (transformer.py:977-982).  Returns (f [Mq, d] fp32, saved) with
+    saved = (h [Mq, ff] bf16: the hidden after ReLU, dropout and its 1/(1-p) scale; y1p [Mq, 128] bf16: the padded operand copy).
+    Every GEMM operand is a 16-byte-aligned bf16 / fp32 buffer with a 128-column feature stride; results are copied into the
+    d-strided tensors of the module boundary by u2gnn_copy_rows."""
     dev = y1.device
     s = _stream()
+    y1p = _pad_bf16(y1, Mq, d)
+    W1p = _pad_cols(p["linear1.weight"], d)                       # [ff, 128]
+    W2Tp = _pad_cols(p["linear2.weight"].t(), d)                  # [ff, 128]
+    b2p = torch.zeros(WIDE_DP, dtype=torch.float32, device=dev)
+    b2p[:d].copy_(p["linear2.bias"])
+    b1 = p["linear1.bias"]
     h = torch.empty((Mq, ff), dtype=torch.bfloat16, device=dev)
-    W1, b1, W2, b2 = p["linear1.weight"], p["linear1.bias"], p["linear2.weight"], p["linear2.bias"]
     for j in range(0, ff, 256):                      # N slices of linear1 (the rows kernel holds N <= 256 accumulator columns)
         n = min(256, ff - j)
-        LIB.call("u2gnn_gemm_tc_rows_ex", _ptr(y1), 0, Mq, d, d, _ptr(W1) + 4 * j * d, 0, n, _ptr(b1) + 4 * j, 0.0,
+        LIB.call("u2gnn_gemm_tc_rows_ex", _ptr(y1p), 1, Mq, WIDE_DP, WIDE_DP, _ptr(W1p) + 4 * j * WIDE_DP, 0, n, _ptr(b1) + 4 * j, 0.0,
                  _ptr(h) + 2 * j, 1, ff, s)
     scale = 256.0 / (256.0 - thr) if thr else 1.0
     LIB.call("u2gnn_relu_dropout_bf16", _ptr(h), Mq, ff, seed, stream_hidden, thr, scale, s)
-    f = torch.empty((Mq, d), dtype=torch.float32, device=dev)
-    W2T = W2.t().contiguous()                        # [ff, d]: a K slice of linear2 is then a contiguous [K, N] block (weights only: 4 * d * ff bytes)
-    for j in range(0, ff, 256):                      # K slices of linear2, accumulated into f
+    fp = torch.empty((Mq, WIDE_DP), dtype=torch.float32, device=dev)
+    for j in range(0, ff, 256):                      # K slices of linear2, accumulated into fp
         k = min(256, ff - j)
-        LIB.call("u2gnn_gemm_tc_rows_ex", _ptr(h) + 2 * j, 1, Mq, k, ff, _ptr(W2T) + 4 * j * d, 1, d, _ptr(b2) if j == 0 else 0,
-                 0.0 if j == 0 else 1.0, _ptr(f), 0, d, s)
+        LIB.call("u2gnn_gemm_tc_rows_ex", _ptr(h) + 2 * j, 1, Mq, k, ff, _ptr(W2Tp) + 4 * j * WIDE_DP, 1, WIDE_DP, _ptr(b2p) if j == 0 else 0,
+                 0.0 if j == 0 else 1.0, _ptr(fp), 0, WIDE_DP, s)
+    f = torch.empty((Mq, d), dtype=torch.float32, device=dev)
+    LIB.call("u2gnn_copy_rows", _ptr(fp), WIDE_DP, _ptr(f), d, Mq, d, 0, s)
     if LIB.timed is not None:                        # both GEMMs go through the rows entry point: 2 x (2 M d ff)
         FLOPS["u2gnn_gemm_tc_rows_ex"] = FLOPS.get("u2gnn_gemm_tc_rows_ex", 0) + 4 * Mq * d * ff
-    return f, h
+    return f, (h, y1p)
 
 
-def ffn_wide_bwd(df, dz, y1, h, Mq, d, ff, p, g, thr):
+def ffn_wide_bwd(df, dz, saved, Mq, d, ff, p, g, thr):
     """Backward of ffn_wide_fwd: dy1 = dz + dPre W1 (accumulated INTO dz and returned), dW1 / db1 / dW2 accumulated into g
-    (db2 = colsum(df) is the caller's).  df [Mq, d] fp32 = gradient at the linear2 output, h = the saved bf16 hidden."""
+    (db2 = colsum(df) is the caller's).  df [Mq, d] fp32 = gradient at the linear2 output."""
     dev = df.device
     s = _stream()
-    W1, W2 = p["linear1.weight"], p["linear2.weight"]
+    h, y1p = saved
     scale = 256.0 / (256.0 - thr) if thr else 1.0
-    W2T = W2.t().contiguous()                        # [ff, d] = [N, K] for dH = df W2
+    dfp = _pad_bf16(df, Mq, d)
+    W1p = _pad_cols(p["linear1.weight"], d)                       # [ff, 128]: rows j.. are a contiguous [K, N] block for dy1
+    W2Tp = _pad_cols(p["linear2.weight"].t(), d)                  # [ff, 128] = [N, K] for dH = df W2
     dh = torch.empty((Mq, ff), dtype=torch.bfloat16, device=dev)
     for j in range(0, ff, 256):
         n = min(256, ff - j)
-        LIB.call("u2gnn_gemm_tc_rows_ex", _ptr(df), 0, Mq, d, d, _ptr(W2T) + 4 * j * d, 0, n, 0, 0.0, _ptr(dh) + 2 * j, 1, ff, s)
+        LIB.call("u2gnn_gemm_tc_rows_ex", _ptr(dfp), 1, Mq, WIDE_DP, WIDE_DP, _ptr(W2Tp) + 4 * j * WIDE_DP, 0, n, 0, 0.0, _ptr(dh) + 2 * j, 1, ff, s)
     # dW2[d, ff] += df^T h: the weight-gradient kernel takes at most 64 columns of its second operand, so 64-wide slices of h;
-    # each slice's [d, 64] result is added into its columns of dW2
+    # each slice's [128, 64] result (rows >= d are the zero padding) is added into its columns of dW2
     n_sl = ff // 64
-    tmp = torch.zeros((n_sl, d * 64), dtype=torch.float32, device=dev)
+    tmp = torch.zeros((n_sl, WIDE_DP * 64), dtype=torch.float32, device=dev)
     for i in range(n_sl):
-        LIB.call("u2gnn_gemm_tc_wgrad_ex", _ptr(df), 0, Mq, d, d, _ptr(h) + 2 * 64 * i, 1, 64, ff, _ptr(tmp) + 4 * i * d * 64, 0, s)
-        LIB.call("u2gnn_copy_rows", _ptr(tmp) + 4 * i * d * 64, 64, _ptr(g["linear2.weight"]) + 4 * 64 * i, ff, d, 64, 1, s)
+        LIB.call("u2gnn_gemm_tc_wgrad_ex", _ptr(dfp), 1, Mq, WIDE_DP, WIDE_DP, _ptr(h) + 2 * 64 * i, 1, 64, ff, _ptr(tmp) + 4 * i * WIDE_DP * 64, 0, s)
+        LIB.call("u2gnn_copy_rows", _ptr(tmp) + 4 * i * WIDE_DP * 64, 64, _ptr(g["linear2.weight"]) + 4 * 64 * i, ff, d, 64, 1, s)
     LIB.call("u2gnn_relu_dropout_bwd_bf16", _ptr(dh), _ptr(h), Mq, ff, scale, s)            # dh is now dPre
-    # dW1[ff, d] += dPre^T y1, db1 += colsum(dPre): 256-row slices of dW1 x (64 | d - 64)-column blocks of y1
+    # dW1[ff, d] += dPre^T y1, db1 += colsum(dPre): 256-row slices of dW1 x two 64-column blocks of the padded y1
     blocks = [(0, 64), (64, d - 64)]
     n_a = (ff + 255) // 256
     tmp1 = torch.zeros((n_a, 2, 256 * 64), dtype=torch.float32, device=dev)
@@ -505,12 +531,15 @@ def ffn_wide_bwd(df, dz, y1, h, Mq, d, ff, p, g, thr):
         n1 = min(256, ff - 256 * i)
         for bi, (c0, nc) in enumerate(blocks):
             t = _ptr(tmp1) + 4 * (i * 2 + bi) * 256 * 64
-            LIB.call("u2gnn_gemm_tc_wgrad_ex", _ptr(dh) + 2 * 256 * i, 1, Mq, n1, ff, _ptr(y1) + 4 * c0, 0, nc, d, t,
+            LIB.call("u2gnn_gemm_tc_wgrad_ex", _ptr(dh) + 2 * 256 * i, 1, Mq, n1, ff, _ptr(y1p) + 2 * c0, 1, 64, WIDE_DP, t,
                      (_ptr(g["linear1.bias"]) + 4 * 256 * i) if bi == 0 else 0, s)
-            LIB.call("u2gnn_copy_rows", t, nc, _ptr(g["linear1.weight"]) + 4 * (256 * i * d + c0), d, n1, nc, 1, s)
-    for j in range(0, ff, 256):                      # dy1 = dz + dPre W1 (K slices; W1 rows j.. are a contiguous [K, N] block)
+            LIB.call("u2gnn_copy_rows", t, 64, _ptr(g["linear1.weight"]) + 4 * (256 * i * d + c0), d, n1, nc, 1, s)
+    dyp = torch.empty((Mq, WIDE_DP), dtype=torch.float32, device=dev)
+    for j in range(0, ff, 256):                      # dPre W1 (K slices; W1p rows j.. are a contiguous [K, N] block)
         k = min(256, ff - j)
-        LIB.call("u2gnn_gemm_tc_rows_ex", _ptr(dh) + 2 * j, 1, Mq, k, ff, _ptr(W1) + 4 * j * d, 1, d, 0, 1.0, _ptr(dz), 0, d, s)
+        LIB.call("u2gnn_gemm_tc_rows_ex", _ptr(dh) + 2 * j, 1, Mq, k, ff, _ptr(W1p) + 4 * j * WIDE_DP, 1, WIDE_DP, 0, 0.0 if j == 0 else 1.0,
+                 _ptr(dyp), 0, WIDE_DP, s)
+    LIB.call("u2gnn_copy_rows", _ptr(dyp), WIDE_DP, _ptr(dz), d, Mq, d, 1, s)               # dy1 = dz + dPre W1
     if LIB.timed is not None:                        # dH and dy1 go through the rows entry point (the two weight gradients through wgrad_ex)
         FLOPS["u2gnn_gemm_tc_rows_ex"] = FLOPS.get("u2gnn_gemm_tc_rows_ex", 0) + 4 * Mq * d * ff
     return dz
@@ -557,7 +586,7 @@ def encoder_layer_bwd(dy2, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
         if df is dz2:                    # no output dropout: df aliases dz2, which ffn_wide_bwd accumulates into
             df = dz2.clone()
         LIB.call("u2gnn_colsum", _ptr(df), Mq, d, d, _ptr(g["linear2.bias"]), 1, _stream())
-        ffn_wide_bwd(df, dz2, sv.y1, sv.hd, Mq, d, ff, p, g, thr)
+        ffn_wide_bwd(df, dz2, sv.hd, Mq, d, ff, p, g, thr)
     elif sv.packed is not None:
         # fused tcgen05 backward: hidden and its gradient recomputed on chip
         if df is dz2:                    # no output dropout: df aliases dz2, which the weight-gradient kernel still reads

@@ -239,6 +239,8 @@ int u2gnn_ffn_tc_bwd(const float* y1, const float* df, const void* y1_img, const
  *      transformer.py:977-982 and their autograd).  fwd: h <- relu(h) * keep * scale in place (keep = engine dropout stream over
  *      element row * ff + col; ff a multiple of 32);  bwd: dh <- (h > 0) ? dh * scale : 0 with h the saved forward result. */
 int u2gnn_relu_dropout_bf16(void* h, int64_t M, int ff, uint64_t seed, uint32_t rng_stream, int thr, float scale, u2gnn_stream_t stream);
+/* fp32 rows [M, d] -> bf16 rows [M, dp] zero-padded (dp a multiple of 8): the 16-byte-aligned operand copy of y1 / dF the GEMMs stream */
+int u2gnn_pad_rows_bf16(const float* src, int64_t M, int d, void* dst, int dp, u2gnn_stream_t stream);
 int u2gnn_relu_dropout_bwd_bf16(void* dh, const void* h, int64_t M, int ff, float scale, u2gnn_stream_t stream);
 
 /* ---- bf16 tensor-core GEMMs for the attention-block projections of the bf16 mode (csrc/gemm_tc.cu): the

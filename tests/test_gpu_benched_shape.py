@@ -203,7 +203,7 @@ def test_wide_ffn_forward_backward_vs_fp64_oracle(U, d, ff, p):
     SEED, ST = 0xC0FFEE, 77
     f, h = E.ffn_wide_fwd(dev(y1), M, d, ff, pt, SEED, ST, thr)
     dzt = dev(dz)
-    dy1 = E.ffn_wide_bwd(dev(df), dzt, dev(y1), h, M, d, ff, pt, gt, thr)
+    dy1 = E.ffn_wide_bwd(dev(df), dzt, h, M, d, ff, pt, gt, thr)
     torch.cuda.synchronize()
     keep = np.ones((M, ff))
     if thr:
