@@ -459,3 +459,22 @@ def test_sampled_softmax_with_pregathered_rows_equals_plain_path(U):
     full = out["rows"][2].clone()
     full.index_add_(0, ids, out["rows"][3])
     assert (full - out["plain"][2]).abs().max().item() <= 1e-5 * out["plain"][2].abs().max().item()
+
+
+def test_device_sampler_rounding_sweep_against_compiled_reference(U):
+    """the device sampler's bit-compatibility rests on device exp() agreeing with glibc exp() at the lround
+    boundaries of value = lround(exp(x ln N)) - 1 (Log_Uniform_Sampler.cpp:57-71).  Sweep: 9 range sizes (primes, powers of two,
+    the cfg4 table) x large unique-sample counts = 2.3 M draws in total, id sequence and try count against the reference class
+    compiled from its own sources (oracle/_ref) or, where that is absent, the C restatement."""
+    from oracle.sampler import OracleSampler, RefSampler
+    checker = RefSampler if RefSampler.available() else OracleSampler
+    draws = 0
+    for V, ns in [(1000, 600), (4096, 3000), (12345, 9000), (99991, 60000), (65536, 40000), (1 << 20, 150000), (2540000, 200000),
+                  (10 ** 7, 250000), (2 ** 31 - 2, 100000)]:
+        a, b = U.LogUniformSampler(V), checker(V)
+        ids = a.sample_device(ns).cpu().numpy()
+        oid, tries = b.sample_with_tries(ns)
+        assert int(a.tries.item()) == tries, (V, ns)
+        assert np.array_equal(np.sort(ids), np.sort(np.asarray(oid))), (V, ns)
+        draws += tries
+    assert draws > 2_000_000
