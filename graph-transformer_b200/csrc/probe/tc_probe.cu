@@ -121,6 +121,96 @@ __global__ void __launch_bounds__(512) tmem_bw_kernel(int warps, int iters, int 
 }
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------
+// cta_group::2 rate probe: a CLUSTER of two CTAs (one TPC) executes M = 256 MMAs - A rows 0-127 from CTA 0's shared / tensor
+// memory, rows 128-255 from CTA 1's, each CTA holding half of B's N columns - issued by one thread of the leader CTA.
+// Measures the cycles per instruction as tc_probe_kernel does for cta_group::1 (operands are constants; results unused).
+// ---------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mma2_ss_acc(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile("tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, 1;" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+}
+__device__ __forceinline__ void mma2_ts_acc(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc) {
+    asm volatile("tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, 1;" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) tc_probe2_kernel(int N, int ts, int count, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5;
+    const uint32_t rank = cluster_ctarank();
+    for (int e = t; e < 65536 / 4; e += 128) reinterpret_cast<uint32_t*>(smem)[e] = 0x3C003C00u;
+    if (t == 0) { tc::mbar_init(&bar, 1); tc::fence_barrier_init(); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tc::smem_u32(&tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (rank == 0 && warp == 1) {
+        const uint32_t idesc = tc::make_idesc(256, N, 0, 0);
+        const uint64_t ad = tc::make_desc_sw128(tc::smem_u32(smem), 16, 1024);
+        const uint64_t bd = tc::make_desc_sw128(tc::smem_u32(smem + 32768), 16, 1024);
+        const uint32_t at = tmem + 448;
+        const long long t0 = clock64();
+        for (int i = 0; i < count; i += 4) {
+            if (tc::elect_one()) {
+                if (ts) {
+                    mma2_ts_acc(tmem, at, bd, idesc);
+                    mma2_ts_acc(tmem, at + 8, bd + 2, idesc);
+                    mma2_ts_acc(tmem, at + 16, bd + 4, idesc);
+                    mma2_ts_acc(tmem, at + 24, bd + 6, idesc);
+                } else {
+                    mma2_ss_acc(tmem, ad, bd, idesc);
+                    mma2_ss_acc(tmem, ad + 2, bd + 2, idesc);
+                    mma2_ss_acc(tmem, ad + 4, bd + 4, idesc);
+                    mma2_ss_acc(tmem, ad + 6, bd + 6, idesc);
+                }
+            }
+            __syncwarp();
+        }
+        const long long t1 = clock64();
+        if (tc::elect_one())
+            asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(tc::smem_u32(&bar)),
+                         "h"((uint16_t)3)
+                         : "memory");
+        __syncwarp();
+        tc::mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        if (t == 32) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    } else if (rank == 1 && t == 0) {
+        tc::mbar_wait(&bar, 0);                  // the multicast commit arrives on the peer's barrier too
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+}  // namespace
+
+extern "C" int u2gnn_tc_probe2(int N, int ts, int count, long long* out, u2gnn_stream_t stream) {
+    if (!out || N < 32 || N > 256 || N % 32 || count < 4 || ts < 0 || ts > 1) return U2GNN_EINVAL;
+    const int smem = 65536 + 1024;
+    cudaFuncSetAttribute(tc_probe2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    tc_probe2_kernel<<<2, 128, smem, as_stream(stream)>>>(N, ts, count, out);
+    U2GNN_CHECK_LAUNCH();
+}
+
 extern "C" int u2gnn_tmem_bw_probe(int warps, int iters, int batch, long long* out, u2gnn_stream_t stream) {
     if (!out || warps < 1 || warps > 16 || iters < 1) return U2GNN_EINVAL;
     tmem_bw_kernel<<<1, 512, 0, as_stream(stream)>>>(warps, iters, batch, out);

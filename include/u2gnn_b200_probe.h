@@ -25,6 +25,8 @@ int u2gnn_tc_selftest(int mode, const float* A, const float* B, float* C, int K,
 
 /* tcgen05.mma rate probe (tools/probe_mma.py): out[0] = issue cycles, out[1] = issue+execute cycles of `count` MMAs */
 int u2gnn_tc_probe(int N, int ts, int rotate, int count, long long* out, u2gnn_stream_t stream);
+/* the same for cta_group::2 (a cluster of two CTAs, M = 256; tools/probe_mma2.py): N a multiple of 32, ts 0 = SS, 1 = A in tensor memory */
+int u2gnn_tc_probe2(int N, int ts, int count, long long* out, u2gnn_stream_t stream);
 /* L2 reduction throughput probe (tools/probe_red.py): `groups` CTAs add into the same 32 KB tile, tile after tile;
    mode 0 red.v4.f32, 1 scalar atomicAdd, 2 plain stores, 3 red.v4.f32 thread-per-row */
 int u2gnn_red_probe(float* buf, int64_t n_tiles, int groups, int mode, u2gnn_stream_t stream);
