@@ -33,6 +33,7 @@ FUSE_PROJ_BWD = os.environ.get("U2GNN_FUSE_PROJ_BWD", "1") != "0"         # bf16
 FUSE_INPROJ_ATTN = os.environ.get("U2GNN_FUSE_INPROJ_ATTN", "1") != "0"   # bf16 mode, d = 64: in_proj inside the attention-forward kernel (qkv written once, never re-read in the forward)
 FFN_FWD_MASK = os.environ.get("U2GNN_FFN_FWD_MASK", "1") != "0"          # bf16 mode: the FFN forward leaves the 1-bit live-and-kept mask of the hidden for the backward
 FFN_BWD_IMAGES = os.environ.get("U2GNN_FFN_BWD_IMAGES", "1") != "0"      # bf16 mode, d = 64: y1 / dF leave their producers as bf16 tile images (no conversion pass in the FFN backward)
+FP32_TC = os.environ.get("U2GNN_FP32_TC", "1") != "0"                     # fp32 mode: linear layers as three-product bf16-split tcgen05 GEMMs (csrc/gemm_split.cu) instead of the CUDA-core SGEMM
 FLOPS = {}    # entry point -> algorithmic flops issued while LIB.timed is active (bench.py roofline)
 BYTES = {}    # entry point -> algorithmic HBM bytes (the tensors the call must read + write once) while LIB.timed is active
 
@@ -235,6 +236,46 @@ def wgrad(dout, M_rows, n_out, inp, n_in, dW, db=None):
         LIB.call("u2gnn_colsum", _ptr(dout), M_rows, n_out, n_out, _ptr(db), 1, _stream())
 
 
+def linear_fp32(A, M, K, W, w_kn, N, C, bias=None, relu=False, drop=None, aux=None, aux_scale=1.0, beta=0.0):
+    """fp32 linear layer C[M,N] = epi(A[M,K] op(W) + bias) (+ beta C); W is [N,K] (w_kn=0, F.linear's layout) or [K,N] (w_kn=1, the
+    input-gradient product).  FP32_TC: tensor cores with the three-product bf16 split (fp32 accuracy); else the CUDA-core SGEMM."""
+    if not FP32_TC:
+        return sgemm(0, 1 - w_kn, M, N, K, A, K, W, N if w_kn else K, C, N, bias=bias, relu=relu, drop=drop, aux=aux,
+                     ldaux=N if aux is not None else 0, aux_scale=aux_scale, beta=beta)
+    epi, seed, stream, thr = 0, 0, 0, 0
+    if bias is not None:
+        epi |= 1
+    if relu:
+        epi |= 2
+    if drop is not None and drop[2] > 0:
+        epi |= 4
+        seed, stream, thr = drop[0], drop[1], drop[2]
+    if aux is not None:
+        epi |= 8
+    if LIB.timed is not None:
+        FLOPS["u2gnn_gemm_split_rows"] = FLOPS.get("u2gnn_gemm_split_rows", 0) + 2 * M * N * K
+    LIB.call("u2gnn_gemm_split_rows", _ptr(A), M, K, K, _ptr(W), int(w_kn), N if w_kn else K, N, _ptr(bias), epi, seed, stream, thr, 0,
+             _ptr(aux), N if aux is not None else 0, aux_scale, beta, _ptr(C), N, _stream())
+    return C
+
+
+def wgrad_fp32(dout, M_rows, n_out, inp, n_in, dW, db=None):
+    """dW[n_out, n_in] += dout[M, n_out]^T @ inp[M, n_in];  db[n_out] += colsum(dout)  (fp32 mode)."""
+    if not FP32_TC:
+        return wgrad(dout, M_rows, n_out, inp, n_in, dW, db)
+    if M_rows == 0:
+        return
+    if LIB.timed is not None:
+        FLOPS["u2gnn_gemm_split_wgrad"] = FLOPS.get("u2gnn_gemm_split_wgrad", 0) + 2 * M_rows * n_out * n_in
+    if n_in > n_out:
+        # the wide side streams as the 128-column operand (fewer passes over the rows); the destination is then transposed
+        LIB.call("u2gnn_gemm_split_wgrad", _ptr(inp), M_rows, n_in, n_in, _ptr(dout), n_out, n_out, _ptr(dW), 1, n_in, 0, _stream())
+        if db is not None:
+            LIB.call("u2gnn_colsum", _ptr(dout), M_rows, n_out, n_out, _ptr(db), 1, _stream())
+    else:
+        LIB.call("u2gnn_gemm_split_wgrad", _ptr(dout), M_rows, n_out, n_out, _ptr(inp), n_in, n_in, _ptr(dW), n_in, 1, _ptr(db), _stream())
+
+
 def linear_tc(A, M, K, W, w_kn, N, bias=None, beta=0.0, out=None, out_bf16=False):
     """bf16 tensor-core projection: out[M,N] = A[M,K] W^T (+bias) (+beta*out).  A may be fp32 or bf16 (the dtype the
     producer stored); out_bf16 stores the result rounded to bf16 (every consumer rounds it anyway)."""
@@ -377,7 +418,7 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
         qkv = linear_tc(x, M, d, p["self_attn.in_proj_weight"], 0, 3 * d, bias=p["self_attn.in_proj_bias"], out_bf16=tc_attn or tc_last)
     else:
         qkv = torch.empty((M, 3 * d), **f32)
-        sgemm(0, 1, M, 3 * d, d, x, d, p["self_attn.in_proj_weight"], d, qkv, 3 * d, bias=p["self_attn.in_proj_bias"])
+        linear_fp32(x, M, d, p["self_attn.in_proj_weight"], 0, 3 * d, qkv, bias=p["self_attn.in_proj_bias"])
     ctx = torch.empty((Mq, d), dtype=torch.bfloat16 if tc_attn else torch.float32, device=dev)
     if long_seq:
         assert B == 1 and Sq == S
@@ -408,7 +449,7 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
             a = linear_tc(ctx, Mq, d, p["self_attn.out_proj.weight"], 0, d, bias=p["self_attn.out_proj.bias"])
         else:
             a = torch.empty((Mq, d), **f32)
-            sgemm(0, 1, Mq, d, d, ctx, d, p["self_attn.out_proj.weight"], d, a, d, bias=p["self_attn.out_proj.bias"])
+            linear_fp32(ctx, Mq, d, p["self_attn.out_proj.weight"], 0, d, a, bias=p["self_attn.out_proj.bias"])
         if Sq == S:
             xq = x
         else:
@@ -439,10 +480,9 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
         sv.packed = packed
     else:
         hd = torch.empty((Mq, ff), **f32)
-        sgemm(0, 1, Mq, ff, d, y1, d, p["linear1.weight"], d, hd, ff, bias=p["linear1.bias"], relu=True,
-              drop=(seed, drop_ids[2], thr))
+        linear_fp32(y1, Mq, d, p["linear1.weight"], 0, ff, hd, bias=p["linear1.bias"], relu=True, drop=(seed, drop_ids[2], thr))
         f = torch.empty((Mq, d), **f32)
-        sgemm(0, 1, Mq, d, ff, hd, ff, p["linear2.weight"], ff, f, d, bias=p["linear2.bias"])
+        linear_fp32(hd, Mq, ff, p["linear2.weight"], 0, d, f, bias=p["linear2.bias"])
         z2, y2, st2 = add_dropout_ln_fwd(y1, f, Mq, d, (seed, drop_ids[3], thr), p["norm2.weight"], p["norm2.bias"])
     sv.xq, sv.qkv, sv.ctx, sv.z1, sv.st1, sv.y1, sv.hd, sv.z2, sv.st2 = xq, qkv, ctx, z1, st1, y1, hd, z2, st2
     return y2, sv
@@ -601,11 +641,11 @@ def encoder_layer_bwd(dy2, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
                  Mq, d, ff, _ptr(sv.packed), drop_scale, seed, drop_ids[2], thr, _ptr(dy1), _ptr(g["linear1.weight"]),
                  _ptr(g["linear1.bias"]), _ptr(g["linear2.weight"]), _ptr(ws), wsb, _stream())
     else:
-        wgrad(df, Mq, d, sv.hd, ff, g["linear2.weight"], g["linear2.bias"])
+        wgrad_fp32(df, Mq, d, sv.hd, ff, g["linear2.weight"], g["linear2.bias"])
         dhpre = torch.empty((Mq, ff), **f32)
-        sgemm(0, 0, Mq, ff, d, df, d, p["linear2.weight"], ff, dhpre, ff, aux=sv.hd, ldaux=ff, aux_scale=drop_scale)
-        wgrad(dhpre, Mq, ff, sv.y1, d, g["linear1.weight"], g["linear1.bias"])
-        sgemm(0, 0, Mq, d, ff, dhpre, ff, p["linear1.weight"], d, dy1, d, beta=1.0)
+        linear_fp32(df, Mq, d, p["linear2.weight"], 1, ff, dhpre, aux=sv.hd, aux_scale=drop_scale)
+        wgrad_fp32(dhpre, Mq, ff, sv.y1, d, g["linear1.weight"], g["linear1.bias"])
+        linear_fp32(dhpre, Mq, ff, p["linear1.weight"], 1, d, dy1, beta=1.0)
         del dhpre
     return _encoder_attn_bwd(dy1, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_dx)
 
@@ -630,9 +670,9 @@ def _encoder_attn_bwd(dy1, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
         wgrad_tc(da, Mq, d, sv.ctx, d, g["self_attn.out_proj.weight"], g["self_attn.out_proj.bias"])
         dctx = linear_tc(da, Mq, d, p["self_attn.out_proj.weight"], 1, d, out_bf16=tc_attn)
     else:
-        wgrad(da, Mq, d, sv.ctx, d, g["self_attn.out_proj.weight"], g["self_attn.out_proj.bias"])
+        wgrad_fp32(da, Mq, d, sv.ctx, d, g["self_attn.out_proj.weight"], g["self_attn.out_proj.bias"])
         dctx = torch.empty((Mq, d), **f32)
-        sgemm(0, 0, Mq, d, d, da, d, p["self_attn.out_proj.weight"], d, dctx, d)
+        linear_fp32(da, Mq, d, p["self_attn.out_proj.weight"], 1, d, dctx)
     tc_last = sv.qkv.dtype == torch.bfloat16 and Sq == 1
     dqkv = torch.empty((M, 3 * d), dtype=torch.bfloat16 if (tc_attn or tc_last) else torch.float32, device=dev)
     if long_seq:
@@ -662,17 +702,20 @@ def _encoder_attn_bwd(dy1, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
     if tc_proj:
         wgrad_tc(dqkv, M, 3 * d, sv.x, d, g["self_attn.in_proj_weight"], g["self_attn.in_proj_bias"])
     else:
-        wgrad(dqkv, M, 3 * d, sv.x, d, g["self_attn.in_proj_weight"], g["self_attn.in_proj_bias"])
+        wgrad_fp32(dqkv, M, 3 * d, sv.x, d, g["self_attn.in_proj_weight"], g["self_attn.in_proj_bias"])
     if not need_dx:
         return None
     if tc_proj and Sq == S:
         # residual gradient folded into the projection epilogue: dz1 += dqkv W_in (saves the separate axpy pass)
         return linear_tc(dqkv, M, 3 * d, p["self_attn.in_proj_weight"], 1, d, beta=1.0, out=dz1)
+    if FP32_TC and Sq == S:
+        # residual gradient folded into the projection epilogue (beta = 1 over dz1)
+        return linear_fp32(dqkv, M, 3 * d, p["self_attn.in_proj_weight"], 1, d, dz1, beta=1.0)
     if tc_proj:
         dx = linear_tc(dqkv, M, 3 * d, p["self_attn.in_proj_weight"], 1, d)
     else:
         dx = torch.empty((M, d), **f32)
-        sgemm(0, 0, M, d, 3 * d, dqkv, 3 * d, p["self_attn.in_proj_weight"], d, dx, d)
+        linear_fp32(dqkv, M, 3 * d, p["self_attn.in_proj_weight"], 1, d, dx)
     if Sq == S:
         LIB.call("u2gnn_axpy", 1.0, _ptr(dz1), _ptr(dx), M * d, _stream())
     else:

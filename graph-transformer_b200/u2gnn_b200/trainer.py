@@ -90,10 +90,11 @@ def effective_smoothing(eps, classes, style="reference"):
 
 def dominant_kernel(precision, d=64):
     """Entry point whose launches bench.py times for the roofline object: the FFN backward (the path's largest dense
-    contraction, tcgen05) in bf16 mode, the CUDA-core SGEMM in fp32 mode; for 64 < d <= 128 in bf16 mode the FFN runs as
-    general tcgen05 rows GEMMs (engine.ffn_wide_*), which are then what is timed."""
+    contraction, tcgen05) in bf16 mode; in fp32 mode the bf16-split tcgen05 rows GEMM (engine.FP32_TC; the CUDA-core SGEMM when
+    that is switched off); for 64 < d <= 128 in bf16 mode the FFN runs as general tcgen05 rows GEMMs (engine.ffn_wide_*), which
+    are then what is timed."""
     if precision == "fp32":
-        return "u2gnn_sgemm"
+        return "u2gnn_gemm_split_rows" if E.FP32_TC else "u2gnn_sgemm"
     return "u2gnn_gemm_tc_rows_ex" if d > 64 else "u2gnn_ffn_tc_bwd"
 
 
@@ -114,7 +115,8 @@ def roofline(model, precision, name, kernel_ms, launches, peaks, flops, ncu_summ
     return {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": traffic, "launches_timed": launches,
             "avg_launch_ms": kernel_ms / max(launches, 1), "peak_source": which,
-            "note": ("fp32 CUDA-core parity path; the tcgen05 path is --precision bf16" if precision == "fp32"
+            "note": ("fp32 mode on the tensor cores: three-product bf16 split (hi/lo) tcgen05 GEMMs, hidden materialised in fp32; achieved counts the algorithmic 2MNK once (the kernel executes 3x that in bf16 MMAs)" if name == "u2gnn_gemm_split_rows"
+                     else "fp32 CUDA-core parity path; the tcgen05 path is --precision bf16" if precision == "fp32"
                      else "bf16 FFN for 64 < d <= 128: four of its six GEMMs (linear1, linear2, dH, dy1) through the general tcgen05 rows kernel, hidden materialised in bf16"
                      if name == "u2gnn_gemm_tc_rows_ex"
                      else "fused bf16 tcgen05 FFN backward (weight-gradient kernel + input-gradient kernel)")}

@@ -81,6 +81,21 @@ int u2gnn_sgemm(int ta, int tb, int64_t M, int N, int64_t K, float alpha, const 
                 const float* B, int64_t ldb, float beta, float* C, int64_t ldc, const float* bias, int epi,
                 uint64_t seed, uint32_t rng_stream, int thr, int64_t rng_row0, const float* aux, int64_t ldaux,
                 float aux_scale, int splitk, u2gnn_stream_t stream);
+/* The same products ON THE TENSOR CORES at fp32 accuracy (csrc/gemm_split.cu): every fp32 operand value is staged as
+ * hi = bf16(a), lo = bf16(a - hi) and every product evaluated as A_hi B_hi + A_lo B_hi + A_hi B_lo (three tcgen05.mma per
+ * k-step, fp32 accumulation in tensor memory; relative error of a product <= ~2^-16).  precision="fp32" runs F.linear and its
+ * autograd (linear1 / linear2, in_proj / out_proj of torch/nn/modules/transformer.py:944-982) through these two entry points.
+ *   rows : C[M,N] = epi(A[M,K] op(W) + bias) (+ beta*C);  W[n*ldw+k] (w_kn=0) or W[k*ldw+n] (w_kn=1); epi bits 1 / 2 / 4 / 8 as
+ *          u2gnn_sgemm (dropout on linear index (rng_row0+m)*N+n).  Any M, K, N, lda, ldw, ldc; 16-byte aligned shapes use
+ *          128-bit accesses.
+ *   wgrad: dW[n1*ldw_n1 + n2*ldw_n2] += sum_m A[m*lda+n1] B[m*ldb+n2];  db[n1] += sum_m A[m*lda+n1] (db may be NULL).
+ *          Accumulates with atomics (the destination strides make a transposed gradient a stride swap). */
+int u2gnn_gemm_split_rows(const float* A, int64_t M, int K, int64_t lda, const float* W, int w_kn, int64_t ldw, int N,
+                          const float* bias, int epi, uint64_t seed, uint32_t rng_stream, int thr, int64_t rng_row0,
+                          const float* aux, int64_t ldaux, float aux_scale, float beta, float* C, int64_t ldc,
+                          u2gnn_stream_t stream);
+int u2gnn_gemm_split_wgrad(const float* A, int64_t M, int N1, int64_t lda, const float* B, int N2, int64_t ldb, float* dW,
+                           int64_t ldw_n1, int64_t ldw_n2, float* db, u2gnn_stream_t stream);
 /* out[n] (+)= sum_m A[m*lda+n] */
 int u2gnn_colsum(const float* A, int64_t M, int N, int64_t lda, float* out, int accumulate, u2gnn_stream_t stream);
 
