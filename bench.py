@@ -408,6 +408,11 @@ def run_ours(args, w):
     batches = []                                   # resident batches, cycled over the timed steps
     if w["kind"] == "sup":
         nodes = args.nodes or w["nodes"]
+        if precision == "fp32" and not args.nodes and nodes > 65536:
+            # the fp32 mode keeps the [rows, ff] hidden of every timestep in HBM (8 KB per row and timestep at ff 2048): 65 536
+            # nodes per step is what fits next to the other saved activations; throughput is per node, the batch is the same shape
+            nodes = 65536
+            note = "fp32 mode: micro-batch of 65 536 nodes (the [rows, ff] fp32 hidden is materialised)"
         model = U.TransformerU2GNN(w["d"], w["ff"], w["C"], w["T"], 0.5, w["L"], attn_axis=w["axis"]).cuda()
         trainer = SupTrainer(model, lr=5e-4, precision=precision)
         # ONE global batch (the same on every rank: seeded device generator), sharded by balanced graph ranges

@@ -117,17 +117,18 @@ struct RowsP {
     int a_vec, w_vec, c_vec;
 };
 
-// shared memory: A hi | A lo (16 KB each) | W hi | W lo (16 KB each: <= 128 output columns x 64) | staging (32 KB)
-constexpr uint32_t kRowsSmem = 4 * 16384 + 32768;
+// shared memory: A hi | A lo (16 KB each) | two weight buffers of W hi | W lo (16 KB each: <= 128 output columns x 64).  The
+// fp32 staging of the epilogue (32 KB) lies over the weight buffer the step's own MMAs have just finished with; the other
+// buffer already holds the next step's weights (staged while those MMAs ran).
+constexpr uint32_t kRowsSmem = 2 * 16384 + 2 * 32768;
 
+template <int EPI>        // 0: generic epilogue (runtime flags, any alignment); 1 / 2 / 3: vectorised specialisations (see the copy-out)
 __global__ void __launch_bounds__(kThreads, 2) gemm_split_rows_kernel(const RowsP p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((tc::smem_u32(smem) & 1023u) != 0u) __trap();
     uint8_t* sAh = smem;
     uint8_t* sAl = smem + 16384;
-    uint8_t* sWh = smem + 32768;
-    uint8_t* sWl = smem + 49152;
-    uint8_t* sOut = smem + 65536;
+    uint8_t* sW = smem + 32768;                              // buffer b: hi at sW + b * 32768, lo 16 KB behind it
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -144,7 +145,6 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_split_rows_kernel(const Rows
     const int NSL = (p.N + NSMAX - 1) / NSMAX;
     const int64_t n_tiles = (p.M + TM - 1) / TM;
     const bool w_resident = (KB == 1 && NSL == 1);
-    const bool w_prefetch = (KB > 1);
     const int wq = warp & 3, half = warp >> 2;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
 
@@ -158,55 +158,41 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_split_rows_kernel(const Rows
         const int nw = n_w(ns);
         return p.w_kn ? 16 * ((nw + 63) / 64 * 64) : 16 * ((nw + 15) / 16 * 16);
     };
-    float a[32], w[32];
+    float a[32];
     auto load_a = [&](int64_t tile, int kb) { blk_load<8>(a, a_src(tile, kb), p.lda, a_rv(tile), k_cv(kb), 6, p.a_vec, 2048, tid); };
-    auto load_w = [&](float (&dst)[32], int ns, int kb, int g0) {
-        // groups [g0, g0 + 2048) of the block (one call covers <= 128 x 64 elements)
+    // weights of (ns, kb) -> buffer wb, through short-lived registers (an L2 read: the weights are a few hundred KB)
+    auto stage_w = [&](int ns, int kb, int wb) {
+        float w[32];
         const int nw = n_w(ns);
+        uint8_t* hi = sW + wb * 32768;
         if (!p.w_kn) {
-            // rows = output columns; this call's groups start at row g0 / 16
-            const int r0 = g0 >> 4;
-            blk_load<8>(dst, p.W + ((int64_t)ns * NSMAX + r0) * p.ldw + (int64_t)kb * KC, p.ldw, nw - r0, k_cv(kb), 6, p.w_vec, w_groups(ns) - g0, tid);
+            blk_load<8>(w, p.W + (int64_t)ns * NSMAX * p.ldw + (int64_t)kb * KC, p.ldw, nw, k_cv(kb), 6, p.w_vec, w_groups(ns), tid);
+            blk_store<8>(hi, hi + 16384, w, 6, 0u, p.w_vec, w_groups(ns), tid);
         } else {
             const int cl2 = (nw > 64) ? 7 : 6;
-            blk_load<8>(dst, p.W + (int64_t)kb * KC * p.ldw + (int64_t)ns * NSMAX, p.ldw, k_cv(kb), nw, cl2, p.w_vec, w_groups(ns), tid);
-        }
-    };
-    auto store_w = [&](const float (&src)[32], int ns, int g0) {
-        const int nw = n_w(ns);
-        if (!p.w_kn) {
-            const int r0 = g0 >> 4;
-            blk_store<8>(sWh + r0 * 128, sWl + r0 * 128, src, 6, 0u, p.w_vec, w_groups(ns) - g0, tid);
-        } else {
-            blk_store<8>(sWh, sWl, src, (nw > 64) ? 7 : 6, 8192u, p.w_vec, w_groups(ns), tid);
+            blk_load<8>(w, p.W + (int64_t)kb * KC * p.ldw + (int64_t)ns * NSMAX, p.ldw, k_cv(kb), nw, cl2, p.w_vec, w_groups(ns), tid);
+            blk_store<8>(hi, hi + 16384, w, cl2, 8192u, p.w_vec, w_groups(ns), tid);
         }
     };
 
     int64_t tile = blockIdx.x;
     int ns = 0, kb = 0;
-    bool valid = tile < n_tiles, first = true, pending = false;
+    bool valid = tile < n_tiles, pending = false;
     uint32_t phase = 0;
+    int wb = 0;                                              // weight buffer of the current step
     if (valid) {
         load_a(tile, 0);
-        if (w_prefetch) load_w(w, 0, 0, 0);
+        stage_w(0, 0, 0);
     }
+    const int rr0 = tid >> 4, c4 = tid & 15;                 // copy-out: 16 lanes x float4 per row, rows rr0 + 16 u
     while (valid) {
         const bool a_new = !(KB == 1 && ns > 0);             // K <= 64: the A tile stays staged across the output slices
-        const bool w_new = !(w_resident && !first);          // one chunk, one slice: the weights stay staged for the whole CTA
-        if (pending) {                                       // the previous step's MMAs have read the staged operands
+        if (pending) {                                       // the previous step's MMAs have read the A tile (and the other weight buffer)
             tc::mbar_wait(&bar, phase);
             phase ^= 1;
             pending = false;
         }
         if (a_new) blk_store<8>(sAh, sAl, a, 6, 0u, p.a_vec, 2048, tid);
-        if (w_new) {
-            if (w_prefetch) {
-                store_w(w, ns, 0);
-            } else {
-                load_w(w, ns, kb, 0);
-                store_w(w, ns, 0);
-            }
-        }
         // next step
         int64_t ntile = tile;
         int nns = ns, nkb = kb + 1;
@@ -219,12 +205,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_split_rows_kernel(const Rows
         }
         const bool nvalid = ntile < n_tiles;
         const bool last_k = (kb == KB - 1);
-        auto prefetch = [&]() {
-            if (!nvalid) return;
-            if (!(KB == 1 && nns > 0)) load_a(ntile, nkb);
-            if (w_prefetch) load_w(w, nns, nkb, 0);
-        };
-        if (!last_k) prefetch();                             // in flight under this step's MMAs
+        const bool next_a = nvalid && !(KB == 1 && nns > 0);
         tc::fence_proxy_async();
         tc::tc_fence_before();
         __syncthreads();
@@ -235,8 +216,9 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_split_rows_kernel(const Rows
             if (tc::elect_one()) {
                 const uint32_t idesc = tc::make_idesc(TM, nps, 0, p.w_kn);
                 const uint64_t ah = tc::make_desc_sw128(tc::smem_u32(sAh), 16, 1024), al = tc::make_desc_sw128(tc::smem_u32(sAl), 16, 1024);
-                const uint64_t wh = p.w_kn ? tc::make_desc_sw128(tc::smem_u32(sWh), 8192, 1024) : tc::make_desc_sw128(tc::smem_u32(sWh), 16, 1024);
-                const uint64_t wl = p.w_kn ? tc::make_desc_sw128(tc::smem_u32(sWl), 8192, 1024) : tc::make_desc_sw128(tc::smem_u32(sWl), 16, 1024);
+                const uint32_t w0 = tc::smem_u32(sW) + (uint32_t)wb * 32768u;
+                const uint64_t wh = p.w_kn ? tc::make_desc_sw128(w0, 8192, 1024) : tc::make_desc_sw128(w0, 16, 1024);
+                const uint64_t wl = p.w_kn ? tc::make_desc_sw128(w0 + 16384, 8192, 1024) : tc::make_desc_sw128(w0 + 16384, 16, 1024);
                 const uint32_t wstep = p.w_kn ? 128u : 2u;   // 16 K rows of an MN-major image = 2 048 B; 16 K columns of a K-major one = 32 B
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
@@ -249,13 +231,21 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_split_rows_kernel(const Rows
             __syncwarp();
         }
         pending = true;
+        // under this step's MMAs: the next A chunk starts its way from HBM into registers (unless an epilogue follows: its
+        // registers are needed there) and the next step's weights are staged into the other buffer
+        if (next_a && !last_k) load_a(ntile, nkb);
+        if (nvalid && !w_resident) stage_w(nns, nkb, wb ^ 1);
+        uint8_t* sOut = sW + (w_resident ? 1 : wb) * 32768;   // resident weights live in buffer 0 for the whole CTA
         if (last_k) {
             tc::mbar_wait(&bar, phase);
             phase ^= 1;
             pending = false;
             tc::tc_fence_after();
             // ---- epilogue of (tile, ns): tensor memory -> registers (thread = row) -> XOR-swizzled fp32 staging -> coalesced
-            // 128-bit rows with bias / ReLU / dropout / aux mask / beta, one 64-column piece at a time
+            // 128-bit rows with bias / ReLU / dropout / aux mask / beta, one 64-column piece at a time.  Everything the copy-out
+            // needs from global memory (bias, the aux mask or the old C: 8 rows per thread) is requested BEFORE the block-wide
+            // barrier: a load inside the guarded row loop exposed its full latency per row (ncu: 63 % long-scoreboard stalls
+            // in the dPre product, profiles/r02_ncu_split_v1_stalls.txt).
             const int64_t row0 = tile * TM;
             const int n0 = ns * NSMAX;
             for (int pc = 0; 64 * pc < nps; ++pc) {
@@ -269,65 +259,142 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_split_rows_kernel(const Rows
                     for (int j = 0; j < 8; ++j)
                         *reinterpret_cast<uint4*>(st + (((8 * half + j) ^ (r & 15)) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
-                __syncthreads();
-#pragma unroll 2
-                for (int u = 0; u < 8; ++u) {
-                    const int e = u * kThreads + tid;
-                    const int rr = e >> 4, c4 = e & 15;
-                    const int64_t row = row0 + rr;
-                    const int col = n0 + 64 * pc + 4 * c4;
-                    if (row >= p.M || col >= p.N) continue;
-                    const float4 o = *reinterpret_cast<const float4*>(sOut + rr * 256 + ((c4 ^ (rr & 15)) << 4));
-                    float x[4] = {o.x, o.y, o.z, o.w};
-                    const int nval = (p.N - col < 4) ? p.N - col : 4;
-                    float* out = p.C + row * p.ldc + col;
-                    if (p.c_vec && nval == 4) {
-                        if (p.flags & 1) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                            x[0] += b.x; x[1] += b.y; x[2] += b.z; x[3] += b.w;
-                        }
-                        if (p.flags & 2) {
+                const int col = n0 + 64 * pc + 4 * c4;       // this thread's four columns in every row of the piece
+                if constexpr (EPI != 0) {
+                    // vectorised copy-out, specialised at compile time (the generic version below spent most of its ISSUE slots on
+                    // flag tests, 64-bit index arithmetic and one dropout word per thread and row: 2 700 instructions per thread and
+                    // step, 57 % issue-active - profiles/r02_ncu_split_v2_linear1.txt):
+                    //   EPI 1  bias + ReLU + dropout (linear1)      EPI 2  aux mask (dPre)      EPI 3  bias / beta (everything else)
+                    const bool col_ok = col < p.N;           // N % 4 == 0: whole float4 pieces
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (EPI != 2 && (p.flags & 1) && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                    const bool use_old = (EPI == 3) && (p.beta != 0.0f);
+                    float4 pre[EPI == 1 ? 1 : 8];            // aux mask rows (EPI 2) or old C rows (EPI 3, beta)
+                    if (EPI == 2 || use_old) {
+                        const float* src = (EPI == 2) ? p.aux + (row0 + rr0) * p.ldaux + col : p.C + (row0 + rr0) * p.ldc + col;
+                        const int64_t step = 16 * ((EPI == 2) ? p.ldaux : p.ldc);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.0f);
+                        for (int u = 0; u < (EPI == 1 ? 1 : 8); ++u) {
+                            pre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (col_ok && row0 + rr0 + 16 * u < p.M) pre[u] = *reinterpret_cast<const float4*>(src + u * step);
+                        }
+                    }
+                    // EPI 1 (N % 32 == 0): the piece holds 128 rows x two 32-element groups of the dropout stream = 32 keep words
+                    // per warp (its 16 rows x 2 groups): lane L evaluates the word of (iteration L >> 2, row L >> 1 & 1, group L & 1)
+                    // and the row loop fetches words with one shuffle
+                    uint32_t my_word = 0xFFFFFFFFu;
+                    if (EPI == 1 && p.thr) {
+                        const int64_t wrow = p.rng_row0 + row0 + 2 * warp + ((lane >> 1) & 1) + 16 * (lane >> 2);
+                        my_word = rng_keep_word_lo(p.keys, (uint64_t)wrow * (uint64_t)(p.N >> 5) + (uint64_t)((n0 + 64 * pc) >> 5) + (uint64_t)(lane & 1),
+                                                   p.thr, p.low);
+                    }
+                    __syncthreads();
+                    float* out = p.C + (row0 + rr0) * p.ldc + col;
+                    const int64_t ostep = 16 * p.ldc;
+                    const int src_lane0 = 2 * (lane >> 4) + ((lane >> 3) & 1);
+                    const float keep_scale = p.thr ? p.drop_scale : 1.0f;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int rr = rr0 + 16 * u;
+                        const bool live = (row0 + rr < p.M) && col_ok;
+                        float4 x = *reinterpret_cast<const float4*>(sOut + rr * 256 + ((c4 ^ (rr & 15)) << 4));
+                        if (EPI != 2) { x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w; }
+                        if (EPI == 1) {
+                            const uint32_t kw = __shfl_sync(0xffffffffu, my_word, 4 * u + src_lane0) >> (4 * (c4 & 7));
+                            x.x = (kw & 1u) ? fmaxf(x.x, 0.0f) * keep_scale : 0.0f;
+                            x.y = (kw & 2u) ? fmaxf(x.y, 0.0f) * keep_scale : 0.0f;
+                            x.z = (kw & 4u) ? fmaxf(x.z, 0.0f) * keep_scale : 0.0f;
+                            x.w = (kw & 8u) ? fmaxf(x.w, 0.0f) * keep_scale : 0.0f;
+                        }
+                        if (EPI == 2) {
+                            x.x = pre[u].x > 0.0f ? x.x * p.aux_scale : 0.0f;
+                            x.y = pre[u].y > 0.0f ? x.y * p.aux_scale : 0.0f;
+                            x.z = pre[u].z > 0.0f ? x.z * p.aux_scale : 0.0f;
+                            x.w = pre[u].w > 0.0f ? x.w * p.aux_scale : 0.0f;
+                        }
+                        if (use_old) {
+                            x.x = fmaf(p.beta, pre[EPI == 1 ? 0 : u].x, x.x); x.y = fmaf(p.beta, pre[EPI == 1 ? 0 : u].y, x.y);
+                            x.z = fmaf(p.beta, pre[EPI == 1 ? 0 : u].z, x.z); x.w = fmaf(p.beta, pre[EPI == 1 ? 0 : u].w, x.w);
+                        }
+                        if (live) *reinterpret_cast<float4*>(out + u * ostep) = x;
+                    }
+                } else if (p.c_vec) {
+                    const bool col_ok = col < p.N;           // N % 4 == 0: whole float4 pieces
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if ((p.flags & 1) && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                    const bool use_aux = (p.flags & 8) != 0, use_old = (p.beta != 0.0f);
+                    float4 pre[8];                           // aux mask rows, or the old C rows when there is no aux
+                    if (use_aux || use_old) {
+                        const float* src = use_aux ? p.aux + (row0 + rr0) * p.ldaux + col : p.C + (row0 + rr0) * p.ldc + col;
+                        const int64_t step = 16 * (use_aux ? p.ldaux : p.ldc);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            pre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (col_ok && row0 + rr0 + 16 * u < p.M) pre[u] = *reinterpret_cast<const float4*>(src + u * step);
+                        }
+                    }
+                    __syncthreads();
+                    uint64_t el = (uint64_t)(p.rng_row0 + row0 + rr0) * (uint64_t)p.N + (uint64_t)col;
+                    float* out = p.C + (row0 + rr0) * p.ldc + col;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u, el += 16ull * (uint64_t)p.N, out += 16 * p.ldc) {
+                        const int rr = rr0 + 16 * u;
+                        const bool live = (row0 + rr < p.M) && col_ok;
+                        if (!live) continue;
+                        float4 x = *reinterpret_cast<const float4*>(sOut + rr * 256 + ((c4 ^ (rr & 15)) << 4));
+                        x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+                        if (p.flags & 2) {
+                            x.x = fmaxf(x.x, 0.0f); x.y = fmaxf(x.y, 0.0f); x.z = fmaxf(x.z, 0.0f); x.w = fmaxf(x.w, 0.0f);
                         }
                         if (p.flags & 4) {
-                            const uint64_t el = (uint64_t)(p.rng_row0 + row) * (uint64_t)p.N + (uint64_t)col;     // N % 4 == 0: one 32-element group
+                            // el % 4 == 0: the four columns lie in one 32-element group of the stream
                             const uint32_t kw = rng_keep_word_lo(p.keys, el >> 5, p.thr, p.low) >> (el & 31);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) x[j] = ((kw >> j) & 1u) ? x[j] * p.drop_scale : 0.0f;
+                            x.x = (kw & 1u) ? x.x * p.drop_scale : 0.0f;
+                            x.y = (kw & 2u) ? x.y * p.drop_scale : 0.0f;
+                            x.z = (kw & 4u) ? x.z * p.drop_scale : 0.0f;
+                            x.w = (kw & 8u) ? x.w * p.drop_scale : 0.0f;
                         }
-                        if (p.flags & 8) {
-                            const float4 m = __ldg(reinterpret_cast<const float4*>(p.aux + row * p.ldaux + col));
-                            x[0] = m.x > 0.0f ? x[0] * p.aux_scale : 0.0f;
-                            x[1] = m.y > 0.0f ? x[1] * p.aux_scale : 0.0f;
-                            x[2] = m.z > 0.0f ? x[2] * p.aux_scale : 0.0f;
-                            x[3] = m.w > 0.0f ? x[3] * p.aux_scale : 0.0f;
+                        if (use_aux) {
+                            x.x = pre[u].x > 0.0f ? x.x * p.aux_scale : 0.0f;
+                            x.y = pre[u].y > 0.0f ? x.y * p.aux_scale : 0.0f;
+                            x.z = pre[u].z > 0.0f ? x.z * p.aux_scale : 0.0f;
+                            x.w = pre[u].w > 0.0f ? x.w * p.aux_scale : 0.0f;
                         }
-                        if (p.beta != 0.0f) {
-                            const float4 c = *reinterpret_cast<const float4*>(out);
-                            x[0] = fmaf(p.beta, c.x, x[0]); x[1] = fmaf(p.beta, c.y, x[1]);
-                            x[2] = fmaf(p.beta, c.z, x[2]); x[3] = fmaf(p.beta, c.w, x[3]);
+                        if (use_old) {
+                            const float4 c = (use_aux && live) ? *reinterpret_cast<const float4*>(out) : pre[u];
+                            x.x = fmaf(p.beta, c.x, x.x); x.y = fmaf(p.beta, c.y, x.y);
+                            x.z = fmaf(p.beta, c.z, x.z); x.w = fmaf(p.beta, c.w, x.w);
                         }
-                        *reinterpret_cast<float4*>(out) = make_float4(x[0], x[1], x[2], x[3]);
-                    } else {
-                        for (int j = 0; j < nval; ++j) {
-                            float y = x[j];
+                        if (live) *reinterpret_cast<float4*>(out) = x;
+                    }
+                } else {
+                    __syncthreads();
+                    // unaligned shapes (parity-sized feature dimensions): element by element
+                    for (int u = 0; u < 8; ++u) {
+                        const int rr = rr0 + 16 * u;
+                        const int64_t row = row0 + rr;
+                        if (row >= p.M) continue;
+                        const float* sp = reinterpret_cast<const float*>(sOut + rr * 256 + ((c4 ^ (rr & 15)) << 4));
+                        for (int j = 0; j < 4 && col + j < p.N; ++j) {
+                            float y = sp[j];
+                            float* o = p.C + row * p.ldc + col + j;
                             if (p.flags & 1) y += p.bias[col + j];
                             if (p.flags & 2) y = fmaxf(y, 0.0f);
                             if (p.flags & 4)
                                 y *= rng_dropout_mult(p.keys, (uint64_t)(p.rng_row0 + row) * (uint64_t)p.N + (uint64_t)(col + j), p.thr, p.drop_scale);
                             if (p.flags & 8) y = (p.aux[row * p.ldaux + col + j] > 0.0f) ? y * p.aux_scale : 0.0f;
-                            if (p.beta != 0.0f) y = fmaf(p.beta, out[j], y);
-                            out[j] = y;
+                            if (p.beta != 0.0f) y = fmaf(p.beta, *o, y);
+                            *o = y;
                         }
                     }
                 }
                 __syncthreads();                              // the staging is reused by the next piece
             }
             tc::tc_fence_before();
-            prefetch();                                      // the epilogue's registers are dead now
+            if (next_a) load_a(ntile, nkb);                  // the epilogue's registers are dead now
         }
-        tile = ntile; ns = nns; kb = nkb; valid = nvalid; first = false;
+        tile = ntile; ns = nns; kb = nkb; valid = nvalid;
+        if (!w_resident) wb ^= 1;
     }
     if (pending) tc::mbar_wait(&bar, phase);
     tc::tc_fence_before();
@@ -479,10 +546,19 @@ extern "C" int u2gnn_gemm_split_rows(const float* A, int64_t M, int K, int64_t l
     p.w_vec = aligned16(W) && (ldw & 3) == 0 && ((w_kn ? N : K) & 3) == 0;
     p.c_vec = aligned16(C) && (ldc & 3) == 0 && (N & 3) == 0 && (!(epi & 1) || aligned16(bias)) &&
               (!(epi & 8) || (aligned16(aux) && (ldaux & 3) == 0));
-    cudaFuncSetAttribute(gemm_split_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmem);
     const int64_t n_tiles = (M + TM - 1) / TM;
     const int64_t cap = (int64_t)U2GNN_NUM_SMS * 2;
-    gemm_split_rows_kernel<<<(int)(n_tiles < cap ? n_tiles : cap), kThreads, kRowsSmem, as_stream(stream)>>>(p);
+    const int grid = (int)(n_tiles < cap ? n_tiles : cap);
+    auto launch = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmem);
+        kern<<<grid, kThreads, kRowsSmem, as_stream(stream)>>>(p);
+    };
+    // epilogue specialisations for the aligned shapes of the throughput configurations; everything else is generic
+    const int e = p.flags;
+    if (p.c_vec && ((e & ~1) == (2 | 4) || (e & ~1) == 2) && beta == 0.0f && (N & 31) == 0) launch(gemm_split_rows_kernel<1>);
+    else if (p.c_vec && e == 8 && beta == 0.0f) launch(gemm_split_rows_kernel<2>);
+    else if (p.c_vec && (e & ~1) == 0) launch(gemm_split_rows_kernel<3>);
+    else launch(gemm_split_rows_kernel<0>);
     U2GNN_CHECK_LAUNCH();
 }
 
