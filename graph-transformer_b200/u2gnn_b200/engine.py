@@ -399,6 +399,34 @@ class LayerSaved:
     y1_img: torch.Tensor = None
     ffn_mask: torch.Tensor = None
     wide: bool = False
+    attn_pad: tuple = None
+
+
+ATTN_PAD = os.environ.get("U2GNN_ATTN_PAD", "1") != "0"     # fp32 attention block for 64 < d <= 128: zero-padded q | k | v blocks (16-byte aligned rows) on the thread-per-row kernels
+
+
+def attn_pad_size(d):
+    """Padded feature size of the q | k | v blocks for 64 < d <= 128 (configs[2]: d = 65 -> 68), or 0.  Rows of 65 floats are not
+    16-byte aligned, which leaves only the warp-per-node attention kernels (4-5x slower than the thread-per-row ones)."""
+    if not ATTN_PAD or not 64 < d <= 128:
+        return 0
+    return next(D for D in (68, 80, 96, 112, 128) if d <= D)
+
+
+def _attn_pad_weights(p, d, DP):
+    """in_proj / out_proj weights in the padded layout: W_in [3 DP, d] (rows d..DP of each block zero, the q block times
+    sqrt(DP / d): the kernels scale q by sqrt(1 / DP)), b_in [3 DP], W_out [d, DP] (columns d..DP zero).  Weights only: plumbing."""
+    W, b, Wo = p["self_attn.in_proj_weight"], p["self_attn.in_proj_bias"], p["self_attn.out_proj.weight"]
+    c = math.sqrt(DP / d)
+    Wp = torch.zeros((3, DP, d), dtype=torch.float32, device=W.device)
+    Wp[:, :d].copy_(W.view(3, d, d))
+    Wp[0].mul_(c)
+    bp = torch.zeros((3, DP), dtype=torch.float32, device=W.device)
+    bp[:, :d].copy_(b.view(3, d))
+    bp[0].mul_(c)
+    Wop = torch.zeros((d, DP), dtype=torch.float32, device=W.device)
+    Wop[:, :d].copy_(Wo)
+    return Wp.view(3 * DP, d), bp.view(3 * DP), Wop, c
 
 
 def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, precision="fp32", for_backward=True):
@@ -417,9 +445,17 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
     elif tc_proj:
         qkv = linear_tc(x, M, d, p["self_attn.in_proj_weight"], 0, 3 * d, bias=p["self_attn.in_proj_bias"], out_bf16=tc_attn or tc_last)
     else:
-        qkv = torch.empty((M, 3 * d), **f32)
-        linear_fp32(x, M, d, p["self_attn.in_proj_weight"], 0, 3 * d, qkv, bias=p["self_attn.in_proj_bias"])
-    ctx = torch.empty((Mq, d), dtype=torch.bfloat16 if tc_attn else torch.float32, device=dev)
+        DP = attn_pad_size(d) if (not long_seq and Sq == S and S >= 2) else 0
+        if DP:
+            Wp, bp, Wop, cq = _attn_pad_weights(p, d, DP)
+            sv.attn_pad = (DP, cq, Wp, Wop)
+            qkv = torch.empty((M, 3 * DP), **f32)
+            linear_fp32(x, M, d, Wp, 0, 3 * DP, qkv, bias=bp)
+        else:
+            qkv = torch.empty((M, 3 * d), **f32)
+            linear_fp32(x, M, d, p["self_attn.in_proj_weight"], 0, 3 * d, qkv, bias=p["self_attn.in_proj_bias"])
+    da_ = sv.attn_pad[0] if sv.attn_pad else d                   # feature size the attention core sees
+    ctx = torch.empty((Mq, da_), dtype=torch.bfloat16 if tc_attn else torch.float32, device=dev)
     if long_seq:
         assert B == 1 and Sq == S
         scores = torch.empty((S, S), **f32)
@@ -439,7 +475,7 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
     elif tc_last:
         LIB.call("u2gnn_seqattn_last_fwd_ex", _ptr(qkv), 1, B, S, d, seed, drop_ids[0], thr, _ptr(ctx), _stream())
     else:
-        LIB.call("u2gnn_seqattn_fwd", _ptr(qkv), B, S, Sq, d, seed, drop_ids[0], thr, _ptr(ctx), _stream())
+        LIB.call("u2gnn_seqattn_fwd", _ptr(qkv), B, S, Sq, da_, seed, drop_ids[0], thr, _ptr(ctx), _stream())
     if tc_proj and d == 64 and FUSE_OUT_PROJ_LN:
         # residual rows read in place (position 0 of each sequence when only that row is live)
         xq = None
@@ -449,7 +485,10 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
             a = linear_tc(ctx, Mq, d, p["self_attn.out_proj.weight"], 0, d, bias=p["self_attn.out_proj.bias"])
         else:
             a = torch.empty((Mq, d), **f32)
-            linear_fp32(ctx, Mq, d, p["self_attn.out_proj.weight"], 0, d, a, bias=p["self_attn.out_proj.bias"])
+            if sv.attn_pad:
+                linear_fp32(ctx, Mq, da_, sv.attn_pad[3], 0, d, a, bias=p["self_attn.out_proj.bias"])
+            else:
+                linear_fp32(ctx, Mq, d, p["self_attn.out_proj.weight"], 0, d, a, bias=p["self_attn.out_proj.bias"])
         if Sq == S:
             xq = x
         else:
@@ -669,6 +708,8 @@ def _encoder_attn_bwd(dy1, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
     elif tc_proj:
         wgrad_tc(da, Mq, d, sv.ctx, d, g["self_attn.out_proj.weight"], g["self_attn.out_proj.bias"])
         dctx = linear_tc(da, Mq, d, p["self_attn.out_proj.weight"], 1, d, out_bf16=tc_attn)
+    elif sv.attn_pad:
+        return _encoder_attn_bwd_padded(da, dz1, sv, p, g, d, drop_ids, seed, thr, need_dx)
     else:
         wgrad_fp32(da, Mq, d, sv.ctx, d, g["self_attn.out_proj.weight"], g["self_attn.out_proj.bias"])
         dctx = torch.empty((Mq, d), **f32)
@@ -721,6 +762,34 @@ def _encoder_attn_bwd(dy1, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
     else:
         copy_rows(dz1, d, dx, S * d, B, d, accumulate=True)
     return dx
+
+
+def _encoder_attn_bwd_padded(da, dz1, sv, p, g, d, drop_ids, seed, thr, need_dx):
+    """Attention half of the backward in the padded q | k | v layout of attn_pad_size (fp32, every query row live): the padded
+    weights' gradients are computed in that layout and their live rows / columns added into the real gradients (the q block
+    times the sqrt(DP / d) folded into its weights)."""
+    DP, cq, Wp, Wop = sv.attn_pad
+    B, S = sv.B, sv.S
+    M = B * S
+    dev = da.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    dWop = torch.zeros((d, DP), **f32)
+    wgrad_fp32(da, M, d, sv.ctx, DP, dWop, g["self_attn.out_proj.bias"])
+    g["self_attn.out_proj.weight"].add_(dWop[:, :d])
+    dctx = torch.empty((M, DP), **f32)
+    linear_fp32(da, M, d, Wop, 1, DP, dctx)
+    dqkv = torch.empty((M, 3 * DP), **f32)
+    LIB.call("u2gnn_seqattn_bwd", _ptr(sv.qkv), _ptr(dctx), B, S, S, DP, seed, drop_ids[0], thr, _ptr(dqkv), _stream())
+    dWp = torch.zeros((3, DP, d), **f32)
+    dbp = torch.zeros((3, DP), **f32)
+    wgrad_fp32(dqkv, M, 3 * DP, sv.x, d, dWp, dbp)
+    dWp[0].mul_(cq)
+    dbp[0].mul_(cq)
+    g["self_attn.in_proj_weight"].view(3, d, d).add_(dWp[:, :d])
+    g["self_attn.in_proj_bias"].view(3, d).add_(dbp[:, :d])
+    if not need_dx:
+        return None
+    return linear_fp32(dqkv, M, 3 * DP, Wp, 1, d, dz1, beta=1.0)      # dx = dz1 + dqkv W_in (residual folded into the epilogue)
 
 
 # --------------------------------------------------------------------------------------
