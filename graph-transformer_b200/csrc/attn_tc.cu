@@ -30,8 +30,12 @@ struct AttnRng {
 
 // rows [row0, row0 + 128) of a strided matrix (64 columns at column offset `coff`; fp32, or bf16 when `bf16_src`: then the
 // producer has already rounded and the tile is a plain copy at half the bytes) -> bf16 swizzled tile
+// idx (fp32 sources only): row r of the tile is row idx[row0 + r] of a table with n_table rows - the gather of
+// F.embedding(input_x, X_concat) (pytorch_U2GNN_Sup.py:32) fused into its consumer; an index outside the table gives a zero
+// row and sets bit 1 of the device error word (as u2gnn_gather_rows does)
 __device__ __forceinline__ void stage_tile(uint8_t* tile, const void* __restrict__ src_, int bf16_src, int64_t ld, int coff, int64_t row0,
-                                           int valid_rows, int tid) {
+                                           int valid_rows, int tid, const int64_t* __restrict__ idx = nullptr, int64_t n_table = 0,
+                                           int* err = nullptr) {
     if (bf16_src) {                                             // (the kernel stages all bf16 tiles at once: stage_tiles_bf16)
         const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(src_);
         uint4 v[4];
@@ -57,7 +61,17 @@ __device__ __forceinline__ void stage_tile(uint8_t* tile, const void* __restrict
             const int e = base + u * kThreads + tid;
             const int r = e >> 4, c4 = e & 15;
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < valid_rows) v[u] = __ldg(reinterpret_cast<const float4*>(src + (row0 + r) * ld + coff) + c4);
+            if (r < valid_rows) {
+                int64_t row = row0 + r;
+                if (idx) {
+                    row = __ldg(idx + row);
+                    if (row < 0 || row >= n_table) {
+                        if (c4 == 0 && err) atomicOr(err, 2);
+                        continue;
+                    }
+                }
+                v[u] = __ldg(reinterpret_cast<const float4*>(src + row * ld + coff) + c4);
+            }
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -116,6 +130,9 @@ struct Params {
     const float* w_in;
     const float* b_in;
     void* qkv_out;
+    const int64_t* x_idx;  // optional: x row r = x[x_idx[r]] (gather fused into the kernel), x_rows = rows of that table
+    int64_t x_rows;
+    int* err;
 };
 
 // shared memory layout (bytes): Q 0, K 16K, V 32K; forward: P~ over Q / K; backward: P~ tile 0 over V, G 48K, P~1 64K, dS 80K / 96K
@@ -169,6 +186,33 @@ __global__ void __launch_bounds__(kThreads, BWD ? 2 : 3) attn_tc_kernel(const Pa
     const int r = wq * 32 + lane;                                // row handled in the per-row phases
     const int64_t n_tiles = (p.B + NB - 1) / NB;
     uint32_t phase = 0;
+    // Backward with bf16 I/O: the four operand tiles of the NEXT tile travel with cp.async (no registers, 16-byte chunks straight
+    // into the swizzled images, rows past the tile zero-filled) while this tile's results are drained - the tile's global
+    // loads were 25 % of the stall samples of the phase-serial version (profiles/r01_ncu_attn_bwd_v27_stalls.txt).
+    constexpr bool kAsync = BWD && !INPROJ;
+    auto prefetch_tiles = [&](int64_t t) {
+        const int64_t n0 = t * NB;
+        const int nrows = (int)((p.B - n0 < NB) ? p.B - n0 : NB) * S;
+        const int64_t r0 = n0 * S;
+        const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(p.qkv);
+        const __nv_bfloat16* gsrc = static_cast<const __nv_bfloat16*>(p.dctx);
+        const uint32_t base = tc::smem_u32(smem);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = u * kThreads + tid;
+            const int rr = e >> 3, c8 = e & 7;
+            const bool ok = rr < nrows;
+            const uint32_t off = tc::sw128_chunk(rr, c8);
+            const __nv_bfloat16* rowp = q + (r0 + (ok ? rr : 0)) * (3 * D) + 8 * c8;
+            const uint32_t nb = ok ? 16u : 0u;
+#pragma unroll
+            for (int t3 = 0; t3 < 3; ++t3)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + (uint32_t)t3 * 16384u + off), "l"(rowp + t3 * D), "r"(nb) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + 49152u + off), "l"(gsrc + (r0 + (ok ? rr : 0)) * D + 8 * c8), "r"(nb) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (kAsync && p.io_bf16 && (int64_t)blockIdx.x < n_tiles) prefetch_tiles(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t node0 = tile * NB;
         const int nodes = (int)((p.B - node0 < NB) ? p.B - node0 : NB);
@@ -180,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, BWD ? 2 : 3) attn_tc_kernel(const Pa
             // CTA stays at 128 columns and three CTAs per SM; thread = row drains them (+ bias, rounded to bf16 once - the value
             // the separate projection kernel stores) into the swizzled operand tiles
             const int half = warp >> 2;
-            stage_tile(sX, p.x, 0, D, 0, row0, rows, tid);
+            stage_tile(sX, p.x, 0, D, 0, row0, rows, tid, p.x_idx, p.x_rows, p.err);
             tc::fence_proxy_async();
             tc::tc_fence_before();
             __syncthreads();
@@ -248,6 +292,8 @@ __global__ void __launch_bounds__(kThreads, BWD ? 2 : 3) attn_tc_kernel(const Pa
                     *reinterpret_cast<uint4*>(sV + tc::sw128_chunk(r, 4 * half + c)) = w;
                 }
             }
+        } else if (kAsync && p.io_bf16) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");     // this tile's operands were requested during the previous tile's epilogue
         } else if (p.io_bf16) {
             // bf16 sources: tiles are plain copies; every 16-byte load of all three / four tiles is in flight before the first
             // shared-memory store (one exposed memory latency per tile-set instead of one per tile)
@@ -444,7 +490,41 @@ __global__ void __launch_bounds__(kThreads, BWD ? 2 : 3) attn_tc_kernel(const Pa
         // Tensor memory -> registers (thread = row) -> fp32 staging in the now dead operand tiles (one 32 KB tile per 64
         // output columns, 16-byte chunks XOR-swizzled with the row so that both the row-per-thread writes and the
         // chunk-per-thread reads are conflict free) -> COALESCED 128-bit global stores.
-        {
+        if (kAsync && p.io_bf16) {
+            // every operand tile is dead: tiles 0-3 take the NEXT tile's operands (cp.async, in flight under the drain below),
+            // tiles 4-6 stage this tile's dqkv rows as bf16 - 384 contiguous bytes per row, 16-byte chunks XOR-swizzled inside
+            // each 128-byte piece - for plain coalesced 16-byte copies to global memory
+            if (tile + gridDim.x < n_tiles) prefetch_tiles(tile + gridDim.x);
+            const int half = warp >> 2;
+            uint8_t* st = smem + 65536 + r * 384;
+#pragma unroll
+            for (int pc = 0; pc < 3; ++pc) {
+                uint32_t v[32];
+                tc::tmem_ld32(tmem + lane_base + 64 * pc + 32 * half, v);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 w;
+                    w.x = epi::cvt2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1]));
+                    w.y = epi::cvt2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                    w.z = epi::cvt2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                    w.w = epi::cvt2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                    *reinterpret_cast<uint4*>(st + 128 * pc + (((4 * half + j) ^ (r & 7)) << 4)) = w;
+                }
+            }
+            tc::tc_fence_before();
+            __syncthreads();
+            __nv_bfloat16* outp = static_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+            for (int u = 0; u < 12; ++u) {
+                const int e = u * kThreads + tid;
+                const int rr = e / 24, c = e - rr * 24;
+                if (rr < rows) {
+                    const uint4 w = *reinterpret_cast<const uint4*>(smem + 65536 + rr * 384 + ((c & ~7) << 4) + (((c & 7) ^ (rr & 7)) << 4));
+                    *reinterpret_cast<uint4*>(outp + (row0 + rr) * (3 * D) + 8 * c) = w;
+                }
+            }
+        } else {
             constexpr int NP = BWD ? 3 : 1;                     // 64-column pieces
             const int half = warp >> 2;                         // 32-column half of a piece handled by this warp
 #pragma unroll
@@ -540,10 +620,10 @@ extern "C" int u2gnn_seqattn_tc_fwd_ex(const void* qkv, int64_t B, int S, int d,
 
 // in_proj + attention core in one kernel (bf16 mode): qkv = x W_in^T + b_in is computed per tile on the tensor cores, written
 // once (bf16, for the backward) and consumed from shared memory; ctx as u2gnn_seqattn_tc_fwd_ex(io_bf16 = 1).
-extern "C" int u2gnn_inproj_seqattn_tc_fwd(const float* x, int64_t B, int S, int d, const float* w_in, const float* b_in,
-                                           uint64_t seed, uint32_t rng_stream, int thr, void* qkv_out, void* ctx,
-                                           u2gnn_stream_t stream) {
-    if (!x || !w_in || !b_in || !qkv_out || !ctx || B < 0 || thr < 0 || thr > 255) return U2GNN_EINVAL;
+extern "C" int u2gnn_inproj_seqattn_tc_fwd(const float* x, const int64_t* x_idx, int64_t x_rows, int64_t B, int S, int d,
+                                           const float* w_in, const float* b_in, uint64_t seed, uint32_t rng_stream, int thr,
+                                           void* qkv_out, void* ctx, int* err, u2gnn_stream_t stream) {
+    if (!x || !w_in || !b_in || !qkv_out || !ctx || B < 0 || thr < 0 || thr > 255 || (x_idx && x_rows < 1)) return U2GNN_EINVAL;
     if (d != D || S < 2 || S > 32) return U2GNN_EUNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(qkv_out) | reinterpret_cast<uintptr_t>(ctx) |
          reinterpret_cast<uintptr_t>(b_in)) % 16)
@@ -554,6 +634,7 @@ extern "C" int u2gnn_inproj_seqattn_tc_fwd(const float* x, int64_t B, int S, int
     p.rng = make_rng(seed, rng_stream, thr);
     p.low = rng_thr_low(thr);
     p.x = x; p.w_in = w_in; p.b_in = b_in; p.qkv_out = qkv_out;
+    p.x_idx = x_idx; p.x_rows = x_rows; p.err = err;
     launch<false, true>(p, as_stream(stream));
     U2GNN_CHECK_LAUNCH();
 }

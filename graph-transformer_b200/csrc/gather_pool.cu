@@ -200,6 +200,15 @@ __global__ void __launch_bounds__(256) segment_sum_vec_kernel(const float* __res
         const int64_t b = rowptr[g], e = rowptr[g + 1];
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         int64_t n = b;
+        // sixteen rows in flight per lane, added in ascending order (the result stays bit-identical to the sequential sum): a graph
+        // of ~60 nodes is four dependent DRAM round trips instead of eight - the kernel is latency-bound at 25 us per 67 MB
+        for (; n + 16 <= e; n += 16) {
+            float4 v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = __ldg(xv + (n + u) * dv + lane);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+        }
         for (; n + 8 <= e; n += 8) {
             float4 v[8];
 #pragma unroll

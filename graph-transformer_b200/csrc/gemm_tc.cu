@@ -106,6 +106,36 @@ __device__ __forceinline__ void stage_rows_bf16(uint8_t* tiles, const void* __re
     }
 }
 
+// fp32 rows idx[row0 + r] of a 64-column table -> one swizzled bf16 [128 x 64] tile (the gather of F.embedding fused into the GEMM
+// operand load); rows >= M and indices outside the table are zero
+template <int NT>
+__device__ __forceinline__ void stage_rows_gather64(uint8_t* tile, const float* __restrict__ table, const int64_t* __restrict__ idx,
+                                                    int64_t n_table, int64_t row0, int64_t M, int64_t ld, int tid) {
+    for (int base = 0; base < TM * 16; base += NT * 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = base + u * NT + tid;
+            const int r = e >> 4, c4 = e & 15;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e < TM * 16 && row0 + r < M) {
+                const int64_t row = __ldg(idx + row0 + r);
+                if (row >= 0 && row < n_table) v[u] = __ldg(reinterpret_cast<const float4*>(table + row * ld) + c4);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = base + u * NT + tid;
+            if (e >= TM * 16) continue;
+            const int r = e >> 4, c4 = e & 15;
+            uint2 w;
+            w.x = epi::cvt2(v[u].x, v[u].y);
+            w.y = epi::cvt2(v[u].z, v[u].w);
+            *reinterpret_cast<uint2*>(tile + tc::sw128_offset(r, c4 * 4)) = w;
+        }
+    }
+}
+
 // bf16 row block -> swizzled tiles with cp.async (16-byte chunk = one swizzle chunk, no registers, asynchronous): issue only,
 // the caller commits / waits.  Rows >= M and chunks >= K_true are zero-filled (src-size 0).  Needs K_true, lda multiples of 8
 // and a 16-byte aligned base (rows_async_ok).
@@ -155,6 +185,8 @@ struct RowsParams {
     //   z = res + dropout(A W^T + bias);  y = LayerNorm(z) * gamma + ln_beta;  stats = (mean, rstd)
     const float* res;
     int64_t ldres;
+    const int64_t* res_idx;   // optional: residual row of output row r = res[res_idx[r]] (gather fused; res_rows = rows of that table)
+    int64_t res_rows;
     RngKeys keys;
     int thr, low;
     float scale;
@@ -246,7 +278,14 @@ __global__ void __launch_bounds__(kThreads, MINB) gemm_tc_rows_kernel(const Rows
                 const int64_t row = row0 + (e >> 4);
                 pre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if constexpr (LN) {
-                    if (row < p.M) pre[u] = __ldg(reinterpret_cast<const float4*>(p.res + row * p.ldres) + (e & 15));
+                    if (row < p.M) {
+                        int64_t rrow = row;
+                        if (p.res_idx) {
+                            rrow = __ldg(p.res_idx + row);
+                            if (rrow < 0 || rrow >= p.res_rows) continue;     // (the forward kernel that gathered x has flagged it)
+                        }
+                        pre[u] = __ldg(reinterpret_cast<const float4*>(p.res + rrow * p.ldres) + (e & 15));
+                    }
                 } else {
                     if (row < p.M && 4 * (e & 15) < p.N) pre[u] = *(reinterpret_cast<const float4*>(static_cast<const float*>(p.C) + row * p.ldc) + (e & 15));
                 }
@@ -437,6 +476,8 @@ struct WgradParams {
     int N1, N2;
     float* dW;            // [N1, N2]
     float* db;            // [N1] or null
+    const int64_t* b_idx; // optional (fp32 B, N2 = 64): B row r = B[b_idx[r]] of a table with b_rows rows
+    int64_t b_rows;
 };
 
 __global__ void __launch_bounds__(kThreads, 2) gemm_tc_wgrad_kernel(const WgradParams p) {
@@ -474,14 +515,15 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_wgrad_kernel(const WgradP
     // stored each operand synchronously: one CTA per SM for the wide in_proj gradient exposed three DRAM round trips per
     // tile - 37 % of the HBM bandwidth.)
     const bool a_async = rows_async_ok(p.A, p.a_bf16, p.N1, p.lda);
-    const bool b_async = rows_async_ok(p.B, p.b_bf16, p.N2, p.ldb);
+    const bool b_async = !p.b_idx && rows_async_ok(p.B, p.b_bf16, p.N2, p.ldb);
     auto issue_async = [&](int64_t tile, uint8_t* st) {
         if (a_async) stage_rows_async<kThreads>(st, p.A, tile * TM, p.M, p.N1, ga * 64, p.lda, tid);
         if (b_async) stage_rows_async<kThreads>(st + ga * 16384, p.B, tile * TM, p.M, p.N2, 64, p.ldb, tid);
     };
     auto finish_sync = [&](int64_t tile, uint8_t* st) {
         if (!a_async) stage_rows_bf16<kThreads>(st, p.A, p.a_bf16, tile * TM, p.M, p.N1, ga * 64, p.lda, tid);
-        if (!b_async) stage_rows_bf16<kThreads>(st + ga * 16384, p.B, p.b_bf16, tile * TM, p.M, p.N2, 64, p.ldb, tid);
+        if (p.b_idx) stage_rows_gather64<kThreads>(st + ga * 16384, static_cast<const float*>(p.B), p.b_idx, p.b_rows, tile * TM, p.M, p.ldb, tid);
+        else if (!b_async) stage_rows_bf16<kThreads>(st + ga * 16384, p.B, p.b_bf16, tile * TM, p.M, p.N2, 64, p.ldb, tid);
     };
     int64_t it = 0;
     if ((int64_t)blockIdx.x < n_tiles) {
@@ -580,6 +622,8 @@ struct BwdParams {
     float beta;
     float* dW;            // [N1, 64]
     float* db;            // [N1] or null
+    const int64_t* b_idx; // optional (fp32 B): B row r = B[b_idx[r]] of a table with b_rows rows
+    int64_t b_rows;
 };
 
 template <int NS>
@@ -619,13 +663,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_dgrad_wgrad_kernel(const 
     const uint32_t idesc_r = tc::make_idesc(TM, 64, 0, 0);    // rows: K-major A tiles and weights
     const uint64_t w_desc = tc::make_desc_sw128(tc::smem_u32(sW), 16, 1024);
     const int64_t n_tiles = (p.M + TM - 1) / TM;
-    const bool b_async = rows_async_ok(p.B, p.b_bf16, 64, p.ldb);
+    const bool b_async = !p.b_idx && rows_async_ok(p.B, p.b_bf16, 64, p.ldb);
     auto issue_async = [&](int64_t tile, uint8_t* st) {
         stage_rows_async<kThreads>(st, p.A, tile * TM, p.M, p.N1, p.N1, p.lda, tid);
         if (b_async) stage_rows_async<kThreads>(st + ga * 16384, p.B, tile * TM, p.M, 64, 64, p.ldb, tid);
     };
     auto finish_sync = [&](int64_t tile, uint8_t* st) {
-        if (!b_async) stage_rows_bf16<kThreads, 64>(st + ga * 16384, p.B, p.b_bf16, tile * TM, p.M, 64, 64, p.ldb, tid);
+        if (p.b_idx) stage_rows_gather64<kThreads>(st + ga * 16384, static_cast<const float*>(p.B), p.b_idx, p.b_rows, tile * TM, p.M, p.ldb, tid);
+        else if (!b_async) stage_rows_bf16<kThreads, 64>(st + ga * 16384, p.B, p.b_bf16, tile * TM, p.M, 64, 64, p.ldb, tid);
     };
     // prologue: tiles 0 .. NS-2 of this CTA
 #pragma unroll
@@ -782,6 +827,7 @@ extern "C" int u2gnn_gemm_tc_rows_ex(const void* A, int a_bf16, int64_t M, int K
     p.A = A; p.a_bf16 = a_bf16; p.c_bf16 = c_bf16; p.M = M; p.lda = lda; p.K = K; p.KP = (K + 63) / 64 * 64;
     p.W = W; p.w_kn = w_kn; p.N = N; p.NP = (N + 15) / 16 * 16;
     p.bias = bias; p.C = C; p.ldc = ldc; p.beta = beta;
+    p.res = nullptr; p.res_idx = nullptr; p.res_rows = 0;
     const int kt = p.KP / 64;
     const size_t smem = 1024 + (size_t)kt * 16384 + (size_t)kt * p.NP * 128 + 128 * 272;
     if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
@@ -804,7 +850,8 @@ extern "C" int u2gnn_gemm_tc_rows_ex(const void* A, int a_bf16, int64_t M, int K
 }
 
 extern "C" int u2gnn_gemm_tc_rows_ln(const void* A, int a_bf16, int64_t M, int K, int64_t lda, const float* W, int w_kn,
-                                     const float* bias, const float* res, int64_t ldres, uint64_t seed, uint32_t rng_stream,
+                                     const float* bias, const float* res, int64_t ldres, const int64_t* res_idx, int64_t res_rows,
+                                     uint64_t seed, uint32_t rng_stream,
                                      int thr, const float* gamma, const float* beta, float* z, float* y, float* stats,
                                      void* y_img, u2gnn_stream_t stream) {
     constexpr int N = 64;
@@ -821,7 +868,8 @@ extern "C" int u2gnn_gemm_tc_rows_ln(const void* A, int a_bf16, int64_t M, int K
     p.A = A; p.a_bf16 = a_bf16; p.c_bf16 = 0; p.M = M; p.lda = lda; p.K = K; p.KP = (K + 63) / 64 * 64;
     p.W = W; p.w_kn = w_kn; p.N = N; p.NP = N;
     p.bias = bias; p.C = nullptr; p.ldc = N; p.beta = 0.0f;
-    p.res = res; p.ldres = ldres; p.keys = rng_keys(seed, rng_stream); p.thr = thr; p.low = rng_thr_low(thr);
+    p.res = res; p.ldres = ldres; p.res_idx = res_idx; p.res_rows = res_rows;
+    p.keys = rng_keys(seed, rng_stream); p.thr = thr; p.low = rng_thr_low(thr);
     p.scale = thr ? rng_keep_scale(thr) : 1.0f;
     p.gamma = gamma; p.ln_beta = beta; p.z = z; p.y = y; p.stats = stats;
     p.y_img = static_cast<uint8_t*>(y_img);
@@ -844,13 +892,15 @@ extern "C" int u2gnn_gemm_tc_rows(const float* A, int64_t M, int K, int64_t lda,
 }
 
 extern "C" int u2gnn_gemm_tc_wgrad_ex(const void* A, int a_bf16, int64_t M, int N1, int64_t lda, const void* B, int b_bf16, int N2,
-                                      int64_t ldb, float* dW, float* db, u2gnn_stream_t stream) {
+                                      int64_t ldb, const int64_t* b_idx, int64_t b_rows, float* dW, float* db, u2gnn_stream_t stream) {
     if (!A || !B || !dW || M < 0 || N1 < 1 || N2 < 1 || lda < N1 || ldb < N2) return U2GNN_EINVAL;
+    if (b_idx && (b_bf16 || N2 != 64 || (ldb & 3) || b_rows < 1)) return U2GNN_EUNSUPPORTED;
     if (N1 > 256 || N2 > 64) return U2GNN_EUNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) % 16) return U2GNN_EALIGN;
     if (M == 0) return U2GNN_OK;
     WgradParams p;
     p.A = A; p.B = B; p.a_bf16 = a_bf16; p.b_bf16 = b_bf16; p.M = M; p.lda = lda; p.ldb = ldb; p.N1 = N1; p.N2 = N2; p.dW = dW; p.db = db;
+    p.b_idx = b_idx; p.b_rows = b_rows;
     const int ga = (N1 + 63) / 64;
     const size_t smem = 1024 + (size_t)2 * (ga + 1) * 16384 + 2 * 16384;
     if (smem > 227 * 1024) return U2GNN_EUNSUPPORTED;
@@ -863,13 +913,14 @@ extern "C" int u2gnn_gemm_tc_wgrad_ex(const void* A, int a_bf16, int64_t M, int 
 
 extern "C" int u2gnn_gemm_tc_wgrad(const float* A, int64_t M, int N1, int64_t lda, const float* B, int N2, int64_t ldb,
                                    float* dW, float* db, u2gnn_stream_t stream) {
-    return u2gnn_gemm_tc_wgrad_ex(A, 0, M, N1, lda, B, 0, N2, ldb, dW, db, stream);
+    return u2gnn_gemm_tc_wgrad_ex(A, 0, M, N1, lda, B, 0, N2, ldb, nullptr, 0, dW, db, stream);
 }
 
 extern "C" int u2gnn_gemm_tc_dgrad_wgrad(const void* A, int64_t M, int N1, int64_t lda, const void* B, int b_bf16, int64_t ldb,
-                                         const float* W, void* C, int c_bf16, int64_t ldc, float beta, float* dW, float* db,
-                                         u2gnn_stream_t stream) {
+                                         const int64_t* b_idx, int64_t b_rows, const float* W, void* C, int c_bf16, int64_t ldc,
+                                         float beta, float* dW, float* db, u2gnn_stream_t stream) {
     if (!A || !B || !W || !C || !dW || M < 0 || N1 < 64 || lda < N1 || ldb < 64 || ldc < 64) return U2GNN_EINVAL;
+    if (b_idx && (b_bf16 || b_rows < 1)) return U2GNN_EUNSUPPORTED;
     if (c_bf16 && beta != 0.0f) return U2GNN_EINVAL;
     if ((N1 & 63) || N1 > 256) return U2GNN_EUNSUPPORTED;
     if ((lda & 7) || (ldc & 7) || (ldb & (b_bf16 ? 7 : 3))) return U2GNN_EALIGN;
@@ -877,7 +928,7 @@ extern "C" int u2gnn_gemm_tc_dgrad_wgrad(const void* A, int64_t M, int N1, int64
     if (M == 0) return U2GNN_OK;
     BwdParams p;
     p.A = A; p.B = B; p.b_bf16 = b_bf16; p.c_bf16 = c_bf16; p.M = M; p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.N1 = N1;
-    p.W = W; p.C = C; p.beta = beta; p.dW = dW; p.db = db;
+    p.W = W; p.C = C; p.beta = beta; p.dW = dW; p.db = db; p.b_idx = b_idx; p.b_rows = b_rows;
     const int ga = N1 / 64;
     const size_t fixed = 1024 + (size_t)ga * 8192 + 128 * 272 + 2 * 16384;
     const size_t stage = (size_t)(ga + 1) * 16384;

@@ -360,8 +360,9 @@ extern "C" int u2gnn_add_dropout_ln_bwd_ex(const float* dy, const float* z, cons
         U2GNN_CHECK_LAUNCH();
     }
     if (da_bf16 || dasum) return U2GNN_EUNSUPPORTED;            // bf16 da / fused column sum: vectorised shapes only
-    // fewer, fatter warps than the forward: each warp flushes d atomics at the end
-    add_dropout_ln_bwd_kernel<<<grid_for(M, 64, 2), 256, 0, as_stream(stream)>>>(dy, z, stats, M, d, gamma,
+    // fewer, fatter warps than the forward: each warp flushes d atomics at the end (six blocks per SM: with two the kernel ran at
+    // 1.4 TB/s on the d = 65 rows of configs[2] - one warp per row has only its own few loads in flight)
+    add_dropout_ln_bwd_kernel<<<grid_for(M, 32, 6), 256, 0, as_stream(stream)>>>(dy, z, stats, M, d, gamma,
                                                                                 make_rng(seed, rng_stream, thr), dz,
                                                                                 static_cast<float*>(da), dgamma, dbeta);
     U2GNN_CHECK_LAUNCH();

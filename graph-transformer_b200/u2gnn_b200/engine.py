@@ -33,6 +33,7 @@ FUSE_PROJ_BWD = os.environ.get("U2GNN_FUSE_PROJ_BWD", "1") != "0"         # bf16
 FUSE_INPROJ_ATTN = os.environ.get("U2GNN_FUSE_INPROJ_ATTN", "1") != "0"   # bf16 mode, d = 64: in_proj inside the attention-forward kernel (qkv written once, never re-read in the forward)
 FFN_FWD_MASK = os.environ.get("U2GNN_FFN_FWD_MASK", "1") != "0"          # bf16 mode: the FFN forward leaves the 1-bit live-and-kept mask of the hidden for the backward
 FFN_BWD_IMAGES = os.environ.get("U2GNN_FFN_BWD_IMAGES", "1") != "0"      # bf16 mode, d = 64: y1 / dF leave their producers as bf16 tile images (no conversion pass in the FFN backward)
+FUSE_GATHER = os.environ.get("U2GNN_FUSE_GATHER", "1") != "0"             # bf16 mode, d = 64: the first timestep's consumers gather their x rows by index (the [N, k+1, d] tensor is never written)
 FP32_TC = os.environ.get("U2GNN_FP32_TC", "1") != "0"                     # fp32 mode: linear layers as three-product bf16-split tcgen05 GEMMs (csrc/gemm_split.cu) instead of the CUDA-core SGEMM
 FLOPS = {}    # entry point -> algorithmic flops issued while LIB.timed is active (bench.py roofline)
 BYTES = {}    # entry point -> algorithmic HBM bytes (the tensors the call must read + write once) while LIB.timed is active
@@ -288,15 +289,17 @@ def linear_tc(A, M, K, W, w_kn, N, bias=None, beta=0.0, out=None, out_bf16=False
     return out
 
 
-def wgrad_tc(dout, M, n_out, inp, n_in, dW, db=None):
-    """dW[n_out, n_in] += dout^T @ inp; db[n_out] += colsum(dout)  (tensor cores, bf16 operands)."""
+def wgrad_tc(dout, M, n_out, inp, n_in, dW, db=None, inp_idx=None):
+    """dW[n_out, n_in] += dout^T @ inp; db[n_out] += colsum(dout)  (tensor cores, bf16 operands).  inp_idx: row r of the input is
+    inp[inp_idx[r]] (fused gather)."""
     if M == 0:
         return
     LIB.call("u2gnn_gemm_tc_wgrad_ex", _ptr(dout), int(dout.dtype == torch.bfloat16), M, n_out, n_out, _ptr(inp),
-             int(inp.dtype == torch.bfloat16), n_in, n_in, _ptr(dW), _ptr(db), _stream())
+             int(inp.dtype == torch.bfloat16), n_in, n_in, _ptr(inp_idx), inp.shape[0] if inp_idx is not None else 0, _ptr(dW), _ptr(db),
+             _stream())
 
 
-def proj_bwd_tc(dout, M, n_out, inp, W, dW, db, out=None, out_bf16=False, beta=0.0):
+def proj_bwd_tc(dout, M, n_out, inp, W, dW, db, out=None, out_bf16=False, beta=0.0, inp_idx=None):
     """Backward of a projection y = inp W^T + b in one pass over dout[M, n_out] (bf16): returns dinp[M, 64] = dout W (+ beta*out)
     and accumulates dW[n_out, 64] += dout^T inp, db += colsum(dout)."""
     if out is None:
@@ -305,8 +308,9 @@ def proj_bwd_tc(dout, M, n_out, inp, W, dW, db, out=None, out_bf16=False, beta=0
                                                   (2 if (out_bf16 or (out is not None and out.dtype == torch.bfloat16)) else 4) * 64 * (2 if beta else 1)))
     if LIB.timed is not None:
         FLOPS["u2gnn_gemm_tc_dgrad_wgrad"] = FLOPS.get("u2gnn_gemm_tc_dgrad_wgrad", 0) + 4 * M * n_out * 64
-    LIB.call("u2gnn_gemm_tc_dgrad_wgrad", _ptr(dout), M, n_out, n_out, _ptr(inp), int(inp.dtype == torch.bfloat16), 64, _ptr(W),
-             _ptr(out), int(out.dtype == torch.bfloat16), 64, beta, _ptr(dW), _ptr(db), _stream())
+    LIB.call("u2gnn_gemm_tc_dgrad_wgrad", _ptr(dout), M, n_out, n_out, _ptr(inp), int(inp.dtype == torch.bfloat16), 64, _ptr(inp_idx),
+             inp.shape[0] if inp_idx is not None else 0, _ptr(W), _ptr(out), int(out.dtype == torch.bfloat16), 64, beta, _ptr(dW), _ptr(db),
+             _stream())
     return out
 
 
@@ -354,7 +358,7 @@ def add_dropout_ln_bwd(dy, z, stats, M, d, gamma, drop, dgamma, dbeta, want_da=T
     return dz, (da if da is not None else dz)
 
 
-def out_proj_ln_tc(ctx, Mq, d, p, res, ldres, drop, want_img=False):
+def out_proj_ln_tc(ctx, Mq, d, p, res, ldres, drop, want_img=False, res_idx=None):
     """out_proj + dropout + residual + LayerNorm1 as ONE kernel (bf16 mode, d = 64): the projection result never reaches HBM.
     want_img: y1 is also written as bf16 tile images, which the FFN backward bulk-copies (no conversion pass there)."""
     dev = ctx.device
@@ -366,7 +370,8 @@ def out_proj_ln_tc(ctx, Mq, d, p, res, ldres, drop, want_img=False):
     if LIB.timed is not None:
         FLOPS["u2gnn_gemm_tc_rows_ln"] = FLOPS.get("u2gnn_gemm_tc_rows_ln", 0) + 2 * Mq * d * d
     LIB.call("u2gnn_gemm_tc_rows_ln", _ptr(ctx), int(ctx.dtype == torch.bfloat16), Mq, d, d, _ptr(p["self_attn.out_proj.weight"]), 0,
-             _ptr(p["self_attn.out_proj.bias"]), _ptr(res), ldres, drop[0], drop[1], drop[2], _ptr(p["norm1.weight"]),
+             _ptr(p["self_attn.out_proj.bias"]), _ptr(res), ldres, _ptr(res_idx), res.shape[0] if res_idx is not None else 0,
+             drop[0], drop[1], drop[2], _ptr(p["norm1.weight"]),
              _ptr(p["norm1.bias"]), _ptr(z), _ptr(y), _ptr(stats), _ptr(img), _stream())
     return z, y, stats, img
 
@@ -400,6 +405,7 @@ class LayerSaved:
     ffn_mask: torch.Tensor = None
     wide: bool = False
     attn_pad: tuple = None
+    x_idx: torch.Tensor = None     # fused gather: x is the TABLE and row r of the layer input is x[x_idx[r]]
 
 
 ATTN_PAD = os.environ.get("U2GNN_ATTN_PAD", "1") != "0"     # fp32 attention block for 64 < d <= 128: zero-padded q | k | v blocks (16-byte aligned rows) on the thread-per-row kernels
@@ -429,13 +435,22 @@ def _attn_pad_weights(p, d, DP):
     return Wp.view(3 * DP, d), bp.view(3 * DP), Wop, c
 
 
-def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, precision="fp32", for_backward=True):
+def gather_fusable(d, ff, S, Sq, precision, long_seq):
+    """The first timestep can read its input rows by index (no materialised gather) when every consumer of x is one of the
+    kernels that take an index array: in_proj + attention forward, out_proj + LayerNorm1 (residual), in_proj backward."""
+    return (FUSE_GATHER and precision == "bf16" and not long_seq and d == 64 and Sq == S and S >= 2 and ffn_tc_supported(d, ff)
+            and FUSE_INPROJ_ATTN and FUSE_OUT_PROJ_LN and FUSE_LN_BWD)
+
+
+def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, precision="fp32", for_backward=True, x_idx=None):
     """x[B*S, d] -> y[B*Sq, d].  p: dict name->tensor.  drop_ids: 4 stream ids.  long_seq selects the
-    attn_axis="nodes" formulation (B == 1, scores materialised as [S, S])."""
+    attn_axis="nodes" formulation (B == 1, scores materialised as [S, S]).  x_idx (only when gather_fusable): x is the
+    gather TABLE and the layer's input row r is x[x_idx[r]]."""
     dev = x.device
     M, Mq = B * S, B * Sq
     f32 = dict(dtype=torch.float32, device=dev)
-    sv = LayerSaved(x=x, B=B, S=S, Sq=Sq)
+    sv = LayerSaved(x=x, B=B, S=S, Sq=Sq, x_idx=x_idx)
+    assert x_idx is None or gather_fusable(d, ff, S, Sq, precision, long_seq)
     tc_proj = precision == "bf16" and not long_seq and d <= 64
     tc_attn = tc_proj and d == 64 and Sq == S and S >= 2        # tensor-core attention core: bf16 qkv / ctx between the kernels
     tc_last = tc_proj and d == 64 and Sq == 1 and S >= 2 and LAST_STEP_BF16     # last timestep: bf16 qkv / dqkv around the position-0 attention
@@ -465,11 +480,13 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
         sgemm(0, 0, S, d, S, pd, S, qkv, 3 * d, ctx, d, b_off=2 * d)
         sv.probs, sv.pd = scores, pd
     elif fused_in:
-        _acct_bytes("u2gnn_inproj_seqattn_tc_fwd", M * (4 * d + 2 * 3 * d + 2 * d))     # x (fp32) -> qkv, ctx (bf16)
+        # x (fp32) -> qkv, ctx (bf16); fused gather: the index per row and the table once (a row gathered k+1 times is re-read from L2)
+        _acct_bytes("u2gnn_inproj_seqattn_tc_fwd", M * (2 * 3 * d + 2 * d) + (M * 4 * d if x_idx is None else M * 8 + min(M, x.shape[0]) * 4 * d))
         if LIB.timed is not None:
             FLOPS["u2gnn_inproj_seqattn_tc_fwd"] = FLOPS.get("u2gnn_inproj_seqattn_tc_fwd", 0) + 2 * M * 3 * d * d
-        LIB.call("u2gnn_inproj_seqattn_tc_fwd", _ptr(x), B, S, d, _ptr(p["self_attn.in_proj_weight"]), _ptr(p["self_attn.in_proj_bias"]),
-                 seed, drop_ids[0], thr, _ptr(qkv), _ptr(ctx), _stream())
+        LIB.call("u2gnn_inproj_seqattn_tc_fwd", _ptr(x), _ptr(x_idx), x.shape[0] if x_idx is not None else 0, B, S, d,
+                 _ptr(p["self_attn.in_proj_weight"]), _ptr(p["self_attn.in_proj_bias"]), seed, drop_ids[0], thr, _ptr(qkv), _ptr(ctx),
+                 _ptr(err_word(dev)), _stream())
     elif tc_attn:
         LIB.call("u2gnn_seqattn_tc_fwd_ex", _ptr(qkv), B, S, d, seed, drop_ids[0], thr, _ptr(ctx), 1, _stream())
     elif tc_last:
@@ -479,7 +496,8 @@ def encoder_layer_fwd(x, B, S, Sq, p, d, ff, drop_ids, seed, thr, long_seq, prec
     if tc_proj and d == 64 and FUSE_OUT_PROJ_LN:
         # residual rows read in place (position 0 of each sequence when only that row is live)
         xq = None
-        z1, y1, st1, sv.y1_img = out_proj_ln_tc(ctx, Mq, d, p, x, d if Sq == S else S * d, (seed, drop_ids[1], thr), want_img=FFN_BWD_IMAGES)
+        z1, y1, st1, sv.y1_img = out_proj_ln_tc(ctx, Mq, d, p, x, d if Sq == S else S * d, (seed, drop_ids[1], thr), want_img=FFN_BWD_IMAGES,
+                                                res_idx=x_idx)
     else:
         if tc_proj:
             a = linear_tc(ctx, Mq, d, p["self_attn.out_proj.weight"], 0, d, bias=p["self_attn.out_proj.bias"])
@@ -599,7 +617,7 @@ def ffn_wide_bwd(df, dz, saved, Mq, d, ff, p, g, thr):
     n_sl = ff // 64
     tmp = torch.zeros((n_sl, WIDE_DP * 64), dtype=torch.float32, device=dev)
     for i in range(n_sl):
-        LIB.call("u2gnn_gemm_tc_wgrad_ex", _ptr(dfp), 1, Mq, WIDE_DP, WIDE_DP, _ptr(h) + 2 * 64 * i, 1, 64, ff, _ptr(tmp) + 4 * i * WIDE_DP * 64, 0, s)
+        LIB.call("u2gnn_gemm_tc_wgrad_ex", _ptr(dfp), 1, Mq, WIDE_DP, WIDE_DP, _ptr(h) + 2 * 64 * i, 1, 64, ff, 0, 0, _ptr(tmp) + 4 * i * WIDE_DP * 64, 0, s)
         LIB.call("u2gnn_copy_rows", _ptr(tmp) + 4 * i * WIDE_DP * 64, 64, _ptr(g["linear2.weight"]) + 4 * 64 * i, ff, d, 64, 1, s)
     LIB.call("u2gnn_relu_dropout_bwd_bf16", _ptr(dh), _ptr(h), Mq, ff, scale, s)            # dh is now dPre
     # dW1[ff, d] += dPre^T y1, db1 += colsum(dPre): 256-row slices of dW1 x two 64-column blocks of the padded y1
@@ -610,7 +628,7 @@ def ffn_wide_bwd(df, dz, saved, Mq, d, ff, p, g, thr):
         n1 = min(256, ff - 256 * i)
         for bi, (c0, nc) in enumerate(blocks):
             t = _ptr(tmp1) + 4 * (i * 2 + bi) * 256 * 64
-            LIB.call("u2gnn_gemm_tc_wgrad_ex", _ptr(dh) + 2 * 256 * i, 1, Mq, n1, ff, _ptr(y1p) + 2 * c0, 1, 64, WIDE_DP, t,
+            LIB.call("u2gnn_gemm_tc_wgrad_ex", _ptr(dh) + 2 * 256 * i, 1, Mq, n1, ff, _ptr(y1p) + 2 * c0, 1, 64, WIDE_DP, 0, 0, t,
                      (_ptr(g["linear1.bias"]) + 4 * 256 * i) if bi == 0 else 0, s)
             LIB.call("u2gnn_copy_rows", t, 64, _ptr(g["linear1.weight"]) + 4 * (256 * i * d + c0), d, n1, nc, 1, s)
     dyp = torch.empty((Mq, WIDE_DP), dtype=torch.float32, device=dev)
@@ -735,13 +753,13 @@ def _encoder_attn_bwd(dy1, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
         # in_proj backward in one pass over dqkv; the residual gradient dz1 is the old C of the epilogue when every row is live
         if Sq == S:
             return proj_bwd_tc(dqkv, M, 3 * d, sv.x, p["self_attn.in_proj_weight"], g["self_attn.in_proj_weight"],
-                               g["self_attn.in_proj_bias"], out=dz1, beta=1.0)
+                               g["self_attn.in_proj_bias"], out=dz1, beta=1.0, inp_idx=sv.x_idx)
         dx = proj_bwd_tc(dqkv, M, 3 * d, sv.x, p["self_attn.in_proj_weight"], g["self_attn.in_proj_weight"],
                          g["self_attn.in_proj_bias"])
         copy_rows(dz1, d, dx, S * d, B, d, accumulate=True)
         return dx
     if tc_proj:
-        wgrad_tc(dqkv, M, 3 * d, sv.x, d, g["self_attn.in_proj_weight"], g["self_attn.in_proj_bias"])
+        wgrad_tc(dqkv, M, 3 * d, sv.x, d, g["self_attn.in_proj_weight"], g["self_attn.in_proj_bias"], inp_idx=sv.x_idx)
     else:
         wgrad_fp32(dqkv, M, 3 * d, sv.x, d, g["self_attn.in_proj_weight"], g["self_attn.in_proj_bias"])
     if not need_dx:
@@ -812,10 +830,14 @@ def u2gnn_layer_fwd(src, input_x, params, l, T, attn_axis, drop: DropoutCfg, pre
     ff = params[0]["linear1.weight"].shape[0]
     thr = drop.thr_enc()
     saved = StackSaved(n_src=src.shape[0], N=N, S=S)
+    x_idx = None
     if attn_axis == "neighbors":
         if S > 32:
             raise ValueError("attn_axis='neighbors' supports num_neighbors <= 31")
-        x = gather_rows(src, input_x)                       # [N*S, d]
+        if T >= 2 and gather_fusable(d, ff, S, S, precision, False):
+            x, x_idx = src, input_x                         # the first timestep's kernels read src[input_x[n, s]] themselves
+        else:
+            x = gather_rows(src, input_x)                   # [N*S, d]
         B, Sseq = N, S
     elif attn_axis == "nodes":
         x = gather_rows(src, input_x, idx_stride=S, n_idx=N)  # column 0 only
@@ -826,7 +848,8 @@ def u2gnn_layer_fwd(src, input_x, params, l, T, attn_axis, drop: DropoutCfg, pre
         last = attn_axis == "neighbors" and t == T - 1
         Sq = 1 if last else Sseq
         ids = [stream_id(l, t, s, T) for s in range(4)]
-        x, sv = encoder_layer_fwd(x, B, Sseq, Sq, params[t], d, ff, ids, drop.seed, thr, attn_axis == "nodes", precision, for_backward)
+        x, sv = encoder_layer_fwd(x, B, Sseq, Sq, params[t], d, ff, ids, drop.seed, thr, attn_axis == "nodes", precision, for_backward,
+                                  x_idx=x_idx if t == 0 else None)
         saved.layers.append(sv)
     return x, saved  # [N, d] in both layouts
 

@@ -280,25 +280,30 @@ int u2gnn_seqattn_tc_bwd(const float* qkv, const float* dctx, int64_t B, int S, 
         dimensions are in ELEMENTS; beta must be 0 for a bf16 C. ---- */
 int u2gnn_gemm_tc_rows_ex(const void* A, int a_bf16, int64_t M, int K, int64_t lda, const float* W, int w_kn, int N,
                           const float* bias, float beta, void* C, int c_bf16, int64_t ldc, u2gnn_stream_t stream);
+/* FUSED GATHER (SURVEY.md 8(a) a3 "fused: no write"): where an entry point below takes an index array next to a row operand
+ * (b_idx / res_idx / x_idx, NULL = rows in place), row r of that operand is row idx[r] of a TABLE with *_rows rows - the
+ * F.embedding(input_x, X_concat) of pytorch_U2GNN_Sup.py:32 evaluated inside its consumers, so that the gathered [N, k+1, d]
+ * tensor of the first timestep is never written to HBM.  Indexed operands are fp32 with 64 columns; an index outside the table
+ * reads as a zero row (u2gnn_inproj_seqattn_tc_fwd also sets bit 1 of the device error word, as u2gnn_gather_rows does). */
 int u2gnn_gemm_tc_wgrad_ex(const void* A, int a_bf16, int64_t M, int N1, int64_t lda, const void* B, int b_bf16, int N2,
-                           int64_t ldb, float* dW, float* db, u2gnn_stream_t stream);
+                           int64_t ldb, const int64_t* b_idx, int64_t b_rows, float* dW, float* db, u2gnn_stream_t stream);
 /* backward of one attention-block projection in a single pass over its output gradient A[M,N1] (bf16; N1 = 64, 128, 192
  * or 256): input gradient C[M,64] = A W (+ beta*C; W = the layer's weight [N1,64]; C fp32, or bf16 with beta 0) AND
  * dW[N1,64] += A^T B, db[N1] += colsum(A) (B[M,64] = the layer's input rows, fp32 or bf16; db may be null).  Same results as
  * u2gnn_gemm_tc_rows_ex(w_kn = 1) + u2gnn_gemm_tc_wgrad_ex on the same operands.  (autograd of the in_proj / out_proj F.linear
  * calls of nn.MultiheadAttention, which pytorch_U2GNN_Sup.py:20-21 instantiates through nn.TransformerEncoderLayer) */
 int u2gnn_gemm_tc_dgrad_wgrad(const void* A, int64_t M, int N1, int64_t lda, const void* B, int b_bf16, int64_t ldb,
-                              const float* W, void* C, int c_bf16, int64_t ldc, float beta, float* dW, float* db,
-                              u2gnn_stream_t stream);
+                              const int64_t* b_idx, int64_t b_rows, const float* W, void* C, int c_bf16, int64_t ldc, float beta,
+                              float* dW, float* db, u2gnn_stream_t stream);
 /* out_proj + dropout + residual + LayerNorm1 in one kernel (torch/nn/modules/transformer.py:946,969-972:
  * x = norm1(x + dropout1(self_attn(x)))): z[M,64] = res + dropout(A[M,K] W^T + bias), y = LayerNorm(z) * gamma + beta,
  * stats[M,2] = (mean, rstd).  N = d = 64 only; res row stride ldres (elements) so the last timestep can read position 0 of
  * each sequence in place.  Same arithmetic as u2gnn_gemm_tc_rows_ex followed by u2gnn_add_dropout_ln_fwd (bit-identical).
  * y_img (may be NULL): y additionally as bf16 swizzled tile images (u2gnn_ffn_tc_image_bytes(M) bytes) for u2gnn_ffn_tc_bwd. */
 int u2gnn_gemm_tc_rows_ln(const void* A, int a_bf16, int64_t M, int K, int64_t lda, const float* W, int w_kn,
-                          const float* bias, const float* res, int64_t ldres, uint64_t seed, uint32_t rng_stream, int thr,
-                          const float* gamma, const float* beta, float* z, float* y, float* stats, void* y_img,
-                          u2gnn_stream_t stream);
+                          const float* bias, const float* res, int64_t ldres, const int64_t* res_idx, int64_t res_rows,
+                          uint64_t seed, uint32_t rng_stream, int thr, const float* gamma, const float* beta, float* z, float* y,
+                          float* stats, void* y_img, u2gnn_stream_t stream);
 int u2gnn_seqattn_tc_fwd_ex(const void* qkv, int64_t B, int S, int d, uint64_t seed, uint32_t rng_stream, int thr,
                             void* ctx, int io_bf16, u2gnn_stream_t stream);
 int u2gnn_seqattn_tc_bwd_ex(const void* qkv, const void* dctx, int64_t B, int S, int d, uint64_t seed,
@@ -308,8 +313,9 @@ int u2gnn_seqattn_tc_bwd_ex(const void* qkv, const void* dctx, int64_t B, int S,
  * (nn.MultiheadAttention in_proj: w_in [192,64], b_in [192]) is computed per tile, written once as bf16 qkv_out[B*S,192] for the
  * backward, and consumed from shared memory; ctx[B*S,64] bf16.  Same results as u2gnn_gemm_tc_rows_ex (bf16 out) followed by
  * u2gnn_seqattn_tc_fwd_ex(io_bf16 = 1). */
-int u2gnn_inproj_seqattn_tc_fwd(const float* x, int64_t B, int S, int d, const float* w_in, const float* b_in, uint64_t seed,
-                                uint32_t rng_stream, int thr, void* qkv_out, void* ctx, u2gnn_stream_t stream);
+int u2gnn_inproj_seqattn_tc_fwd(const float* x, const int64_t* x_idx, int64_t x_rows, int64_t B, int S, int d, const float* w_in,
+                                const float* b_in, uint64_t seed, uint32_t rng_stream, int thr, void* qkv_out, void* ctx, int* err,
+                                u2gnn_stream_t stream);
 /* last timestep of a U2GNN layer (only query position 0 of each node live): same contract as
  * u2gnn_seqattn_fwd / _bwd with Sq = 1, with qkv (and dqkv) optionally stored as bf16 [B*S, 3d]; ctx / dctx are fp32 [B, d].
  * d in {32, 64}, 2 <= S <= 32. */

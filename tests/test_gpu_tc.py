@@ -495,8 +495,8 @@ def test_inproj_attention_fused_equals_projection_then_attention(U, B, S, p):
     U.LIB.call("u2gnn_seqattn_tc_fwd_ex", qkv0.data_ptr(), B, S, d, SEED, ST, thr, ctx0.data_ptr(), 1, E._stream())
     qkv1 = torch.full((B * S, 3 * d), float("nan"), device="cuda", dtype=torch.bfloat16)
     ctx1 = torch.full((B * S, d), float("nan"), device="cuda", dtype=torch.bfloat16)
-    U.LIB.call("u2gnn_inproj_seqattn_tc_fwd", x.data_ptr(), B, S, d, W.data_ptr(), b.data_ptr(), SEED, ST, thr, qkv1.data_ptr(),
-               ctx1.data_ptr(), E._stream())
+    U.LIB.call("u2gnn_inproj_seqattn_tc_fwd", x.data_ptr(), 0, 0, B, S, d, W.data_ptr(), b.data_ptr(), SEED, ST, thr, qkv1.data_ptr(),
+               ctx1.data_ptr(), 0, E._stream())
     torch.cuda.synchronize()
     assert torch.equal(qkv1, qkv0)
     assert torch.equal(ctx1, ctx0)
@@ -654,3 +654,73 @@ def test_ffn_kernels_write_nothing_outside_their_outputs(U, M, ff, p):
         assert o.intact(), n
     for n in ("z", "xn", "dy1", "dW1", "dW2"):
         assert bool(torch.isfinite(out[n].view).all()) and not bool((out[n].view == SENT).any()), n
+
+
+# ------------------------------------------------------------------ gather fused into its consumers
+@pytest.mark.parametrize("nodes,S,T", [(300, 17, 3), (129, 9, 2), (1000, 17, 4)])
+def test_fused_gather_layer_is_bit_identical_to_the_materialised_gather(U, nodes, S, T, monkeypatch):
+    """u2gnn_layer_fwd / _bwd with the first timestep's kernels reading src[input_x] by index (in_proj + attention forward,
+    out_proj + LayerNorm1 residual, in_proj backward) against the same layer on the gathered [N, S, d] tensor: the index-driven
+    loads fetch the very same fp32 rows, so every output and every gradient must be bit-identical (weight gradients are
+    accumulated with atomics in both: compared at 1e-5 of their largest entry)."""
+    from u2gnn_b200 import engine as E
+    d, ff = 64, 256
+    g = torch.Generator(device="cuda").manual_seed(nodes)
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    src = rnd(nodes, d)
+    input_x = torch.randint(0, nodes, (nodes, S), device="cuda", generator=g)
+    input_x[:, 0] = torch.arange(nodes, device="cuda")
+    params = [{"self_attn.in_proj_weight": rnd(3 * d, d) / 8, "self_attn.in_proj_bias": 0.1 * rnd(3 * d),
+               "self_attn.out_proj.weight": rnd(d, d) / 8, "self_attn.out_proj.bias": 0.1 * rnd(d), "linear1.weight": rnd(ff, d) / 8,
+               "linear1.bias": 0.1 * rnd(ff), "linear2.weight": rnd(d, ff) / 16, "linear2.bias": 0.1 * rnd(d),
+               "norm1.weight": 1 + 0.1 * rnd(d), "norm1.bias": 0.1 * rnd(d), "norm2.weight": 1 + 0.1 * rnd(d), "norm2.bias": 0.1 * rnd(d)}
+              for _ in range(T)]
+    dout = rnd(nodes, d)
+    drop = E.DropoutCfg(enabled=True, seed=77, p_enc=0.5, p_out=0.5)
+    res = {}
+    for fused in (True, False):
+        monkeypatch.setattr(E, "FUSE_GATHER", fused)
+        grads = [{n: torch.zeros_like(v) for n, v in p.items()} for p in params]
+        out, saved = E.u2gnn_layer_fwd(src, input_x, params, 0, T, "neighbors", drop, "bf16")
+        assert (saved.layers[0].x_idx is not None) == fused
+        dsrc = E.u2gnn_layer_bwd(dout.clone(), saved, input_x, params, grads, 0, T, "neighbors", drop, need_dsrc=True,
+                                 transpose=E.IndexTranspose(input_x, nodes))
+        torch.cuda.synchronize()
+        res[fused] = (out, dsrc, grads)
+    assert torch.equal(res[True][0], res[False][0])
+    assert torch.equal(res[True][1], res[False][1])
+    for ga, gb in zip(res[True][2], res[False][2]):
+        for n in ga:
+            assert float((ga[n] - gb[n]).abs().max()) <= 1e-5 * max(float(gb[n].abs().max()), 1e-30), n
+
+
+def test_fused_gather_out_of_range_index_gives_zero_row_and_sets_the_error_word(U):
+    """An index outside the table - where F.embedding raises (pytorch_U2GNN_Sup.py:32) - is a zero input row and bit 1 of the
+    device error word, exactly as in u2gnn_gather_rows."""
+    from u2gnn_b200 import engine as E
+    B, S, d = 40, 17, 64
+    g = torch.Generator(device="cuda").manual_seed(4)
+    table = torch.randn(100, d, device="cuda", generator=g)
+    idx = torch.randint(0, 100, (B, S), device="cuda", generator=g)
+    idx[3, 5] = 100
+    idx[7, 0] = -1
+    W = torch.randn(3 * d, d, device="cuda", generator=g) / 8
+    b = torch.randn(3 * d, device="cuda", generator=g)
+    qkv = torch.empty((B * S, 3 * d), dtype=torch.bfloat16, device="cuda")
+    ctx = torch.empty((B * S, d), dtype=torch.bfloat16, device="cuda")
+    err = E.err_word(table.device)
+    err.zero_()
+    U.LIB.call("u2gnn_inproj_seqattn_tc_fwd", table.data_ptr(), idx.data_ptr(), 100, B, S, d, W.data_ptr(), b.data_ptr(), 1, 2, 0,
+               qkv.data_ptr(), ctx.data_ptr(), err.data_ptr(), E._stream())
+    torch.cuda.synchronize()
+    assert int(err.item()) & 2
+    err.zero_()
+    # a zero input row projects to the bias alone
+    for r in (3 * S + 5, 7 * S):
+        assert torch.equal(qkv[r], b.bfloat16())
+    xg = E.gather_rows(table, idx.clamp(0, 99))
+    ref = (xg.bfloat16().float() @ W.bfloat16().float().T + b)
+    ok = torch.ones(B * S, dtype=torch.bool, device="cuda")
+    ok[3 * S + 5] = False
+    ok[7 * S] = False
+    assert float((qkv.float()[ok] - ref[ok]).abs().max()) < 0.05
