@@ -108,20 +108,28 @@ __device__ __forceinline__ void stage_rows_bf16(uint8_t* tiles, const void* __re
 
 // fp32 rows idx[row0 + r] of a 64-column table -> one swizzled bf16 [128 x 64] tile (the gather of F.embedding fused into the GEMM
 // operand load); rows >= M and indices outside the table are zero
+// the 8 table rows thread `tid` of a 256-thread CTA reads for the tile at row0 (-1 past M): loaded one tile AHEAD of the rows
+// themselves so that the index -> row dependency is not a second exposed memory latency per tile
+// (32-bit: a 64-column fp32 table with 2^31 rows would be 550 GB; out-of-range indices become -1)
+__device__ __forceinline__ void gather_idx8(int (&rows)[8], const int64_t* __restrict__ idx, int64_t n_table, int64_t row0, int64_t M, int tid) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int64_t r = row0 + ((u * kThreads + tid) >> 4);
+        const int64_t v = (r < M) ? __ldg(idx + r) : -1;
+        rows[u] = (v >= 0 && v < n_table) ? (int)v : -1;
+    }
+}
 template <int NT>
-__device__ __forceinline__ void stage_rows_gather64(uint8_t* tile, const float* __restrict__ table, const int64_t* __restrict__ idx,
-                                                    int64_t n_table, int64_t row0, int64_t M, int64_t ld, int tid) {
+__device__ __forceinline__ void stage_rows_gather64(uint8_t* tile, const float* __restrict__ table, const int (&rows)[8], int64_t ld, int tid) {
+    static_assert(NT == kThreads, "one batch of 8 float4 per thread");
     for (int base = 0; base < TM * 16; base += NT * 8) {
         float4 v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int e = base + u * NT + tid;
-            const int r = e >> 4, c4 = e & 15;
+            const int c4 = e & 15;
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e < TM * 16 && row0 + r < M) {
-                const int64_t row = __ldg(idx + row0 + r);
-                if (row >= 0 && row < n_table) v[u] = __ldg(reinterpret_cast<const float4*>(table + row * ld) + c4);
-            }
+            if (rows[u] >= 0) v[u] = __ldg(reinterpret_cast<const float4*>(table + (int64_t)rows[u] * ld) + c4);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -248,6 +256,8 @@ __global__ void __launch_bounds__(kThreads, MINB) gemm_tc_rows_kernel(const Rows
     uint32_t phase = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row0 = tile * TM;
+        int rrows[8];                                           // fused gather of the residual: its table rows, requested before the operand tile
+        if (LN && p.res_idx) gather_idx8(rrows, p.res_idx, p.res_rows, row0, p.M, tid);
         if (p.KP == 64) stage_rows_bf16<kThreads, 64>(sA, p.A, p.a_bf16, row0, p.M, p.K, 64, p.lda, tid);
         else if (p.KP == 192) stage_rows_bf16<kThreads, 192>(sA, p.A, p.a_bf16, row0, p.M, p.K, 192, p.lda, tid);
         else stage_rows_bf16<kThreads>(sA, p.A, p.a_bf16, row0, p.M, p.K, p.KP, p.lda, tid);
@@ -281,8 +291,8 @@ __global__ void __launch_bounds__(kThreads, MINB) gemm_tc_rows_kernel(const Rows
                     if (row < p.M) {
                         int64_t rrow = row;
                         if (p.res_idx) {
-                            rrow = __ldg(p.res_idx + row);
-                            if (rrow < 0 || rrow >= p.res_rows) continue;     // (the forward kernel that gathered x has flagged it)
+                            rrow = rrows[u];
+                            if (rrow < 0) continue;                           // (the forward kernel that gathered x has flagged it)
                         }
                         pre[u] = __ldg(reinterpret_cast<const float4*>(p.res + rrow * p.ldres) + (e & 15));
                     }
@@ -520,13 +530,17 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc_wgrad_kernel(const WgradP
         if (a_async) stage_rows_async<kThreads>(st, p.A, tile * TM, p.M, p.N1, ga * 64, p.lda, tid);
         if (b_async) stage_rows_async<kThreads>(st + ga * 16384, p.B, tile * TM, p.M, p.N2, 64, p.ldb, tid);
     };
+    int grows[8];                                           // fused gather: table rows of the tile the next finish_sync stages
     auto finish_sync = [&](int64_t tile, uint8_t* st) {
         if (!a_async) stage_rows_bf16<kThreads>(st, p.A, p.a_bf16, tile * TM, p.M, p.N1, ga * 64, p.lda, tid);
-        if (p.b_idx) stage_rows_gather64<kThreads>(st + ga * 16384, static_cast<const float*>(p.B), p.b_idx, p.b_rows, tile * TM, p.M, p.ldb, tid);
-        else if (!b_async) stage_rows_bf16<kThreads>(st + ga * 16384, p.B, p.b_bf16, tile * TM, p.M, p.N2, 64, p.ldb, tid);
+        if (p.b_idx) {
+            stage_rows_gather64<kThreads>(st + ga * 16384, static_cast<const float*>(p.B), grows, p.ldb, tid);
+            gather_idx8(grows, p.b_idx, p.b_rows, (tile + gridDim.x) * TM, p.M, tid);       // for the tile after this one
+        } else if (!b_async) stage_rows_bf16<kThreads>(st + ga * 16384, p.B, p.b_bf16, tile * TM, p.M, p.N2, 64, p.ldb, tid);
     };
     int64_t it = 0;
     if ((int64_t)blockIdx.x < n_tiles) {
+        if (p.b_idx) gather_idx8(grows, p.b_idx, p.b_rows, (int64_t)blockIdx.x * TM, p.M, tid);
         issue_async(blockIdx.x, smem);
         cp_async_commit();
         finish_sync(blockIdx.x, smem);
@@ -669,8 +683,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_dgrad_wgrad_kernel(const 
         if (b_async) stage_rows_async<kThreads>(st + ga * 16384, p.B, tile * TM, p.M, 64, 64, p.ldb, tid);
     };
     auto finish_sync = [&](int64_t tile, uint8_t* st) {
-        if (p.b_idx) stage_rows_gather64<kThreads>(st + ga * 16384, static_cast<const float*>(p.B), p.b_idx, p.b_rows, tile * TM, p.M, p.ldb, tid);
-        else if (!b_async) stage_rows_bf16<kThreads, 64>(st + ga * 16384, p.B, p.b_bf16, tile * TM, p.M, 64, 64, p.ldb, tid);
+        if (p.b_idx) {
+            int grows[8];
+            gather_idx8(grows, p.b_idx, p.b_rows, tile * TM, p.M, tid);
+            stage_rows_gather64<kThreads>(st + ga * 16384, static_cast<const float*>(p.B), grows, p.ldb, tid);
+        } else if (!b_async) stage_rows_bf16<kThreads, 64>(st + ga * 16384, p.B, p.b_bf16, tile * TM, p.M, 64, 64, p.ldb, tid);
     };
     // prologue: tiles 0 .. NS-2 of this CTA
 #pragma unroll
