@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(256, 3) ln_bwd_vec_kernel(const float* __restr
 }
 
 bool vec_ok(int d, const void* a, const void* b, const void* c, const void* e, const void* f) {
-    if (d != 16 && d != 32 && d != 64 && d != 128) return false;
+    if (d != 4 && d != 8 && d != 16 && d != 32 && d != 64 && d != 128) return false;   // LPR = d / 4 lanes per row (d = 4: one lane per row, 32 rows per warp)
     const uintptr_t m = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
                         reinterpret_cast<uintptr_t>(e) | reinterpret_cast<uintptr_t>(f);
     return (m % 16) == 0;
@@ -328,7 +328,9 @@ extern "C" int u2gnn_add_dropout_ln_fwd(const float* res, const float* a, int64_
         const int rpb = 8 * (128 / d);                       // rows per 256-thread block
         const int grid = grid_for(M, rpb, 8);
         cudaStream_t st = as_stream(stream);
-        if (d == 16) ln_fwd_vec_kernel<4><<<grid, 256, 0, st>>>(res, a, M, rng, low, gamma, beta, z, y, stats);
+        if (d == 4) ln_fwd_vec_kernel<1><<<grid, 256, 0, st>>>(res, a, M, rng, low, gamma, beta, z, y, stats);
+        else if (d == 8) ln_fwd_vec_kernel<2><<<grid, 256, 0, st>>>(res, a, M, rng, low, gamma, beta, z, y, stats);
+        else if (d == 16) ln_fwd_vec_kernel<4><<<grid, 256, 0, st>>>(res, a, M, rng, low, gamma, beta, z, y, stats);
         else if (d == 32) ln_fwd_vec_kernel<8><<<grid, 256, 0, st>>>(res, a, M, rng, low, gamma, beta, z, y, stats);
         else if (d == 64) ln_fwd_vec_kernel<16><<<grid, 256, 0, st>>>(res, a, M, rng, low, gamma, beta, z, y, stats);
         else ln_fwd_vec_kernel<32><<<grid, 256, 0, st>>>(res, a, M, rng, low, gamma, beta, z, y, stats);
@@ -353,7 +355,9 @@ extern "C" int u2gnn_add_dropout_ln_bwd_ex(const float* dy, const float* z, cons
         const int low = rng_thr_low(thr);
         const int grid = grid_for(M, 64 * (128 / d), 3);
         cudaStream_t st = as_stream(stream);
-        if (d == 16) ln_bwd_vec_kernel<4><<<grid, 256, 0, st>>>(dy, z, stats, M, gamma, rng, low, dz, da, da_bf16, dgamma, dbeta, dasum);
+        if (d == 4) ln_bwd_vec_kernel<1><<<grid, 256, 0, st>>>(dy, z, stats, M, gamma, rng, low, dz, da, da_bf16, dgamma, dbeta, dasum);
+        else if (d == 8) ln_bwd_vec_kernel<2><<<grid, 256, 0, st>>>(dy, z, stats, M, gamma, rng, low, dz, da, da_bf16, dgamma, dbeta, dasum);
+        else if (d == 16) ln_bwd_vec_kernel<4><<<grid, 256, 0, st>>>(dy, z, stats, M, gamma, rng, low, dz, da, da_bf16, dgamma, dbeta, dasum);
         else if (d == 32) ln_bwd_vec_kernel<8><<<grid, 256, 0, st>>>(dy, z, stats, M, gamma, rng, low, dz, da, da_bf16, dgamma, dbeta, dasum);
         else if (d == 64) ln_bwd_vec_kernel<16><<<grid, 256, 0, st>>>(dy, z, stats, M, gamma, rng, low, dz, da, da_bf16, dgamma, dbeta, dasum);
         else ln_bwd_vec_kernel<32><<<grid, 256, 0, st>>>(dy, z, stats, M, gamma, rng, low, dz, da, da_bf16, dgamma, dbeta, dasum);

@@ -464,6 +464,10 @@ int seqattn_rows_try_fwd(const float* qkv, int64_t B, int S, int Sq, int d, uint
     }
     if (d == 64) return launch_fwd<64>(qkv, B, S, rng, ctx, st);
     if (d == 32) return launch_fwd<32>(qkv, B, S, rng, ctx, st);
+    // small feature sizes of the unsupervised configurations (configs[1] / configs[3]: d = 4): a row is one float4
+    if (d == 16) return launch_fwd<16>(qkv, B, S, rng, ctx, st);
+    if (d == 8) return launch_fwd<8>(qkv, B, S, rng, ctx, st);
+    if (d == 4) return launch_fwd<4>(qkv, B, S, rng, ctx, st);
     // padded feature sizes of engine.py's attention block for 64 < d <= 128 (configs[2], d = 65 -> 68): q | k | v blocks
     // zero-padded to a multiple of 4 floats so that every row is 16-byte aligned; the sqrt(1/d) scale is folded into W_q
     if (d == 68) return launch_fwd<68>(qkv, B, S, rng, ctx, st);
@@ -485,6 +489,9 @@ int seqattn_rows_try_bwd(const float* qkv, const float* dctx, int64_t B, int S, 
     }
     if (d == 64) return launch_bwd<64>(qkv, dctx, B, S, rng, dqkv, st);
     if (d == 32) return launch_bwd<32>(qkv, dctx, B, S, rng, dqkv, st);
+    if (d == 16) return launch_bwd<16>(qkv, dctx, B, S, rng, dqkv, st);
+    if (d == 8) return launch_bwd<8>(qkv, dctx, B, S, rng, dqkv, st);
+    if (d == 4) return launch_bwd<4>(qkv, dctx, B, S, rng, dqkv, st);
     if (d == 68) return launch_bwd<68>(qkv, dctx, B, S, rng, dqkv, st);
     if (d == 80) return launch_bwd<80>(qkv, dctx, B, S, rng, dqkv, st);
     if (d == 96) return launch_bwd<96>(qkv, dctx, B, S, rng, dqkv, st);

@@ -668,7 +668,7 @@ def encoder_layer_bwd(dy2, sv, p, g, d, ff, drop_ids, seed, thr, long_seq, need_
     f32 = dict(dtype=torch.float32, device=dev)
     drop_scale = 256.0 / (256.0 - thr) if thr else 1.0
     # LayerNorm2 + FFN
-    fold = sv.packed is not None and d in (16, 32, 64, 128) and FUSE_LN_BWD     # linear2 bias gradient inside the LayerNorm2 backward
+    fold = sv.packed is not None and d in (4, 8, 16, 32, 64, 128) and FUSE_LN_BWD     # linear2 bias gradient inside the LayerNorm2 backward
     df_img = None
     if fold and d == 64 and sv.y1_img is not None:
         # dF leaves the LayerNorm2 backward as bf16 tile images: the FFN backward bulk-copies them, the fp32 dF never exists

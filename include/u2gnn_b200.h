@@ -126,7 +126,7 @@ int u2gnn_add_dropout_ln_bwd(const float* dy, const float* z, const float* stats
                              float* dgamma, float* dbeta, u2gnn_stream_t stream);
 /* same, with da optionally stored as bf16 (da_bf16 = 1: its consumers are tensor-core kernels that round on load, so
  * rounding once here is bit-identical at half the bytes) and dasum[d] += colsum(dz * dropout mask) (fp32 values before
- * rounding; may be null; works without da) - the bias gradient of the linear layer that produced a.  Both options need d in {16, 32, 64, 128}.
+ * rounding; may be null; works without da) - the bias gradient of the linear layer that produced a.  Both options need d in {4, 8, 16, 32, 64, 128}.
  * da_bf16 = 2 (d = 64): da is written as bf16 swizzled [128 x 64] tile images (row r -> image r / 128, 128-byte rows, 16-byte chunk
  * index XOR (r & 7)), the operand format u2gnn_ffn_tc_bwd bulk-copies (df_img): the fp32 gradient never reaches HBM. */
 int u2gnn_add_dropout_ln_bwd_ex(const float* dy, const float* z, const float* stats, int64_t M, int d,
