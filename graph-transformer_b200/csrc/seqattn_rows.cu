@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(NT) seqattn_last_fwd_kernel(const void* __rest
 template <int D, int NT, bool BF>      // BF: qkv AND dqkv stored as bf16 (their other producers / consumers are tensor-core GEMMs)
 __global__ void __launch_bounds__(NT) seqattn_last_bwd_kernel(const void* __restrict__ qkv, const float* __restrict__ dctx,
                                                               int64_t B, int S, AttnRng rng, int low, void* __restrict__ dqkv) {
-    static_assert(D == 64 || D == 32, "lane = 4 feature columns");
+    static_assert(D == 64 || D == 32 || D == 16 || D == 8 || D == 4, "lane = 4 feature columns");
     constexpr int LPN = D / 4;                                        // lanes per node (16: half a warp, 8: a quarter)
     constexpr int NPW = 32 / LPN;                                     // nodes per warp
     const int hl = threadIdx.x % LPN;
@@ -460,6 +460,9 @@ int seqattn_rows_try_fwd(const float* qkv, int64_t B, int S, int Sq, int d, uint
     if (Sq == 1) {
         if (d == 64) return launch_last_fwd<64>(qkv, B, S, rng, ctx, st);
         if (d == 32) return launch_last_fwd<32>(qkv, B, S, rng, ctx, st);
+        if (d == 16) return launch_last_fwd<16>(qkv, B, S, rng, ctx, st);
+        if (d == 8) return launch_last_fwd<8>(qkv, B, S, rng, ctx, st);
+        if (d == 4) return launch_last_fwd<4>(qkv, B, S, rng, ctx, st);
         return 0;
     }
     if (d == 64) return launch_fwd<64>(qkv, B, S, rng, ctx, st);
@@ -485,6 +488,9 @@ int seqattn_rows_try_bwd(const float* qkv, const float* dctx, int64_t B, int S, 
     if (Sq == 1) {
         if (d == 64) return launch_last_bwd<64>(qkv, dctx, B, S, rng, dqkv, st);
         if (d == 32) return launch_last_bwd<32>(qkv, dctx, B, S, rng, dqkv, st);
+        if (d == 16) return launch_last_bwd<16>(qkv, dctx, B, S, rng, dqkv, st);
+        if (d == 8) return launch_last_bwd<8>(qkv, dctx, B, S, rng, dqkv, st);
+        if (d == 4) return launch_last_bwd<4>(qkv, dctx, B, S, rng, dqkv, st);
         return 0;
     }
     if (d == 64) return launch_bwd<64>(qkv, dctx, B, S, rng, dqkv, st);
