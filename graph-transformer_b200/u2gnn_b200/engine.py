@@ -255,6 +255,8 @@ def linear_fp32(A, M, K, W, w_kn, N, C, bias=None, relu=False, drop=None, aux=No
         epi |= 8
     if LIB.timed is not None:
         FLOPS["u2gnn_gemm_split_rows"] = FLOPS.get("u2gnn_gemm_split_rows", 0) + 2 * M * N * K
+        # the bytes the product must move once: A, the result (twice with beta), the aux mask, the weights
+        _acct_bytes("u2gnn_gemm_split_rows", 4 * (M * K + M * N * (1 + (1 if beta else 0) + (1 if aux is not None else 0)) + N * K))
     LIB.call("u2gnn_gemm_split_rows", _ptr(A), M, K, K, _ptr(W), int(w_kn), N if w_kn else K, N, _ptr(bias), epi, seed, stream, thr, 0,
              _ptr(aux), N if aux is not None else 0, aux_scale, beta, _ptr(C), N, _stream())
     return C
