@@ -95,10 +95,13 @@ __device__ __forceinline__ void blk_store(uint8_t* hi, uint8_t* lo, const float 
 // rows GEMM
 // ---------------------------------------------------------------------------------------------------------------
 struct RowsP {
-    const float* A;
+    const void* A;        // fp32 (split mode) or bf16 (plain mode) row-major
+    int a_bf16, c_bf16, aux_bf16;   // plain mode (split = 0): bf16 operands / results stored by tensor-core producers and consumers
+    int split;            // 1: three-product hi / lo split of fp32 operands; 0: one bf16 product per k-step
     int64_t M, lda;
     int K;
     const float* W;
+    const uint8_t* Wp;    // optional: the weights ALREADY as swizzled bf16 images (gemm_split_pack_kernel): a step's weights are one bulk copy
     int w_kn;
     int64_t ldw;
     int N;
@@ -108,32 +111,57 @@ struct RowsP {
     int thr, low;
     float drop_scale;
     int64_t rng_row0;
-    const float* aux;
+    const void* aux;
     int64_t ldaux;
     float aux_scale;
     float beta;
-    float* C;
+    void* C;
     int64_t ldc;
     int a_vec, w_vec, c_vec;
 };
+
+// bf16 rows -> one swizzled [128 x 64] tile: a plain copy of 16-byte chunks (4 per thread), zero past rv / cv (cv a multiple of 8).
+// The chunk bits travel in the first 16 words of the fp32 prefetch registers (one register file for both modes).
+__device__ __forceinline__ void tile_load_bf16(float (&v)[32], const __nv_bfloat16* __restrict__ src, int64_t ld, int rv, int cv, int tid) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int g = u * kThreads + tid;
+        const int r = g >> 3, c8 = g & 7;
+        uint4 x = make_uint4(0u, 0u, 0u, 0u);
+        if (r < rv && 8 * c8 < cv) x = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)r * ld) + c8);
+        v[4 * u] = __uint_as_float(x.x); v[4 * u + 1] = __uint_as_float(x.y); v[4 * u + 2] = __uint_as_float(x.z); v[4 * u + 3] = __uint_as_float(x.w);
+    }
+}
+__device__ __forceinline__ void tile_store_bf16(uint8_t* tile, const float (&v)[32], int tid) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int g = u * kThreads + tid;
+        *reinterpret_cast<uint4*>(tile + tc::sw128_chunk(g >> 3, g & 7)) =
+            make_uint4(__float_as_uint(v[4 * u]), __float_as_uint(v[4 * u + 1]), __float_as_uint(v[4 * u + 2]), __float_as_uint(v[4 * u + 3]));
+    }
+}
 
 // shared memory: A hi | A lo (16 KB each) | two weight buffers of W hi | W lo (16 KB each: <= 128 output columns x 64).  The
 // fp32 staging of the epilogue (32 KB) lies over the weight buffer the step's own MMAs have just finished with; the other
 // buffer already holds the next step's weights (staged while those MMAs ran).
 constexpr uint32_t kRowsSmem = 2 * 16384 + 2 * 32768;
 
-template <int EPI>        // 0: generic epilogue (runtime flags, any alignment); 1 / 2 / 3: vectorised specialisations (see the copy-out)
+template <int EPI, bool PLAIN>   // EPI 0: generic epilogue (runtime flags, any alignment); 1 / 2 / 3: vectorised specialisations (see the copy-out)
+                                 // PLAIN: bf16 A rows, one product per k-step, optional bf16 result / aux (compiled out of the fp32 split kernels)
 __global__ void __launch_bounds__(kThreads, 2) gemm_split_rows_kernel(const RowsP p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((tc::smem_u32(smem) & 1023u) != 0u) __trap();
     uint8_t* sAh = smem;
     uint8_t* sAl = smem + 16384;
     uint8_t* sW = smem + 32768;                              // buffer b: hi at sW + b * 32768, lo 16 KB behind it
+    __shared__ uint64_t wbar[2];                             // packed weights: bytes of buffer b have landed
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         tc::mbar_init(&bar, 1);
+        tc::mbar_init(&wbar[0], 1);
+        tc::mbar_init(&wbar[1], 1);
         tc::fence_barrier_init();
     }
     if (warp == 0) tc::tmem_alloc<NSMAX>(&tmem_slot);
@@ -149,7 +177,8 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_split_rows_kernel(const Rows
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
 
     // geometry of a step
-    auto a_src = [&](int64_t tile, int kb) { return p.A + tile * TM * p.lda + (int64_t)kb * KC; };
+    auto a_src = [&](int64_t tile, int kb) { return static_cast<const float*>(p.A) + tile * TM * p.lda + (int64_t)kb * KC; };
+    auto a_src16 = [&](int64_t tile, int kb) { return static_cast<const __nv_bfloat16*>(p.A) + tile * TM * p.lda + (int64_t)kb * KC; };
     auto a_rv = [&](int64_t tile) { const int64_t r = p.M - tile * TM; return (int)(r < TM ? r : TM); };
     auto k_cv = [&](int kb) { const int c = p.K - kb * KC; return c < KC ? c : KC; };
     auto n_w = [&](int ns) { const int c = p.N - ns * NSMAX; return c < NSMAX ? c : NSMAX; };
@@ -159,9 +188,24 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_split_rows_kernel(const Rows
         return p.w_kn ? 16 * ((nw + 63) / 64 * 64) : 16 * ((nw + 15) / 16 * 16);
     };
     float a[32];
-    auto load_a = [&](int64_t tile, int kb) { blk_load<8>(a, a_src(tile, kb), p.lda, a_rv(tile), k_cv(kb), 6, p.a_vec, 2048, tid); };
+    auto load_a = [&](int64_t tile, int kb) {
+        if constexpr (PLAIN) tile_load_bf16(a, a_src16(tile, kb), p.lda, a_rv(tile), k_cv(kb), tid);
+        else blk_load<8>(a, a_src(tile, kb), p.lda, a_rv(tile), k_cv(kb), 6, p.a_vec, 2048, tid);
+    };
+    auto store_a = [&]() {
+        if constexpr (PLAIN) tile_store_bf16(sAh, a, tid);
+        else blk_store<8>(sAh, sAl, a, 6, 0u, p.a_vec, 2048, tid);
+    };
     // weights of (ns, kb) -> buffer wb, through short-lived registers (an L2 read: the weights are a few hundred KB)
+    const uint32_t w_bytes = PLAIN ? 16384u : 32768u;        // packed image of one (slice, chunk): hi (+ lo)
     auto stage_w = [&](int ns, int kb, int wb) {
+        if (p.Wp) {                                          // one asynchronous bulk copy, no registers, no conversion
+            if (tid == 0) {
+                tc::mbar_arrive_expect_tx(&wbar[wb], w_bytes);
+                tc::bulk_g2s(sW + wb * 32768, p.Wp + ((size_t)ns * KB + kb) * 32768, w_bytes, &wbar[wb]);
+            }
+            return;
+        }
         float w[32];
         const int nw = n_w(ns);
         uint8_t* hi = sW + wb * 32768;
@@ -180,6 +224,8 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_split_rows_kernel(const Rows
     bool valid = tile < n_tiles, pending = false;
     uint32_t phase = 0;
     int wb = 0;                                              // weight buffer of the current step
+    uint32_t wphase[2] = {0u, 0u};
+    bool w_waited = false;
     if (valid) {
         load_a(tile, 0);
         stage_w(0, 0, 0);
@@ -192,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_split_rows_kernel(const Rows
             phase ^= 1;
             pending = false;
         }
-        if (a_new) blk_store<8>(sAh, sAl, a, 6, 0u, p.a_vec, 2048, tid);
+        if (a_new) store_a();
         // next step
         int64_t ntile = tile;
         int nns = ns, nkb = kb + 1;
@@ -212,6 +258,11 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_split_rows_kernel(const Rows
         tc::tc_fence_after();
         const int nw = n_w(ns);
         const int nps = (nw + 15) / 16 * 16;
+        if (p.Wp && (!w_resident || !w_waited)) {            // (uniform) the step's packed weights have landed
+            if (warp == 0) tc::mbar_wait(&wbar[wb], wphase[wb]);
+            wphase[wb] ^= 1;
+            w_waited = true;
+        }
         if (warp == 0) {
             if (tc::elect_one()) {
                 const uint32_t idesc = tc::make_idesc(TM, nps, 0, p.w_kn);
@@ -220,11 +271,16 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_split_rows_kernel(const Rows
                 const uint64_t wh = p.w_kn ? tc::make_desc_sw128(w0, 8192, 1024) : tc::make_desc_sw128(w0, 16, 1024);
                 const uint64_t wl = p.w_kn ? tc::make_desc_sw128(w0 + 16384, 8192, 1024) : tc::make_desc_sw128(w0 + 16384, 16, 1024);
                 const uint32_t wstep = p.w_kn ? 128u : 2u;   // 16 K rows of an MN-major image = 2 048 B; 16 K columns of a K-major one = 32 B
+                if constexpr (!PLAIN) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    tc::mma_ss(tmem, ah + 2 * ks, wh + wstep * ks, idesc, (kb > 0 || ks > 0));
-                    tc::mma_ss_acc(tmem, al + 2 * ks, wh + wstep * ks, idesc);
-                    tc::mma_ss_acc(tmem, ah + 2 * ks, wl + wstep * ks, idesc);
+                    for (int ks = 0; ks < 4; ++ks) {
+                        tc::mma_ss(tmem, ah + 2 * ks, wh + wstep * ks, idesc, (kb > 0 || ks > 0));
+                        tc::mma_ss_acc(tmem, al + 2 * ks, wh + wstep * ks, idesc);
+                        tc::mma_ss_acc(tmem, ah + 2 * ks, wl + wstep * ks, idesc);
+                    }
+                } else {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) tc::mma_ss(tmem, ah + 2 * ks, wh + wstep * ks, idesc, (kb > 0 || ks > 0));
                 }
                 tc::mma_commit(&bar);
             }
@@ -270,8 +326,22 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_split_rows_kernel(const Rows
                     if (EPI != 2 && (p.flags & 1) && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
                     const bool use_old = (EPI == 3) && (p.beta != 0.0f);
                     float4 pre[EPI == 1 ? 1 : 8];            // aux mask rows (EPI 2) or old C rows (EPI 3, beta)
-                    if (EPI == 2 || use_old) {
-                        const float* src = (EPI == 2) ? p.aux + (row0 + rr0) * p.ldaux + col : p.C + (row0 + rr0) * p.ldc + col;
+                    if (PLAIN && EPI == 2 && p.aux_bf16) {
+                        // plain mode: the saved hidden is bf16 (8 bytes per thread and row); only its sign / zero matters
+                        const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(p.aux) + (row0 + rr0) * p.ldaux + col;
+                        const int64_t step = 16 * p.ldaux;
+#pragma unroll
+                        for (int u = 0; u < (EPI == 1 ? 1 : 8); ++u) {
+                            pre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (col_ok && row0 + rr0 + 16 * u < p.M) {
+                                const uint2 w = *reinterpret_cast<const uint2*>(src + u * step);
+                                pre[u] = make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u), __uint_as_float(w.y << 16),
+                                                     __uint_as_float(w.y & 0xFFFF0000u));
+                            }
+                        }
+                    } else if (EPI == 2 || use_old) {
+                        const float* src = (EPI == 2) ? static_cast<const float*>(p.aux) + (row0 + rr0) * p.ldaux + col
+                                                      : static_cast<const float*>(p.C) + (row0 + rr0) * p.ldc + col;
                         const int64_t step = 16 * ((EPI == 2) ? p.ldaux : p.ldc);
 #pragma unroll
                         for (int u = 0; u < (EPI == 1 ? 1 : 8); ++u) {
@@ -289,7 +359,8 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_split_rows_kernel(const Rows
                                                    p.thr, p.low);
                     }
                     __syncthreads();
-                    float* out = p.C + (row0 + rr0) * p.ldc + col;
+                    float* out = static_cast<float*>(p.C) + (row0 + rr0) * p.ldc + col;
+                    __nv_bfloat16* out16 = static_cast<__nv_bfloat16*>(p.C) + (row0 + rr0) * p.ldc + col;
                     const int64_t ostep = 16 * p.ldc;
                     const int src_lane0 = 2 * (lane >> 4) + ((lane >> 3) & 1);
                     const float keep_scale = p.thr ? p.drop_scale : 1.0f;
@@ -316,7 +387,10 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_split_rows_kernel(const Rows
                             x.x = fmaf(p.beta, pre[EPI == 1 ? 0 : u].x, x.x); x.y = fmaf(p.beta, pre[EPI == 1 ? 0 : u].y, x.y);
                             x.z = fmaf(p.beta, pre[EPI == 1 ? 0 : u].z, x.z); x.w = fmaf(p.beta, pre[EPI == 1 ? 0 : u].w, x.w);
                         }
-                        if (live) *reinterpret_cast<float4*>(out + u * ostep) = x;
+                        if (live) {
+                            if (PLAIN && p.c_bf16) *reinterpret_cast<uint2*>(out16 + u * ostep) = make_uint2(epi::cvt2(x.x, x.y), epi::cvt2(x.z, x.w));
+                            else *reinterpret_cast<float4*>(out + u * ostep) = x;
+                        }
                     }
                 } else if (p.c_vec) {
                     const bool col_ok = col < p.N;           // N % 4 == 0: whole float4 pieces
@@ -325,7 +399,8 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_split_rows_kernel(const Rows
                     const bool use_aux = (p.flags & 8) != 0, use_old = (p.beta != 0.0f);
                     float4 pre[8];                           // aux mask rows, or the old C rows when there is no aux
                     if (use_aux || use_old) {
-                        const float* src = use_aux ? p.aux + (row0 + rr0) * p.ldaux + col : p.C + (row0 + rr0) * p.ldc + col;
+                        const float* src = use_aux ? static_cast<const float*>(p.aux) + (row0 + rr0) * p.ldaux + col
+                                                   : static_cast<const float*>(p.C) + (row0 + rr0) * p.ldc + col;
                         const int64_t step = 16 * (use_aux ? p.ldaux : p.ldc);
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
@@ -335,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_split_rows_kernel(const Rows
                     }
                     __syncthreads();
                     uint64_t el = (uint64_t)(p.rng_row0 + row0 + rr0) * (uint64_t)p.N + (uint64_t)col;
-                    float* out = p.C + (row0 + rr0) * p.ldc + col;
+                    float* out = static_cast<float*>(p.C) + (row0 + rr0) * p.ldc + col;
 #pragma unroll
                     for (int u = 0; u < 8; ++u, el += 16ull * (uint64_t)p.N, out += 16 * p.ldc) {
                         const int rr = rr0 + 16 * u;
@@ -377,12 +452,12 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_split_rows_kernel(const Rows
                         const float* sp = reinterpret_cast<const float*>(sOut + rr * 256 + ((c4 ^ (rr & 15)) << 4));
                         for (int j = 0; j < 4 && col + j < p.N; ++j) {
                             float y = sp[j];
-                            float* o = p.C + row * p.ldc + col + j;
+                            float* o = static_cast<float*>(p.C) + row * p.ldc + col + j;
                             if (p.flags & 1) y += p.bias[col + j];
                             if (p.flags & 2) y = fmaxf(y, 0.0f);
                             if (p.flags & 4)
                                 y *= rng_dropout_mult(p.keys, (uint64_t)(p.rng_row0 + row) * (uint64_t)p.N + (uint64_t)(col + j), p.thr, p.drop_scale);
-                            if (p.flags & 8) y = (p.aux[row * p.ldaux + col + j] > 0.0f) ? y * p.aux_scale : 0.0f;
+                            if (p.flags & 8) y = (static_cast<const float*>(p.aux)[row * p.ldaux + col + j] > 0.0f) ? y * p.aux_scale : 0.0f;
                             if (p.beta != 0.0f) y = fmaf(p.beta, *o, y);
                             *o = y;
                         }
@@ -522,44 +597,124 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_split_wgrad_kernel(const WgP
     if (warp == 0) tc::tmem_dealloc<128>(tmem);
 }
 
+// Weights -> the swizzled bf16 images the rows kernel multiplies: block (ns, kb) = 32 KB, hi image in the first 16 KB, lo image (split
+// mode) in the second, laid out exactly as the in-kernel staging writes them.  One CTA per block; a few microseconds per weight.
+__global__ void __launch_bounds__(kThreads) gemm_split_pack_kernel(const float* __restrict__ W, int w_kn, int64_t ldw, int N, int K, int w_vec,
+                                                                   uint8_t* __restrict__ out) {
+    const int KB = (K + KC - 1) / KC;
+    const int ns = blockIdx.x / KB, kb = blockIdx.x - ns * KB;
+    const int tid = threadIdx.x;
+    const int nw = (N - ns * NSMAX < NSMAX) ? N - ns * NSMAX : NSMAX;
+    const int cv = (K - kb * KC < KC) ? K - kb * KC : KC;
+    uint8_t* hi = out + (size_t)blockIdx.x * 32768;
+    float w[32];
+    // zero first: rows / columns the image does not cover must read as zero operands
+    for (int e = tid; e < 32768 / 16; e += kThreads) reinterpret_cast<uint4*>(hi)[e] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    if (!w_kn) {
+        const int groups = 16 * ((nw + 15) / 16 * 16);
+        blk_load<8>(w, W + (int64_t)ns * NSMAX * ldw + (int64_t)kb * KC, ldw, nw, cv, 6, w_vec, groups, tid);
+        blk_store<8>(hi, hi + 16384, w, 6, 0u, w_vec, groups, tid);
+    } else {
+        const int cl2 = (nw > 64) ? 7 : 6;
+        const int groups = 16 * ((nw + 63) / 64 * 64);
+        blk_load<8>(w, W + (int64_t)kb * KC * ldw + (int64_t)ns * NSMAX, ldw, cv, nw, cl2, w_vec, groups, tid);
+        blk_store<8>(hi, hi + 16384, w, cl2, 8192u, w_vec, groups, tid);
+    }
+}
+
 bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
 
 }  // namespace
 
-extern "C" int u2gnn_gemm_split_rows(const float* A, int64_t M, int K, int64_t lda, const float* W, int w_kn, int64_t ldw, int N,
-                                     const float* bias, int epi, uint64_t seed, uint32_t rng_stream, int thr, int64_t rng_row0,
-                                     const float* aux, int64_t ldaux, float aux_scale, float beta, float* C, int64_t ldc,
-                                     u2gnn_stream_t stream) {
+namespace {
+// shared launcher of the split (fp32 operands, three products) and plain (bf16 operands, one product) rows GEMM
+int launch_rows(const void* A, int a_bf16, int64_t M, int K, int64_t lda, const float* W, int w_kn, int64_t ldw, int N, const float* bias,
+                int epi, uint64_t seed, uint32_t rng_stream, int thr, int64_t rng_row0, const void* aux, int aux_bf16, int64_t ldaux,
+                float aux_scale, float beta, void* C, int c_bf16, int64_t ldc, int split, const void* packed_w, cudaStream_t stream) {
     if (!A || !W || !C || M < 0 || K < 1 || N < 1 || lda < K || ldc < N || ldw < (w_kn ? N : K)) return U2GNN_EINVAL;
     if ((epi & 1) && !bias) return U2GNN_EINVAL;
     if ((epi & 8) && (!aux || ldaux < N)) return U2GNN_EINVAL;
     if (epi & ~15) return U2GNN_EINVAL;
     if (thr < 0 || thr > 255) return U2GNN_EINVAL;
+    if (split && (a_bf16 || c_bf16 || aux_bf16)) return U2GNN_EINVAL;      // the split exists to keep fp32 operands exact
+    if (!split && !a_bf16) return U2GNN_EUNSUPPORTED;                       // plain mode streams bf16 rows (fp32 rows: u2gnn_gemm_tc_rows_ex)
+    if (c_bf16 && beta != 0.0f) return U2GNN_EINVAL;
     if (M == 0) return U2GNN_OK;
     if ((epi & 4) && thr == 0) epi &= ~4;
     RowsP p;
-    p.A = A; p.M = M; p.lda = lda; p.K = K; p.W = W; p.w_kn = w_kn; p.ldw = ldw; p.N = N;
+    p.A = A; p.a_bf16 = a_bf16; p.c_bf16 = c_bf16; p.aux_bf16 = aux_bf16; p.split = split;
+    p.M = M; p.lda = lda; p.K = K; p.W = W; p.w_kn = w_kn; p.ldw = ldw; p.N = N;
+    p.Wp = static_cast<const uint8_t*>(packed_w);
+    if (p.Wp && !aligned16(p.Wp)) return U2GNN_EALIGN;
     p.bias = bias; p.flags = epi; p.keys = rng_keys(seed, rng_stream); p.thr = thr; p.low = rng_thr_low(thr);
     p.drop_scale = thr ? rng_keep_scale(thr) : 1.0f; p.rng_row0 = rng_row0;
     p.aux = aux; p.ldaux = ldaux; p.aux_scale = aux_scale; p.beta = beta; p.C = C; p.ldc = ldc;
-    p.a_vec = aligned16(A) && (lda & 3) == 0 && (K & 3) == 0;
+    p.a_vec = aligned16(A) && (lda & (a_bf16 ? 7 : 3)) == 0 && (K & (a_bf16 ? 7 : 3)) == 0;
     p.w_vec = aligned16(W) && (ldw & 3) == 0 && ((w_kn ? N : K) & 3) == 0;
-    p.c_vec = aligned16(C) && (ldc & 3) == 0 && (N & 3) == 0 && (!(epi & 1) || aligned16(bias)) &&
-              (!(epi & 8) || (aligned16(aux) && (ldaux & 3) == 0));
+    p.c_vec = (reinterpret_cast<uintptr_t>(C) % (c_bf16 ? 8 : 16)) == 0 && (ldc & 3) == 0 && (N & 3) == 0 && (!(epi & 1) || aligned16(bias)) &&
+              (!(epi & 8) || ((reinterpret_cast<uintptr_t>(aux) % (aux_bf16 ? 8 : 16)) == 0 && (ldaux & 3) == 0));
+    if (a_bf16 && !p.a_vec) return U2GNN_EALIGN;
     const int64_t n_tiles = (M + TM - 1) / TM;
     const int64_t cap = (int64_t)U2GNN_NUM_SMS * 2;
     const int grid = (int)(n_tiles < cap ? n_tiles : cap);
     auto launch = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmem);
-        kern<<<grid, kThreads, kRowsSmem, as_stream(stream)>>>(p);
+        kern<<<grid, kThreads, kRowsSmem, stream>>>(p);
     };
     // epilogue specialisations for the aligned shapes of the throughput configurations; everything else is generic
     const int e = p.flags;
-    if (p.c_vec && ((e & ~1) == (2 | 4) || (e & ~1) == 2) && beta == 0.0f && (N & 31) == 0) launch(gemm_split_rows_kernel<1>);
-    else if (p.c_vec && e == 8 && beta == 0.0f) launch(gemm_split_rows_kernel<2>);
-    else if (p.c_vec && (e & ~1) == 0) launch(gemm_split_rows_kernel<3>);
-    else launch(gemm_split_rows_kernel<0>);
+    const int kind = (p.c_vec && ((e & ~1) == (2 | 4) || (e & ~1) == 2) && beta == 0.0f && (N & 31) == 0) ? 1
+                     : (p.c_vec && e == 8 && beta == 0.0f) ? 2 : (p.c_vec && (e & ~1) == 0) ? 3 : 0;
+    if (kind == 0 && (c_bf16 || aux_bf16)) return U2GNN_EUNSUPPORTED;       // bf16 results / masks: the vectorised epilogues only
+    if (split) {
+        if (kind == 1) launch(gemm_split_rows_kernel<1, false>);
+        else if (kind == 2) launch(gemm_split_rows_kernel<2, false>);
+        else if (kind == 3) launch(gemm_split_rows_kernel<3, false>);
+        else launch(gemm_split_rows_kernel<0, false>);
+    } else {
+        if (kind == 1) launch(gemm_split_rows_kernel<1, true>);
+        else if (kind == 2) launch(gemm_split_rows_kernel<2, true>);
+        else if (kind == 3) launch(gemm_split_rows_kernel<3, true>);
+        else launch(gemm_split_rows_kernel<0, true>);
+    }
     U2GNN_CHECK_LAUNCH();
+}
+}  // namespace
+
+extern "C" int u2gnn_gemm_split_rows(const float* A, int64_t M, int K, int64_t lda, const float* W, int w_kn, int64_t ldw, int N,
+                                     const float* bias, int epi, uint64_t seed, uint32_t rng_stream, int thr, int64_t rng_row0,
+                                     const float* aux, int64_t ldaux, float aux_scale, float beta, float* C, int64_t ldc,
+                                     const void* packed_w, u2gnn_stream_t stream) {
+    return launch_rows(A, 0, M, K, lda, W, w_kn, ldw, N, bias, epi, seed, rng_stream, thr, rng_row0, aux, 0, ldaux, aux_scale, beta, C, 0, ldc, 1,
+                       packed_w, as_stream(stream));
+}
+
+extern "C" size_t u2gnn_gemm_split_packed_bytes(int N, int K) {
+    if (N < 1 || K < 1) return 0;
+    return (size_t)((N + NSMAX - 1) / NSMAX) * (size_t)((K + KC - 1) / KC) * 32768;
+}
+
+extern "C" int u2gnn_gemm_split_pack(const float* W, int w_kn, int64_t ldw, int N, int K, void* packed, size_t packed_size,
+                                     u2gnn_stream_t stream) {
+    if (!W || !packed || N < 1 || K < 1 || ldw < (w_kn ? N : K)) return U2GNN_EINVAL;
+    if (packed_size < u2gnn_gemm_split_packed_bytes(N, K)) return U2GNN_EWORKSPACE;
+    if (!aligned16(packed)) return U2GNN_EALIGN;
+    const int w_vec = aligned16(W) && (ldw & 3) == 0 && ((w_kn ? N : K) & 3) == 0;
+    const int blocks = ((N + NSMAX - 1) / NSMAX) * ((K + KC - 1) / KC);
+    gemm_split_pack_kernel<<<blocks, kThreads, 0, as_stream(stream)>>>(W, w_kn, ldw, N, K, w_vec, static_cast<uint8_t*>(packed));
+    U2GNN_CHECK_LAUNCH();
+}
+
+// The same K-looping kernel with ONE bf16 product per k-step: A bf16 rows (any K that is a multiple of 8, any N), result fp32 or bf16,
+// aux mask fp32 or bf16.  The FFN of 64 < d <= 128 (engine.ffn_wide_*) runs linear1 + ReLU + dropout, linear2, dH + mask and dy1 as one
+// launch each (u2gnn_gemm_tc_rows_ex holds all of K in shared memory: K, N <= 256 per launch, separate elementwise passes).
+extern "C" int u2gnn_gemm_tc_rows_kloop(const void* A, int64_t M, int K, int64_t lda, const float* W, int w_kn, int64_t ldw, int N,
+                                        const float* bias, int epi, uint64_t seed, uint32_t rng_stream, int thr, int64_t rng_row0,
+                                        const void* aux, int aux_bf16, int64_t ldaux, float aux_scale, float beta, void* C, int c_bf16,
+                                        int64_t ldc, const void* packed_w, u2gnn_stream_t stream) {
+    return launch_rows(A, 1, M, K, lda, W, w_kn, ldw, N, bias, epi, seed, rng_stream, thr, rng_row0, aux, aux_bf16, ldaux, aux_scale, beta, C,
+                       c_bf16, ldc, 0, packed_w, as_stream(stream));
 }
 
 extern "C" int u2gnn_gemm_split_wgrad(const float* A, int64_t M, int N1, int64_t lda, const float* B, int N2, int64_t ldb, float* dW,

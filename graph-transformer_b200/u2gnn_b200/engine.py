@@ -257,8 +257,9 @@ def linear_fp32(A, M, K, W, w_kn, N, C, bias=None, relu=False, drop=None, aux=No
         FLOPS["u2gnn_gemm_split_rows"] = FLOPS.get("u2gnn_gemm_split_rows", 0) + 2 * M * N * K
         # the bytes the product must move once: A, the result (twice with beta), the aux mask, the weights
         _acct_bytes("u2gnn_gemm_split_rows", 4 * (M * K + M * N * (1 + (1 if beta else 0) + (1 if aux is not None else 0)) + N * K))
+    pk = _pack_w(W, w_kn, N if w_kn else K, N, K, M)
     LIB.call("u2gnn_gemm_split_rows", _ptr(A), M, K, K, _ptr(W), int(w_kn), N if w_kn else K, N, _ptr(bias), epi, seed, stream, thr, 0,
-             _ptr(aux), N if aux is not None else 0, aux_scale, beta, _ptr(C), N, _stream())
+             _ptr(aux), N if aux is not None else 0, aux_scale, beta, _ptr(C), N, _ptr(pk), _stream())
     return C
 
 
@@ -552,6 +553,8 @@ def ffn_wide_supported(d, ff):
     return 64 < d <= 128 and ff % 64 == 0 and ff >= 64
 
 
+WIDE_NS = int(os.environ.get("U2GNN_WIDE_NS", "256"))     # output-column slice of linear1 / dH per launch of the rows kernel
+WIDE_KS = int(os.environ.get("U2GNN_WIDE_KS", "256"))     # K slice of linear2 / dy1 per launch
 WIDE_DP = 128      # padded feature size of the wide path's operand copies (two 64-column K atoms, 256-byte bf16 rows)
 
 
@@ -559,6 +562,43 @@ def _pad_bf16(x, M, d):
     out = torch.empty((M, WIDE_DP), dtype=torch.bfloat16, device=x.device)
     LIB.call("u2gnn_pad_rows_bf16", _ptr(x), M, d, _ptr(out), WIDE_DP, _stream())
     return out
+
+
+PACK_MIN_ROWS = int(os.environ.get("U2GNN_PACK_MIN_ROWS", "8192"))   # rows GEMMs of at least this many rows get their weights pre-packed (one extra tiny launch)
+
+
+def _pack_w(W, w_kn, ldw, N, K, M):
+    """Swizzled bf16 operand images of a weight for the K-looping rows GEMMs (u2gnn_gemm_split_pack), or None for small batches."""
+    if M < PACK_MIN_ROWS:
+        return None
+    nbytes = LIB.call("u2gnn_gemm_split_packed_bytes", N, K)
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=W.device)
+    LIB.call("u2gnn_gemm_split_pack", _ptr(W), int(w_kn), ldw, N, K, _ptr(buf), nbytes, _stream())
+    return buf
+
+
+WIDE_KLOOP = os.environ.get("U2GNN_WIDE_KLOOP", "1") != "0"   # wide bf16 FFN: K-looping rows GEMM with fused ReLU / dropout / mask epilogues (one launch per product)
+
+
+def _rows_kloop(A, M, K, lda, W, w_kn, N, C, ldc, bias=None, relu=False, drop=None, aux=None, aux_scale=1.0):
+    """C[M, N] = epi(A[M, K] op(W) + bias): A bf16 (lda), W fp32 with a WIDE_DP leading dimension, C / aux fp32 or bf16 by dtype."""
+    epi, seed, stream, thr = 0, 0, 0, 0
+    if bias is not None:
+        epi |= 1
+    if relu:
+        epi |= 2
+    if drop is not None and drop[2] > 0:
+        epi |= 4
+        seed, stream, thr = drop[0], drop[1], drop[2]
+    if aux is not None:
+        epi |= 8
+    if LIB.timed is not None:
+        FLOPS["u2gnn_gemm_tc_rows_kloop"] = FLOPS.get("u2gnn_gemm_tc_rows_kloop", 0) + 2 * M * N * K
+    pk = _pack_w(W, w_kn, WIDE_DP, N, K, M)
+    LIB.call("u2gnn_gemm_tc_rows_kloop", _ptr(A), M, K, lda, _ptr(W), int(w_kn), WIDE_DP, N, _ptr(bias), epi, seed, stream, thr, 0, _ptr(aux),
+             int(aux is not None and aux.dtype == torch.bfloat16), aux.shape[1] if aux is not None else 0, aux_scale, 0.0, _ptr(C),
+             int(C.dtype == torch.bfloat16), ldc, _ptr(pk), _stream())
+    return C
 
 
 def _pad_cols(W, d):
@@ -582,15 +622,25 @@ def ffn_wide_fwd(y1, Mq, d, ff, p, seed, stream_hidden, thr):
     b2p[:d].copy_(p["linear2.bias"])
     b1 = p["linear1.bias"]
     h = torch.empty((Mq, ff), dtype=torch.bfloat16, device=dev)
-    for j in range(0, ff, 256):                      # N slices of linear1 (the rows kernel holds N <= 256 accumulator columns)
-        n = min(256, ff - j)
+    if WIDE_KLOOP:
+        # one launch per product: linear1 + bias + ReLU + dropout -> h (bf16); linear2 over all of ff -> fp.  K of linear1 / N of
+        # linear2 = d rounded up to 8 columns of the 128-column padded operands (the zero padding beyond is never loaded / written)
+        d8 = (d + 7) // 8 * 8
+        _rows_kloop(y1p, Mq, d8, WIDE_DP, W1p, 0, ff, h, ff, bias=b1, relu=True, drop=(seed, stream_hidden, thr))
+        fp = torch.empty((Mq, WIDE_DP), dtype=torch.float32, device=dev)
+        _rows_kloop(h, Mq, ff, ff, W2Tp, 1, d8, fp, WIDE_DP, bias=b2p)
+        f = torch.empty((Mq, d), dtype=torch.float32, device=dev)
+        LIB.call("u2gnn_copy_rows", _ptr(fp), WIDE_DP, _ptr(f), d, Mq, d, 0, s)
+        return f, (h, y1p)
+    for j in range(0, ff, WIDE_NS):                  # N slices of linear1 (the rows kernel holds N <= 256 accumulator columns)
+        n = min(WIDE_NS, ff - j)
         LIB.call("u2gnn_gemm_tc_rows_ex", _ptr(y1p), 1, Mq, WIDE_DP, WIDE_DP, _ptr(W1p) + 4 * j * WIDE_DP, 0, n, _ptr(b1) + 4 * j, 0.0,
                  _ptr(h) + 2 * j, 1, ff, s)
     scale = 256.0 / (256.0 - thr) if thr else 1.0
     LIB.call("u2gnn_relu_dropout_bf16", _ptr(h), Mq, ff, seed, stream_hidden, thr, scale, s)
     fp = torch.empty((Mq, WIDE_DP), dtype=torch.float32, device=dev)
-    for j in range(0, ff, 256):                      # K slices of linear2, accumulated into fp
-        k = min(256, ff - j)
+    for j in range(0, ff, WIDE_KS):                  # K slices of linear2, accumulated into fp
+        k = min(WIDE_KS, ff - j)
         LIB.call("u2gnn_gemm_tc_rows_ex", _ptr(h) + 2 * j, 1, Mq, k, ff, _ptr(W2Tp) + 4 * j * WIDE_DP, 1, WIDE_DP, _ptr(b2p) if j == 0 else 0,
                  0.0 if j == 0 else 1.0, _ptr(fp), 0, WIDE_DP, s)
     f = torch.empty((Mq, d), dtype=torch.float32, device=dev)
@@ -611,9 +661,14 @@ def ffn_wide_bwd(df, dz, saved, Mq, d, ff, p, g, thr):
     W1p = _pad_cols(p["linear1.weight"], d)                       # [ff, 128]: rows j.. are a contiguous [K, N] block for dy1
     W2Tp = _pad_cols(p["linear2.weight"].t(), d)                  # [ff, 128] = [N, K] for dH = df W2
     dh = torch.empty((Mq, ff), dtype=torch.bfloat16, device=dev)
-    for j in range(0, ff, 256):
-        n = min(256, ff - j)
-        LIB.call("u2gnn_gemm_tc_rows_ex", _ptr(dfp), 1, Mq, WIDE_DP, WIDE_DP, _ptr(W2Tp) + 4 * j * WIDE_DP, 0, n, 0, 0.0, _ptr(dh) + 2 * j, 1, ff, s)
+    d8 = (d + 7) // 8 * 8
+    if WIDE_KLOOP:
+        # dPre = (df W2) masked by the saved hidden (ReLU live AND kept) and scaled, in the GEMM epilogue: one launch, no elementwise pass
+        _rows_kloop(dfp, Mq, d8, WIDE_DP, W2Tp, 0, ff, dh, ff, aux=h, aux_scale=scale)
+    else:
+        for j in range(0, ff, WIDE_NS):
+            n = min(WIDE_NS, ff - j)
+            LIB.call("u2gnn_gemm_tc_rows_ex", _ptr(dfp), 1, Mq, WIDE_DP, WIDE_DP, _ptr(W2Tp) + 4 * j * WIDE_DP, 0, n, 0, 0.0, _ptr(dh) + 2 * j, 1, ff, s)
     # dW2[d, ff] += df^T h: the weight-gradient kernel takes at most 64 columns of its second operand, so 64-wide slices of h;
     # each slice's [128, 64] result (rows >= d are the zero padding) is added into its columns of dW2
     n_sl = ff // 64
@@ -621,7 +676,8 @@ def ffn_wide_bwd(df, dz, saved, Mq, d, ff, p, g, thr):
     for i in range(n_sl):
         LIB.call("u2gnn_gemm_tc_wgrad_ex", _ptr(dfp), 1, Mq, WIDE_DP, WIDE_DP, _ptr(h) + 2 * 64 * i, 1, 64, ff, 0, 0, _ptr(tmp) + 4 * i * WIDE_DP * 64, 0, s)
         LIB.call("u2gnn_copy_rows", _ptr(tmp) + 4 * i * WIDE_DP * 64, 64, _ptr(g["linear2.weight"]) + 4 * 64 * i, ff, d, 64, 1, s)
-    LIB.call("u2gnn_relu_dropout_bwd_bf16", _ptr(dh), _ptr(h), Mq, ff, scale, s)            # dh is now dPre
+    if not WIDE_KLOOP:
+        LIB.call("u2gnn_relu_dropout_bwd_bf16", _ptr(dh), _ptr(h), Mq, ff, scale, s)        # dh is now dPre
     # dW1[ff, d] += dPre^T y1, db1 += colsum(dPre): 256-row slices of dW1 x two 64-column blocks of the padded y1
     blocks = [(0, 64), (64, d - 64)]
     n_a = (ff + 255) // 256
@@ -634,12 +690,15 @@ def ffn_wide_bwd(df, dz, saved, Mq, d, ff, p, g, thr):
                      (_ptr(g["linear1.bias"]) + 4 * 256 * i) if bi == 0 else 0, s)
             LIB.call("u2gnn_copy_rows", t, 64, _ptr(g["linear1.weight"]) + 4 * (256 * i * d + c0), d, n1, nc, 1, s)
     dyp = torch.empty((Mq, WIDE_DP), dtype=torch.float32, device=dev)
-    for j in range(0, ff, 256):                      # dPre W1 (K slices; W1p rows j.. are a contiguous [K, N] block)
-        k = min(256, ff - j)
-        LIB.call("u2gnn_gemm_tc_rows_ex", _ptr(dh) + 2 * j, 1, Mq, k, ff, _ptr(W1p) + 4 * j * WIDE_DP, 1, WIDE_DP, 0, 0.0 if j == 0 else 1.0,
-                 _ptr(dyp), 0, WIDE_DP, s)
+    if WIDE_KLOOP:
+        _rows_kloop(dh, Mq, ff, ff, W1p, 1, d8, dyp, WIDE_DP)                               # dPre W1 over all of ff in one launch
+    else:
+        for j in range(0, ff, WIDE_KS):              # dPre W1 (K slices; W1p rows j.. are a contiguous [K, N] block)
+            k = min(WIDE_KS, ff - j)
+            LIB.call("u2gnn_gemm_tc_rows_ex", _ptr(dh) + 2 * j, 1, Mq, k, ff, _ptr(W1p) + 4 * j * WIDE_DP, 1, WIDE_DP, 0, 0.0 if j == 0 else 1.0,
+                     _ptr(dyp), 0, WIDE_DP, s)
     LIB.call("u2gnn_copy_rows", _ptr(dyp), WIDE_DP, _ptr(dz), d, Mq, d, 1, s)               # dy1 = dz + dPre W1
-    if LIB.timed is not None:                        # dH and dy1 go through the rows entry point (the two weight gradients through wgrad_ex)
+    if LIB.timed is not None and not WIDE_KLOOP:                        # dH and dy1 go through the rows entry point (the two weight gradients through wgrad_ex)
         FLOPS["u2gnn_gemm_tc_rows_ex"] = FLOPS.get("u2gnn_gemm_tc_rows_ex", 0) + 4 * Mq * d * ff
     return dz
 

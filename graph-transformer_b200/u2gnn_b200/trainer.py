@@ -95,7 +95,9 @@ def dominant_kernel(precision, d=64):
     are then what is timed."""
     if precision == "fp32":
         return "u2gnn_gemm_split_rows" if E.FP32_TC else "u2gnn_sgemm"
-    return "u2gnn_gemm_tc_rows_ex" if d > 64 else "u2gnn_ffn_tc_bwd"
+    if d > 64:
+        return "u2gnn_gemm_tc_rows_kloop" if E.WIDE_KLOOP else "u2gnn_gemm_tc_rows_ex"
+    return "u2gnn_ffn_tc_bwd"
 
 
 def roofline(model, precision, name, kernel_ms, launches, peaks, flops, ncu_summary=None):
@@ -128,7 +130,7 @@ def roofline(model, precision, name, kernel_ms, launches, peaks, flops, ncu_summ
             "note": ("fp32 mode on the tensor cores: three-product bf16 split (hi/lo) tcgen05 GEMMs, hidden materialised in fp32; achieved counts the algorithmic 2MNK once (the kernel executes 3x that in bf16 MMAs)" if name == "u2gnn_gemm_split_rows"
                      else "fp32 CUDA-core parity path; the tcgen05 path is --precision bf16" if precision == "fp32"
                      else "bf16 FFN for 64 < d <= 128: four of its six GEMMs (linear1, linear2, dH, dy1) through the general tcgen05 rows kernel, hidden materialised in bf16"
-                     if name == "u2gnn_gemm_tc_rows_ex"
+                     if name in ("u2gnn_gemm_tc_rows_ex", "u2gnn_gemm_tc_rows_kloop")
                      else "fused bf16 tcgen05 FFN backward (weight-gradient kernel + input-gradient kernel)")}
 
 

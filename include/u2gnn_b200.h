@@ -93,9 +93,24 @@ int u2gnn_sgemm(int ta, int tb, int64_t M, int N, int64_t K, float alpha, const 
 int u2gnn_gemm_split_rows(const float* A, int64_t M, int K, int64_t lda, const float* W, int w_kn, int64_t ldw, int N,
                           const float* bias, int epi, uint64_t seed, uint32_t rng_stream, int thr, int64_t rng_row0,
                           const float* aux, int64_t ldaux, float aux_scale, float beta, float* C, int64_t ldc,
-                          u2gnn_stream_t stream);
+                          const void* packed_w, u2gnn_stream_t stream);
+/* packed_w (optional, both rows entry points): the weights already converted to the kernel's swizzled bf16 operand images by
+ * u2gnn_gemm_split_pack (u2gnn_gemm_split_packed_bytes(N, K) bytes, 16-byte aligned; the hi / lo images of the split mode serve the plain
+ * mode too).  A step's weights are then ONE asynchronous bulk copy instead of an L2 read + conversion by all 256 threads: worth one extra
+ * tiny launch per weight for batches of more than a few thousand rows.  W must still be passed (shapes, and when packed_w is NULL). */
+size_t u2gnn_gemm_split_packed_bytes(int N, int K);
+int u2gnn_gemm_split_pack(const float* W, int w_kn, int64_t ldw, int N, int K, void* packed, size_t packed_size, u2gnn_stream_t stream);
 int u2gnn_gemm_split_wgrad(const float* A, int64_t M, int N1, int64_t lda, const float* B, int N2, int64_t ldb, float* dW,
                            int64_t ldw_n1, int64_t ldw_n2, float* db, u2gnn_stream_t stream);
+/* The rows kernel above with ONE bf16 product per k-step (plain bf16 mode): A is bf16 row-major (lda, K multiples of 8, 16-byte aligned),
+ * W fp32 as above, the result fp32 (c_bf16 = 0) or bf16 (c_bf16 = 1: beta must be 0), the aux mask fp32 or bf16 (only its sign is
+ * used).  Loops over K inside the kernel (any K) and over 128-column slices of N, with the u2gnn_sgemm epilogue bits fused: the
+ * bf16 FFN of 64 < d <= 128 (csrc/ffn_wide.cu, BASELINE.json configs[2]) runs linear1 + ReLU + dropout, linear2, the hidden's gradient
+ * with its mask and dy1 as one launch each.  bf16 results / masks need 4-element aligned shapes (N, ldc, ldaux multiples of 4). */
+int u2gnn_gemm_tc_rows_kloop(const void* A, int64_t M, int K, int64_t lda, const float* W, int w_kn, int64_t ldw, int N,
+                             const float* bias, int epi, uint64_t seed, uint32_t rng_stream, int thr, int64_t rng_row0,
+                             const void* aux, int aux_bf16, int64_t ldaux, float aux_scale, float beta, void* C, int c_bf16,
+                             int64_t ldc, const void* packed_w, u2gnn_stream_t stream);
 /* out[n] (+)= sum_m A[m*lda+n] */
 int u2gnn_colsum(const float* A, int64_t M, int N, int64_t lda, float* out, int accumulate, u2gnn_stream_t stream);
 

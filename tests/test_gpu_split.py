@@ -29,14 +29,14 @@ def dev(a):
 
 
 def call_rows(U, A, W, w_kn, N, bias=None, epi=0, seed=0, stream=0, thr=0, aux=None, aux_scale=1.0, beta=0.0, C0=None, lda=None,
-              ldw=None, ldc=None):
+              ldw=None, ldc=None, packed=None):
     from u2gnn_b200 import engine as E
     M, K = A.shape
     lda = lda or A.stride(0)
     ldw = ldw or W.stride(0)
     C = torch.zeros((M, ldc or N), dtype=torch.float32, device="cuda") if C0 is None else C0
     U.LIB.call("u2gnn_gemm_split_rows", A.data_ptr(), M, K, lda, W.data_ptr(), w_kn, ldw, N, E._ptr(bias), epi, seed, stream, thr, 0,
-               E._ptr(aux), 0 if aux is None else aux.stride(0), aux_scale, beta, C.data_ptr(), C.stride(0), E._stream())
+               E._ptr(aux), 0 if aux is None else aux.stride(0), aux_scale, beta, C.data_ptr(), C.stride(0), E._ptr(packed), E._stream())
     torch.cuda.synchronize()
     return C
 
@@ -51,6 +51,14 @@ def test_split_rows_matches_fp64(U, M, K, N, w_kn):
     ref = A.astype(np.float64) @ (W.astype(np.float64) if w_kn else W.astype(np.float64).T) + b
     C = call_rows(U, dev(A), dev(W), w_kn, N, bias=dev(b), epi=1)
     assert rel_err(C.cpu().numpy(), ref) < TOL
+    # the same product with the weights pre-packed into the kernel's operand images (one bulk copy per step): bit-identical
+    from u2gnn_b200 import engine as E
+    Wd = dev(W)
+    nb = U.LIB.call("u2gnn_gemm_split_packed_bytes", N, K)
+    pk = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    U.LIB.call("u2gnn_gemm_split_pack", Wd.data_ptr(), w_kn, Wd.stride(0), N, K, pk.data_ptr(), nb, E._stream())
+    Cp = call_rows(U, dev(A), Wd, w_kn, N, bias=dev(b), epi=1, packed=pk)
+    assert torch.equal(Cp, C)
     # beta = 1 accumulates over the old C
     C0 = rng.standard_normal((M, N)).astype(np.float32)
     C2 = call_rows(U, dev(A), dev(W), w_kn, N, beta=1.0, C0=dev(C0))
@@ -78,14 +86,14 @@ def test_split_rows_strided_operands_and_unaligned_pointers(U):
     ref = Ab[:, :K].astype(np.float64) @ Wb[:, :K].astype(np.float64).T
     from u2gnn_b200 import engine as E
     U.LIB.call("u2gnn_gemm_split_rows", A.data_ptr(), M, K, K + 8, W.data_ptr(), 0, K + 4, N, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0.0,
-               Cb.data_ptr(), N + 12, E._stream())
+               Cb.data_ptr(), N + 12, 0, E._stream())
     assert rel_err(Cb[:, :N].cpu().numpy(), ref) < TOL
     assert float(Cb[:, N:].abs().max()) == 0.0                       # nothing written outside the N columns
     # odd element offsets: the scalar path
     A1 = dev(np.concatenate([[0.0], Ab[:, :K].reshape(-1)]).astype(np.float32))
     C1 = torch.zeros((M, N), device="cuda")
     U.LIB.call("u2gnn_gemm_split_rows", A1.data_ptr() + 4, M, K, K, W.data_ptr(), 0, K + 4, N, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0.0,
-               C1.data_ptr(), N, E._stream())
+               C1.data_ptr(), N, 0, E._stream())
     assert rel_err(C1.cpu().numpy(), ref) < TOL
 
 
