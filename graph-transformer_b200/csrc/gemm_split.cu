@@ -325,26 +325,22 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_split_rows_kernel(const Rows
                     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (EPI != 2 && (p.flags & 1) && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
                     const bool use_old = (EPI == 3) && (p.beta != 0.0f);
-                    float4 pre[EPI == 1 ? 1 : 8];            // aux mask rows (EPI 2) or old C rows (EPI 3, beta)
-                    if (PLAIN && EPI == 2 && p.aux_bf16) {
-                        // plain mode: the saved hidden is bf16 (8 bytes per thread and row); only its sign / zero matters
+                    float4 pre[(EPI == 1 || (PLAIN && EPI == 2)) ? 1 : 8];   // aux mask rows (EPI 2) or old C rows (EPI 3, beta)
+                    uint2 prew[(PLAIN && EPI == 2) ? 8 : 1];   // plain mode: the saved hidden is bf16 (8 bytes per thread and row), kept as raw bits
+                    if constexpr (PLAIN && EPI == 2) {
                         const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(p.aux) + (row0 + rr0) * p.ldaux + col;
                         const int64_t step = 16 * p.ldaux;
 #pragma unroll
-                        for (int u = 0; u < (EPI == 1 ? 1 : 8); ++u) {
-                            pre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (col_ok && row0 + rr0 + 16 * u < p.M) {
-                                const uint2 w = *reinterpret_cast<const uint2*>(src + u * step);
-                                pre[u] = make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u), __uint_as_float(w.y << 16),
-                                                     __uint_as_float(w.y & 0xFFFF0000u));
-                            }
+                        for (int u = 0; u < 8; ++u) {
+                            prew[u] = make_uint2(0u, 0u);
+                            if (col_ok && row0 + rr0 + 16 * u < p.M) prew[u] = *reinterpret_cast<const uint2*>(src + u * step);
                         }
                     } else if (EPI == 2 || use_old) {
                         const float* src = (EPI == 2) ? static_cast<const float*>(p.aux) + (row0 + rr0) * p.ldaux + col
                                                       : static_cast<const float*>(p.C) + (row0 + rr0) * p.ldc + col;
                         const int64_t step = 16 * ((EPI == 2) ? p.ldaux : p.ldc);
 #pragma unroll
-                        for (int u = 0; u < (EPI == 1 ? 1 : 8); ++u) {
+                        for (int u = 0; u < ((EPI == 1 || (PLAIN && EPI == 2)) ? 1 : 8); ++u) {
                             pre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (col_ok && row0 + rr0 + 16 * u < p.M) pre[u] = *reinterpret_cast<const float4*>(src + u * step);
                         }
@@ -377,15 +373,23 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_split_rows_kernel(const Rows
                             x.z = (kw & 4u) ? fmaxf(x.z, 0.0f) * keep_scale : 0.0f;
                             x.w = (kw & 8u) ? fmaxf(x.w, 0.0f) * keep_scale : 0.0f;
                         }
-                        if (EPI == 2) {
+                        if constexpr (PLAIN && EPI == 2) {
+                            // the hidden is >= 0 (after ReLU): live and kept <=> its bf16 bits are not (plus or minus) zero
+                            const uint2 m = prew[u];
+                            x.x = (m.x & 0x00007FFFu) ? x.x * p.aux_scale : 0.0f;
+                            x.y = (m.x & 0x7FFF0000u) ? x.y * p.aux_scale : 0.0f;
+                            x.z = (m.y & 0x00007FFFu) ? x.z * p.aux_scale : 0.0f;
+                            x.w = (m.y & 0x7FFF0000u) ? x.w * p.aux_scale : 0.0f;
+                        } else if (EPI == 2) {
                             x.x = pre[u].x > 0.0f ? x.x * p.aux_scale : 0.0f;
                             x.y = pre[u].y > 0.0f ? x.y * p.aux_scale : 0.0f;
                             x.z = pre[u].z > 0.0f ? x.z * p.aux_scale : 0.0f;
                             x.w = pre[u].w > 0.0f ? x.w * p.aux_scale : 0.0f;
                         }
                         if (use_old) {
-                            x.x = fmaf(p.beta, pre[EPI == 1 ? 0 : u].x, x.x); x.y = fmaf(p.beta, pre[EPI == 1 ? 0 : u].y, x.y);
-                            x.z = fmaf(p.beta, pre[EPI == 1 ? 0 : u].z, x.z); x.w = fmaf(p.beta, pre[EPI == 1 ? 0 : u].w, x.w);
+                            constexpr bool one = (EPI == 1 || (PLAIN && EPI == 2));
+                            x.x = fmaf(p.beta, pre[one ? 0 : u].x, x.x); x.y = fmaf(p.beta, pre[one ? 0 : u].y, x.y);
+                            x.z = fmaf(p.beta, pre[one ? 0 : u].z, x.z); x.w = fmaf(p.beta, pre[one ? 0 : u].w, x.w);
                         }
                         if (live) {
                             if (PLAIN && p.c_bf16) *reinterpret_cast<uint2*>(out16 + u * ostep) = make_uint2(epi::cvt2(x.x, x.y), epi::cvt2(x.z, x.w));
@@ -639,6 +643,7 @@ int launch_rows(const void* A, int a_bf16, int64_t M, int K, int64_t lda, const 
     if (thr < 0 || thr > 255) return U2GNN_EINVAL;
     if (split && (a_bf16 || c_bf16 || aux_bf16)) return U2GNN_EINVAL;      // the split exists to keep fp32 operands exact
     if (!split && !a_bf16) return U2GNN_EUNSUPPORTED;                       // plain mode streams bf16 rows (fp32 rows: u2gnn_gemm_tc_rows_ex)
+    if (!split && (epi & 8) && !aux_bf16) return U2GNN_EUNSUPPORTED;        // ... and masks with a bf16 hidden
     if (c_bf16 && beta != 0.0f) return U2GNN_EINVAL;
     if (M == 0) return U2GNN_OK;
     if ((epi & 4) && thr == 0) epi &= ~4;
