@@ -179,3 +179,68 @@ def test_fixtures_still_pass_on_the_cuda_core_sgemm(U, case, monkeypatch):
     with torch.no_grad():
         s = m(dev(c["input_x"]), gp, dev(c["X"]))
     assert rel_err(s.cpu().numpy(), c["eval_scores"]) < 1e-4
+
+
+# ------------------------------------------------------------------ plain bf16 mode of the K-looping rows kernel (wide bf16 FFN, configs[2])
+def call_kloop(U, A, W, w_kn, N, K=None, bias=None, epi=0, seed=0, stream=0, thr=0, aux=None, aux_scale=1.0, out_bf16=False, packed=None):
+    from u2gnn_b200 import engine as E
+    M = A.shape[0]
+    K = K or A.shape[1]
+    C = torch.zeros((M, N), dtype=torch.bfloat16 if out_bf16 else torch.float32, device="cuda")
+    U.LIB.call("u2gnn_gemm_tc_rows_kloop", A.data_ptr(), M, K, A.stride(0), W.data_ptr(), w_kn, W.stride(0), N, E._ptr(bias), epi, seed, stream,
+               thr, 0, E._ptr(aux), int(aux is not None), 0 if aux is None else aux.stride(0), aux_scale, 0.0, C.data_ptr(), int(out_bf16),
+               C.stride(0), E._ptr(packed), E._stream())
+    torch.cuda.synchronize()
+    return C
+
+
+@pytest.mark.parametrize("M,K,N,w_kn,packed", [(1000, 72, 1024, 0, True), (300, 1024, 72, 1, True), (129, 64, 320, 0, False), (4097, 1024, 128, 1, False),
+                                                (257, 104, 64, 0, True), (640, 2048, 80, 1, True)])
+def test_kloop_plain_bf16_rows_match_fp64_on_rounded_operands(U, M, K, N, w_kn, packed):
+    """u2gnn_gemm_tc_rows_kloop: A bf16 rows (a 128-column padded buffer, K = the columns actually used), one bf16 product per k-step,
+    fp32 accumulation: against fp64 arithmetic on the SAME bf16-rounded operands (the weights are rounded inside the kernel)."""
+    from u2gnn_b200 import engine as E
+    rng = np.random.default_rng(M + K + N)
+    lda = max(128, (K + 7) // 8 * 8)
+    Ab = torch.zeros((M, lda), dtype=torch.bfloat16, device="cuda")
+    Ab[:, :K] = dev(rng.standard_normal((M, K)).astype(np.float32)).bfloat16()
+    W = dev((rng.standard_normal((K, N) if w_kn else (N, K)) / np.sqrt(K)).astype(np.float32))
+    b = dev(rng.standard_normal(N).astype(np.float32))
+    A64 = Ab[:, :K].float().cpu().numpy().astype(np.float64)
+    W64 = W.bfloat16().float().cpu().numpy().astype(np.float64)
+    ref = A64 @ (W64 if w_kn else W64.T) + b.cpu().numpy()
+    pk = None
+    if packed:
+        nb = U.LIB.call("u2gnn_gemm_split_packed_bytes", N, K)
+        pk = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        U.LIB.call("u2gnn_gemm_split_pack", W.data_ptr(), w_kn, W.stride(0), N, K, pk.data_ptr(), nb, E._stream())
+    C = call_kloop(U, Ab, W, w_kn, N, K=K, bias=b, epi=1, packed=pk)
+    assert rel_err(C.cpu().numpy(), ref) < 1e-5                       # fp32 accumulation of exact bf16 products
+    Cb = call_kloop(U, Ab, W, w_kn, N, K=K, bias=b, epi=1, out_bf16=True, packed=pk)
+    assert torch.equal(Cb, C.bfloat16())                              # the bf16 result is the fp32 one rounded once
+
+
+def test_kloop_plain_relu_dropout_and_mask_epilogues(U):
+    """linear1 + ReLU + dropout -> bf16 hidden, then dH masked by that hidden (engine.ffn_wide_fwd / _bwd): keep bits from the oracle's
+    restatement of the dropout stream; the mask epilogue tests the bf16 hidden's bits (live and kept <=> non-zero)."""
+    rng = np.random.default_rng(21)
+    M, K, N = 700, 72, 1024
+    Ab = torch.zeros((M, 128), dtype=torch.bfloat16, device="cuda")
+    Ab[:, :K] = dev(rng.standard_normal((M, K)).astype(np.float32)).bfloat16()
+    W = dev((rng.standard_normal((N, K)) / 8).astype(np.float32))
+    b = dev(rng.standard_normal(N).astype(np.float32))
+    seed, stream, p = 0xABCDEF123, 9, 0.5
+    keep, scale = O.dropout_keep_mask(seed, stream, M * N, p)
+    pre = Ab[:, :K].float().cpu().numpy().astype(np.float64) @ W.bfloat16().float().cpu().numpy().astype(np.float64).T + b.cpu().numpy()
+    ref = np.maximum(pre, 0.0) * keep.reshape(M, N) * scale
+    h = call_kloop(U, Ab, W, 0, N, K=K, bias=b, epi=1 | 2 | 4, seed=seed, stream=stream, thr=128, out_bf16=True)
+    hf = h.float().cpu().numpy()
+    assert rel_err(hf, ref) < 5e-3                                    # one bf16 rounding of the result
+    assert np.mean((hf == 0.0) != (ref == 0.0)) < 1e-3
+    df = torch.zeros((M, 128), dtype=torch.bfloat16, device="cuda")
+    df[:, :K] = dev(rng.standard_normal((M, K)).astype(np.float32)).bfloat16()
+    W2 = dev((rng.standard_normal((N, 128)) / 8).astype(np.float32))           # [N = hidden][K = feature] with a 128-column stride
+    dh = call_kloop(U, df, W2, 0, N, K=K, epi=8, aux=h, aux_scale=2.0, out_bf16=True)
+    refd = (df[:, :K].float().cpu().numpy().astype(np.float64) @ W2[:, :K].bfloat16().float().cpu().numpy().astype(np.float64).T) * (hf > 0) * 2.0
+    assert rel_err(dh.float().cpu().numpy(), refd) < 5e-3
+    assert not np.any(dh.float().cpu().numpy()[hf == 0.0])             # dropped / dead hidden units carry no gradient
