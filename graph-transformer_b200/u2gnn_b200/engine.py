@@ -602,6 +602,7 @@ def _rows_kloop(A, M, K, lda, W, w_kn, N, C, ldc, bias=None, relu=False, drop=No
         epi |= 8
     if LIB.timed is not None:
         FLOPS["u2gnn_gemm_tc_rows_kloop"] = FLOPS.get("u2gnn_gemm_tc_rows_kloop", 0) + 2 * M * N * K
+        _acct_bytes("u2gnn_gemm_tc_rows_kloop", M * (2 * K + C.element_size() * N + (aux.element_size() * N if aux is not None else 0)) + 4 * N * K)
     pk = _pack_w(W, w_kn, WIDE_DP, N, K, M)
     LIB.call("u2gnn_gemm_tc_rows_kloop", _ptr(A), M, K, lda, _ptr(W), int(w_kn), WIDE_DP, N, _ptr(bias), epi, seed, stream, thr, 0, _ptr(aux),
              int(aux is not None and aux.dtype == torch.bfloat16), aux.shape[1] if aux is not None else 0, aux_scale, 0.0, _ptr(C),

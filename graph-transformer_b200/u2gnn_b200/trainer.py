@@ -106,6 +106,16 @@ def roofline(model, precision, name, kernel_ms, launches, peaks, flops, ncu_summ
     which = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
     if peak is None:
         peak, which = 1590.0, "fallback (B200_PROFILING.md)"
+    if name == "u2gnn_gemm_tc_rows_kloop":
+        # wide bf16 FFN (64 < d <= 128): its four row products stream the materialised bf16 hidden - HBM-bound like the fp32 mode's
+        hbm = peaks.get("hbm_gbs", 6550.0)
+        gbs = E.BYTES.get(name, 0) / max(kernel_ms, 1e-9) / 1e6
+        return {"bound": "hbm", "kernel": name, "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": None,
+                "launches_timed": launches, "avg_launch_ms": kernel_ms / max(launches, 1),
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)",
+                "tensor_tflops_algorithmic": flops.get(name, 0) / max(kernel_ms, 1e-9) / 1e9,
+                "note": "bf16 FFN for 64 < d <= 128 on the K-looping tcgen05 rows kernel (one launch per product, fused ReLU / dropout / mask "
+                        "epilogues, hidden materialised in bf16); achieved = the bytes every product must move once / CUDA-event time of its launches"}
     if name == "u2gnn_gemm_split_rows":
         # fp32 mode: the bf16-split GEMMs stream the materialised fp32 hidden - HBM is what bounds them
         hbm = peaks.get("hbm_gbs", 6550.0)

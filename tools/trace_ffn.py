@@ -25,12 +25,14 @@ def main():
     packed = torch.zeros(nb, dtype=torch.uint8, device="cuda")
     PROBE.call("u2gnn_ffn_tc_prepare", W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), d, ff, 2.0, packed.data_ptr(), nb, E._stream())
     z = torch.empty_like(y1); xn = torch.empty_like(y1); st = torch.empty(M, 2, device="cuda")
+    emit = int(sys.argv[2]) if len(sys.argv) > 2 else 1       # 1 = write the mask words as the product step does
+    mask = torch.empty(PROBE.call("u2gnn_ffn_tc_mask_bytes", M, ff), dtype=torch.uint8, device="cuda") if emit else None
     CAP = 1024
     SLOTS = 21
     tr = torch.zeros(SLOTS * CAP, dtype=torch.int32, device="cuda")
     def run():
         PROBE.call("u2gnn_ffn_tc_fwd", y1.data_ptr(), M, d, ff, packed.data_ptr(), 1, 2, 3, thr, gamma.data_ptr(), beta.data_ptr(),
-                   z.data_ptr(), st.data_ptr(), xn.data_ptr(), 0, E._stream())
+                   z.data_ptr(), st.data_ptr(), xn.data_ptr(), mask.data_ptr() if emit else 0, E._stream())
     run(); torch.cuda.synchronize()
     PROBE.call("u2gnn_ffn_tc_set_trace", tr.data_ptr())
     run(); torch.cuda.synchronize()
