@@ -63,6 +63,55 @@ __device__ __forceinline__ void split_masks16(uint32_t w, uint32_t (&m)[16]) {
         m[j] = prmt(sh[7 - (j & 7)], 0u, (hi << 12) | (hi << 8) | (lo << 4) | lo);
     }
 }
+// ---- forward-kernel variant (round 2, tools/probe_epi_ops.cu): F2FP, HSET2, LOP3 and PRMT all issue on the ALU pipe (2 cycles per
+// warp instruction per scheduler), HFMA2 / HMUL2 / IMAD on the FMA pipe.  The chunk epilogue of the forward kernel was ALU-pipe bound
+// (5 ALU + 1 FMA instruction per register pair), so dropout is applied as a MULTIPLICATION there: the keep bits of a pair are isolated
+// at bits 14 / 30 of a word - the bf16 pair (2.0 | 0.0, 2.0 | 0.0) - by one IMAD (FMA pipe) and one LOP3, and
+//     tn = c * -1 + (-b1),   g = tn * (2 keep) + 0,   h' = relu(g * -1 + 0) = 2 relu(c + b1) keep      (three HFMA2)
+// sign(g) is set exactly where the hidden value is live AND kept (t = +-0 gives g = +0), so the mask word is gathered from the sign
+// bytes of two g registers by one PRMT + one LOP3 per TWO pairs.  2 h is exact in bf16; the forward's W2c image carries the 0.5.
+__device__ __forceinline__ uint32_t fma2(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t fma_relu2(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// keep word (bit e = element e kept) -> 16 factor pairs (2.0 kept, 0.0 dropped: 0x4000 / 0x0000 per half).  Pair j needs bit 2j at
+// bit 14 and bit 2j + 1 at bit 30: x * (2^(14-2j) + 2^(29-2j)) puts them there, and the two shifted copies of x never overlap (no
+// carries) when x holds at most 14 low bits - hence the four pre-masked words.
+__device__ __forceinline__ void keep_factors16(uint32_t keep, uint32_t (&kp)[16]) {
+    const uint32_t hi16 = keep >> 16;
+    const uint32_t xa = keep & 0x3FFFu, xb = keep & 0xC000u, ya = hi16 & 0x3FFFu, yb = hi16 & 0xC000u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t cj = (1u << (14 - 2 * j)) + (1u << (29 - 2 * j));
+        kp[j] = ((j < 7 ? xa : xb) * cj) & 0x40004000u;
+        kp[8 + j] = ((j < 7 ? ya : yb) * cj) & 0x40004000u;
+    }
+}
+// "flag" word: the order in which the sign bytes of the g registers of pairs 2k, 2k + 1 land (prmt 0xFBD9: byte 0 = low half of
+// pair 2k, byte 1 = low half of pair 2k + 1, bytes 2 / 3 = their high halves; bit k of each byte).  Element e = 2 j + half of a
+// 32-element group sits at bit 16 half + 8 (j & 1) + (j >> 1): both halves of a pair are 16 bits apart, like a split-pair word.
+// This is the bit order of the mask words the FFN kernels exchange.
+__device__ __forceinline__ int flag_pos(int e) { return 16 * (e & 1) + 8 * ((e >> 1) & 1) + (e >> 2); }
+__device__ __forceinline__ int flag_elem(int b) { return (b >> 4) + 2 * ((b >> 3) & 1) + 4 * (b & 7); }
+__device__ __forceinline__ uint32_t flag_gather(uint32_t g_even, uint32_t g_odd) { return prmt(g_even, g_odd, 0xFBD9u); }
+// flag word -> 16 pair masks (0xFFFF per set element)
+__device__ __forceinline__ void flag_masks16(uint32_t w, uint32_t (&m)[16]) {
+    uint32_t sh[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) sh[s] = w << s;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const uint32_t lo = 8u | (uint32_t)(j & 1), hi = 8u | (uint32_t)(2 + (j & 1));
+        m[j] = prmt(sh[7 - (j >> 1)], 0u, (hi << 12) | (hi << 8) | (lo << 4) | lo);
+    }
+}
+
 // position of element e in a split-pair word, and its inverse
 __device__ __forceinline__ int split_pos(int e) { return (e & 1) * 16 + (e >> 1); }
 __device__ __forceinline__ int split_elem(int b) { return (b < 16) ? 2 * b : 2 * (b - 16) + 1; }

@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(256) ffn_pack_kernel(const float* __restrict__
         // W1c  : B of GEMM1  [N = hidden r][K = feature k]
         *reinterpret_cast<__nv_bfloat16*>(blk + 16384 + tc::sw128_offset(r, k)) = __float2bfloat16(w1);
         // W2c  : B of GEMM2  [N = feature k][K = hidden r]  (two K atoms of 64)
-        *reinterpret_cast<__nv_bfloat16*>(blk + (r >> 6) * 8192 + tc::sw128_offset(k, r & 63)) = __float2bfloat16(w2);
+        // (times 0.5, exact: the forward's chunk epilogue leaves 2 h in tensor memory - epi::keep_factors16)
+        *reinterpret_cast<__nv_bfloat16*>(blk + (r >> 6) * 8192 + tc::sw128_offset(k, r & 63)) = __float2bfloat16(0.5f * w2);
         // W2Tc : B of dH = dF W2c   [N = hidden r][K = feature k]
         *reinterpret_cast<__nv_bfloat16*>(blk + 32768 + tc::sw128_offset(r, k)) = __float2bfloat16(w2);
         // W1Tc : B of dy1 += dPre W1c  [N = feature k][K = hidden r]
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset on the shared-window address: keeps LDS / STS (a uintptr_t round trip makes every access generic)
     uint8_t* sW = smem;                                    // STAGES x 16 KB
     uint8_t* sX = sW + STAGES * STAGE_BYTES;               // [2 buffers][2 tiles][128 rows x 272 B] fp32 staging
-    uint32_t* sB1h = reinterpret_cast<uint32_t*>(sX + 4 * XS_TILE_BYTES);    // b1 as packed bf16 pairs (ff/2 words)
+    uint32_t* sB1h = reinterpret_cast<uint32_t*>(sX + 4 * XS_TILE_BYTES);    // -b1 as packed bf16 pairs (ff/2 words)
     float* sB2 = reinterpret_cast<float*>(sB1h + p.ff / 2);                  // 64 floats
     float* sG = sB2 + DP;                                  // gamma, beta (2 x 64)
     __shared__ FwdBars bars;
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams
     if (warp == kMmaWarp) tc::tmem_alloc<512>(&tmem_slot);
     {   // biases / LayerNorm affine into shared memory
         const float* b1g = packed_b1(p.packed, p.ff);
-        for (int e = threadIdx.x; e < p.ff / 2; e += kThreads) sB1h[e] = epi::cvt2(b1g[2 * e], b1g[2 * e + 1]);
+        for (int e = threadIdx.x; e < p.ff / 2; e += kThreads) sB1h[e] = epi::cvt2(-b1g[2 * e], -b1g[2 * e + 1]);     // NEGATED (chunk epilogue: tn = -(c + b1))
         for (int e = threadIdx.x; e < DP; e += kThreads) {
             sB2[e] = b1g[p.ff + e];
             sG[e] = (e < p.d) ? p.gamma[e] : 0.0f;
@@ -299,22 +300,24 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams
                     const uint32_t s_addr = s_addr0 + 128 * i;
                     uint32_t v[32];
                     tc::tmem_ld32(s_addr, v);
-                    // independent work under the load latency: the 16 pair masks of this step and its packed bias
-                    uint32_t km[16];
-                    if (thr) epi::keep_masks16(k0, km);
+                    // independent work under the load latency: the 16 keep-factor pairs of this step and its packed bias
+                    uint32_t kp[16];
+                    epi::keep_factors16(k0, kp);       // 2.0 kept / 0.0 dropped (no dropout: k0 = all ones)
                     uint32_t bw[16];
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4)
                         tc::lds128(b1_addr + (uint32_t)c * 256u + 16u * q4, bw[4 * q4], bw[4 * q4 + 1], bw[4 * q4 + 2], bw[4 * q4 + 3]);
                     tc::tmem_ld_wait();
                     stamp(ew + 1);
-                    uint32_t nz = 0;                   // "split-pair" mask word: bit j = hidden 2j of the group is live and kept, bit 16 + j = hidden 2j + 1
+                    uint32_t nz = 0;                   // flag word (epi::flag_pos): hidden e of the group is live and kept
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        uint32_t h2 = epi::relu_bias2(epi::cvt2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bw[j]);
-                        if (thr) h2 &= km[j];
-                        v[j] = h2;                                 // in place: entries 2j, 2j+1 are already consumed
-                        if (EMIT) nz |= epi::gt0_mask2(h2) & (0x00010001u << j);
+                    for (int j = 0; j < 16; j += 2) {
+                        // tn = -(bf16(S) + b1);  g = 2 tn keep (sign set <=> live and kept; +0 when dropped or t = 0);  h' = relu(-g) = 2 relu(t) keep
+                        const uint32_t g0 = epi::fma2(epi::fma2(epi::cvt2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), 0xBF80BF80u, bw[j]), kp[j], 0u);
+                        const uint32_t g1 = epi::fma2(epi::fma2(epi::cvt2(__uint_as_float(v[2 * j + 2]), __uint_as_float(v[2 * j + 3])), 0xBF80BF80u, bw[j + 1]), kp[j + 1], 0u);
+                        v[j] = epi::fma_relu2(g0, 0xBF80BF80u, 0u);          // in place: entries 2j .. 2j+3 are already consumed; W2c carries the 0.5
+                        v[j + 1] = epi::fma_relu2(g1, 0xBF80BF80u, 0u);
+                        if (EMIT) nz |= epi::flag_gather(g0, g1) & (0x01010101u << (j >> 1));
                     }
                     stamp(ew + 1);
                     tc::tmem_st16(s_addr, v);          // packed H over the first 16 of this thread's own 32 S columns

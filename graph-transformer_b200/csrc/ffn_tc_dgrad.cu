@@ -228,8 +228,8 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_dgrad_kernel(const Params 
                 uint32_t km[32];
                 {
                     uint32_t k0[16], k1[16];
-                    epi::split_masks16(mw[0], k0);
-                    epi::split_masks16(mw[TM], k1);
+                    epi::flag_masks16(mw[0], k0);
+                    epi::flag_masks16(mw[TM], k1);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) { km[j] = k0[j]; km[16 + j] = k1[j]; }
                 }

@@ -241,12 +241,12 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params 
                 uint32_t kw = 0xFFFFFFFFu;                  // bit r = this hidden unit is kept (FWD_MASK: kept AND live) in row row0 + r
                 if (FWD_MASK) {
                     // lane j holds the word of row row0 + j (loaded one tile AHEAD: a load issued here would expose its full
-                    // latency); after the transpose lane k holds the row bits of the hidden unit at split-pair position k, so
-                    // hidden unit `lane` fetches them from lane split_pos(lane)
+                    // latency); after the transpose lane k holds the row bits of the hidden unit at flag-word position k, so
+                    // hidden unit `lane` fetches them from lane flag_pos(lane)
                     const uint32_t w = mw_next;
                     if (n + 1 < my_tiles)
                         mw_next = __ldg(p.mask + (((size_t)(tile + n_slices) * NC + c) * 4 + wq) * TM + 32 * cg + lane);
-                    kw = __shfl_sync(0xffffffffu, transpose32(w, lane), epi::split_pos(lane));
+                    kw = __shfl_sync(0xffffffffu, transpose32(w, lane), epi::flag_pos(lane));
                 } else if (thr) {
                     kw = transpose32(rng_keep_word_lo(keys2, (uint64_t)(row0 + lane) * g_per_row + (uint64_t)(4 * c + wq), thr, low), lane);
                 }
@@ -274,9 +274,10 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params 
                 if (lane == 0) tc::mbar_arrive(&bars.a_done[i]);
                 nz_cur = FWD_MASK ? kw : nz;                // FWD_MASK: natural row order (bit r = row r); else split-pair over the rows
                 if (!FWD_MASK && p.mask) {
-                    // hidden units are moved to their split-pair lane first, so that after the transpose lane k holds the word of
-                    // row split_elem(k) with the hidden bits in split-pair order - the format the forward kernel writes
-                    const uint32_t w = transpose32(__shfl_sync(0xffffffffu, nz, epi::split_elem(lane)), lane);
+                    // hidden units are moved to their flag-word lane first, so that after the transpose lane k holds the word of
+                    // row split_elem(k) (nz is split-pair over the rows) with the hidden bits in flag-word order (epi::flag_pos) - the
+                    // format the forward kernel writes
+                    const uint32_t w = transpose32(__shfl_sync(0xffffffffu, nz, epi::flag_elem(lane)), lane);
                     p.mask[(((size_t)tile * NC + c) * 4 + wq) * TM + 32 * cg + epi::split_elem(lane)] = w;
                 }
                 stamp(warp - 3);
