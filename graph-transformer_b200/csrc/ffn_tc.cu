@@ -291,6 +291,9 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_fwd_kernel(const FwdParams
             for (int c = 0; c < NC; ++c, ++scount) {
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
+                    // (measured, tools/trace_ffn.py: evaluating the keep word one step AHEAD under the previous step's tensor-memory
+                    // load moves its ~25 instructions from here into the load phase and leaves the chunk-pair period where it was,
+                    // 3 197 vs 3 211 cycles - the sixteen warps are bound by instruction issue, not by this serial chain)
                     uint32_t k0 = 0xFFFFFFFFu;
                     if (thr) k0 = keep_word(pair, c, i);
                     stamp(ew + 1);
