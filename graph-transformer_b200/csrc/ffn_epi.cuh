@@ -83,7 +83,7 @@ __device__ __forceinline__ uint32_t fma_relu2(uint32_t a, uint32_t b, uint32_t c
 // keep word (bit e = element e kept) -> 16 factor pairs (2.0 kept, 0.0 dropped: 0x4000 / 0x0000 per half).  Pair j needs bit 2j at
 // bit 14 and bit 2j + 1 at bit 30: x * (2^(14-2j) + 2^(29-2j)) puts them there, and the two shifted copies of x never overlap (no
 // carries) when x holds at most 14 low bits - hence the four pre-masked words.
-__device__ __forceinline__ void keep_factors16(uint32_t keep, uint32_t (&kp)[16]) {
+__host__ __device__ __forceinline__ void keep_factors16(uint32_t keep, uint32_t (&kp)[16]) {
     const uint32_t hi16 = keep >> 16;
     const uint32_t xa = keep & 0x3FFFu, xb = keep & 0xC000u, ya = hi16 & 0x3FFFu, yb = hi16 & 0xC000u;
 #pragma unroll
@@ -97,8 +97,8 @@ __device__ __forceinline__ void keep_factors16(uint32_t keep, uint32_t (&kp)[16]
 // pair 2k, byte 1 = low half of pair 2k + 1, bytes 2 / 3 = their high halves; bit k of each byte).  Element e = 2 j + half of a
 // 32-element group sits at bit 16 half + 8 (j & 1) + (j >> 1): both halves of a pair are 16 bits apart, like a split-pair word.
 // This is the bit order of the mask words the FFN kernels exchange.
-__device__ __forceinline__ int flag_pos(int e) { return 16 * (e & 1) + 8 * ((e >> 1) & 1) + (e >> 2); }
-__device__ __forceinline__ int flag_elem(int b) { return (b >> 4) + 2 * ((b >> 3) & 1) + 4 * (b & 7); }
+__host__ __device__ __forceinline__ int flag_pos(int e) { return 16 * (e & 1) + 8 * ((e >> 1) & 1) + (e >> 2); }
+__host__ __device__ __forceinline__ int flag_elem(int b) { return (b >> 4) + 2 * ((b >> 3) & 1) + 4 * (b & 7); }
 __device__ __forceinline__ uint32_t flag_gather(uint32_t g_even, uint32_t g_odd) { return prmt(g_even, g_odd, 0xFBD9u); }
 // flag word -> 16 pair masks (0xFFFF per set element)
 __device__ __forceinline__ void flag_masks16(uint32_t w, uint32_t (&m)[16]) {

@@ -33,6 +33,11 @@ int u2gnn_red_probe(float* buf, int64_t n_tiles, int groups, int mode, u2gnn_str
 /* TMEM -> register bandwidth probe: out[0] = cycles, out[1] = bytes */
 int u2gnn_tmem_bw_probe(int warps, int iters, int batch, long long* out, u2gnn_stream_t stream);
 
+/* host evaluation of the bit arithmetic of the FFN chunk epilogue (csrc/ffn_epi.cuh; tests/test_cabi_host.py): kp16[j] = the bf16
+ * factor pair (0x4000 = 2.0 kept, 0 dropped, per half) of register pair j for a natural-order keep word (epi::keep_factors16);
+ * pos32[e] = epi::flag_pos(e), elem32[b] = epi::flag_elem(b): the bit order of the mask words the FFN kernels exchange. */
+int u2gnn_epi_bits_host(uint32_t keep, uint32_t* kp16, int* pos32, int* elem32);
+
 #ifdef __cplusplus
 }
 #endif

@@ -169,3 +169,28 @@ def test_tf_style_label_smoothing_is_the_reference_formula_with_rescaled_eps(U):
         assert effective_smoothing(eps, C, "reference") == eps
     with pytest.raises(ValueError):
         effective_smoothing(0.1, 2, "other")
+
+
+def test_ffn_epilogue_bit_arithmetic_on_the_host():
+    """csrc/ffn_epi.cuh, forward chunk epilogue: dropout is a bf16 multiplication there - the keep bits of register pair j (elements
+    2j, 2j + 1 of a 32-element group) must land at bits 14 / 30 of a word (the bf16 pair 2.0 | 0.0 per half) through ONE integer
+    multiplication of a pre-masked word and one AND, with no carry between the two shifted copies; and the mask words the three FFN
+    kernels exchange use the order in which the sign bytes of two g registers land (flag_pos / flag_elem are inverse permutations with
+    both halves of a pair 16 bits apart).  The same inline functions, compiled for the host in the probe library."""
+    from u2gnn_b200._lib import probe_lib
+    P = probe_lib()
+    kp = (ctypes.c_uint32 * 16)()
+    pos = (ctypes.c_int * 32)()
+    elem = (ctypes.c_int * 32)()
+    rng = np.random.RandomState(5)
+    words = [0, 0xFFFFFFFF, 0x55555555, 0xAAAAAAAA, 0x0000FFFF, 0xFFFF0000, 0x00008000, 0x00004000, 0x80000000, 0xC000C000, 0x3FFF3FFF]
+    words += [int(w) for w in rng.randint(0, 2 ** 32, size=2000, dtype=np.uint64)]
+    for w in words:
+        assert P.call("u2gnn_epi_bits_host", w, ctypes.addressof(kp), ctypes.addressof(pos), ctypes.addressof(elem)) == 0
+        for j in range(16):
+            want = (0x4000 if (w >> (2 * j)) & 1 else 0) | (0x40000000 if (w >> (2 * j + 1)) & 1 else 0)
+            assert kp[j] == want, (hex(w), j, hex(kp[j]), hex(want))
+    p, e = list(pos), list(elem)
+    assert sorted(p) == list(range(32)) and all(e[p[i]] == i for i in range(32))
+    for j in range(16):
+        assert p[2 * j + 1] == p[2 * j] + 16 and p[2 * j] == 8 * (j & 1) + (j >> 1)
