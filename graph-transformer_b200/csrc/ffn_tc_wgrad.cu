@@ -41,7 +41,7 @@ struct Params {
     float* db1;   // [ff]
     float* dW2;   // [d, ff]
     uint32_t* mask;    // [n_tiles][ff / 128][4][128] words: word (tile, chunk, q, row) holds the live-and-kept bits of hidden units
-                       // 128 chunk + 32 q + [0, 32) of that row in split-pair order (ffn_epi.cuh).  FWD_MASK: read; else written (may be null)
+                       // 128 chunk + 32 q + [0, 32) of that row in flag-word order (ffn_epi.cuh, epi::flag_pos).  FWD_MASK: read; else written (may be null)
     uint32_t* trace;   // debug clock stamps of CTA 0 (probe build only)
 };
 constexpr int TRACE_CAP = 1024;
@@ -385,6 +385,11 @@ int ffn_tc_wgrad_launch(const void* xb, const void* fb, int64_t M, int d, int ff
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int NC = ff / CH;
     const int64_t n_tiles = (M + TM - 1) / TM;
+    // 148 = 16 * 9 + 4: a whole number of slices per chunk leaves 4 SMs without a CTA.  Measured (round 2, tools/ab_lib.sh,
+    // profiles/r02_ab_wgrad_tail_ctas.txt): four extra CTAs that take the last 1/37 of the tiles for four chunks each (flush + weight
+    // reload between passes; per-CTA tile counts equal, results identical) make the kernel SLOWER - backward 8.37 -> 8.55-8.92 ms per
+    // 4.46 M rows, step 53.6 -> 54.0 ms at the same 1 845 MHz: the step runs at the board's power cap, where 2.7 % more busy SMs buy
+    // no throughput and the extra passes' fill / drain / flush are pure cost.  Not kept.
     int n_slices = U2GNN_NUM_SMS / NC;
     if (n_slices < 1) n_slices = 1;
     if (n_slices > n_tiles) n_slices = (int)n_tiles;
