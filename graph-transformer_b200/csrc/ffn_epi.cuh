@@ -51,8 +51,8 @@ __device__ __forceinline__ void keep_masks16(uint32_t keep, uint32_t (&m)[16]) {
 }
 
 // "split-pair" word (bit j = element 2j, bit 16 + j = element 2j + 1: what one LOP3 per register pair builds from the
-// set.gt masks of packed values) -> 16 pair masks (0xFFFF per set element).  The mask words the FFN kernels exchange use
-// this bit order over the 32 hidden units of a group.
+// set.gt masks of packed values) -> 16 pair masks (0xFFFF per set element).  The weight-gradient kernel keeps its own row bits in
+// this order when it evaluates the masks itself; the mask words the FFN kernels EXCHANGE use the flag-word order above.
 __device__ __forceinline__ void split_masks16(uint32_t w, uint32_t (&m)[16]) {
     uint32_t sh[8];
 #pragma unroll
