@@ -256,14 +256,18 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params 
                 tc::tc_fence_after();
                 uint32_t v[32];
                 tc::tmem_ld32(r_addr0 + 128 * i, v);
-                uint32_t km[16];
-                if (FWD_MASK || thr) epi::keep_masks16(kw, km);
+                // phase A sits on the kernel's critical chain (S(n+1) -> A -> W2 / D(n+1)) and was ALU-pipe bound (cvt, and, prmt
+                // per pair + the word transpose): the mask is applied as a bf16 MULTIPLICATION like in the forward kernel
+                // (epi::keep_factors16: one IMAD + one LOP3 per pair; tools/probe_epi_ops.cu) - H^T leaves as 2 h, exact, and the
+                // flush of dW2 carries the 0.5
+                uint32_t kp[16];
+                epi::keep_factors16(kw, kp);               // 2.0 kept (and live) / 0.0; no mask: kw = all ones
                 tc::tmem_ld_wait();
                 uint32_t nz = 0;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    uint32_t h2 = epi::relu_bias2(epi::cvt2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bb);
-                    if (FWD_MASK || thr) h2 &= km[j];
+                    const uint32_t t2 = epi::fma2(epi::cvt2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), 0x3F803F80u, bb);
+                    const uint32_t h2 = epi::fma_relu2(t2, kp[j], 0u);        // 2 relu(t) keep
                     v[j] = h2;
                     if (!FWD_MASK) nz |= epi::gt0_mask2(h2) & (0x00010001u << j);
                 }
@@ -334,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_tc_wgrad_kernel(const Params 
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (32 * half + j < p.d)
-                            atomicAdd(p.dW2 + (size_t)(32 * half + j) * p.ff + h, __uint_as_float(v[j]) * p.hidden_scale);
+                            atomicAdd(p.dW2 + (size_t)(32 * half + j) * p.ff + h, __uint_as_float(v[j]) * (0.5f * p.hidden_scale));   // H^T was 2 h
                 }
                 uint32_t b16[16];
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
